@@ -1,0 +1,190 @@
+/*
+ * neptune_oracle.h -- CPU ORACLE (test infrastructure, NOT the product).
+ *
+ * Plain-C restatement of the algorithm on NEPTUNE's per-agent replan hot path
+ * (SURVEY.md section 8a).  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this library.  The product
+ * (neptune_b200/) never links, imports or executes anything in oracle/.
+ *
+ * PARITY STATUS: "parity unpinned" against a recorded Gurobi/GLPK/CGAL run --
+ * the reference ships no golden vectors and none of Gurobi 9.1.2, GLPK 4.65,
+ * CGAL 4.14.2, Eigen3 or ROS exist in this image, so /root/reference cannot
+ * be compiled (oracle/_ref is therefore absent).  The oracle is
+ * pinned instead by (i) the one known answer in the tree
+ * (submodules/separator/src/test_separator.cpp:23-32 => Solved=1),
+ * (ii) HiGHS (scipy) as an independent LP/QP solver on every golden scene,
+ * (iii) analytic cases.  tests/test_oracle_*.py hold those checks.
+ *
+ * Every function cites the reference file:line it restates (paths relative
+ * to /root/reference).
+ */
+#ifndef NEPTUNE_ORACLE_H
+#define NEPTUNE_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORC_NPOL_MAX 8
+#define ORC_HMAX 64 /* max hull vertices the oracle handles per polygon */
+
+/* status path of PolySolverGurobi::optimize (solver_gurobi_poly.cpp:832-861) */
+#define ORC_STATUS_OK 0       /* first solve accepted */
+#define ORC_STATUS_FALLBACK 1 /* terminal v/a rows dropped, soft cost, re-solve accepted */
+#define ORC_STATUS_FAILED 2   /* both solves failed: pwp_out = pwp_init */
+
+typedef struct orc_params
+{
+  int num_pol;      /* par_.num_pol */
+  int num_agents;   /* N = pb.size() */
+  int num_static;   /* M */
+  int samples;      /* num_sample_per_interval */
+  double T_span;
+  double weight;    /* weight_term */
+  double lim_min[3], lim_max[3]; /* x,y,z box (setMaxValues) */
+  double v_max, a_max;
+  double drone_radius;
+  int ent_cap;      /* storage capacity of alphas lists (entries) */
+  int bp_max;       /* storage capacity of a bend-point list */
+  int ent_slots;    /* LP slots reserved per interval for entangle constraints */
+  int ipm_max_iter;
+  double ipm_tol;
+} orc_params;
+
+/* ---- constants: solver_gurobi_poly.cpp:25-134, mader_types.hpp:152-162 ---- */
+void orc_basis(double T, double Ainv[16], double V[9], double Ainv01[16]);
+
+/* ---- separator: separator_glpk.cpp:248-373 / :375-498 (canonical vertex) ---- */
+int orc_separate(const double* A, int nA, const double* B, int nB, double out[3]);
+/* generic LP feasibility of the same rows (phase-1 simplex); dim = 2 or 3 */
+int orc_lp_separable(const double* A, int nA, const double* B, int nB, int dim);
+
+/* ---- hulls / samples: neptune.cpp:224-452, :463-566; cgal_utils.cpp:157-174 ---- */
+int orc_convex_hull_2d(const double* pts, int n, double* out);
+void orc_hull_of_interval(const double* times, int nt, const double* cx, const double* cy, double t_start,
+                          double t_end, double T_span, const double delta[3], double* hull, int* hull_n,
+                          double* hull2, int* hull2_n, int idx[2]);
+void orc_sample_interval_points(const double* times, int nt, const double* cx, const double* cy,
+                                double t_start, double t_end, int num_pol, int S, double* out, int* idx_out);
+
+/* ---- GJK: gjk.cpp:76-148 ---- */
+int orc_gjk_collision(const double* v1, int n1, const double* v2, int n2);
+
+/* ---- entanglement chain: entangle_utils.cpp:1129-1722 ---- */
+typedef struct orc_ent
+{
+  int n_alpha, n_bend;
+  int* alpha;   /* [cap][2] */
+  double* beta; /* [cap]    */
+  int* bend;    /* [cap]    */
+  int* active;  /* [N+M]    */
+} orc_ent;
+
+typedef struct orc_ectx
+{
+  int N, M, self;      /* self = 0-based index of the planning agent */
+  int cap;             /* storage capacity of lists */
+  const double* pb;    /* [N][2] */
+  const double* strep; /* [M][2 cols][2] staticObsRep */
+  const int* bp_cnt;   /* [N] */
+  const double* bp_xy; /* [N][bp_max][2] */
+  int bp_max;
+} orc_ectx;
+
+int orc_hsig_agent(int* toadd, int nadd, const double pk[2], const double pk1[2], const double pik[2],
+                   const double pik1[2], const double pb_self[2], const double* bend, int nbend, int agent_id);
+int orc_hsig_static(int* toadd, int nadd, const double pk[2], const double pk1[2], const double* strep,
+                    int M, int N);
+int orc_add_alpha_beta(int* toadd, int nadd, orc_ent* es, const double pk[2], const orc_ectx* cx);
+void orc_update_bend_pts(orc_ent* es, const double pk1[2], const orc_ectx* cx);
+
+/* Neptune::PredictAlphasBetas neptune.cpp:976-1008 */
+int orc_predict(orc_ent* es, const orc_ectx* cx, const double* prev_pos /*[N+1][2]*/,
+                const double* prev_pos_agent /*[N][2]*/, const double cur[2],
+                const double* samp0 /*[N][2] first sample of each agent*/, const unsigned char* known);
+/* KinodynamicSearch::entangleCheckGivenPwp kinodynamic_search.cpp:897-985 */
+int orc_entangle_check_pwp(orc_ent* es, const orc_ectx* cx, int n, const double* cxy /*[2][n][4]*/,
+                           const double* samp /*[N][num_pol][S+1][2]*/, const unsigned char* known,
+                           int num_pol, int S, double T);
+/* per-interval chain of KinodynamicSearch::entanglesWithOtherAgents :707-895
+ * (tether-length test omitted); writes the state after every interval. */
+int orc_entangle_rollout(const orc_ent* es0, const orc_ectx* cx, int n, const double* cxy,
+                         const double* samp, const unsigned char* known, int num_pol, int S, double T,
+                         int* out_cnt /*[n+1][2]*/, int* out_alpha /*[n+1][cap][2]*/,
+                         double* out_beta, int* out_bend, int* out_active /*[n+1][N+M]*/);
+
+/* ---- back end: solver_gurobi_poly.cpp:187-936 ---- */
+typedef struct orc_replan_in
+{
+  int agent_id;                 /* 1-based */
+  int n;                        /* intervals of pwp_init */
+  const double* coeff_init;     /* [3][8][4] */
+  int n_hull_slots;             /* slots per interval for other agents' hulls */
+  const long long* hull_ptr;    /* [slots*8+1] vertex offsets, slot-major then interval */
+  const double* hull_xy;
+  const double* nih0;           /* [N][8][2] col(0) of hullsNoInflation_ (NaN = empty) */
+  const long long* st_ptr;      /* [M+1] */
+  const double* st_xy;
+  const int* esv_cnt;           /* [9][2] */
+  const int* esv_alpha;         /* [9][cap][2] */
+  const int* esv_active;        /* [9][N+M] */
+  const int* bp_cnt;            /* [N] */
+  const double* bp_xy;          /* [N][bp_max][2] */
+  const double* pb;             /* [N][2] */
+} orc_replan_in;
+
+typedef struct orc_replan_out
+{
+  double* coeff_out; /* [3][8][4] */
+  double* obj;       /* [1] */
+  int* status;       /* [1] */
+  int* iters;        /* [2] */
+  double* lines;     /* [8][LS][3]  LS = n_hull_slots + N + M + ent_slots */
+  unsigned char* line_ok; /* [8][LS] 0 = not attempted, 1 = solved, 2 = attempted, unsolved */
+} orc_replan_out;
+
+int orc_replan(const orc_params* par, const orc_replan_in* in, orc_replan_out* out);
+
+/* dense export of the full-space QP the reference hands to Gurobi (for HiGHS cross-checks).
+ * Returns number of inequality rows written; P is 12n x 12n, rows are dense 12n. */
+int orc_export_qp(const orc_params* par, const orc_replan_in* in, int fallback, const double* lines,
+                  const unsigned char* line_ok, int LS, double* P, double* q, double* c0, double* Aeq,
+                  double* beq, int* n_eq, double* G, double* h, int max_rows, int* has_qc);
+
+/* PolySolverGurobi::generatePwpOut :889-936 ; returns number of states written */
+int orc_generate_traj(const double* coeff /*[3][8][4]*/, int n, double T, double dc, double* states, int max_states);
+
+/* batch driver used as CPU baseline: arrays are the same SoA buffers the C-ABI takes. */
+typedef struct orc_batch
+{
+  int B;
+  const int* agent_id;        /* [B] */
+  const int* n_int;           /* [B] */
+  const double* coeff_init;   /* [B][3][8][4] */
+  int n_hull_slots;
+  const long long* hull_ptr;  /* [B*slots*8+1] */
+  const double* hull_xy;
+  const double* nih0;         /* [B][N][8][2] */
+  const long long* st_ptr;
+  const double* st_xy;
+  const int* esv_cnt;         /* [B][9][2] */
+  const int* esv_alpha;       /* [B][9][cap][2] */
+  const int* esv_active;      /* [B][9][N+M] */
+  int bp_shared;              /* 1: bp arrays are [N]..., 0: [B][N]... */
+  const int* bp_cnt;
+  const double* bp_xy;
+  const double* pb;
+  double* coeff_out;          /* [B][3][8][4] */
+  double* obj;                /* [B] */
+  int* status;                /* [B] */
+  int* iters;                 /* [B][2] */
+  double* lines;              /* [B][8][LS][3] or NULL */
+  unsigned char* line_ok;     /* [B][8][LS] or NULL */
+} orc_batch;
+
+int orc_replan_batch(const orc_params* par, const orc_batch* b, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
