@@ -1,0 +1,148 @@
+/*
+ * neptune_b200.h -- C-ABI of the B200-native NEPTUNE replan hot path (libneptune_b200.so).
+ *
+ * Drop-in boundary: these entry points are what a cgo/ctypes/C++ binding of
+ * the reference's back end would bind.  Plain pointers and sizes only; no torch, Eigen or CUDA types
+ * in the signatures (streams travel as void*).  All functions return 0 on success or a negative
+ * nb_error; nothing throws across the ABI.  Paths cited are relative to the reference tree.
+ *
+ * Batch convention: every call processes B independent replans ("one replan = one agent, one
+ * cycle").  The reference runs B = 1 per process (one PolySolverGurobi per agent,
+ * neptune/include/neptune.hpp:183); the C++ shim in neptune_b200/csrc/poly_solver_b200.hpp does the
+ * same through this ABI, the benchmark harness passes B = number of agents on the rank.
+ *
+ * Memory spaces: pointers inside nb_replan_args / nb_* batches are HOST pointers when
+ * `space == NB_HOST` (the library stages them through pinned memory and copies results back:
+ * the end-to-end path) or DEVICE pointers when `space == NB_DEVICE` (inputs resident in HBM).
+ */
+#ifndef NEPTUNE_B200_H
+#define NEPTUNE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_NPOL 8 /* storage stride for intervals (num_pol <= 8 in every shipped YAML) */
+
+typedef enum nb_error
+{
+  NB_OK = 0,
+  NB_ERR_CUDA = -1,       /* a CUDA call failed; nb_last_error() has the text */
+  NB_ERR_ARG = -2,        /* invalid argument */
+  NB_ERR_CAPACITY = -3,   /* a fixed-capacity list would overflow (ent_slots / ent_cap / bp_max) */
+  NB_ERR_NO_DEVICE = -4   /* no CUDA device: there is no CPU fallback */
+} nb_error;
+
+typedef enum nb_space { NB_HOST = 0, NB_DEVICE = 1 } nb_space;
+
+/* status of one replan == PolySolverGurobi::optimize status path (solver_gurobi_poly.cpp:832-861) */
+#define NB_STATUS_OK 0       /* first solve accepted */
+#define NB_STATUS_FALLBACK 1 /* terminal v/a rows dropped + soft cost, re-solve accepted (:838-847) */
+#define NB_STATUS_FAILED 2   /* both failed: pwp_out = pwp_init, optimize() == false (:856-859) */
+
+/*
+ * Replaces the constructor + one-time setters of PolySolverGurobi
+ * (solver_gurobi_poly.cpp:25-134 ctor; :140-175 setMaxValues; :177-185 setTetherLength/setMaxRuntime;
+ * call site neptune.cpp:102-107).
+ */
+typedef struct nb_params
+{
+  int32_t num_pol;      /* ctor num_pol (<= NB_NPOL) */
+  int32_t deg_pol;      /* ctor deg_pol; only 3 is supported, as in the reference */
+  int32_t num_agents;   /* pb.size() */
+  int32_t num_static;   /* setStaticObstVert: number of static obstacles */
+  int32_t samples;      /* num_sample_per_interval (entangle check) */
+  int32_t use_linear_constraints; /* ctor flag; only 1 (the shipped mode) is supported */
+  double T_span;        /* ctor T_span */
+  double weight;        /* ctor weight_term */
+  double lim_min[3];    /* setMaxValues x_min,y_min,z_min */
+  double lim_max[3];    /* setMaxValues x_max,y_max,z_max */
+  double v_max, a_max;  /* setMaxValues v_max, a_max (j_max is not a QP constraint) */
+  double drone_radius;  /* hull inflation (neptune.cpp:340) */
+  double tether_length; /* setTetherLength (stored; not a QP constraint in the reference either) */
+  int32_t ent_cap;      /* storage capacity of an alphas list */
+  int32_t bp_max;       /* storage capacity of a bend-point list (base included) */
+  int32_t ent_slots;    /* LP slots per interval reserved for non-entangling constraints */
+  int32_t ipm_max_iter; /* stands in for setMaxRuntime: iteration cap of the interior-point solve */
+  double ipm_tol;
+} nb_params;
+
+typedef struct nb_handle nb_handle;
+
+/* pb: [num_agents][2] base positions (ctor argument pb). device < 0 selects the current device. */
+int nb_create(const nb_params* par, const double* pb, int device, nb_handle** out);
+void nb_destroy(nb_handle* h);
+const char* nb_last_error(void);
+/* number of kernels this library has launched since nb_create (bench.py's gpu_launches) */
+long long nb_launch_count(const nb_handle* h);
+
+/*
+ * Replaces PolySolverGurobi::setStaticObstVert (solver_gurobi_poly.cpp:316-320; caller
+ * Neptune::setStaticObst neptune.cpp:639-664 passes the INFLATED hulls).  Host pointers.
+ * st_ptr: [M+1] vertex offsets, st_xy: [st_ptr[M]][2].  strep: [M][2][2] staticObsRep_ (col0,col1)
+ * used by the entanglement chain (Neptune::setStaticObstRep neptune.cpp:666-671), may be NULL if M==0.
+ */
+int nb_set_static(nb_handle* h, const int64_t* st_ptr, const double* st_xy, const double* strep);
+
+/*
+ * One batch of back-end replans.  Replaces, per agent, the per-replan call sequence
+ *   setInitTrajectory (:187-244) -> setHulls (:246-281) -> setHullsNoInflation (:283-288) ->
+ *   setEntStateVector (:307-314) -> optimize (:804-887)            [neptune.cpp:1514-1519]
+ * including every separator::Separator::solveModel call optimize() makes
+ * (separator_glpk.cpp:248-373 and :375-498; call sites solver_gurobi_poly.cpp:480, :543, :584, :751).
+ */
+typedef struct nb_replan_args
+{
+  int32_t B;
+  int32_t space;              /* nb_space of every pointer below */
+  const int32_t* agent_id;    /* [B] 1-based id (ctor argument id) */
+  const int32_t* n_int;       /* [B] intervals of pwp_init */
+  const double* coeff_init;   /* [B][3][8][4] pwp_init coeff_x/y/z, [a b c d], t in seconds */
+  int32_t n_hull_slots;       /* hull slots per agent; slot s, interval i -> polygon hull_ptr[(b*slots+s)*8+i] */
+  const int64_t* hull_ptr;    /* [B*slots*8+1] vertex offsets; empty polygon = slot unused */
+  const double* hull_xy;      /* [hull_ptr[last]][2] CCW convex polygons (setHulls) */
+  int64_t hull_nvert;         /* total vertices in hull_xy */
+  const double* nih0;         /* [B][N][8][2] col(0) of hullsNoInflation_[j][i]; NaN = unknown */
+  const int32_t* esv_cnt;     /* [B][9][2] (alphas.size(), bendPointsIdx.size()) of entStateVec[i] */
+  const int32_t* esv_alpha;   /* [B][9][ent_cap][2] */
+  const int32_t* esv_active;  /* [B][9][N+M] active_cases */
+  const int32_t* bp_cnt;      /* [N] bendPtsForAgents_[j].size() (shared by the batch) */
+  const double* bp_xy;        /* [N][bp_max][2] */
+  /* outputs */
+  double* coeff_out;          /* [B][3][8][4] pwp_out_ coefficients */
+  double* obj;                /* [B] objective_value */
+  int32_t* status;            /* [B] NB_STATUS_* */
+  int32_t* iters;             /* [B][2] interior-point iterations (direct, fallback) */
+  double* lines;              /* optional [B][8][LS][3] every separating line (n0,n1,d) by slot */
+  uint8_t* line_ok;           /* optional [B][8][LS]: 0 not attempted, 1 solved, 2 unsolved */
+} nb_replan_args;
+
+/* LS = n_hull_slots + num_agents + num_static + ent_slots: agents | bases | static | non-entangling */
+int nb_line_slots(const nb_handle* h, int n_hull_slots);
+
+/* stream: cudaStream_t as void* (NULL = default stream).  Synchronous w.r.t. the host for
+ * NB_HOST arguments; asynchronous on `stream` for NB_DEVICE arguments. */
+int nb_replan_batch(nb_handle* h, const nb_replan_args* args, void* stream);
+
+/*
+ * Replaces separator::Separator::solveModel, 2-D overloads (separator_glpk.cpp:248, :375, :500), L LPs
+ * at once.  Point set A of LP l is a_xy[a_ptr[l] .. a_ptr[l+1]) (for the 4-arg overload the caller
+ * appends pointsAPlus to pointsA), B likewise.  a_polygon != 0 promises every A is a convex polygon
+ * in cyclic order (what CGAL returns); 0 makes no assumption.  out_line: [L][3] (n0,n1,d),
+ * out_ok: [L] 1 = GLP_OPT/GLP_FEAS, 0 = infeasible.
+ */
+int nb_separate_batch(nb_handle* h, int32_t L, int32_t space, const int64_t* a_ptr, const double* a_xy,
+                      const int64_t* b_ptr, const double* b_xy, int32_t a_polygon, double* out_line,
+                      uint8_t* out_ok, void* stream);
+
+/* PolySolverGurobi::generatePwpOut sampling loop (:911-934): states [B][max_states][12]
+ * (pos, vel, accel, jerk), n_states[B]. */
+int nb_generate_traj_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
+                           double dc, int32_t max_states, double* states, int32_t* n_states, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEPTUNE_B200_H */

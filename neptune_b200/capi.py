@@ -1,0 +1,173 @@
+"""ctypes binding of the C-ABI in include/neptune_b200.h (libneptune_b200.so).
+
+This is the only compute path of the package.  There is no CPU fallback: if the shared library is
+missing, or no CUDA device is present, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .batch import NPOL, ReplanBatch, ReplanResult
+from .params import Params
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libneptune_b200.so")
+NB_HOST, NB_DEVICE = 0, 1
+_P = C.c_void_p
+
+
+class NbParams(C.Structure):
+    _fields_ = [("num_pol", C.c_int32), ("deg_pol", C.c_int32), ("num_agents", C.c_int32),
+                ("num_static", C.c_int32), ("samples", C.c_int32), ("use_linear_constraints", C.c_int32),
+                ("T_span", C.c_double), ("weight", C.c_double), ("lim_min", C.c_double * 3),
+                ("lim_max", C.c_double * 3), ("v_max", C.c_double), ("a_max", C.c_double),
+                ("drone_radius", C.c_double), ("tether_length", C.c_double), ("ent_cap", C.c_int32),
+                ("bp_max", C.c_int32), ("ent_slots", C.c_int32), ("ipm_max_iter", C.c_int32),
+                ("ipm_tol", C.c_double)]
+
+
+class NbReplanArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("space", C.c_int32), ("agent_id", _P), ("n_int", _P), ("coeff_init", _P),
+                ("n_hull_slots", C.c_int32), ("hull_ptr", _P), ("hull_xy", _P), ("hull_nvert", C.c_int64),
+                ("nih0", _P), ("esv_cnt", _P), ("esv_alpha", _P), ("esv_active", _P), ("bp_cnt", _P),
+                ("bp_xy", _P), ("coeff_out", _P), ("obj", _P), ("status", _P), ("iters", _P), ("lines", _P),
+                ("line_ok", _P)]
+
+
+def make_nb_params(par: Params) -> NbParams:
+    p = NbParams()
+    p.num_pol, p.deg_pol, p.num_agents, p.num_static = par.num_pol, par.deg_pol, par.num_of_agents, par.num_of_static_obst
+    p.samples, p.use_linear_constraints = par.num_sample_per_interval, int(par.use_linear_constraints)
+    p.T_span, p.weight = par.T_span, par.weight
+    p.lim_min[:] = [par.x_min, par.y_min, par.z_min]
+    p.lim_max[:] = [par.x_max, par.y_max, par.z_max]
+    p.v_max, p.a_max, p.drone_radius, p.tether_length = par.v_max, par.a_max, par.drone_radius, par.tetherLength
+    p.ent_cap, p.bp_max, p.ent_slots = par.ent_cap, par.bp_max, par.ent_slots
+    p.ipm_max_iter, p.ipm_tol = par.ipm_max_iter, par.ipm_tol
+    return p
+
+
+def _np(a):
+    return None if a is None else a.ctypes.data_as(_P)
+
+
+def host_args(batch: ReplanBatch, res: ReplanResult) -> NbReplanArgs:
+    """nb_replan_args over host (numpy) buffers."""
+    a = NbReplanArgs()
+    a.B, a.space = batch.B, NB_HOST
+    a.agent_id, a.n_int, a.coeff_init = _np(batch.agent_id), _np(batch.n_int), _np(batch.coeff_init)
+    a.n_hull_slots, a.hull_ptr, a.hull_xy = batch.n_hull_slots, _np(batch.hull_ptr), _np(batch.hull_xy)
+    a.hull_nvert = int(batch.hull_xy.shape[0])
+    a.nih0, a.esv_cnt, a.esv_alpha, a.esv_active = _np(batch.nih0), _np(batch.esv_cnt), _np(batch.esv_alpha), _np(batch.esv_active)
+    a.bp_cnt, a.bp_xy = _np(batch.bp_cnt), _np(batch.bp_xy)
+    a.coeff_out, a.obj, a.status, a.iters = _np(res.coeff_out), _np(res.obj), _np(res.status), _np(res.iters)
+    a.lines, a.line_ok = _np(res.lines), _np(res.line_ok)
+    return a
+
+
+_lib = None
+
+
+def lib():
+    """Load libneptune_b200.so; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). neptune_b200 has no CPU fallback.")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.nb_last_error.restype = C.c_char_p
+        _lib.nb_launch_count.restype = C.c_longlong
+        _lib.nb_launch_count.argtypes = [_P]
+        _lib.nb_create.argtypes = [C.POINTER(NbParams), _P, C.c_int, C.POINTER(_P)]
+        _lib.nb_destroy.argtypes = [_P]
+        _lib.nb_set_static.argtypes = [_P, _P, _P, _P]
+        _lib.nb_replan_batch.argtypes = [_P, C.POINTER(NbReplanArgs), _P]
+        _lib.nb_line_slots.argtypes = [_P, C.c_int]
+    return _lib
+
+
+class NbError(RuntimeError):
+    pass
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise NbError(f"{what} failed with nb_error {rc}: {lib().nb_last_error().decode()}")
+
+
+class Solver:
+    """Long-lived back-end object: the batched counterpart of one ``PolySolverGurobi`` per agent
+    (reference ``neptune/include/neptune.hpp:183``; constructed at ``neptune.cpp:102-107``)."""
+
+    def __init__(self, par: Params, device: int = -1):
+        self.par = par
+        self._h = _P()
+        nbp = make_nb_params(par)
+        pb = np.ascontiguousarray(par.pb, dtype=np.float64)
+        assert pb.shape == (par.num_of_agents, 2)
+        _check(lib().nb_create(C.byref(nbp), _np(pb), device, C.byref(self._h)), "nb_create")
+
+    def close(self) -> None:
+        if self._h:
+            lib().nb_destroy(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def launch_count(self) -> int:
+        return int(lib().nb_launch_count(self._h))
+
+    def set_static(self, st_ptr: np.ndarray, st_xy: np.ndarray, strep: np.ndarray | None = None) -> None:
+        """``setStaticObstVert`` (+ ``setStaticObstRep``) with the inflated static hulls."""
+        st_ptr = np.ascontiguousarray(st_ptr, np.int64)
+        st_xy = np.ascontiguousarray(st_xy, np.float64)
+        strep = None if strep is None or len(strep) == 0 else np.ascontiguousarray(strep, np.float64)
+        _check(lib().nb_set_static(self._h, _np(st_ptr), _np(st_xy), _np(strep)), "nb_set_static")
+
+    def replan(self, batch: ReplanBatch, with_lines: bool = True, stream=None) -> ReplanResult:
+        """setInitTrajectory .. optimize for every agent of the batch, host buffers in and out."""
+        res = ReplanResult.empty(batch, with_lines)
+        a = host_args(batch, res)
+        _check(lib().nb_replan_batch(self._h, C.byref(a), _P(stream or 0)), "nb_replan_batch")
+        return res
+
+    def replan_args(self, a: NbReplanArgs, stream=None) -> None:
+        """Raw call with caller-built arguments (device pointers for the HBM-resident path)."""
+        _check(lib().nb_replan_batch(self._h, C.byref(a), _P(stream or 0)), "nb_replan_batch")
+
+    def separate(self, a_ptr, a_xy, b_ptr, b_xy, a_polygon: bool):
+        """L separating-line LPs: ``separator::Separator::solveModel`` 2-D, batched."""
+        a_ptr, b_ptr = np.ascontiguousarray(a_ptr, np.int64), np.ascontiguousarray(b_ptr, np.int64)
+        a_xy, b_xy = np.ascontiguousarray(a_xy, np.float64), np.ascontiguousarray(b_xy, np.float64)
+        L = len(a_ptr) - 1
+        line, ok = np.zeros((L, 3)), np.zeros(L, np.uint8)
+        f = lib().nb_separate_batch
+        f.argtypes = [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, C.c_int32, _P, _P, _P]
+        _check(f(self._h, L, NB_HOST, _np(a_ptr), _np(a_xy), _np(b_ptr), _np(b_xy), int(a_polygon), _np(line), _np(ok),
+                 None), "nb_separate_batch")
+        return ok.astype(bool), line
+
+    def generate_traj(self, n_int, coeff, dc: float):
+        """``generatePwpOut`` sampling loop, batched -> (states [B][K][12], n_states [B])."""
+        n_int, coeff = np.ascontiguousarray(n_int, np.int32), np.ascontiguousarray(coeff, np.float64)
+        B = len(n_int)
+        mx = int(self.par.num_pol * self.par.T_span / dc) + 8
+        states, ns = np.zeros((B, mx, 12)), np.zeros(B, np.int32)
+        f = lib().nb_generate_traj_batch
+        f.argtypes = [_P, C.c_int32, C.c_int32, _P, _P, C.c_double, C.c_int32, _P, _P, _P]
+        _check(f(self._h, B, NB_HOST, _np(n_int), _np(coeff), dc, mx, _np(states), _np(ns), None),
+               "nb_generate_traj_batch")
+        return states, ns

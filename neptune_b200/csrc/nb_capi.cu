@@ -1,0 +1,484 @@
+// nb_capi.cu -- C-ABI (include/neptune_b200.h) and kernel launches of libneptune_b200.so.
+// sm_100a only; no CPU fallback: every entry point fails with NB_ERR_NO_DEVICE / NB_ERR_CUDA when no
+// B200-class device is usable.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/neptune_b200.h"
+#include "nb_common.cuh"
+#include "nb_lines.cuh"
+#include "nb_qp.cuh"
+#include "nb_sep.cuh"
+#include "nb_tables.h"
+
+static thread_local std::string g_err;
+extern "C" const char* nb_last_error(void) { return g_err.c_str(); }
+
+#define NB_CUDA(call)                                                                         \
+  do                                                                                          \
+  {                                                                                           \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+    {                                                                                         \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_);                             \
+      return NB_ERR_CUDA;                                                                     \
+    }                                                                                         \
+  } while (0)
+
+struct DevBuf
+{
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes)
+  {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    if (cudaMalloc(&p, want) != cudaSuccess) return -1;
+    cap = want;
+    return 0;
+  }
+  void release()
+  {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct nb_handle
+{
+  nb_params par;
+  NbConsts cs;
+  int device;
+  long long launches;
+  NbQpTable* d_tables;  // [2][NB_NPOL] : mode-major
+  double* d_pb;
+  int64_t* d_st_ptr;
+  double* d_st_xy;
+  double* d_strep;
+  int64_t st_nvert;
+  // staging of NB_HOST arguments
+  DevBuf in[16], out[8];
+  // scratch
+  DevBuf lines, line_ok, cl, lstart, rows, err;
+};
+
+// ------------------------------------------------------------------------------------------ kernels
+
+__global__ void __launch_bounds__(128) k_lines(NbConsts cs, NbLinesIn in, int LS, double* lines, uint8_t* ok, int* err)
+{
+  const int b = blockIdx.x / NB_NPOL, i = blockIdx.x % NB_NPOL;
+  nb_lines_task<128>(threadIdx.x, b, i, cs, in, lines + (size_t)blockIdx.x * LS * 3, ok + (size_t)blockIdx.x * LS, err);
+}
+
+struct NbQpArgs
+{
+  const int* n_int;
+  const double* coeff_init;
+  const double* lines;  // [B][8][LS][3]
+  const uint8_t* ok;    // [B][8][LS]
+  int LS;
+  double* cl;           // [B][8*LS][3]
+  int* lstart;          // [B][9]
+  double* rows;         // [B][4][RS]
+  int RS;
+  double* coeff_out;
+  double* obj;
+  int* status;
+  int* iters;
+};
+
+__global__ void __launch_bounds__(32) k_qp(NbConsts cs, const NbQpTable* tables, NbQpArgs a)
+{
+  __shared__ NbQpShared sh;
+  __shared__ double xout[96];
+  const int b = blockIdx.x;
+  Group<32> g(threadIdx.x);
+  const int n = a.n_int[b];
+  const double* ci = a.coeff_init + (size_t)b * 96;
+  double* cl = a.cl + (size_t)b * NB_NPOL * a.LS * 3;
+  int* lstart = a.lstart + (size_t)b * 9;
+  const int nl = nb_compact_lines<32>(g, n, a.LS, a.lines + (size_t)b * NB_NPOL * a.LS * 3,
+                                      a.ok + (size_t)b * NB_NPOL * a.LS, cl, lstart);
+  NbQpRows R;
+  double* rb = a.rows + (size_t)b * 4 * a.RS;
+  R.s = rb;
+  R.lam = rb + a.RS;
+  R.dsa = rb + 2 * (size_t)a.RS;
+  R.dla = rb + 3 * (size_t)a.RS;
+  R.cl = cl;
+  R.lstart = lstart;
+  int status = NB_STATUS_FAILED, it0 = 0, it1 = 0;
+  double obj = 0.0;
+  bool ok = nb_qp_solve<32>(g, cs, tables + (n - 1), &sh, R, ci, nl, xout, &it0, &obj);
+  if (ok)
+    status = NB_STATUS_OK;
+  else
+  {
+    ok = nb_qp_solve<32>(g, cs, tables + NB_NPOL + (n - 1), &sh, R, ci, nl, xout, &it1, &obj);
+    if (ok) status = NB_STATUS_FALLBACK;
+  }
+  g.sync();
+  // copy the solution (:866-876) or keep the initial path (:858); z override (:879-880)
+  const double T = cs.T;
+  double pfx = 0, pfy = 0;
+  {
+    const double qp[4] = { T * T * T, T * T, T, 1.0 };
+    for (int r = 0; r < 4; r++)
+    {
+      pfx += qp[r] * ci[4 * (n - 1) + r];
+      pfy += qp[r] * ci[32 + 4 * (n - 1) + r];
+    }
+  }
+  const double dx = ci[3] - pfx, dy = ci[32 + 3] - pfy;
+  const bool keep_z = sqrt(dx * dx + dy * dy) < 1.0;
+  double* co = a.coeff_out + (size_t)b * 96;
+  for (int q = threadIdx.x; q < 96; q += 32)
+  {
+    const int ax = q / 32, r = q % 32;
+    double v = ci[q];
+    if (ok && r < 4 * n && !(ax == 2 && keep_z)) v = xout[q];
+    co[q] = v;
+  }
+  if (threadIdx.x == 0)
+  {
+    a.obj[b] = ok ? obj : 0.0;
+    a.status[b] = status;
+    a.iters[2 * b] = it0;
+    a.iters[2 * b + 1] = it1;
+  }
+}
+
+__global__ void k_separate(int L, const int64_t* a_ptr, const double* a_xy, const int64_t* b_ptr, const double* b_xy,
+                           int a_polygon, double* out_line, uint8_t* out_ok)
+{
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  double o[3];
+  const bool ok = nb_separate(a_xy + 2 * a_ptr[l], (int)(a_ptr[l + 1] - a_ptr[l]), a_polygon != 0, b_xy + 2 * b_ptr[l],
+                              (int)(b_ptr[l + 1] - b_ptr[l]), o);
+  out_line[3 * l] = o[0];
+  out_line[3 * l + 1] = o[1];
+  out_line[3 * l + 2] = o[2];
+  out_ok[l] = ok ? 1 : 0;
+}
+
+// PolySolverGurobi::generatePwpOut sampling loop (solver_gurobi_poly.cpp:911-934)
+__global__ void k_traj(int B, const int* n_int, const double* coeff, double T, double dc, int max_states, double* states,
+                       int* n_states)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int n = n_int[b];
+  const double* cf = coeff + (size_t)b * 96;
+  double t = 0;
+  int i = 0, cnt = 0;
+  while (i < n && cnt < max_states)
+  {
+    const double dt = t - i * T;
+    double* st = states + ((size_t)b * max_states + cnt) * 12;
+    for (int ax = 0; ax < 3; ax++)
+    {
+      const double* c = cf + ax * 32 + 4 * i;
+      st[ax] = c[0] * dt * dt * dt + c[1] * dt * dt + c[2] * dt + c[3];
+      st[3 + ax] = c[0] * 3 * dt * dt + c[1] * 2 * dt + c[2];
+      st[6 + ax] = c[0] * 6 * dt + c[1] * 2;
+      st[9 + ax] = c[0] * 6;
+    }
+    cnt++;
+    t += dc;
+    if (t > (i + 1) * T) i++;
+  }
+  n_states[b] = cnt;
+}
+
+// ------------------------------------------------------------------------------------------ ABI
+
+extern "C" int nb_create(const nb_params* par, const double* pb, int device, nb_handle** out)
+{
+  if (!par || !pb || !out) return NB_ERR_ARG;
+  if (par->num_pol < 1 || par->num_pol > NB_NPOL || par->deg_pol != 3 || par->use_linear_constraints != 1 ||
+      par->num_agents < 1 || par->T_span <= 0)
+  {
+    g_err = "nb_create: unsupported parameters (num_pol<=8, deg_pol==3, use_linear_constraints==1)";
+    return NB_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+  {
+    g_err = "no CUDA device visible: libneptune_b200 has no CPU fallback";
+    return NB_ERR_NO_DEVICE;
+  }
+  if (device < 0) NB_CUDA(cudaGetDevice(&device));
+  NB_CUDA(cudaSetDevice(device));
+  nb_handle* h = new nb_handle();
+  h->par = *par;
+  h->device = device;
+  h->launches = 0;
+  nb_build_consts(par, &h->cs);
+  std::vector<NbQpTable> tabs(2 * NB_NPOL);
+  for (int mode = 0; mode < 2; mode++)
+    for (int n = 1; n <= NB_NPOL; n++)
+      if (!nb_build_table(&h->cs, n, mode, &tabs[mode * NB_NPOL + n - 1]))
+      {
+        g_err = "nb_create: degenerate QP table";
+        delete h;
+        return NB_ERR_ARG;
+      }
+  NB_CUDA(cudaMalloc(&h->d_tables, sizeof(NbQpTable) * tabs.size()));
+  NB_CUDA(cudaMemcpy(h->d_tables, tabs.data(), sizeof(NbQpTable) * tabs.size(), cudaMemcpyHostToDevice));
+  NB_CUDA(cudaMalloc(&h->d_pb, sizeof(double) * 2 * par->num_agents));
+  NB_CUDA(cudaMemcpy(h->d_pb, pb, sizeof(double) * 2 * par->num_agents, cudaMemcpyHostToDevice));
+  h->d_st_ptr = nullptr;
+  h->d_st_xy = nullptr;
+  h->d_strep = nullptr;
+  h->st_nvert = 0;
+  NB_CUDA(cudaMalloc(&h->d_st_ptr, sizeof(int64_t) * (par->num_static + 1)));
+  NB_CUDA(cudaMemset(h->d_st_ptr, 0, sizeof(int64_t) * (par->num_static + 1)));
+  *out = h;
+  return NB_OK;
+}
+
+extern "C" void nb_destroy(nb_handle* h)
+{
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_tables);
+  cudaFree(h->d_pb);
+  cudaFree(h->d_st_ptr);
+  cudaFree(h->d_st_xy);
+  cudaFree(h->d_strep);
+  for (auto& b : h->in) b.release();
+  for (auto& b : h->out) b.release();
+  h->lines.release(), h->line_ok.release(), h->cl.release(), h->lstart.release(), h->rows.release(), h->err.release();
+  delete h;
+}
+
+extern "C" long long nb_launch_count(const nb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int nb_line_slots(const nb_handle* h, int n_hull_slots)
+{
+  return n_hull_slots + h->par.num_agents + h->par.num_static + h->par.ent_slots;
+}
+
+extern "C" int nb_set_static(nb_handle* h, const int64_t* st_ptr, const double* st_xy, const double* strep)
+{
+  if (!h) return NB_ERR_ARG;
+  const int M = h->par.num_static;
+  if (M == 0) return NB_OK;
+  if (!st_ptr || !st_xy) return NB_ERR_ARG;
+  NB_CUDA(cudaSetDevice(h->device));
+  h->st_nvert = st_ptr[M];
+  cudaFree(h->d_st_xy);
+  cudaFree(h->d_strep);
+  h->d_st_xy = nullptr;
+  h->d_strep = nullptr;
+  NB_CUDA(cudaMemcpy(h->d_st_ptr, st_ptr, sizeof(int64_t) * (M + 1), cudaMemcpyHostToDevice));
+  NB_CUDA(cudaMalloc(&h->d_st_xy, sizeof(double) * 2 * h->st_nvert));
+  NB_CUDA(cudaMemcpy(h->d_st_xy, st_xy, sizeof(double) * 2 * h->st_nvert, cudaMemcpyHostToDevice));
+  if (strep)
+  {
+    NB_CUDA(cudaMalloc(&h->d_strep, sizeof(double) * 4 * M));
+    NB_CUDA(cudaMemcpy(h->d_strep, strep, sizeof(double) * 4 * M, cudaMemcpyHostToDevice));
+  }
+  return NB_OK;
+}
+
+namespace
+{
+// stage one NB_HOST input array (or pass an NB_DEVICE pointer through)
+template <typename T>
+int stage_in(nb_handle* h, int slot, int space, const T* src, size_t count, cudaStream_t st, const T** dst)
+{
+  if (space == NB_DEVICE || src == nullptr || count == 0)
+  {
+    *dst = src;
+    return NB_OK;
+  }
+  if (h->in[slot].ensure(count * sizeof(T)))
+  {
+    g_err = "cudaMalloc failed while staging inputs";
+    return NB_ERR_CUDA;
+  }
+  NB_CUDA(cudaMemcpyAsync(h->in[slot].p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+  *dst = (const T*)h->in[slot].p;
+  return NB_OK;
+}
+template <typename T>
+int stage_out(nb_handle* h, int slot, int space, T* user, size_t count, T** dst)
+{
+  if (space == NB_DEVICE || user == nullptr)
+  {
+    *dst = user;
+    return NB_OK;
+  }
+  if (h->out[slot].ensure(count * sizeof(T)))
+  {
+    g_err = "cudaMalloc failed while staging outputs";
+    return NB_ERR_CUDA;
+  }
+  *dst = (T*)h->out[slot].p;
+  return NB_OK;
+}
+}  // namespace
+
+extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stream)
+{
+  if (!h || !a || a->B < 0) return NB_ERR_ARG;
+  if (a->B == 0) return NB_OK;
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = a->B, N = h->par.num_agents, M = h->par.num_static, NA = N + M, cap = h->par.ent_cap;
+  const int NH = a->n_hull_slots, LS = nb_line_slots(h, NH);
+  const int sp = a->space;
+  int rc;
+  NbLinesIn in;
+  in.NH = NH;
+  if ((rc = stage_in(h, 0, sp, a->agent_id, (size_t)B, st, &in.agent_id))) return rc;
+  if ((rc = stage_in(h, 1, sp, a->n_int, (size_t)B, st, &in.n_int))) return rc;
+  if ((rc = stage_in(h, 2, sp, a->coeff_init, (size_t)B * 96, st, &in.coeff_init))) return rc;
+  if ((rc = stage_in(h, 3, sp, a->hull_ptr, (size_t)B * NH * 8 + 1, st, &in.hull_ptr))) return rc;
+  if ((rc = stage_in(h, 4, sp, a->hull_xy, (size_t)a->hull_nvert * 2, st, &in.hull_xy))) return rc;
+  if ((rc = stage_in(h, 5, sp, a->nih0, (size_t)B * N * 16, st, &in.nih0))) return rc;
+  if ((rc = stage_in(h, 6, sp, a->esv_cnt, (size_t)B * 18, st, &in.esv_cnt))) return rc;
+  if ((rc = stage_in(h, 7, sp, a->esv_alpha, (size_t)B * 9 * cap * 2, st, &in.esv_alpha))) return rc;
+  if ((rc = stage_in(h, 8, sp, a->esv_active, (size_t)B * 9 * NA, st, &in.esv_active))) return rc;
+  if ((rc = stage_in(h, 9, sp, a->bp_cnt, (size_t)N, st, &in.bp_cnt))) return rc;
+  if ((rc = stage_in(h, 10, sp, a->bp_xy, (size_t)N * h->par.bp_max * 2, st, &in.bp_xy))) return rc;
+  in.st_ptr = h->d_st_ptr;
+  in.st_xy = h->d_st_xy;
+  in.pb = h->d_pb;
+  if (M > 0 && !h->d_st_xy)
+  {
+    g_err = "nb_replan_batch: num_static > 0 but nb_set_static was never called";
+    return NB_ERR_ARG;
+  }
+  // scratch
+  const size_t nslots = (size_t)B * NB_NPOL * LS;
+  const int RS = 6 * NB_NFEAT_AX + 4 * NB_NPOL * LS;
+  if (h->lines.ensure(nslots * 3 * sizeof(double)) || h->line_ok.ensure(nslots) ||
+      h->cl.ensure(nslots * 3 * sizeof(double)) || h->lstart.ensure((size_t)B * 9 * sizeof(int)) ||
+      h->rows.ensure((size_t)B * 4 * RS * sizeof(double)) || h->err.ensure(sizeof(int)))
+  {
+    g_err = "cudaMalloc failed for scratch buffers";
+    return NB_ERR_CUDA;
+  }
+  NB_CUDA(cudaMemsetAsync(h->err.p, 0, sizeof(int), st));
+  NbQpArgs q;
+  q.n_int = in.n_int;
+  q.coeff_init = in.coeff_init;
+  q.lines = (const double*)h->lines.p;
+  q.ok = (const uint8_t*)h->line_ok.p;
+  q.LS = LS;
+  q.cl = (double*)h->cl.p;
+  q.lstart = (int*)h->lstart.p;
+  q.rows = (double*)h->rows.p;
+  q.RS = RS;
+  if ((rc = stage_out(h, 0, sp, a->coeff_out, (size_t)B * 96, &q.coeff_out))) return rc;
+  if ((rc = stage_out(h, 1, sp, a->obj, (size_t)B, &q.obj))) return rc;
+  if ((rc = stage_out(h, 2, sp, a->status, (size_t)B, &q.status))) return rc;
+  if ((rc = stage_out(h, 3, sp, a->iters, (size_t)B * 2, &q.iters))) return rc;
+
+  k_lines<<<B * NB_NPOL, 128, 0, st>>>(h->cs, in, LS, (double*)h->lines.p, (uint8_t*)h->line_ok.p, (int*)h->err.p);
+  k_qp<<<B, 32, 0, st>>>(h->cs, h->d_tables, q);
+  h->launches += 2;
+  NB_CUDA(cudaGetLastError());
+
+  if (sp == NB_HOST)
+  {
+    NB_CUDA(cudaMemcpyAsync(a->coeff_out, q.coeff_out, (size_t)B * 96 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(a->obj, q.obj, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(a->status, q.status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(a->iters, q.iters, (size_t)B * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  if (a->lines)
+    NB_CUDA(cudaMemcpyAsync(a->lines, h->lines.p, nslots * 3 * sizeof(double),
+                            sp == NB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  if (a->line_ok)
+    NB_CUDA(cudaMemcpyAsync(a->line_ok, h->line_ok.p, nslots,
+                            sp == NB_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+  if (sp == NB_HOST)
+  {
+    int err = 0;
+    NB_CUDA(cudaMemcpyAsync(&err, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaStreamSynchronize(st));
+    if (err)
+    {
+      g_err = "nb_replan_batch: more non-entangling LPs than ent_slots in some interval";
+      return NB_ERR_CAPACITY;
+    }
+  }
+  return NB_OK;
+}
+
+extern "C" int nb_separate_batch(nb_handle* h, int32_t L, int32_t space, const int64_t* a_ptr, const double* a_xy,
+                                 const int64_t* b_ptr, const double* b_xy, int32_t a_polygon, double* out_line,
+                                 uint8_t* out_ok, void* stream)
+{
+  if (!h || L < 0) return NB_ERR_ARG;
+  if (L == 0) return NB_OK;
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t *dap, *dbp;
+  const double *dax, *dbx;
+  double* dline;
+  uint8_t* dok;
+  int rc;
+  size_t na = 0, nb = 0;
+  if (space == NB_HOST)
+  {
+    na = (size_t)a_ptr[L];
+    nb = (size_t)b_ptr[L];
+  }
+  if ((rc = stage_in(h, 0, space, a_ptr, (size_t)L + 1, st, &dap))) return rc;
+  if ((rc = stage_in(h, 1, space, a_xy, na * 2, st, &dax))) return rc;
+  if ((rc = stage_in(h, 2, space, b_ptr, (size_t)L + 1, st, &dbp))) return rc;
+  if ((rc = stage_in(h, 3, space, b_xy, nb * 2, st, &dbx))) return rc;
+  if ((rc = stage_out(h, 0, space, out_line, (size_t)L * 3, &dline))) return rc;
+  if ((rc = stage_out(h, 1, space, out_ok, (size_t)L, &dok))) return rc;
+  k_separate<<<(L + 127) / 128, 128, 0, st>>>(L, dap, dax, dbp, dbx, a_polygon, dline, dok);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
+  if (space == NB_HOST)
+  {
+    NB_CUDA(cudaMemcpyAsync(out_line, dline, (size_t)L * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(out_ok, dok, (size_t)L, cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaStreamSynchronize(st));
+  }
+  return NB_OK;
+}
+
+extern "C" int nb_generate_traj_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
+                                      double dc, int32_t max_states, double* states, int32_t* n_states, void* stream)
+{
+  if (!h || B < 0 || max_states <= 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int* dn;
+  const double* dc_;
+  double* dstates;
+  int* dns;
+  int rc;
+  if ((rc = stage_in(h, 0, space, n_int, (size_t)B, st, &dn))) return rc;
+  if ((rc = stage_in(h, 1, space, coeff, (size_t)B * 96, st, &dc_))) return rc;
+  if ((rc = stage_out(h, 0, space, states, (size_t)B * max_states * 12, &dstates))) return rc;
+  if ((rc = stage_out(h, 1, space, n_states, (size_t)B, &dns))) return rc;
+  k_traj<<<(B + 63) / 64, 64, 0, st>>>(B, dn, dc_, h->cs.T, dc, max_states, dstates, dns);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
+  if (space == NB_HOST)
+  {
+    NB_CUDA(cudaMemcpyAsync(states, dstates, (size_t)B * max_states * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(n_states, dns, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaStreamSynchronize(st));
+  }
+  return NB_OK;
+}

@@ -1,0 +1,629 @@
+// nb_qp.cuh -- K4: batched trajectory QP, one agent per warp-group.
+//
+// Replaces PolySolverGurobi::optimize's two m_.optimize() calls and the model they are run on
+// (reference neptune/src/solver_gurobi_poly.cpp:322-383 addObjective, :385-471 + :659-708
+// addConstraints, :804-887 optimize).  The QP is solved in the reduced
+// coordinates w of NbQpTable (equalities eliminated on the host once) by an infeasible-start
+// Mehrotra predictor-corrector interior-point method.  Every inequality row is a function of one
+// "feature" (a MINVO position / velocity control point or an end acceleration of one axis and
+// interval: bound rows :441-470) or of the (x,y) pair of one position control point (separating-line
+// rows :485-489, :546-550, :587-591, :754-758), so the normal matrix is assembled as
+// Hr + C^T W C with W diagonal plus one 2x2 coupling per control point -- no per-row outer products.
+//
+// Lane-strided SPMD phases over shared (small vectors, K) and global scratch (per-row s, lambda);
+// compiles with NL = 32 on the device and NL = 1 in the host emulation.
+#pragma once
+#include "nb_common.cuh"
+
+struct NbQpShared
+{
+  double y[3 * NB_NFEAT_AX];   // feature values
+  double dy[3 * NB_NFEAT_AX];  // feature values of a direction
+  double om[3 * NB_NFEAT_AX];  // diagonal weights  sum lambda/s
+  double La[3 * NB_NFEAT_AX];  // per-feature load of a row vector (G^T v reduced to features)
+  double Sxy[4 * NB_NPOL];     // x-y coupling weight of control point (i,k)
+  double K[NB_NV_MAX * NB_NV_MAX];
+  double w[NB_NV_MAX], dw[NB_NV_MAX], rd[NB_NV_MAX], rhs[NB_NV_MAX], g0[NB_NV_MAX], gq[NB_NV_MAX];
+  double gobj[NB_NV_MAX], invd[NB_NV_MAX];
+  double init3[3][3], pf[3], e3[3];
+  double xin[3][4 * NB_NPOL];
+};
+
+struct NbQpRows  // per-agent global scratch
+{
+  double* s;    // [384 + 4*LCAP]
+  double* lam;
+  double* dsa;
+  double* dla;
+  const double* cl;  // [L][3] compact kept lines: n0, n1, c = 1 - d
+  const int* lstart; // [n+1] first line of each interval
+};
+
+NB_HD void nb_feat_bounds(const NbConsts& cs, int ax, int j, double& lo, double& hi)
+{
+  if (j < 4)
+  {
+    lo = cs.lim_min[ax];
+    hi = cs.lim_max[ax];
+  }
+  else if (j < 7)
+  {
+    lo = -cs.v_max;
+    hi = cs.v_max;
+  }
+  else
+  {
+    lo = -cs.a_max;
+    hi = cs.a_max;
+  }
+}
+
+// y = c0 . init3 + C w  (with_const) or dy = C dw
+template <int NL>
+NB_HD void nb_qp_features(const Group<NL>& g, const NbQpTable* tb, const NbQpShared* sh_c, double* out,
+                          const double* vec, bool with_const)
+{
+  const int n = tb->n, dof = tb->dof;
+  for (int q = g.lane; q < 3 * 8 * n; q += NL)
+  {
+    const int ax = q / (8 * n), fl = q - ax * 8 * n;
+    double v = 0.0;
+    if (with_const)
+      v = tb->c0[fl][0] * sh_c->init3[ax][0] + tb->c0[fl][1] * sh_c->init3[ax][1] + tb->c0[fl][2] * sh_c->init3[ax][2];
+    for (int c = 0; c < dof; c++) v += tb->C[fl][c] * vec[ax * dof + c];
+    out[ax * NB_NFEAT_AX + fl] = v;
+  }
+}
+
+enum
+{
+  NB_PASS_RESID = 0,  // residuals, weights, predictor load; sums mu, |rp|max
+  NB_PASS_DIR_PRED,   // predictor direction: ds, dl -> scratch; step length, mu_aff sums
+  NB_PASS_LOAD_CORR,  // corrector load with rc = s lam + dsa dla - sigma mu
+  NB_PASS_DIR_CORR,   // final direction: ds, dl -> scratch; step length
+  NB_PASS_UPDATE,     // s += a ds, lam += a dl
+  NB_PASS_START       // Nocedal-Wright start: s = max(1,|s+ds|), lam likewise
+};
+
+struct NbPassAcc
+{
+  double sum_sl, rp_max, amax, sum_cross, sum_dd;
+};
+
+// one inequality row: v = row value (<= 0 wanted), gd = row . direction.  Returns the load tau that
+// this row puts on its feature(s) (for RESID / LOAD_CORR), and the diagonal weight in `wgt`.
+template <int MODE>
+NB_HD double nb_row(double* s_, double* lam_, double* dsa_, double* dla_, double v, double gd, double sigmu,
+                    double alpha, NbPassAcc& acc, double& wgt)
+{
+  double s = *s_, lam = *lam_;
+  wgt = 0.0;
+  if (MODE == NB_PASS_RESID)
+  {
+    const double rp = v + s;
+    const double inv = 1.0 / s;
+    wgt = lam * inv;
+    acc.sum_sl += s * lam;
+    acc.rp_max = fmax(acc.rp_max, fabs(rp));
+    return (lam * rp - s * lam) * inv;  // predictor: rc = s lam
+  }
+  if (MODE == NB_PASS_DIR_PRED || MODE == NB_PASS_DIR_CORR)
+  {
+    const double rp = v + s;
+    const double rc = (MODE == NB_PASS_DIR_PRED) ? s * lam : s * lam + (*dsa_) * (*dla_) - sigmu;
+    const double ds = -rp - gd;
+    const double dl = (-rc - lam * ds) / s;
+    if (ds < 0.0) acc.amax = fmin(acc.amax, -s / ds);
+    if (dl < 0.0) acc.amax = fmin(acc.amax, -lam / dl);
+    if (MODE == NB_PASS_DIR_PRED)
+    {
+      acc.sum_cross += s * dl + lam * ds;
+      acc.sum_dd += ds * dl;
+    }
+    *dsa_ = ds;
+    *dla_ = dl;
+    return 0.0;
+  }
+  if (MODE == NB_PASS_LOAD_CORR)
+  {
+    const double rp = v + s;
+    const double rc = s * lam + (*dsa_) * (*dla_) - sigmu;
+    return (lam * rp - rc) / s;
+  }
+  if (MODE == NB_PASS_UPDATE)
+  {
+    *s_ = s + alpha * (*dsa_);
+    *lam_ = lam + alpha * (*dla_);
+    return 0.0;
+  }
+  // NB_PASS_START
+  {
+    const double a = fabs(s + *dsa_), b = fabs(lam + *dla_);
+    *s_ = a > 1.0 ? a : 1.0;
+    *lam_ = b > 1.0 ? b : 1.0;
+  }
+  return 0.0;
+}
+
+// One sweep over every inequality row.  Bound rows are visited feature by feature (both sides of a
+// feature by the same lane), line rows control point by control point (lane <-> (interval, k)), so
+// all per-feature accumulations are conflict-free and in a fixed order.
+template <int NL, int MODE>
+NB_HD void nb_qp_pass(const Group<NL>& g, const NbConsts& cs, const NbQpTable* tb, NbQpShared* sh,
+                      const NbQpRows& R, double sigmu, double alpha, NbPassAcc& acc)
+{
+  const int n = tb->n;
+  const bool loads = (MODE == NB_PASS_RESID || MODE == NB_PASS_LOAD_CORR);
+  for (int q = g.lane; q < 3 * 8 * n; q += NL)
+  {
+    const int ax = q / (8 * n), fl = q - ax * 8 * n, f = ax * NB_NFEAT_AX + fl;
+    double lo, hi, w_u, w_l;
+    nb_feat_bounds(cs, ax, fl & 7, lo, hi);
+    const double yv = sh->y[f], dv = sh->dy[f];
+    const int rs = 2 * f;
+    const double t_u = nb_row<MODE>(R.s + rs, R.lam + rs, R.dsa + rs, R.dla + rs, yv - hi, dv, sigmu, alpha, acc, w_u);
+    const double t_l = nb_row<MODE>(R.s + rs + 1, R.lam + rs + 1, R.dsa + rs + 1, R.dla + rs + 1, lo - yv, -dv,
+                                    sigmu, alpha, acc, w_l);
+    if (loads)
+    {
+      sh->La[f] = t_u - t_l;
+      if (MODE == NB_PASS_RESID)
+      {
+        sh->om[f] = w_u + w_l;
+        sh->dy[f] = R.lam[rs] - R.lam[rs + 1];  // dual load for r_d, parked in dy during RESID
+      }
+    }
+  }
+  g.sync();
+  for (int q = g.lane; q < 4 * n; q += NL)
+  {
+    const int i = q >> 2, k = q & 3;
+    const int fx = i * 8 + k, fy = NB_NFEAT_AX + i * 8 + k;
+    const double yx = sh->y[fx], yy = sh->y[fy];
+    const double dx = (MODE == NB_PASS_RESID) ? 0.0 : sh->dy[fx], dyv = (MODE == NB_PASS_RESID) ? 0.0 : sh->dy[fy];
+    double sxx = 0, sxy = 0, syy = 0, lx = 0, ly = 0, dlx = 0, dly = 0;
+    for (int l = R.lstart[i]; l < R.lstart[i + 1]; l++)
+    {
+      const double n0 = R.cl[3 * l], n1 = R.cl[3 * l + 1], c = R.cl[3 * l + 2];
+      const int rs = 6 * NB_NFEAT_AX + 4 * l + k;
+      double wgt;
+      const double t = nb_row<MODE>(R.s + rs, R.lam + rs, R.dsa + rs, R.dla + rs, n0 * yx + n1 * yy - c,
+                                    n0 * dx + n1 * dyv, sigmu, alpha, acc, wgt);
+      if (loads)
+      {
+        lx += t * n0;
+        ly += t * n1;
+        if (MODE == NB_PASS_RESID)
+        {
+          sxx += wgt * n0 * n0;
+          sxy += wgt * n0 * n1;
+          syy += wgt * n1 * n1;
+          const double lam = R.lam[rs];
+          dlx += lam * n0;
+          dly += lam * n1;
+        }
+      }
+    }
+    if (loads)
+    {
+      sh->La[fx] += lx;
+      sh->La[fy] += ly;
+      if (MODE == NB_PASS_RESID)
+      {
+        sh->om[fx] += sxx;
+        sh->om[fy] += syy;
+        sh->Sxy[q] = sxy;
+        sh->dy[fx] += dlx;
+        sh->dy[fy] += dly;
+      }
+    }
+  }
+  g.sync();
+}
+
+// out[a] = sum_f C[f][c] * vecF[ax*64+f]   (a = ax*dof + c): C^T applied to a per-feature vector
+template <int NL>
+NB_HD double nb_qp_ct(const NbQpTable* tb, const double* vecF, int ax, int c)
+{
+  const int n = tb->n;
+  double v = 0.0;
+  for (int fl = 0; fl < 8 * n; fl++) v += tb->C[fl][c] * vecF[ax * NB_NFEAT_AX + fl];
+  return v;
+}
+
+// Cholesky of the nv x nv matrix in sh->K (lower, row-major, ld = nv) and solves.
+template <int NL>
+NB_HD void nb_qp_chol(const Group<NL>& g, NbQpShared* sh, int nv)
+{
+  double* K = sh->K;
+  for (int k = 0; k < nv; k++)
+  {
+    g.sync();
+    const double orig = K[k * nv + k];
+    // rank-deficiency guard identical in spirit to the oracle's: floor the pivot
+    double d = orig;
+    d = d > 1e-300 ? d : 1e-300;
+    const double piv = sqrt(d), ip = 1.0 / piv;
+    g.sync();
+    if (g.lane == 0)
+    {
+      K[k * nv + k] = piv;
+      sh->invd[k] = ip;
+    }
+    for (int i = k + 1 + g.lane; i < nv; i += NL) K[i * nv + k] *= ip;
+    g.sync();
+    const int rem = nv - k - 1;
+    for (int q = g.lane; q < rem * rem; q += NL)
+    {
+      const int i = k + 1 + q / rem, j = k + 1 + q % rem;
+      if (j <= i) K[i * nv + j] -= K[i * nv + k] * K[j * nv + k];
+    }
+  }
+  g.sync();
+}
+
+template <int NL>
+NB_HD void nb_qp_cholsolve(const Group<NL>& g, NbQpShared* sh, int nv, double* b)
+{
+  const double* K = sh->K;
+  for (int k = 0; k < nv; k++)
+  {
+    g.sync();
+    const double xk = b[k] * sh->invd[k];
+    g.sync();
+    if (g.lane == 0) b[k] = xk;
+    for (int i = k + 1 + g.lane; i < nv; i += NL) b[i] -= K[i * nv + k] * xk;
+  }
+  for (int k = nv - 1; k >= 0; k--)
+  {
+    g.sync();
+    const double xk = b[k] * sh->invd[k];
+    g.sync();
+    if (g.lane == 0) b[k] = xk;
+    for (int i = g.lane; i < k; i += NL) b[i] -= K[k * nv + i] * xk;
+  }
+  g.sync();
+}
+
+// objective value at the full coefficients (solver_gurobi_poly.cpp:322-380, :882)
+NB_HD double nb_objective(const NbConsts& cs, int n, int mode, const double* x /*[3][32]*/, const double pf[3])
+{
+  const double T = cs.T;
+  double f = 0.0;
+  for (int ax = 0; ax < 3; ax++)
+  {
+    for (int i = 0; i < n; i++) f += 36.0 * T * x[ax * 32 + 4 * i] * x[ax * 32 + 4 * i];
+    const double* c = x + ax * 32 + 4 * (n - 1);
+    const double e = T * T * T * c[0] + T * T * c[1] + T * c[2] + c[3] - pf[ax];
+    f += cs.W * e * e;
+    if (mode == 1)
+    {
+      const double v = 3 * T * T * c[0] + 2 * T * c[1] + c[2], a = 6 * T * c[0] + 2 * c[1];
+      f += cs.W * (v * v + a * a);
+    }
+  }
+  return f;
+}
+
+// Solve one QP attempt.  coeff_init: [3][8][4] of this agent.  On success writes x_out [3][32]
+// (coefficients, axis-major) and returns true.  *iters_out = interior-point iterations used.
+template <int NL>
+NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* tb, NbQpShared* sh,
+                       const NbQpRows& R, const double* coeff_init, int nlines, double* x_out, int* iters_out,
+                       double* obj_out)
+{
+  const int n = tb->n, dof = tb->dof, nv = 3 * dof, mode = tb->mode;
+  const double T = cs.T;
+  const double qp[4] = { T * T * T, T * T, T, 1.0 };
+  *iters_out = 0;
+  // ---- per-agent constants
+  g.sync();
+  for (int q = g.lane; q < 3 * 4 * n; q += NL)
+  {
+    const int ax = q / (4 * n), r = q - ax * 4 * n;
+    sh->xin[ax][r] = coeff_init[ax * 32 + r];
+  }
+  if (g.lane == 0)
+    for (int ax = 0; ax < 3; ax++)
+    {
+      const double* c0 = coeff_init + ax * 32;
+      sh->init3[ax][0] = c0[1];
+      sh->init3[ax][1] = c0[2];
+      sh->init3[ax][2] = c0[3];
+      const double* cl = coeff_init + ax * 32 + 4 * (n - 1);
+      sh->pf[ax] = qp[0] * cl[0] + qp[1] * cl[1] + qp[2] * cl[2] + qp[3] * cl[3];  // final_pos_ :226-228
+    }
+  g.sync();
+  const double ddx = sh->init3[0][2] - sh->pf[0], ddy = sh->init3[1][2] - sh->pf[1], ddz = sh->init3[2][2] - sh->pf[2];
+  const bool has_qc = sqrt(ddx * ddx + ddy * ddy + ddz * ddz) < 1.0;  // :697-702
+  const int m = 48 * n + 4 * nlines, mq = m + (has_qc ? 1 : 0);
+  double bmax = 0.0, hn = 0.0;
+  for (int ax = 0; ax < 3; ax++)
+    for (int c = 0; c < 3; c++) bmax = fmax(bmax, fabs(sh->init3[ax][c]));
+  for (int ax = 0; ax < 3; ax++) hn = fmax(hn, fmax(fabs(cs.lim_min[ax]), fabs(cs.lim_max[ax])));
+  hn = fmax(hn, fmax(cs.v_max, cs.a_max));
+  {
+    double hl = 0.0;
+    for (int l = g.lane; l < nlines; l += NL) hl = fmax(hl, fabs(R.cl[3 * l + 2]));
+    hn = fmax(hn, g.max(hl));
+  }
+  if (tb->has_resid)
+  {  // n = 1 with terminal v/a equalities: 5 rows on 4 unknowns per axis
+    double r = 0.0;
+    for (int ax = 0; ax < 3; ax++)
+      for (int q = 0; q < 2; q++)
+        r = fmax(r, fabs(tb->Rres[q][0] * sh->init3[ax][0] + tb->Rres[q][1] * sh->init3[ax][1] +
+                         tb->Rres[q][2] * sh->init3[ax][2]));
+    if (r > 1e-9 * (1.0 + bmax)) return false;
+  }
+  // w0 = Z^T (x_frontend - Pm init3), g0 = Gr init3 + gpf pf
+  for (int a = g.lane; a < nv; a += NL)
+  {
+    const int ax = a / dof, c = a - ax * dof;
+    double v = 0.0;
+    for (int r = 0; r < 4 * n; r++)
+    {
+      const double xp = tb->Pm[r][0] * sh->init3[ax][0] + tb->Pm[r][1] * sh->init3[ax][1] + tb->Pm[r][2] * sh->init3[ax][2];
+      v += tb->Z[r][c] * (sh->xin[ax][r] - xp);
+    }
+    sh->w[a] = v;
+    sh->g0[a] = tb->Gr[c][0] * sh->init3[ax][0] + tb->Gr[c][1] * sh->init3[ax][1] + tb->Gr[c][2] * sh->init3[ax][2] +
+                tb->gpf[c] * sh->pf[ax];
+    sh->dw[a] = 0.0;
+  }
+  g.sync();
+  // objective at w = 0 (constant term of the reduced objective)
+  double fconst;
+  {
+    double xp[96];
+    for (int ax = 0; ax < 3; ax++)
+      for (int r = 0; r < 4 * n; r++)
+        xp[ax * 32 + r] = tb->Pm[r][0] * sh->init3[ax][0] + tb->Pm[r][1] * sh->init3[ax][1] + tb->Pm[r][2] * sh->init3[ax][2];
+    fconst = nb_objective(cs, n, mode, xp, sh->pf);
+  }
+  nb_qp_features<NL>(g, tb, sh, sh->y, sh->w, true);
+  g.sync();
+
+#define NB_QC_EVAL(cval)                                                                                   \
+  {                                                                                                        \
+    cval = -0.10 * 0.10;                                                                                   \
+    for (int ax = 0; ax < 3; ax++)                                                                         \
+    {                                                                                                      \
+      double e = tb->tq0[0] * sh->init3[ax][0] + tb->tq0[1] * sh->init3[ax][1] + tb->tq0[2] * sh->init3[ax][2] - \
+                 sh->pf[ax];                                                                               \
+      for (int c = 0; c < dof; c++) e += tb->tq[c] * sh->w[ax * dof + c];                                  \
+      e3[ax] = e;                                                                                          \
+      cval += e * e;                                                                                       \
+    }                                                                                                      \
+  }
+
+  double e3[3] = { 0, 0, 0 };
+  bool converged = false;
+  if (dof == 0)
+  {  // the equalities leave a single point: feasible iff every row holds there
+    double worst = -1e300;
+    for (int q = g.lane; q < 3 * 8 * n; q += NL)
+    {
+      const int ax = q / (8 * n), fl = q - ax * 8 * n;
+      double lo, hi;
+      nb_feat_bounds(cs, ax, fl & 7, lo, hi);
+      const double yv = sh->y[ax * NB_NFEAT_AX + fl];
+      worst = fmax(worst, fmax(yv - hi, lo - yv));
+    }
+    for (int q = g.lane; q < 4 * n; q += NL)
+    {
+      const int i = q >> 2, k = q & 3;
+      for (int l = R.lstart[i]; l < R.lstart[i + 1]; l++)
+        worst = fmax(worst, R.cl[3 * l] * sh->y[i * 8 + k] + R.cl[3 * l + 1] * sh->y[NB_NFEAT_AX + i * 8 + k] - R.cl[3 * l + 2]);
+    }
+    worst = g.max(worst);
+    bool ok = !(worst > 1e-9 * (1.0 + hn));
+    if (has_qc)
+    {
+      double cval;
+      NB_QC_EVAL(cval);
+      if (cval > 1e-9) ok = false;
+    }
+    converged = ok;
+  }
+  else
+  {
+    // ---- start: s = max(h - G w, 1), lam = 1
+    for (int q = g.lane; q < 3 * 8 * n; q += NL)
+    {
+      const int ax = q / (8 * n), fl = q - ax * 8 * n, f = ax * NB_NFEAT_AX + fl;
+      double lo, hi;
+      nb_feat_bounds(cs, ax, fl & 7, lo, hi);
+      const double yv = sh->y[f];
+      R.s[2 * f] = fmax(hi - yv, 1.0);
+      R.s[2 * f + 1] = fmax(yv - lo, 1.0);
+      R.lam[2 * f] = 1.0;
+      R.lam[2 * f + 1] = 1.0;
+    }
+    for (int q = g.lane; q < 4 * n; q += NL)
+    {
+      const int i = q >> 2, k = q & 3;
+      for (int l = R.lstart[i]; l < R.lstart[i + 1]; l++)
+      {
+        const int rs = 6 * NB_NFEAT_AX + 4 * l + k;
+        const double v = R.cl[3 * l + 2] - R.cl[3 * l] * sh->y[i * 8 + k] - R.cl[3 * l + 1] * sh->y[NB_NFEAT_AX + i * 8 + k];
+        R.s[rs] = fmax(v, 1.0);
+        R.lam[rs] = 1.0;
+      }
+    }
+    double s_q = 1.0, lam_q = 1.0, dsa_q = 0.0, dla_q = 0.0;
+    if (has_qc)
+    {
+      double cval;
+      NB_QC_EVAL(cval);
+      s_q = fmax(-cval, 1.0);
+    }
+    g.sync();
+
+    int it = 0;
+    for (it = 0; it <= cs.max_iter; it++)
+    {
+      const bool init_pass = (it == 0);
+      // ---- residuals and weights
+      NbPassAcc acc = { 0.0, 0.0, 1e300, 0.0, 0.0 };
+      nb_qp_pass<NL, NB_PASS_RESID>(g, cs, tb, sh, R, 0.0, 0.0, acc);
+      double cval = 0.0, rp_q = 0.0;
+      if (has_qc)
+      {
+        NB_QC_EVAL(cval);
+        rp_q = cval + s_q;
+      }
+      double mu = g.sum(acc.sum_sl) + (has_qc ? s_q * lam_q : 0.0);
+      mu /= mq;
+      double rpn = g.max(acc.rp_max);
+      if (has_qc) rpn = fmax(rpn, fabs(rp_q));
+      // r_d = Hr w + g0 + C^T(lambda load) + lam_q grad c ; gobj = Hr w + g0
+      for (int a = g.lane; a < nv; a += NL)
+      {
+        const int ax = a / dof, c = a - ax * dof;
+        double go = sh->g0[a];
+        for (int c2 = 0; c2 < dof; c2++) go += tb->Hr[c][c2] * sh->w[ax * dof + c2];
+        sh->gobj[a] = go;
+        const double gqa = has_qc ? 2.0 * e3[ax] * tb->tq[c] : 0.0;
+        sh->gq[a] = gqa;
+        sh->rd[a] = go + nb_qp_ct<NL>(tb, sh->dy, ax, c) + lam_q * gqa * (has_qc ? 1.0 : 0.0);
+      }
+      g.sync();
+      double rdn = 0.0, gn = 0.0, fobj = fconst;
+      for (int a = 0; a < nv; a++)
+      {
+        rdn = fmax(rdn, fabs(sh->rd[a]));
+        gn = fmax(gn, fabs(sh->gobj[a]));
+        fobj += 0.5 * (sh->g0[a] + sh->gobj[a]) * sh->w[a];
+      }
+      if (!init_pass)
+      {
+        if (rpn <= cs.tol * (1.0 + hn) && rdn <= cs.tol * (1.0 + gn) && mu * mq <= cs.tol * (1.0 + fabs(fobj)))
+        {
+          converged = true;
+          break;
+        }
+        if (it == cs.max_iter) break;
+        if (!(mu == mu) || !(rpn == rpn) || !(rdn == rdn)) break;
+      }
+      // ---- K = Hobj + C^T W C (+ quadratic-constraint terms), lower triangle
+      const double d_q = has_qc ? lam_q / s_q : 0.0;
+      for (int q = g.lane; q < nv * nv; q += NL)
+      {
+        const int a = q / nv, b = q - a * nv;
+        if (b > a) continue;
+        const int axa = a / dof, ca = a - axa * dof, axb = b / dof, cb = b - axb * dof;
+        double v = 0.0;
+        if (axa == axb)
+        {
+          v = tb->Hr[ca][cb];
+          const double* om = sh->om + axa * NB_NFEAT_AX;
+          for (int fl = 0; fl < 8 * n; fl++) v += om[fl] * tb->C[fl][ca] * tb->C[fl][cb];
+          if (has_qc) v += lam_q * 2.0 * tb->tq[ca] * tb->tq[cb];
+        }
+        else if (axa == 1 && axb == 0)
+        {
+          for (int i = 0; i < n; i++)
+            for (int k = 0; k < 4; k++) v += sh->Sxy[i * 4 + k] * tb->C[i * 8 + k][ca] * tb->C[i * 8 + k][cb];
+        }
+        if (has_qc) v += d_q * sh->gq[a] * sh->gq[b];
+        sh->K[a * nv + b] = v;
+      }
+      g.sync();
+      nb_qp_chol<NL>(g, sh, nv);
+      // ---- predictor
+      const double tau_q = has_qc ? (lam_q * rp_q - s_q * lam_q) / s_q : 0.0;
+      for (int a = g.lane; a < nv; a += NL)
+      {
+        const int ax = a / dof, c = a - ax * dof;
+        sh->dw[a] = -sh->rd[a] - nb_qp_ct<NL>(tb, sh->La, ax, c) - sh->gq[a] * tau_q;
+      }
+      g.sync();
+      nb_qp_cholsolve<NL>(g, sh, nv, sh->dw);
+      nb_qp_features<NL>(g, tb, sh, sh->dy, sh->dw, false);
+      g.sync();
+      acc = NbPassAcc{ 0.0, 0.0, 1e300, 0.0, 0.0 };
+      nb_qp_pass<NL, NB_PASS_DIR_PRED>(g, cs, tb, sh, R, 0.0, 0.0, acc);
+      double amax = g.min(acc.amax), scross = g.sum(acc.sum_cross), sdd = g.sum(acc.sum_dd);
+      if (has_qc)
+      {
+        double gd = 0.0;
+        for (int a = 0; a < nv; a++) gd += sh->gq[a] * sh->dw[a];
+        dsa_q = -rp_q - gd;
+        dla_q = (-s_q * lam_q - lam_q * dsa_q) / s_q;
+        if (dsa_q < 0.0) amax = fmin(amax, -s_q / dsa_q);
+        if (dla_q < 0.0) amax = fmin(amax, -lam_q / dla_q);
+        scross += s_q * dla_q + lam_q * dsa_q;
+        sdd += dsa_q * dla_q;
+      }
+      if (init_pass)
+      {  // Nocedal-Wright starting-point correction
+        nb_qp_pass<NL, NB_PASS_START>(g, cs, tb, sh, R, 0.0, 0.0, acc);
+        if (has_qc)
+        {
+          s_q = fmax(fabs(s_q + dsa_q), 1.0);
+          lam_q = fmax(fabs(lam_q + dla_q), 1.0);
+        }
+        continue;
+      }
+      const double a_aff = amax < 1.0 ? amax : 1.0;
+      const double mu_aff = (mu * mq + a_aff * scross + a_aff * a_aff * sdd) / mq;
+      const double rat = mu_aff / mu;
+      const double sigmu = rat * rat * rat * mu;
+      // ---- corrector
+      nb_qp_pass<NL, NB_PASS_LOAD_CORR>(g, cs, tb, sh, R, sigmu, 0.0, acc);
+      const double rc_q = s_q * lam_q + dsa_q * dla_q - sigmu;
+      const double tau_q2 = has_qc ? (lam_q * rp_q - rc_q) / s_q : 0.0;
+      for (int a = g.lane; a < nv; a += NL)
+      {
+        const int ax = a / dof, c = a - ax * dof;
+        sh->dw[a] = -sh->rd[a] - nb_qp_ct<NL>(tb, sh->La, ax, c) - sh->gq[a] * tau_q2;
+      }
+      g.sync();
+      nb_qp_cholsolve<NL>(g, sh, nv, sh->dw);
+      nb_qp_features<NL>(g, tb, sh, sh->dy, sh->dw, false);
+      g.sync();
+      acc = NbPassAcc{ 0.0, 0.0, 1e300, 0.0, 0.0 };
+      nb_qp_pass<NL, NB_PASS_DIR_CORR>(g, cs, tb, sh, R, sigmu, 0.0, acc);
+      amax = g.min(acc.amax);
+      double ds_q = 0.0, dl_q = 0.0;
+      if (has_qc)
+      {
+        double gd = 0.0;
+        for (int a = 0; a < nv; a++) gd += sh->gq[a] * sh->dw[a];
+        ds_q = -rp_q - gd;
+        dl_q = (-rc_q - lam_q * ds_q) / s_q;
+        if (ds_q < 0.0) amax = fmin(amax, -s_q / ds_q);
+        if (dl_q < 0.0) amax = fmin(amax, -lam_q / dl_q);
+      }
+      const double eta = 1.0 - 1.0 / ((it + 3.0) * (it + 3.0));
+      double al = eta * amax;
+      if (al > 1.0) al = 1.0;
+      nb_qp_pass<NL, NB_PASS_UPDATE>(g, cs, tb, sh, R, 0.0, al, acc);
+      if (has_qc)
+      {
+        s_q += al * ds_q;
+        lam_q += al * dl_q;
+      }
+      for (int a = g.lane; a < nv; a += NL) sh->w[a] += al * sh->dw[a];
+      g.sync();
+      nb_qp_features<NL>(g, tb, sh, sh->y, sh->w, true);
+      g.sync();
+    }
+    *iters_out = it;
+  }
+#undef NB_QC_EVAL
+  if (converged)
+  {
+    for (int q = g.lane; q < 3 * 4 * n; q += NL)
+    {
+      const int ax = q / (4 * n), r = q - ax * 4 * n;
+      double v = tb->Pm[r][0] * sh->init3[ax][0] + tb->Pm[r][1] * sh->init3[ax][1] + tb->Pm[r][2] * sh->init3[ax][2];
+      for (int c = 0; c < dof; c++) v += tb->Z[r][c] * sh->w[ax * dof + c];
+      x_out[ax * 32 + r] = v;
+    }
+    g.sync();
+    *obj_out = nb_objective(cs, n, mode, x_out, sh->pf);
+  }
+  return converged;
+}

@@ -1,0 +1,44 @@
+"""ctypes binding of tests/emul/_build/libnb_emul.so: the device kernels compiled for ONE host lane.
+CPU-side debugging harness for pytest -m "not gpu"; never used by the neptune_b200 package."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from neptune_b200.batch import ReplanResult
+from neptune_b200.capi import host_args, make_nb_params
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "libnb_emul.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+        _lib = C.CDLL(_LIB)
+    return _lib
+
+
+def replan(batch, with_lines=True) -> ReplanResult:
+    par = batch.par
+    res = ReplanResult.empty(batch, with_lines)
+    a = host_args(batch, res)
+    nbp = make_nb_params(par)
+    pb = np.ascontiguousarray(par.pb, np.float64)
+    rc = lib().emul_replan_batch(C.byref(nbp), pb.ctypes.data_as(C.c_void_p), batch.st_ptr.ctypes.data_as(C.c_void_p),
+                                 batch.st_xy.ctypes.data_as(C.c_void_p), C.byref(a))
+    assert rc == 0, rc
+    return res
+
+
+def separate(A, B, a_polygon):
+    A, B = np.ascontiguousarray(A, np.float64), np.ascontiguousarray(B, np.float64)
+    out = np.zeros(3)
+    ok = lib().emul_separate(A.ctypes.data_as(C.c_void_p), len(A), int(a_polygon), B.ctypes.data_as(C.c_void_p), len(B),
+                             out.ctypes.data_as(C.c_void_p))
+    return bool(ok), out
