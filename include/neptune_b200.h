@@ -77,6 +77,14 @@ void nb_destroy(nb_handle* h);
 const char* nb_last_error(void);
 /* number of kernels this library has launched since nb_create (bench.py's gpu_launches) */
 long long nb_launch_count(const nb_handle* h);
+/* Measurement hooks (no reference counterpart).  With profiling on, every kernel of
+ * nb_replan_batch is bracketed by CUDA events on the launching stream; nb_kernel_times waits for
+ * them and writes the durations of the last call in ms: [0] line generation, [1] QP. */
+int nb_set_profiling(nb_handle* h, int on);
+int nb_kernel_times(nb_handle* h, double* ms, int n);
+/* NB_DEVICE calls are asynchronous: capacity overflows are latched on the device; this call
+ * synchronises `stream` and returns NB_ERR_CAPACITY if any call since the last check overflowed. */
+int nb_check_async_errors(nb_handle* h, void* stream);
 
 /*
  * Replaces PolySolverGurobi::setStaticObstVert (solver_gurobi_poly.cpp:316-320; caller

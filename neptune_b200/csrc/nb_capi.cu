@@ -68,6 +68,8 @@ struct nb_handle
   DevBuf in[16], out[8];
   // scratch
   DevBuf lines, line_ok, cl, lstart, rows, err;
+  int profiling = 0;
+  cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
 };
 
 // ------------------------------------------------------------------------------------------ kernels
@@ -242,6 +244,12 @@ extern "C" int nb_create(const nb_params* par, const double* pb, int device, nb_
   h->st_nvert = 0;
   NB_CUDA(cudaMalloc(&h->d_st_ptr, sizeof(int64_t) * (par->num_static + 1)));
   NB_CUDA(cudaMemset(h->d_st_ptr, 0, sizeof(int64_t) * (par->num_static + 1)));
+  if (h->err.ensure(sizeof(int)))
+  {
+    g_err = "cudaMalloc failed";
+    return NB_ERR_CUDA;
+  }
+  NB_CUDA(cudaMemset(h->err.p, 0, sizeof(int)));
   *out = h;
   return NB_OK;
 }
@@ -257,11 +265,53 @@ extern "C" void nb_destroy(nb_handle* h)
   cudaFree(h->d_strep);
   for (auto& b : h->in) b.release();
   for (auto& b : h->out) b.release();
+  for (auto& e : h->ev)
+    if (e) cudaEventDestroy(e);
   h->lines.release(), h->line_ok.release(), h->cl.release(), h->lstart.release(), h->rows.release(), h->err.release();
   delete h;
 }
 
 extern "C" long long nb_launch_count(const nb_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int nb_set_profiling(nb_handle* h, int on)
+{
+  if (!h) return NB_ERR_ARG;
+  NB_CUDA(cudaSetDevice(h->device));
+  if (on && !h->ev[0])
+    for (auto& e : h->ev) NB_CUDA(cudaEventCreate(&e));
+  h->profiling = on ? 1 : 0;
+  return NB_OK;
+}
+
+extern "C" int nb_kernel_times(nb_handle* h, double* ms, int n)
+{
+  if (!h || !ms || !h->ev[0]) return NB_ERR_ARG;
+  NB_CUDA(cudaEventSynchronize(h->ev[2]));
+  for (int k = 0; k < n && k < 2; k++)
+  {
+    float f = 0.f;
+    NB_CUDA(cudaEventElapsedTime(&f, h->ev[k], h->ev[k + 1]));
+    ms[k] = f;
+  }
+  return NB_OK;
+}
+
+extern "C" int nb_check_async_errors(nb_handle* h, void* stream)
+{
+  if (!h) return NB_ERR_ARG;
+  if (!h->err.p) return NB_OK;
+  NB_CUDA(cudaSetDevice(h->device));
+  int err = 0;
+  NB_CUDA(cudaMemcpyAsync(&err, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  NB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  NB_CUDA(cudaMemsetAsync(h->err.p, 0, sizeof(int), (cudaStream_t)stream));
+  if (err)
+  {
+    g_err = "a fixed-capacity list overflowed in an asynchronous call (ent_slots)";
+    return NB_ERR_CAPACITY;
+  }
+  return NB_OK;
+}
 
 extern "C" int nb_line_slots(const nb_handle* h, int n_hull_slots)
 {
@@ -370,7 +420,7 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
     g_err = "cudaMalloc failed for scratch buffers";
     return NB_ERR_CUDA;
   }
-  NB_CUDA(cudaMemsetAsync(h->err.p, 0, sizeof(int), st));
+  if (sp == NB_HOST) NB_CUDA(cudaMemsetAsync(h->err.p, 0, sizeof(int), st));
   NbQpArgs q;
   q.n_int = in.n_int;
   q.coeff_init = in.coeff_init;
@@ -386,8 +436,11 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   if ((rc = stage_out(h, 2, sp, a->status, (size_t)B, &q.status))) return rc;
   if ((rc = stage_out(h, 3, sp, a->iters, (size_t)B * 2, &q.iters))) return rc;
 
+  if (h->profiling) cudaEventRecord(h->ev[0], st);
   k_lines<<<B * NB_NPOL, 128, 0, st>>>(h->cs, in, LS, (double*)h->lines.p, (uint8_t*)h->line_ok.p, (int*)h->err.p);
+  if (h->profiling) cudaEventRecord(h->ev[1], st);
   k_qp<<<B, 32, 0, st>>>(h->cs, h->d_tables, q);
+  if (h->profiling) cudaEventRecord(h->ev[2], st);
   h->launches += 2;
   NB_CUDA(cudaGetLastError());
 
