@@ -150,6 +150,48 @@ int nb_separate_batch(nb_handle* h, int32_t L, int32_t space, const int64_t* a_p
 int nb_generate_traj_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
                            double dc, int32_t max_states, double* states, int32_t* n_states, void* stream);
 
+/*
+ * Entanglement-signature chain, batched (one agent per warp).  State = eu::ent_state
+ * (neptune/include/entangle_utils.hpp:23-29) with fixed storage: cnt [B][2] = (alphas.size(),
+ * bendPointsIdx.size()), alpha [B][ent_cap][2], beta [B][ent_cap], bend [B][ent_cap], active [B][N+M].
+ * known: [B][N] 1 where SampledPointsForAll[j] is non-empty.  samp: sampled positions of the other
+ * agents, [B][N][8][S+1][2] or, when samp_shared != 0, [N][8][S+1][2] shared by the batch.
+ * Static representation and base points come from nb_set_static / nb_create.
+ */
+typedef struct nb_ent_state
+{
+  int32_t* cnt;
+  int32_t* alpha;
+  double* beta;
+  int32_t* bend;
+  int32_t* active;
+} nb_ent_state;
+
+/* Replaces Neptune::PredictAlphasBetas (neptune.cpp:976-1008) and its eu:: callees
+ * (entangle_utils.cpp:1129-1228, :1231-1277, :1402-1534, :1536-1604): state is updated in place.
+ * prev_pos [B][N+1][2] previousCheckingPos_, prev_pos_agent [B][N][2], cur [B][2] (start point A),
+ * samp0 [B][N][2] = SampledPointsForAll[j][0].col(0). */
+int nb_entangle_predict_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const uint8_t* known,
+                              const int32_t* bp_cnt, const double* bp_xy, nb_ent_state st, const double* prev_pos,
+                              const double* prev_pos_agent, const double* cur, const double* samp0, void* stream);
+
+/* Replaces the per-interval chain of KinodynamicSearch::entanglesWithOtherAgents
+ * (kinodynamic_search.cpp:707-895; list bound N+M, tether-length test excluded) that produces
+ * entStateVec (recoverEntStateVector :582-603).  in: state at A.  out: states after 0..n intervals,
+ * [B][9][...] (entries past n_int are copies of the last), done [B] = intervals before the first
+ * entangling step (n if none). */
+int nb_entangle_rollout_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const uint8_t* known,
+                              const int32_t* bp_cnt, const double* bp_xy, nb_ent_state in, const int32_t* n_int,
+                              const double* coeff, const double* samp, int32_t samp_shared, nb_ent_state out,
+                              int32_t* done, void* stream);
+
+/* Replaces KinodynamicSearch::entangleCheckGivenPwp (kinodynamic_search.cpp:897-985), including its
+ * quirk of evaluating interval 0 only.  state updated in place; entangled [B] = its return value. */
+int nb_entangle_check_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const uint8_t* known,
+                            const int32_t* bp_cnt, const double* bp_xy, nb_ent_state st, const int32_t* n_int,
+                            const double* coeff, const double* samp, int32_t samp_shared, int32_t* entangled,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,40 @@ def host_args(batch: ReplanBatch, res: ReplanResult) -> NbReplanArgs:
     return a
 
 
+class NbEntState(C.Structure):
+    _fields_ = [("cnt", _P), ("alpha", _P), ("beta", _P), ("bend", _P), ("active", _P)]
+
+
+class EntArrays:
+    """eu::ent_state for a batch: fixed-capacity numpy storage ([S] states)."""
+
+    def __init__(self, par: Params, shape):
+        shape = tuple(np.atleast_1d(shape))
+        self.cnt = np.zeros(shape + (2,), np.int32)
+        self.alpha = np.zeros(shape + (par.ent_cap, 2), np.int32)
+        self.beta = np.zeros(shape + (par.ent_cap,), np.float64)
+        self.bend = np.zeros(shape + (par.ent_cap,), np.int32)
+        self.active = np.zeros(shape + (par.NA,), np.int32)
+
+    @staticmethod
+    def of(par, cnt, alpha, beta, bend, active):
+        e = EntArrays.__new__(EntArrays)
+        e.cnt, e.alpha, e.beta = np.ascontiguousarray(cnt, np.int32), np.ascontiguousarray(alpha, np.int32), np.ascontiguousarray(beta, np.float64)
+        e.bend, e.active = np.ascontiguousarray(bend, np.int32), np.ascontiguousarray(active, np.int32)
+        return e
+
+    def copy(self):
+        return EntArrays.of(None, self.cnt.copy(), self.alpha.copy(), self.beta.copy(), self.bend.copy(), self.active.copy())
+
+    def c(self) -> NbEntState:
+        s = NbEntState()
+        s.cnt, s.alpha, s.beta, s.bend, s.active = _np(self.cnt), _np(self.alpha), _np(self.beta), _np(self.bend), _np(self.active)
+        return s
+
+    def tuple(self):
+        return self.cnt, self.alpha, self.beta, self.bend, self.active
+
+
 _lib = None
 
 
@@ -171,3 +205,72 @@ class Solver:
         _check(f(self._h, B, NB_HOST, _np(n_int), _np(coeff), dc, mx, _np(states), _np(ns), None),
                "nb_generate_traj_batch")
         return states, ns
+
+    # ---- entanglement-signature chain (K3)
+    def entangle_predict(self, agent_id, known, bp_cnt, bp_xy, state: EntArrays, prev_pos, prev_pos_agent, cur, samp0):
+        """``Neptune::PredictAlphasBetas``: returns entangle_state_A for every agent (input untouched)."""
+        st = state.copy()
+        arrs = [np.ascontiguousarray(agent_id, np.int32), np.ascontiguousarray(known, np.uint8),
+                np.ascontiguousarray(bp_cnt, np.int32), np.ascontiguousarray(bp_xy, np.float64),
+                np.ascontiguousarray(prev_pos, np.float64), np.ascontiguousarray(prev_pos_agent, np.float64),
+                np.ascontiguousarray(cur, np.float64), np.ascontiguousarray(samp0, np.float64)]
+        f = lib().nb_entangle_predict_batch
+        f.argtypes = [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, NbEntState, _P, _P, _P, _P, _P]
+        _check(f(self._h, len(arrs[0]), NB_HOST, _np(arrs[0]), _np(arrs[1]), _np(arrs[2]), _np(arrs[3]), st.c(),
+                 _np(arrs[4]), _np(arrs[5]), _np(arrs[6]), _np(arrs[7]), None), "nb_entangle_predict_batch")
+        return st
+
+    def entangle_rollout(self, agent_id, known, bp_cnt, bp_xy, state: EntArrays, n_int, coeff, samp, samp_shared=False):
+        """Front-end chain along a path: (done [B], states after 0..n intervals as EntArrays [B][9])."""
+        B = len(agent_id)
+        out = EntArrays(self.par, (B, NPOL + 1))
+        done = np.zeros(B, np.int32)
+        arrs = [np.ascontiguousarray(agent_id, np.int32), np.ascontiguousarray(known, np.uint8),
+                np.ascontiguousarray(bp_cnt, np.int32), np.ascontiguousarray(bp_xy, np.float64),
+                np.ascontiguousarray(n_int, np.int32), np.ascontiguousarray(coeff, np.float64),
+                np.ascontiguousarray(samp, np.float64)]
+        f = lib().nb_entangle_rollout_batch
+        f.argtypes = [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, NbEntState, _P, _P, _P, C.c_int32, NbEntState, _P, _P]
+        _check(f(self._h, B, NB_HOST, _np(arrs[0]), _np(arrs[1]), _np(arrs[2]), _np(arrs[3]), state.c(), _np(arrs[4]),
+                 _np(arrs[5]), _np(arrs[6]), int(samp_shared), out.c(), _np(done), None), "nb_entangle_rollout_batch")
+        return done, out
+
+    def entangle_check(self, agent_id, known, bp_cnt, bp_xy, state: EntArrays, n_int, coeff, samp, samp_shared=False):
+        """``entangleCheckGivenPwp``: (entangled [B], updated state)."""
+        B = len(agent_id)
+        st = state.copy()
+        ent = np.zeros(B, np.int32)
+        arrs = [np.ascontiguousarray(agent_id, np.int32), np.ascontiguousarray(known, np.uint8),
+                np.ascontiguousarray(bp_cnt, np.int32), np.ascontiguousarray(bp_xy, np.float64),
+                np.ascontiguousarray(n_int, np.int32), np.ascontiguousarray(coeff, np.float64),
+                np.ascontiguousarray(samp, np.float64)]
+        f = lib().nb_entangle_check_batch
+        f.argtypes = [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, NbEntState, _P, _P, _P, C.c_int32, _P, _P]
+        _check(f(self._h, B, NB_HOST, _np(arrs[0]), _np(arrs[1]), _np(arrs[2]), _np(arrs[3]), st.c(), _np(arrs[4]),
+                 _np(arrs[5]), _np(arrs[6]), int(samp_shared), _np(ent), None), "nb_entangle_check_batch")
+        return ent, st
+
+
+class DeviceEntBackend:
+    """Entanglement back end for ``neptune_b200.scenes.fill_entangle`` running on the product's K3
+    kernels (used by bench.py so that the workload generator never touches the oracle)."""
+
+    def __init__(self, solver: Solver):
+        self.s = solver
+
+    def predict_batch(self, par, agent_id, prev_pos, prev_pos_agent, cur, samp0, known, strep, bp_cnt, bp_xy,
+                      cnt, alpha, beta, bend, active):
+        st = self.s.entangle_predict(agent_id, known, bp_cnt, bp_xy, EntArrays.of(par, cnt, alpha, beta, bend, active),
+                                     prev_pos, prev_pos_agent, cur, samp0)
+        return st.tuple()
+
+    def rollout_batch(self, par, agent_id, n_int, coeff, samp, known, strep, bp_cnt, bp_xy, cnt, alpha, beta, bend,
+                      active):
+        done, out = self.s.entangle_rollout(agent_id, known, bp_cnt, bp_xy,
+                                            EntArrays.of(par, cnt, alpha, beta, bend, active), n_int, coeff, samp)
+        return (done,) + out.tuple()
+
+    def check_batch(self, par, agent_id, n_int, coeff, samp, known, strep, bp_cnt, bp_xy, cnt, alpha, beta, bend, active):
+        ent, st = self.s.entangle_check(agent_id, known, bp_cnt, bp_xy,
+                                        EntArrays.of(par, cnt, alpha, beta, bend, active), n_int, coeff, samp)
+        return (ent,) + st.tuple()

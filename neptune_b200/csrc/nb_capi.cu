@@ -10,6 +10,7 @@
 
 #include "../../include/neptune_b200.h"
 #include "nb_common.cuh"
+#include "nb_entangle.cuh"
 #include "nb_lines.cuh"
 #include "nb_qp.cuh"
 #include "nb_sep.cuh"
@@ -67,17 +68,33 @@ struct nb_handle
   // staging of NB_HOST arguments
   DevBuf in[16], out[8];
   // scratch
-  DevBuf lines, line_ok, cl, lstart, rows, err;
+  DevBuf lines, line_ok, keep, cl, rows, err;
+  int qp_smem_set = 0;
   int profiling = 0;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
 };
 
 // ------------------------------------------------------------------------------------------ kernels
 
-__global__ void __launch_bounds__(128) k_lines(NbConsts cs, NbLinesIn in, int LS, double* lines, uint8_t* ok, int* err)
+__global__ void __launch_bounds__(128) k_lines(NbConsts cs, NbLinesIn in, int LS, double* lines, uint8_t* ok,
+                                               uint8_t* keep, int* err)
 {
+  extern __shared__ double smem_d[];
+  NbPruneShared ps;
+  ps.px = smem_d;
+  ps.py = ps.px + (LS + 1);
+  ps.red = (int*)(ps.py + (LS + 1));
+  ps.hull = ps.red + 128;
+  ps.misc = ps.hull + (NB_PRUNE_KMAX + 1);
+  ps.valid = (uint8_t*)(ps.misc + 8);
   const int b = blockIdx.x / NB_NPOL, i = blockIdx.x % NB_NPOL;
-  nb_lines_task<128>(threadIdx.x, b, i, cs, in, lines + (size_t)blockIdx.x * LS * 3, ok + (size_t)blockIdx.x * LS, err);
+  nb_lines_task<128>(threadIdx.x, b, i, cs, in, lines + (size_t)blockIdx.x * LS * 3, ok + (size_t)blockIdx.x * LS,
+                     keep + (size_t)blockIdx.x * LS, ps, err);
+}
+
+static size_t lines_smem_bytes(int LS)
+{
+  return (size_t)(LS + 1) * 16 + (128 + NB_PRUNE_KMAX + 1 + 8) * sizeof(int) + (size_t)(LS + 1) + 16;
 }
 
 struct NbQpArgs
@@ -85,11 +102,10 @@ struct NbQpArgs
   const int* n_int;
   const double* coeff_init;
   const double* lines;  // [B][8][LS][3]
-  const uint8_t* ok;    // [B][8][LS]
+  const uint8_t* keep;  // [B][8][LS]
   int LS;
-  double* cl;           // [B][8*LS][3]
-  int* lstart;          // [B][9]
-  double* rows;         // [B][4][RS]
+  double* cl;           // [B][8*LS][3]   (only used when an agent keeps more than NB_QP_SMEM_LINES lines)
+  double* rows;         // [B][4][RS]     (same)
   int RS;
   double* coeff_out;
   double* obj;
@@ -97,35 +113,54 @@ struct NbQpArgs
   int* iters;
 };
 
+#define NB_QP_SMEM_LINES 160
+#define NB_QP_SMEM_ROWS (6 * NB_NFEAT_AX + 4 * NB_QP_SMEM_LINES)
+
+struct NbQpSmem
+{
+  NbQpShared sh;
+  NbQpTable tb;
+  double rows[4 * NB_QP_SMEM_ROWS];
+  double cl[3 * NB_QP_SMEM_LINES];
+  double xout[96];
+  int lstart[12];
+};
+
 __global__ void __launch_bounds__(32) k_qp(NbConsts cs, const NbQpTable* tables, NbQpArgs a)
 {
-  __shared__ NbQpShared sh;
-  __shared__ double xout[96];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NbQpSmem* sm = reinterpret_cast<NbQpSmem*>(smem_raw);
   const int b = blockIdx.x;
   Group<32> g(threadIdx.x);
   const int n = a.n_int[b];
   const double* ci = a.coeff_init + (size_t)b * 96;
-  double* cl = a.cl + (size_t)b * NB_NPOL * a.LS * 3;
-  int* lstart = a.lstart + (size_t)b * 9;
-  const int nl = nb_compact_lines<32>(g, n, a.LS, a.lines + (size_t)b * NB_NPOL * a.LS * 3,
-                                      a.ok + (size_t)b * NB_NPOL * a.LS, cl, lstart);
+  const uint8_t* keep = a.keep + (size_t)b * NB_NPOL * a.LS;
+  const int nkeep = nb_count_lines<32>(g, n, a.LS, keep);
+  const bool in_smem = nkeep <= NB_QP_SMEM_LINES;
+  double* cl = in_smem ? sm->cl : a.cl + (size_t)b * NB_NPOL * a.LS * 3;
+  const int nl = nb_compact_lines<32>(g, n, a.LS, a.lines + (size_t)b * NB_NPOL * a.LS * 3, keep, cl, sm->lstart);
   NbQpRows R;
-  double* rb = a.rows + (size_t)b * 4 * a.RS;
+  const size_t rs = in_smem ? NB_QP_SMEM_ROWS : a.RS;
+  double* rb = in_smem ? sm->rows : a.rows + (size_t)b * 4 * a.RS;
   R.s = rb;
-  R.lam = rb + a.RS;
-  R.dsa = rb + 2 * (size_t)a.RS;
-  R.dla = rb + 3 * (size_t)a.RS;
+  R.lam = rb + rs;
+  R.dsa = rb + 2 * rs;
+  R.dla = rb + 3 * rs;
   R.cl = cl;
-  R.lstart = lstart;
+  R.lstart = sm->lstart;
   int status = NB_STATUS_FAILED, it0 = 0, it1 = 0;
   double obj = 0.0;
-  bool ok = nb_qp_solve<32>(g, cs, tables + (n - 1), &sh, R, ci, nl, xout, &it0, &obj);
-  if (ok)
-    status = NB_STATUS_OK;
-  else
+  bool ok = false;
+  for (int mode = 0; mode < 2 && !ok; mode++)
   {
-    ok = nb_qp_solve<32>(g, cs, tables + NB_NPOL + (n - 1), &sh, R, ci, nl, xout, &it1, &obj);
-    if (ok) status = NB_STATUS_FALLBACK;
+    // stage the (n, mode) table in shared memory
+    const double* src = reinterpret_cast<const double*>(tables + mode * NB_NPOL + (n - 1));
+    double* dst = reinterpret_cast<double*>(&sm->tb);
+    g.sync();
+    for (int q = threadIdx.x; q < (int)(sizeof(NbQpTable) / sizeof(double)); q += 32) dst[q] = src[q];
+    g.sync();
+    ok = nb_qp_solve<32>(g, cs, &sm->tb, &sm->sh, R, ci, nl, sm->xout, mode == 0 ? &it0 : &it1, &obj);
+    if (ok) status = mode == 0 ? NB_STATUS_OK : NB_STATUS_FALLBACK;
   }
   g.sync();
   // copy the solution (:866-876) or keep the initial path (:858); z override (:879-880)
@@ -146,7 +181,7 @@ __global__ void __launch_bounds__(32) k_qp(NbConsts cs, const NbQpTable* tables,
   {
     const int ax = q / 32, r = q % 32;
     double v = ci[q];
-    if (ok && r < 4 * n && !(ax == 2 && keep_z)) v = xout[q];
+    if (ok && r < 4 * n && !(ax == 2 && keep_z)) v = sm->xout[q];
     co[q] = v;
   }
   if (threadIdx.x == 0)
@@ -199,6 +234,13 @@ __global__ void k_traj(int B, const int* n_int, const double* coeff, double T, d
     if (t > (i + 1) * T) i++;
   }
   n_states[b] = cnt;
+}
+
+__global__ void __launch_bounds__(32) k_entangle(NbEntArgs a)
+{
+  extern __shared__ int smem_i[];
+  Group<32> g(threadIdx.x);
+  nb_entangle_task<32>(g, blockIdx.x, a, smem_i, smem_i + 2 * a.tcap);
 }
 
 // ------------------------------------------------------------------------------------------ ABI
@@ -267,7 +309,7 @@ extern "C" void nb_destroy(nb_handle* h)
   for (auto& b : h->out) b.release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
-  h->lines.release(), h->line_ok.release(), h->cl.release(), h->lstart.release(), h->rows.release(), h->err.release();
+  h->lines.release(), h->line_ok.release(), h->keep.release(), h->cl.release(), h->rows.release(), h->err.release();
   delete h;
 }
 
@@ -414,7 +456,7 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   const size_t nslots = (size_t)B * NB_NPOL * LS;
   const int RS = 6 * NB_NFEAT_AX + 4 * NB_NPOL * LS;
   if (h->lines.ensure(nslots * 3 * sizeof(double)) || h->line_ok.ensure(nslots) ||
-      h->cl.ensure(nslots * 3 * sizeof(double)) || h->lstart.ensure((size_t)B * 9 * sizeof(int)) ||
+      h->cl.ensure(nslots * 3 * sizeof(double)) || h->keep.ensure(nslots) ||
       h->rows.ensure((size_t)B * 4 * RS * sizeof(double)) || h->err.ensure(sizeof(int)))
   {
     g_err = "cudaMalloc failed for scratch buffers";
@@ -425,10 +467,9 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   q.n_int = in.n_int;
   q.coeff_init = in.coeff_init;
   q.lines = (const double*)h->lines.p;
-  q.ok = (const uint8_t*)h->line_ok.p;
+  q.keep = (const uint8_t*)h->keep.p;
   q.LS = LS;
   q.cl = (double*)h->cl.p;
-  q.lstart = (int*)h->lstart.p;
   q.rows = (double*)h->rows.p;
   q.RS = RS;
   if ((rc = stage_out(h, 0, sp, a->coeff_out, (size_t)B * 96, &q.coeff_out))) return rc;
@@ -437,9 +478,22 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   if ((rc = stage_out(h, 3, sp, a->iters, (size_t)B * 2, &q.iters))) return rc;
 
   if (h->profiling) cudaEventRecord(h->ev[0], st);
-  k_lines<<<B * NB_NPOL, 128, 0, st>>>(h->cs, in, LS, (double*)h->lines.p, (uint8_t*)h->line_ok.p, (int*)h->err.p);
+  const size_t lsm = lines_smem_bytes(LS);
+  if (!h->qp_smem_set)
+  {
+    NB_CUDA(cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NbQpSmem)));
+    NB_CUDA(cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    h->qp_smem_set = 1;
+  }
+  if (lsm > 200 * 1024)
+  {
+    g_err = "nb_replan_batch: too many line slots per interval for the pruning stage";
+    return NB_ERR_CAPACITY;
+  }
+  k_lines<<<B * NB_NPOL, 128, lsm, st>>>(h->cs, in, LS, (double*)h->lines.p, (uint8_t*)h->line_ok.p,
+                                         (uint8_t*)h->keep.p, (int*)h->err.p);
   if (h->profiling) cudaEventRecord(h->ev[1], st);
-  k_qp<<<B, 32, 0, st>>>(h->cs, h->d_tables, q);
+  k_qp<<<B, 32, sizeof(NbQpSmem), st>>>(h->cs, h->d_tables, q);
   if (h->profiling) cudaEventRecord(h->ev[2], st);
   h->launches += 2;
   NB_CUDA(cudaGetLastError());
@@ -534,4 +588,208 @@ extern "C" int nb_generate_traj_batch(nb_handle* h, int32_t B, int32_t space, co
     NB_CUDA(cudaStreamSynchronize(st));
   }
   return NB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ K3 ABI
+namespace
+{
+struct EntStage
+{
+  nb_ent_state dev;
+};
+
+int stage_state_in(nb_handle* h, int slot0, int space, const nb_ent_state& u, size_t nstates, cudaStream_t st,
+                   nb_ent_state* d, bool copy)
+{
+  const int cap = h->par.ent_cap, NA = h->par.num_agents + h->par.num_static;
+  if (space == NB_DEVICE)
+  {
+    *d = u;
+    return NB_OK;
+  }
+  const size_t sz[5] = { nstates * 2 * sizeof(int), nstates * cap * 2 * sizeof(int), nstates * cap * sizeof(double),
+                         nstates * cap * sizeof(int), nstates * NA * sizeof(int) };
+  void* up[5] = { u.cnt, u.alpha, u.beta, u.bend, u.active };
+  void* dp[5];
+  for (int k = 0; k < 5; k++)
+  {
+    if (h->in[slot0 + k].ensure(sz[k]))
+    {
+      g_err = "cudaMalloc failed while staging entanglement state";
+      return NB_ERR_CUDA;
+    }
+    dp[k] = h->in[slot0 + k].p;
+    if (copy) NB_CUDA(cudaMemcpyAsync(dp[k], up[k], sz[k], cudaMemcpyHostToDevice, st));
+  }
+  d->cnt = (int32_t*)dp[0], d->alpha = (int32_t*)dp[1], d->beta = (double*)dp[2], d->bend = (int32_t*)dp[3];
+  d->active = (int32_t*)dp[4];
+  return NB_OK;
+}
+
+int state_out(nb_handle* h, int space, const nb_ent_state& u, const nb_ent_state& d, size_t nstates, cudaStream_t st)
+{
+  if (space == NB_DEVICE) return NB_OK;
+  const int cap = h->par.ent_cap, NA = h->par.num_agents + h->par.num_static;
+  NB_CUDA(cudaMemcpyAsync(u.cnt, d.cnt, nstates * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  NB_CUDA(cudaMemcpyAsync(u.alpha, d.alpha, nstates * cap * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  NB_CUDA(cudaMemcpyAsync(u.beta, d.beta, nstates * cap * sizeof(double), cudaMemcpyDeviceToHost, st));
+  NB_CUDA(cudaMemcpyAsync(u.bend, d.bend, nstates * cap * sizeof(int), cudaMemcpyDeviceToHost, st));
+  NB_CUDA(cudaMemcpyAsync(u.active, d.active, nstates * NA * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return NB_OK;
+}
+
+int ent_common(nb_handle* h, NbEntArgs* a, int mode, int B, int space, const int32_t* agent_id, const uint8_t* known,
+               const int32_t* bp_cnt, const double* bp_xy, cudaStream_t st)
+{
+  const int N = h->par.num_agents, M = h->par.num_static;
+  memset(a, 0, sizeof(*a));
+  a->mode = mode, a->N = N, a->M = M, a->cap = h->par.ent_cap, a->bp_max = h->par.bp_max;
+  a->num_pol = h->par.num_pol, a->S = h->par.samples, a->T = h->par.T_span;
+  int tcap = 4 * (N + M) + 16;
+  a->tcap = tcap > 1024 ? 1024 : tcap;
+  a->pb = h->d_pb;
+  a->strep = h->d_strep;
+  if (M > 0 && !h->d_strep)
+  {
+    g_err = "entanglement call with static obstacles but nb_set_static(strep) was never called";
+    return NB_ERR_ARG;
+  }
+  int rc;
+  if ((rc = stage_in(h, 0, space, agent_id, (size_t)B, st, &a->agent_id))) return rc;
+  if ((rc = stage_in(h, 1, space, known, (size_t)B * N, st, &a->known))) return rc;
+  if ((rc = stage_in(h, 2, space, bp_cnt, (size_t)N, st, &a->bp_cnt))) return rc;
+  if ((rc = stage_in(h, 3, space, bp_xy, (size_t)N * h->par.bp_max * 2, st, &a->bp_xy))) return rc;
+  if (h->keep.ensure((size_t)B * (N + M) * sizeof(int)))  // reuse as act_old scratch when larger
+  {
+    g_err = "cudaMalloc failed";
+    return NB_ERR_CUDA;
+  }
+  a->act_old = (int*)h->keep.p;
+  a->err = (int*)h->err.p;
+  return NB_OK;
+}
+
+int ent_launch(nb_handle* h, const NbEntArgs& a, int B, cudaStream_t st)
+{
+  const size_t sm = (size_t)(2 * a.tcap + 4) * sizeof(int);
+  k_entangle<<<B, 32, sm, st>>>(a);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+int ent_finish(nb_handle* h, int space, cudaStream_t st)
+{
+  if (space != NB_HOST) return NB_OK;
+  int err = 0;
+  NB_CUDA(cudaMemcpyAsync(&err, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  NB_CUDA(cudaStreamSynchronize(st));
+  if (err)
+  {
+    NB_CUDA(cudaMemsetAsync(h->err.p, 0, sizeof(int), st));
+    g_err = "entanglement chain: fixed-capacity list overflow (ent_cap / crossing buffer)";
+    return NB_ERR_CAPACITY;
+  }
+  return NB_OK;
+}
+}  // namespace
+
+extern "C" int nb_entangle_predict_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id,
+                                         const uint8_t* known, const int32_t* bp_cnt, const double* bp_xy,
+                                         nb_ent_state stt, const double* prev_pos, const double* prev_pos_agent,
+                                         const double* cur, const double* samp0, void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->par.num_agents;
+  NbEntArgs a;
+  int rc;
+  if ((rc = ent_common(h, &a, 0, B, space, agent_id, known, bp_cnt, bp_xy, st))) return rc;
+  nb_ent_state d;
+  if ((rc = stage_state_in(h, 4, space, stt, (size_t)B, st, &d, true))) return rc;
+  a.st = d;
+  if ((rc = stage_in(h, 9, space, prev_pos, (size_t)B * (N + 1) * 2, st, &a.prev_pos))) return rc;
+  if ((rc = stage_in(h, 10, space, prev_pos_agent, (size_t)B * N * 2, st, &a.prev_pos_agent))) return rc;
+  if ((rc = stage_in(h, 11, space, cur, (size_t)B * 2, st, &a.cur))) return rc;
+  if ((rc = stage_in(h, 12, space, samp0, (size_t)B * N * 2, st, &a.samp0))) return rc;
+  if ((rc = ent_launch(h, a, B, st))) return rc;
+  if ((rc = state_out(h, space, stt, d, (size_t)B, st))) return rc;
+  return ent_finish(h, space, st);
+}
+
+extern "C" int nb_entangle_rollout_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id,
+                                         const uint8_t* known, const int32_t* bp_cnt, const double* bp_xy,
+                                         nb_ent_state in, const int32_t* n_int, const double* coeff, const double* samp,
+                                         int32_t samp_shared, nb_ent_state out, int32_t* done, void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->par.num_agents, S = h->par.samples;
+  NbEntArgs a;
+  int rc;
+  if ((rc = ent_common(h, &a, 1, B, space, agent_id, known, bp_cnt, bp_xy, st))) return rc;
+  nb_ent_state din, dout;
+  if ((rc = stage_state_in(h, 4, space, in, (size_t)B, st, &din, true))) return rc;
+  a.st = din;
+  if ((rc = stage_in(h, 9, space, n_int, (size_t)B, st, &a.n_int))) return rc;
+  if ((rc = stage_in(h, 10, space, coeff, (size_t)B * 96, st, &a.coeff))) return rc;
+  if ((rc = stage_in(h, 11, space, samp, (size_t)(samp_shared ? 1 : B) * N * h->par.num_pol * (S + 1) * 2, st, &a.samp)))
+    return rc;
+  a.samp_shared = samp_shared;
+  // outputs: staged in out[] slots 2..6 + 7
+  const int cap = h->par.ent_cap, NA = N + h->par.num_static;
+  if (space == NB_HOST)
+  {
+    const size_t ns = (size_t)B * 9;
+    const size_t sz[5] = { ns * 2 * sizeof(int), ns * cap * 2 * sizeof(int), ns * cap * sizeof(double),
+                           ns * cap * sizeof(int), ns * NA * sizeof(int) };
+    for (int k = 0; k < 5; k++)
+      if (h->out[2 + k].ensure(sz[k]))
+      {
+        g_err = "cudaMalloc failed";
+        return NB_ERR_CUDA;
+      }
+    dout.cnt = (int32_t*)h->out[2].p, dout.alpha = (int32_t*)h->out[3].p, dout.beta = (double*)h->out[4].p;
+    dout.bend = (int32_t*)h->out[5].p, dout.active = (int32_t*)h->out[6].p;
+  }
+  else
+    dout = out;
+  a.out = dout;
+  if ((rc = stage_out(h, 7, space, done, (size_t)B, &a.result))) return rc;
+  if ((rc = ent_launch(h, a, B, st))) return rc;
+  if ((rc = state_out(h, space, out, dout, (size_t)B * 9, st))) return rc;
+  if (space == NB_HOST) NB_CUDA(cudaMemcpyAsync(done, a.result, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return ent_finish(h, space, st);
+}
+
+extern "C" int nb_entangle_check_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id,
+                                       const uint8_t* known, const int32_t* bp_cnt, const double* bp_xy, nb_ent_state stt,
+                                       const int32_t* n_int, const double* coeff, const double* samp, int32_t samp_shared,
+                                       int32_t* entangled, void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->par.num_agents, S = h->par.samples;
+  NbEntArgs a;
+  int rc;
+  if ((rc = ent_common(h, &a, 2, B, space, agent_id, known, bp_cnt, bp_xy, st))) return rc;
+  nb_ent_state d;
+  if ((rc = stage_state_in(h, 4, space, stt, (size_t)B, st, &d, true))) return rc;
+  a.st = d;
+  if ((rc = stage_in(h, 9, space, n_int, (size_t)B, st, &a.n_int))) return rc;
+  if ((rc = stage_in(h, 10, space, coeff, (size_t)B * 96, st, &a.coeff))) return rc;
+  if ((rc = stage_in(h, 11, space, samp, (size_t)(samp_shared ? 1 : B) * N * h->par.num_pol * (S + 1) * 2, st, &a.samp)))
+    return rc;
+  a.samp_shared = samp_shared;
+  if ((rc = stage_out(h, 7, space, entangled, (size_t)B, &a.result))) return rc;
+  if ((rc = ent_launch(h, a, B, st))) return rc;
+  if ((rc = state_out(h, space, stt, d, (size_t)B, st))) return rc;
+  if (space == NB_HOST) NB_CUDA(cudaMemcpyAsync(entangled, a.result, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return ent_finish(h, space, st);
 }

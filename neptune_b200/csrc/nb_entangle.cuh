@@ -1,0 +1,607 @@
+// nb_entangle.cuh -- K3: tether entanglement-signature chain, one agent per warp-group.
+//
+// Replaces (reference neptune/src/entangle_utils.cpp) eu::vectorWedge2 :16-27,
+// eu::entangleHSigToAddAgentInd (8-arg) :1129-1228, eu::entangleHSigToAddStatic :1231-1277,
+// eu::addAlphaBetaToList :1402-1534, eu::updateBendPts :1536-1604, eu::breakcondition :1608-1647,
+// eu::getBendPt2d :1649-1679, eu::calculateBetaForCase :1709-1722, and their drivers
+// Neptune::PredictAlphasBetas (neptune.cpp:976-1008), KinodynamicSearch::entangleCheckGivenPwp
+// (kinodynamic_search.cpp:897-985) and the per-interval chain of entanglesWithOtherAgents (:707-895).
+//
+// The crossing tests against the N other tethers and M static obstacles are independent: lanes take
+// one tether each, keep their (id, case) entries locally and a warp prefix sum places them in the
+// shared list in agent order, exactly the order the reference's sequential loop produces.  The
+// variable-length signature word is then reduced by lane 0 (it is a short, inherently sequential
+// integer automaton).  All outputs are integers decided by IEEE comparisons of FP64 wedges.
+#pragma once
+#include "../../include/neptune_b200.h"
+#include "nb_common.cuh"
+
+#define NB_ENT_LOCAL 24  // entries one tether can add in one step: bp_max + 2 <= 24 pairs... (ints = 2x)
+
+struct NbEntState
+{
+  int n_alpha, n_bend;
+  int* alpha;    // [cap][2]
+  double* beta;  // [cap]
+  int* bend;     // [cap]
+  int* active;   // [N+M]
+};
+
+struct NbEntCtx
+{
+  int N, M, self, cap, bp_max;
+  const double* pb;     // [N][2]
+  const double* strep;  // [M][2][2]
+  const int* bp_cnt;    // [N]
+  const double* bp_xy;  // [N][bp_max][2]
+};
+
+// eu::vectorWedge2 (:16-27): (b-a) x (c-a); ab, ac returned when asked for
+NB_HD double nb_wedge(const double* a, const double* b, const double* c, double* ab, double* ac)
+{
+  const double abx = b[0] - a[0], aby = b[1] - a[1], acx = c[0] - a[0], acy = c[1] - a[1];
+  if (ab)
+  {
+    ab[0] = abx, ab[1] = aby, ac[0] = acx, ac[1] = acy;
+  }
+#if defined(__CUDA_ARCH__)
+  return __dsub_rn(__dmul_rn(abx, acy), __dmul_rn(acx, aby));  // no FMA contraction: sign must match the CPU
+#else
+  return abx * acy - acx * aby;
+#endif
+}
+
+// classification ratio on the dominant coordinate (:1164-1172, :1194-1202)
+NB_HD double nb_cross_ratio(const double* ab, const double* ac)
+{
+#if defined(__CUDA_ARCH__)
+  if (fabs(__dmul_rn(ab[1], ac[1])) > fabs(__dmul_rn(ab[0], ac[0]))) return __ddiv_rn(ab[1], ac[1]);
+  return __ddiv_rn(ab[0], ac[0]);
+#else
+  if (fabs(ab[1] * ac[1]) > fabs(ab[0] * ac[0])) return ab[1] / ac[1];
+  return ab[0] / ac[0];
+#endif
+}
+
+NB_HD bool nb_neg_product(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b) < 0;
+#else
+  return a * b < 0;
+#endif
+}
+
+// eu::entangleHSigToAddAgentInd, 8-arg (:1129-1228): entries of ONE tether into loc; returns count
+NB_HD int nb_hsig_agent(int* loc, const double* pk, const double* pk1, const double* pik, const double* pik1,
+                        const double* pb_self, const double* bend, int nbend, int agent_id)
+{
+  int nadd = 0;
+  bool base_add = false;
+  for (int i = 0; i < nbend; i++)
+  {
+    double ab[2], ac[2], c1, c2;
+    const double* bi = bend + 2 * i;
+    const bool last = (i == nbend - 1);
+    if (!last)
+    {
+      c1 = nb_wedge(pk, bend + 2 * (i + 1), bi, ab, ac);
+      c2 = nb_wedge(pk1, bend + 2 * (i + 1), bi, nullptr, nullptr);
+    }
+    else
+    {
+      c1 = nb_wedge(pk, pik, bi, ab, ac);
+      c2 = nb_wedge(pk1, pik1, bi, nullptr, nullptr);
+    }
+    if (last)
+    {
+      double fb[2], fc[2];
+      const double f1 = nb_wedge(pb_self, pik, bi, fb, fc);
+      const double f2 = nb_wedge(pb_self, pik1, bi, nullptr, nullptr);
+      if (nb_neg_product(f1, f2))
+      {
+        const double a = nb_cross_ratio(fb, fc);
+        if (a < 0)
+        {
+        }
+        else if (a < 1)
+        {
+          loc[2 * nadd] = agent_id, loc[2 * nadd + 1] = 1;
+          nadd++;
+        }
+        else if (i == 0)
+        {
+          loc[2 * nadd] = agent_id, loc[2 * nadd + 1] = 0;
+          nadd++;
+        }
+        base_add = true;
+      }
+    }
+    if (nb_neg_product(c1, c2))
+    {
+      const double a = nb_cross_ratio(ab, ac);
+      if (a < 0)
+      {
+        loc[2 * nadd] = agent_id, loc[2 * nadd + 1] = i + 2;
+        nadd++;
+      }
+      else if (a < 1 && last)
+      {
+        loc[2 * nadd] = agent_id, loc[2 * nadd + 1] = 1;
+        nadd++;
+      }
+      else if (a >= 1 && i == 0)
+      {
+        loc[2 * nadd] = agent_id, loc[2 * nadd + 1] = 0;
+        nadd++;
+      }
+    }
+  }
+  if (base_add && nadd >= 2 && loc[2 * (nadd - 1)] == loc[2 * (nadd - 2)] && loc[2 * (nadd - 1) + 1] == loc[2 * (nadd - 2) + 1])
+    nadd -= 2;
+  return nadd;
+}
+
+// eu::entangleHSigToAddStatic (:1231-1277) for ONE static obstacle
+NB_HD int nb_hsig_static_one(int* loc, const double* pk, const double* pk1, const double* rep /*[2][2]*/, int id)
+{
+  const double* pbi = rep;      // col(0)
+  const double* pik = rep + 2;  // col(1)
+  double ab[2], ac[2];
+  const double c1 = nb_wedge(pk, pik, pbi, ab, ac);
+  const double c2 = nb_wedge(pk1, pik, pbi, nullptr, nullptr);
+  if (!nb_neg_product(c1, c2)) return 0;
+  const double a = nb_cross_ratio(ab, ac);
+  if (a < 0) return 0;
+  loc[0] = id;
+  loc[1] = (a < 1) ? 1 : 0;
+  return 1;
+}
+
+// warp-exclusive prefix sum of per-lane counts; total returned to every lane
+template <int NL>
+NB_HD int nb_excl_scan(const Group<NL>& g, int v, int& total)
+{
+#if defined(__CUDA_ARCH__)
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < NL; o <<= 1)
+  {
+    const int y = __shfl_up_sync(0xffffffffu, x, o);
+    if (g.lane >= o) x += y;
+  }
+  total = __shfl_sync(0xffffffffu, x, NL - 1);
+  return x - v;
+#else
+  total = v;
+  return 0;
+#endif
+}
+
+// All crossing tests of one step pk -> pk+1: tethers of the known agents (positions pik -> pik+1 per
+// agent: pik_all[j], pik1_all[j]) then the static obstacles.  toadd: shared list [tcap][2].
+// Returns the number of entries, or -1 if tcap would be exceeded.
+template <int NL>
+NB_HD int nb_collect_toadd(const Group<NL>& g, const NbEntCtx& cx, const double* pk, const double* pk_agents,
+                           const double* pk1, const double* pik_all, int pik_stride, const double* pik1_all,
+                           int pik1_stride, const unsigned char* known, int* toadd, int tcap)
+{
+  int nadd = 0;
+  const double* pb_self = cx.pb + 2 * cx.self;
+  for (int base = 0; base < cx.N + cx.M; base += NL)
+  {
+    const int j = base + g.lane;
+    int loc[2 * NB_ENT_LOCAL];
+    int cnt = 0;
+    if (j < cx.N)
+    {
+      if (j != cx.self && known[j])
+      {
+        int nb = cx.bp_cnt[j];
+        if (nb > NB_ENT_LOCAL - 2) nb = NB_ENT_LOCAL - 2;
+        cnt = nb_hsig_agent(loc, pk_agents ? pk_agents + 2 * j : pk, pk1, pik_all + (size_t)j * pik_stride, pik1_all + (size_t)j * pik1_stride, pb_self,
+                            cx.bp_xy + (size_t)2 * cx.bp_max * j, nb, j + 1);
+      }
+    }
+    else if (j < cx.N + cx.M)
+      cnt = nb_hsig_static_one(loc, pk, pk1, cx.strep + 4 * (j - cx.N), j + 1);
+    int total;
+    const int off = nb_excl_scan<NL>(g, cnt, total);
+    if (nadd + total > tcap) return -1;
+    for (int e = 0; e < cnt; e++)
+    {
+      toadd[2 * (nadd + off + e)] = loc[2 * e];
+      toadd[2 * (nadd + off + e) + 1] = loc[2 * e + 1];
+    }
+    nadd += total;
+  }
+  g.sync();
+  return nadd;
+}
+
+// eu::getBendPt2d (:1649-1679)
+NB_HD void nb_bend_pt(double* bp, const NbEntState& es, const NbEntCtx& cx)
+{
+  if (es.n_bend == 0)
+  {
+    bp[0] = cx.pb[2 * cx.self], bp[1] = cx.pb[2 * cx.self + 1];
+    return;
+  }
+  const int q = es.bend[es.n_bend - 1];
+  const int id = es.alpha[2 * q], cs = es.alpha[2 * q + 1];
+  if (id <= cx.N && id >= 1)
+    bp[0] = cx.pb[2 * (id - 1)], bp[1] = cx.pb[2 * (id - 1) + 1];
+  else if (id > cx.N)
+    bp[0] = cx.strep[4 * (id - cx.N - 1) + 2 * cs], bp[1] = cx.strep[4 * (id - cx.N - 1) + 2 * cs + 1];
+}
+
+NB_HD void nb_bend_coord(double* bp, int id, int cs, const NbEntCtx& cx)
+{
+  if (id <= cx.N)
+    bp[0] = cx.pb[2 * (id - 1)], bp[1] = cx.pb[2 * (id - 1) + 1];
+  else
+    bp[0] = cx.strep[4 * (id - cx.N - 1) + 2 * cs], bp[1] = cx.strep[4 * (id - cx.N - 1) + 2 * cs + 1];
+}
+
+// eu::calculateBetaForCase (:1709-1722)
+NB_HD double nb_beta_for_case(int id, int cs, const double* pk, const double* bp, const NbEntCtx& cx)
+{
+  if (id <= cx.N) return 0.0;
+  return nb_wedge(pk, cx.strep + 4 * (id - cx.N - 1) + 2 * cs, bp, nullptr, nullptr);
+}
+
+// eu::breakcondition (:1608-1647)
+NB_HD bool nb_break_condition(int aid, int acs, int lid, int N, int idx_to_check, int idx_last_bend)
+{
+  if (aid <= N && acs >= 2) return idx_to_check <= idx_last_bend;
+  if (aid <= N) return false;
+  return lid > N || idx_to_check <= idx_last_bend;
+}
+
+// eu::addAlphaBetaToList (:1402-1534); single lane.  Returns 0, or -1 on storage overflow.
+NB_HD int nb_add_alpha_beta(int* toadd, int nadd, NbEntState& es, const double* pk, const NbEntCtx& cx)
+{
+  const int N = cx.N;
+  bool have = true;
+  while (have)
+  {
+    have = false;
+    const int b = es.n_bend == 0 ? -1 : es.bend[es.n_bend - 1];
+    for (int i = 0; i < nadd && !have; i++)
+    {
+      const int aid = toadd[2 * i], acs = toadd[2 * i + 1];
+      const int nb = (aid <= N) ? cx.bp_cnt[aid - 1] : 0;
+      for (int j = es.n_alpha - 1; j >= 0; j--)
+      {
+        const int lid = es.alpha[2 * j], lcs = es.alpha[2 * j + 1];
+        const int diff = acs > lcs ? acs - lcs : lcs - acs;
+        const bool cond = (lid == aid && lcs == acs) || (aid <= N && lid == aid && acs >= nb + 1 && acs < lcs) ||
+                          (aid <= N && lid == aid && lcs >= 2 && acs >= 2 && diff == 1 && j > b);
+        if (cond)
+        {
+          es.active[aid - 1] -= 1;
+          for (int q = i; q < nadd - 1; q++) toadd[2 * q] = toadd[2 * (q + 1)], toadd[2 * q + 1] = toadd[2 * (q + 1) + 1];
+          nadd--;
+          for (int q = j; q < es.n_alpha - 1; q++)
+          {
+            es.alpha[2 * q] = es.alpha[2 * (q + 1)], es.alpha[2 * q + 1] = es.alpha[2 * (q + 1) + 1];
+            es.beta[q] = es.beta[q + 1];
+          }
+          es.n_alpha--;
+          if (j == b)
+          {
+            es.n_bend--;
+            double bp[2];
+            nb_bend_pt(bp, es, cx);
+            for (int k = j; k < es.n_alpha; k++) es.beta[k] = nb_beta_for_case(es.alpha[2 * k], es.alpha[2 * k + 1], pk, bp, cx);
+          }
+          else if (j < b)
+          {
+            es.bend[es.n_bend - 1] = b - 1;
+            for (int k = es.n_bend - 2; k >= 0; k--)
+            {
+              if (es.bend[k] > j)
+                es.bend[k] -= 1;
+              else
+                break;
+            }
+          }
+          have = true;
+          break;
+        }
+        if (nb_break_condition(aid, acs, lid, N, j, b)) break;
+      }
+    }
+  }
+  if (nadd == 0) return 0;
+  double bp[2];
+  nb_bend_pt(bp, es, cx);
+  for (int i = 0; i < nadd; i++)
+  {
+    if (es.n_alpha >= cx.cap) return -1;
+    es.alpha[2 * es.n_alpha] = toadd[2 * i];
+    es.alpha[2 * es.n_alpha + 1] = toadd[2 * i + 1];
+    es.active[toadd[2 * i] - 1] += 1;
+    es.beta[es.n_alpha] = nb_beta_for_case(toadd[2 * i], toadd[2 * i + 1], pk, bp, cx);
+    es.n_alpha++;
+  }
+  return 0;
+}
+
+NB_HD bool nb_lt_prod(double a, double b, double thr)
+{
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b) < thr;
+#else
+  return a * b < thr;
+#endif
+}
+
+NB_HD bool nb_gt_prod(double a, double b, double thr)
+{
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b) > thr;
+#else
+  return a * b > thr;
+#endif
+}
+
+// eu::updateBendPts (:1536-1604); single lane
+NB_HD void nb_update_bend_pts(NbEntState& es, const double* pk1, const NbEntCtx& cx)
+{
+  double bp[2];
+  nb_bend_pt(bp, es, cx);
+  int idx_new = -1;
+  const int start = es.n_bend == 0 ? -1 : es.bend[es.n_bend - 1];
+  for (int i = start + 1; i < es.n_alpha; i++)
+  {
+    const double beta = nb_beta_for_case(es.alpha[2 * i], es.alpha[2 * i + 1], pk1, bp, cx);
+    if (nb_lt_prod(beta, es.beta[i], -1e-7)) idx_new = i;
+  }
+  if (idx_new > -1)
+  {
+    if (es.n_bend < cx.cap) es.bend[es.n_bend++] = idx_new;
+    double nbp[2];
+    nb_bend_coord(nbp, es.alpha[2 * idx_new], es.alpha[2 * idx_new + 1], cx);
+    for (int i = idx_new + 1; i < es.n_alpha; i++)
+      es.beta[i] = nb_beta_for_case(es.alpha[2 * i], es.alpha[2 * i + 1], pk1, nbp, cx);
+    return;
+  }
+  while (es.n_bend > 0)
+  {
+    double prev[2];
+    if (es.n_bend == 1)
+      prev[0] = cx.pb[2 * cx.self], prev[1] = cx.pb[2 * cx.self + 1];
+    else
+    {
+      const int q = es.bend[es.n_bend - 2];
+      nb_bend_coord(prev, es.alpha[2 * q], es.alpha[2 * q + 1], cx);
+    }
+    const int lb = es.bend[es.n_bend - 1];
+    const double beta = nb_beta_for_case(es.alpha[2 * lb], es.alpha[2 * lb + 1], pk1, prev, cx);
+    if (nb_gt_prod(beta, es.beta[lb], 1e-7))
+    {
+      for (int k = lb + 1; k < es.n_alpha; k++)
+        es.beta[k] = nb_beta_for_case(es.alpha[2 * k], es.alpha[2 * k + 1], pk1, prev, cx);
+      es.n_bend--;
+    }
+    else
+      break;
+  }
+}
+
+NB_HD void nb_eval_xy(const double* cxy /*[3][8][4] of agent*/, int i, double t, double* p)
+{
+  const double* x = cxy + 4 * i;
+  const double* y = cxy + 32 + 4 * i;
+  const double t3 = t * t * t, t2 = t * t;
+#if defined(__CUDA_ARCH__)
+  p[0] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(x[0], t3), __dmul_rn(x[1], t2)), __dmul_rn(x[2], t)), x[3]);
+  p[1] = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(y[0], t3), __dmul_rn(y[1], t2)), __dmul_rn(y[2], t)), y[3]);
+#else
+  p[0] = x[0] * t3 + x[1] * t2 + x[2] * t + x[3];
+  p[1] = y[0] * t3 + y[1] * t2 + y[2] * t + y[3];
+#endif
+}
+
+// One S-step pass over interval ii: shared by the front-end chain (kinodynamic_search.cpp:813-881)
+// and the post-check (:909-972).  samp: [N][num_pol][S+1][2] of this planning agent.
+// Returns 1 entangling, 0 fine, -1 capacity overflow.  Group-uniform result.
+template <int NL>
+NB_HD int nb_ent_interval_pass(const Group<NL>& g, NbEntState& es, const NbEntCtx& cx, const double* cxy, int ii,
+                               const double* samp, const unsigned char* known, int num_pol, int S, double T, int limit,
+                               int* toadd, int tcap, int* act_old, int* flag /*shared int*/)
+{
+  const int NA = cx.N + cx.M;
+  double pk[2] = { cxy[4 * ii + 3], cxy[32 + 4 * ii + 3] }, pk1[2];
+  for (int q = g.lane; q < NA; q += NL) act_old[q] = es.active[q];
+  g.sync();
+  for (int j = 1; j <= S; j++)
+  {
+    const double t = (j < S) ? T * j / S : T;
+    nb_eval_xy(cxy, ii, t, pk1);
+    const double *pik, *pik1;
+    const int stride = num_pol * (S + 1) * 2;
+    if (ii > num_pol - 1)
+    {
+      pik = samp + ((size_t)(num_pol - 1) * (S + 1) + S) * 2;
+      pik1 = pik;
+    }
+    else
+    {
+      pik = samp + ((size_t)ii * (S + 1) + (j - 1)) * 2;
+      pik1 = samp + ((size_t)ii * (S + 1) + j) * 2;
+    }
+    const int nadd = nb_collect_toadd<NL>(g, cx, pk, nullptr, pk1, pik, stride, pik1, stride, known, toadd, tcap);
+    if (nadd < 0) return -1;
+    if (g.lane == 0)
+    {
+      int r = 0;
+      if (es.n_alpha + nadd > limit)
+        r = 1;
+      else if (nb_add_alpha_beta(toadd, nadd, es, pk, cx))
+        r = -1;
+      else
+      {
+        for (int a = 0; a < cx.N; a++)
+        {
+          if (act_old[a] < 2 && es.active[a] >= 2) r = 1;
+          if (act_old[a] >= 2 && es.active[a] > act_old[a]) r = 1;
+        }
+        if (r == 0) nb_update_bend_pts(es, pk1, cx);
+      }
+      flag[0] = r;
+      flag[1] = es.n_alpha;
+      flag[2] = es.n_bend;
+    }
+    g.sync();
+    const int r = flag[0];
+    es.n_alpha = flag[1];
+    es.n_bend = flag[2];
+    g.sync();
+    if (r != 0) return r;
+    for (int q = g.lane; q < NA; q += NL) act_old[q] = es.active[q];
+    g.sync();
+    pk[0] = pk1[0];
+    pk[1] = pk1[1];
+  }
+  return 0;
+}
+
+// ---- K3 task: one agent per warp-group.  mode 0 predict, 1 rollout, 2 check-given-pwp
+struct NbEntArgs
+{
+  int mode, N, M, cap, bp_max, num_pol, S, tcap;
+  double T;
+  const int* agent_id;
+  const uint8_t* known;  // [B][N]
+  const int* bp_cnt;
+  const double* bp_xy;
+  const double* pb;
+  const double* strep;
+  nb_ent_state st;       // in (and out for predict / check)
+  nb_ent_state out;      // rollout: [B][9][...]
+  const int* n_int;
+  const double* coeff;   // [B][3][8][4]
+  const double* samp;    // [B or 1][N][8][S+1][2]
+  int samp_shared;
+  const double* prev_pos;        // predict
+  const double* prev_pos_agent;
+  const double* cur;
+  const double* samp0;
+  int* result;           // done / entangled
+  int* act_old;          // [B][N+M] scratch
+  int* err;
+};
+
+template <int NL>
+NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* toadd /*[tcap][2]*/, int* flag /*[4]*/)
+{
+  const int NA = a.N + a.M;
+  NbEntCtx cx;
+  cx.N = a.N, cx.M = a.M, cx.self = a.agent_id[b] - 1, cx.cap = a.cap, cx.bp_max = a.bp_max;
+  cx.pb = a.pb, cx.strep = a.strep, cx.bp_cnt = a.bp_cnt, cx.bp_xy = a.bp_xy;
+  const uint8_t* known = a.known + (size_t)b * a.N;
+  int* act_old = a.act_old + (size_t)b * NA;
+  NbEntState es;
+  if (a.mode == 1)
+  {  // work on slot 0 of the output, then replicate forward
+    const size_t o = (size_t)b * 9;
+    es.alpha = a.out.alpha + o * a.cap * 2, es.beta = a.out.beta + o * a.cap, es.bend = a.out.bend + o * a.cap;
+    es.active = a.out.active + o * NA;
+    for (int q = g.lane; q < a.cap; q += NL)
+    {
+      es.alpha[2 * q] = a.st.alpha[((size_t)b * a.cap + q) * 2], es.alpha[2 * q + 1] = a.st.alpha[((size_t)b * a.cap + q) * 2 + 1];
+      es.beta[q] = a.st.beta[(size_t)b * a.cap + q];
+      es.bend[q] = a.st.bend[(size_t)b * a.cap + q];
+    }
+    for (int q = g.lane; q < NA; q += NL) es.active[q] = a.st.active[(size_t)b * NA + q];
+  }
+  else
+  {
+    es.alpha = a.st.alpha + (size_t)b * a.cap * 2, es.beta = a.st.beta + (size_t)b * a.cap;
+    es.bend = a.st.bend + (size_t)b * a.cap, es.active = a.st.active + (size_t)b * NA;
+  }
+  es.n_alpha = a.st.cnt[2 * b];
+  es.n_bend = a.st.cnt[2 * b + 1];
+  g.sync();
+  const double* samp = a.samp ? a.samp + (a.samp_shared ? 0 : (size_t)b * a.N * a.num_pol * (a.S + 1) * 2) : nullptr;
+  const double* cxy = a.coeff ? a.coeff + (size_t)b * 96 : nullptr;
+  int bad = 0;
+  if (a.mode == 0)
+  {  // Neptune::PredictAlphasBetas neptune.cpp:976-1008
+    const double* pp = a.prev_pos + (size_t)b * (a.N + 1) * 2;
+    const double* cur = a.cur + 2 * b;
+    const int nadd = nb_collect_toadd<NL>(g, cx, pp + 2 * a.N, pp, cur, a.prev_pos_agent + (size_t)b * a.N * 2, 2,
+                                          a.samp0 + (size_t)b * a.N * 2, 2, known, toadd, a.tcap);
+    if (nadd < 0)
+      bad = 1;
+    else if (g.lane == 0)
+    {
+      if (nb_add_alpha_beta(toadd, nadd, es, pp + 2 * a.N, cx))
+        flag[3] = 1;
+      else
+      {
+        flag[3] = 0;
+        nb_update_bend_pts(es, cur, cx);
+      }
+      a.st.cnt[2 * b] = es.n_alpha;
+      a.st.cnt[2 * b + 1] = es.n_bend;
+    }
+    g.sync();
+    if (!bad && flag[3]) bad = 1;
+  }
+  else if (a.mode == 2)
+  {  // entangleCheckGivenPwp: interval 0 only (kinodynamic_search.cpp:899, :982-983)
+    int r = 0;
+    if (a.n_int[b] > 0)
+      r = nb_ent_interval_pass<NL>(g, es, cx, cxy, 0, samp, known, a.num_pol, a.S, a.T, 3 * NA, toadd, a.tcap, act_old, flag);
+    if (r < 0) bad = 1;
+    if (g.lane == 0)
+    {
+      a.result[b] = r > 0 ? 1 : 0;
+      a.st.cnt[2 * b] = es.n_alpha;
+      a.st.cnt[2 * b + 1] = es.n_bend;
+    }
+  }
+  else
+  {  // rollout: states after 0..n intervals
+    const int n = a.n_int[b];
+    int done = n;
+    for (int i = 0; i <= NB_NPOL; i++)
+    {
+      const size_t o = (size_t)b * 9 + i;
+      if (i > 0)
+      {  // copy state i-1 forward, then advance it when i <= n
+        int* al = a.out.alpha + o * a.cap * 2;
+        double* be = a.out.beta + o * a.cap;
+        int* bd = a.out.bend + o * a.cap;
+        int* ac = a.out.active + o * NA;
+        for (int q = g.lane; q < a.cap; q += NL)
+        {
+          al[2 * q] = es.alpha[2 * q], al[2 * q + 1] = es.alpha[2 * q + 1];
+          be[q] = es.beta[q];
+          bd[q] = es.bend[q];
+        }
+        for (int q = g.lane; q < NA; q += NL) ac[q] = es.active[q];
+        g.sync();
+        es.alpha = al, es.beta = be, es.bend = bd, es.active = ac;
+        if (i <= n && !bad)
+        {
+          const int r = nb_ent_interval_pass<NL>(g, es, cx, cxy, i - 1, samp, known, a.num_pol, a.S, a.T, NA, toadd,
+                                                 a.tcap, act_old, flag);
+          if (r < 0) bad = 1;
+          if (r > 0 && done == n) done = i - 1;
+        }
+      }
+      if (g.lane == 0)
+      {
+        a.out.cnt[2 * o] = es.n_alpha;
+        a.out.cnt[2 * o + 1] = es.n_bend;
+      }
+    }
+    if (g.lane == 0) a.result[b] = bad ? -1 : done;
+  }
+  if (bad && g.lane == 0) *a.err = 2;
+}
+

@@ -8,6 +8,7 @@
 //   [0,NH) other agents' hulls | [NH,NH+N) bases | [NH+N,NH+N+M) static | [..,+ent_slots) tether.
 #pragma once
 #include "nb_common.cuh"
+#include "nb_prune.cuh"
 #include "nb_sep.cuh"
 
 struct NbLinesIn
@@ -55,14 +56,18 @@ NB_HD void nb_ctrl_pts(const NbConsts& cs, const double* ci /*[3][8][4] of agent
 // non-entangling constraints.  lines: [LS][3], ok: [LS] of this (b, i).  Sets *err on overflow.
 template <int NT>
 NB_HD void nb_lines_task(int tid, int b, int i, const NbConsts& cs, const NbLinesIn& in, double* lines,
-                         uint8_t* ok, int* err)
+                         uint8_t* ok, uint8_t* keep, const NbPruneShared& ps, int* err)
 {
   const int N = cs.N, M = cs.M, NH = in.NH;
   const int LS = NH + N + M + cs.ent_slots;
   const int n = in.n_int[b];
   if (i >= n)
   {
-    for (int s = tid; s < LS; s += NT) ok[s] = 0;
+    for (int s = tid; s < LS; s += NT)
+    {
+      ok[s] = 0;
+      keep[s] = 0;
+    }
     return;
   }
   double cp[8];
@@ -161,7 +166,7 @@ NB_HD void nb_lines_task(int tid, int b, int i, const NbConsts& cs, const NbLine
         if (eslot >= cs.ent_slots)
         {
           *err = 1;
-          return;
+          break;
         }
         const double Aset[4] = { pA[0], pA[1], pB[0], pB[1] };
         double l[3];
@@ -174,13 +179,24 @@ NB_HD void nb_lines_task(int tid, int b, int i, const NbConsts& cs, const NbLine
       }
     }
   }
+  Cta<NT> cta(tid);
+  cta.sync();
+  nb_prune_lines<NT>(cta, LS, lines, ok, cp, ps, keep);
 }
 
 // Gather the solved lines of one agent, interval by interval, into the compact list the QP reads:
 // cl[l] = (n0, n1, 1 - d).  Group-cooperative; returns the total number of lines.
 template <int NL>
+NB_HD int nb_count_lines(const Group<NL>& g, int n, int LS, const uint8_t* keep /*[8][LS]*/)
+{
+  double c = 0.0;
+  for (int q = g.lane; q < n * LS; q += NL) c += (keep[q] == 1) ? 1.0 : 0.0;
+  return (int)(g.sum(c) + 0.5);
+}
+
+template <int NL>
 NB_HD int nb_compact_lines(const Group<NL>& g, int n, int LS, const double* lines /*[8][LS][3]*/,
-                           const uint8_t* ok /*[8][LS]*/, double* cl, int* lstart)
+                           const uint8_t* ok /*[8][LS] keep flags*/, double* cl, int* lstart)
 {
   int total = 0;
   for (int i = 0; i < n; i++)

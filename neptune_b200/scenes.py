@@ -426,7 +426,7 @@ def fill_entangle(sc: Scene, be, rng) -> None:
         cur = sc.prev_pos[bi, 0]
         start = pb[b] + 0.8 * (cur - pb[b]) / max(np.linalg.norm(cur - pb[b]), 1e-9)
         mid = 0.5 * (start + cur) + rng.normal(0, 3.0, size=2)
-        wps = [start] + [start + (mid - start) * k / 3 for k in (1, 2, 3)] + [mid + (cur - mid) * k / 4 for k in (1, 2, 3, 4)]
+        wps = [start] + [start + (mid - start) * k / 4 for k in (1, 2, 3, 4)] + [mid + (cur - mid) * k / 4 for k in (1, 2, 3, 4)]
         for i in range(8):
             vel = (wps[i + 1] - wps[i]) / T
             hist[bi, 0, i] = [0, 0, vel[0], wps[i][0]]

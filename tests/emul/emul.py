@@ -24,14 +24,15 @@ def lib():
     return _lib
 
 
-def replan(batch, with_lines=True) -> ReplanResult:
+def replan(batch, with_lines=True, prune=True, n_lines=None) -> ReplanResult:
     par = batch.par
     res = ReplanResult.empty(batch, with_lines)
     a = host_args(batch, res)
     nbp = make_nb_params(par)
     pb = np.ascontiguousarray(par.pb, np.float64)
     rc = lib().emul_replan_batch(C.byref(nbp), pb.ctypes.data_as(C.c_void_p), batch.st_ptr.ctypes.data_as(C.c_void_p),
-                                 batch.st_xy.ctypes.data_as(C.c_void_p), C.byref(a))
+                                 batch.st_xy.ctypes.data_as(C.c_void_p), C.byref(a), int(prune),
+                                 None if n_lines is None else n_lines.ctypes.data_as(C.c_void_p))
     assert rc == 0, rc
     return res
 

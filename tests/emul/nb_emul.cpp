@@ -29,7 +29,7 @@ extern "C" int emul_table(const nb_params* par, int n, int mode, NbQpTable* out)
 }
 
 extern "C" int emul_replan_batch(const nb_params* par, const double* pb, const int64_t* st_ptr, const double* st_xy,
-                                 const nb_replan_args* a)
+                                 const nb_replan_args* a, int prune, int* n_lines_out)
 {
   NbConsts cs;
   nb_build_consts(par, &cs);
@@ -46,19 +46,25 @@ extern "C" int emul_replan_batch(const nb_params* par, const double* pb, const i
   in.esv_cnt = a->esv_cnt, in.esv_alpha = a->esv_alpha, in.esv_active = a->esv_active;
   in.bp_cnt = a->bp_cnt, in.bp_xy = a->bp_xy, in.pb = pb;
   std::vector<double> lines((size_t)NB_NPOL * LS * 3), cl((size_t)NB_NPOL * LS * 3), rows((size_t)4 * RS);
-  std::vector<uint8_t> ok((size_t)NB_NPOL * LS);
+  std::vector<uint8_t> ok((size_t)NB_NPOL * LS), keep((size_t)NB_NPOL * LS), valid(LS + 1);
+  std::vector<double> px(LS + 1), py(LS + 1);
+  int red[1], hull[NB_PRUNE_KMAX + 1], misc[8];
+  NbPruneShared ps;
+  ps.px = px.data(), ps.py = py.data(), ps.valid = valid.data(), ps.red = red, ps.hull = hull, ps.misc = misc;
   int lstart[9], err = 0;
   NbQpShared* sh = new NbQpShared();
   Group<1> g(0);
   for (int b = 0; b < B; b++)
   {
     for (int i = 0; i < NB_NPOL; i++)
-      nb_lines_task<1>(0, b, i, cs, in, lines.data() + (size_t)i * LS * 3, ok.data() + (size_t)i * LS, &err);
+      nb_lines_task<1>(0, b, i, cs, in, lines.data() + (size_t)i * LS * 3, ok.data() + (size_t)i * LS,
+                       keep.data() + (size_t)i * LS, ps, &err);
     if (a->lines) memcpy(a->lines + (size_t)b * NB_NPOL * LS * 3, lines.data(), sizeof(double) * lines.size());
     if (a->line_ok) memcpy(a->line_ok + (size_t)b * NB_NPOL * LS, ok.data(), ok.size());
     const int n = a->n_int[b];
     const double* ci = a->coeff_init + (size_t)b * 96;
-    const int nl = nb_compact_lines<1>(g, n, LS, lines.data(), ok.data(), cl.data(), lstart);
+    const int nl = nb_compact_lines<1>(g, n, LS, lines.data(), prune ? keep.data() : ok.data(), cl.data(), lstart);
+    if (n_lines_out) n_lines_out[b] = nl;
     NbQpRows R;
     R.s = rows.data(), R.lam = R.s + RS, R.dsa = R.lam + RS, R.dla = R.dsa + RS, R.cl = cl.data(), R.lstart = lstart;
     double xout[96], obj = 0;
@@ -94,5 +100,32 @@ extern "C" int emul_replan_batch(const nb_params* par, const double* pb, const i
     a->iters[2 * b + 1] = it1;
   }
   delete sh;
+  return err ? NB_ERR_CAPACITY : 0;
+}
+
+#include "../../neptune_b200/csrc/nb_entangle.cuh"
+
+extern "C" int emul_entangle(const nb_params* par, const double* pb, const double* strep, int mode, int B,
+                             const int32_t* agent_id, const uint8_t* known, const int32_t* bp_cnt, const double* bp_xy,
+                             nb_ent_state st, nb_ent_state out, const int32_t* n_int, const double* coeff,
+                             const double* samp, int samp_shared, const double* prev_pos, const double* prev_pos_agent,
+                             const double* cur, const double* samp0, int32_t* result)
+{
+  NbEntArgs a;
+  memset(&a, 0, sizeof(a));
+  const int N = par->num_agents, M = par->num_static;
+  a.mode = mode, a.N = N, a.M = M, a.cap = par->ent_cap, a.bp_max = par->bp_max, a.num_pol = par->num_pol;
+  a.S = par->samples, a.T = par->T_span;
+  int tcap = 4 * (N + M) + 16;
+  a.tcap = tcap > 1024 ? 1024 : tcap;
+  a.agent_id = agent_id, a.known = known, a.bp_cnt = bp_cnt, a.bp_xy = bp_xy, a.pb = pb, a.strep = strep;
+  a.st = st, a.out = out, a.n_int = n_int, a.coeff = coeff, a.samp = samp, a.samp_shared = samp_shared;
+  a.prev_pos = prev_pos, a.prev_pos_agent = prev_pos_agent, a.cur = cur, a.samp0 = samp0, a.result = result;
+  std::vector<int> act_old((size_t)B * (N + M)), toadd(2 * a.tcap + 8);
+  int err = 0;
+  a.act_old = act_old.data();
+  a.err = &err;
+  Group<1> g(0);
+  for (int b = 0; b < B; b++) nb_entangle_task<1>(g, b, a, toadd.data(), toadd.data() + 2 * a.tcap);
   return err ? NB_ERR_CAPACITY : 0;
 }

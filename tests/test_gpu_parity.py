@@ -90,3 +90,33 @@ def test_missing_static_is_an_error(capi):
     with pytest.raises(capi.NbError):
         s.replan(sc.batch)
     s.close()
+
+
+@pytest.mark.parametrize("cfg,seeds", [("mtlp5", (2002, 2005)), ("obst8", (3003, 3004, 3006))])
+def test_entangle_chain_bit_exact(capi, oracle, cfg, seeds):
+    """K3 vs oracle: alphas, active_cases, bendPointsIdx bit-exact (betas too: same IEEE operations)
+    for the history walk, PredictAlphasBetas, the front-end chain and entangleCheckGivenPwp."""
+    from tests.ent_backends import OracleEntBackend
+    par = config(cfg)
+    for seed in seeds:
+        ref = make_scene(par, seed, sync=False, ent_backend=OracleEntBackend(oracle))
+        s = capi.Solver(par)
+        if par.num_of_static_obst:
+            s.set_static(ref.batch.st_ptr, ref.batch.st_xy, ref.strep)
+        dev = capi.DeviceEntBackend(s)
+        got = make_scene(par, seed, sync=False, ent_backend=dev)
+        for k in ("es0_cnt", "es0_alpha", "es0_beta", "es0_bend", "es0_active", "esA_cnt", "esA_alpha", "esA_beta",
+                  "esA_bend", "esA_active"):
+            assert np.array_equal(getattr(got, k), getattr(ref, k)), k
+        for k in ("esv_cnt", "esv_alpha", "esv_active"):
+            assert np.array_equal(getattr(got.batch, k), getattr(ref.batch, k)), k
+        # post-check on the optimised trajectory (a17), both sides from the same state
+        res = s.replan(ref.batch)
+        b = ref.batch
+        args = (par, b.agent_id, b.n_int, res.coeff_out, ref.samp, ref.known, ref.strep, b.bp_cnt, b.bp_xy,
+                ref.esA_cnt, ref.esA_alpha, ref.esA_beta, ref.esA_bend, ref.esA_active)
+        g = dev.check_batch(*args)
+        r = OracleEntBackend(oracle).check_batch(*args)
+        for x, y in zip(g, r):
+            assert np.array_equal(x, y)
+        s.close()
