@@ -112,6 +112,8 @@ typedef struct nb_replan_args
   const int64_t* hull_ptr;    /* [B*slots*8+1] vertex offsets; empty polygon = slot unused */
   const double* hull_xy;      /* [hull_ptr[last]][2] CCW convex polygons (setHulls) */
   int64_t hull_nvert;         /* total vertices in hull_xy */
+  const int32_t* hull_cnt;    /* optional [B*slots*8] vertex counts; NULL: count = hull_ptr[k+1]-hull_ptr[k] (CSR).
+                                 With counts, hull_ptr needs only B*slots*8 entries (nb_hulls_batch output). */
   const double* nih0;         /* [B][N][8][2] col(0) of hullsNoInflation_[j][i]; NaN = unknown */
   const int32_t* esv_cnt;     /* [B][9][2] (alphas.size(), bendPointsIdx.size()) of entStateVec[i] */
   const int32_t* esv_alpha;   /* [B][9][ent_cap][2] */
@@ -149,6 +151,39 @@ int nb_separate_batch(nb_handle* h, int32_t L, int32_t space, const int64_t* a_p
  * (pos, vel, accel, jerk), n_states[B]. */
 int nb_generate_traj_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
                            double dc, int32_t max_states, double* states, int32_t* n_states, void* stream);
+
+/*
+ * Committed-trajectory record: the fixed-stride payload of the per-cycle all-gather (the batched
+ * form of mader_msgs/DynTraj.msg + PieceWisePolTraj.msg): NB_REC_DOUBLES doubles per agent,
+ *   [0] n_pieces (<= 16), [1..17] times, [18..209] coeff[3][16][4] ([a b c d] per axis and piece).
+ */
+#define NB_REC_PIECES 16
+#define NB_REC_DOUBLES (1 + (NB_REC_PIECES + 1) + 3 * NB_REC_PIECES * 4)
+#define NB_HULL_STRIDE 24 /* vertices reserved per hull in nb_hulls_batch output */
+
+/*
+ * Replaces Neptune::convexHullsOfCurves2d (neptune.cpp:224-267 and callees :269-452, with
+ * cu::convexHullOfPoints2d cgal_utils.cpp:157-174) and Neptune::SamplePointsOfCurves
+ * (neptune.cpp:463-566) for B planning agents against the N committed trajectories `recs`.
+ * Windows are [t_start[b] + i T, t_start[b] + (i+1) T], i < num_pol.  delta = bbox/2 + drone_radius
+ * (neptune.cpp:340).  known [B][N]: 0 = no trajectory of j at agent b (or j is b itself).
+ * Outputs (fixed stride, directly usable as nb_replan_args.hull_* with n_hull_slots = N):
+ *   hull_xy [B][N][8][NB_HULL_STRIDE][2], hull_cnt [B][N][8] (0 when unknown),
+ *   hull_ptr [B*N*8] (= k * NB_HULL_STRIDE), nih0 [B][N][8][2] (NaN when unknown),
+ *   samp [B][N][8][S+1][2], idx [B][N][8][2] = (index_first_interval, index_last_interval), optional.
+ */
+int nb_hulls_batch(nb_handle* h, int32_t B, int32_t space, const double* t_start, const double* recs,
+                   const uint8_t* known, double delta, double* hull_xy, int32_t* hull_cnt, int64_t* hull_ptr,
+                   double* nih0, double* samp, int32_t* idx, void* stream);
+
+/*
+ * Replaces the geometric half of Neptune::safetyCheckAfterReplan (neptune.cpp:719-765):
+ * trajsAndPwpAreInCollision2d (:767-806) with gjk::collision (gjk.cpp:76-148), for every (b, j) with
+ * late[b][j] != 0 (trajectory of j received after time_init_opt_).  collide [B] = 1 if any collides.
+ */
+int nb_postcheck_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
+                       const double* t_start, const double* recs, const uint8_t* late, double delta,
+                       int32_t* collide, void* stream);
 
 /*
  * Entanglement-signature chain, batched (one agent per warp).  State = eu::ent_state

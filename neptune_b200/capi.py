@@ -32,7 +32,7 @@ class NbParams(C.Structure):
 class NbReplanArgs(C.Structure):
     _fields_ = [("B", C.c_int32), ("space", C.c_int32), ("agent_id", _P), ("n_int", _P), ("coeff_init", _P),
                 ("n_hull_slots", C.c_int32), ("hull_ptr", _P), ("hull_xy", _P), ("hull_nvert", C.c_int64),
-                ("nih0", _P), ("esv_cnt", _P), ("esv_alpha", _P), ("esv_active", _P), ("bp_cnt", _P),
+                ("hull_cnt", _P), ("nih0", _P), ("esv_cnt", _P), ("esv_alpha", _P), ("esv_active", _P), ("bp_cnt", _P),
                 ("bp_xy", _P), ("coeff_out", _P), ("obj", _P), ("status", _P), ("iters", _P), ("lines", _P),
                 ("line_ok", _P)]
 
@@ -61,6 +61,7 @@ def host_args(batch: ReplanBatch, res: ReplanResult) -> NbReplanArgs:
     a.agent_id, a.n_int, a.coeff_init = _np(batch.agent_id), _np(batch.n_int), _np(batch.coeff_init)
     a.n_hull_slots, a.hull_ptr, a.hull_xy = batch.n_hull_slots, _np(batch.hull_ptr), _np(batch.hull_xy)
     a.hull_nvert = int(batch.hull_xy.shape[0])
+    a.hull_cnt = None
     a.nih0, a.esv_cnt, a.esv_alpha, a.esv_active = _np(batch.nih0), _np(batch.esv_cnt), _np(batch.esv_alpha), _np(batch.esv_active)
     a.bp_cnt, a.bp_xy = _np(batch.bp_cnt), _np(batch.bp_xy)
     a.coeff_out, a.obj, a.status, a.iters = _np(res.coeff_out), _np(res.obj), _np(res.status), _np(res.iters)
@@ -249,6 +250,62 @@ class Solver:
         _check(f(self._h, B, NB_HOST, _np(arrs[0]), _np(arrs[1]), _np(arrs[2]), _np(arrs[3]), st.c(), _np(arrs[4]),
                  _np(arrs[5]), _np(arrs[6]), int(samp_shared), _np(ent), None), "nb_entangle_check_batch")
         return ent, st
+
+
+NB_REC_DOUBLES = 1 + 17 + 3 * 16 * 4
+NB_HULL_STRIDE = 24
+
+
+def make_records(committed) -> np.ndarray:
+    """Committed-trajectory records (the all-gather payload) from (times, cx, cy, cz) tuples."""
+    recs = np.zeros((len(committed), NB_REC_DOUBLES))
+    for j, (tm, cx, cy, cz) in enumerate(committed):
+        n = len(cx)
+        assert n <= 16
+        recs[j, 0] = n
+        recs[j, 1:2 + n] = tm
+        co = recs[j, 18:].reshape(3, 16, 4)
+        co[0, :n], co[1, :n], co[2, :n] = cx, cy, cz
+    return recs
+
+
+def _hulls_impl(fn, par, t_start, recs, known, delta, want_idx=True):
+    B, N, S = len(t_start), par.num_of_agents, par.num_sample_per_interval
+    t_start, recs = np.ascontiguousarray(t_start, np.float64), np.ascontiguousarray(recs, np.float64)
+    known = np.ascontiguousarray(known, np.uint8)
+    out = dict(hull_xy=np.zeros((B, N, NPOL, NB_HULL_STRIDE, 2)), hull_cnt=np.zeros((B, N, NPOL), np.int32),
+               hull_ptr=np.zeros(B * N * NPOL, np.int64), nih0=np.zeros((B, N, NPOL, 2)),
+               samp=np.zeros((B, N, par.num_pol, S + 1, 2)), idx=np.zeros((B, N, NPOL, 2), np.int32))
+    fn(B, _np(t_start), _np(recs), _np(known), C.c_double(delta), _np(out["hull_xy"]), _np(out["hull_cnt"]),
+       _np(out["hull_ptr"]), _np(out["nih0"]), _np(out["samp"]), _np(out["idx"]) if want_idx else None)
+    return out
+
+
+def solver_hulls(self, t_start, recs, known, delta):
+    """K1: hulls, nih0 and samples of every committed trajectory for every planning agent."""
+    f = lib().nb_hulls_batch
+    f.argtypes = [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_double, _P, _P, _P, _P, _P, _P, _P]
+
+    def call(B, ts, rc, kn, dl, hx, hc, hp, n0, sm, ix):
+        _check(f(self._h, B, NB_HOST, ts, rc, kn, dl, hx, hc, hp, n0, sm, ix, None), "nb_hulls_batch")
+    return _hulls_impl(call, self.par, t_start, recs, known, delta)
+
+
+def solver_postcheck(self, n_int, coeff, t_start, recs, late, delta):
+    """K5: ``trajsAndPwpAreInCollision2d`` of every agent's optimised pwp against the late trajectories."""
+    n_int, coeff = np.ascontiguousarray(n_int, np.int32), np.ascontiguousarray(coeff, np.float64)
+    t_start, recs = np.ascontiguousarray(t_start, np.float64), np.ascontiguousarray(recs, np.float64)
+    late = np.ascontiguousarray(late, np.uint8)
+    col = np.zeros(len(n_int), np.int32)
+    f = lib().nb_postcheck_batch
+    f.argtypes = [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, C.c_double, _P, _P]
+    _check(f(self._h, len(n_int), NB_HOST, _np(n_int), _np(coeff), _np(t_start), _np(recs), _np(late), delta, _np(col),
+             None), "nb_postcheck_batch")
+    return col
+
+
+Solver.hulls = solver_hulls
+Solver.postcheck = solver_postcheck
 
 
 class DeviceEntBackend:

@@ -11,6 +11,7 @@
 #include "../../include/neptune_b200.h"
 #include "nb_common.cuh"
 #include "nb_entangle.cuh"
+#include "nb_hull.cuh"
 #include "nb_lines.cuh"
 #include "nb_qp.cuh"
 #include "nb_sep.cuh"
@@ -243,6 +244,66 @@ __global__ void __launch_bounds__(32) k_entangle(NbEntArgs a)
   nb_entangle_task<32>(g, blockIdx.x, a, smem_i, smem_i + 2 * a.tcap);
 }
 
+// ---- K1 / K5 kernels
+__global__ void k_hulls(NbConsts cs, int B, const double* t_start, const double* recs, const uint8_t* known, double delta,
+                        double* hull_xy, int* hull_cnt, int64_t* hull_ptr, double* nih0, int* idx, int* err)
+{
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j, i)
+  const size_t total = (size_t)B * cs.N * NB_NPOL;
+  if (k >= total) return;
+  const int i = (int)(k % NB_NPOL), j = (int)((k / NB_NPOL) % cs.N), b = (int)(k / ((size_t)NB_NPOL * cs.N));
+  hull_ptr[k] = (int64_t)k * NB_HMAX;
+  int cnt = 0, id2[2] = { -1, -1 };
+  double n0[2];
+#if defined(__CUDA_ARCH__)
+  n0[0] = n0[1] = __longlong_as_double(0x7ff8000000000000LL);
+#endif
+  if (i < cs.num_pol && known[(size_t)b * cs.N + j])
+  {
+    const double t0 = NB_ADD(t_start[b], NB_MUL((double)i, cs.T)), t1 = NB_ADD(t_start[b], NB_MUL((double)(i + 1), cs.T));
+    cnt = nb_hull_of_window(cs, recs + (size_t)j * NB_REC, t0, t1, delta, hull_xy + k * NB_HMAX * 2, n0, id2);
+    if (cnt < 0 || cnt > NB_HMAX)
+    {
+      *err = 3;
+      cnt = 0;
+    }
+  }
+  hull_cnt[k] = cnt;
+  nih0[2 * k] = n0[0];
+  nih0[2 * k + 1] = n0[1];
+  if (idx)
+  {
+    idx[2 * k] = id2[0];
+    idx[2 * k + 1] = id2[1];
+  }
+}
+
+__global__ void k_samples(NbConsts cs, int B, const double* t_start, const double* recs, const uint8_t* known, double* samp)
+{
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j)
+  if (k >= (size_t)B * cs.N) return;
+  const int j = (int)(k % cs.N), b = (int)(k / cs.N);
+  double* out = samp + k * cs.num_pol * (cs.S + 1) * 2;
+  if (!known[k])
+  {
+    for (int q = 0; q < cs.num_pol * (cs.S + 1) * 2; q++) out[q] = 0.0;
+    return;
+  }
+  nb_sample_points(cs, recs + (size_t)j * NB_REC, t_start[b], NB_ADD(t_start[b], NB_MUL(cs.T, (double)cs.num_pol)), out, nullptr);
+}
+
+__global__ void k_postcheck(NbConsts cs, int B, const int* n_int, const double* coeff, const double* t_start,
+                            const double* recs, const uint8_t* late, double delta, int* collide, int* err)
+{
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j)
+  if (k >= (size_t)B * cs.N) return;
+  const int j = (int)(k % cs.N), b = (int)(k / cs.N);
+  if (!late[k]) return;
+  const int r = nb_pwp_collides(cs, coeff + (size_t)b * 96, n_int[b], t_start[b], recs + (size_t)j * NB_REC, delta);
+  if (r < 0) *err = 3;
+  if (r > 0) atomicOr(collide + b, 1);
+}
+
 // ------------------------------------------------------------------------------------------ ABI
 
 extern "C" int nb_create(const nb_params* par, const double* pb, int device, nb_handle** out)
@@ -436,8 +497,9 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   if ((rc = stage_in(h, 0, sp, a->agent_id, (size_t)B, st, &in.agent_id))) return rc;
   if ((rc = stage_in(h, 1, sp, a->n_int, (size_t)B, st, &in.n_int))) return rc;
   if ((rc = stage_in(h, 2, sp, a->coeff_init, (size_t)B * 96, st, &in.coeff_init))) return rc;
-  if ((rc = stage_in(h, 3, sp, a->hull_ptr, (size_t)B * NH * 8 + 1, st, &in.hull_ptr))) return rc;
+  if ((rc = stage_in(h, 3, sp, a->hull_ptr, (size_t)B * NH * 8 + (a->hull_cnt ? 0 : 1), st, &in.hull_ptr))) return rc;
   if ((rc = stage_in(h, 4, sp, a->hull_xy, (size_t)a->hull_nvert * 2, st, &in.hull_xy))) return rc;
+  if ((rc = stage_in(h, 11, sp, a->hull_cnt, (size_t)B * NH * 8, st, &in.hull_cnt))) return rc;
   if ((rc = stage_in(h, 5, sp, a->nih0, (size_t)B * N * 16, st, &in.nih0))) return rc;
   if ((rc = stage_in(h, 6, sp, a->esv_cnt, (size_t)B * 18, st, &in.esv_cnt))) return rc;
   if ((rc = stage_in(h, 7, sp, a->esv_alpha, (size_t)B * 9 * cap * 2, st, &in.esv_alpha))) return rc;
@@ -792,4 +854,92 @@ extern "C" int nb_entangle_check_batch(nb_handle* h, int32_t B, int32_t space, c
   if ((rc = state_out(h, space, stt, d, (size_t)B, st))) return rc;
   if (space == NB_HOST) NB_CUDA(cudaMemcpyAsync(entangled, a.result, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
   return ent_finish(h, space, st);
+}
+
+// ------------------------------------------------------------------------------------------ K1 / K5 ABI
+extern "C" int nb_hulls_batch(nb_handle* h, int32_t B, int32_t space, const double* t_start, const double* recs,
+                              const uint8_t* known, double delta, double* hull_xy, int32_t* hull_cnt, int64_t* hull_ptr,
+                              double* nih0, double* samp, int32_t* idx, void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  static_assert(NB_REC == NB_REC_DOUBLES && NB_HMAX == NB_HULL_STRIDE, "record layout");
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->par.num_agents, S = h->par.samples, P = h->par.num_pol;
+  const size_t nh = (size_t)B * N * NB_NPOL;
+  const double *dt, *dr;
+  const uint8_t* dk;
+  double *dxy, *dn0, *dsamp;
+  int *dcnt, *didx;
+  int64_t* dptr;
+  int rc;
+  if ((rc = stage_in(h, 0, space, t_start, (size_t)B, st, &dt))) return rc;
+  if ((rc = stage_in(h, 1, space, recs, (size_t)N * NB_REC, st, &dr))) return rc;
+  if ((rc = stage_in(h, 2, space, known, (size_t)B * N, st, &dk))) return rc;
+  if ((rc = stage_out(h, 0, space, hull_xy, nh * NB_HMAX * 2, &dxy))) return rc;
+  if ((rc = stage_out(h, 1, space, hull_cnt, nh, &dcnt))) return rc;
+  if ((rc = stage_out(h, 2, space, hull_ptr, nh, &dptr))) return rc;
+  if ((rc = stage_out(h, 3, space, nih0, nh * 2, &dn0))) return rc;
+  if ((rc = stage_out(h, 4, space, samp, (size_t)B * N * P * (S + 1) * 2, &dsamp))) return rc;
+  if ((rc = stage_out(h, 5, space, idx, nh * 2, &didx))) return rc;
+  k_hulls<<<(unsigned)((nh + 127) / 128), 128, 0, st>>>(h->cs, B, dt, dr, dk, delta, dxy, dcnt, dptr, dn0, didx, (int*)h->err.p);
+  h->launches += 1;
+  if (dsamp)
+  {
+    k_samples<<<(unsigned)(((size_t)B * N + 127) / 128), 128, 0, st>>>(h->cs, B, dt, dr, dk, dsamp);
+    h->launches += 1;
+  }
+  NB_CUDA(cudaGetLastError());
+  if (space == NB_HOST)
+  {
+    NB_CUDA(cudaMemcpyAsync(hull_xy, dxy, nh * NB_HMAX * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(hull_cnt, dcnt, nh * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(hull_ptr, dptr, nh * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(nih0, dn0, nh * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (samp) NB_CUDA(cudaMemcpyAsync(samp, dsamp, (size_t)B * N * P * (S + 1) * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (idx) NB_CUDA(cudaMemcpyAsync(idx, didx, nh * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    int err = 0;
+    NB_CUDA(cudaMemcpyAsync(&err, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaStreamSynchronize(st));
+    if (err)
+    {
+      NB_CUDA(cudaMemsetAsync(h->err.p, 0, sizeof(int), st));
+      g_err = "nb_hulls_batch: a window overlaps too many pieces or a hull has too many vertices";
+      return NB_ERR_CAPACITY;
+    }
+  }
+  return NB_OK;
+}
+
+extern "C" int nb_postcheck_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
+                                  const double* t_start, const double* recs, const uint8_t* late, double delta,
+                                  int32_t* collide, void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->par.num_agents;
+  const int* dn;
+  const double *dc, *dt, *dr;
+  const uint8_t* dl;
+  int* dcol;
+  int rc;
+  if ((rc = stage_in(h, 0, space, n_int, (size_t)B, st, &dn))) return rc;
+  if ((rc = stage_in(h, 1, space, coeff, (size_t)B * 96, st, &dc))) return rc;
+  if ((rc = stage_in(h, 2, space, t_start, (size_t)B, st, &dt))) return rc;
+  if ((rc = stage_in(h, 3, space, recs, (size_t)N * NB_REC, st, &dr))) return rc;
+  if ((rc = stage_in(h, 4, space, late, (size_t)B * N, st, &dl))) return rc;
+  if ((rc = stage_out(h, 0, space, collide, (size_t)B, &dcol))) return rc;
+  NB_CUDA(cudaMemsetAsync(dcol, 0, (size_t)B * sizeof(int), st));
+  k_postcheck<<<(unsigned)(((size_t)B * N + 127) / 128), 128, 0, st>>>(h->cs, B, dn, dc, dt, dr, dl, delta, dcol, (int*)h->err.p);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
+  if (space == NB_HOST)
+  {
+    NB_CUDA(cudaMemcpyAsync(collide, dcol, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaStreamSynchronize(st));
+  }
+  return NB_OK;
 }

@@ -1,0 +1,329 @@
+// nb_hull.cuh -- K1 (hulls and samples of the other agents' committed trajectories) and K5 (GJK
+// post-check).
+//
+// K1 replaces Neptune::convexHullsOfCurves2d / convexHullsOfCurve2d / convexHullOfInterval2d /
+// vertexesOfInterval2d (reference neptune/src/neptune.cpp:224-267, :269-285, :288-325, :349-452) with
+// cu::convexHullOfPoints2d (cgal_utils.cpp:157-174), and Neptune::SamplePointsOfCurves /
+// SamplePointsOfIntervals (neptune.cpp:463-498, :500-566).  One thread per (planning agent, other
+// agent, window).  The hull is Andrew's monotone chain on the same operands and in the same operation
+// order as the oracle (no FMA contraction), so vertex sets, vertex order and interval indices are
+// bit-exact.  CGAL convention adopted: strict extreme points, counter-clockwise from the
+// lexicographically smallest point.
+//
+// K5 replaces Neptune::trajsAndPwpAreInCollision2d (neptune.cpp:767-806) with gjk::collision
+// (gjk.cpp:76-148), the geometric half of Neptune::safetyCheckAfterReplan (neptune.cpp:719-765).
+#pragma once
+#include "nb_common.cuh"
+
+#define NB_TP 16                           // pieces a committed trajectory can hold
+#define NB_REC (1 + (NB_TP + 1) + 3 * NB_TP * 4)  // doubles per committed-trajectory record
+#define NB_HMAX 24                         // vertices of an inflated hull (<= 4 + control points)
+#define NB_HPCS 4                          // pieces one window may overlap
+
+// committed-trajectory record (the all-gather payload): [0] n_pieces, [1..17] times, then coeff[3][16][4]
+NB_HD int nb_rec_np(const double* rec) { return (int)rec[0]; }
+NB_HD const double* nb_rec_times(const double* rec) { return rec + 1; }
+NB_HD const double* nb_rec_coeff(const double* rec, int ax) { return rec + 1 + (NB_TP + 1) + ax * NB_TP * 4; }
+
+#if defined(__CUDA_ARCH__)
+#define NB_MUL(a, b) __dmul_rn((a), (b))
+#define NB_ADD(a, b) __dadd_rn((a), (b))
+#define NB_SUB(a, b) __dsub_rn((a), (b))
+#else
+#define NB_MUL(a, b) ((a) * (b))
+#define NB_ADD(a, b) ((a) + (b))
+#define NB_SUB(a, b) ((a) - (b))
+#endif
+
+NB_HD double nb_cross3(const double* o, const double* a, const double* b)
+{
+  return NB_SUB(NB_MUL(NB_SUB(a[0], o[0]), NB_SUB(b[1], o[1])), NB_MUL(NB_SUB(a[1], o[1]), NB_SUB(b[0], o[0])));
+}
+
+NB_HD bool nb_pt_less(const double* p, const double* q) { return p[0] < q[0] || (p[0] == q[0] && p[1] < q[1]); }
+
+// strict convex hull of n points (destroys pts: sorted in place), CCW from the lexicographic minimum
+NB_HD int nb_convex_hull(double* pts, int n, double* out, int out_cap)
+{
+  for (int i = 1; i < n; i++)
+  {  // insertion sort, lexicographic
+    const double x = pts[2 * i], y = pts[2 * i + 1];
+    int j = i - 1;
+    while (j >= 0 && (x < pts[2 * j] || (x == pts[2 * j] && y < pts[2 * j + 1])))
+    {
+      pts[2 * j + 2] = pts[2 * j];
+      pts[2 * j + 3] = pts[2 * j + 1];
+      j--;
+    }
+    pts[2 * j + 2] = x;
+    pts[2 * j + 3] = y;
+  }
+  int m = 0;
+  for (int i = 0; i < n; i++)
+    if (m == 0 || pts[2 * i] != pts[2 * (m - 1)] || pts[2 * i + 1] != pts[2 * (m - 1) + 1])
+    {
+      pts[2 * m] = pts[2 * i];
+      pts[2 * m + 1] = pts[2 * i + 1];
+      m++;
+    }
+  if (m <= 2)
+  {
+    for (int i = 0; i < m && i < out_cap; i++) out[2 * i] = pts[2 * i], out[2 * i + 1] = pts[2 * i + 1];
+    return m;
+  }
+  // the chain is built in a scratch that can hold every point: reuse a local buffer
+  double h[2 * (4 * 4 * NB_HPCS + 2)];
+  int k = 0;
+  for (int i = 0; i < m; i++)
+  {
+    while (k >= 2 && nb_cross3(h + 2 * (k - 2), h + 2 * (k - 1), pts + 2 * i) <= 0) k--;
+    h[2 * k] = pts[2 * i], h[2 * k + 1] = pts[2 * i + 1];
+    k++;
+  }
+  for (int i = m - 2, t = k + 1; i >= 0; i--)
+  {
+    while (k >= t && nb_cross3(h + 2 * (k - 2), h + 2 * (k - 1), pts + 2 * i) <= 0) k--;
+    h[2 * k] = pts[2 * i], h[2 * k + 1] = pts[2 * i + 1];
+    k++;
+  }
+  k--;
+  const int kk = k < out_cap ? k : out_cap;
+  for (int i = 0; i < kk; i++) out[2 * i] = h[2 * i], out[2 * i + 1] = h[2 * i + 1];
+  return k;
+}
+
+NB_HD int nb_lower_bound(const double* a, int n, double v)
+{
+  int i = 0;
+  while (i < n && a[i] < v) i++;
+  return i;
+}
+NB_HD int nb_upper_bound(const double* a, int n, double v)
+{
+  int i = 0;
+  while (i < n && !(v < a[i])) i++;
+  return i;
+}
+NB_HD int nb_sat(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// MINVO control points of every piece overlapping [t0,t1] (neptune.cpp:379-448).  cps: [<=16][2].
+// idx = {index_first_interval, index_last_interval}.  Returns the number of control points, or -1
+// when the window overlaps more than NB_HPCS pieces.
+NB_HD int nb_window_ctrl_pts(const NbConsts& cs, const double* rec, double t0, double t1, double* cps, int* idx)
+{
+  const int np = nb_rec_np(rec), nt = np + 1;
+  const double* times = nb_rec_times(rec);
+  const double* cx = nb_rec_coeff(rec, 0);
+  const double* cy = nb_rec_coeff(rec, 1);
+  int first = nb_sat(nb_lower_bound(times, nt, t0) - 1, 0, np - 1);
+  int last = nb_sat(nb_upper_bound(times, nt, t1) - 1, 0, np - 1);
+  idx[0] = first;
+  idx[1] = last;
+  if (last - first + 1 > NB_HPCS) return -1;
+  int n = 0;
+  for (int i = first; i <= last; i++)
+  {
+    double t;
+    if (i != last)
+      t = NB_SUB(times[i + 1], times[i]);
+    else if (t1 > times[i + 1])
+      t = NB_SUB(times[i + 1], times[i]);
+    else
+      t = NB_SUB(t1, times[i]);
+    if (t > cs.T)
+      t = cs.T;
+    else if (t < 0)
+      t = 0;
+    const double sc[4] = { NB_MUL(NB_MUL(t, t), t), NB_MUL(t, t), t, 1.0 };
+    for (int k = 0; k < 4; k++)
+    {
+      double x = 0, y = 0;
+      for (int r = 0; r < 4; r++)
+      {
+        x = NB_ADD(x, NB_MUL(NB_MUL(cx[4 * i + r], sc[r]), cs.Ainv01[r * 4 + k]));
+        y = NB_ADD(y, NB_MUL(NB_MUL(cy[4 * i + r], sc[r]), cs.Ainv01[r * 4 + k]));
+      }
+      cps[2 * n] = x, cps[2 * n + 1] = y;
+      n++;
+    }
+  }
+  return n;
+}
+
+// Neptune::convexHullOfInterval2d (neptune.cpp:288-309): inflated hull + col(0) of the un-inflated one
+NB_HD int nb_hull_of_window(const NbConsts& cs, const double* rec, double t0, double t1, double delta, double* hull,
+                            double* nih0, int* idx)
+{
+  double cps[2 * 4 * NB_HPCS], pts[2 * 16 * NB_HPCS];
+  const int nc = nb_window_ctrl_pts(cs, rec, t0, t1, cps, idx);
+  if (nc < 0) return -1;
+  int best = 0, np = 0;
+  const double sx[4] = { 1, 1, -1, -1 }, sy[4] = { 1, -1, -1, 1 };
+  for (int q = 0; q < nc; q++)
+  {
+    if (nb_pt_less(cps + 2 * q, cps + 2 * best)) best = q;
+    for (int c = 0; c < 4; c++)
+    {
+      pts[2 * np] = NB_ADD(cps[2 * q], NB_MUL(sx[c], delta));
+      pts[2 * np + 1] = NB_ADD(cps[2 * q + 1], NB_MUL(sy[c], delta));
+      np++;
+    }
+  }
+  nih0[0] = cps[2 * best];  // first vertex of a CCW-from-lexicographic-minimum hull
+  nih0[1] = cps[2 * best + 1];
+  return nb_convex_hull(pts, np, hull, NB_HMAX);
+}
+
+// Neptune::SamplePointsOfIntervals (neptune.cpp:500-566): out [num_pol][S+1][2], idx [num_pol][S+1]
+NB_HD void nb_sample_points(const NbConsts& cs, const double* rec, double t_start, double t_end, double* out, int* idx_out)
+{
+  const int np = nb_rec_np(rec), nt = np + 1, S = cs.S;
+  const double* times = nb_rec_times(rec);
+  const double* cx = nb_rec_coeff(rec, 0);
+  const double* cy = nb_rec_coeff(rec, 1);
+  const double deltaT = NB_SUB(t_end, t_start) / (1.0 * cs.num_pol);
+  for (int i = 0; i < cs.num_pol; i++)
+    for (int j = 0; j <= S; j++)
+    {
+      const double ts = NB_ADD(NB_ADD(t_start, NB_MUL(deltaT, (double)i)), NB_MUL(deltaT / S, (double)j));
+      const int low = nb_upper_bound(times, nt, ts);
+      int ii;
+      double te;
+      if (low != nt)
+      {
+        ii = nb_sat(low - 1, 0, np - 1);
+        te = NB_SUB(ts, times[ii]);
+        if (te < 0)
+          te = 0;
+        else if (te > deltaT)
+          te = deltaT;
+      }
+      else
+      {
+        const int k = low - 1;
+        te = NB_SUB(times[k], times[k - 1]);
+        ii = k - 1;
+      }
+      const double tv[4] = { NB_MUL(NB_MUL(te, te), te), NB_MUL(te, te), te, 1.0 };
+      double x = 0, y = 0;
+      for (int r = 0; r < 4; r++)
+      {
+        x = NB_ADD(x, NB_MUL(cx[4 * ii + r], tv[r]));
+        y = NB_ADD(y, NB_MUL(cy[4 * ii + r], tv[r]));
+      }
+      out[(i * (S + 1) + j) * 2] = x;
+      out[(i * (S + 1) + j) * 2 + 1] = y;
+      if (idx_out) idx_out[i * (S + 1) + j] = ii;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ GJK
+NB_HD int nb_gjk_furthest(const double* v, int n, double dx, double dy)
+{
+  double best = NB_ADD(NB_MUL(dx, v[0]), NB_MUL(dy, v[1]));
+  int idx = 0;
+  for (int i = 1; i < n; i++)
+  {
+    const double p = NB_ADD(NB_MUL(dx, v[2 * i]), NB_MUL(dy, v[2 * i + 1]));
+    if (p > best)
+    {
+      best = p;
+      idx = i;
+    }
+  }
+  return idx;
+}
+NB_HD void nb_gjk_support(const double* v1, int n1, const double* v2, int n2, double dx, double dy, double* s)
+{
+  const int i = nb_gjk_furthest(v1, n1, dx, dy), j = nb_gjk_furthest(v2, n2, -dx, -dy);
+  s[0] = NB_SUB(v1[2 * i], v2[2 * j]);
+  s[1] = NB_SUB(v1[2 * i + 1], v2[2 * j + 1]);
+}
+NB_HD double nb_dot2(const double* a, const double* b) { return NB_ADD(NB_MUL(a[0], b[0]), NB_MUL(a[1], b[1])); }
+// b*(a.c) - a*(b.c)   (gjk.cpp:25-28)
+NB_HD void nb_gjk_triple(const double* a, const double* b, const double* c, double* r)
+{
+  const double ac = nb_dot2(a, c), bc = nb_dot2(b, c);
+  r[0] = NB_SUB(NB_MUL(b[0], ac), NB_MUL(a[0], bc));
+  r[1] = NB_SUB(NB_MUL(b[1], ac), NB_MUL(a[1], bc));
+}
+
+// gjk::collision (gjk.cpp:76-148)
+NB_HD bool nb_gjk_collision(const double* v1, int n1, const double* v2, int n2)
+{
+  double simplex[3][2], a[2], b[2], c[2], d[2], ao[2], ab[2], ac[2], abp[2], acp[2];
+  double p1[2] = { 0, 0 }, p2[2] = { 0, 0 };
+  int index = 0;
+  for (int i = 0; i < n1; i++) p1[0] = NB_ADD(p1[0], v1[2 * i]), p1[1] = NB_ADD(p1[1], v1[2 * i + 1]);
+  for (int i = 0; i < n2; i++) p2[0] = NB_ADD(p2[0], v2[2 * i]), p2[1] = NB_ADD(p2[1], v2[2 * i + 1]);
+  d[0] = NB_SUB(p1[0] / n1, p2[0] / n2);
+  d[1] = NB_SUB(p1[1] / n1, p2[1] / n2);
+  if (d[0] == 0 && d[1] == 0) d[0] = 1.0;
+  nb_gjk_support(v1, n1, v2, n2, d[0], d[1], simplex[0]);
+  a[0] = simplex[0][0], a[1] = simplex[0][1];
+  if (nb_dot2(a, d) <= 0) return false;
+  d[0] = -a[0], d[1] = -a[1];
+  for (int guard = 0; guard < 1000; guard++)
+  {
+    ++index;
+    nb_gjk_support(v1, n1, v2, n2, d[0], d[1], simplex[index]);
+    a[0] = simplex[index][0], a[1] = simplex[index][1];
+    if (nb_dot2(a, d) <= 0) return false;
+    ao[0] = -a[0], ao[1] = -a[1];
+    if (index < 2)
+    {
+      b[0] = simplex[0][0], b[1] = simplex[0][1];
+      ab[0] = NB_SUB(b[0], a[0]), ab[1] = NB_SUB(b[1], a[1]);
+      nb_gjk_triple(ab, ao, ab, d);
+      if (sqrt(NB_ADD(NB_MUL(d[0], d[0]), NB_MUL(d[1], d[1]))) == 0) d[0] = ab[1], d[1] = -ab[0];
+      continue;
+    }
+    b[0] = simplex[1][0], b[1] = simplex[1][1];
+    c[0] = simplex[0][0], c[1] = simplex[0][1];
+    ab[0] = NB_SUB(b[0], a[0]), ab[1] = NB_SUB(b[1], a[1]);
+    ac[0] = NB_SUB(c[0], a[0]), ac[1] = NB_SUB(c[1], a[1]);
+    nb_gjk_triple(ab, ac, ac, acp);
+    if (nb_dot2(acp, ao) >= 0)
+      d[0] = acp[0], d[1] = acp[1];
+    else
+    {
+      nb_gjk_triple(ac, ab, ab, abp);
+      if (nb_dot2(abp, ao) < 0) return true;
+      simplex[0][0] = simplex[1][0], simplex[0][1] = simplex[1][1];
+      d[0] = abp[0], d[1] = abp[1];
+    }
+    simplex[1][0] = simplex[2][0], simplex[1][1] = simplex[2][1];
+    --index;
+  }
+  return false;
+}
+
+// Neptune::trajsAndPwpAreInCollision2d (neptune.cpp:767-806): my optimised pwp (n intervals from
+// t_start) against one other agent's record.  Returns 1 collision, 0 free, -1 capacity.
+NB_HD int nb_pwp_collides(const NbConsts& cs, const double* coeff /*[3][8][4]*/, int n, double t_start, const double* rec,
+                          double delta)
+{
+  const double t_end = NB_ADD(t_start, NB_MUL(cs.T, (double)n));
+  const double deltaT = NB_SUB(t_end, t_start) / n;
+  if (fabs(NB_SUB(deltaT, cs.T)) > 0.1) return 1;  // :772-780
+  for (int i = 0; i < n; i++)
+  {
+    double A[8], hull[2 * NB_HMAX], nih0[2];
+    int idx[2];
+    for (int k = 0; k < 4; k++)
+    {  // pointsA = P * A_rest_pos_basis_t_inverse_  (:786-789)
+      double x = 0, y = 0;
+      for (int r = 0; r < 4; r++)
+      {
+        x = NB_ADD(x, NB_MUL(coeff[4 * i + r], cs.Ainv[r * 4 + k]));
+        y = NB_ADD(y, NB_MUL(coeff[32 + 4 * i + r], cs.Ainv[r * 4 + k]));
+      }
+      A[2 * k] = x, A[2 * k + 1] = y;
+    }
+    const double w0 = NB_ADD(t_start, NB_MUL(deltaT, (double)i)), w1 = NB_ADD(t_start, NB_MUL(deltaT, (double)(i + 1)));
+    const int hn = nb_hull_of_window(cs, rec, w0, w1, delta, hull, nih0, idx);
+    if (hn < 0) return -1;
+    if (nb_gjk_collision(hull, hn < NB_HMAX ? hn : NB_HMAX, A, 4)) return 1;
+  }
+  return 0;
+}

@@ -17,7 +17,8 @@ struct NbLinesIn
   const int* n_int;          // [B]
   const double* coeff_init;  // [B][3][8][4]
   int NH;
-  const int64_t* hull_ptr;   // [B*NH*8+1]
+  const int64_t* hull_ptr;   // [B*NH*8+1] (or [B*NH*8] with hull_cnt)
+  const int* hull_cnt;       // optional [B*NH*8]
   const double* hull_xy;
   const double* nih0;        // [B][N][8][2]
   const int64_t* st_ptr;     // [M+1]
@@ -79,8 +80,9 @@ NB_HD void nb_lines_task(int tid, int b, int i, const NbConsts& cs, const NbLine
     double l[3] = { 0, 0, 0 };
     if (s < NH)
     {  // other agents :477-495
-      const int64_t o0 = in.hull_ptr[((size_t)b * NH + s) * 8 + i], o1 = in.hull_ptr[((size_t)b * NH + s) * 8 + i + 1];
-      const int cnt = (int)(o1 - o0);
+      const size_t hk = ((size_t)b * NH + s) * 8 + i;
+      const int64_t o0 = in.hull_ptr[hk];
+      const int cnt = in.hull_cnt ? in.hull_cnt[hk] : (int)(in.hull_ptr[hk + 1] - o0);
       if (cnt > 0) res = nb_separate(in.hull_xy + 2 * o0, cnt, true, cp, 4, l) ? 1 : 2;
     }
     else if (s < NH + N)

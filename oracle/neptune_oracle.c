@@ -622,6 +622,41 @@ int orc_gjk_collision(const double* v1, int n1, const double* v2, int n2)
   return 0;
 }
 
+/*
+ * Neptune::trajsAndPwpAreInCollision2d (neptune.cpp:767-806): my optimised pwp (n intervals of
+ * length T_span from t_start) against another agent's trajectory; per interval the GJK test of my
+ * MINVO control points (P * A_rest_pos_basis_t_inverse_, :789) against the other's inflated hull.
+ */
+int orc_pwp_collides(const double* coeff, int n, double t_start, double T_span, const double* times, int nt,
+                     const double* cx, const double* cy, const double delta[3])
+{
+  double Ainv[16], V[9];
+  orc_basis(T_span, Ainv, V, 0);
+  const double t_end = t_start + T_span * n;
+  const double deltaT = (t_end - t_start) / n;
+  if (fabs(deltaT - T_span) > 0.1) return 1; /* :772-780 */
+  for (int i = 0; i < n; i++)
+  {
+    double A[8], hull[2 * ORC_HMAX];
+    int hn, idx[2];
+    for (int k = 0; k < 4; k++)
+    {
+      double x = 0, y = 0;
+      for (int r = 0; r < 4; r++)
+      {
+        x += coeff[4 * i + r] * Ainv[r * 4 + k];
+        y += coeff[32 + 4 * i + r] * Ainv[r * 4 + k];
+      }
+      A[2 * k] = x;
+      A[2 * k + 1] = y;
+    }
+    orc_hull_of_interval(times, nt, cx, cy, t_start + deltaT * i, t_start + deltaT * (i + 1), T_span, delta, hull, &hn,
+                         0, 0, idx);
+    if (orc_gjk_collision(hull, hn, A, 4)) return 1;
+  }
+  return 0;
+}
+
 /* ------------------------------------------------------------------------- */
 /* entanglement chain                                                         */
 /* ------------------------------------------------------------------------- */

@@ -70,6 +70,10 @@ void orc_sample_interval_points(const double* times, int nt, const double* cx, c
 /* ---- GJK: gjk.cpp:76-148 ---- */
 int orc_gjk_collision(const double* v1, int n1, const double* v2, int n2);
 
+/* Neptune::trajsAndPwpAreInCollision2d neptune.cpp:767-806 */
+int orc_pwp_collides(const double* coeff /*[3][8][4]*/, int n, double t_start, double T_span, const double* times,
+                     int nt, const double* cx, const double* cy, const double delta[3]);
+
 /* ---- entanglement chain: entangle_utils.cpp:1129-1722 ---- */
 typedef struct orc_ent
 {

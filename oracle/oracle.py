@@ -154,6 +154,15 @@ def gjk_collision(v1, v2) -> bool:
     return bool(lib().orc_gjk_collision(_p(v1), C.c_int(v1.shape[0]), _p(v2), C.c_int(v2.shape[0])))
 
 
+def pwp_collides(coeff, n, t_start, T_span, times, cx, cy, delta) -> bool:
+    coeff, times, cx, cy = _c(coeff, np.float64), _c(times, np.float64), _c(cx, np.float64), _c(cy, np.float64)
+    delta = _c(delta, np.float64)
+    f = lib().orc_pwp_collides
+    f.restype = C.c_int
+    return bool(f(_p(coeff), C.c_int(n), C.c_double(t_start), C.c_double(T_span), _p(times), C.c_int(times.shape[0]),
+                  _p(cx), _p(cy), _p(delta)))
+
+
 def generate_traj(coeff, n, T, dc):
     coeff = _c(coeff, np.float64)
     mx = int(n * T / dc) + 8

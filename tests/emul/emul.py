@@ -43,3 +43,26 @@ def separate(A, B, a_polygon):
     ok = lib().emul_separate(A.ctypes.data_as(C.c_void_p), len(A), int(a_polygon), B.ctypes.data_as(C.c_void_p), len(B),
                              out.ctypes.data_as(C.c_void_p))
     return bool(ok), out
+
+
+def hulls(par, t_start, recs, known, delta):
+    from neptune_b200.capi import _hulls_impl
+    nbp = make_nb_params(par)
+
+    def call(B, ts, rc, kn, dl, hx, hc, hp, n0, sm, ix):
+        f = lib().emul_hulls
+        f.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3 + [C.c_double] + [C.c_void_p] * 6
+        assert f(C.addressof(nbp), B, ts, rc, kn, dl, hx, hc, hp, n0, sm, ix) == 0
+    return _hulls_impl(call, par, t_start, recs, known, delta)
+
+
+def postcheck(par, n_int, coeff, t_start, recs, late, delta):
+    nbp = make_nb_params(par)
+    arrs = [np.ascontiguousarray(n_int, np.int32), np.ascontiguousarray(coeff, np.float64),
+            np.ascontiguousarray(t_start, np.float64), np.ascontiguousarray(recs, np.float64),
+            np.ascontiguousarray(late, np.uint8)]
+    col = np.zeros(len(arrs[0]), np.int32)
+    f = lib().emul_postcheck
+    f.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_double, C.c_void_p]
+    f(C.addressof(nbp), len(arrs[0]), *[a.ctypes.data_as(C.c_void_p) for a in arrs], delta, col.ctypes.data_as(C.c_void_p))
+    return col

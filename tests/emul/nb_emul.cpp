@@ -42,7 +42,7 @@ extern "C" int emul_replan_batch(const nb_params* par, const double* pb, const i
   const int RS = 6 * NB_NFEAT_AX + 4 * NB_NPOL * LS;
   NbLinesIn in;
   in.agent_id = a->agent_id, in.n_int = a->n_int, in.coeff_init = a->coeff_init, in.NH = NH;
-  in.hull_ptr = a->hull_ptr, in.hull_xy = a->hull_xy, in.nih0 = a->nih0, in.st_ptr = st_ptr, in.st_xy = st_xy;
+  in.hull_ptr = a->hull_ptr, in.hull_cnt = a->hull_cnt, in.hull_xy = a->hull_xy, in.nih0 = a->nih0, in.st_ptr = st_ptr, in.st_xy = st_xy;
   in.esv_cnt = a->esv_cnt, in.esv_alpha = a->esv_alpha, in.esv_active = a->esv_active;
   in.bp_cnt = a->bp_cnt, in.bp_xy = a->bp_xy, in.pb = pb;
   std::vector<double> lines((size_t)NB_NPOL * LS * 3), cl((size_t)NB_NPOL * LS * 3), rows((size_t)4 * RS);
@@ -128,4 +128,55 @@ extern "C" int emul_entangle(const nb_params* par, const double* pb, const doubl
   Group<1> g(0);
   for (int b = 0; b < B; b++) nb_entangle_task<1>(g, b, a, toadd.data(), toadd.data() + 2 * a.tcap);
   return err ? NB_ERR_CAPACITY : 0;
+}
+
+#include "../../neptune_b200/csrc/nb_hull.cuh"
+
+extern "C" int emul_hulls(const nb_params* par, int B, const double* t_start, const double* recs, const uint8_t* known,
+                          double delta, double* hull_xy, int32_t* hull_cnt, int64_t* hull_ptr, double* nih0, double* samp,
+                          int32_t* idx)
+{
+  NbConsts cs;
+  nb_build_consts(par, &cs);
+  int err = 0;
+  for (int b = 0; b < B; b++)
+    for (int j = 0; j < cs.N; j++)
+    {
+      for (int i = 0; i < NB_NPOL; i++)
+      {
+        const size_t k = ((size_t)b * cs.N + j) * NB_NPOL + i;
+        hull_ptr[k] = (int64_t)k * NB_HMAX;
+        int cnt = 0, id2[2] = { -1, -1 };
+        double n0[2] = { NAN, NAN };
+        if (i < cs.num_pol && known[(size_t)b * cs.N + j])
+        {
+          const double t0 = t_start[b] + (double)i * cs.T, t1 = t_start[b] + (double)(i + 1) * cs.T;
+          cnt = nb_hull_of_window(cs, recs + (size_t)j * NB_REC, t0, t1, delta, hull_xy + k * NB_HMAX * 2, n0, id2);
+          if (cnt < 0 || cnt > NB_HMAX) err = 3, cnt = 0;
+        }
+        hull_cnt[k] = cnt;
+        nih0[2 * k] = n0[0], nih0[2 * k + 1] = n0[1];
+        if (idx) idx[2 * k] = id2[0], idx[2 * k + 1] = id2[1];
+      }
+      double* out = samp + ((size_t)b * cs.N + j) * cs.num_pol * (cs.S + 1) * 2;
+      if (known[(size_t)b * cs.N + j])
+        nb_sample_points(cs, recs + (size_t)j * NB_REC, t_start[b], t_start[b] + cs.T * (double)cs.num_pol, out, nullptr);
+    }
+  return err ? NB_ERR_CAPACITY : 0;
+}
+
+extern "C" int emul_postcheck(const nb_params* par, int B, const int32_t* n_int, const double* coeff, const double* t_start,
+                              const double* recs, const uint8_t* late, double delta, int32_t* collide)
+{
+  NbConsts cs;
+  nb_build_consts(par, &cs);
+  for (int b = 0; b < B; b++)
+  {
+    collide[b] = 0;
+    for (int j = 0; j < cs.N; j++)
+      if (late[(size_t)b * cs.N + j] &&
+          nb_pwp_collides(cs, coeff + (size_t)b * 96, n_int[b], t_start[b], recs + (size_t)j * NB_REC, delta) > 0)
+        collide[b] = 1;
+  }
+  return 0;
 }

@@ -120,3 +120,55 @@ def test_entangle_chain_bit_exact(capi, oracle, cfg, seeds):
         for x, y in zip(g, r):
             assert np.array_equal(x, y)
         s.close()
+
+
+@pytest.mark.parametrize("cfg,seed", [("mtlp5", 2002), ("obst8", 3003), ("mtlp5", 2004)])
+def test_hulls_samples_postcheck_bit_exact(capi, oracle, cfg, seed):
+    """K1 / K5 vs oracle: hull vertices and order, vertex counts, interval indices, nih0 and samples
+    bit-exact (same operands, same operation order, no FMA contraction); collision flags equal."""
+    par = config(cfg)
+    sc = make_scene(par, seed, sync=False)
+    s = _solver(capi, par, sc)
+    recs = capi.make_records(sc.committed)
+    delta = 2 * par.drone_radius
+    out = s.hulls(sc.t_start, recs, sc.known, delta)
+    b = sc.batch
+    for bi in range(b.B):
+        for j in range(par.num_of_agents):
+            if not sc.known[bi, j]:
+                assert out["hull_cnt"][bi, j].sum() == 0 and np.isnan(out["nih0"][bi, j]).all()
+                continue
+            tm, cx, cy, _ = sc.committed[j]
+            for i in range(par.num_pol):
+                t0 = sc.t_start[bi] + i * par.T_span
+                h, h2, idx = oracle.hull_of_interval(tm, cx, cy, t0, sc.t_start[bi] + (i + 1) * par.T_span, par.T_span, [delta] * 3)
+                c = out["hull_cnt"][bi, j, i]
+                assert c == len(h) and np.array_equal(out["hull_xy"][bi, j, i, :c], h)
+                assert np.array_equal(out["nih0"][bi, j, i], h2[0])
+                assert np.array_equal(out["idx"][bi, j, i], idx)
+            smp, _ = oracle.sample_points(tm, cx, cy, sc.t_start[bi], sc.t_start[bi] + par.T_span * par.num_pol,
+                                          par.num_pol, par.num_sample_per_interval)
+            assert np.array_equal(out["samp"][bi, j], smp)
+    # device-generated hulls straight into the back end == oracle on the packed scene hulls
+    import ctypes as C
+    res = ReplanResult.empty(b)
+    a = capi.host_args(b, res)
+    hx, hc, hp, n0 = (np.ascontiguousarray(out[k]) for k in ("hull_xy", "hull_cnt", "hull_ptr", "nih0"))
+    a.hull_xy, a.hull_cnt, a.hull_ptr, a.nih0 = (x.ctypes.data_as(C.c_void_p) for x in (hx, hc, hp, n0))
+    a.hull_nvert = hx.shape[0] * hx.shape[1] * hx.shape[2] * hx.shape[3]
+    s.replan_args(a)
+    ref = ReplanResult.empty(b)
+    assert oracle.replan_batch(b, ref, 1) == 0
+    assert (res.line_ok == ref.line_ok).all() and (res.status == ref.status).all()
+    assert np.abs(res.coeff_out - ref.coeff_out).max() <= 1e-6 * max(1.0, np.abs(ref.coeff_out).max())
+    # post-check of the optimised trajectories against everybody's committed trajectory
+    col = s.postcheck(b.n_int, res.coeff_out, sc.t_start, recs, sc.known, delta)
+    want = np.zeros(b.B, np.int32)
+    for bi in range(b.B):
+        for j in range(par.num_of_agents):
+            if sc.known[bi, j]:
+                tm, cx, cy, _ = sc.committed[j]
+                if oracle.pwp_collides(res.coeff_out[bi], int(b.n_int[bi]), sc.t_start[bi], par.T_span, tm, cx, cy, [delta] * 3):
+                    want[bi] = 1
+    assert np.array_equal(col, want)
+    s.close()
