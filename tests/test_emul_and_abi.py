@@ -1,0 +1,122 @@
+"""CPU: host logic, the C-ABI surface, and the device kernels compiled for one host lane
+(tests/emul: a debugging harness, not a fallback) against the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from neptune_b200 import capi, config
+from neptune_b200.batch import ReplanResult
+from neptune_b200.scenes import make_scene
+from tests.golden_util import golden_files, load
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    """libneptune_b200.so loads without a GPU and exports every function include/neptune_b200.h declares."""
+    if not os.path.exists(capi.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = C.CDLL(capi.LIB_PATH)
+    hdr = open(os.path.join(ROOT, "include", "neptune_b200.h")).read()
+    names = set(re.findall(r"\b(nb_[a-z_0-9]+)\s*\(", hdr))
+    assert {"nb_create", "nb_replan_batch", "nb_separate_batch", "nb_entangle_predict_batch", "nb_hulls_batch",
+            "nb_postcheck_batch", "nb_destroy"} <= names
+    for n in sorted(names):
+        assert hasattr(lib, n), n
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device nb_create must fail loudly (NB_ERR_NO_DEVICE), never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.NbError):
+        capi.Solver(config("mtlp5"))
+
+
+def test_product_does_not_touch_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "neptune_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("oracle/", "ORC").replace("Oracle", "") or \
+                    "import oracle" not in src and "from oracle" not in src
+                assert "from oracle" not in src and "import oracle" not in src and "liboracle" not in src
+
+
+@pytest.mark.parametrize("path", golden_files())
+def test_emulated_kernels_match_golden(path):
+    from tests.emul import emul
+    par, b, z = load(path)
+    got = emul.replan(b)
+    assert np.array_equal(got.line_ok, z["orc_line_ok"])
+    m = z["orc_line_ok"] == 1
+    assert np.abs(got.lines[m] - z["orc_lines"][m]).max(initial=0) <= 1e-9 * max(1.0, np.abs(z["orc_lines"][m]).max(initial=0))
+    assert np.array_equal(got.status, z["orc_status"])
+    assert np.abs(got.coeff_out - z["orc_coeff"]).max() <= 1e-6 * max(1.0, np.abs(z["orc_coeff"]).max())
+    assert np.abs(got.obj - z["orc_obj"]).max() <= 1e-8 * max(1.0, np.abs(z["orc_obj"]).max())
+
+
+def test_emulated_pruning_is_exact(oracle):
+    """Dropping redundant lines must not change the optimum: pruned vs unpruned vs oracle (all rows)."""
+    from tests.emul import emul
+    par = config("obst8")
+    sc = make_scene(par, 3005, sync=False)
+    n0, n1 = np.zeros(sc.batch.B, np.int32), np.zeros(sc.batch.B, np.int32)
+    full = emul.replan(sc.batch, prune=False, n_lines=n0)
+    pruned = emul.replan(sc.batch, prune=True, n_lines=n1)
+    ref = ReplanResult.empty(sc.batch)
+    oracle.replan_batch(sc.batch, ref, 2)
+    assert (n1 <= n0).all() and n1.sum() < n0.sum()
+    assert np.array_equal(full.status, ref.status) and np.array_equal(pruned.status, ref.status)
+    assert np.abs(pruned.coeff_out - ref.coeff_out).max() <= 1e-6
+    assert np.abs(full.coeff_out - ref.coeff_out).max() <= 1e-6
+
+
+def test_emulated_entangle_hulls_postcheck(oracle):
+    from tests.emul import emul
+    from tests.ent_backends import EmulEntBackend, OracleEntBackend
+    par = config("obst8")
+    ref = make_scene(par, 3004, sync=False, ent_backend=OracleEntBackend(oracle))
+    got = make_scene(par, 3004, sync=False, ent_backend=EmulEntBackend())
+    for k in ("es0_cnt", "es0_alpha", "es0_beta", "es0_bend", "es0_active", "esA_cnt", "esA_alpha", "esA_beta",
+              "esA_bend", "esA_active"):
+        assert np.array_equal(getattr(got, k), getattr(ref, k)), k
+    for k in ("esv_cnt", "esv_alpha", "esv_active"):
+        assert np.array_equal(getattr(got.batch, k), getattr(ref.batch, k)), k
+    assert ref.es0_cnt[:, 0].sum() > 0  # the history walk did produce signature entries
+    recs = capi.make_records(ref.committed)
+    delta = 2 * par.drone_radius
+    out = emul.hulls(par, ref.t_start, recs, ref.known, delta)
+    for bi in range(ref.batch.B):
+        for j in range(par.num_of_agents):
+            if not ref.known[bi, j]:
+                continue
+            tm, cx, cy, _ = ref.committed[j]
+            for i in range(par.num_pol):
+                h, h2, idx = oracle.hull_of_interval(tm, cx, cy, ref.t_start[bi] + i * par.T_span,
+                                                     ref.t_start[bi] + (i + 1) * par.T_span, par.T_span, [delta] * 3)
+                c = out["hull_cnt"][bi, j, i]
+                assert c == len(h) and np.array_equal(out["hull_xy"][bi, j, i, :c], h)
+                assert np.array_equal(out["idx"][bi, j, i], idx) and np.array_equal(out["nih0"][bi, j, i], h2[0])
+    col = emul.postcheck(par, ref.batch.n_int, ref.batch.coeff_init, ref.t_start, recs, ref.known, delta)
+    want = np.zeros(ref.batch.B, np.int32)
+    for bi in range(ref.batch.B):
+        for j in range(par.num_of_agents):
+            if ref.known[bi, j]:
+                tm, cx, cy, _ = ref.committed[j]
+                if oracle.pwp_collides(ref.batch.coeff_init[bi], int(ref.batch.n_int[bi]), ref.t_start[bi], par.T_span,
+                                       tm, cx, cy, [delta] * 3):
+                    want[bi] = 1
+    assert np.array_equal(col, want)
+
+
+def test_scene_is_deterministic_and_valid():
+    par = config("mtlp5")
+    a, b = make_scene(par, 2002, sync=False), make_scene(par, 2002, sync=False)
+    assert np.array_equal(a.batch.coeff_init, b.batch.coeff_init) and np.array_equal(a.batch.hull_xy, b.batch.hull_xy)
+    assert a.batch.algorithmic_bytes() > 0 and (a.batch.n_int >= 1).all()
