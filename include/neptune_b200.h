@@ -186,6 +186,15 @@ int nb_postcheck_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_
                        int32_t* collide, void* stream);
 
 /*
+ * Committed-trajectory records of this rank's agents for the all-gather: the pwp_now of
+ * PolySolverGurobi::generatePwpOut (times shifted by t_start, solver_gurobi_poly.cpp:892-907).
+ * recs_out [B][NB_REC_DOUBLES].  mu::composePieceWisePol with the previous plan (utils.cpp:318-402) is
+ * SURVEY section 8(f) "next #2" and not applied here.
+ */
+int nb_commit_records_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
+                            const double* t_start, double* recs_out, void* stream);
+
+/*
  * Entanglement-signature chain, batched (one agent per warp).  State = eu::ent_state
  * (neptune/include/entangle_utils.hpp:23-29) with fixed storage: cnt [B][2] = (alphas.size(),
  * bendPointsIdx.size()), alpha [B][ent_cap][2], beta [B][ent_cap], bend [B][ent_cap], active [B][N+M].

@@ -304,6 +304,31 @@ __global__ void k_postcheck(NbConsts cs, int B, const int* n_int, const double* 
   if (r > 0) atomicOr(collide + b, 1);
 }
 
+__global__ void k_commit(int B, const int* n_int, const double* coeff, const double* t_start, double T, double* recs)
+{
+  const int b = blockIdx.x;
+  if (b >= B) return;
+  double* r = recs + (size_t)b * NB_REC;
+  const int n = n_int[b];
+  for (int q = threadIdx.x; q < NB_REC; q += blockDim.x)
+  {
+    double v = 0.0;
+    if (q == 0)
+      v = (double)n;
+    else if (q <= NB_TP + 1)
+    {
+      const int k = q - 1;
+      v = k <= n ? NB_ADD(t_start[b], NB_MUL((double)k, T)) : 0.0;  // pwp_out.times[i] += t_start (:898)
+    }
+    else
+    {
+      const int e = q - (NB_TP + 2), ax = e / (NB_TP * 4), rem = e % (NB_TP * 4), piece = rem / 4, c = rem % 4;
+      v = piece < n ? coeff[(size_t)b * 96 + ax * 32 + piece * 4 + c] : 0.0;
+    }
+    r[q] = v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ ABI
 
 extern "C" int nb_create(const nb_params* par, const double* pb, int device, nb_handle** out)
@@ -939,6 +964,32 @@ extern "C" int nb_postcheck_batch(nb_handle* h, int32_t B, int32_t space, const 
   if (space == NB_HOST)
   {
     NB_CUDA(cudaMemcpyAsync(collide, dcol, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaStreamSynchronize(st));
+  }
+  return NB_OK;
+}
+
+extern "C" int nb_commit_records_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
+                                       const double* t_start, double* recs_out, void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int* dn;
+  const double *dc, *dt;
+  double* dr;
+  int rc;
+  if ((rc = stage_in(h, 0, space, n_int, (size_t)B, st, &dn))) return rc;
+  if ((rc = stage_in(h, 1, space, coeff, (size_t)B * 96, st, &dc))) return rc;
+  if ((rc = stage_in(h, 2, space, t_start, (size_t)B, st, &dt))) return rc;
+  if ((rc = stage_out(h, 0, space, recs_out, (size_t)B * NB_REC, &dr))) return rc;
+  k_commit<<<B, 64, 0, st>>>(B, dn, dc, dt, h->cs.T, dr);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
+  if (space == NB_HOST)
+  {
+    NB_CUDA(cudaMemcpyAsync(recs_out, dr, (size_t)B * NB_REC * sizeof(double), cudaMemcpyDeviceToHost, st));
     NB_CUDA(cudaStreamSynchronize(st));
   }
   return NB_OK;

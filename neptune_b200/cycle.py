@@ -1,0 +1,203 @@
+"""One replan cycle for the agents of one rank: host-side mirror of ``Neptune::replanFull``'s hot part
+(reference ``neptune/src/neptune.cpp:1430-1448`` hulls/samples + PredictAlphasBetas, ``:1512-1529``
+back end, ``:1641-1647`` post-check) and of the inter-agent exchange (ROS topic ``/trajs``,
+``neptune_ros.cpp:172-179, :434-480``) as ONE all-gather of committed-trajectory records per cycle.
+
+PyTorch is used for device memory, streams and ``torch.distributed`` only; all math runs in
+libneptune_b200.so through the C-ABI with device pointers.  The front end (the kinodynamic search that
+produces ``pwp_init`` / ``entStateVec``) is out of scope: its outputs are inputs here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .batch import NPOL
+from .params import Params
+
+REC = capi.NB_REC_DOUBLES
+HS = capi.NB_HULL_STRIDE
+
+
+def shard_agents(n_agents: int, world: int, rank: int) -> np.ndarray:
+    """Block partition of agent indices (0-based) over ranks; the last ranks may own one agent less."""
+    base, extra = divmod(n_agents, world)
+    start = rank * base + min(rank, extra)
+    return np.arange(start, start + base + (1 if rank < extra else 0))
+
+
+def gather_records(local, world: int, group=None, sizes=None):
+    """All-gather of fixed-stride committed-trajectory records: [B_r][REC] per rank -> [sum B_r][REC]
+    in rank order.  Works on CUDA tensors (NCCL over NVLink) and CPU tensors (gloo, used by the tests).
+    sizes: per-rank record counts when the shards are uneven."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return local
+    local = local.contiguous()
+    if sizes is None or len(set(sizes)) == 1:
+        out = torch.empty((world * local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+    # uneven shards: pad to the largest shard (collectives need equal sizes), gather, drop the padding
+    mx = max(sizes)
+    pad = torch.zeros((mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((world * mx,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return torch.cat([out[r * mx:r * mx + sizes[r]] for r in range(world)], dim=0)
+
+
+class ReplanCycle:
+    """Device-resident state and launch sequence of one rank."""
+
+    def __init__(self, par: Params, agents: np.ndarray, device, static=None, world: int = 1, group=None):
+        import torch
+        self.torch = torch
+        self.par, self.agents, self.world, self.group = par, np.asarray(agents), world, group
+        self.dev = torch.device(device)
+        self.B, self.N = len(agents), par.num_of_agents
+        self.solver = capi.Solver(par, device=self.dev.index or 0)
+        if par.num_of_static_obst:
+            st_ptr, st_xy, strep = static
+            self.solver.set_static(st_ptr, st_xy, strep)
+        B, N, S, cap, NA = self.B, self.N, par.num_sample_per_interval, par.ent_cap, par.NA
+        f64, i32, u8, i64 = torch.float64, torch.int32, torch.uint8, torch.int64
+
+        def z(shape, dt):
+            return torch.zeros(shape, dtype=dt, device=self.dev)
+        # inputs of a cycle
+        self.d = dict(
+            agent_id=z(B, i32), n_int=z(B, i32), coeff_init=z((B, 3, NPOL, 4), f64), t_start=z(B, f64),
+            recs=z((N, REC), f64), known=z((B, N), u8), late=z((B, N), u8),
+            esv_cnt=z((B, NPOL + 1, 2), i32), esv_alpha=z((B, NPOL + 1, cap, 2), i32), esv_active=z((B, NPOL + 1, NA), i32),
+            bp_cnt=z(N, i32), bp_xy=z((N, par.bp_max, 2), f64),
+            es_cnt=z((B, 2), i32), es_alpha=z((B, cap, 2), i32), es_beta=z((B, cap), f64), es_bend=z((B, cap), i32),
+            es_active=z((B, NA), i32), prev_pos=z((B, N + 1, 2), f64), prev_pos_agent=z((B, N, 2), f64), cur=z((B, 2), f64))
+        # intermediates and outputs
+        self.o = dict(
+            hull_xy=z((B, N, NPOL, HS, 2), f64), hull_cnt=z((B, N, NPOL), i32), hull_ptr=z(B * N * NPOL, i64),
+            nih0=z((B, N, NPOL, 2), f64), samp=z((B, N, par.num_pol, S + 1, 2), f64), samp0=z((B, N, 2), f64),
+            esA_cnt=z((B, 2), i32), esA_alpha=z((B, cap, 2), i32), esA_beta=z((B, cap), f64), esA_bend=z((B, cap), i32),
+            esA_active=z((B, NA), i32),
+            esC_cnt=z((B, 2), i32), esC_alpha=z((B, cap, 2), i32), esC_beta=z((B, cap), f64), esC_bend=z((B, cap), i32),
+            esC_active=z((B, NA), i32),
+            coeff_out=z((B, 3, NPOL, 4), f64), obj=z(B, f64), status=z(B, i32), iters=z((B, 2), i32),
+            entangled=z(B, i32), collide=z(B, i32), new_recs=z((B, REC), f64))
+        self.gathered = None
+        self.delta = 2.0 * par.drone_radius  # bbox/2 + drone_radius with bbox = 2 drone_radius (neptune_ros.cpp:447-449)
+        self._lib = capi.lib()
+        self._sig()
+        self.pinned = None
+
+    def _sig(self):
+        P, L = C.c_void_p, self._lib
+        L.nb_hulls_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, C.c_double, P, P, P, P, P, P, P]
+        L.nb_entangle_predict_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, capi.NbEntState, P, P, P, P, P]
+        L.nb_entangle_check_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, capi.NbEntState, P, P, P, C.c_int32, P, P]
+        L.nb_postcheck_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, P, C.c_double, P, P]
+        L.nb_commit_records_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, P]
+
+    # ------------------------------------------------------------------ host <-> device
+    HOST_KEYS = ("agent_id", "n_int", "coeff_init", "t_start", "recs", "known", "late", "esv_cnt", "esv_alpha",
+                 "esv_active", "bp_cnt", "bp_xy", "es_cnt", "es_alpha", "es_beta", "es_bend", "es_active", "prev_pos",
+                 "prev_pos_agent", "cur")
+    OUT_KEYS = ("coeff_out", "obj", "status", "iters", "entangled", "collide")
+
+    def host_inputs(self, scene) -> dict:
+        """Pinned host copies of everything a cycle needs from the planner core / front end."""
+        torch = self.torch
+        b = scene.batch
+        src = dict(agent_id=b.agent_id, n_int=b.n_int, coeff_init=b.coeff_init, t_start=scene.t_start,
+                   recs=capi.make_records(scene.committed), known=scene.known, late=scene.known,
+                   esv_cnt=b.esv_cnt, esv_alpha=b.esv_alpha, esv_active=b.esv_active, bp_cnt=b.bp_cnt, bp_xy=b.bp_xy,
+                   es_cnt=scene.es0_cnt, es_alpha=scene.es0_alpha, es_beta=scene.es0_beta, es_bend=scene.es0_bend,
+                   es_active=scene.es0_active, prev_pos=scene.prev_pos, prev_pos_agent=scene.prev_pos_agent,
+                   cur=np.ascontiguousarray(scene.state_A[:, 0, :2]))
+        out = {}
+        for k in self.HOST_KEYS:
+            t = torch.from_numpy(np.ascontiguousarray(src[k]).astype(
+                {torch.float64: np.float64, torch.int32: np.int32, torch.uint8: np.uint8}[self.d[k].dtype]))
+            out[k] = t.pin_memory() if torch.cuda.is_available() else t
+        return out
+
+    def upload(self, host: dict) -> int:
+        n = 0
+        for k in self.HOST_KEYS:
+            self.d[k].copy_(host[k], non_blocking=True)
+            n += host[k].numel() * host[k].element_size()
+        return n
+
+    def download(self, host_out: dict) -> int:
+        n = 0
+        for k in self.OUT_KEYS:
+            host_out[k].copy_(self.o[k], non_blocking=True)
+            n += host_out[k].numel() * host_out[k].element_size()
+        return n
+
+    def host_outputs(self) -> dict:
+        return {k: self.torch.empty_like(self.o[k], device="cpu").pin_memory() for k in self.OUT_KEYS}
+
+    # ------------------------------------------------------------------ the cycle
+    def step(self, exchange: bool = True):
+        """hulls/samples (K1) -> PredictAlphasBetas (K3) -> LPs + QP (K2, K4) -> post-check (K5, K3) ->
+        commit records -> all-gather.  Everything is enqueued on the current CUDA stream."""
+        torch, L, h, d, o, B = self.torch, self._lib, self.solver.handle, self.d, self.o, self.B
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+        DEV = capi.NB_DEVICE
+        chk = capi._check
+        chk(L.nb_hulls_batch(h, B, DEV, p(d["t_start"]), p(d["recs"]), p(d["known"]), self.delta, p(o["hull_xy"]),
+                             p(o["hull_cnt"]), p(o["hull_ptr"]), p(o["nih0"]), p(o["samp"]), None, st), "nb_hulls_batch")
+        # entangle_state_A = PredictAlphasBetas(entangle_state_)
+        for k in ("cnt", "alpha", "beta", "bend", "active"):
+            o["esA_" + k].copy_(d["es_" + k])
+        o["samp0"].copy_(o["samp"][:, :, 0, 0, :])
+        esA = capi.NbEntState()
+        esA.cnt, esA.alpha, esA.beta, esA.bend, esA.active = (p(o["esA_" + k]) for k in ("cnt", "alpha", "beta", "bend", "active"))
+        chk(L.nb_entangle_predict_batch(h, B, DEV, p(d["agent_id"]), p(d["known"]), p(d["bp_cnt"]), p(d["bp_xy"]), esA,
+                                        p(d["prev_pos"]), p(d["prev_pos_agent"]), p(d["cur"]), p(o["samp0"]), st),
+            "nb_entangle_predict_batch")
+        a = capi.NbReplanArgs()
+        a.B, a.space, a.n_hull_slots = B, DEV, self.N
+        a.agent_id, a.n_int, a.coeff_init = d["agent_id"].data_ptr(), d["n_int"].data_ptr(), d["coeff_init"].data_ptr()
+        a.hull_ptr, a.hull_xy, a.hull_cnt = o["hull_ptr"].data_ptr(), o["hull_xy"].data_ptr(), o["hull_cnt"].data_ptr()
+        a.hull_nvert = B * self.N * NPOL * HS
+        a.nih0 = o["nih0"].data_ptr()
+        a.esv_cnt, a.esv_alpha, a.esv_active = d["esv_cnt"].data_ptr(), d["esv_alpha"].data_ptr(), d["esv_active"].data_ptr()
+        a.bp_cnt, a.bp_xy = d["bp_cnt"].data_ptr(), d["bp_xy"].data_ptr()
+        a.coeff_out, a.obj, a.status, a.iters = (o[k].data_ptr() for k in ("coeff_out", "obj", "status", "iters"))
+        a.lines, a.line_ok = None, None
+        chk(L.nb_replan_batch(h, C.byref(a), st), "nb_replan_batch")
+        # safetyCheckAfterReplan: geometric check against the late trajectories, then the entangle re-check
+        chk(L.nb_postcheck_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["t_start"]), p(d["recs"]), p(d["late"]),
+                                 self.delta, p(o["collide"]), st), "nb_postcheck_batch")
+        if self.par.enable_entangle_check:
+            # entangleCheckGivenPwp works on a copy (ent_state_begin is a local in safetyCheckAfterReplan)
+            esC = capi.NbEntState()
+            for k in ("cnt", "alpha", "beta", "bend", "active"):
+                o["esC_" + k].copy_(o["esA_" + k])
+            esC.cnt, esC.alpha, esC.beta, esC.bend, esC.active = (p(o["esC_" + k]) for k in ("cnt", "alpha", "beta", "bend", "active"))
+            chk(L.nb_entangle_check_batch(h, B, DEV, p(d["agent_id"]), p(d["known"]), p(d["bp_cnt"]), p(d["bp_xy"]), esC,
+                                          p(d["n_int"]), p(o["coeff_out"]), p(o["samp"]), 0, p(o["entangled"]), st),
+                "nb_entangle_check_batch")
+        chk(L.nb_commit_records_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["t_start"]), p(o["new_recs"]), st),
+            "nb_commit_records_batch")
+        if exchange and self.world > 1:
+            sizes = [len(shard_agents(self.N, self.world, r)) for r in range(self.world)]
+            self.gathered = gather_records(o["new_recs"], self.world, self.group, sizes)
+        return o
+
+    def step_from_host(self, host_in: dict, host_out: dict, exchange: bool = True):
+        """End-to-end cycle: pinned host inputs -> device, all kernels, results back to the host."""
+        h2d = self.upload(host_in)
+        self.step(exchange)
+        d2h = self.download(host_out)
+        self.torch.cuda.current_stream().synchronize()
+        return h2d, d2h
+
+    def check_errors(self):
+        st = C.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+        capi._check(self._lib.nb_check_async_errors(self.solver.handle, st), "nb_check_async_errors")

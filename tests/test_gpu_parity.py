@@ -172,3 +172,48 @@ def test_hulls_samples_postcheck_bit_exact(capi, oracle, cfg, seed):
                     want[bi] = 1
     assert np.array_equal(col, want)
     s.close()
+
+
+@pytest.mark.parametrize("cfg,seed", [("mtlp5", 2005), ("obst8", 3004)])
+def test_replan_cycle_matches_oracle_composite(capi, oracle, cfg, seed):
+    """The whole device-resident cycle (K1 -> K3 predict -> K2/K4 -> K5 + K3 check -> commit) against
+    the same chain executed by the oracle."""
+    import torch
+    from neptune_b200.cycle import ReplanCycle
+    from tests.ent_backends import OracleEntBackend
+    par = config(cfg)
+    ob = OracleEntBackend(oracle)
+    sc = make_scene(par, seed, sync=False, ent_backend=ob)
+    b = sc.batch
+    cyc = ReplanCycle(par, b.agent_id - 1, "cuda:0", static=(b.st_ptr, b.st_xy, sc.strep))
+    hin, hout = cyc.host_inputs(sc), cyc.host_outputs()
+    cyc.step_from_host(hin, hout)
+    cyc.check_errors()
+    o = {k: v.cpu().numpy() for k, v in cyc.o.items()}
+    for k in ("cnt", "alpha", "beta", "bend", "active"):
+        assert np.array_equal(o["esA_" + k], getattr(sc, "esA_" + k)), k
+    ref = ReplanResult.empty(b)
+    assert oracle.replan_batch(b, ref, 2) == 0
+    assert np.array_equal(hout["status"].numpy(), ref.status)
+    assert np.abs(hout["coeff_out"].numpy() - ref.coeff_out).max() <= 1e-6 * max(1.0, np.abs(ref.coeff_out).max())
+    delta = 2 * par.drone_radius
+    want_col = np.zeros(b.B, np.int32)
+    for bi in range(b.B):
+        for j in range(par.num_of_agents):
+            if sc.known[bi, j]:
+                tm, cx, cy, _ = sc.committed[j]
+                if oracle.pwp_collides(ref.coeff_out[bi], int(b.n_int[bi]), sc.t_start[bi], par.T_span, tm, cx, cy, [delta] * 3):
+                    want_col[bi] = 1
+    assert np.array_equal(hout["collide"].numpy(), want_col)
+    ent = ob.check_batch(par, b.agent_id, b.n_int, ref.coeff_out, sc.samp, sc.known, sc.strep, b.bp_cnt, b.bp_xy,
+                         sc.esA_cnt, sc.esA_alpha, sc.esA_beta, sc.esA_bend, sc.esA_active)[0]
+    assert np.array_equal(hout["entangled"].numpy(), ent)
+    # committed records: times shifted by t_start (generatePwpOut :898), coefficients of pwp_out
+    rec = o["new_recs"]
+    for bi in range(b.B):
+        n = int(b.n_int[bi])
+        assert rec[bi, 0] == n
+        assert np.allclose(rec[bi, 1:2 + n], sc.t_start[bi] + par.T_span * np.arange(n + 1), atol=1e-12)
+        assert np.array_equal(rec[bi, 18:].reshape(3, 16, 4)[:, :n], o["coeff_out"][bi, :, :n])
+    del cyc
+    torch.cuda.synchronize()
