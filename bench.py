@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """bench.py -- replans/sec of the NEPTUNE replan hot path on B200 (BASELINE.json metric).
 
-One "step" = one replan cycle: every agent of the world replans once (separating-line LPs ->
-trajectory QP with the reference's fallback path), the ranks exchange committed trajectories with one
-NCCL all-gather.  Workload: BASELINE.json configs[3] family -- a grid world with 64 agents per GPU
+One "step" = one replan cycle of neptune_b200.cycle.ReplanCycle: hulls/samples of every other
+agent's committed trajectory (K1), PredictAlphasBetas (K3), separating-line LPs + pruning (K2), the
+trajectory QP with the reference's fallback path (K4), the post-check (K5 GJK + K3 entangle re-check),
+commit; the ranks exchange committed-trajectory records with one NCCL all-gather.  Workload: BASELINE.json configs[3] family -- a grid world with 64 agents per GPU
 (N=1 is exactly "64 agents synthetic random goals"); every agent plans against ALL other agents of
 the world (faithful, no culling), so per-agent work grows with the world while agents/GPU stay fixed.
 
@@ -46,11 +47,11 @@ def world_params(n_gpus: int):
     return p
 
 
-def make_world(n_gpus: int, rank: int, n_scenes: int):
+def make_world(n_gpus: int, rank: int, n_scenes: int, ent_backend=None):
     from neptune_b200.scenes import make_scene
     par = world_params(n_gpus)
     agents = np.arange(rank * AGENTS_PER_GPU, (rank + 1) * AGENTS_PER_GPU)
-    return par, [make_scene(par, SEED + k, agents=agents) for k in range(n_scenes)]
+    return par, [make_scene(par, SEED + k, agents=agents, ent_backend=ent_backend) for k in range(n_scenes)]
 
 
 class ClockSampler:
@@ -63,7 +64,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -107,41 +108,47 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
-def cpu_baseline(par, scene, budget_s: float, threads: int):
-    """Oracle (CPU restatement of the reference algorithm) on the host cores: replans/s."""
-    from neptune_b200.batch import ReplanResult
+def cpu_cycle(scene, threads: int):
+    """One whole cycle of the scene's agents on the CPU oracle (hulls/samples, predict, LPs + QP,
+    post-check, entangle re-check): the restatement of the reference algorithm, all host threads."""
+    from neptune_b200 import capi
     from oracle import oracle as orc
-    res = ReplanResult.empty(scene.batch, with_lines=False)
-    orc.replan_batch(scene.batch, res, threads)  # warm
+    recs = capi.make_records(scene.committed)
+    rc, out = orc.cycle_batch(scene, recs, threads)
+    assert rc == 0
+    return out
+
+
+def cpu_baseline(scene, budget_s: float, threads: int):
+    cpu_cycle(scene, threads)  # warm
     t0, reps = time.perf_counter(), 0
     while True:
-        orc.replan_batch(scene.batch, res, threads)
+        out = cpu_cycle(scene, threads)
         reps += 1
         el = time.perf_counter() - t0
         if el >= budget_s or reps >= 50:
             break
-    return scene.batch.B * reps / el, reps, el, res
+    return scene.batch.B * reps / el, reps, el, out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    par, scenes = make_world(args.gpus, 0, 1)
-    threads = os.cpu_count() or 1
-    from neptune_b200.batch import ReplanResult
     from oracle import oracle as orc
-    res = ReplanResult.empty(scenes[0].batch, with_lines=False)
+    from tests.ent_backends import OracleEntBackend
+    par, scenes = make_world(args.gpus, 0, 1, OracleEntBackend(orc))
+    threads = os.cpu_count() or 1
     for _ in range(args.warmup):
-        orc.replan_batch(scenes[0].batch, res, threads)
+        cpu_cycle(scenes[0], threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.replan_batch(scenes[0].batch, res, threads)
+        cpu_cycle(scenes[0], threads)
     el = time.perf_counter() - t0
     B = scenes[0].batch.B
     val = B * args.steps / el
     sample = (f"{B} of the world's {par.num_of_agents} agents (rank-0 shard) x {args.steps} cycles, "
-              f"each against all {par.num_of_agents - 1} others")
+              f"each against all {par.num_of_agents - 1} others; oracle/neptune_oracle.c orc_cycle_batch")
     line = {"impl": "reference", "metric": "replans_per_sec", "value": val, "unit": "replans/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -164,7 +171,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from neptune_b200 import capi
-    from neptune_b200.batch import NPOL, ReplanResult
+    from neptune_b200.cycle import ReplanCycle
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -175,91 +182,46 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    par, scenes = make_world(args.gpus, rank, args.scenes)
-    solver = capi.Solver(par, device=local_rank)
-    stream = torch.cuda.current_stream().cuda_stream
-    B = scenes[0].batch.B
-
-    # ---------------- device-resident inputs (value) and pinned host inputs (e2e)
-    def dev_args(sc):
-        b = sc.batch
-        t = {k: torch.from_numpy(np.ascontiguousarray(getattr(b, k))).to(dev) for k in
-             ("agent_id", "n_int", "coeff_init", "hull_ptr", "hull_xy", "nih0", "esv_cnt", "esv_alpha", "esv_active",
-              "bp_cnt", "bp_xy")}
-        t["coeff_out"] = torch.zeros((B, 3, NPOL, 4), dtype=torch.float64, device=dev)
-        t["obj"] = torch.zeros(B, dtype=torch.float64, device=dev)
-        t["status"] = torch.zeros(B, dtype=torch.int32, device=dev)
-        t["iters"] = torch.zeros((B, 2), dtype=torch.int32, device=dev)
-        a = capi.NbReplanArgs()
-        a.B, a.space, a.n_hull_slots, a.hull_nvert = B, capi.NB_DEVICE, b.n_hull_slots, int(b.hull_xy.shape[0])
-        for k, v in t.items():
-            setattr(a, k, v.data_ptr())
-        a.lines, a.line_ok = None, None
-        return a, t
-
-    def pinned_batch(sc):
-        import dataclasses
-        b = sc.batch
-        keep = {}
-        for k in ("agent_id", "n_int", "coeff_init", "hull_ptr", "hull_xy", "nih0", "esv_cnt", "esv_alpha",
-                  "esv_active", "bp_cnt", "bp_xy"):
-            tt = torch.from_numpy(np.ascontiguousarray(getattr(b, k))).pin_memory()
-            keep[k] = tt
-        pb = dataclasses.replace(b, **{k: v.numpy() for k, v in keep.items()})
-        res = ReplanResult(coeff_out=torch.zeros((B, 3, NPOL, 4), dtype=torch.float64).pin_memory().numpy(),
-                           obj=torch.zeros(B, dtype=torch.float64).pin_memory().numpy(),
-                           status=torch.zeros(B, dtype=torch.int32).pin_memory().numpy(),
-                           iters=torch.zeros((B, 2), dtype=torch.int32).pin_memory().numpy())
-        return capi.host_args(pb, res), (keep, pb, res)
-
-    dargs = [dev_args(sc) for sc in scenes]
-    hargs = [pinned_batch(sc) for sc in scenes]
+    par = world_params(args.gpus)
+    agents = np.arange(rank * AGENTS_PER_GPU, (rank + 1) * AGENTS_PER_GPU)
+    cyc = ReplanCycle(par, agents, dev, world=world)
+    # the workload generator fills entanglement states through the product's own K3 kernels
+    _, scenes = make_world(args.gpus, rank, args.scenes, capi.DeviceEntBackend(cyc.solver))
+    B = cyc.B
+    hins = [cyc.host_inputs(sc) for sc in scenes]
+    hout = cyc.host_outputs()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    gathered = torch.zeros((world * B, 100), dtype=torch.float64, device=dev) if world > 1 else None
-    record = torch.zeros((B, 100), dtype=torch.float64, device=dev)
-
-    def exchange(t):
-        """committed-trajectory record per agent: coefficients + (id, n) -> one NCCL all-gather"""
-        if world == 1:
-            return
-        record[:, :96] = t["coeff_out"].reshape(B, 96)
-        record[:, 96] = t["agent_id"].to(torch.float64)
-        record[:, 97] = t["n_int"].to(torch.float64)
-        dist.all_gather_into_tensor(gathered, record)
+    lib = capi.lib()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- value: inputs resident in HBM, CUDA events, max over ranks
-    solver_lib = capi.lib()
-    solver_lib.nb_set_profiling(solver.handle, 1)
+    # ---------------- value: inputs resident in HBM before the timed region, CUDA events, max over ranks
+    lib.nb_set_profiling(cyc.solver.handle, 1)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ktimes = []
-    sampler = None
+    ktimes, sampler, l0 = [], None, 0
     for it in range(args.warmup + args.steps):
         k = it - args.warmup
         if k == 0:
             barrier()
             sampler = ClockSampler(local_rank)
-            l0 = solver.launch_count()
-        a, t = dargs[it % len(dargs)]
+            l0 = cyc.solver.launch_count()
+        cyc.upload(hins[it % len(hins)])       # untimed: this leg measures with inputs already in HBM
         flush.zero_()
         if k >= 0:
             ev[k][0].record()
-        solver.replan_args(a, stream)
-        exchange(t)
+        cyc.step()
         if k >= 0:
             ev[k][1].record()
             ms = (C.c_double * 2)()
-            solver_lib.nb_kernel_times(solver.handle, ms, 2)
+            lib.nb_kernel_times(cyc.solver.handle, ms, 2)
             ktimes.append((ms[0], ms[1]))
     barrier()
-    launches = solver.launch_count() - l0
+    launches = cyc.solver.launch_count() - l0
     clocks = sampler.stop()
-    rc = solver_lib.nb_check_async_errors(solver.handle, C.c_void_p(stream))
-    assert rc == 0, "capacity overflow during the timed region"
+    cyc.check_errors()
     step_ms = np.array([e0.elapsed_time(e1) for e0, e1 in ev])
     total_ms = float(step_ms.sum())
     if world > 1:
@@ -267,15 +229,30 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
     value = world * B * args.steps / (total_ms * 1e-3)
+    st = cyc.o["status"].cpu().numpy()
+    itn = cyc.o["iters"].cpu().numpy()
+    ent, col = cyc.o["entangled"].cpu().numpy(), cyc.o["collide"].cpu().numpy()
 
-    # ---------------- e2e: host buffers through the C-ABI, H2D + kernels + D2H inside the timed region
+    # ---------------- per-stage times (separate short pass, synchronised between stages)
+    cyc.profile = True
+    stage = {}
+    for it in range(5):
+        cyc.upload(hins[it % len(hins)])
+        flush.zero_()
+        cyc.step()
+        for k2, v in cyc.stage_ms.items():
+            stage.setdefault(k2, []).append(v)
+    cyc.profile = False
+    stage = {k2: float(np.mean(v)) for k2, v in stage.items()}
+
+    # ---------------- e2e: pinned host inputs -> H2D -> all kernels -> D2H, every step
     for it in range(2):
-        solver.replan_args(hargs[it % len(hargs)][0], stream)
+        cyc.step_from_host(hins[it % len(hins)], hout)
     barrier()
     t0 = time.perf_counter()
+    h2d = d2h = 0
     for it in range(args.steps):
-        solver.replan_args(hargs[it % len(hargs)][0], stream)  # synchronous: returns after the D2H copies
-        exchange(dargs[0][1])
+        h2d, d2h = cyc.step_from_host(hins[it % len(hins)], hout)
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -283,14 +260,8 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     e2e = world * B * args.steps / e2e_s
-    b0 = scenes[0].batch
-    h2d = b0.input_bytes() + b0.bp_cnt.nbytes + b0.bp_xy.nbytes
-    d2h = B * (96 * 8 + 8 + 4 + 8)
 
     if rank == 0:
-        # status histogram of the last device-resident step, to show what work the step did
-        st = dargs[(args.warmup + args.steps - 1) % len(dargs)][1]["status"].cpu().numpy()
-        itn = dargs[(args.warmup + args.steps - 1) % len(dargs)][1]["iters"].cpu().numpy()
         kt = np.array(ktimes)
         dom = int(np.argmax(kt.mean(axis=0)))
         dom_ms = float(kt[:, dom].mean())
@@ -305,17 +276,20 @@ def run_ours(args):
                 "e2e": {"value": e2e, "unit": "replans/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
                 "kernels_ms": {"k_lines": float(kt[:, 0].mean()), "k_qp": float(kt[:, 1].mean())},
+                "stage_ms": stage,
                 "roofline": {"bound": "hbm", "kernel": ["k_lines", "k_qp"][dom], "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": which,
                              "algorithmic_bytes_per_launch": alg_bytes,
                              "note": "latency/FP64-issue bound at this size, not HBM bound (DESIGN.md)"},
-                "status_hist": {str(k): int((st == k).sum()) for k in (0, 1, 2)},
+                "status_hist": {str(k2): int((st == k2).sum()) for k2 in (0, 1, 2)},
+                "postcheck": {"entangled": int(ent.sum()), "collide": int(col.sum())},
                 "ipm_iters_mean": float(itn.sum(axis=1).mean()),
                 "clocks": clocks}
         if world == 1 and not args.no_cpu:
-            v, reps, el, ref = cpu_baseline(par, scenes[0], args.cpu_budget, os.cpu_count() or 1)
+            v, reps, el, ref = cpu_baseline(scenes[0], args.cpu_budget, os.cpu_count() or 1)
             line["cpu_baseline"] = {"value": v, "unit": "replans/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": f"{B} agents x {reps} cycles of scene 0 ({el:.1f} s), oracle/neptune_oracle.c"}
+                                    "sample": f"{B} agents x {reps} whole cycles of scene 0 ({el:.1f} s), "
+                                              "oracle/neptune_oracle.c orc_cycle_batch"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -90,7 +90,8 @@ class ReplanCycle:
         self.delta = 2.0 * par.drone_radius  # bbox/2 + drone_radius with bbox = 2 drone_radius (neptune_ros.cpp:447-449)
         self._lib = capi.lib()
         self._sig()
-        self.pinned = None
+        self.profile = False   # True: synchronise and time every stage of step() with CUDA events
+        self.stage_ms = {}
 
     def _sig(self):
         P, L = C.c_void_p, self._lib
@@ -149,8 +150,17 @@ class ReplanCycle:
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
         DEV = capi.NB_DEVICE
         chk = capi._check
+        marks = []
+
+        def mark(name):
+            if self.profile:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+        mark("start")
         chk(L.nb_hulls_batch(h, B, DEV, p(d["t_start"]), p(d["recs"]), p(d["known"]), self.delta, p(o["hull_xy"]),
                              p(o["hull_cnt"]), p(o["hull_ptr"]), p(o["nih0"]), p(o["samp"]), None, st), "nb_hulls_batch")
+        mark("hulls_samples")
         # entangle_state_A = PredictAlphasBetas(entangle_state_)
         for k in ("cnt", "alpha", "beta", "bend", "active"):
             o["esA_" + k].copy_(d["es_" + k])
@@ -160,6 +170,7 @@ class ReplanCycle:
         chk(L.nb_entangle_predict_batch(h, B, DEV, p(d["agent_id"]), p(d["known"]), p(d["bp_cnt"]), p(d["bp_xy"]), esA,
                                         p(d["prev_pos"]), p(d["prev_pos_agent"]), p(d["cur"]), p(o["samp0"]), st),
             "nb_entangle_predict_batch")
+        mark("predict")
         a = capi.NbReplanArgs()
         a.B, a.space, a.n_hull_slots = B, DEV, self.N
         a.agent_id, a.n_int, a.coeff_init = d["agent_id"].data_ptr(), d["n_int"].data_ptr(), d["coeff_init"].data_ptr()
@@ -171,6 +182,7 @@ class ReplanCycle:
         a.coeff_out, a.obj, a.status, a.iters = (o[k].data_ptr() for k in ("coeff_out", "obj", "status", "iters"))
         a.lines, a.line_ok = None, None
         chk(L.nb_replan_batch(h, C.byref(a), st), "nb_replan_batch")
+        mark("lines_qp")
         # safetyCheckAfterReplan: geometric check against the late trajectories, then the entangle re-check
         chk(L.nb_postcheck_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["t_start"]), p(d["recs"]), p(d["late"]),
                                  self.delta, p(o["collide"]), st), "nb_postcheck_batch")
@@ -183,11 +195,16 @@ class ReplanCycle:
             chk(L.nb_entangle_check_batch(h, B, DEV, p(d["agent_id"]), p(d["known"]), p(d["bp_cnt"]), p(d["bp_xy"]), esC,
                                           p(d["n_int"]), p(o["coeff_out"]), p(o["samp"]), 0, p(o["entangled"]), st),
                 "nb_entangle_check_batch")
+        mark("postcheck")
         chk(L.nb_commit_records_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["t_start"]), p(o["new_recs"]), st),
             "nb_commit_records_batch")
         if exchange and self.world > 1:
             sizes = [len(shard_agents(self.N, self.world, r)) for r in range(self.world)]
             self.gathered = gather_records(o["new_recs"], self.world, self.group, sizes)
+        mark("commit_exchange")
+        if self.profile:
+            torch.cuda.synchronize()
+            self.stage_ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
         return o
 
     def step_from_host(self, host_in: dict, host_out: dict, exchange: bool = True):

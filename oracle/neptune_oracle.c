@@ -2097,3 +2097,138 @@ int orc_replan_batch(const orc_params* par, const orc_batch* b, int nthreads)
   }
   return rc_all;
 }
+
+/*
+ * One full replan cycle for one agent, as the reference's planner core runs it around the back end
+ * (neptune.cpp:1430-1448 hulls/samples + PredictAlphasBetas, :1512-1529 back end, :719-765
+ * post-check against every known trajectory, with the entangle re-check).  Inputs are the
+ * committed-trajectory records of all N agents (layout of include/neptune_b200.h) -- this is the
+ * CPU baseline that bench.py times next to the device-resident cycle.
+ */
+#define ORC_REC_TP 16
+#define ORC_REC (1 + (ORC_REC_TP + 1) + 3 * ORC_REC_TP * 4)
+
+int orc_cycle_batch(const orc_params* par, int B, const int* agent_id, const int* n_int, const double* coeff_init,
+                    const double* t_start, const double* recs, const unsigned char* known, const double* pb,
+                    const long long* st_ptr, const double* st_xy, const double* strep, const int* bp_cnt,
+                    const double* bp_xy, const int* esv_cnt, const int* esv_alpha, const int* esv_active,
+                    const int* es_cnt, const int* es_alpha, const double* es_beta, const int* es_bend,
+                    const int* es_active, const double* prev_pos, const double* prev_pos_agent, const double* cur,
+                    double delta, int do_entangle, double* coeff_out, double* obj, int* status, int* iters,
+                    int* entangled, int* collide, int nthreads)
+{
+  const int N = par->num_agents, M = par->num_static, NA = N + M, cap = par->ent_cap, S = par->samples, P = par->num_pol;
+  int rc_all = 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+  for (int b = 0; b < B; b++)
+  {
+    const unsigned char* kn = known + (size_t)b * N;
+    /* hulls and samples of every other agent (neptune.cpp:1433-1434) */
+    long long* hptr = (long long*)malloc(sizeof(long long) * ((size_t)N * 8 + 1));
+    double* hxy = (double*)malloc(sizeof(double) * 2 * ORC_HMAX * (size_t)N * 8);
+    double* nih0 = (double*)malloc(sizeof(double) * (size_t)N * 16);
+    double* samp = (double*)calloc((size_t)N * P * (S + 1) * 2, sizeof(double));
+    double* samp0 = (double*)calloc((size_t)N * 2, sizeof(double));
+    const double d3[3] = { delta, delta, delta };
+    long long nv = 0;
+    for (int j = 0; j < N; j++)
+    {
+      const double* rec = recs + (size_t)j * ORC_REC;
+      const int np = (int)rec[0];
+      const double* times = rec + 1;
+      const double* cx = rec + 1 + (ORC_REC_TP + 1);
+      const double* cy = cx + ORC_REC_TP * 4;
+      for (int i = 0; i < 8; i++)
+      {
+        hptr[j * 8 + i] = nv;
+        nih0[(j * 8 + i) * 2] = nih0[(j * 8 + i) * 2 + 1] = NAN;
+        if (!kn[j] || i >= P) continue;
+        double h2[2 * ORC_HMAX];
+        int hn = 0, h2n = 0, idx[2];
+        orc_hull_of_interval(times, np + 1, cx, cy, t_start[b] + i * par->T_span, t_start[b] + (i + 1) * par->T_span,
+                             par->T_span, d3, hxy + 2 * nv, &hn, h2, &h2n, idx);
+        nv += hn;
+        if (h2n > 0)
+        {
+          nih0[(j * 8 + i) * 2] = h2[0];
+          nih0[(j * 8 + i) * 2 + 1] = h2[1];
+        }
+      }
+      if (kn[j])
+      {
+        orc_sample_interval_points(times, np + 1, cx, cy, t_start[b], t_start[b] + par->T_span * P, P, S,
+                                   samp + (size_t)j * P * (S + 1) * 2, 0);
+        samp0[2 * j] = samp[(size_t)j * P * (S + 1) * 2];
+        samp0[2 * j + 1] = samp[(size_t)j * P * (S + 1) * 2 + 1];
+      }
+    }
+    hptr[N * 8] = nv;
+    /* PredictAlphasBetas */
+    orc_ent es;
+    es.alpha = (int*)malloc(sizeof(int) * 2 * cap);
+    es.beta = (double*)malloc(sizeof(double) * cap);
+    es.bend = (int*)malloc(sizeof(int) * cap);
+    es.active = (int*)malloc(sizeof(int) * NA);
+    es.n_alpha = es_cnt[2 * b];
+    es.n_bend = es_cnt[2 * b + 1];
+    memcpy(es.alpha, es_alpha + (size_t)b * cap * 2, sizeof(int) * 2 * cap);
+    memcpy(es.beta, es_beta + (size_t)b * cap, sizeof(double) * cap);
+    memcpy(es.bend, es_bend + (size_t)b * cap, sizeof(int) * cap);
+    memcpy(es.active, es_active + (size_t)b * NA, sizeof(int) * NA);
+    orc_ectx cx;
+    cx.N = N, cx.M = M, cx.self = agent_id[b] - 1, cx.cap = cap, cx.pb = pb, cx.strep = strep, cx.bp_cnt = bp_cnt;
+    cx.bp_xy = bp_xy, cx.bp_max = par->bp_max;
+    int rc = 0;
+    if (do_entangle)
+      rc = orc_predict(&es, &cx, prev_pos + (size_t)b * (N + 1) * 2, prev_pos_agent + (size_t)b * N * 2, cur + 2 * b,
+                       samp0, kn);
+    /* back end */
+    orc_replan_in in;
+    orc_replan_out out;
+    in.agent_id = agent_id[b], in.n = n_int[b], in.coeff_init = coeff_init + (size_t)b * 96, in.n_hull_slots = N;
+    in.hull_ptr = hptr, in.hull_xy = hxy, in.nih0 = nih0, in.st_ptr = st_ptr, in.st_xy = st_xy;
+    in.esv_cnt = esv_cnt + (size_t)b * 18, in.esv_alpha = esv_alpha + (size_t)b * 9 * cap * 2;
+    in.esv_active = esv_active + (size_t)b * 9 * NA, in.bp_cnt = bp_cnt, in.bp_xy = bp_xy, in.pb = pb;
+    out.coeff_out = coeff_out + (size_t)b * 96, out.obj = obj + b, out.status = status + b, out.iters = iters + 2 * b;
+    out.lines = 0, out.line_ok = 0;
+    if (!rc) rc = orc_replan(par, &in, &out);
+    /* safetyCheckAfterReplan: every known trajectory treated as late (worst case) */
+    int col = 0;
+    for (int j = 0; j < N && !col; j++)
+      if (kn[j])
+      {
+        const double* rec = recs + (size_t)j * ORC_REC;
+        const double* cxj = rec + 1 + (ORC_REC_TP + 1);
+        if (orc_pwp_collides(out.coeff_out, n_int[b], t_start[b], par->T_span, rec + 1, (int)rec[0] + 1, cxj,
+                             cxj + ORC_REC_TP * 4, d3))
+          col = 1;
+      }
+    collide[b] = col;
+    entangled[b] = 0;
+    if (do_entangle && !rc)
+    {
+      double cxy[2 * 32];
+      for (int i = 0; i < n_int[b]; i++)
+        for (int r = 0; r < 4; r++)
+        {
+          cxy[4 * i + r] = out.coeff_out[4 * i + r];
+          cxy[4 * n_int[b] + 4 * i + r] = out.coeff_out[32 + 4 * i + r];
+        }
+      int e = orc_entangle_check_pwp(&es, &cx, n_int[b], cxy, samp, kn, P, S, par->T_span);
+      entangled[b] = e > 0;
+      if (e < 0) rc = e;
+    }
+    free(hptr), free(hxy), free(nih0), free(samp), free(samp0), free(es.alpha), free(es.beta), free(es.bend), free(es.active);
+    if (rc)
+    {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+      rc_all = rc;
+    }
+  }
+  return rc_all;
+}

@@ -188,6 +188,16 @@ typedef struct orc_batch
 
 int orc_replan_batch(const orc_params* par, const orc_batch* b, int nthreads);
 
+/* whole cycle per agent (hulls/samples, predict, back end, post-check): the CPU baseline of bench.py */
+int orc_cycle_batch(const orc_params* par, int B, const int* agent_id, const int* n_int, const double* coeff_init,
+                    const double* t_start, const double* recs, const unsigned char* known, const double* pb,
+                    const long long* st_ptr, const double* st_xy, const double* strep, const int* bp_cnt,
+                    const double* bp_xy, const int* esv_cnt, const int* esv_alpha, const int* esv_active,
+                    const int* es_cnt, const int* es_alpha, const double* es_beta, const int* es_bend,
+                    const int* es_active, const double* prev_pos, const double* prev_pos_agent, const double* cur,
+                    double delta, int do_entangle, double* coeff_out, double* obj, int* status, int* iters,
+                    int* entangled, int* collide, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -297,3 +297,31 @@ def export_qp(batch, a: int, fallback: bool, lines, line_ok):
     ne = n_eq.value
     return dict(P=P, q=q, c0=c0.value, Aeq=Aeq[:ne].copy(), beq=beq[:ne].copy(), G=G[:m].copy(), h=h[:m].copy(),
                 has_qc=bool(has_qc.value), n=n)
+
+
+def cycle_batch(scene, recs, nthreads: int = 1, do_entangle: bool = True):
+    """orc_cycle_batch over a neptune_b200.scenes.Scene: the whole per-agent cycle on the CPU."""
+    b, par = scene.batch, scene.par
+    op = make_params(par)
+    B = b.B
+    strep = _c(scene.strep, np.float64) if par.num_of_static_obst else np.zeros((1, 2, 2))
+    arrs = dict(agent_id=_c(b.agent_id, np.int32), n_int=_c(b.n_int, np.int32), coeff_init=_c(b.coeff_init, np.float64),
+                t_start=_c(scene.t_start, np.float64), recs=_c(recs, np.float64), known=_c(scene.known, np.uint8),
+                pb=_c(par.pb, np.float64), st_ptr=_c(b.st_ptr, np.int64), st_xy=_c(b.st_xy, np.float64), strep=strep,
+                bp_cnt=_c(b.bp_cnt, np.int32), bp_xy=_c(b.bp_xy, np.float64), esv_cnt=_c(b.esv_cnt, np.int32),
+                esv_alpha=_c(b.esv_alpha, np.int32), esv_active=_c(b.esv_active, np.int32),
+                es_cnt=_c(scene.es0_cnt, np.int32), es_alpha=_c(scene.es0_alpha, np.int32),
+                es_beta=_c(scene.es0_beta, np.float64), es_bend=_c(scene.es0_bend, np.int32),
+                es_active=_c(scene.es0_active, np.int32), prev_pos=_c(scene.prev_pos, np.float64),
+                prev_pos_agent=_c(scene.prev_pos_agent, np.float64), cur=_c(scene.state_A[:, 0, :2], np.float64))
+    out = dict(coeff_out=np.zeros((B, 3, 8, 4)), obj=np.zeros(B), status=np.zeros(B, np.int32),
+               iters=np.zeros((B, 2), np.int32), entangled=np.zeros(B, np.int32), collide=np.zeros(B, np.int32))
+    f = lib().orc_cycle_batch
+    f.restype = C.c_int
+    order = ("agent_id", "n_int", "coeff_init", "t_start", "recs", "known", "pb", "st_ptr", "st_xy", "strep", "bp_cnt",
+             "bp_xy", "esv_cnt", "esv_alpha", "esv_active", "es_cnt", "es_alpha", "es_beta", "es_bend", "es_active",
+             "prev_pos", "prev_pos_agent", "cur")
+    rc = f(C.byref(op), C.c_int(B), *[_p(arrs[k]) for k in order], C.c_double(2 * par.drone_radius),
+           C.c_int(int(do_entangle)), _p(out["coeff_out"]), _p(out["obj"]), _p(out["status"]), _p(out["iters"]),
+           _p(out["entangled"]), _p(out["collide"]), C.c_int(nthreads))
+    return rc, out
