@@ -106,7 +106,7 @@ struct NbQpArgs
   const uint8_t* keep;  // [B][8][LS]
   int LS;
   double* cl;           // [B][8*LS][3]   (only used when an agent keeps more than NB_QP_SMEM_LINES lines)
-  double* rows;         // [B][4][RS]     (same)
+  double* rows;         // [B][5][RS]     (same)
   int RS;
   double* coeff_out;
   double* obj;
@@ -115,38 +115,49 @@ struct NbQpArgs
 };
 
 #define NB_QP_SMEM_LINES 160
+#define NB_QP_THREADS 128
 #define NB_QP_SMEM_ROWS (6 * NB_NFEAT_AX + 4 * NB_QP_SMEM_LINES)
 
 struct NbQpSmem
 {
   NbQpShared sh;
   NbQpTable tb;
-  double rows[4 * NB_QP_SMEM_ROWS];
+  double rows[5 * NB_QP_SMEM_ROWS];
   double cl[3 * NB_QP_SMEM_LINES];
   double xout[96];
+  double red[8 * NB_QP_THREADS / 32];
   int lstart[12];
+  int nl;
 };
 
-__global__ void __launch_bounds__(32) k_qp(NbConsts cs, const NbQpTable* tables, NbQpArgs a)
+__global__ void __launch_bounds__(NB_QP_THREADS) k_qp(NbConsts cs, const NbQpTable* tables, NbQpArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   NbQpSmem* sm = reinterpret_cast<NbQpSmem*>(smem_raw);
   const int b = blockIdx.x;
-  Group<32> g(threadIdx.x);
+  Group<NB_QP_THREADS> g(threadIdx.x, sm->red);
   const int n = a.n_int[b];
   const double* ci = a.coeff_init + (size_t)b * 96;
   const uint8_t* keep = a.keep + (size_t)b * NB_NPOL * a.LS;
-  const int nkeep = nb_count_lines<32>(g, n, a.LS, keep);
+  const int nkeep = nb_count_lines<NB_QP_THREADS>(g, n, a.LS, keep);
   const bool in_smem = nkeep <= NB_QP_SMEM_LINES;
   double* cl = in_smem ? sm->cl : a.cl + (size_t)b * NB_NPOL * a.LS * 3;
-  const int nl = nb_compact_lines<32>(g, n, a.LS, a.lines + (size_t)b * NB_NPOL * a.LS * 3, keep, cl, sm->lstart);
+  if (threadIdx.x < 32)
+  {  // ordered compaction of the kept lines by warp 0 (ballot prefix)
+    Group<32> gw(threadIdx.x);
+    const int nl0 = nb_compact_lines<32>(gw, n, a.LS, a.lines + (size_t)b * NB_NPOL * a.LS * 3, keep, cl, sm->lstart);
+    if (threadIdx.x == 0) sm->nl = nl0;
+  }
+  __syncthreads();
+  const int nl = sm->nl;
   NbQpRows R;
   const size_t rs = in_smem ? NB_QP_SMEM_ROWS : a.RS;
-  double* rb = in_smem ? sm->rows : a.rows + (size_t)b * 4 * a.RS;
+  double* rb = in_smem ? sm->rows : a.rows + (size_t)b * 5 * a.RS;
   R.s = rb;
   R.lam = rb + rs;
   R.dsa = rb + 2 * rs;
   R.dla = rb + 3 * rs;
+  R.inv = rb + 4 * rs;
   R.cl = cl;
   R.lstart = sm->lstart;
   int status = NB_STATUS_FAILED, it0 = 0, it1 = 0;
@@ -158,9 +169,9 @@ __global__ void __launch_bounds__(32) k_qp(NbConsts cs, const NbQpTable* tables,
     const double* src = reinterpret_cast<const double*>(tables + mode * NB_NPOL + (n - 1));
     double* dst = reinterpret_cast<double*>(&sm->tb);
     g.sync();
-    for (int q = threadIdx.x; q < (int)(sizeof(NbQpTable) / sizeof(double)); q += 32) dst[q] = src[q];
+    for (int q = threadIdx.x; q < (int)(sizeof(NbQpTable) / sizeof(double)); q += NB_QP_THREADS) dst[q] = src[q];
     g.sync();
-    ok = nb_qp_solve<32>(g, cs, &sm->tb, &sm->sh, R, ci, nl, sm->xout, mode == 0 ? &it0 : &it1, &obj);
+    ok = nb_qp_solve<NB_QP_THREADS>(g, cs, &sm->tb, &sm->sh, R, ci, nl, sm->xout, mode == 0 ? &it0 : &it1, &obj);
     if (ok) status = mode == 0 ? NB_STATUS_OK : NB_STATUS_FALLBACK;
   }
   g.sync();
@@ -178,7 +189,7 @@ __global__ void __launch_bounds__(32) k_qp(NbConsts cs, const NbQpTable* tables,
   const double dx = ci[3] - pfx, dy = ci[32 + 3] - pfy;
   const bool keep_z = sqrt(dx * dx + dy * dy) < 1.0;
   double* co = a.coeff_out + (size_t)b * 96;
-  for (int q = threadIdx.x; q < 96; q += 32)
+  for (int q = threadIdx.x; q < 96; q += NB_QP_THREADS)
   {
     const int ax = q / 32, r = q % 32;
     double v = ci[q];
@@ -544,7 +555,7 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   const int RS = 6 * NB_NFEAT_AX + 4 * NB_NPOL * LS;
   if (h->lines.ensure(nslots * 3 * sizeof(double)) || h->line_ok.ensure(nslots) ||
       h->cl.ensure(nslots * 3 * sizeof(double)) || h->keep.ensure(nslots) ||
-      h->rows.ensure((size_t)B * 4 * RS * sizeof(double)) || h->err.ensure(sizeof(int)))
+      h->rows.ensure((size_t)B * 5 * RS * sizeof(double)) || h->err.ensure(sizeof(int)))
   {
     g_err = "cudaMalloc failed for scratch buffers";
     return NB_ERR_CUDA;
@@ -580,7 +591,7 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   k_lines<<<B * NB_NPOL, 128, lsm, st>>>(h->cs, in, LS, (double*)h->lines.p, (uint8_t*)h->line_ok.p,
                                          (uint8_t*)h->keep.p, (int*)h->err.p);
   if (h->profiling) cudaEventRecord(h->ev[1], st);
-  k_qp<<<B, 32, sizeof(NbQpSmem), st>>>(h->cs, h->d_tables, q);
+  k_qp<<<B, NB_QP_THREADS, sizeof(NbQpSmem), st>>>(h->cs, h->d_tables, q);
   if (h->profiling) cudaEventRecord(h->ev[2], st);
   h->launches += 2;
   NB_CUDA(cudaGetLastError());

@@ -22,38 +22,95 @@
 #define NB_NFEAT_AX 64   // features per axis: 8 intervals x (4 pos CP + 3 vel CP + 1 acc)
 #define NB_SEP_EPS 1e-9
 
-// ---------------------------------------------------------------- warp-group abstraction
+// ---------------------------------------------------------------- thread-group abstraction
+// NL = 1   : host emulation (one lane runs every phase sequentially)
+// NL = 32  : one warp (sync = __syncwarp, reductions by shuffles)
+// NL = 128 : one CTA of four warps (sync = __syncthreads, reductions through `red` in shared memory)
 template <int NL>
 struct Group
 {
-  int lane;
-  NB_HD Group(int l) : lane(l) {}
+  int lane;     // thread index within the group
+  double* red;  // shared scratch, >= 8 * (NL / 32) doubles when NL > 32
+  static constexpr int SUB = (NL >= 128) ? 4 : 1;  // adjacent lanes that may split one item
+  NB_HD Group(int l, double* r = nullptr) : lane(l), red(r) {}
 #if defined(__CUDA_ARCH__)
-  NB_DEV void sync() const { __syncwarp(); }
-  NB_DEV double sum(double v) const
+  NB_DEV void sync() const
   {
+    if (NL <= 32)
+      __syncwarp();
+    else
+      __syncthreads();
+  }
+  template <int OP>  // 0 sum, 1 max, 2 min
+  NB_DEV static double comb(double a, double b)
+  {
+    return OP == 0 ? a + b : (OP == 1 ? fmax(a, b) : fmin(a, b));
+  }
+  template <int OP>
+  NB_DEV double reduce(double v) const
+  {
+    constexpr int W = NL < 32 ? NL : 32;
 #pragma unroll
-    for (int o = NL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = W / 2; o > 0; o >>= 1) v = comb<OP>(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (NL > 32)
+    {
+      if ((lane & 31) == 0) red[lane >> 5] = v;
+      __syncthreads();
+      v = red[0];
+#pragma unroll
+      for (int w = 1; w < NL / 32; w++) v = comb<OP>(v, red[w]);
+      __syncthreads();
+    }
     return v;
   }
-  NB_DEV double max(double v) const
+  NB_DEV double sum(double v) const { return reduce<0>(v); }
+  NB_DEV double max(double v) const { return reduce<1>(v); }
+  NB_DEV double min(double v) const { return reduce<2>(v); }
+  // five values at once: (sum, max, min, sum, sum) -- one shared-memory exchange instead of five
+  NB_DEV void reduce5(double& s0, double& mx, double& mn, double& s1, double& s2) const
+  {
+    constexpr int W = NL < 32 ? NL : 32;
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1)
+    {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (NL > 32)
+    {
+      const int w = lane >> 5;
+      if ((lane & 31) == 0)
+      {
+        red[5 * w] = s0, red[5 * w + 1] = mx, red[5 * w + 2] = mn, red[5 * w + 3] = s1, red[5 * w + 4] = s2;
+      }
+      __syncthreads();
+      s0 = red[0], mx = red[1], mn = red[2], s1 = red[3], s2 = red[4];
+#pragma unroll
+      for (int q = 1; q < NL / 32; q++)
+      {
+        s0 += red[5 * q], mx = fmax(mx, red[5 * q + 1]), mn = fmin(mn, red[5 * q + 2]), s1 += red[5 * q + 3], s2 += red[5 * q + 4];
+      }
+      __syncthreads();
+    }
+  }
+  // sum over the SUB adjacent lanes that share an item
+  NB_DEV double sub_sum(double v) const
   {
 #pragma unroll
-    for (int o = NL / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    for (int o = 1; o < SUB; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   }
-  NB_DEV double min(double v) const
-  {
-#pragma unroll
-    for (int o = NL / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-  }
-  NB_DEV int any(int p) const { return __any_sync(0xffffffffu, p); }
+  NB_DEV int any(int p) const { return NL <= 32 ? __any_sync(0xffffffffu, p) : __syncthreads_or(p); }
 #else
   void sync() const {}
   double sum(double v) const { return v; }
   double max(double v) const { return v; }
   double min(double v) const { return v; }
+  void reduce5(double&, double&, double&, double&, double&) const {}
+  double sub_sum(double v) const { return v; }
   int any(int p) const { return p; }
 #endif
 };

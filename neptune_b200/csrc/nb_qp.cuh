@@ -10,8 +10,9 @@
 // rows :485-489, :546-550, :587-591, :754-758), so the normal matrix is assembled as
 // Hr + C^T W C with W diagonal plus one 2x2 coupling per control point -- no per-row outer products.
 //
-// Lane-strided SPMD phases over shared (small vectors, K) and global scratch (per-row s, lambda);
-// compiles with NL = 32 on the device and NL = 1 in the host emulation.
+// Lane-strided SPMD phases over shared memory (vectors, K, per-row s / lambda; global scratch only when an
+// agent keeps more lines than fit); compiles with NL = 128 (one CTA per agent) on the device and NL = 1 in
+// the host emulation.
 #pragma once
 #include "nb_common.cuh"
 
@@ -29,12 +30,22 @@ struct NbQpShared
   double xin[3][4 * NB_NPOL];
 };
 
-struct NbQpRows  // per-agent global scratch
+NB_HD double nb_rcp(double x)
+{
+#if defined(__CUDA_ARCH__)
+  return __drcp_rn(x);  // correctly rounded reciprocal == 1.0 / x, without the division slow path
+#else
+  return 1.0 / x;
+#endif
+}
+
+struct NbQpRows  // per-agent row state (shared memory when it fits, else global scratch)
 {
   double* s;    // [384 + 4*LCAP]
   double* lam;
   double* dsa;
   double* dla;
+  double* inv;  // 1/s of the current iterate (written by the RESID pass)
   const double* cl;  // [L][3] compact kept lines: n0, n1, c = 1 - d
   const int* lstart; // [n+1] first line of each interval
 };
@@ -87,39 +98,48 @@ enum
 
 struct NbPassAcc
 {
-  double sum_sl, rp_max, amax, sum_cross, sum_dd;
+  double sum_sl, rp_max, rmax, sum_cross, sum_dd;  // rmax = max over rows of (-ds/s, -dl/lam): alpha_max = 1/rmax
 };
 
 // one inequality row: v = row value (<= 0 wanted), gd = row . direction.  Returns the load tau that
 // this row puts on its feature(s) (for RESID / LOAD_CORR), and the diagonal weight in `wgt`.
 template <int MODE>
-NB_HD double nb_row(double* s_, double* lam_, double* dsa_, double* dla_, double v, double gd, double sigmu,
-                    double alpha, NbPassAcc& acc, double& wgt)
+NB_HD double nb_row(double* s_, double* lam_, double* dsa_, double* dla_, double* inv_, double v, double gd,
+                    double sigmu, double alpha, NbPassAcc& acc, double& wgt)
 {
-  double s = *s_, lam = *lam_;
+  const double s = *s_, lam = *lam_;
   wgt = 0.0;
   if (MODE == NB_PASS_RESID)
   {
     const double rp = v + s;
-    const double inv = 1.0 / s;
+    const double inv = nb_rcp(s);
+    *inv_ = inv;
     wgt = lam * inv;
     acc.sum_sl += s * lam;
     acc.rp_max = fmax(acc.rp_max, fabs(rp));
     return (lam * rp - s * lam) * inv;  // predictor: rc = s lam
   }
-  if (MODE == NB_PASS_DIR_PRED || MODE == NB_PASS_DIR_CORR)
+  if (MODE == NB_PASS_DIR_PRED)
   {
-    const double rp = v + s;
-    const double rc = (MODE == NB_PASS_DIR_PRED) ? s * lam : s * lam + (*dsa_) * (*dla_) - sigmu;
-    const double ds = -rp - gd;
-    const double dl = (-rc - lam * ds) / s;
-    if (ds < 0.0) acc.amax = fmin(acc.amax, -s / ds);
-    if (dl < 0.0) acc.amax = fmin(acc.amax, -lam / dl);
-    if (MODE == NB_PASS_DIR_PRED)
-    {
-      acc.sum_cross += s * dl + lam * ds;
-      acc.sum_dd += ds * dl;
-    }
+    const double inv = *inv_;
+    const double ds = -(v + s) - gd;
+    const double dl = (-s * lam - lam * ds) * inv;
+    acc.rmax = fmax(acc.rmax, -ds * inv);       // -ds/s
+    acc.rmax = fmax(acc.rmax, 1.0 + ds * inv);  // -dl/lam = (s + ds)/s for the predictor
+    acc.sum_cross += s * dl + lam * ds;
+    acc.sum_dd += ds * dl;
+    *dsa_ = ds;
+    *dla_ = dl;
+    return 0.0;
+  }
+  if (MODE == NB_PASS_DIR_CORR)
+  {
+    const double inv = *inv_;
+    const double rc = s * lam + (*dsa_) * (*dla_) - sigmu;
+    const double ds = -(v + s) - gd;
+    const double dl = (-rc - lam * ds) * inv;
+    acc.rmax = fmax(acc.rmax, -ds * inv);
+    acc.rmax = fmax(acc.rmax, -dl * nb_rcp(lam));
     *dsa_ = ds;
     *dla_ = dl;
     return 0.0;
@@ -128,7 +148,7 @@ NB_HD double nb_row(double* s_, double* lam_, double* dsa_, double* dla_, double
   {
     const double rp = v + s;
     const double rc = s * lam + (*dsa_) * (*dla_) - sigmu;
-    return (lam * rp - rc) / s;
+    return (lam * rp - rc) * (*inv_);
   }
   if (MODE == NB_PASS_UPDATE)
   {
@@ -146,12 +166,14 @@ NB_HD double nb_row(double* s_, double* lam_, double* dsa_, double* dla_, double
 }
 
 // One sweep over every inequality row.  Bound rows are visited feature by feature (both sides of a
-// feature by the same lane), line rows control point by control point (lane <-> (interval, k)), so
-// all per-feature accumulations are conflict-free and in a fixed order.
+// feature by the same lane), line rows control point by control point: item (interval i, control
+// point k, sub-lane) where the SUB adjacent lanes of an item split its lines and combine by shuffle.
+// All per-feature accumulations are conflict-free and in a fixed order.
 template <int NL, int MODE>
 NB_HD void nb_qp_pass(const Group<NL>& g, const NbConsts& cs, const NbQpTable* tb, NbQpShared* sh,
                       const NbQpRows& R, double sigmu, double alpha, NbPassAcc& acc)
 {
+  constexpr int SUB = Group<NL>::SUB;
   const int n = tb->n;
   const bool loads = (MODE == NB_PASS_RESID || MODE == NB_PASS_LOAD_CORR);
   for (int q = g.lane; q < 3 * 8 * n; q += NL)
@@ -161,9 +183,10 @@ NB_HD void nb_qp_pass(const Group<NL>& g, const NbConsts& cs, const NbQpTable* t
     nb_feat_bounds(cs, ax, fl & 7, lo, hi);
     const double yv = sh->y[f], dv = sh->dy[f];
     const int rs = 2 * f;
-    const double t_u = nb_row<MODE>(R.s + rs, R.lam + rs, R.dsa + rs, R.dla + rs, yv - hi, dv, sigmu, alpha, acc, w_u);
-    const double t_l = nb_row<MODE>(R.s + rs + 1, R.lam + rs + 1, R.dsa + rs + 1, R.dla + rs + 1, lo - yv, -dv,
-                                    sigmu, alpha, acc, w_l);
+    const double t_u = nb_row<MODE>(R.s + rs, R.lam + rs, R.dsa + rs, R.dla + rs, R.inv + rs, yv - hi, dv, sigmu, alpha,
+                                    acc, w_u);
+    const double t_l = nb_row<MODE>(R.s + rs + 1, R.lam + rs + 1, R.dsa + rs + 1, R.dla + rs + 1, R.inv + rs + 1,
+                                    lo - yv, -dv, sigmu, alpha, acc, w_l);
     if (loads)
     {
       sh->La[f] = t_u - t_l;
@@ -175,113 +198,159 @@ NB_HD void nb_qp_pass(const Group<NL>& g, const NbConsts& cs, const NbQpTable* t
     }
   }
   g.sync();
-  for (int q = g.lane; q < 4 * n; q += NL)
+  const int items = 4 * n * SUB;  // <= NL for SUB > 1, so every lane reaches the shuffles below
+  for (int base = 0; base < items; base += NL)
   {
-    const int i = q >> 2, k = q & 3;
+    const int q = base + g.lane;
+    const bool on = q < items;
+    const int gq = on ? q / SUB : 0, sub = q % SUB;
+    const int i = gq >> 2, k = gq & 3;
     const int fx = i * 8 + k, fy = NB_NFEAT_AX + i * 8 + k;
     const double yx = sh->y[fx], yy = sh->y[fy];
     const double dx = (MODE == NB_PASS_RESID) ? 0.0 : sh->dy[fx], dyv = (MODE == NB_PASS_RESID) ? 0.0 : sh->dy[fy];
     double sxx = 0, sxy = 0, syy = 0, lx = 0, ly = 0, dlx = 0, dly = 0;
-    for (int l = R.lstart[i]; l < R.lstart[i + 1]; l++)
-    {
-      const double n0 = R.cl[3 * l], n1 = R.cl[3 * l + 1], c = R.cl[3 * l + 2];
-      const int rs = 6 * NB_NFEAT_AX + 4 * l + k;
-      double wgt;
-      const double t = nb_row<MODE>(R.s + rs, R.lam + rs, R.dsa + rs, R.dla + rs, n0 * yx + n1 * yy - c,
-                                    n0 * dx + n1 * dyv, sigmu, alpha, acc, wgt);
-      if (loads)
+    if (on)
+      for (int l = R.lstart[i] + sub; l < R.lstart[i + 1]; l += SUB)
       {
-        lx += t * n0;
-        ly += t * n1;
-        if (MODE == NB_PASS_RESID)
+        const double n0 = R.cl[3 * l], n1 = R.cl[3 * l + 1], c = R.cl[3 * l + 2];
+        const int rs = 6 * NB_NFEAT_AX + 4 * l + k;
+        double wgt;
+        const double t = nb_row<MODE>(R.s + rs, R.lam + rs, R.dsa + rs, R.dla + rs, R.inv + rs, n0 * yx + n1 * yy - c,
+                                      n0 * dx + n1 * dyv, sigmu, alpha, acc, wgt);
+        if (loads)
         {
-          sxx += wgt * n0 * n0;
-          sxy += wgt * n0 * n1;
-          syy += wgt * n1 * n1;
-          const double lam = R.lam[rs];
-          dlx += lam * n0;
-          dly += lam * n1;
+          lx += t * n0;
+          ly += t * n1;
+          if (MODE == NB_PASS_RESID)
+          {
+            sxx += wgt * n0 * n0;
+            sxy += wgt * n0 * n1;
+            syy += wgt * n1 * n1;
+            const double lam = R.lam[rs];
+            dlx += lam * n0;
+            dly += lam * n1;
+          }
         }
       }
-    }
     if (loads)
     {
-      sh->La[fx] += lx;
-      sh->La[fy] += ly;
+      lx = g.sub_sum(lx), ly = g.sub_sum(ly);
       if (MODE == NB_PASS_RESID)
       {
-        sh->om[fx] += sxx;
-        sh->om[fy] += syy;
-        sh->Sxy[q] = sxy;
-        sh->dy[fx] += dlx;
-        sh->dy[fy] += dly;
+        sxx = g.sub_sum(sxx), sxy = g.sub_sum(sxy), syy = g.sub_sum(syy), dlx = g.sub_sum(dlx), dly = g.sub_sum(dly);
+      }
+      if (on && sub == 0)
+      {
+        sh->La[fx] += lx;
+        sh->La[fy] += ly;
+        if (MODE == NB_PASS_RESID)
+        {
+          sh->om[fx] += sxx;
+          sh->om[fy] += syy;
+          sh->Sxy[gq] = sxy;
+          sh->dy[fx] += dlx;
+          sh->dy[fy] += dly;
+        }
       }
     }
   }
   g.sync();
 }
 
-// out[a] = sum_f C[f][c] * vecF[ax*64+f]   (a = ax*dof + c): C^T applied to a per-feature vector
+// out[a] = sum_f C[f][c] * vecF[ax*64+f]   (a = ax*dof + c): C^T applied to a per-feature vector, then
+// dst[a] = bsign * base[a] + sign * that + es * extra[a]; item (a, sub-lane) with shuffle combine
 template <int NL>
-NB_HD double nb_qp_ct(const NbQpTable* tb, const double* vecF, int ax, int c)
+NB_HD void nb_qp_ct_all(const Group<NL>& g, const NbQpTable* tb, const double* vecF, double* dst, const double* base,
+                        double bsign, double sign, const double* extra, double es)
 {
-  const int n = tb->n;
-  double v = 0.0;
-  for (int fl = 0; fl < 8 * n; fl++) v += tb->C[fl][c] * vecF[ax * NB_NFEAT_AX + fl];
-  return v;
+  constexpr int SUB = Group<NL>::SUB;
+  const int n = tb->n, dof = tb->dof, nv = 3 * dof;
+  const int items = nv * SUB;
+  for (int b0 = 0; b0 < items; b0 += NL)
+  {
+    const int q = b0 + g.lane;
+    const bool on = q < items;
+    const int a = on ? q / SUB : 0, sub = q % SUB;
+    const int ax = a / dof, c = a - ax * dof;
+    double v0 = 0.0, v1 = 0.0;
+    if (on)
+    {
+      const double* vf = vecF + ax * NB_NFEAT_AX;
+      int fl = sub;
+      for (; fl + SUB < 8 * n; fl += 2 * SUB)
+      {
+        v0 += tb->C[fl][c] * vf[fl];
+        v1 += tb->C[fl + SUB][c] * vf[fl + SUB];
+      }
+      if (fl < 8 * n) v0 += tb->C[fl][c] * vf[fl];
+    }
+    const double v = g.sub_sum(v0 + v1);
+    if (on && sub == 0) dst[a] = bsign * base[a] + sign * v + (extra ? extra[a] * es : 0.0);
+  }
 }
 
-// Cholesky of the nv x nv matrix in sh->K (lower, row-major, ld = nv) and solves.
+// Factorisation K = L D L^T of the nv x nv matrix in sh->K (lower triangle, row-major, ld = nv):
+// afterwards K[i][k] (i > k) = L[i][k] and invd[k] = 1 / D[k].  sh->rhs is used as a column scratch.
 template <int NL>
-NB_HD void nb_qp_chol(const Group<NL>& g, NbQpShared* sh, int nv)
+NB_HD void nb_qp_factor(const Group<NL>& g, NbQpShared* sh, int nv)
 {
   double* K = sh->K;
+  double* col = sh->rhs;
   for (int k = 0; k < nv; k++)
   {
-    g.sync();
-    const double orig = K[k * nv + k];
-    // rank-deficiency guard identical in spirit to the oracle's: floor the pivot
-    double d = orig;
-    d = d > 1e-300 ? d : 1e-300;
-    const double piv = sqrt(d), ip = 1.0 / piv;
-    g.sync();
-    if (g.lane == 0)
+    double d = K[k * nv + k];
+    d = d > 1e-300 ? d : 1e-300;  // rank-deficiency guard (K is positive definite by construction)
+    const double ip = nb_rcp(d);
+    if (g.lane == 0) sh->invd[k] = ip;
+    for (int i = k + 1 + g.lane; i < nv; i += NL)
     {
-      K[k * nv + k] = piv;
-      sh->invd[k] = ip;
+      const double t = K[i * nv + k];
+      col[i] = t;
+      K[i * nv + k] = t * ip;
     }
-    for (int i = k + 1 + g.lane; i < nv; i += NL) K[i * nv + k] *= ip;
     g.sync();
     const int rem = nv - k - 1;
     for (int q = g.lane; q < rem * rem; q += NL)
     {
       const int i = k + 1 + q / rem, j = k + 1 + q % rem;
-      if (j <= i) K[i * nv + j] -= K[i * nv + k] * K[j * nv + k];
+      if (j <= i) K[i * nv + j] -= K[i * nv + k] * col[j];
     }
+    g.sync();
   }
-  g.sync();
 }
 
+// Solve L D L^T x = b in place.  Device: one warp, x in registers, broadcasts by shuffle (no block
+// barriers); host emulation: plain loops in the same summation order.
 template <int NL>
-NB_HD void nb_qp_cholsolve(const Group<NL>& g, NbQpShared* sh, int nv, double* b)
+NB_HD void nb_qp_solve_ldl(const Group<NL>& g, NbQpShared* sh, int nv, double* b)
 {
   const double* K = sh->K;
+  g.sync();
+#if defined(__CUDA_ARCH__)
+  if (g.lane < 32)
+  {
+    const int i = g.lane;
+    double x = i < nv ? b[i] : 0.0;
+    for (int k = 0; k < nv; k++)
+    {  // forward: unit lower
+      const double xk = __shfl_sync(0xffffffffu, x, k);
+      if (i > k && i < nv) x -= K[i * nv + k] * xk;
+    }
+    if (i < nv) x *= sh->invd[i];
+    for (int k = nv - 1; k >= 0; k--)
+    {  // backward: L^T
+      const double xk = __shfl_sync(0xffffffffu, x, k);
+      if (i < k) x -= K[k * nv + i] * xk;
+    }
+    if (i < nv) b[i] = x;
+  }
+#else
   for (int k = 0; k < nv; k++)
-  {
-    g.sync();
-    const double xk = b[k] * sh->invd[k];
-    g.sync();
-    if (g.lane == 0) b[k] = xk;
-    for (int i = k + 1 + g.lane; i < nv; i += NL) b[i] -= K[i * nv + k] * xk;
-  }
+    for (int i = k + 1; i < nv; i++) b[i] -= K[i * nv + k] * b[k];
+  for (int i = 0; i < nv; i++) b[i] *= sh->invd[i];
   for (int k = nv - 1; k >= 0; k--)
-  {
-    g.sync();
-    const double xk = b[k] * sh->invd[k];
-    g.sync();
-    if (g.lane == 0) b[k] = xk;
-    for (int i = g.lane; i < k; i += NL) b[i] -= K[k * nv + i] * xk;
-  }
+    for (int i = 0; i < k; i++) b[i] -= K[k * nv + i] * b[k];
+#endif
   g.sync();
 }
 
@@ -371,16 +440,14 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
                 tb->gpf[c] * sh->pf[ax];
     sh->dw[a] = 0.0;
   }
-  g.sync();
-  // objective at w = 0 (constant term of the reduced objective)
-  double fconst;
+  // objective at w = 0 (constant term of the reduced objective): lanes rebuild x_p cooperatively
+  for (int q = g.lane; q < 3 * 4 * n; q += NL)
   {
-    double xp[96];
-    for (int ax = 0; ax < 3; ax++)
-      for (int r = 0; r < 4 * n; r++)
-        xp[ax * 32 + r] = tb->Pm[r][0] * sh->init3[ax][0] + tb->Pm[r][1] * sh->init3[ax][1] + tb->Pm[r][2] * sh->init3[ax][2];
-    fconst = nb_objective(cs, n, mode, xp, sh->pf);
+    const int ax = q / (4 * n), r = q - ax * 4 * n;
+    x_out[ax * 32 + r] = tb->Pm[r][0] * sh->init3[ax][0] + tb->Pm[r][1] * sh->init3[ax][1] + tb->Pm[r][2] * sh->init3[ax][2];
   }
+  g.sync();
+  const double fconst = nb_objective(cs, n, mode, x_out, sh->pf);
   nb_qp_features<NL>(g, tb, sh, sh->y, sh->w, true);
   g.sync();
 
@@ -440,16 +507,15 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       R.lam[2 * f] = 1.0;
       R.lam[2 * f + 1] = 1.0;
     }
-    for (int q = g.lane; q < 4 * n; q += NL)
+    for (int q = g.lane; q < 4 * nlines; q += NL)
     {
-      const int i = q >> 2, k = q & 3;
-      for (int l = R.lstart[i]; l < R.lstart[i + 1]; l++)
-      {
-        const int rs = 6 * NB_NFEAT_AX + 4 * l + k;
-        const double v = R.cl[3 * l + 2] - R.cl[3 * l] * sh->y[i * 8 + k] - R.cl[3 * l + 1] * sh->y[NB_NFEAT_AX + i * 8 + k];
-        R.s[rs] = fmax(v, 1.0);
-        R.lam[rs] = 1.0;
-      }
+      const int l = q >> 2, k = q & 3;
+      int i = 0;
+      while (l >= R.lstart[i + 1]) i++;
+      const int rs = 6 * NB_NFEAT_AX + q;
+      const double v = R.cl[3 * l + 2] - R.cl[3 * l] * sh->y[i * 8 + k] - R.cl[3 * l + 1] * sh->y[NB_NFEAT_AX + i * 8 + k];
+      R.s[rs] = fmax(v, 1.0);
+      R.lam[rs] = 1.0;
     }
     double s_q = 1.0, lam_q = 1.0, dsa_q = 0.0, dla_q = 0.0;
     if (has_qc)
@@ -465,7 +531,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
     {
       const bool init_pass = (it == 0);
       // ---- residuals and weights
-      NbPassAcc acc = { 0.0, 0.0, 1e300, 0.0, 0.0 };
+      NbPassAcc acc = { 0.0, 0.0, 0.0, 0.0, 0.0 };
       nb_qp_pass<NL, NB_PASS_RESID>(g, cs, tb, sh, R, 0.0, 0.0, acc);
       double cval = 0.0, rp_q = 0.0;
       if (has_qc)
@@ -473,21 +539,22 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
         NB_QC_EVAL(cval);
         rp_q = cval + s_q;
       }
-      double mu = g.sum(acc.sum_sl) + (has_qc ? s_q * lam_q : 0.0);
-      mu /= mq;
-      double rpn = g.max(acc.rp_max);
+      double d0 = 0.0, d1 = 0.0;
+      g.reduce5(acc.sum_sl, acc.rp_max, acc.rmax, d0, d1);
+      const double mu = (acc.sum_sl + (has_qc ? s_q * lam_q : 0.0)) / mq;
+      double rpn = acc.rp_max;
       if (has_qc) rpn = fmax(rpn, fabs(rp_q));
-      // r_d = Hr w + g0 + C^T(lambda load) + lam_q grad c ; gobj = Hr w + g0
+      // gobj = Hr w + g0 ; r_d = gobj + C^T(lambda load) + lam_q grad c
       for (int a = g.lane; a < nv; a += NL)
       {
         const int ax = a / dof, c = a - ax * dof;
         double go = sh->g0[a];
         for (int c2 = 0; c2 < dof; c2++) go += tb->Hr[c][c2] * sh->w[ax * dof + c2];
         sh->gobj[a] = go;
-        const double gqa = has_qc ? 2.0 * e3[ax] * tb->tq[c] : 0.0;
-        sh->gq[a] = gqa;
-        sh->rd[a] = go + nb_qp_ct<NL>(tb, sh->dy, ax, c) + lam_q * gqa * (has_qc ? 1.0 : 0.0);
+        sh->gq[a] = has_qc ? 2.0 * e3[ax] * tb->tq[c] : 0.0;
       }
+      g.sync();
+      nb_qp_ct_all<NL>(g, tb, sh->dy, sh->rd, sh->gobj, 1.0, 1.0, sh->gq, has_qc ? lam_q : 0.0);
       g.sync();
       double rdn = 0.0, gn = 0.0, fobj = fconst;
       for (int a = 0; a < nv; a++)
@@ -516,43 +583,50 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
         double v = 0.0;
         if (axa == axb)
         {
-          v = tb->Hr[ca][cb];
           const double* om = sh->om + axa * NB_NFEAT_AX;
-          for (int fl = 0; fl < 8 * n; fl++) v += om[fl] * tb->C[fl][ca] * tb->C[fl][cb];
+          double v0 = tb->Hr[ca][cb], v1 = 0.0;
+          for (int fl = 0; fl < 8 * n; fl += 2)
+          {
+            v0 += om[fl] * tb->C[fl][ca] * tb->C[fl][cb];
+            v1 += om[fl + 1] * tb->C[fl + 1][ca] * tb->C[fl + 1][cb];
+          }
+          v = v0 + v1;
           if (has_qc) v += lam_q * 2.0 * tb->tq[ca] * tb->tq[cb];
         }
         else if (axa == 1 && axb == 0)
         {
+          double v0 = 0.0, v1 = 0.0;
           for (int i = 0; i < n; i++)
-            for (int k = 0; k < 4; k++) v += sh->Sxy[i * 4 + k] * tb->C[i * 8 + k][ca] * tb->C[i * 8 + k][cb];
+          {
+            v0 += sh->Sxy[i * 4] * tb->C[i * 8][ca] * tb->C[i * 8][cb] +
+                  sh->Sxy[i * 4 + 2] * tb->C[i * 8 + 2][ca] * tb->C[i * 8 + 2][cb];
+            v1 += sh->Sxy[i * 4 + 1] * tb->C[i * 8 + 1][ca] * tb->C[i * 8 + 1][cb] +
+                  sh->Sxy[i * 4 + 3] * tb->C[i * 8 + 3][ca] * tb->C[i * 8 + 3][cb];
+          }
+          v = v0 + v1;
         }
         if (has_qc) v += d_q * sh->gq[a] * sh->gq[b];
         sh->K[a * nv + b] = v;
       }
       g.sync();
-      nb_qp_chol<NL>(g, sh, nv);
+      nb_qp_factor<NL>(g, sh, nv);
       // ---- predictor
       const double tau_q = has_qc ? (lam_q * rp_q - s_q * lam_q) / s_q : 0.0;
-      for (int a = g.lane; a < nv; a += NL)
-      {
-        const int ax = a / dof, c = a - ax * dof;
-        sh->dw[a] = -sh->rd[a] - nb_qp_ct<NL>(tb, sh->La, ax, c) - sh->gq[a] * tau_q;
-      }
-      g.sync();
-      nb_qp_cholsolve<NL>(g, sh, nv, sh->dw);
+      nb_qp_ct_all<NL>(g, tb, sh->La, sh->dw, sh->rd, -1.0, -1.0, sh->gq, -tau_q);
+      nb_qp_solve_ldl<NL>(g, sh, nv, sh->dw);
       nb_qp_features<NL>(g, tb, sh, sh->dy, sh->dw, false);
       g.sync();
-      acc = NbPassAcc{ 0.0, 0.0, 1e300, 0.0, 0.0 };
+      acc = NbPassAcc{ 0.0, 0.0, 0.0, 0.0, 0.0 };
       nb_qp_pass<NL, NB_PASS_DIR_PRED>(g, cs, tb, sh, R, 0.0, 0.0, acc);
-      double amax = g.min(acc.amax), scross = g.sum(acc.sum_cross), sdd = g.sum(acc.sum_dd);
+      g.reduce5(d0, acc.rmax, d1, acc.sum_cross, acc.sum_dd);
+      double rmax = acc.rmax, scross = acc.sum_cross, sdd = acc.sum_dd;
       if (has_qc)
       {
         double gd = 0.0;
         for (int a = 0; a < nv; a++) gd += sh->gq[a] * sh->dw[a];
         dsa_q = -rp_q - gd;
         dla_q = (-s_q * lam_q - lam_q * dsa_q) / s_q;
-        if (dsa_q < 0.0) amax = fmin(amax, -s_q / dsa_q);
-        if (dla_q < 0.0) amax = fmin(amax, -lam_q / dla_q);
+        rmax = fmax(rmax, fmax(-dsa_q / s_q, -dla_q / lam_q));
         scross += s_q * dla_q + lam_q * dsa_q;
         sdd += dsa_q * dla_q;
       }
@@ -566,7 +640,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
         }
         continue;
       }
-      const double a_aff = amax < 1.0 ? amax : 1.0;
+      const double a_aff = rmax > 1.0 ? 1.0 / rmax : 1.0;
       const double mu_aff = (mu * mq + a_aff * scross + a_aff * a_aff * sdd) / mq;
       const double rat = mu_aff / mu;
       const double sigmu = rat * rat * rat * mu;
@@ -574,18 +648,13 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       nb_qp_pass<NL, NB_PASS_LOAD_CORR>(g, cs, tb, sh, R, sigmu, 0.0, acc);
       const double rc_q = s_q * lam_q + dsa_q * dla_q - sigmu;
       const double tau_q2 = has_qc ? (lam_q * rp_q - rc_q) / s_q : 0.0;
-      for (int a = g.lane; a < nv; a += NL)
-      {
-        const int ax = a / dof, c = a - ax * dof;
-        sh->dw[a] = -sh->rd[a] - nb_qp_ct<NL>(tb, sh->La, ax, c) - sh->gq[a] * tau_q2;
-      }
-      g.sync();
-      nb_qp_cholsolve<NL>(g, sh, nv, sh->dw);
+      nb_qp_ct_all<NL>(g, tb, sh->La, sh->dw, sh->rd, -1.0, -1.0, sh->gq, -tau_q2);
+      nb_qp_solve_ldl<NL>(g, sh, nv, sh->dw);
       nb_qp_features<NL>(g, tb, sh, sh->dy, sh->dw, false);
       g.sync();
-      acc = NbPassAcc{ 0.0, 0.0, 1e300, 0.0, 0.0 };
+      acc = NbPassAcc{ 0.0, 0.0, 0.0, 0.0, 0.0 };
       nb_qp_pass<NL, NB_PASS_DIR_CORR>(g, cs, tb, sh, R, sigmu, 0.0, acc);
-      amax = g.min(acc.amax);
+      rmax = g.max(acc.rmax);
       double ds_q = 0.0, dl_q = 0.0;
       if (has_qc)
       {
@@ -593,11 +662,10 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
         for (int a = 0; a < nv; a++) gd += sh->gq[a] * sh->dw[a];
         ds_q = -rp_q - gd;
         dl_q = (-rc_q - lam_q * ds_q) / s_q;
-        if (ds_q < 0.0) amax = fmin(amax, -s_q / ds_q);
-        if (dl_q < 0.0) amax = fmin(amax, -lam_q / dl_q);
+        rmax = fmax(rmax, fmax(-ds_q / s_q, -dl_q / lam_q));
       }
       const double eta = 1.0 - 1.0 / ((it + 3.0) * (it + 3.0));
-      double al = eta * amax;
+      double al = rmax > 0.0 ? eta / rmax : 1.0;
       if (al > 1.0) al = 1.0;
       nb_qp_pass<NL, NB_PASS_UPDATE>(g, cs, tb, sh, R, 0.0, al, acc);
       if (has_qc)

@@ -45,7 +45,7 @@ extern "C" int emul_replan_batch(const nb_params* par, const double* pb, const i
   in.hull_ptr = a->hull_ptr, in.hull_cnt = a->hull_cnt, in.hull_xy = a->hull_xy, in.nih0 = a->nih0, in.st_ptr = st_ptr, in.st_xy = st_xy;
   in.esv_cnt = a->esv_cnt, in.esv_alpha = a->esv_alpha, in.esv_active = a->esv_active;
   in.bp_cnt = a->bp_cnt, in.bp_xy = a->bp_xy, in.pb = pb;
-  std::vector<double> lines((size_t)NB_NPOL * LS * 3), cl((size_t)NB_NPOL * LS * 3), rows((size_t)4 * RS);
+  std::vector<double> lines((size_t)NB_NPOL * LS * 3), cl((size_t)NB_NPOL * LS * 3), rows((size_t)5 * RS);
   std::vector<uint8_t> ok((size_t)NB_NPOL * LS), keep((size_t)NB_NPOL * LS), valid(LS + 1);
   std::vector<double> px(LS + 1), py(LS + 1);
   int red[1], hull[NB_PRUNE_KMAX + 1], misc[8];
@@ -66,7 +66,7 @@ extern "C" int emul_replan_batch(const nb_params* par, const double* pb, const i
     const int nl = nb_compact_lines<1>(g, n, LS, lines.data(), prune ? keep.data() : ok.data(), cl.data(), lstart);
     if (n_lines_out) n_lines_out[b] = nl;
     NbQpRows R;
-    R.s = rows.data(), R.lam = R.s + RS, R.dsa = R.lam + RS, R.dla = R.dsa + RS, R.cl = cl.data(), R.lstart = lstart;
+    R.s = rows.data(), R.lam = R.s + RS, R.dsa = R.lam + RS, R.dla = R.dsa + RS, R.inv = R.dla + RS, R.cl = cl.data(), R.lstart = lstart;
     double xout[96], obj = 0;
     int it0 = 0, it1 = 0, status = NB_STATUS_FAILED;
     bool okq = nb_qp_solve<1>(g, cs, &tabs[n - 1], sh, R, ci, nl, xout, &it0, &obj);
