@@ -306,11 +306,13 @@ __global__ void k_samples(NbConsts cs, int B, const double* t_start, const doubl
 __global__ void k_postcheck(NbConsts cs, int B, const int* n_int, const double* coeff, const double* t_start,
                             const double* recs, const uint8_t* late, double delta, int* collide, int* err)
 {
-  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j)
-  if (k >= (size_t)B * cs.N) return;
-  const int j = (int)(k % cs.N), b = (int)(k / cs.N);
-  if (!late[k]) return;
-  const int r = nb_pwp_collides(cs, coeff + (size_t)b * 96, n_int[b], t_start[b], recs + (size_t)j * NB_REC, delta);
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j, i)
+  if (k >= (size_t)B * cs.N * NB_NPOL) return;
+  const int i = (int)(k % NB_NPOL);
+  const size_t bj = k / NB_NPOL;
+  const int j = (int)(bj % cs.N), b = (int)(bj / cs.N);
+  if (!late[bj] || i >= n_int[b]) return;
+  const int r = nb_pwp_collides_interval(cs, coeff + (size_t)b * 96, n_int[b], i, t_start[b], recs + (size_t)j * NB_REC, delta);
   if (r < 0) *err = 3;
   if (r > 0) atomicOr(collide + b, 1);
 }
@@ -969,7 +971,7 @@ extern "C" int nb_postcheck_batch(nb_handle* h, int32_t B, int32_t space, const 
   if ((rc = stage_in(h, 4, space, late, (size_t)B * N, st, &dl))) return rc;
   if ((rc = stage_out(h, 0, space, collide, (size_t)B, &dcol))) return rc;
   NB_CUDA(cudaMemsetAsync(dcol, 0, (size_t)B * sizeof(int), st));
-  k_postcheck<<<(unsigned)(((size_t)B * N + 127) / 128), 128, 0, st>>>(h->cs, B, dn, dc, dt, dr, dl, delta, dcol, (int*)h->err.p);
+  k_postcheck<<<(unsigned)(((size_t)B * N * NB_NPOL + 127) / 128), 128, 0, st>>>(h->cs, B, dn, dc, dt, dr, dl, delta, dcol, (int*)h->err.p);
   h->launches += 1;
   NB_CUDA(cudaGetLastError());
   if (space == NB_HOST)

@@ -298,32 +298,42 @@ NB_HD bool nb_gjk_collision(const double* v1, int n1, const double* v2, int n2)
   return false;
 }
 
-// Neptune::trajsAndPwpAreInCollision2d (neptune.cpp:767-806): my optimised pwp (n intervals from
-// t_start) against one other agent's record.  Returns 1 collision, 0 free, -1 capacity.
-NB_HD int nb_pwp_collides(const NbConsts& cs, const double* coeff /*[3][8][4]*/, int n, double t_start, const double* rec,
-                          double delta)
+// One interval of Neptune::trajsAndPwpAreInCollision2d (neptune.cpp:781-802): my MINVO control points of
+// interval i (P * A_rest_pos_basis_t_inverse_, :786-789) against the other agent's inflated hull over
+// the same window.  Returns 1 collision, 0 free, -1 capacity.
+NB_HD int nb_pwp_collides_interval(const NbConsts& cs, const double* coeff /*[3][8][4]*/, int n, int i, double t_start,
+                                   const double* rec, double delta)
 {
   const double t_end = NB_ADD(t_start, NB_MUL(cs.T, (double)n));
   const double deltaT = NB_SUB(t_end, t_start) / n;
   if (fabs(NB_SUB(deltaT, cs.T)) > 0.1) return 1;  // :772-780
+  double A[8], hull[2 * NB_HMAX], nih0[2];
+  int idx[2];
+  for (int k = 0; k < 4; k++)
+  {
+    double x = 0, y = 0;
+    for (int r = 0; r < 4; r++)
+    {
+      x = NB_ADD(x, NB_MUL(coeff[4 * i + r], cs.Ainv[r * 4 + k]));
+      y = NB_ADD(y, NB_MUL(coeff[32 + 4 * i + r], cs.Ainv[r * 4 + k]));
+    }
+    A[2 * k] = x, A[2 * k + 1] = y;
+  }
+  const double w0 = NB_ADD(t_start, NB_MUL(deltaT, (double)i)), w1 = NB_ADD(t_start, NB_MUL(deltaT, (double)(i + 1)));
+  const int hn = nb_hull_of_window(cs, rec, w0, w1, delta, hull, nih0, idx);
+  if (hn < 0) return -1;
+  return nb_gjk_collision(hull, hn < NB_HMAX ? hn : NB_HMAX, A, 4) ? 1 : 0;
+}
+
+// Neptune::trajsAndPwpAreInCollision2d (neptune.cpp:767-806): all intervals (used by the host emulation;
+// the device kernel runs one interval per thread)
+NB_HD int nb_pwp_collides(const NbConsts& cs, const double* coeff /*[3][8][4]*/, int n, double t_start, const double* rec,
+                          double delta)
+{
   for (int i = 0; i < n; i++)
   {
-    double A[8], hull[2 * NB_HMAX], nih0[2];
-    int idx[2];
-    for (int k = 0; k < 4; k++)
-    {  // pointsA = P * A_rest_pos_basis_t_inverse_  (:786-789)
-      double x = 0, y = 0;
-      for (int r = 0; r < 4; r++)
-      {
-        x = NB_ADD(x, NB_MUL(coeff[4 * i + r], cs.Ainv[r * 4 + k]));
-        y = NB_ADD(y, NB_MUL(coeff[32 + 4 * i + r], cs.Ainv[r * 4 + k]));
-      }
-      A[2 * k] = x, A[2 * k + 1] = y;
-    }
-    const double w0 = NB_ADD(t_start, NB_MUL(deltaT, (double)i)), w1 = NB_ADD(t_start, NB_MUL(deltaT, (double)(i + 1)));
-    const int hn = nb_hull_of_window(cs, rec, w0, w1, delta, hull, nih0, idx);
-    if (hn < 0) return -1;
-    if (nb_gjk_collision(hull, hn < NB_HMAX ? hn : NB_HMAX, A, 4)) return 1;
+    const int r = nb_pwp_collides_interval(cs, coeff, n, i, t_start, rec, delta);
+    if (r != 0) return r;
   }
   return 0;
 }
