@@ -217,3 +217,47 @@ def test_replan_cycle_matches_oracle_composite(capi, oracle, cfg, seed):
         assert np.array_equal(rec[bi, 18:].reshape(3, 16, 4)[:, :n], o["coeff_out"][bi, :, :n])
     del cyc
     torch.cuda.synchronize()
+
+
+def test_cpp_shim_polysolvergurobi_and_separator(capi, oracle, tmp_path):
+    """The C++ drop-in classes (PolySolverGurobi / separator::Separator with the reference's method
+    names and call order) through the C-ABI, against the oracle on the same agent."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "_build", "test_shim")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(root, "tests", "cpp")], check=True, capture_output=True)
+    par = config("mtlp5")
+    sc = make_scene(par, 2002, sync=False)
+    b = sc.batch
+    ref = ReplanResult.empty(b)
+    assert oracle.replan_batch(b, ref, 1) == 0
+    for a in (0, 2):
+        n, N, NH = int(b.n_int[a]), par.num_of_agents, b.n_hull_slots
+        lines = [f"{N} {int(b.agent_id[a])} {n} {NH} {par.T_span!r} {par.weight!r}",
+                 " ".join(repr(float(v)) for v in (par.x_min, par.x_max, par.y_min, par.y_max, par.z_min, par.z_max)),
+                 f"{par.v_max!r} {par.a_max!r}"]
+        lines += [f"{float(p[0])!r} {float(p[1])!r}" for p in np.asarray(par.pb, float)]
+        for ax in range(3):
+            for i in range(n):
+                lines.append(" ".join(repr(float(v)) for v in b.coeff_init[a, ax, i]))
+        for s in range(NH):
+            for i in range(n):
+                k = (a * NH + s) * 8 + i
+                pts = b.hull_xy[b.hull_ptr[k]:b.hull_ptr[k + 1]]
+                lines.append(str(len(pts)) + " " + " ".join(f"{float(p[0])!r} {float(p[1])!r}" for p in pts))
+        fn = tmp_path / f"agent{a}.txt"
+        fn.write_text("\n".join(lines) + "\n")
+        out = subprocess.run([exe, str(fn)], check=True, capture_output=True, text=True).stdout.split("\n")
+        ok, status, obj, ntraj = out[0].split()
+        assert int(status) == ref.status[a] and int(ok) == int(ref.status[a] != 2)
+        co = np.array([[float(v) for v in ln.split()] for ln in out[1:1 + 3 * n]]).reshape(3, n, 4)
+        assert np.abs(co - ref.coeff_out[a, :, :n]).max() <= 1e-6 * max(1.0, np.abs(ref.coeff_out[a]).max())
+        assert abs(float(obj) - ref.obj[a]) <= 1e-8 * max(1.0, abs(ref.obj[a]))
+        assert abs(int(ntraj) - n * par.T_span / par.dc) <= 1.5
+        s_ok = int(out[1 + 3 * n].split()[0])      # separator::Separator::solveModel on hulls[0][0]
+        k0 = a * NH * 8
+        first = b.hull_xy[b.hull_ptr[k0]:b.hull_ptr[k0 + 1]]
+        far = np.array([[100.0, 100.0], [101.0, 100.0], [101.0, 101.0], [100.0, 101.0]])
+        assert s_ok == int(len(first) > 0 and oracle.separate(first, far)[0])
