@@ -100,6 +100,15 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return int(json.load(f)["per_launch_dram_bytes"][kernel])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -278,7 +287,8 @@ def run_ours(args):
                 "kernels_ms": {"k_lines": float(kt[:, 0].mean()), "k_qp": float(kt[:, 1].mean())},
                 "stage_ms": stage,
                 "roofline": {"bound": "hbm", "kernel": ["k_lines", "k_qp"][dom], "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": which,
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(["k_lines", "k_qp"][dom]),
+                             "peak_source": which,
                              "algorithmic_bytes_per_launch": alg_bytes,
                              "note": "latency/FP64-issue bound at this size, not HBM bound (DESIGN.md)"},
                 "status_hist": {str(k2): int((st == k2).sum()) for k2 in (0, 1, 2)},
