@@ -33,8 +33,10 @@ AGENTS_PER_GPU = 64
 SEED = 4004
 
 
-def world_params(n_gpus: int):
-    from neptune_b200.params import Params
+def world_params(n_gpus: int, workload: str = "grid64"):
+    from neptune_b200.params import Params, config
+    if workload == "grid1024":   # BASELINE.json configs[4]: 1024 agents / 200 static obstacles, fixed world
+        return config("grid1024")
     nx, ny = 8, 8 * n_gpus
     pitch = 8.0
     xs = (np.arange(nx) - (nx - 1) / 2.0) * pitch
@@ -47,11 +49,21 @@ def world_params(n_gpus: int):
     return p
 
 
-def make_world(n_gpus: int, rank: int, n_scenes: int, ent_backend=None):
+def rank_agents(par, n_gpus: int, rank: int, workload: str):
+    from neptune_b200.cycle import shard_agents
+    if workload == "grid1024":   # strong scaling: the fixed world is split over the ranks
+        return shard_agents(par.num_of_agents, n_gpus, rank)
+    return np.arange(rank * AGENTS_PER_GPU, (rank + 1) * AGENTS_PER_GPU)
+
+
+def make_world(n_gpus: int, rank: int, n_scenes: int, ent_backend=None, workload: str = "grid64", agents=None):
     from neptune_b200.scenes import make_scene
-    par = world_params(n_gpus)
-    agents = np.arange(rank * AGENTS_PER_GPU, (rank + 1) * AGENTS_PER_GPU)
-    return par, [make_scene(par, SEED + k, agents=agents, ent_backend=ent_backend) for k in range(n_scenes)]
+    par = world_params(n_gpus, workload)
+    if agents is None:
+        agents = rank_agents(par, n_gpus, rank, workload)
+    seed = SEED if workload == "grid64" else 5005
+    return par, [make_scene(par, seed + k, agents=agents, ent_backend=ent_backend,
+                            pack_hulls=(par.num_of_agents <= 256)) for k in range(n_scenes)]
 
 
 class ClockSampler:
@@ -146,7 +158,10 @@ def run_reference(args):
         return
     from oracle import oracle as orc
     from tests.ent_backends import OracleEntBackend
-    par, scenes = make_world(args.gpus, 0, 1, OracleEntBackend(orc))
+    agents = None
+    if args.workload == "grid1024":   # bounded sample: the first 32 agents of the rank-0 shard
+        agents = np.arange(32)
+    par, scenes = make_world(args.gpus, 0, 1, OracleEntBackend(orc), args.workload, agents)
     threads = os.cpu_count() or 1
     for _ in range(args.warmup):
         cpu_cycle(scenes[0], threads)
@@ -160,18 +175,28 @@ def run_reference(args):
               f"each against all {par.num_of_agents - 1} others; oracle/neptune_oracle.c orc_cycle_batch")
     line = {"impl": "reference", "metric": "replans_per_sec", "value": val, "unit": "replans/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(par, args.gpus),
+            "higher_is_better": True, "scaling": scaling_kind(args.workload), "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(par, args.gpus, args.workload),
             "cpu_baseline": {"value": val, "unit": "replans/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "replans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def config_dict(par, n_gpus):
-    return {"workload": f"grid world, {AGENTS_PER_GPU} agents/GPU x {n_gpus} GPU = {par.num_of_agents} agents "
-                        "(BASELINE.json configs[3] at N=1), random goals, no static obstacles, faithful (no culling)",
-            "agents": par.num_of_agents, "agents_per_gpu": AGENTS_PER_GPU, "num_pol": par.num_pol,
-            "T_span": par.T_span, "seed": SEED, "l2": "flushed between timed iterations (256 MiB write)",
+def scaling_kind(workload: str) -> str:
+    return "strong" if workload == "grid1024" else "weak"
+
+
+def config_dict(par, n_gpus, workload="grid64"):
+    if workload == "grid1024":
+        wl = (f"BASELINE.json configs[4]: {par.num_of_agents} agents / {par.num_of_static_obst} static obstacles, "
+              f"32x32 base grid, sharded over {n_gpus} GPU(s), random goals, faithful (no culling)")
+    else:
+        wl = (f"grid world, {AGENTS_PER_GPU} agents/GPU x {n_gpus} GPU = {par.num_of_agents} agents "
+              "(BASELINE.json configs[3] at N=1), random goals, no static obstacles, faithful (no culling)")
+    return {"workload": wl, "agents": par.num_of_agents, "agents_per_gpu": par.num_of_agents // n_gpus
+            if workload == "grid1024" else AGENTS_PER_GPU, "static_obstacles": par.num_of_static_obst,
+            "num_pol": par.num_pol, "T_span": par.T_span, "seed": SEED if workload == "grid64" else 5005,
+            "l2": "flushed between timed iterations (256 MiB write)",
             "parallelism": f"agents sharded over {n_gpus} rank(s); one all-gather of committed trajectories per cycle"}
 
 
@@ -191,11 +216,16 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    par = world_params(args.gpus)
-    agents = np.arange(rank * AGENTS_PER_GPU, (rank + 1) * AGENTS_PER_GPU)
-    cyc = ReplanCycle(par, agents, dev, world=world)
+    par = world_params(args.gpus, args.workload)
+    agents = rank_agents(par, args.gpus, rank, args.workload)
+    static = None
+    if par.num_of_static_obst:   # static obstacles are part of the world: build them once, before the solver
+        from neptune_b200.scenes import make_scene
+        s0 = make_scene(par, 5005, agents=agents[:1], pack_hulls=False)
+        static = (s0.batch.st_ptr, s0.batch.st_xy, s0.strep)
+    cyc = ReplanCycle(par, agents, dev, static=static, world=world)
     # the workload generator fills entanglement states through the product's own K3 kernels
-    _, scenes = make_world(args.gpus, rank, args.scenes, capi.DeviceEntBackend(cyc.solver))
+    _, scenes = make_world(args.gpus, rank, args.scenes, capi.DeviceEntBackend(cyc.solver), args.workload)
     B = cyc.B
     hins = [cyc.host_inputs(sc) for sc in scenes]
     hout = cyc.host_outputs()
@@ -275,12 +305,14 @@ def run_ours(args):
         dom = int(np.argmax(kt.mean(axis=0)))
         dom_ms = float(kt[:, dom].mean())
         alg_bytes = float(np.mean([sc.batch.algorithmic_bytes() for sc in scenes]))
+        if scenes[0].batch.hull_xy.shape[0] == 0:   # hulls were built on the device only: count their real vertices
+            alg_bytes += 16.0 * float(cyc.o["hull_cnt"].sum().item()) + 16.0 * float(scenes[0].known.sum()) * par.num_pol
         peak, which = measured_peak_gbs()
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
         line = {"metric": "replans_per_sec", "value": value, "unit": "replans/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config_dict(par, world),
+                "scaling": scaling_kind(args.workload), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_dict(par, world, args.workload),
                 "p50_ms_per_replan_cycle": float(np.median(step_ms)),
                 "e2e": {"value": e2e, "unit": "replans/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches),
@@ -295,7 +327,7 @@ def run_ours(args):
                 "postcheck": {"entangled": int(ent.sum()), "collide": int(col.sum())},
                 "ipm_iters_mean": float(itn.sum(axis=1).mean()),
                 "clocks": clocks}
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.workload == "grid64":
             v, reps, el, ref = cpu_baseline(scenes[0], args.cpu_budget, os.cpu_count() or 1)
             line["cpu_baseline"] = {"value": v, "unit": "replans/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": f"{B} agents x {reps} whole cycles of scene 0 ({el:.1f} s), "
@@ -312,6 +344,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=4)
+    ap.add_argument("--workload", default="grid64", choices=["grid64", "grid1024"],
+                    help="grid64: configs[3] family, 64 agents per GPU (default); grid1024: configs[4], fixed world")
     ap.add_argument("--cpu-budget", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -257,8 +257,11 @@ def _static_rep(poly, theta):
 
 
 def make_scene(par: Params, seed: int, *, n_fixed: int | None = None, sync: bool = True,
-               ent_backend=None, agents: np.ndarray | None = None, spread: float | None = None) -> Scene:
-    """Build one replan cycle's inputs for the planning agents `agents` (0-based, default all)."""
+               ent_backend=None, agents: np.ndarray | None = None, spread: float | None = None,
+               pack_hulls: bool = True) -> Scene:
+    """Build one replan cycle's inputs for the planning agents `agents` (0-based, default all).
+    pack_hulls=False skips the host-side packed hull arrays (large worlds: the device builds the hulls
+    from the committed-trajectory records, K1)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     N, M, T, S = par.num_of_agents, par.num_of_static_obst, par.T_span, par.num_sample_per_interval
     pb = np.asarray(par.pb, float)
@@ -347,10 +350,11 @@ def make_scene(par: Params, seed: int, *, n_fixed: int | None = None, sync: bool
             if j == b:
                 continue
             hs = hull_cache[(ts, j)]
-            for i in range(par.num_pol):
-                cnt[bi, j, i] = len(hs[i][0])
-                chunks.append(hs[i][0])
-                nih0[bi, j, i] = hs[i][1][0]
+            if pack_hulls:
+                for i in range(par.num_pol):
+                    cnt[bi, j, i] = len(hs[i][0])
+                    chunks.append(hs[i][0])
+                    nih0[bi, j, i] = hs[i][1][0]
             samp[bi, j] = samp_cache[(ts, j)]
     hull_ptr = np.zeros(B * NH * NPOL + 1, np.int64)
     np.cumsum(cnt.reshape(-1), out=hull_ptr[1:])
@@ -359,15 +363,14 @@ def make_scene(par: Params, seed: int, *, n_fixed: int | None = None, sync: bool
     # front-end stub: pwp_init per planning agent against the other agents' window AABBs
     coeff_init = np.zeros((B, 3, NPOL, 4))
     n_int = np.zeros(B, np.int32)
+    box_cache = {ts: [np.array([[h[:, 0].min(), h[:, 1].min(), h[:, 0].max(), h[:, 1].max()]
+                                 for j in range(N) for h in (hull_cache[(ts, j)][i][0],)]) for i in range(par.num_pol)]
+                 for ts in uniq}
+    bx = np.array([[q[0] - 0.7, q[1] - 0.7, q[0] + 0.7, q[1] + 0.7] for q in pb])
     for bi, b in enumerate(agents):
         ts = float(t_start[bi])
-        boxes = []
-        for i in range(par.num_pol):
-            bl = [[h[:, 0].min(), h[:, 1].min(), h[:, 0].max(), h[:, 1].max()]
-                  for j in range(N) if j != b for h in (hull_cache[(ts, j)][i][0],)]
-            bl = np.array(bl).reshape(-1, 4)
-            bx = np.array([[q[0] - 0.7, q[1] - 0.7, q[0] + 0.7, q[1] + 0.7] for q in pb])
-            boxes.append(np.concatenate([bl, bx, st_boxes], axis=0))
+        boxes = [np.concatenate([np.delete(box_cache[ts][i], b, axis=0), bx, st_boxes], axis=0)
+                 for i in range(par.num_pol)]
         nmax = par.num_pol if n_fixed is None else n_fixed
         cx, cy = lattice_path(par, Ainv, V, state_A[bi, 0, :2], state_A[bi, 1, :2], state_A[bi, 2, :2],
                               goals[b, :2], pb[b], boxes, nmax)
