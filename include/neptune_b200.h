@@ -115,6 +115,8 @@ typedef struct nb_replan_args
   const int32_t* hull_cnt;    /* optional [B*slots*8] vertex counts; NULL: count = hull_ptr[k+1]-hull_ptr[k] (CSR).
                                  With counts, hull_ptr needs only B*slots*8 entries (nb_hulls_batch output). */
   const double* nih0;         /* [B][N][8][2] col(0) of hullsNoInflation_[j][i]; NaN = unknown */
+  const int32_t* nih0_group;  /* optional [B]: nih0 is then [G][N][8][2] and agent b reads block nih0_group[b]
+                                 (agents planning over the same windows share it, see nb_hull_index_batch) */
   const int32_t* esv_cnt;     /* [B][9][2] (alphas.size(), bendPointsIdx.size()) of entStateVec[i] */
   const int32_t* esv_alpha;   /* [B][9][ent_cap][2] */
   const int32_t* esv_active;  /* [B][9][N+M] active_cases */
@@ -175,6 +177,24 @@ int nb_generate_traj_batch(nb_handle* h, int32_t B, int32_t space, const int32_t
 int nb_hulls_batch(nb_handle* h, int32_t B, int32_t space, const double* t_start, const double* recs,
                    const uint8_t* known, double delta, double* hull_xy, int32_t* hull_cnt, int64_t* hull_ptr,
                    double* nih0, double* samp, int32_t* idx, void* stream);
+
+/*
+ * Window sharing.  Agents whose replans start at the same t_start look at the same windows of every
+ * other agent, so hulls / samples need to be built once per distinct t_start ("group"), not once per
+ * planning agent: call nb_hulls_batch with B = G groups, then this function to give every planning agent
+ * its own (hull_ptr, hull_cnt) view of the shared hulls: slot j of agent b points at hull (group[b], j, i)
+ * and is empty when j is b itself or known[b][j] == 0.  Results are identical to the per-agent call.
+ * hull_cnt_g [G][N][8] -> hull_ptr [B][N][8], hull_cnt [B][N][8].
+ */
+int nb_hull_index_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const int32_t* group,
+                        const uint8_t* known, const int32_t* hull_cnt_g, int64_t* hull_ptr, int32_t* hull_cnt,
+                        void* stream);
+
+/* nb_postcheck_batch on hulls already built by nb_hulls_batch from the late records, per group:
+ * hull_xy_g [G][N][8][NB_HULL_STRIDE][2], hull_cnt_g [G][N][8]. */
+int nb_postcheck_hulls_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
+                             const int32_t* group, const double* hull_xy_g, const int32_t* hull_cnt_g,
+                             const uint8_t* late, int32_t* collide, void* stream);
 
 /*
  * Replaces the geometric half of Neptune::safetyCheckAfterReplan (neptune.cpp:719-765):

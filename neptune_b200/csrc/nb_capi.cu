@@ -317,6 +317,46 @@ __global__ void k_postcheck(NbConsts cs, int B, const int* n_int, const double* 
   if (r > 0) atomicOr(collide + b, 1);
 }
 
+__global__ void k_hull_index(int B, int N, const int* agent_id, const int* group, const uint8_t* known,
+                             const int* hull_cnt_g, int64_t* hull_ptr, int* hull_cnt)
+{
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j, i)
+  if (k >= (size_t)B * N * NB_NPOL) return;
+  const int i = (int)(k % NB_NPOL);
+  const size_t bj = k / NB_NPOL;
+  const int j = (int)(bj % N), b = (int)(bj / N);
+  const size_t src = ((size_t)group[b] * N + j) * NB_NPOL + i;
+  hull_ptr[k] = (int64_t)src * NB_HMAX;
+  hull_cnt[k] = (j == agent_id[b] - 1 || !known[bj]) ? 0 : hull_cnt_g[src];
+}
+
+__global__ void k_postcheck_hulls(NbConsts cs, int B, const int* n_int, const double* coeff, const int* group,
+                                  const double* hull_xy_g, const int* hull_cnt_g, const uint8_t* late, int* collide)
+{
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j, i)
+  if (k >= (size_t)B * cs.N * NB_NPOL) return;
+  const int i = (int)(k % NB_NPOL);
+  const size_t bj = k / NB_NPOL;
+  const int j = (int)(bj % cs.N), b = (int)(bj / cs.N);
+  if (!late[bj] || i >= n_int[b]) return;
+  const size_t src = ((size_t)group[b] * cs.N + j) * NB_NPOL + i;
+  const int hn = hull_cnt_g[src];
+  if (hn <= 0) return;
+  const double* cf = coeff + (size_t)b * 96;
+  double A[8];
+  for (int q = 0; q < 4; q++)
+  {  // pointsA = P * A_rest_pos_basis_t_inverse_ (neptune.cpp:786-789)
+    double x = 0, y = 0;
+    for (int r = 0; r < 4; r++)
+    {
+      x = NB_ADD(x, NB_MUL(cf[4 * i + r], cs.Ainv[r * 4 + q]));
+      y = NB_ADD(y, NB_MUL(cf[32 + 4 * i + r], cs.Ainv[r * 4 + q]));
+    }
+    A[2 * q] = x, A[2 * q + 1] = y;
+  }
+  if (nb_gjk_collision(hull_xy_g + src * NB_HMAX * 2, hn, A, 4)) atomicOr(collide + b, 1);
+}
+
 __global__ void k_commit(int B, const int* n_int, const double* coeff, const double* t_start, double T, double* recs)
 {
   const int b = blockIdx.x;
@@ -538,6 +578,12 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   if ((rc = stage_in(h, 3, sp, a->hull_ptr, (size_t)B * NH * 8 + (a->hull_cnt ? 0 : 1), st, &in.hull_ptr))) return rc;
   if ((rc = stage_in(h, 4, sp, a->hull_xy, (size_t)a->hull_nvert * 2, st, &in.hull_xy))) return rc;
   if ((rc = stage_in(h, 11, sp, a->hull_cnt, (size_t)B * NH * 8, st, &in.hull_cnt))) return rc;
+  if (a->nih0_group && sp == NB_HOST)
+  {
+    g_err = "nb_replan_batch: nih0_group is only supported with device pointers";
+    return NB_ERR_ARG;
+  }
+  in.nih0_group = a->nih0_group;
   if ((rc = stage_in(h, 5, sp, a->nih0, (size_t)B * N * 16, st, &in.nih0))) return rc;
   if ((rc = stage_in(h, 6, sp, a->esv_cnt, (size_t)B * 18, st, &in.esv_cnt))) return rc;
   if ((rc = stage_in(h, 7, sp, a->esv_alpha, (size_t)B * 9 * cap * 2, st, &in.esv_alpha))) return rc;
@@ -1005,5 +1051,48 @@ extern "C" int nb_commit_records_batch(nb_handle* h, int32_t B, int32_t space, c
     NB_CUDA(cudaMemcpyAsync(recs_out, dr, (size_t)B * NB_REC * sizeof(double), cudaMemcpyDeviceToHost, st));
     NB_CUDA(cudaStreamSynchronize(st));
   }
+  return NB_OK;
+}
+
+extern "C" int nb_hull_index_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const int32_t* group,
+                                   const uint8_t* known, const int32_t* hull_cnt_g, int64_t* hull_ptr, int32_t* hull_cnt,
+                                   void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  if (space != NB_DEVICE)
+  {
+    g_err = "nb_hull_index_batch: device pointers only (it indexes device-resident hulls)";
+    return NB_ERR_ARG;
+  }
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)B * h->par.num_agents * NB_NPOL;
+  k_hull_index<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(B, h->par.num_agents, agent_id, group, known, hull_cnt_g, hull_ptr,
+                                                          hull_cnt);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+extern "C" int nb_postcheck_hulls_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
+                                        const int32_t* group, const double* hull_xy_g, const int32_t* hull_cnt_g,
+                                        const uint8_t* late, int32_t* collide, void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  if (space != NB_DEVICE)
+  {
+    g_err = "nb_postcheck_hulls_batch: device pointers only";
+    return NB_ERR_ARG;
+  }
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)B * h->par.num_agents * NB_NPOL;
+  NB_CUDA(cudaMemsetAsync(collide, 0, (size_t)B * sizeof(int), st));
+  k_postcheck_hulls<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(h->cs, B, n_int, coeff, group, hull_xy_g, hull_cnt_g, late,
+                                                               collide);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
   return NB_OK;
 }

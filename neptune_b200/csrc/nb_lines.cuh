@@ -20,7 +20,8 @@ struct NbLinesIn
   const int64_t* hull_ptr;   // [B*NH*8+1] (or [B*NH*8] with hull_cnt)
   const int* hull_cnt;       // optional [B*NH*8]
   const double* hull_xy;
-  const double* nih0;        // [B][N][8][2]
+  const double* nih0;        // [B][N][8][2] (or [G][N][8][2] with nih0_group)
+  const int* nih0_group;     // optional [B]
   const int64_t* st_ptr;     // [M+1]
   const double* st_xy;
   const int* esv_cnt;        // [B][9][2]
@@ -144,7 +145,7 @@ NB_HD void nb_lines_task(int tid, int b, int i, const NbConsts& cs, const NbLine
       if (case_id == 0) continue;
       const int nb = in.bp_cnt[j];
       const double* bend = in.bp_xy + (size_t)2 * cs.bp_max * j;
-      const double* posj = in.nih0 + (((size_t)b * N + j) * 8 + i) * 2;
+      const double* posj = in.nih0 + (((size_t)(in.nih0_group ? in.nih0_group[b] : b) * N + j) * 8 + i) * 2;
       if (nb < 1 || posj[0] != posj[0]) continue;
       for (int k = 1; k < nb + 1; k++)
       {

@@ -76,16 +76,18 @@ class ReplanCycle:
             bp_cnt=z(N, i32), bp_xy=z((N, par.bp_max, 2), f64),
             es_cnt=z((B, 2), i32), es_alpha=z((B, cap, 2), i32), es_beta=z((B, cap), f64), es_bend=z((B, cap), i32),
             es_active=z((B, NA), i32), prev_pos=z((B, N + 1, 2), f64), prev_pos_agent=z((B, N, 2), f64), cur=z((B, 2), f64))
-        # intermediates and outputs
+        self.d["late_recs"] = z((N, REC), f64)   # trajectories received while optimising (post-check)
+        # intermediates and outputs (group-shaped buffers are sized by _ensure_groups)
         self.o = dict(
-            hull_xy=z((B, N, NPOL, HS, 2), f64), hull_cnt=z((B, N, NPOL), i32), hull_ptr=z(B * N * NPOL, i64),
-            nih0=z((B, N, NPOL, 2), f64), samp=z((B, N, par.num_pol, S + 1, 2), f64), samp0=z((B, N, 2), f64),
+            hull_ptr=z(B * N * NPOL, i64), hull_cnt=z((B, N, NPOL), i32), samp0=z((B, N, 2), f64),
             esA_cnt=z((B, 2), i32), esA_alpha=z((B, cap, 2), i32), esA_beta=z((B, cap), f64), esA_bend=z((B, cap), i32),
             esA_active=z((B, NA), i32),
             esC_cnt=z((B, 2), i32), esC_alpha=z((B, cap, 2), i32), esC_beta=z((B, cap), f64), esC_bend=z((B, cap), i32),
             esC_active=z((B, NA), i32),
             coeff_out=z((B, 3, NPOL, 4), f64), obj=z(B, f64), status=z(B, i32), iters=z((B, 2), i32),
             entangled=z(B, i32), collide=z(B, i32), new_recs=z((B, REC), f64))
+        self.G = 0
+        self.d["group"] = z(B, i32)
         self.gathered = None
         self.delta = 2.0 * par.drone_radius  # bbox/2 + drone_radius with bbox = 2 drone_radius (neptune_ros.cpp:447-449)
         self._lib = capi.lib()
@@ -93,8 +95,31 @@ class ReplanCycle:
         self.profile = False   # True: synchronise and time every stage of step() with CUDA events
         self.stage_ms = {}
 
+    def _ensure_groups(self, G: int):
+        """Buffers shaped by the number of distinct t_start values (window groups)."""
+        if G == self.G:
+            return
+        torch, N, S = self.torch, self.N, self.par.num_sample_per_interval
+        f64, i32, u8, i64 = torch.float64, torch.int32, torch.uint8, torch.int64
+
+        def z(shape, dt):
+            return torch.zeros(shape, dtype=dt, device=self.dev)
+        self.G = G
+        self.d["t_group"] = z(G, f64)
+        self.d["ones_g"] = torch.ones((G, N), dtype=u8, device=self.dev)
+        for tag in ("", "_l"):   # planning-time trajectories, late trajectories
+            self.o["hull_xy_g" + tag] = z((G, N, NPOL, HS, 2), f64)
+            self.o["hull_cnt_g" + tag] = z((G, N, NPOL), i32)
+            self.o["hull_ptr_g" + tag] = z(G * N * NPOL, i64)
+            self.o["nih0_g" + tag] = z((G, N, NPOL, 2), f64)
+            self.o["samp_g" + tag] = z((G, N, self.par.num_pol, S + 1, 2), f64)
+        if G > 1:
+            self.o["samp_b"] = z((self.B, N, self.par.num_pol, S + 1, 2), f64)
+
     def _sig(self):
         P, L = C.c_void_p, self._lib
+        L.nb_hull_index_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, P, P, P]
+        L.nb_postcheck_hulls_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, P, P, P, P]
         L.nb_hulls_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, C.c_double, P, P, P, P, P, P, P]
         L.nb_entangle_predict_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, capi.NbEntState, P, P, P, P, P]
         L.nb_entangle_check_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, capi.NbEntState, P, P, P, C.c_int32, P, P]
@@ -102,7 +127,7 @@ class ReplanCycle:
         L.nb_commit_records_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, P]
 
     # ------------------------------------------------------------------ host <-> device
-    HOST_KEYS = ("agent_id", "n_int", "coeff_init", "t_start", "recs", "known", "late", "esv_cnt", "esv_alpha",
+    HOST_KEYS = ("agent_id", "n_int", "coeff_init", "t_start", "recs", "late_recs", "known", "late", "esv_cnt", "esv_alpha",
                  "esv_active", "bp_cnt", "bp_xy", "es_cnt", "es_alpha", "es_beta", "es_bend", "es_active", "prev_pos",
                  "prev_pos_agent", "cur")
     OUT_KEYS = ("coeff_out", "obj", "status", "iters", "entangled", "collide")
@@ -112,7 +137,8 @@ class ReplanCycle:
         torch = self.torch
         b = scene.batch
         src = dict(agent_id=b.agent_id, n_int=b.n_int, coeff_init=b.coeff_init, t_start=scene.t_start,
-                   recs=capi.make_records(scene.committed), known=scene.known, late=scene.known,
+                   recs=capi.make_records(scene.committed), late_recs=capi.make_records(scene.committed),
+                   known=scene.known, late=scene.known,
                    esv_cnt=b.esv_cnt, esv_alpha=b.esv_alpha, esv_active=b.esv_active, bp_cnt=b.bp_cnt, bp_xy=b.bp_xy,
                    es_cnt=scene.es0_cnt, es_alpha=scene.es0_alpha, es_beta=scene.es0_beta, es_bend=scene.es0_bend,
                    es_active=scene.es0_active, prev_pos=scene.prev_pos, prev_pos_agent=scene.prev_pos_agent,
@@ -122,11 +148,18 @@ class ReplanCycle:
             t = torch.from_numpy(np.ascontiguousarray(src[k]).astype(
                 {torch.float64: np.float64, torch.int32: np.int32, torch.uint8: np.uint8}[self.d[k].dtype]))
             out[k] = t.pin_memory() if torch.cuda.is_available() else t
+        # window groups: agents with the same t_start share hulls and samples
+        uniq, inv = np.unique(np.asarray(scene.t_start, np.float64), return_inverse=True)
+        out["t_group"] = torch.from_numpy(uniq.copy())
+        out["group"] = torch.from_numpy(inv.astype(np.int32))
+        if torch.cuda.is_available():
+            out["t_group"], out["group"] = out["t_group"].pin_memory(), out["group"].pin_memory()
         return out
 
     def upload(self, host: dict) -> int:
         n = 0
-        for k in self.HOST_KEYS:
+        self._ensure_groups(int(host["t_group"].numel()))
+        for k in self.HOST_KEYS + ("t_group", "group"):
             self.d[k].copy_(host[k], non_blocking=True)
             n += host[k].numel() * host[k].element_size()
         return n
@@ -158,13 +191,17 @@ class ReplanCycle:
                 e.record()
                 marks.append((name, e))
         mark("start")
-        chk(L.nb_hulls_batch(h, B, DEV, p(d["t_start"]), p(d["recs"]), p(d["known"]), self.delta, p(o["hull_xy"]),
-                             p(o["hull_cnt"]), p(o["hull_ptr"]), p(o["nih0"]), p(o["samp"]), None, st), "nb_hulls_batch")
+        G = self.G
+        chk(L.nb_hulls_batch(h, G, DEV, p(d["t_group"]), p(d["recs"]), p(d["ones_g"]), self.delta, p(o["hull_xy_g"]),
+                             p(o["hull_cnt_g"]), p(o["hull_ptr_g"]), p(o["nih0_g"]), p(o["samp_g"]), None, st), "nb_hulls_batch")
+        chk(L.nb_hull_index_batch(h, B, DEV, p(d["agent_id"]), p(d["group"]), p(d["known"]), p(o["hull_cnt_g"]),
+                                  p(o["hull_ptr"]), p(o["hull_cnt"]), st), "nb_hull_index_batch")
         mark("hulls_samples")
         # entangle_state_A = PredictAlphasBetas(entangle_state_)
         for k in ("cnt", "alpha", "beta", "bend", "active"):
             o["esA_" + k].copy_(d["es_" + k])
-        o["samp0"].copy_(o["samp"][:, :, 0, 0, :])
+        gl = d["group"].long()
+        o["samp0"].copy_(o["samp_g"][:, :, 0, 0, :].index_select(0, gl))
         esA = capi.NbEntState()
         esA.cnt, esA.alpha, esA.beta, esA.bend, esA.active = (p(o["esA_" + k]) for k in ("cnt", "alpha", "beta", "bend", "active"))
         chk(L.nb_entangle_predict_batch(h, B, DEV, p(d["agent_id"]), p(d["known"]), p(d["bp_cnt"]), p(d["bp_xy"]), esA,
@@ -174,9 +211,9 @@ class ReplanCycle:
         a = capi.NbReplanArgs()
         a.B, a.space, a.n_hull_slots = B, DEV, self.N
         a.agent_id, a.n_int, a.coeff_init = d["agent_id"].data_ptr(), d["n_int"].data_ptr(), d["coeff_init"].data_ptr()
-        a.hull_ptr, a.hull_xy, a.hull_cnt = o["hull_ptr"].data_ptr(), o["hull_xy"].data_ptr(), o["hull_cnt"].data_ptr()
-        a.hull_nvert = B * self.N * NPOL * HS
-        a.nih0 = o["nih0"].data_ptr()
+        a.hull_ptr, a.hull_xy, a.hull_cnt = o["hull_ptr"].data_ptr(), o["hull_xy_g"].data_ptr(), o["hull_cnt"].data_ptr()
+        a.hull_nvert = G * self.N * NPOL * HS
+        a.nih0, a.nih0_group = o["nih0_g"].data_ptr(), d["group"].data_ptr()
         a.esv_cnt, a.esv_alpha, a.esv_active = d["esv_cnt"].data_ptr(), d["esv_alpha"].data_ptr(), d["esv_active"].data_ptr()
         a.bp_cnt, a.bp_xy = d["bp_cnt"].data_ptr(), d["bp_xy"].data_ptr()
         a.coeff_out, a.obj, a.status, a.iters = (o[k].data_ptr() for k in ("coeff_out", "obj", "status", "iters"))
@@ -184,16 +221,25 @@ class ReplanCycle:
         chk(L.nb_replan_batch(h, C.byref(a), st), "nb_replan_batch")
         mark("lines_qp")
         # safetyCheckAfterReplan: geometric check against the late trajectories, then the entangle re-check
-        chk(L.nb_postcheck_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["t_start"]), p(d["recs"]), p(d["late"]),
-                                 self.delta, p(o["collide"]), st), "nb_postcheck_batch")
+        # hulls / samples of the late trajectories over the same windows (neptune.cpp:737-741, :792)
+        chk(L.nb_hulls_batch(h, G, DEV, p(d["t_group"]), p(d["late_recs"]), p(d["ones_g"]), self.delta, p(o["hull_xy_g_l"]),
+                             p(o["hull_cnt_g_l"]), p(o["hull_ptr_g_l"]), p(o["nih0_g_l"]), p(o["samp_g_l"]), None, st),
+            "nb_hulls_batch")
+        chk(L.nb_postcheck_hulls_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["group"]), p(o["hull_xy_g_l"]),
+                                       p(o["hull_cnt_g_l"]), p(d["late"]), p(o["collide"]), st), "nb_postcheck_hulls_batch")
         if self.par.enable_entangle_check:
             # entangleCheckGivenPwp works on a copy (ent_state_begin is a local in safetyCheckAfterReplan)
             esC = capi.NbEntState()
             for k in ("cnt", "alpha", "beta", "bend", "active"):
                 o["esC_" + k].copy_(o["esA_" + k])
             esC.cnt, esC.alpha, esC.beta, esC.bend, esC.active = (p(o["esC_" + k]) for k in ("cnt", "alpha", "beta", "bend", "active"))
+            if G == 1:
+                samp_ptr, shared = p(o["samp_g_l"]), 1
+            else:
+                o["samp_b"].copy_(o["samp_g_l"].index_select(0, gl))
+                samp_ptr, shared = p(o["samp_b"]), 0
             chk(L.nb_entangle_check_batch(h, B, DEV, p(d["agent_id"]), p(d["known"]), p(d["bp_cnt"]), p(d["bp_xy"]), esC,
-                                          p(d["n_int"]), p(o["coeff_out"]), p(o["samp"]), 0, p(o["entangled"]), st),
+                                          p(d["n_int"]), p(o["coeff_out"]), samp_ptr, shared, p(o["entangled"]), st),
                 "nb_entangle_check_batch")
         mark("postcheck")
         chk(L.nb_commit_records_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["t_start"]), p(o["new_recs"]), st),
