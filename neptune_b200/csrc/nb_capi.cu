@@ -69,7 +69,7 @@ struct nb_handle
   // staging of NB_HOST arguments
   DevBuf in[16], out[8];
   // scratch
-  DevBuf lines, line_ok, keep, cl, rows, err;
+  DevBuf lines, line_ok, keep, cl, rows, err, ent_scratch;
   int qp_smem_set = 0;
   int profiling = 0;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -448,7 +448,7 @@ extern "C" void nb_destroy(nb_handle* h)
   for (auto& b : h->out) b.release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
-  h->lines.release(), h->line_ok.release(), h->keep.release(), h->cl.release(), h->rows.release(), h->err.release();
+  h->lines.release(), h->line_ok.release(), h->keep.release(), h->cl.release(), h->rows.release(), h->err.release(), h->ent_scratch.release();
   delete h;
 }
 
@@ -805,12 +805,12 @@ int ent_common(nb_handle* h, NbEntArgs* a, int mode, int B, int space, const int
   if ((rc = stage_in(h, 1, space, known, (size_t)B * N, st, &a->known))) return rc;
   if ((rc = stage_in(h, 2, space, bp_cnt, (size_t)N, st, &a->bp_cnt))) return rc;
   if ((rc = stage_in(h, 3, space, bp_xy, (size_t)N * h->par.bp_max * 2, st, &a->bp_xy))) return rc;
-  if (h->keep.ensure((size_t)B * (N + M) * sizeof(int)))  // reuse as act_old scratch when larger
+  if (h->ent_scratch.ensure((size_t)B * (N + M) * sizeof(int)))  // own scratch: K3 may overlap K2/K4 on another stream
   {
     g_err = "cudaMalloc failed";
     return NB_ERR_CUDA;
   }
-  a->act_old = (int*)h->keep.p;
+  a->act_old = (int*)h->ent_scratch.p;
   a->err = (int*)h->err.p;
   return NB_OK;
 }

@@ -92,8 +92,11 @@ class ReplanCycle:
         self.delta = 2.0 * par.drone_radius  # bbox/2 + drone_radius with bbox = 2 drone_radius (neptune_ros.cpp:447-449)
         self._lib = capi.lib()
         self._sig()
-        self.profile = False   # True: synchronise and time every stage of step() with CUDA events
+        self.profile = False   # True: one stream, synchronise and time every stage of step() with CUDA events
         self.stage_ms = {}
+        self.overlap = True    # independent stages on side streams (predict; late-trajectory hulls)
+        self.side = [torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)] \
+            if self.dev.type == "cuda" else []
 
     def _ensure_groups(self, G: int):
         """Buffers shaped by the number of distinct t_start values (window groups)."""
@@ -192,21 +195,42 @@ class ReplanCycle:
                 marks.append((name, e))
         mark("start")
         G = self.G
+        main = torch.cuda.current_stream()
+        par_streams = self.overlap and not self.profile and len(self.side) == 2
+        sB, sC = (self.side if par_streams else (main, main))
+        stB, stC = C.c_void_p(sB.cuda_stream), C.c_void_p(sC.cuda_stream)
+        gl = d["group"].long()
+        if par_streams:
+            sC.wait_stream(main)
+        # (stream C) hulls / samples of the late trajectories over the same windows (neptune.cpp:737-741, :792):
+        # independent of the optimisation, so they overlap it
+        with torch.cuda.stream(sC):
+            chk(L.nb_hulls_batch(h, G, DEV, p(d["t_group"]), p(d["late_recs"]), p(d["ones_g"]), self.delta,
+                                 p(o["hull_xy_g_l"]), p(o["hull_cnt_g_l"]), p(o["hull_ptr_g_l"]), p(o["nih0_g_l"]),
+                                 p(o["samp_g_l"]), None, stC), "nb_hulls_batch")
+            if G > 1:
+                o["samp_b"].copy_(o["samp_g_l"].index_select(0, gl))
+        mark("late_hulls")
+        # (main) hulls / samples of the committed trajectories the agents plan against
         chk(L.nb_hulls_batch(h, G, DEV, p(d["t_group"]), p(d["recs"]), p(d["ones_g"]), self.delta, p(o["hull_xy_g"]),
                              p(o["hull_cnt_g"]), p(o["hull_ptr_g"]), p(o["nih0_g"]), p(o["samp_g"]), None, st), "nb_hulls_batch")
         chk(L.nb_hull_index_batch(h, B, DEV, p(d["agent_id"]), p(d["group"]), p(d["known"]), p(o["hull_cnt_g"]),
                                   p(o["hull_ptr"]), p(o["hull_cnt"]), st), "nb_hull_index_batch")
         mark("hulls_samples")
-        # entangle_state_A = PredictAlphasBetas(entangle_state_)
-        for k in ("cnt", "alpha", "beta", "bend", "active"):
-            o["esA_" + k].copy_(d["es_" + k])
-        gl = d["group"].long()
-        o["samp0"].copy_(o["samp_g"][:, :, 0, 0, :].index_select(0, gl))
+        # (stream B) entangle_state_A = PredictAlphasBetas(entangle_state_): needs the samples only
+        if par_streams:
+            sB.wait_stream(main)
         esA = capi.NbEntState()
         esA.cnt, esA.alpha, esA.beta, esA.bend, esA.active = (p(o["esA_" + k]) for k in ("cnt", "alpha", "beta", "bend", "active"))
-        chk(L.nb_entangle_predict_batch(h, B, DEV, p(d["agent_id"]), p(d["known"]), p(d["bp_cnt"]), p(d["bp_xy"]), esA,
-                                        p(d["prev_pos"]), p(d["prev_pos_agent"]), p(d["cur"]), p(o["samp0"]), st),
-            "nb_entangle_predict_batch")
+        with torch.cuda.stream(sB):
+            for k in ("cnt", "alpha", "beta", "bend", "active"):
+                o["esA_" + k].copy_(d["es_" + k])
+            o["samp0"].copy_(o["samp_g"][:, :, 0, 0, :].index_select(0, gl))
+            chk(L.nb_entangle_predict_batch(h, B, DEV, p(d["agent_id"]), p(d["known"]), p(d["bp_cnt"]), p(d["bp_xy"]), esA,
+                                            p(d["prev_pos"]), p(d["prev_pos_agent"]), p(d["cur"]), p(o["samp0"]), stB),
+                "nb_entangle_predict_batch")
+            for k in ("cnt", "alpha", "beta", "bend", "active"):   # copy for entangleCheckGivenPwp (works on a local)
+                o["esC_" + k].copy_(o["esA_" + k])
         mark("predict")
         a = capi.NbReplanArgs()
         a.B, a.space, a.n_hull_slots = B, DEV, self.N
@@ -221,23 +245,15 @@ class ReplanCycle:
         chk(L.nb_replan_batch(h, C.byref(a), st), "nb_replan_batch")
         mark("lines_qp")
         # safetyCheckAfterReplan: geometric check against the late trajectories, then the entangle re-check
-        # hulls / samples of the late trajectories over the same windows (neptune.cpp:737-741, :792)
-        chk(L.nb_hulls_batch(h, G, DEV, p(d["t_group"]), p(d["late_recs"]), p(d["ones_g"]), self.delta, p(o["hull_xy_g_l"]),
-                             p(o["hull_cnt_g_l"]), p(o["hull_ptr_g_l"]), p(o["nih0_g_l"]), p(o["samp_g_l"]), None, st),
-            "nb_hulls_batch")
+        if par_streams:
+            main.wait_stream(sC)
+            main.wait_stream(sB)
         chk(L.nb_postcheck_hulls_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["group"]), p(o["hull_xy_g_l"]),
                                        p(o["hull_cnt_g_l"]), p(d["late"]), p(o["collide"]), st), "nb_postcheck_hulls_batch")
         if self.par.enable_entangle_check:
-            # entangleCheckGivenPwp works on a copy (ent_state_begin is a local in safetyCheckAfterReplan)
             esC = capi.NbEntState()
-            for k in ("cnt", "alpha", "beta", "bend", "active"):
-                o["esC_" + k].copy_(o["esA_" + k])
             esC.cnt, esC.alpha, esC.beta, esC.bend, esC.active = (p(o["esC_" + k]) for k in ("cnt", "alpha", "beta", "bend", "active"))
-            if G == 1:
-                samp_ptr, shared = p(o["samp_g_l"]), 1
-            else:
-                o["samp_b"].copy_(o["samp_g_l"].index_select(0, gl))
-                samp_ptr, shared = p(o["samp_b"]), 0
+            samp_ptr, shared = (p(o["samp_g_l"]), 1) if G == 1 else (p(o["samp_b"]), 0)
             chk(L.nb_entangle_check_batch(h, B, DEV, p(d["agent_id"]), p(d["known"]), p(d["bp_cnt"]), p(d["bp_xy"]), esC,
                                           p(d["n_int"]), p(o["coeff_out"]), samp_ptr, shared, p(o["entangled"]), st),
                 "nb_entangle_check_batch")
