@@ -147,7 +147,7 @@ def cpu_baseline(scene, budget_s: float, threads: int):
         out = cpu_cycle(scene, threads)
         reps += 1
         el = time.perf_counter() - t0
-        if el >= budget_s or reps >= 50:
+        if el >= budget_s or reps >= 2000:
             break
     return scene.batch.B * reps / el, reps, el, out
 
@@ -340,8 +340,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=4)
     ap.add_argument("--workload", default="grid64", choices=["grid64", "grid1024"],

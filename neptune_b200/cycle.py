@@ -68,15 +68,27 @@ class ReplanCycle:
 
         def z(shape, dt):
             return torch.zeros(shape, dtype=dt, device=self.dev)
-        # inputs of a cycle
-        self.d = dict(
-            agent_id=z(B, i32), n_int=z(B, i32), coeff_init=z((B, 3, NPOL, 4), f64), t_start=z(B, f64),
-            recs=z((N, REC), f64), known=z((B, N), u8), late=z((B, N), u8),
-            esv_cnt=z((B, NPOL + 1, 2), i32), esv_alpha=z((B, NPOL + 1, cap, 2), i32), esv_active=z((B, NPOL + 1, NA), i32),
-            bp_cnt=z(N, i32), bp_xy=z((N, par.bp_max, 2), f64),
-            es_cnt=z((B, 2), i32), es_alpha=z((B, cap, 2), i32), es_beta=z((B, cap), f64), es_bend=z((B, cap), i32),
-            es_active=z((B, NA), i32), prev_pos=z((B, N + 1, 2), f64), prev_pos_agent=z((B, N, 2), f64), cur=z((B, 2), f64))
-        self.d["late_recs"] = z((N, REC), f64)   # trajectories received while optimising (post-check)
+        # inputs of a cycle: views into ONE packed device buffer, mirrored by one pinned host buffer, so that
+        # the end-to-end path pays one H2D copy per cycle instead of twenty small ones
+        np_of = {f64: np.float64, i32: np.int32, u8: np.uint8}
+        spec = dict(
+            agent_id=(B, i32), n_int=(B, i32), coeff_init=((B, 3, NPOL, 4), f64), t_start=(B, f64),
+            recs=((N, REC), f64), late_recs=((N, REC), f64), known=((B, N), u8), late=((B, N), u8),
+            esv_cnt=((B, NPOL + 1, 2), i32), esv_alpha=((B, NPOL + 1, cap, 2), i32), esv_active=((B, NPOL + 1, NA), i32),
+            bp_cnt=(N, i32), bp_xy=((N, par.bp_max, 2), f64),
+            es_cnt=((B, 2), i32), es_alpha=((B, cap, 2), i32), es_beta=((B, cap), f64), es_bend=((B, cap), i32),
+            es_active=((B, NA), i32), prev_pos=((B, N + 1, 2), f64), prev_pos_agent=((B, N, 2), f64), cur=((B, 2), f64),
+            t_group=(B, f64), group=(B, i32))
+        self.layout, off = {}, 0
+        for k, (shape, dt) in spec.items():
+            shape = (shape,) if isinstance(shape, int) else tuple(shape)
+            nbytes = int(np.prod(shape)) * np.dtype(np_of[dt]).itemsize
+            self.layout[k] = (off, nbytes, shape, dt)
+            off += (nbytes + 255) // 256 * 256
+        self.in_bytes = off
+        self.in_buf = torch.zeros(off, dtype=u8, device=self.dev)
+        self.d = {k: self.in_buf[o:o + nb].view(dt).view(shape) for k, (o, nb, shape, dt) in self.layout.items()}
+        self._np_of = np_of
         # intermediates and outputs (group-shaped buffers are sized by _ensure_groups)
         self.o = dict(
             hull_ptr=z(B * N * NPOL, i64), hull_cnt=z((B, N, NPOL), i32), samp0=z((B, N, 2), f64),
@@ -84,10 +96,21 @@ class ReplanCycle:
             esA_active=z((B, NA), i32),
             esC_cnt=z((B, 2), i32), esC_alpha=z((B, cap, 2), i32), esC_beta=z((B, cap), f64), esC_bend=z((B, cap), i32),
             esC_active=z((B, NA), i32),
-            coeff_out=z((B, 3, NPOL, 4), f64), obj=z(B, f64), status=z(B, i32), iters=z((B, 2), i32),
-            entangled=z(B, i32), collide=z(B, i32), new_recs=z((B, REC), f64))
+            new_recs=z((B, REC), f64))
         self.G = 0
-        self.d["group"] = z(B, i32)
+        # packed outputs (one D2H copy)
+        ospec = dict(coeff_out=((B, 3, NPOL, 4), f64), obj=(B, f64), status=(B, i32), iters=((B, 2), i32),
+                     entangled=(B, i32), collide=(B, i32))
+        self.olayout, off = {}, 0
+        for k, (shape, dt) in ospec.items():
+            shape = (shape,) if isinstance(shape, int) else tuple(shape)
+            nbytes = int(np.prod(shape)) * np.dtype(np_of[dt]).itemsize
+            self.olayout[k] = (off, nbytes, shape, dt)
+            off += (nbytes + 255) // 256 * 256
+        self.out_bytes = off
+        self.out_buf = torch.zeros(off, dtype=u8, device=self.dev)
+        for k, (o_, nb, shape, dt) in self.olayout.items():
+            self.o[k] = self.out_buf[o_:o_ + nb].view(dt).view(shape)
         self.gathered = None
         self.delta = 2.0 * par.drone_radius  # bbox/2 + drone_radius with bbox = 2 drone_radius (neptune_ros.cpp:447-449)
         self._lib = capi.lib()
@@ -108,7 +131,6 @@ class ReplanCycle:
         def z(shape, dt):
             return torch.zeros(shape, dtype=dt, device=self.dev)
         self.G = G
-        self.d["t_group"] = z(G, f64)
         self.d["ones_g"] = torch.ones((G, N), dtype=u8, device=self.dev)
         for tag in ("", "_l"):   # planning-time trajectories, late trajectories
             self.o["hull_xy_g" + tag] = z((G, N, NPOL, HS, 2), f64)
@@ -130,52 +152,52 @@ class ReplanCycle:
         L.nb_commit_records_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, P]
 
     # ------------------------------------------------------------------ host <-> device
-    HOST_KEYS = ("agent_id", "n_int", "coeff_init", "t_start", "recs", "late_recs", "known", "late", "esv_cnt", "esv_alpha",
-                 "esv_active", "bp_cnt", "bp_xy", "es_cnt", "es_alpha", "es_beta", "es_bend", "es_active", "prev_pos",
-                 "prev_pos_agent", "cur")
     OUT_KEYS = ("coeff_out", "obj", "status", "iters", "entangled", "collide")
 
     def host_inputs(self, scene) -> dict:
-        """Pinned host copies of everything a cycle needs from the planner core / front end."""
+        """Pinned host copy of everything a cycle needs from the planner core / front end, laid out exactly
+        like the packed device buffer.  Returns {"buf": pinned uint8 tensor, "G": groups, <name>: numpy views}."""
         torch = self.torch
         b = scene.batch
+        recs = capi.make_records(scene.committed)
+        uniq, inv = np.unique(np.asarray(scene.t_start, np.float64), return_inverse=True)
+        tg = np.zeros(self.B)
+        tg[:len(uniq)] = uniq
         src = dict(agent_id=b.agent_id, n_int=b.n_int, coeff_init=b.coeff_init, t_start=scene.t_start,
-                   recs=capi.make_records(scene.committed), late_recs=capi.make_records(scene.committed),
-                   known=scene.known, late=scene.known,
+                   recs=recs, late_recs=recs, known=scene.known, late=scene.known,
                    esv_cnt=b.esv_cnt, esv_alpha=b.esv_alpha, esv_active=b.esv_active, bp_cnt=b.bp_cnt, bp_xy=b.bp_xy,
                    es_cnt=scene.es0_cnt, es_alpha=scene.es0_alpha, es_beta=scene.es0_beta, es_bend=scene.es0_bend,
                    es_active=scene.es0_active, prev_pos=scene.prev_pos, prev_pos_agent=scene.prev_pos_agent,
-                   cur=np.ascontiguousarray(scene.state_A[:, 0, :2]))
-        out = {}
-        for k in self.HOST_KEYS:
-            t = torch.from_numpy(np.ascontiguousarray(src[k]).astype(
-                {torch.float64: np.float64, torch.int32: np.int32, torch.uint8: np.uint8}[self.d[k].dtype]))
-            out[k] = t.pin_memory() if torch.cuda.is_available() else t
-        # window groups: agents with the same t_start share hulls and samples
-        uniq, inv = np.unique(np.asarray(scene.t_start, np.float64), return_inverse=True)
-        out["t_group"] = torch.from_numpy(uniq.copy())
-        out["group"] = torch.from_numpy(inv.astype(np.int32))
+                   cur=np.ascontiguousarray(scene.state_A[:, 0, :2]), t_group=tg, group=inv.astype(np.int32))
+        buf = torch.zeros(self.in_bytes, dtype=torch.uint8)
         if torch.cuda.is_available():
-            out["t_group"], out["group"] = out["t_group"].pin_memory(), out["group"].pin_memory()
+            buf = buf.pin_memory()
+        out = {"buf": buf, "G": len(uniq)}
+        nb = buf.numpy()
+        for k, (o, nbytes, shape, dt) in self.layout.items():
+            view = nb[o:o + nbytes].view(self._np_of[dt]).reshape(shape)
+            view[...] = np.asarray(src[k]).astype(self._np_of[dt]).reshape(shape)
+            out[k] = view
         return out
 
     def upload(self, host: dict) -> int:
-        n = 0
-        self._ensure_groups(int(host["t_group"].numel()))
-        for k in self.HOST_KEYS + ("t_group", "group"):
-            self.d[k].copy_(host[k], non_blocking=True)
-            n += host[k].numel() * host[k].element_size()
-        return n
+        """One H2D copy of the packed per-cycle inputs."""
+        self._ensure_groups(int(host["G"]))
+        self.in_buf.copy_(host["buf"], non_blocking=True)
+        return self.in_bytes
 
     def download(self, host_out: dict) -> int:
-        n = 0
-        for k in self.OUT_KEYS:
-            host_out[k].copy_(self.o[k], non_blocking=True)
-            n += host_out[k].numel() * host_out[k].element_size()
-        return n
+        """One D2H copy of the packed results."""
+        host_out["buf"].copy_(self.out_buf, non_blocking=True)
+        return self.out_bytes
 
     def host_outputs(self) -> dict:
-        return {k: self.torch.empty_like(self.o[k], device="cpu").pin_memory() for k in self.OUT_KEYS}
+        buf = self.torch.zeros(self.out_bytes, dtype=self.torch.uint8).pin_memory()
+        out = {"buf": buf}
+        nb = buf.numpy()
+        for k, (o, nbytes, shape, dt) in self.olayout.items():
+            out[k] = nb[o:o + nbytes].view(self._np_of[dt]).reshape(shape)
+        return out
 
     # ------------------------------------------------------------------ the cycle
     def step(self, exchange: bool = True):

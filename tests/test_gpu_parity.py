@@ -194,8 +194,8 @@ def test_replan_cycle_matches_oracle_composite(capi, oracle, cfg, seed):
         assert np.array_equal(o["esA_" + k], getattr(sc, "esA_" + k)), k
     ref = ReplanResult.empty(b)
     assert oracle.replan_batch(b, ref, 2) == 0
-    assert np.array_equal(hout["status"].numpy(), ref.status)
-    assert np.abs(hout["coeff_out"].numpy() - ref.coeff_out).max() <= 1e-6 * max(1.0, np.abs(ref.coeff_out).max())
+    assert np.array_equal(hout["status"], ref.status)
+    assert np.abs(hout["coeff_out"] - ref.coeff_out).max() <= 1e-6 * max(1.0, np.abs(ref.coeff_out).max())
     delta = 2 * par.drone_radius
     want_col = np.zeros(b.B, np.int32)
     for bi in range(b.B):
@@ -204,10 +204,10 @@ def test_replan_cycle_matches_oracle_composite(capi, oracle, cfg, seed):
                 tm, cx, cy, _ = sc.committed[j]
                 if oracle.pwp_collides(ref.coeff_out[bi], int(b.n_int[bi]), sc.t_start[bi], par.T_span, tm, cx, cy, [delta] * 3):
                     want_col[bi] = 1
-    assert np.array_equal(hout["collide"].numpy(), want_col)
+    assert np.array_equal(hout["collide"], want_col)
     ent = ob.check_batch(par, b.agent_id, b.n_int, ref.coeff_out, sc.samp, sc.known, sc.strep, b.bp_cnt, b.bp_xy,
                          sc.esA_cnt, sc.esA_alpha, sc.esA_beta, sc.esA_bend, sc.esA_active)[0]
-    assert np.array_equal(hout["entangled"].numpy(), ent)
+    assert np.array_equal(hout["entangled"], ent)
     # committed records: times shifted by t_start (generatePwpOut :898), coefficients of pwp_out
     rec = o["new_recs"]
     for bi in range(b.B):
