@@ -124,61 +124,78 @@ NB_HD void nb_lines_task(int tid, int b, int i, const NbConsts& cs, const NbLine
     lines[3 * s + 1] = l[1];
     lines[3 * s + 2] = l[2];
   }
-  if (tid == 0)
   {  // non-entangling :620-642 -> :715-784
     const int cap = cs.ent_cap, NA = N + M;
     const int* alpha = in.esv_alpha + ((size_t)b * 9 + i) * cap * 2;
     const int n_alpha = in.esv_cnt[((size_t)b * 9 + i) * 2];
     const int* active = in.esv_active + ((size_t)b * 9 + i) * NA;
     const int self = in.agent_id[b] - 1;
-    int eslot = 0;
-    double hulldist = 0.0;
-    for (int k = 0; k < 3; k++) hulldist += nb_dist(cp + 2 * (k + 1), cp + 2 * k);
-    for (int e = 0; e < cs.ent_slots; e++) ok[NH + N + M + e] = 0;
-    // only agents that appear in the alphas list can have active_cases == 1
-    for (int j = 0; j < N; j++)
+    for (int e = tid; e < cs.ent_slots; e += NT) ok[NH + N + M + e] = 0;
+    Cta<NT>(tid).sync();
+    // an agent with active_cases == 1 appears in the alphas list: walk the (short) list instead of all N
+    // agents, in increasing agent order as the reference's loop over j does
+    if (tid == 0)
     {
-      if (j == self || active[j] != 1) continue;
-      int case_id = 0;
-      for (int jj = 0; jj < n_alpha; jj++)
-        if (alpha[2 * jj] == j + 1) case_id = alpha[2 * jj + 1];
-      if (case_id == 0) continue;
-      const int nb = in.bp_cnt[j];
-      const double* bend = in.bp_xy + (size_t)2 * cs.bp_max * j;
-      const double* posj = in.nih0 + (((size_t)(in.nih0_group ? in.nih0_group[b] : b) * N + j) * 8 + i) * 2;
-      if (nb < 1 || posj[0] != posj[0]) continue;
-      for (int k = 1; k < nb + 1; k++)
+      int eslot = 0;
+      double hulldist = 0.0;
+      for (int k = 0; k < 3; k++) hulldist += nb_dist(cp + 2 * (k + 1), cp + 2 * k);
+      int prev_j = -1;
+      while (true)
       {
-        if (k == case_id) continue;
-        double pA[2], pB[2];
-        if (k == 1)
-        {  // :719-724 ray beyond agent j
-          pA[0] = (1 - cs.long_length) * bend[2 * (nb - 1)] + cs.long_length * posj[0];
-          pA[1] = (1 - cs.long_length) * bend[2 * (nb - 1) + 1] + cs.long_length * posj[1];
-          pB[0] = posj[0];
-          pB[1] = posj[1];
-        }
-        else
-        {  // :725-730 tether segment k-2 -> k-1
-          pA[0] = bend[2 * (k - 2)];
-          pA[1] = bend[2 * (k - 2) + 1];
-          pB[0] = bend[2 * (k - 1)];
-          pB[1] = bend[2 * (k - 1) + 1];
-        }
-        if (nb_dist(pA, cp) - hulldist > 0 && nb_dist(pB, cp) - hulldist > 0) continue;  // :743-745
-        if (eslot >= cs.ent_slots)
+        // next agent id (> prev_j) present in the list
+        int j = N;
+        for (int jj = 0; jj < n_alpha; jj++)
         {
-          *err = 1;
-          break;
+          const int id = alpha[2 * jj] - 1;
+          if (id > prev_j && id < j) j = id;
         }
-        const double Aset[4] = { pA[0], pA[1], pB[0], pB[1] };
-        double l[3];
-        const int sl = NH + N + M + eslot;
-        ok[sl] = nb_separate(Aset, 2, false, cp, 4, l) ? 1 : 2;  // :751
-        lines[3 * sl] = l[0];
-        lines[3 * sl + 1] = l[1];
-        lines[3 * sl + 2] = l[2];
-        eslot++;
+        if (j >= N) break;
+        prev_j = j;
+        if (j == self || active[j] != 1) continue;
+        int case_id = 0;
+        for (int jj = 0; jj < n_alpha; jj++)
+          if (alpha[2 * jj] == j + 1) case_id = alpha[2 * jj + 1];
+        if (case_id == 0) continue;
+        const int nb = in.bp_cnt[j];
+        const double* bend = in.bp_xy + (size_t)2 * cs.bp_max * j;
+        const double* posj = in.nih0 + (((size_t)(in.nih0_group ? in.nih0_group[b] : b) * N + j) * 8 + i) * 2;
+        if (nb < 1 || posj[0] != posj[0]) continue;
+        bool over = false;
+        for (int k = 1; k < nb + 1; k++)
+        {
+          if (k == case_id) continue;
+          double pA[2], pB[2];
+          if (k == 1)
+          {  // :719-724 ray beyond agent j
+            pA[0] = (1 - cs.long_length) * bend[2 * (nb - 1)] + cs.long_length * posj[0];
+            pA[1] = (1 - cs.long_length) * bend[2 * (nb - 1) + 1] + cs.long_length * posj[1];
+            pB[0] = posj[0];
+            pB[1] = posj[1];
+          }
+          else
+          {  // :725-730 tether segment k-2 -> k-1
+            pA[0] = bend[2 * (k - 2)];
+            pA[1] = bend[2 * (k - 2) + 1];
+            pB[0] = bend[2 * (k - 1)];
+            pB[1] = bend[2 * (k - 1) + 1];
+          }
+          if (nb_dist(pA, cp) - hulldist > 0 && nb_dist(pB, cp) - hulldist > 0) continue;  // :743-745
+          if (eslot >= cs.ent_slots)
+          {
+            *err = 1;
+            over = true;
+            break;
+          }
+          const double Aset[4] = { pA[0], pA[1], pB[0], pB[1] };
+          double l[3];
+          const int sl = NH + N + M + eslot;
+          ok[sl] = nb_separate(Aset, 2, false, cp, 4, l) ? 1 : 2;  // :751
+          lines[3 * sl] = l[0];
+          lines[3 * sl + 1] = l[1];
+          lines[3 * sl + 2] = l[2];
+          eslot++;
+        }
+        if (over) break;
       }
     }
   }

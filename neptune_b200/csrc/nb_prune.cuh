@@ -54,22 +54,36 @@ NB_HD bool nb_wrap_better(const double* px, const double* py, int c, int a, int 
 template <int NT>
 NB_HD int nb_cta_reduce_wrap(const Cta<NT>& cta, const NbPruneShared& ps, int c, int mine)
 {
-  ps.red[cta.tid] = mine;
-  cta.sync();
   constexpr int NW = (NT + 31) / 32;
-  if (cta.tid < NW)
+#if defined(__CUDA_ARCH__)
+  // butterfly inside each warp (nb_wrap_better is a strict total order, so every lane converges on the
+  // same winner), then one shared-memory exchange between the warps
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
   {
-    int best = -1;
-    for (int t = cta.tid * 32; t < NT && t < cta.tid * 32 + 32; t++)
-      if (nb_wrap_better(ps.px, ps.py, c, ps.red[t], best)) best = ps.red[t];
-    ps.misc[cta.tid] = best;  // NW <= 4
+    const int other = __shfl_xor_sync(0xffffffffu, mine, o);
+    if (other != mine && nb_wrap_better(ps.px, ps.py, c, other, mine)) mine = other;
   }
+  if ((cta.tid & 31) == 0) ps.misc[cta.tid >> 5] = mine;
   cta.sync();
+#else
+  ps.misc[0] = mine;
+#endif
   int best = -1;
   for (int w = 0; w < NW; w++)
-    if (nb_wrap_better(ps.px, ps.py, c, ps.misc[w], best)) best = ps.misc[w];
+    if (ps.misc[w] != best && nb_wrap_better(ps.px, ps.py, c, ps.misc[w], best)) best = ps.misc[w];
   cta.sync();
   return best;
+}
+
+// lexicographic "a before b" on dual points, ties by slot index
+NB_HD bool nb_lex_before(const double* px, const double* py, int a, int b)
+{
+  if (b < 0) return true;
+  if (a < 0) return false;
+  if (px[a] != px[b]) return px[a] < px[b];
+  if (py[a] != py[b]) return py[a] < py[b];
+  return a < b;
 }
 
 // ok[s] == 1 marks a solved line in slot s; keep[s] is set to 1 for the lines the QP must see.
@@ -107,30 +121,40 @@ NB_HD void nb_prune_lines(const Cta<NT>& cta, int LS, const double* lines, const
     if (s < LS) keep[s] = (v != 0) ? 1 : 0;
   }
   cta.sync();
-  // lexicographically smallest valid point
-  int mine = -1;
+  // lexicographically smallest valid point and the number of valid lines
+  int mine = -1, cnt_local = 0;
   for (int s = cta.tid; s <= LS; s += NT)
-    if (ps.valid[s] == 1 &&
-        (mine < 0 || ps.px[s] < ps.px[mine] || (ps.px[s] == ps.px[mine] && ps.py[s] < ps.py[mine])))
-      mine = s;
-  ps.red[cta.tid] = mine;
-  cta.sync();
-  if (cta.tid == 0)
-  {
-    int best = -1, total = 0;
-    for (int t = 0; t < NT; t++)
+    if (ps.valid[s] == 1)
     {
-      const int s = ps.red[t];
-      if (s >= 0 && (best < 0 || ps.px[s] < ps.px[best] || (ps.px[s] == ps.px[best] && ps.py[s] < ps.py[best]) ||
-                     (ps.px[s] == ps.px[best] && ps.py[s] == ps.py[best] && s < best)))
-        best = s;
+      if (s < LS) cnt_local++;
+      if (nb_lex_before(ps.px, ps.py, s, mine)) mine = s;
     }
-    for (int s = 0; s < LS; s++) total += (ps.valid[s] == 1);
-    ps.hull[0] = best;
-    ps.misc[4] = total;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    const int other = __shfl_xor_sync(0xffffffffu, mine, o);
+    cnt_local += __shfl_xor_sync(0xffffffffu, cnt_local, o);
+    if (other != mine && nb_lex_before(ps.px, ps.py, other, mine)) mine = other;
+  }
+  if ((cta.tid & 31) == 0)
+  {
+    ps.misc[cta.tid >> 5] = mine;
+    ps.red[cta.tid >> 5] = cnt_local;
   }
   cta.sync();
-  const int start = ps.hull[0], total = ps.misc[4];
+#else
+  ps.misc[0] = mine;
+  ps.red[0] = cnt_local;
+#endif
+  int start = -1, total = 0;
+  for (int w = 0; w < (NT + 31) / 32; w++)
+  {
+    total += ps.red[w];
+    if (ps.misc[w] != start && nb_lex_before(ps.px, ps.py, ps.misc[w], start)) start = ps.misc[w];
+  }
+  cta.sync();
+  if (cta.tid == 0) ps.hull[0] = start;
   cta.sync();
   if (total <= 3) return;  // nothing worth pruning
   // gift wrapping, counter-clockwise

@@ -28,6 +28,10 @@ struct NbQpShared
   double gobj[NB_NV_MAX], invd[NB_NV_MAX];
   double init3[3][3], pf[3], e3[3];
   double xin[3][4 * NB_NPOL];
+  double blo[24], bhi[24];                     // bounds of feature kind (axis, j)
+  unsigned char ax_of[NB_NV_MAX], c_of[NB_NV_MAX];  // variable a -> (axis, column)
+  unsigned char pa[NB_NV_MAX * (NB_NV_MAX + 1) / 2], pb[NB_NV_MAX * (NB_NV_MAX + 1) / 2];  // lower-triangle pairs
+  int npairs;
 };
 
 NB_HD double nb_rcp(double x)
@@ -75,9 +79,10 @@ NB_HD void nb_qp_features(const Group<NL>& g, const NbQpTable* tb, const NbQpSha
                           const double* vec, bool with_const)
 {
   const int n = tb->n, dof = tb->dof;
-  for (int q = g.lane; q < 3 * 8 * n; q += NL)
+  for (int q = g.lane; q < 3 * NB_NFEAT_AX; q += NL)
   {
-    const int ax = q / (8 * n), fl = q - ax * 8 * n;
+    const int ax = q >> 6, fl = q & 63;
+    if (fl >= 8 * n) continue;
     double v = 0.0;
     if (with_const)
       v = tb->c0[fl][0] * sh_c->init3[ax][0] + tb->c0[fl][1] * sh_c->init3[ax][1] + tb->c0[fl][2] * sh_c->init3[ax][2];
@@ -176,11 +181,12 @@ NB_HD void nb_qp_pass(const Group<NL>& g, const NbConsts& cs, const NbQpTable* t
   constexpr int SUB = Group<NL>::SUB;
   const int n = tb->n;
   const bool loads = (MODE == NB_PASS_RESID || MODE == NB_PASS_LOAD_CORR);
-  for (int q = g.lane; q < 3 * 8 * n; q += NL)
+  for (int q = g.lane; q < 3 * NB_NFEAT_AX; q += NL)
   {
-    const int ax = q / (8 * n), fl = q - ax * 8 * n, f = ax * NB_NFEAT_AX + fl;
-    double lo, hi, w_u, w_l;
-    nb_feat_bounds(cs, ax, fl & 7, lo, hi);
+    const int ax = q >> 6, fl = q & 63, f = q;
+    if (fl >= 8 * n) continue;
+    double w_u, w_l;
+    const double lo = sh->blo[ax * 8 + (fl & 7)], hi = sh->bhi[ax * 8 + (fl & 7)];
     const double yv = sh->y[f], dv = sh->dy[f];
     const int rs = 2 * f;
     const double t_u = nb_row<MODE>(R.s + rs, R.lam + rs, R.dsa + rs, R.dla + rs, R.inv + rs, yv - hi, dv, sigmu, alpha,
@@ -260,8 +266,8 @@ NB_HD void nb_qp_pass(const Group<NL>& g, const NbConsts& cs, const NbQpTable* t
 // out[a] = sum_f C[f][c] * vecF[ax*64+f]   (a = ax*dof + c): C^T applied to a per-feature vector, then
 // dst[a] = bsign * base[a] + sign * that + es * extra[a]; item (a, sub-lane) with shuffle combine
 template <int NL>
-NB_HD void nb_qp_ct_all(const Group<NL>& g, const NbQpTable* tb, const double* vecF, double* dst, const double* base,
-                        double bsign, double sign, const double* extra, double es)
+NB_HD void nb_qp_ct_all(const Group<NL>& g, const NbQpTable* tb, const NbQpShared* sh_t, const double* vecF, double* dst,
+                        const double* base, double bsign, double sign, const double* extra, double es)
 {
   constexpr int SUB = Group<NL>::SUB;
   const int n = tb->n, dof = tb->dof, nv = 3 * dof;
@@ -271,7 +277,7 @@ NB_HD void nb_qp_ct_all(const Group<NL>& g, const NbQpTable* tb, const double* v
     const int q = b0 + g.lane;
     const bool on = q < items;
     const int a = on ? q / SUB : 0, sub = q % SUB;
-    const int ax = a / dof, c = a - ax * dof;
+    const int ax = sh_t->ax_of[a], c = sh_t->c_of[a];
     double v0 = 0.0, v1 = 0.0;
     if (on)
     {
@@ -309,11 +315,10 @@ NB_HD void nb_qp_factor(const Group<NL>& g, NbQpShared* sh, int nv)
       K[i * nv + k] = t * ip;
     }
     g.sync();
-    const int rem = nv - k - 1;
-    for (int q = g.lane; q < rem * rem; q += NL)
+    for (int q = g.lane; q < sh->npairs; q += NL)
     {
-      const int i = k + 1 + q / rem, j = k + 1 + q % rem;
-      if (j <= i) K[i * nv + j] -= K[i * nv + k] * col[j];
+      const int i = sh->pa[q], j = sh->pb[q];
+      if (j > k) K[i * nv + j] -= K[i * nv + k] * col[j];
     }
     g.sync();
   }
@@ -387,6 +392,24 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
   *iters_out = 0;
   // ---- per-agent constants
   g.sync();
+  for (int q = g.lane; q < 24; q += NL) nb_feat_bounds(cs, q >> 3, q & 7, sh->blo[q], sh->bhi[q]);
+  for (int a = g.lane; a < nv; a += NL)
+  {
+    sh->ax_of[a] = (unsigned char)(a / (dof > 0 ? dof : 1));
+    sh->c_of[a] = (unsigned char)(a - (a / (dof > 0 ? dof : 1)) * dof);
+  }
+  if (g.lane == 0)
+  {
+    int q = 0;
+    for (int a = 0; a < nv; a++)
+      for (int b = 0; b <= a; b++)
+      {
+        sh->pa[q] = (unsigned char)a;
+        sh->pb[q] = (unsigned char)b;
+        q++;
+      }
+    sh->npairs = q;
+  }
   for (int q = g.lane; q < 3 * 4 * n; q += NL)
   {
     const int ax = q / (4 * n), r = q - ax * 4 * n;
@@ -428,7 +451,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
   // w0 = Z^T (x_frontend - Pm init3), g0 = Gr init3 + gpf pf
   for (int a = g.lane; a < nv; a += NL)
   {
-    const int ax = a / dof, c = a - ax * dof;
+    const int ax = sh->ax_of[a], c = sh->c_of[a];
     double v = 0.0;
     for (int r = 0; r < 4 * n; r++)
     {
@@ -469,12 +492,12 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
   if (dof == 0)
   {  // the equalities leave a single point: feasible iff every row holds there
     double worst = -1e300;
-    for (int q = g.lane; q < 3 * 8 * n; q += NL)
+    for (int q = g.lane; q < 3 * NB_NFEAT_AX; q += NL)
     {
-      const int ax = q / (8 * n), fl = q - ax * 8 * n;
-      double lo, hi;
-      nb_feat_bounds(cs, ax, fl & 7, lo, hi);
-      const double yv = sh->y[ax * NB_NFEAT_AX + fl];
+      const int ax = q >> 6, fl = q & 63;
+      if (fl >= 8 * n) continue;
+      const double lo = sh->blo[ax * 8 + (fl & 7)], hi = sh->bhi[ax * 8 + (fl & 7)];
+      const double yv = sh->y[q];
       worst = fmax(worst, fmax(yv - hi, lo - yv));
     }
     for (int q = g.lane; q < 4 * n; q += NL)
@@ -496,11 +519,11 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
   else
   {
     // ---- start: s = max(h - G w, 1), lam = 1
-    for (int q = g.lane; q < 3 * 8 * n; q += NL)
+    for (int q = g.lane; q < 3 * NB_NFEAT_AX; q += NL)
     {
-      const int ax = q / (8 * n), fl = q - ax * 8 * n, f = ax * NB_NFEAT_AX + fl;
-      double lo, hi;
-      nb_feat_bounds(cs, ax, fl & 7, lo, hi);
+      const int ax = q >> 6, fl = q & 63, f = q;
+      if (fl >= 8 * n) continue;
+      const double lo = sh->blo[ax * 8 + (fl & 7)], hi = sh->bhi[ax * 8 + (fl & 7)];
       const double yv = sh->y[f];
       R.s[2 * f] = fmax(hi - yv, 1.0);
       R.s[2 * f + 1] = fmax(yv - lo, 1.0);
@@ -547,14 +570,14 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       // gobj = Hr w + g0 ; r_d = gobj + C^T(lambda load) + lam_q grad c
       for (int a = g.lane; a < nv; a += NL)
       {
-        const int ax = a / dof, c = a - ax * dof;
+        const int ax = sh->ax_of[a], c = sh->c_of[a];
         double go = sh->g0[a];
         for (int c2 = 0; c2 < dof; c2++) go += tb->Hr[c][c2] * sh->w[ax * dof + c2];
         sh->gobj[a] = go;
         sh->gq[a] = has_qc ? 2.0 * e3[ax] * tb->tq[c] : 0.0;
       }
       g.sync();
-      nb_qp_ct_all<NL>(g, tb, sh->dy, sh->rd, sh->gobj, 1.0, 1.0, sh->gq, has_qc ? lam_q : 0.0);
+      nb_qp_ct_all<NL>(g, tb, sh, sh->dy, sh->rd, sh->gobj, 1.0, 1.0, sh->gq, has_qc ? lam_q : 0.0);
       g.sync();
       double rdn = 0.0, gn = 0.0, fobj = fconst;
       for (int a = 0; a < nv; a++)
@@ -575,11 +598,10 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       }
       // ---- K = Hobj + C^T W C (+ quadratic-constraint terms), lower triangle
       const double d_q = has_qc ? lam_q / s_q : 0.0;
-      for (int q = g.lane; q < nv * nv; q += NL)
+      for (int q = g.lane; q < sh->npairs; q += NL)
       {
-        const int a = q / nv, b = q - a * nv;
-        if (b > a) continue;
-        const int axa = a / dof, ca = a - axa * dof, axb = b / dof, cb = b - axb * dof;
+        const int a = sh->pa[q], b = sh->pb[q];
+        const int axa = sh->ax_of[a], ca = sh->c_of[a], axb = sh->ax_of[b], cb = sh->c_of[b];
         double v = 0.0;
         if (axa == axb)
         {
@@ -612,7 +634,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       nb_qp_factor<NL>(g, sh, nv);
       // ---- predictor
       const double tau_q = has_qc ? (lam_q * rp_q - s_q * lam_q) / s_q : 0.0;
-      nb_qp_ct_all<NL>(g, tb, sh->La, sh->dw, sh->rd, -1.0, -1.0, sh->gq, -tau_q);
+      nb_qp_ct_all<NL>(g, tb, sh, sh->La, sh->dw, sh->rd, -1.0, -1.0, sh->gq, -tau_q);
       nb_qp_solve_ldl<NL>(g, sh, nv, sh->dw);
       nb_qp_features<NL>(g, tb, sh, sh->dy, sh->dw, false);
       g.sync();
@@ -648,7 +670,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       nb_qp_pass<NL, NB_PASS_LOAD_CORR>(g, cs, tb, sh, R, sigmu, 0.0, acc);
       const double rc_q = s_q * lam_q + dsa_q * dla_q - sigmu;
       const double tau_q2 = has_qc ? (lam_q * rp_q - rc_q) / s_q : 0.0;
-      nb_qp_ct_all<NL>(g, tb, sh->La, sh->dw, sh->rd, -1.0, -1.0, sh->gq, -tau_q2);
+      nb_qp_ct_all<NL>(g, tb, sh, sh->La, sh->dw, sh->rd, -1.0, -1.0, sh->gq, -tau_q2);
       nb_qp_solve_ldl<NL>(g, sh, nv, sh->dw);
       nb_qp_features<NL>(g, tb, sh, sh->dy, sh->dw, false);
       g.sync();
