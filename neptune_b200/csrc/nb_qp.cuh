@@ -112,10 +112,17 @@ template <int MODE>
 NB_HD double nb_row(double* s_, double* lam_, double* dsa_, double* dla_, double* inv_, double v, double gd,
                     double sigmu, double alpha, NbPassAcc& acc, double& wgt)
 {
-  const double s = *s_, lam = *lam_;
+  double s = *s_, lam = *lam_;
   wgt = 0.0;
   if (MODE == NB_PASS_RESID)
   {
+    if (alpha != 0.0)
+    {  // pending step of the previous iteration (s, lam) += alpha (ds, dl); v already is at the new point
+      s += alpha * (*dsa_);
+      lam += alpha * (*dla_);
+      *s_ = s;
+      *lam_ = lam;
+    }
     const double rp = v + s;
     const double inv = nb_rcp(s);
     *inv_ = inv;
@@ -187,7 +194,13 @@ NB_HD void nb_qp_pass(const Group<NL>& g, const NbConsts& cs, const NbQpTable* t
     if (fl >= 8 * n) continue;
     double w_u, w_l;
     const double lo = sh->blo[ax * 8 + (fl & 7)], hi = sh->bhi[ax * 8 + (fl & 7)];
-    const double yv = sh->y[f], dv = sh->dy[f];
+    double yv = sh->y[f];
+    const double dv = sh->dy[f];
+    if (MODE == NB_PASS_RESID && alpha != 0.0)
+    {  // features are linear in w: y(w + alpha dw) = y + alpha dy
+      yv += alpha * dv;
+      sh->y[f] = yv;
+    }
     const int rs = 2 * f;
     const double t_u = nb_row<MODE>(R.s + rs, R.lam + rs, R.dsa + rs, R.dla + rs, R.inv + rs, yv - hi, dv, sigmu, alpha,
                                     acc, w_u);
@@ -550,12 +563,14 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
     g.sync();
 
     int it = 0;
+    double al_pending = 0.0;  // step of the previous iteration, applied to (s, lam, y) by the next RESID sweep
     for (it = 0; it <= cs.max_iter; it++)
     {
       const bool init_pass = (it == 0);
       // ---- residuals and weights
       NbPassAcc acc = { 0.0, 0.0, 0.0, 0.0, 0.0 };
-      nb_qp_pass<NL, NB_PASS_RESID>(g, cs, tb, sh, R, 0.0, 0.0, acc);
+      nb_qp_pass<NL, NB_PASS_RESID>(g, cs, tb, sh, R, 0.0, al_pending, acc);
+      al_pending = 0.0;
       double cval = 0.0, rp_q = 0.0;
       if (has_qc)
       {
@@ -689,15 +704,13 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       const double eta = 1.0 - 1.0 / ((it + 3.0) * (it + 3.0));
       double al = rmax > 0.0 ? eta / rmax : 1.0;
       if (al > 1.0) al = 1.0;
-      nb_qp_pass<NL, NB_PASS_UPDATE>(g, cs, tb, sh, R, 0.0, al, acc);
+      al_pending = al;
       if (has_qc)
       {
         s_q += al * ds_q;
         lam_q += al * dl_q;
       }
       for (int a = g.lane; a < nv; a += NL) sh->w[a] += al * sh->dw[a];
-      g.sync();
-      nb_qp_features<NL>(g, tb, sh, sh->y, sh->w, true);
       g.sync();
     }
     *iters_out = it;
