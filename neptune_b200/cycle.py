@@ -200,9 +200,38 @@ class ReplanCycle:
         return out
 
     # ------------------------------------------------------------------ the cycle
+    def capture(self):
+        """Capture the launch sequence of one cycle (for the current window grouping) in a CUDA graph:
+        the ~25 launches of a cycle are short, so replaying one graph removes the host launch cost."""
+        torch = self.torch
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._step_impl()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        l0 = self.solver.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step_impl()
+        self.launches_per_cycle = self.solver.launch_count() - l0   # library kernels one replay launches
+        self.graph_G = self.G
+
     def step(self, exchange: bool = True):
+        """One cycle on the current CUDA stream (graph replay when captured), then the all-gather."""
+        if getattr(self, "graph", None) is not None and self.graph_G == self.G and not self.profile:
+            self.graph.replay()
+        else:
+            self._step_impl()
+        if exchange and self.world > 1:
+            sizes = [len(shard_agents(self.N, self.world, r)) for r in range(self.world)]
+            self.gathered = gather_records(self.o["new_recs"], self.world, self.group, sizes)
+        return self.o
+
+    def _step_impl(self):
         """hulls/samples (K1) -> PredictAlphasBetas (K3) -> LPs + QP (K2, K4) -> post-check (K5, K3) ->
-        commit records -> all-gather.  Everything is enqueued on the current CUDA stream."""
+        commit records.  Everything is enqueued on the current CUDA stream (and two side streams)."""
         torch, L, h, d, o, B = self.torch, self._lib, self.solver.handle, self.d, self.o, self.B
         st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
@@ -282,10 +311,7 @@ class ReplanCycle:
         mark("postcheck")
         chk(L.nb_commit_records_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["t_start"]), p(o["new_recs"]), st),
             "nb_commit_records_batch")
-        if exchange and self.world > 1:
-            sizes = [len(shard_agents(self.N, self.world, r)) for r in range(self.world)]
-            self.gathered = gather_records(o["new_recs"], self.world, self.group, sizes)
-        mark("commit_exchange")
+        mark("commit")
         if self.profile:
             torch.cuda.synchronize()
             self.stage_ms = {marks[i][0]: marks[i - 1][1].elapsed_time(marks[i][1]) for i in range(1, len(marks))}
