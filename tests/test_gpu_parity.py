@@ -261,3 +261,15 @@ def test_cpp_shim_polysolvergurobi_and_separator(capi, oracle, tmp_path):
         first = b.hull_xy[b.hull_ptr[k0]:b.hull_ptr[k0 + 1]]
         far = np.array([[100.0, 100.0], [101.0, 100.0], [101.0, 101.0], [100.0, 101.0]])
         assert s_ok == int(len(first) > 0 and oracle.separate(first, far)[0])
+
+
+def test_entangle_random_walks_bend_points(capi, oracle):
+    """K3 on walks that create and release bend points: bit-exact against the oracle."""
+    from tests.ent_backends import OracleEntBackend
+    from tests.ent_walks import compare_backends
+    par = config("obst8")
+    sc = make_scene(par, 3003, sync=False)
+    s = _solver(capi, par, sc)
+    mx_a, mx_b = compare_backends(par, sc, OracleEntBackend(oracle), capi.DeviceEntBackend(s), trials=20)
+    assert mx_a >= 8 and mx_b >= 2
+    s.close()
