@@ -117,6 +117,11 @@ typedef struct nb_replan_args
   const double* nih0;         /* [B][N][8][2] col(0) of hullsNoInflation_[j][i]; NaN = unknown */
   const int32_t* nih0_group;  /* optional [B]: nih0 is then [G][N][8][2] and agent b reads block nih0_group[b]
                                  (agents planning over the same windows share it, see nb_hull_index_batch) */
+  const uint8_t* hull_known;  /* optional [B][N], with nih0_group: shared-window mode for the hulls too --
+                                 hull_xy / hull_cnt are the group-shaped outputs of nb_hulls_batch
+                                 ([G][N][8][NB_HULL_STRIDE][2], [G][N][8]), hull_ptr is ignored, slot j of agent
+                                 b is hull (nih0_group[b], j, i), empty when j is b itself or hull_known[b][j]
+                                 == 0 (what nb_hull_index_batch would materialise) */
   const int32_t* esv_cnt;     /* [B][9][2] (alphas.size(), bendPointsIdx.size()) of entStateVec[i] */
   const int32_t* esv_alpha;   /* [B][9][ent_cap][2] */
   const int32_t* esv_active;  /* [B][9][N+M] active_cases */

@@ -32,7 +32,7 @@ class NbParams(C.Structure):
 class NbReplanArgs(C.Structure):
     _fields_ = [("B", C.c_int32), ("space", C.c_int32), ("agent_id", _P), ("n_int", _P), ("coeff_init", _P),
                 ("n_hull_slots", C.c_int32), ("hull_ptr", _P), ("hull_xy", _P), ("hull_nvert", C.c_int64),
-                ("hull_cnt", _P), ("nih0", _P), ("nih0_group", _P), ("esv_cnt", _P), ("esv_alpha", _P), ("esv_active", _P), ("bp_cnt", _P),
+                ("hull_cnt", _P), ("nih0", _P), ("nih0_group", _P), ("hull_known", _P), ("esv_cnt", _P), ("esv_alpha", _P), ("esv_active", _P), ("bp_cnt", _P),
                 ("bp_xy", _P), ("coeff_out", _P), ("obj", _P), ("status", _P), ("iters", _P), ("lines", _P),
                 ("line_ok", _P)]
 
@@ -63,6 +63,7 @@ def host_args(batch: ReplanBatch, res: ReplanResult) -> NbReplanArgs:
     a.hull_nvert = int(batch.hull_xy.shape[0])
     a.hull_cnt = None
     a.nih0_group = None
+    a.hull_known = None
     a.nih0, a.esv_cnt, a.esv_alpha, a.esv_active = _np(batch.nih0), _np(batch.esv_cnt), _np(batch.esv_alpha), _np(batch.esv_active)
     a.bp_cnt, a.bp_xy = _np(batch.bp_cnt), _np(batch.bp_xy)
     a.coeff_out, a.obj, a.status, a.iters = _np(res.coeff_out), _np(res.obj), _np(res.status), _np(res.iters)

@@ -257,18 +257,30 @@ __global__ void __launch_bounds__(32) k_entangle(NbEntArgs a)
 
 // ---- K1 / K5 kernels
 __global__ void k_hulls(NbConsts cs, int B, const double* t_start, const double* recs, const uint8_t* known, double delta,
-                        double* hull_xy, int* hull_cnt, int64_t* hull_ptr, double* nih0, int* idx, int* err)
+                        double* hull_xy, int* hull_cnt, int64_t* hull_ptr, double* nih0, int* idx, double* samp, int* err)
 {
-  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j, i)
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j, i), then the sample sets (b, j)
   const size_t total = (size_t)B * cs.N * NB_NPOL;
-  if (k >= total) return;
+  if (k >= total)
+  {  // Neptune::SamplePointsOfCurves: one thread per (b, j), same launch (independent work)
+    const size_t q = k - total;
+    if (!samp || q >= (size_t)B * cs.N) return;
+    const int j = (int)(q % cs.N), b = (int)(q / cs.N);
+    double* out = samp + q * cs.num_pol * (cs.S + 1) * 2;
+    if (!known[q])
+    {
+      for (int e = 0; e < cs.num_pol * (cs.S + 1) * 2; e++) out[e] = 0.0;
+      return;
+    }
+    nb_sample_points(cs, recs + (size_t)j * NB_REC, t_start[b], NB_ADD(t_start[b], NB_MUL(cs.T, (double)cs.num_pol)), out,
+                     nullptr);
+    return;
+  }
   const int i = (int)(k % NB_NPOL), j = (int)((k / NB_NPOL) % cs.N), b = (int)(k / ((size_t)NB_NPOL * cs.N));
   hull_ptr[k] = (int64_t)k * NB_HMAX;
   int cnt = 0, id2[2] = { -1, -1 };
   double n0[2];
-#if defined(__CUDA_ARCH__)
   n0[0] = n0[1] = __longlong_as_double(0x7ff8000000000000LL);
-#endif
   if (i < cs.num_pol && known[(size_t)b * cs.N + j])
   {
     const double t0 = NB_ADD(t_start[b], NB_MUL((double)i, cs.T)), t1 = NB_ADD(t_start[b], NB_MUL((double)(i + 1), cs.T));
@@ -287,20 +299,6 @@ __global__ void k_hulls(NbConsts cs, int B, const double* t_start, const double*
     idx[2 * k] = id2[0];
     idx[2 * k + 1] = id2[1];
   }
-}
-
-__global__ void k_samples(NbConsts cs, int B, const double* t_start, const double* recs, const uint8_t* known, double* samp)
-{
-  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j)
-  if (k >= (size_t)B * cs.N) return;
-  const int j = (int)(k % cs.N), b = (int)(k / cs.N);
-  double* out = samp + k * cs.num_pol * (cs.S + 1) * 2;
-  if (!known[k])
-  {
-    for (int q = 0; q < cs.num_pol * (cs.S + 1) * 2; q++) out[q] = 0.0;
-    return;
-  }
-  nb_sample_points(cs, recs + (size_t)j * NB_REC, t_start[b], NB_ADD(t_start[b], NB_MUL(cs.T, (double)cs.num_pol)), out, nullptr);
 }
 
 __global__ void k_postcheck(NbConsts cs, int B, const int* n_int, const double* coeff, const double* t_start,
@@ -575,7 +573,7 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   if ((rc = stage_in(h, 0, sp, a->agent_id, (size_t)B, st, &in.agent_id))) return rc;
   if ((rc = stage_in(h, 1, sp, a->n_int, (size_t)B, st, &in.n_int))) return rc;
   if ((rc = stage_in(h, 2, sp, a->coeff_init, (size_t)B * 96, st, &in.coeff_init))) return rc;
-  if ((rc = stage_in(h, 3, sp, a->hull_ptr, (size_t)B * NH * 8 + (a->hull_cnt ? 0 : 1), st, &in.hull_ptr))) return rc;
+  if ((rc = stage_in(h, 3, sp, a->hull_ptr, a->hull_known ? 0 : (size_t)B * NH * 8 + (a->hull_cnt ? 0 : 1), st, &in.hull_ptr))) return rc;
   if ((rc = stage_in(h, 4, sp, a->hull_xy, (size_t)a->hull_nvert * 2, st, &in.hull_xy))) return rc;
   if ((rc = stage_in(h, 11, sp, a->hull_cnt, (size_t)B * NH * 8, st, &in.hull_cnt))) return rc;
   if (a->nih0_group && sp == NB_HOST)
@@ -584,6 +582,12 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
     return NB_ERR_ARG;
   }
   in.nih0_group = a->nih0_group;
+  in.hull_known = a->hull_known;
+  if (a->hull_known && (!a->nih0_group || !a->hull_cnt || NH != N))
+  {
+    g_err = "nb_replan_batch: hull_known needs nih0_group, hull_cnt and n_hull_slots == num_agents";
+    return NB_ERR_ARG;
+  }
   if ((rc = stage_in(h, 5, sp, a->nih0, (size_t)B * N * 16, st, &in.nih0))) return rc;
   if ((rc = stage_in(h, 6, sp, a->esv_cnt, (size_t)B * 18, st, &in.esv_cnt))) return rc;
   if ((rc = stage_in(h, 7, sp, a->esv_alpha, (size_t)B * 9 * cap * 2, st, &in.esv_alpha))) return rc;
@@ -967,13 +971,10 @@ extern "C" int nb_hulls_batch(nb_handle* h, int32_t B, int32_t space, const doub
   if ((rc = stage_out(h, 3, space, nih0, nh * 2, &dn0))) return rc;
   if ((rc = stage_out(h, 4, space, samp, (size_t)B * N * P * (S + 1) * 2, &dsamp))) return rc;
   if ((rc = stage_out(h, 5, space, idx, nh * 2, &didx))) return rc;
-  k_hulls<<<(unsigned)((nh + 127) / 128), 128, 0, st>>>(h->cs, B, dt, dr, dk, delta, dxy, dcnt, dptr, dn0, didx, (int*)h->err.p);
+  const size_t nthreads = nh + (dsamp ? (size_t)B * N : 0);
+  k_hulls<<<(unsigned)((nthreads + 63) / 64), 64, 0, st>>>(h->cs, B, dt, dr, dk, delta, dxy, dcnt, dptr, dn0, didx, dsamp,
+                                                         (int*)h->err.p);
   h->launches += 1;
-  if (dsamp)
-  {
-    k_samples<<<(unsigned)(((size_t)B * N + 127) / 128), 128, 0, st>>>(h->cs, B, dt, dr, dk, dsamp);
-    h->launches += 1;
-  }
   NB_CUDA(cudaGetLastError());
   if (space == NB_HOST)
   {

@@ -22,6 +22,7 @@ struct NbLinesIn
   const double* hull_xy;
   const double* nih0;        // [B][N][8][2] (or [G][N][8][2] with nih0_group)
   const int* nih0_group;     // optional [B]
+  const uint8_t* hull_known; // optional [B][N]: shared-window hulls (group-shaped hull_xy / hull_cnt)
   const int64_t* st_ptr;     // [M+1]
   const double* st_xy;
   const int* esv_cnt;        // [B][9][2]
@@ -81,9 +82,20 @@ NB_HD void nb_lines_task(int tid, int b, int i, const NbConsts& cs, const NbLine
     double l[3] = { 0, 0, 0 };
     if (s < NH)
     {  // other agents :477-495
-      const size_t hk = ((size_t)b * NH + s) * 8 + i;
-      const int64_t o0 = in.hull_ptr[hk];
-      const int cnt = in.hull_cnt ? in.hull_cnt[hk] : (int)(in.hull_ptr[hk + 1] - o0);
+      int64_t o0;
+      int cnt;
+      if (in.hull_known)
+      {  // shared windows: hull (group, s, i) of nb_hulls_batch, fixed stride; own slot / unknown agents empty
+        const size_t src = ((size_t)in.nih0_group[b] * NH + s) * 8 + i;
+        o0 = (int64_t)src * 24;
+        cnt = (s == in.agent_id[b] - 1 || !in.hull_known[(size_t)b * NH + s]) ? 0 : in.hull_cnt[src];
+      }
+      else
+      {
+        const size_t hk = ((size_t)b * NH + s) * 8 + i;
+        o0 = in.hull_ptr[hk];
+        cnt = in.hull_cnt ? in.hull_cnt[hk] : (int)(in.hull_ptr[hk + 1] - o0);
+      }
       if (cnt > 0) res = nb_separate(in.hull_xy + 2 * o0, cnt, true, cp, 4, l) ? 1 : 2;
     }
     else if (s < NH + N)

@@ -28,39 +28,95 @@ NB_HD double nb_pt_seg(double px, double py, double ux, double uy, double vx, do
   return dx * dx + dy * dy;
 }
 
+NB_HD double nb_sep_rcp(double x)
+{
+#if defined(__CUDA_ARCH__)
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
+
+// squared distance from p to the segment u + t e, t in [0,1], with inv = 1/|e|^2 (0 for a degenerate segment)
+NB_HD double nb_pt_seg_inv(double px, double py, double ux, double uy, double ex, double ey, double inv, double& cx,
+                           double& cy)
+{
+  double t = ((px - ux) * ex + (py - uy) * ey) * inv;
+  t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+  cx = ux + t * ex;
+  cy = uy + t * ey;
+  const double dx = px - cx, dy = py - cy;
+  return dx * dx + dy * dy;
+}
+
 // A: nA points (x,y interleaved); a_polygon: vertices are in cyclic order of a convex polygon.
 // B: nB points (the agent's MINVO control points; any order).  Returns true iff separable.
+// Reciprocals of the squared segment lengths are hoisted: 6 for the segments of B (nB = 4) and one per
+// edge of A, instead of one division per point-segment pair.
 NB_HD bool nb_separate(const double* A, int nA, bool a_polygon, const double* B, int nB, double out[3])
 {
   double best = 1e300, pax = 0, pay = 0, pbx = 0, pby = 0, cx, cy;
   out[0] = out[1] = out[2] = 0.0;
   if (nA <= 0 || nB <= 0) return false;
-  // vertices of A against every segment of B (B is tiny: all pairs; a single point is its own segment)
-  for (int i = 0; i < nA; i++)
+  // segments of B (all pairs; a single point is its own degenerate segment)
+  double sux[6], suy[6], sex[6], sey[6], sinv[6];
+  int ns = 0;
+  if (nB <= 4)
   {
-    const double ax = A[2 * i], ay = A[2 * i + 1];
     for (int j = 0; j < nB; j++)
       for (int k = (nB == 1 ? j : j + 1); k < nB; k++)
       {
-        const double d2 = nb_pt_seg(ax, ay, B[2 * j], B[2 * j + 1], B[2 * k], B[2 * k + 1], cx, cy);
+        sux[ns] = B[2 * j], suy[ns] = B[2 * j + 1];
+        sex[ns] = B[2 * k] - B[2 * j], sey[ns] = B[2 * k + 1] - B[2 * j + 1];
+        const double e2 = sex[ns] * sex[ns] + sey[ns] * sey[ns];
+        sinv[ns] = e2 > 0.0 ? nb_sep_rcp(e2) : 0.0;
+        ns++;
+      }
+    for (int i = 0; i < nA; i++)
+    {
+      const double ax = A[2 * i], ay = A[2 * i + 1];
+      for (int q = 0; q < ns; q++)
+      {
+        const double d2 = nb_pt_seg_inv(ax, ay, sux[q], suy[q], sex[q], sey[q], sinv[q], cx, cy);
         if (d2 < best)
         {
           best = d2;
           pax = ax, pay = ay, pbx = cx, pby = cy;
         }
       }
+    }
+  }
+  else
+  {
+    for (int i = 0; i < nA; i++)
+    {
+      const double ax = A[2 * i], ay = A[2 * i + 1];
+      for (int j = 0; j < nB; j++)
+        for (int k = j + 1; k < nB; k++)
+        {
+          const double d2 = nb_pt_seg(ax, ay, B[2 * j], B[2 * j + 1], B[2 * k], B[2 * k + 1], cx, cy);
+          if (d2 < best)
+          {
+            best = d2;
+            pax = ax, pay = ay, pbx = cx, pby = cy;
+          }
+        }
+    }
   }
   // vertices of B against the segments of A: polygon edges when ordered, else all pairs
-  for (int i = 0; i < nB; i++)
+  if (a_polygon || nA <= 2)
   {
-    const double bx = B[2 * i], by = B[2 * i + 1];
-    if (a_polygon || nA <= 2)
+    const int ne = nA <= 2 ? 1 : nA;
+    for (int j = 0; j < ne; j++)
     {
-      const int ne = nA <= 2 ? 1 : nA;
-      for (int j = 0; j < ne; j++)
+      const int k = (j + 1 < nA) ? j + 1 : 0;
+      const double ux = A[2 * j], uy = A[2 * j + 1], ex = A[2 * k] - ux, ey = A[2 * k + 1] - uy;
+      const double e2 = ex * ex + ey * ey;
+      const double inv = e2 > 0.0 ? nb_sep_rcp(e2) : 0.0;
+      for (int i = 0; i < nB; i++)
       {
-        const int k = (j + 1 < nA) ? j + 1 : 0;
-        const double d2 = nb_pt_seg(bx, by, A[2 * j], A[2 * j + 1], A[2 * k], A[2 * k + 1], cx, cy);
+        const double bx = B[2 * i], by = B[2 * i + 1];
+        const double d2 = nb_pt_seg_inv(bx, by, ux, uy, ex, ey, inv, cx, cy);
         if (d2 < best)
         {
           best = d2;
@@ -68,23 +124,31 @@ NB_HD bool nb_separate(const double* A, int nA, bool a_polygon, const double* B,
         }
       }
     }
-    else
-    {
-      for (int j = 0; j < nA; j++)
-        for (int k = j + 1; k < nA; k++)
+  }
+  else
+  {
+    for (int j = 0; j < nA; j++)
+      for (int k = j + 1; k < nA; k++)
+      {
+        const double ux = A[2 * j], uy = A[2 * j + 1], ex = A[2 * k] - ux, ey = A[2 * k + 1] - uy;
+        const double e2 = ex * ex + ey * ey;
+        const double inv = e2 > 0.0 ? nb_sep_rcp(e2) : 0.0;
+        for (int i = 0; i < nB; i++)
         {
-          const double d2 = nb_pt_seg(bx, by, A[2 * j], A[2 * j + 1], A[2 * k], A[2 * k + 1], cx, cy);
+          const double bx = B[2 * i], by = B[2 * i + 1];
+          const double d2 = nb_pt_seg_inv(bx, by, ux, uy, ex, ey, inv, cx, cy);
           if (d2 < best)
           {
             best = d2;
             pax = cx, pay = cy, pbx = bx, pby = by;
           }
         }
-    }
+      }
   }
   if (!(best > 1e-24)) return false;
   const double ux = pax - pbx, uy = pay - pby;
-  const double n0 = 2.0 * ux / best, n1 = 2.0 * uy / best;
+  const double ib = 2.0 * nb_sep_rcp(best);
+  const double n0 = ux * ib, n1 = uy * ib;
   const double d = -(n0 * (pax + pbx) + n1 * (pay + pby)) * 0.5;
   for (int i = 0; i < nA; i++)
     if (!(n0 * A[2 * i] + n1 * A[2 * i + 1] + d >= 1.0 - NB_SEP_EPS)) return false;

@@ -91,7 +91,7 @@ class ReplanCycle:
         self._np_of = np_of
         # intermediates and outputs (group-shaped buffers are sized by _ensure_groups)
         self.o = dict(
-            hull_ptr=z(B * N * NPOL, i64), hull_cnt=z((B, N, NPOL), i32), samp0=z((B, N, 2), f64),
+            samp0=z((B, N, 2), f64),
             esA_cnt=z((B, 2), i32), esA_alpha=z((B, cap, 2), i32), esA_beta=z((B, cap), f64), esA_bend=z((B, cap), i32),
             esA_active=z((B, NA), i32),
             esC_cnt=z((B, 2), i32), esC_alpha=z((B, cap, 2), i32), esC_beta=z((B, cap), f64), esC_bend=z((B, cap), i32),
@@ -213,7 +213,8 @@ class ReplanCycle:
         torch.cuda.synchronize()
         l0 = self.solver.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self._step_impl()
         self.launches_per_cycle = self.solver.launch_count() - l0   # library kernels one replay launches
         self.graph_G = self.G
@@ -265,8 +266,6 @@ class ReplanCycle:
         # (main) hulls / samples of the committed trajectories the agents plan against
         chk(L.nb_hulls_batch(h, G, DEV, p(d["t_group"]), p(d["recs"]), p(d["ones_g"]), self.delta, p(o["hull_xy_g"]),
                              p(o["hull_cnt_g"]), p(o["hull_ptr_g"]), p(o["nih0_g"]), p(o["samp_g"]), None, st), "nb_hulls_batch")
-        chk(L.nb_hull_index_batch(h, B, DEV, p(d["agent_id"]), p(d["group"]), p(d["known"]), p(o["hull_cnt_g"]),
-                                  p(o["hull_ptr"]), p(o["hull_cnt"]), st), "nb_hull_index_batch")
         mark("hulls_samples")
         # (stream B) entangle_state_A = PredictAlphasBetas(entangle_state_): needs the samples only
         if par_streams:
@@ -286,9 +285,10 @@ class ReplanCycle:
         a = capi.NbReplanArgs()
         a.B, a.space, a.n_hull_slots = B, DEV, self.N
         a.agent_id, a.n_int, a.coeff_init = d["agent_id"].data_ptr(), d["n_int"].data_ptr(), d["coeff_init"].data_ptr()
-        a.hull_ptr, a.hull_xy, a.hull_cnt = o["hull_ptr"].data_ptr(), o["hull_xy_g"].data_ptr(), o["hull_cnt"].data_ptr()
+        # shared-window mode: the lines kernel reads hull (group[b], j, i) directly (own slot / unknown empty)
+        a.hull_ptr, a.hull_xy, a.hull_cnt = None, o["hull_xy_g"].data_ptr(), o["hull_cnt_g"].data_ptr()
         a.hull_nvert = G * self.N * NPOL * HS
-        a.nih0, a.nih0_group = o["nih0_g"].data_ptr(), d["group"].data_ptr()
+        a.nih0, a.nih0_group, a.hull_known = o["nih0_g"].data_ptr(), d["group"].data_ptr(), d["known"].data_ptr()
         a.esv_cnt, a.esv_alpha, a.esv_active = d["esv_cnt"].data_ptr(), d["esv_alpha"].data_ptr(), d["esv_active"].data_ptr()
         a.bp_cnt, a.bp_xy = d["bp_cnt"].data_ptr(), d["bp_xy"].data_ptr()
         a.coeff_out, a.obj, a.status, a.iters = (o[k].data_ptr() for k in ("coeff_out", "obj", "status", "iters"))

@@ -42,7 +42,7 @@ extern "C" int emul_replan_batch(const nb_params* par, const double* pb, const i
   const int RS = 6 * NB_NFEAT_AX + 4 * NB_NPOL * LS;
   NbLinesIn in;
   in.agent_id = a->agent_id, in.n_int = a->n_int, in.coeff_init = a->coeff_init, in.NH = NH;
-  in.hull_ptr = a->hull_ptr, in.hull_cnt = a->hull_cnt, in.hull_xy = a->hull_xy, in.nih0 = a->nih0, in.nih0_group = a->nih0_group, in.st_ptr = st_ptr, in.st_xy = st_xy;
+  in.hull_ptr = a->hull_ptr, in.hull_cnt = a->hull_cnt, in.hull_xy = a->hull_xy, in.nih0 = a->nih0, in.nih0_group = a->nih0_group, in.hull_known = a->hull_known, in.st_ptr = st_ptr, in.st_xy = st_xy;
   in.esv_cnt = a->esv_cnt, in.esv_alpha = a->esv_alpha, in.esv_active = a->esv_active;
   in.bp_cnt = a->bp_cnt, in.bp_xy = a->bp_xy, in.pb = pb;
   std::vector<double> lines((size_t)NB_NPOL * LS * 3), cl((size_t)NB_NPOL * LS * 3), rows((size_t)5 * RS);
