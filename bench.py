@@ -42,7 +42,9 @@ def world_params(n_gpus: int, workload: str = "grid64"):
     xs = (np.arange(nx) - (nx - 1) / 2.0) * pitch
     ys = (np.arange(ny) - (ny - 1) / 2.0) * pitch
     gx, gy = np.meshgrid(xs, ys, indexing="ij")
-    p = Params(num_of_agents=nx * ny, tetherLength=25.0)
+    # ent_cap >= N + M: the front-end chain can then never overflow its storage (it declares a step
+    # entangling before the word exceeds N + M entries, kinodynamic_search.cpp:844-848)
+    p = Params(num_of_agents=nx * ny, tetherLength=25.0, ent_cap=max(48, nx * ny + 8))
     p.pb = np.stack([gx.ravel(), gy.ravel()], axis=1)
     p.x_min, p.x_max = xs[0] - 12.0, xs[-1] + 12.0
     p.y_min, p.y_max = ys[0] - 12.0, ys[-1] + 12.0
@@ -319,7 +321,9 @@ def run_ours(args):
         dom_ms = float(kt[:, dom].mean())
         alg_bytes = float(np.mean([sc.batch.algorithmic_bytes() for sc in scenes]))
         if scenes[0].batch.hull_xy.shape[0] == 0:   # hulls were built on the device only: count their real vertices
-            alg_bytes += 16.0 * float(cyc.o["hull_cnt"].sum().item()) + 16.0 * float(scenes[0].known.sum()) * par.num_pol
+            cnt_b = cyc.o["hull_cnt_g"].index_select(0, cyc.d["group"].long())          # [B][N][8]
+            kn = torch.from_numpy(scenes[0].known.astype(np.bool_)).to(dev)[:, :, None]
+            alg_bytes += 16.0 * float((cnt_b * kn).sum().item()) + 16.0 * float(scenes[0].known.sum()) * par.num_pol
         peak, which = measured_peak_gbs()
         achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
         line = {"metric": "replans_per_sec", "value": value, "unit": "replans/s", "n_gpus": world, "steps": args.steps,
@@ -332,7 +336,7 @@ def run_ours(args):
                 "kernels_ms": {"k_lines": float(kt[:, 0].mean()), "k_qp": float(kt[:, 1].mean())},
                 "stage_ms": stage,
                 "roofline": {"bound": "hbm", "kernel": ["k_lines", "k_qp"][dom], "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(["k_lines", "k_qp"][dom]),
+                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(["k_lines", "k_qp"][dom]) if args.workload == "grid64" and world == 1 else None,
                              "peak_source": which,
                              "algorithmic_bytes_per_launch": alg_bytes,
                              "note": "latency/FP64-issue bound at this size, not HBM bound (DESIGN.md)"},
