@@ -680,7 +680,10 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       const double a_aff = rmax > 1.0 ? 1.0 / rmax : 1.0;
       const double mu_aff = (mu * mq + a_aff * scross + a_aff * a_aff * sdd) / mq;
       const double rat = mu_aff / mu;
-      const double sigmu = rat * rat * rat * mu;
+      double sigmu = rat * rat * rat * mu;
+      // do not drive the complementarity below a tenth of what the stopping test needs: at mu ~ 1e-12 the
+      // normal matrix is too ill-conditioned for the dual residual to reach its tolerance
+      sigmu = fmax(sigmu, 0.1 * cs.tol * (1.0 + fabs(fobj)) / mq);
       // ---- corrector
       nb_qp_pass<NL, NB_PASS_LOAD_CORR>(g, cs, tb, sh, R, sigmu, 0.0, acc);
       const double rc_q = s_q * lam_q + dsa_q * dla_q - sigmu;

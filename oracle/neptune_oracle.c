@@ -1744,6 +1744,12 @@ static int ipm_solve(const qmodel* md, double* x, int max_iter, double tol, int*
         for (int r = 0; r < mq; r++) mua += (s[r] + alpha * ds[r]) * (lam[r] + alpha * dl[r]);
         mua /= mq;
         sigma = (mua / mu) * (mua / mu) * (mua / mu);
+        /* do not drive the complementarity below a tenth of what the stopping test needs: at mu ~ 1e-12
+         * the normal matrix is too ill-conditioned for the dual residual to reach its tolerance */
+        {
+          const double mu_floor = 0.1 * tol * (1.0 + fabs(fobj)) / mq;
+          if (sigma * mu < mu_floor) sigma = mu_floor / mu;
+        }
         memcpy(dsa, ds, sizeof(double) * mq);
         memcpy(dla, dl, sizeof(double) * mq);
       }
