@@ -135,9 +135,11 @@ def cpu_cycle(scene, threads: int):
     """One whole cycle of the scene's agents on the CPU oracle (hulls/samples, predict, LPs + QP,
     post-check, entangle re-check): the restatement of the reference algorithm, all host threads."""
     from neptune_b200 import capi
+    from neptune_b200.cycle import ReplanCycle
     from oracle import oracle as orc
     recs = capi.make_records(scene.committed)
-    rc, out = orc.cycle_batch(scene, recs, threads)
+    t_now = np.asarray(scene.t_start, np.float64) - ReplanCycle.DELTA_T_STEPS * scene.par.dc
+    rc, out = orc.cycle_batch(scene, recs, threads, t_now=t_now)
     assert rc == 0
     return out
 

@@ -214,10 +214,32 @@ int nb_postcheck_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_
  * Committed-trajectory records of this rank's agents for the all-gather: the pwp_now of
  * PolySolverGurobi::generatePwpOut (times shifted by t_start, solver_gurobi_poly.cpp:892-907).
  * recs_out [B][NB_REC_DOUBLES].  mu::composePieceWisePol with the previous plan (utils.cpp:318-402) is
- * SURVEY section 8(f) "next #2" and not applied here.
+ * applied by nb_commit_compose_batch / nb_compose_records_batch below.
  */
 int nb_commit_records_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
                             const double* t_start, double* recs_out, void* stream);
+
+/*
+ * Fused commit of the resident cycle, the tail of Neptune::replanFull (neptune.cpp:1685-1699): pwp_now from
+ * coeff/t_start as above, then recs_out[b] = composePieceWisePol(t_now[b], dc, prev[prev_agent[b] - 1], pwp_now)
+ * (prev_agent: 1-based agent ids as in nb_replan_args, NULL: prev[b]; has_prev NULL: all have a previous plan).  Where status[b] >= 2, entangled[b] != 0
+ * or collide[b] != 0 (each nullable) the replan is rejected and recs_out[b] = the previous record, as
+ * replanFull returns before publishing.  Device pointers only.  Overflow of the 16-piece record is reported
+ * by nb_check_async_errors.  n_pieces [B] nullable.
+ */
+int nb_commit_compose_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
+                            const double* t_start, const double* t_now, const double* prev, const int32_t* prev_agent,
+                            const uint8_t* has_prev, const int32_t* status, const int32_t* entangled,
+                            const int32_t* collide, double* recs_out, int32_t* n_pieces, void* stream);
+
+/*
+ * Replaces mu::composePieceWisePol (neptune/src/utils.cpp:318-402) as used by Neptune::replanFull
+ * (neptune.cpp:1689-1699): out[b] = pieces of prev[b] between t[b] and the start of now[b], then now[b];
+ * where has_prev[b] == 0, out[b] = now[b] (exists_previous_pwp_ == false).  All [B][NB_REC_DOUBLES].
+ * n_pieces [B]: pieces of out (0 = the reference's empty "dummy" result).  SURVEY section 8(f) "next #2".
+ */
+int nb_compose_records_batch(nb_handle* h, int32_t B, int32_t space, const double* t, const uint8_t* has_prev,
+                             const double* prev, const double* now, double* out, int32_t* n_pieces, void* stream);
 
 /*
  * Entanglement-signature chain, batched (one agent per warp).  State = eu::ent_state

@@ -306,6 +306,19 @@ def solver_postcheck(self, n_int, coeff, t_start, recs, late, delta):
     return col
 
 
+def solver_compose(self, t, has_prev, prev, now):
+    """``mu::composePieceWisePol`` on committed-trajectory records -> (n_pieces [B], out [B][210])."""
+    arrs = [np.ascontiguousarray(t, np.float64), np.ascontiguousarray(has_prev, np.uint8),
+            np.ascontiguousarray(prev, np.float64), np.ascontiguousarray(now, np.float64)]
+    out, npc = np.zeros_like(arrs[3]), np.zeros(len(arrs[0]), np.int32)
+    f = lib().nb_compose_records_batch
+    f.argtypes = [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P]
+    _check(f(self._h, len(arrs[0]), NB_HOST, _np(arrs[0]), _np(arrs[1]), _np(arrs[2]), _np(arrs[3]), _np(out), _np(npc),
+             None), "nb_compose_records_batch")
+    return npc, out
+
+
+Solver.compose = solver_compose
 Solver.hulls = solver_hulls
 Solver.postcheck = solver_postcheck
 

@@ -355,12 +355,43 @@ __global__ void k_postcheck_hulls(NbConsts cs, int B, const int* n_int, const do
   if (nb_gjk_collision(hull_xy_g + src * NB_HMAX * 2, hn, A, 4)) atomicOr(collide + b, 1);
 }
 
-__global__ void k_commit(int B, const int* n_int, const double* coeff, const double* t_start, double T, double* recs)
+__global__ void k_compose(int B, const double* t, const uint8_t* has_prev, const double* prev, const double* now,
+                          double* out, int* n_pieces, int* err)
 {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* nw = now + (size_t)b * NB_REC;
+  double* o = out + (size_t)b * NB_REC;
+  int np;
+  if (!has_prev[b])
+  {
+    for (int q = 0; q < NB_REC; q++) o[q] = nw[q];
+    np = (int)nw[0];
+  }
+  else
+    np = nb_compose_records(t[b], prev + (size_t)b * NB_REC, nw, o);
+  if (np < 0)
+  {
+    *err = 4;
+    np = 0;
+  }
+  n_pieces[b] = np;
+}
+
+// pwp_now of generatePwpOut (times shifted by t_start, solver_gurobi_poly.cpp:892-907) and, when t_now is
+// given, pwp_out = composePieceWisePol(time_now, dc, pwp_prev, pwp_now) of Neptune::replanFull
+// (neptune.cpp:1689-1699).  An agent whose replan failed, ended entangled or collides in the post-check keeps
+// its previous record (replanFull returns before pwp_out is touched).
+__global__ void k_commit(int B, const int* n_int, const double* coeff, const double* t_start, double T, double* recs,
+                         const double* t_now, const double* prev, const int* prev_agent, const uint8_t* has_prev,
+                         const int* status, const int* entangled, const int* collide, int* n_pieces, int* err)
+{
+  __shared__ double now[NB_REC];
   const int b = blockIdx.x;
   if (b >= B) return;
   double* r = recs + (size_t)b * NB_REC;
   const int n = n_int[b];
+  const bool compose = t_now != nullptr;
   for (int q = threadIdx.x; q < NB_REC; q += blockDim.x)
   {
     double v = 0.0;
@@ -376,7 +407,32 @@ __global__ void k_commit(int B, const int* n_int, const double* coeff, const dou
       const int e = q - (NB_TP + 2), ax = e / (NB_TP * 4), rem = e % (NB_TP * 4), piece = rem / 4, c = rem % 4;
       v = piece < n ? coeff[(size_t)b * 96 + ax * 32 + piece * 4 + c] : 0.0;
     }
-    r[q] = v;
+    if (compose)
+      now[q] = v;
+    else
+      r[q] = v;
+  }
+  if (!compose) return;
+  __syncthreads();
+  const double* pv = prev + (size_t)(prev_agent ? prev_agent[b] - 1 : b) * NB_REC;
+  const bool hp = has_prev == nullptr || has_prev[b];
+  const bool ok = !((status && status[b] >= 2) || (entangled && entangled[b]) || (collide && collide[b]));
+  if (!ok || !hp)
+  {
+    const double* src = (!ok && hp) ? pv : now;  // failed without a previous plan: nothing better to publish than pwp_now
+    for (int q = threadIdx.x; q < NB_REC; q += blockDim.x) r[q] = src[q];
+    if (threadIdx.x == 0 && n_pieces) n_pieces[b] = (int)src[0];
+    return;
+  }
+  if (threadIdx.x == 0)
+  {
+    int np = nb_compose_records(t_now[b], pv, now, r);
+    if (np < 0)
+    {
+      *err = 4;
+      np = 0;
+    }
+    if (n_pieces) n_pieces[b] = np;
   }
 }
 
@@ -486,7 +542,7 @@ extern "C" int nb_check_async_errors(nb_handle* h, void* stream)
   NB_CUDA(cudaMemsetAsync(h->err.p, 0, sizeof(int), (cudaStream_t)stream));
   if (err)
   {
-    g_err = "a fixed-capacity list overflowed in an asynchronous call (ent_slots)";
+    g_err = "a fixed-capacity list overflowed in an asynchronous call (ent_slots, ent_cap or a 16-piece record)";
     return NB_ERR_CAPACITY;
   }
   return NB_OK;
@@ -1044,7 +1100,8 @@ extern "C" int nb_commit_records_batch(nb_handle* h, int32_t B, int32_t space, c
   if ((rc = stage_in(h, 1, space, coeff, (size_t)B * 96, st, &dc))) return rc;
   if ((rc = stage_in(h, 2, space, t_start, (size_t)B, st, &dt))) return rc;
   if ((rc = stage_out(h, 0, space, recs_out, (size_t)B * NB_REC, &dr))) return rc;
-  k_commit<<<B, 64, 0, st>>>(B, dn, dc, dt, h->cs.T, dr);
+  k_commit<<<B, 64, 0, st>>>(B, dn, dc, dt, h->cs.T, dr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                             (int*)h->err.p);
   h->launches += 1;
   NB_CUDA(cudaGetLastError());
   if (space == NB_HOST)
@@ -1093,6 +1150,72 @@ extern "C" int nb_postcheck_hulls_batch(nb_handle* h, int32_t B, int32_t space, 
   NB_CUDA(cudaMemsetAsync(collide, 0, (size_t)B * sizeof(int), st));
   k_postcheck_hulls<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(h->cs, B, n_int, coeff, group, hull_xy_g, hull_cnt_g, late,
                                                                collide);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+extern "C" int nb_compose_records_batch(nb_handle* h, int32_t B, int32_t space, const double* t, const uint8_t* has_prev,
+                                        const double* prev, const double* now, double* out, int32_t* n_pieces,
+                                        void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const double *dt, *dp, *dn;
+  const uint8_t* dh;
+  double* dout;
+  int* dnp;
+  int rc;
+  if ((rc = stage_in(h, 0, space, t, (size_t)B, st, &dt))) return rc;
+  if ((rc = stage_in(h, 1, space, has_prev, (size_t)B, st, &dh))) return rc;
+  if ((rc = stage_in(h, 2, space, prev, (size_t)B * NB_REC, st, &dp))) return rc;
+  if ((rc = stage_in(h, 3, space, now, (size_t)B * NB_REC, st, &dn))) return rc;
+  if ((rc = stage_out(h, 0, space, out, (size_t)B * NB_REC, &dout))) return rc;
+  if ((rc = stage_out(h, 1, space, n_pieces, (size_t)B, &dnp))) return rc;
+  k_compose<<<(B + 63) / 64, 64, 0, st>>>(B, dt, dh, dp, dn, dout, dnp, (int*)h->err.p);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
+  if (space == NB_HOST)
+  {
+    NB_CUDA(cudaMemcpyAsync(out, dout, (size_t)B * NB_REC * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(n_pieces, dnp, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    int err = 0;
+    NB_CUDA(cudaMemcpyAsync(&err, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaStreamSynchronize(st));
+    if (err)
+    {
+      NB_CUDA(cudaMemsetAsync(h->err.p, 0, sizeof(int), st));
+      g_err = "nb_compose_records_batch: composed trajectory exceeds 16 pieces";
+      return NB_ERR_CAPACITY;
+    }
+  }
+  return NB_OK;
+}
+
+extern "C" int nb_commit_compose_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* n_int, const double* coeff,
+                                       const double* t_start, const double* t_now, const double* prev,
+                                       const int32_t* prev_agent, const uint8_t* has_prev, const int32_t* status,
+                                       const int32_t* entangled, const int32_t* collide, double* recs_out,
+                                       int32_t* n_pieces, void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  if (space != NB_DEVICE)
+  {
+    g_err = "nb_commit_compose_batch: device pointers only (it runs inside the resident replan cycle)";
+    return NB_ERR_ARG;
+  }
+  if (!t_now || !prev)
+  {
+    g_err = "nb_commit_compose_batch: t_now and prev are required";
+    return NB_ERR_ARG;
+  }
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  k_commit<<<B, 64, 0, st>>>(B, n_int, coeff, t_start, h->cs.T, recs_out, t_now, prev, prev_agent, has_prev, status, entangled,
+                             collide, n_pieces, (int*)h->err.p);
   h->launches += 1;
   NB_CUDA(cudaGetLastError());
   return NB_OK;

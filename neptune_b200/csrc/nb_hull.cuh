@@ -400,3 +400,56 @@ NB_HD int nb_pwp_collides(const NbConsts& cs, const double* coeff /*[3][8][4]*/,
   }
   return 0;
 }
+
+// mu::composePieceWisePol (utils.cpp:318-402) on committed-trajectory records: the pieces of p1 that start
+// after t and before p2 begins, then p2 (Neptune::replanFull neptune.cpp:1689-1699).  p1 / p2 are local
+// copies whose first / last times are adjusted exactly as the reference adjusts its arguments (:320-336).
+// Returns the number of pieces, 0 for the reference's empty "dummy" (:342-354), -1 beyond NB_TP pieces.
+NB_HD int nb_compose_records(double t, const double* p1_in, const double* p2_in, double* out)
+{
+  const int n1 = (int)p1_in[0], n2 = (int)p2_in[0];
+  double t1[NB_TP + 1], t2[NB_TP + 1];
+  if (n1 < 1 || n2 < 1 || n1 > NB_TP || n2 > NB_TP)  // empty pwp: the reference reads .back() of an empty vector
+  {
+    for (int q = 0; q < NB_REC; q++) out[q] = 0.0;
+    return 0;
+  }
+  for (int i = 0; i <= NB_TP; i++) t1[i] = p1_in[1 + i], t2[i] = p2_in[1 + i];
+  if (t > t1[n1] && t < t2[0]) t2[0] = t;
+  if (t1[n1] < t2[0]) t2[0] = t1[n1];
+  if (t < t1[0]) t1[0] = t;
+  if (fabs(t - t2[0]) < 1e-5)
+  {
+    for (int q = 0; q < NB_REC; q++) out[q] = p2_in[q];
+    out[1] = t2[0];
+    return n2;
+  }
+  for (int q = 0; q < NB_REC; q++) out[q] = 0.0;
+  if (t1[n1] < t2[0] || t > t2[n2] || t < t1[0]) return 0;
+  int np = 0;
+  out[1] = t;
+  for (int i = 1; i <= n1; i++)  // i = 0 never qualifies: t1[0] <= t after :332-336
+    if (t1[i] > t && t1[i] < t2[0])
+    {
+      if (np >= NB_TP) return -1;
+      for (int ax = 0; ax < 3; ax++)
+        for (int c = 0; c < 4; c++)
+          out[1 + (NB_TP + 1) + ax * NB_TP * 4 + 4 * np + c] = p1_in[1 + (NB_TP + 1) + ax * NB_TP * 4 + 4 * (i - 1) + c];
+      np++;
+      out[1 + np] = t1[i];
+    }
+  for (int i = 0; i <= n2; i++)
+    if (t2[i] > t)
+    {
+      if (np >= NB_TP) return -1;
+      const double* src = (i == 0) ? p1_in : p2_in;
+      const int k = (i == 0) ? n1 - 1 : i - 1;
+      for (int ax = 0; ax < 3; ax++)
+        for (int c = 0; c < 4; c++)
+          out[1 + (NB_TP + 1) + ax * NB_TP * 4 + 4 * np + c] = src[1 + (NB_TP + 1) + ax * NB_TP * 4 + 4 * k + c];
+      np++;
+      out[1 + np] = t2[i];
+    }
+  out[0] = (double)np;
+  return np;
+}

@@ -78,7 +78,7 @@ class ReplanCycle:
             bp_cnt=(N, i32), bp_xy=((N, par.bp_max, 2), f64),
             es_cnt=((B, 2), i32), es_alpha=((B, cap, 2), i32), es_beta=((B, cap), f64), es_bend=((B, cap), i32),
             es_active=((B, NA), i32), prev_pos=((B, N + 1, 2), f64), prev_pos_agent=((B, N, 2), f64), cur=((B, 2), f64),
-            t_group=(B, f64), group=(B, i32))
+            t_group=(B, f64), group=(B, i32), t_now=(B, f64))
         self.layout, off = {}, 0
         for k, (shape, dt) in spec.items():
             shape = (shape,) if isinstance(shape, int) else tuple(shape)
@@ -96,7 +96,7 @@ class ReplanCycle:
             esA_active=z((B, NA), i32),
             esC_cnt=z((B, 2), i32), esC_alpha=z((B, cap, 2), i32), esC_beta=z((B, cap), f64), esC_bend=z((B, cap), i32),
             esC_active=z((B, NA), i32),
-            new_recs=z((B, REC), f64))
+            new_recs=z((B, REC), f64), new_pieces=z(B, i32))
         self.G = 0
         # packed outputs (one D2H copy)
         ospec = dict(coeff_out=((B, 3, NPOL, 4), f64), obj=(B, f64), status=(B, i32), iters=((B, 2), i32),
@@ -149,9 +149,10 @@ class ReplanCycle:
         L.nb_entangle_predict_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, capi.NbEntState, P, P, P, P, P]
         L.nb_entangle_check_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, capi.NbEntState, P, P, P, C.c_int32, P, P]
         L.nb_postcheck_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, P, C.c_double, P, P]
-        L.nb_commit_records_batch.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, P]
+        L.nb_commit_compose_batch.argtypes = [P, C.c_int32, C.c_int32] + [P] * 13
 
     # ------------------------------------------------------------------ host <-> device
+    DELTA_T_STEPS = 2   # t_start - time_now in units of dc (deltaT_ of neptune.cpp:1236-1262 for the synthetic world)
     OUT_KEYS = ("coeff_out", "obj", "status", "iters", "entangled", "collide")
 
     def host_inputs(self, scene) -> dict:
@@ -168,7 +169,8 @@ class ReplanCycle:
                    esv_cnt=b.esv_cnt, esv_alpha=b.esv_alpha, esv_active=b.esv_active, bp_cnt=b.bp_cnt, bp_xy=b.bp_xy,
                    es_cnt=scene.es0_cnt, es_alpha=scene.es0_alpha, es_beta=scene.es0_beta, es_bend=scene.es0_bend,
                    es_active=scene.es0_active, prev_pos=scene.prev_pos, prev_pos_agent=scene.prev_pos_agent,
-                   cur=np.ascontiguousarray(scene.state_A[:, 0, :2]), t_group=tg, group=inv.astype(np.int32))
+                   cur=np.ascontiguousarray(scene.state_A[:, 0, :2]), t_group=tg, group=inv.astype(np.int32),
+                   t_now=np.asarray(scene.t_start, np.float64) - self.DELTA_T_STEPS * self.par.dc)
         buf = torch.zeros(self.in_bytes, dtype=torch.uint8)
         if torch.cuda.is_available():
             buf = buf.pin_memory()
@@ -309,8 +311,12 @@ class ReplanCycle:
                                           p(d["n_int"]), p(o["coeff_out"]), samp_ptr, shared, p(o["entangled"]), st),
                 "nb_entangle_check_batch")
         mark("postcheck")
-        chk(L.nb_commit_records_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["t_start"]), p(o["new_recs"]), st),
-            "nb_commit_records_batch")
+        # tail of replanFull (neptune.cpp:1685-1699): pwp_out = composePieceWisePol(time_now, dc, pwp_prev, pwp_now);
+        # an agent whose replan was rejected keeps publishing its previous trajectory
+        chk(L.nb_commit_compose_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["t_start"]), p(d["t_now"]),
+                                      p(d["recs"]), p(d["agent_id"]), None, p(o["status"]), p(o["entangled"]),
+                                      p(o["collide"]), p(o["new_recs"]), p(o["new_pieces"]), st),
+            "nb_commit_compose_batch")
         mark("commit")
         if self.profile:
             torch.cuda.synchronize()

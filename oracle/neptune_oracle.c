@@ -2238,3 +2238,101 @@ int orc_cycle_batch(const orc_params* par, int B, const int* agent_id, const int
   }
   return rc_all;
 }
+
+/*
+ * mu::composePieceWisePol (utils.cpp:318-402) on committed-trajectory records (layout of
+ * include/neptune_b200.h): out = the pieces of p1 that start after t and before p2 begins, then p2
+ * (caller: Neptune::replanFull neptune.cpp:1689-1699).  p1 and p2 are modified in place exactly as the
+ * reference modifies its arguments (times.front() adjustments :320-336).  Returns the number of pieces
+ * of out, 0 for the "dummy" empty result (:342-354), -1 if out would exceed 16 pieces.
+ */
+int orc_compose_records(double t, double dc, double* p1, double* p2, double* out)
+{
+  (void)dc;
+  int n1 = (int)p1[0], n2 = (int)p2[0];
+  double* t1 = p1 + 1;
+  double* t2 = p2 + 1;
+  if (n1 < 1 || n2 < 1 || n1 > ORC_REC_TP || n2 > ORC_REC_TP) /* empty pwp: the reference reads .back() of an empty vector */
+  {
+    memset(out, 0, sizeof(double) * ORC_REC);
+    return 0;
+  }
+  if (t > t1[n1] && t < t2[0]) t2[0] = t;
+  if (t1[n1] < t2[0]) t2[0] = t1[n1];
+  if (t < t1[0]) t1[0] = t;
+  if (fabs(t - t2[0]) < 1e-5)
+  {
+    memcpy(out, p2, sizeof(double) * ORC_REC);
+    return n2;
+  }
+  memset(out, 0, sizeof(double) * ORC_REC);
+  if (t1[n1] < t2[0] || t > t2[n2] || t < t1[0]) return 0;
+  double* to = out + 1;
+  int np = 0;
+  to[0] = t;
+#define COPY_PIECE(src, k)                                                                   \
+  do                                                                                         \
+  {                                                                                          \
+    if (np >= ORC_REC_TP) return -1;                                                         \
+    for (int ax = 0; ax < 3; ax++)                                                           \
+      memcpy(out + 1 + (ORC_REC_TP + 1) + ax * ORC_REC_TP * 4 + 4 * np,                      \
+             (src) + 1 + (ORC_REC_TP + 1) + ax * ORC_REC_TP * 4 + 4 * (k), sizeof(double) * 4); \
+  } while (0)
+  for (int i = 1; i <= n1; i++) /* i = 0 never qualifies: t1[0] <= t after :332-336 */
+    if (t1[i] > t && t1[i] < t2[0])
+    {
+      COPY_PIECE(p1, i - 1);
+      np++;
+      to[np] = t1[i];
+    }
+  for (int i = 0; i <= n2; i++)
+    if (t2[i] > t)
+    {
+      if (i == 0)
+        COPY_PIECE(p1, n1 - 1);
+      else
+        COPY_PIECE(p2, i - 1);
+      np++;
+      to[np] = t2[i];
+    }
+#undef COPY_PIECE
+  out[0] = (double)np;
+  return np;
+}
+
+/*
+ * Tail of Neptune::replanFull (neptune.cpp:1685-1699) for a batch: pwp_now = coefficients with times shifted
+ * by t_start (generatePwpOut, solver_gurobi_poly.cpp:892-907), pwp_out = composePieceWisePol(time_now, dc,
+ * pwp_prev, pwp_now).  A rejected replan (status >= 2, entangled, collide) keeps the previous record.
+ * recs [N][210] (prev of agent b = recs[agent_id[b] - 1]); new_recs [B][210]; n_pieces [B].
+ */
+int orc_commit_compose_batch(const orc_params* par, int B, const int* agent_id, const int* n_int, const double* coeff_out,
+                             const double* t_start, const double* t_now, const double* recs, const int* status,
+                             const int* entangled, const int* collide, double* new_recs, int* n_pieces)
+{
+  int rc = 0;
+  for (int b = 0; b < B; b++)
+  {
+    double now[ORC_REC], prev[ORC_REC];
+    double* out = new_recs + (size_t)b * ORC_REC;
+    memset(now, 0, sizeof(now));
+    memcpy(prev, recs + (size_t)(agent_id[b] - 1) * ORC_REC, sizeof(prev));
+    const int n = n_int[b];
+    now[0] = (double)n;
+    for (int k = 0; k <= n; k++) now[1 + k] = t_start[b] + (double)k * par->T_span;
+    for (int ax = 0; ax < 3; ax++)
+      for (int i = 0; i < n; i++)
+        for (int c = 0; c < 4; c++)
+          now[1 + (ORC_REC_TP + 1) + ax * ORC_REC_TP * 4 + 4 * i + c] = coeff_out[(size_t)b * 96 + ax * 32 + 4 * i + c];
+    if (status[b] >= 2 || entangled[b] || collide[b])
+    {
+      memcpy(out, prev, sizeof(prev));
+      n_pieces[b] = (int)prev[0];
+      continue;
+    }
+    int np = orc_compose_records(t_now[b], 0.0 /* dc: unused by the reference body */, prev, now, out);
+    if (np < 0) rc = -1, np = 0;
+    n_pieces[b] = np;
+  }
+  return rc;
+}

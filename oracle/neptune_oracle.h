@@ -188,6 +188,14 @@ typedef struct orc_batch
 
 int orc_replan_batch(const orc_params* par, const orc_batch* b, int nthreads);
 
+/* mu::composePieceWisePol utils.cpp:318-402 on 210-double records; p1, p2 modified like the reference's arguments */
+int orc_compose_records(double t, double dc, double* p1, double* p2, double* out);
+
+/* tail of replanFull (neptune.cpp:1685-1699): pwp_now + composePieceWisePol with the previous record */
+int orc_commit_compose_batch(const orc_params* par, int B, const int* agent_id, const int* n_int, const double* coeff_out,
+                             const double* t_start, const double* t_now, const double* recs, const int* status,
+                             const int* entangled, const int* collide, double* new_recs, int* n_pieces);
+
 /* whole cycle per agent (hulls/samples, predict, back end, post-check): the CPU baseline of bench.py */
 int orc_cycle_batch(const orc_params* par, int B, const int* agent_id, const int* n_int, const double* coeff_init,
                     const double* t_start, const double* recs, const unsigned char* known, const double* pb,

@@ -299,7 +299,7 @@ def export_qp(batch, a: int, fallback: bool, lines, line_ok):
                 has_qc=bool(has_qc.value), n=n)
 
 
-def cycle_batch(scene, recs, nthreads: int = 1, do_entangle: bool = True):
+def cycle_batch(scene, recs, nthreads: int = 1, do_entangle: bool = True, t_now=None):
     """orc_cycle_batch over a neptune_b200.scenes.Scene: the whole per-agent cycle on the CPU."""
     b, par = scene.batch, scene.par
     op = make_params(par)
@@ -324,4 +324,21 @@ def cycle_batch(scene, recs, nthreads: int = 1, do_entangle: bool = True):
     rc = f(C.byref(op), C.c_int(B), *[_p(arrs[k]) for k in order], C.c_double(2 * par.drone_radius),
            C.c_int(int(do_entangle)), _p(out["coeff_out"]), _p(out["obj"]), _p(out["status"]), _p(out["iters"]),
            _p(out["entangled"]), _p(out["collide"]), C.c_int(nthreads))
+    if rc == 0 and t_now is not None:
+        out["new_recs"], out["new_pieces"] = np.zeros((B, 210)), np.zeros(B, np.int32)
+        g = lib().orc_commit_compose_batch
+        g.restype = C.c_int
+        rc = g(C.byref(op), C.c_int(B), _p(arrs["agent_id"]), _p(arrs["n_int"]), _p(out["coeff_out"]), _p(arrs["t_start"]),
+               _p(_c(t_now, np.float64)), _p(arrs["recs"]), _p(out["status"]), _p(out["entangled"]), _p(out["collide"]),
+               _p(out["new_recs"]), _p(out["new_pieces"]))
     return rc, out
+
+
+def compose_records(t, dc, p1, p2):
+    """mu::composePieceWisePol on records; returns (n_pieces, out, p1_modified, p2_modified)."""
+    p1, p2 = _c(p1, np.float64).copy(), _c(p2, np.float64).copy()
+    out = np.zeros_like(p1)
+    f = lib().orc_compose_records
+    f.restype = C.c_int
+    n = f(C.c_double(t), C.c_double(dc), _p(p1), _p(p2), _p(out))
+    return n, out, p1, p2

@@ -66,3 +66,13 @@ def postcheck(par, n_int, coeff, t_start, recs, late, delta):
     f.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5 + [C.c_double, C.c_void_p]
     f(C.addressof(nbp), len(arrs[0]), *[a.ctypes.data_as(C.c_void_p) for a in arrs], delta, col.ctypes.data_as(C.c_void_p))
     return col
+
+
+def compose(t, has_prev, prev, now):
+    arrs = [np.ascontiguousarray(t, np.float64), np.ascontiguousarray(has_prev, np.uint8),
+            np.ascontiguousarray(prev, np.float64), np.ascontiguousarray(now, np.float64)]
+    out, npc = np.zeros_like(arrs[3]), np.zeros(len(arrs[0]), np.int32)
+    f = lib().emul_compose
+    f.argtypes = [C.c_int] + [C.c_void_p] * 6
+    f(len(arrs[0]), *[a.ctypes.data_as(C.c_void_p) for a in arrs], out.ctypes.data_as(C.c_void_p), npc.ctypes.data_as(C.c_void_p))
+    return npc, out

@@ -180,3 +180,19 @@ extern "C" int emul_postcheck(const nb_params* par, int B, const int32_t* n_int,
   }
   return 0;
 }
+
+extern "C" int emul_compose(int B, const double* t, const uint8_t* has_prev, const double* prev, const double* now,
+                            double* out, int32_t* n_pieces)
+{
+  for (int b = 0; b < B; b++)
+  {
+    if (!has_prev[b])
+    {
+      memcpy(out + (size_t)b * NB_REC, now + (size_t)b * NB_REC, sizeof(double) * NB_REC);
+      n_pieces[b] = (int)now[(size_t)b * NB_REC];
+    }
+    else
+      n_pieces[b] = nb_compose_records(t[b], prev + (size_t)b * NB_REC, now + (size_t)b * NB_REC, out + (size_t)b * NB_REC);
+  }
+  return 0;
+}

@@ -23,7 +23,7 @@ def test_abi_exports_every_declared_symbol():
     lib = C.CDLL(capi.LIB_PATH)
     hdr = open(os.path.join(ROOT, "include", "neptune_b200.h")).read()
     names = set(re.findall(r"\b(nb_[a-z_0-9]+)\s*\(", hdr))
-    assert {"nb_create", "nb_replan_batch", "nb_separate_batch", "nb_entangle_predict_batch", "nb_hulls_batch",
+    assert {"nb_create", "nb_replan_batch", "nb_separate_batch", "nb_entangle_predict_batch", "nb_hulls_batch", "nb_compose_records_batch",
             "nb_postcheck_batch", "nb_destroy"} <= names
     for n in sorted(names):
         assert hasattr(lib, n), n
@@ -129,3 +129,49 @@ def test_emulated_entangle_random_walks_bend_points(oracle):
     sc = make_scene(par, 3003, sync=False)
     mx_a, mx_b = compare_backends(par, sc, OracleEntBackend(oracle), EmulEntBackend())
     assert mx_a >= 8 and mx_b >= 2   # the walks do exercise long words and bend points
+
+
+def test_compose_records_oracle_restatement_and_emulation(oracle):
+    """mu::composePieceWisePol (utils.cpp:318-402): the C oracle agrees with a list-based restatement on
+    every branch, and the device source (compiled for the host) agrees with the oracle bit for bit."""
+    from tests import compose_util as cu
+    from tests.emul import emul
+    rng = np.random.default_rng(5)
+    ts, prevs, nows, outs, nps = [], [], [], [], []
+    seen = set()
+    for it in range(700):
+        kind = cu.KINDS[it % len(cu.KINDS)]
+        t, p1, p2 = cu.random_case(rng, kind)
+        n, out, _, _ = oracle.compose_records(t, 0.05, p1, p2)
+        times, pieces = cu.compose_lists(t, cu.rec_to(p1), cu.rec_to(p2))
+        assert n == max(len(times) - 1, 0), kind
+        if n > 0:
+            ot, oc = cu.rec_to(out)
+            assert ot == [float(x) for x in times]
+            assert np.array_equal(oc, np.stack(pieces, axis=1))
+            assert all(ot[i] < ot[i + 1] for i in range(n)) or kind in ("same", "knot")
+        else:
+            assert not out.any()
+        seen.add((kind, n > 0))
+        ts.append(t), prevs.append(p1), nows.append(p2), outs.append(out), nps.append(n)
+    assert ("mid", True) in seen and ("stale", False) in seen and ("gap", True) in seen
+    has_prev = np.ones(len(ts), np.uint8)
+    has_prev[::11] = 0
+    npc, eo = emul.compose(ts, has_prev, np.stack(prevs), np.stack(nows))
+    for b in range(len(ts)):
+        if has_prev[b]:
+            assert npc[b] == nps[b] and np.array_equal(eo[b], outs[b]), b
+        else:
+            assert np.array_equal(eo[b], nows[b])
+
+
+def test_compose_records_overflow_is_reported(oracle):
+    from tests import compose_util as cu
+    from tests.emul import emul
+    t1 = 0.1 * np.arange(17)
+    p1 = cu.rec_from(t1, np.ones((3, 16, 4)))
+    p2 = cu.rec_from(1.55 + 0.5 * np.arange(9), np.ones((3, 8, 4)))
+    n, _, _, _ = oracle.compose_records(0.05, 0.05, p1, p2)
+    assert n == -1
+    npc, _ = emul.compose([0.05], [1], p1[None], p2[None])
+    assert npc[0] == -1

@@ -231,3 +231,31 @@ def test_empty_batch_is_a_noop(capi):
     a.B, a.space = 0, 0
     s.replan_args(a)
     s.close()
+
+
+@pytest.mark.gpu
+def test_compose_records_matches_oracle(capi, oracle):
+    """nb_compose_records_batch (mu::composePieceWisePol, utils.cpp:318-402): bit-exact against the oracle on
+    every branch of the reference function; more than 16 pieces is a loud capacity error."""
+    from tests import compose_util as cu
+    par = config("mtlp5")
+    sv = capi.Solver(par)
+    rng = np.random.default_rng(17)
+    ts, prevs, nows, outs, nps = [], [], [], [], []
+    for it in range(2100):
+        t, p1, p2 = cu.random_case(rng, cu.KINDS[it % len(cu.KINDS)])
+        n, out, _, _ = oracle.compose_records(t, par.dc, p1, p2)
+        ts.append(t), prevs.append(p1), nows.append(p2), outs.append(out), nps.append(n)
+    has_prev = np.ones(len(ts), np.uint8)
+    has_prev[::13] = 0
+    npc, go = sv.compose(ts, has_prev, np.stack(prevs), np.stack(nows))
+    for b in range(len(ts)):
+        if has_prev[b]:
+            assert npc[b] == nps[b] and np.array_equal(go[b], outs[b]), b
+        else:
+            assert npc[b] == int(nows[b][0]) and np.array_equal(go[b], nows[b])
+    p1 = cu.rec_from(0.1 * np.arange(17), np.ones((3, 16, 4)))
+    p2 = cu.rec_from(1.55 + 0.5 * np.arange(9), np.ones((3, 8, 4)))
+    with pytest.raises(RuntimeError, match="16 pieces"):
+        sv.compose([0.05], [1], p1[None], p2[None])
+    sv.compose(ts[:4], has_prev[:4], np.stack(prevs[:4]), np.stack(nows[:4]))   # the handle stays usable

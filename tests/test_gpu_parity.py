@@ -208,13 +208,23 @@ def test_replan_cycle_matches_oracle_composite(capi, oracle, cfg, seed):
     ent = ob.check_batch(par, b.agent_id, b.n_int, ref.coeff_out, sc.samp, sc.known, sc.strep, b.bp_cnt, b.bp_xy,
                          sc.esA_cnt, sc.esA_alpha, sc.esA_beta, sc.esA_bend, sc.esA_active)[0]
     assert np.array_equal(hout["entangled"], ent)
-    # committed records: times shifted by t_start (generatePwpOut :898), coefficients of pwp_out
-    rec = o["new_recs"]
+    # published records: pwp_now (times shifted by t_start, generatePwpOut :898) composed with the agent's previous
+    # record at time_now (replanFull neptune.cpp:1689-1699); a rejected replan keeps the previous record
+    rec, recs_in = o["new_recs"], capi.make_records(sc.committed)
     for bi in range(b.B):
         n = int(b.n_int[bi])
-        assert rec[bi, 0] == n
-        assert np.allclose(rec[bi, 1:2 + n], sc.t_start[bi] + par.T_span * np.arange(n + 1), atol=1e-12)
-        assert np.array_equal(rec[bi, 18:].reshape(3, 16, 4)[:, :n], o["coeff_out"][bi, :, :n])
+        now = np.zeros(210)
+        now[0] = n
+        now[1:2 + n] = sc.t_start[bi] + par.T_span * np.arange(n + 1)
+        now[18:].reshape(3, 16, 4)[:, :n] = o["coeff_out"][bi, :, :n]
+        prev = recs_in[int(b.agent_id[bi]) - 1]
+        if hout["status"][bi] >= 2 or hout["entangled"][bi] or hout["collide"][bi]:
+            assert np.array_equal(rec[bi], prev)
+            continue
+        npc, want, _, _ = oracle.compose_records(hin["t_now"][bi], par.dc, prev, now)
+        assert npc == o["new_pieces"][bi] and npc >= n
+        assert np.array_equal(rec[bi], want)
+        assert rec[bi, 1] == hin["t_now"][bi] and rec[bi, 1 + npc] == now[1 + n]
     del cyc
     torch.cuda.synchronize()
 
