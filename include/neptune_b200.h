@@ -283,6 +283,73 @@ int nb_entangle_check_batch(nb_handle* h, int32_t B, int32_t space, const int32_
                             const double* coeff, const double* samp, int32_t samp_shared, int32_t* entangled,
                             void* stream);
 
+/*
+ * ---- Front end: KinodynamicSearch (neptune/src/kinodynamic_search.cpp), SURVEY.md section 8(f) #1 ----
+ *
+ * Replaces the one-time setters of KinodynamicSearch (setMaxValuesAndSamples :272-327, setXYZMinMaxAndRa
+ * :329-344, setBias :346, setGoalSize :360, setRunTime :356, constructor flags :29-138; call site
+ * neptune.cpp:88-97).  Bounds, v_max, a_max, T_span, num_pol, samples and the tether length come from
+ * nb_params.  Two fields replace non-deterministic state of the reference: max_expansions (pops of the open
+ * list allowed, for the wall-clock max_runtime_ of :1646) and the jerk-sample order passed per call.
+ */
+typedef struct nb_search_params
+{
+  int32_t num_samples;        /* a_star_samp_x (jerk samples per axis, <= 5) */
+  double j_max;
+  double voxel_size;          /* a_star_fraction_voxel_size */
+  double bias;                /* setBias (1.1 in neptune.cpp:97) */
+  double goal_size;           /* goal_radius */
+  int32_t enable_entangle_check;
+  int32_t use_not_reaching_soln;
+  int32_t max_nodes;          /* node_num_max_ (:370-371) */
+  int32_t max_expansions;     /* stands in for max_runtime_ */
+  int32_t ecap;               /* storage capacity of a search node's alphas list (semantic bound N+M) */
+} nb_search_params;
+
+int nb_search_configure(nb_handle* h, const nb_search_params* sp);
+
+/* Second argument of KinodynamicSearch::setStaticObstRep (:385-390): staticObsLongestDist [M][2]. Host pointer. */
+int nb_set_static_longest(nb_handle* h, const double* longest);
+
+/*
+ * One batch of front-end searches.  Replaces, per agent, KinodynamicSearch::setUp (:190-249) + run
+ * (:1629-1827) + getPwpOut_0tstart / getEntStateVector (:610-618)          [neptune.cpp:1453-1510].
+ * Hulls and samples are the group-shaped outputs of nb_hulls_batch (agents planning over the same
+ * windows share them): agent b reads group[b] (NULL: b), the slot of b itself and of agents with
+ * known[b][j] == 0 is empty.  The outputs coeff / n_int / esv are laid out exactly like
+ * nb_replan_args.coeff_init / n_int / esv_* so the back end can consume them in place.
+ */
+typedef struct nb_search_args
+{
+  int32_t B;
+  int32_t space;
+  const int32_t* agent_id;   /* [B] 1-based */
+  const double* init;        /* [B][6] px py vx vy ax ay of the start state A */
+  const double* goal;        /* [B][2] */
+  const double* coeffs_z;    /* [B][8][4] setInitZCoeffs (getInitialZPwp) */
+  int32_t n_groups;          /* G */
+  const int32_t* group;      /* [B] or NULL */
+  const double* hull_xy;     /* [G][N][8][NB_HULL_STRIDE][2] */
+  const int32_t* hull_cnt;   /* [G][N][8] */
+  const double* samp;        /* [G][N][num_pol][S+1][2] */
+  const uint8_t* known;      /* [B][N] */
+  nb_ent_state es;           /* entangle_state_A, [B] states, stride ent_cap */
+  const int32_t* bp_cnt;     /* [N] */
+  const double* bp_xy;       /* [N][bp_max][2] */
+  const uint8_t* comb;       /* [ns*ns] (comb_shared != 0) or [B][ns*ns]: order of the jerk samples, jx*ns+jy */
+  int32_t comb_shared;
+  /* outputs */
+  int32_t* status;           /* [B] 0 runtime reached, 1 goal reached, 2 open list empty (:1637-1639) */
+  int32_t* solved;           /* [B] return value of run() */
+  int32_t* n_int;            /* [B] pieces of pwp_out_ */
+  double* coeff;             /* [B][3][8][4] pwp_out_ */
+  nb_ent_state esv;          /* entStateVec: [B][9] states, stride ent_cap */
+  int32_t* stats;            /* [B][4] nodes used, pops, index of the best node, goal_occupied */
+  double* cost;              /* [B] g of the best node */
+} nb_search_args;
+
+int nb_search_batch(nb_handle* h, const nb_search_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,6 +105,44 @@ class EntArrays:
         return self.cnt, self.alpha, self.beta, self.bend, self.active
 
 
+class NbSearchParams(C.Structure):
+    _fields_ = [("num_samples", C.c_int32), ("j_max", C.c_double), ("voxel_size", C.c_double), ("bias", C.c_double),
+                ("goal_size", C.c_double), ("enable_entangle_check", C.c_int32), ("use_not_reaching_soln", C.c_int32),
+                ("max_nodes", C.c_int32), ("max_expansions", C.c_int32), ("ecap", C.c_int32)]
+
+
+class NbSearchArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("space", C.c_int32), ("agent_id", _P), ("init", _P), ("goal", _P), ("coeffs_z", _P),
+                ("n_groups", C.c_int32), ("group", _P), ("hull_xy", _P), ("hull_cnt", _P), ("samp", _P), ("known", _P),
+                ("es", NbEntState), ("bp_cnt", _P), ("bp_xy", _P), ("comb", _P), ("comb_shared", C.c_int32),
+                ("status", _P), ("solved", _P), ("n_int", _P), ("coeff", _P), ("esv", NbEntState), ("stats", _P),
+                ("cost", _P)]
+
+
+def make_search_params(par: Params) -> NbSearchParams:
+    sp = NbSearchParams()
+    sp.num_samples, sp.j_max, sp.voxel_size = par.a_star_samp_x, par.j_max, par.a_star_fraction_voxel_size
+    sp.bias, sp.goal_size = par.a_star_bias, par.goal_radius
+    sp.enable_entangle_check, sp.use_not_reaching_soln = int(par.enable_entangle_check), int(par.use_not_reaching_soln)
+    sp.max_nodes, sp.max_expansions, sp.ecap = par.search_max_nodes, par.search_max_expansions, par.search_ecap
+    return sp
+
+
+def host_search_args(sb, res) -> NbSearchArgs:
+    """nb_search_args over the host (numpy) buffers of a SearchBatch / SearchResult."""
+    a = NbSearchArgs()
+    a.B, a.space = sb.B, NB_HOST
+    a.agent_id, a.init, a.goal, a.coeffs_z = _np(sb.agent_id), _np(sb.init), _np(sb.goal), _np(sb.coeffs_z)
+    a.n_groups, a.group = sb.G, _np(sb.group)
+    a.hull_xy, a.hull_cnt, a.samp, a.known = _np(sb.hull_xy), _np(sb.hull_cnt), _np(sb.samp), _np(sb.known)
+    a.es.cnt, a.es.alpha, a.es.beta, a.es.bend, a.es.active = _np(sb.es_cnt), _np(sb.es_alpha), _np(sb.es_beta), _np(sb.es_bend), _np(sb.es_active)
+    a.bp_cnt, a.bp_xy, a.comb, a.comb_shared = _np(sb.bp_cnt), _np(sb.bp_xy), _np(sb.comb), int(sb.comb.ndim == 1)
+    a.status, a.solved, a.n_int, a.coeff = _np(res.status), _np(res.solved), _np(res.n_int), _np(res.coeff)
+    a.esv.cnt, a.esv.alpha, a.esv.beta, a.esv.bend, a.esv.active = _np(res.esv_cnt), _np(res.esv_alpha), _np(res.esv_beta), _np(res.esv_bend), _np(res.esv_active)
+    a.stats, a.cost = _np(res.stats), _np(res.cost)
+    return a
+
+
 _lib = None
 
 
@@ -125,6 +163,9 @@ def lib():
         _lib.nb_set_static.argtypes = [_P, _P, _P, _P]
         _lib.nb_replan_batch.argtypes = [_P, C.POINTER(NbReplanArgs), _P]
         _lib.nb_line_slots.argtypes = [_P, C.c_int]
+        _lib.nb_search_configure.argtypes = [_P, C.POINTER(NbSearchParams)]
+        _lib.nb_set_static_longest.argtypes = [_P, _P]
+        _lib.nb_search_batch.argtypes = [_P, C.POINTER(NbSearchArgs), _P]
     return _lib
 
 
@@ -180,6 +221,29 @@ class Solver:
         a = host_args(batch, res)
         _check(lib().nb_replan_batch(self._h, C.byref(a), _P(stream or 0)), "nb_replan_batch")
         return res
+
+    # ---- front end (K0)
+    def search_configure(self, par: Params | None = None) -> None:
+        """One-time setters of ``KinodynamicSearch`` (``neptune.cpp:88-97``)."""
+        sp = make_search_params(par or self.par)
+        _check(lib().nb_search_configure(self._h, C.byref(sp)), "nb_search_configure")
+
+    def set_static_longest(self, longest: np.ndarray) -> None:
+        """``staticObsLongestDist`` of ``setStaticObstRep``."""
+        if self.par.num_of_static_obst:
+            longest = np.ascontiguousarray(longest, np.float64)
+            _check(lib().nb_set_static_longest(self._h, _np(longest)), "nb_set_static_longest")
+
+    def search(self, sb, stream=None):
+        """``KinodynamicSearch::setUp`` + ``run`` for every agent of a SearchBatch, host buffers in and out."""
+        from .search import SearchResult
+        res = SearchResult.empty(sb)
+        a = host_search_args(sb, res)
+        _check(lib().nb_search_batch(self._h, C.byref(a), _P(stream or 0)), "nb_search_batch")
+        return res
+
+    def search_args(self, a: "NbSearchArgs", stream=None) -> None:
+        _check(lib().nb_search_batch(self._h, C.byref(a), _P(stream or 0)), "nb_search_batch")
 
     def replan_args(self, a: NbReplanArgs, stream=None) -> None:
         """Raw call with caller-built arguments (device pointers for the HBM-resident path)."""

@@ -14,6 +14,8 @@
 #include "nb_hull.cuh"
 #include "nb_lines.cuh"
 #include "nb_qp.cuh"
+#include "nb_search.cuh"
+#include "nb_search_launch.h"
 #include "nb_sep.cuh"
 #include "nb_tables.h"
 
@@ -70,6 +72,11 @@ struct nb_handle
   DevBuf in[16], out[8];
   // scratch
   DevBuf lines, line_ok, keep, cl, rows, err, ent_scratch;
+  // front-end search: configuration, staging and workspace
+  nb_search_params sp;
+  int sp_set = 0;
+  double* d_st_longest = nullptr;
+  DevBuf sin[20], sout[12], sw_meta, sw_kin, sw_alpha, sw_beta, sw_bend, sw_hash, sw_heap, sw_gh, sw_chi, sw_chd;
   int qp_smem_set = 0;
   int profiling = 0;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -503,6 +510,11 @@ extern "C" void nb_destroy(nb_handle* h)
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
   h->lines.release(), h->line_ok.release(), h->keep.release(), h->cl.release(), h->rows.release(), h->err.release(), h->ent_scratch.release();
+  cudaFree(h->d_st_longest);
+  for (auto& b : h->sin) b.release();
+  for (auto& b : h->sout) b.release();
+  h->sw_meta.release(), h->sw_kin.release(), h->sw_alpha.release(), h->sw_beta.release(), h->sw_bend.release();
+  h->sw_hash.release(), h->sw_heap.release(), h->sw_gh.release(), h->sw_chi.release(), h->sw_chd.release();
   delete h;
 }
 
@@ -1218,5 +1230,181 @@ extern "C" int nb_commit_compose_batch(nb_handle* h, int32_t B, int32_t space, c
                              collide, n_pieces, (int*)h->err.p);
   h->launches += 1;
   NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+// ------------------------------------------------------------------------------------------ K0 ABI (front end)
+extern "C" int nb_search_configure(nb_handle* h, const nb_search_params* sp)
+{
+  if (!h || !sp) return NB_ERR_ARG;
+  if (sp->num_samples < 2 || sp->num_samples * sp->num_samples > NB_SEARCH_MAXCHILD || sp->max_nodes < 64 ||
+      sp->max_expansions < 0 || sp->ecap < 1 || sp->ecap > 0x7fff || !(sp->voxel_size > 0) || !(sp->j_max > 0))
+  {
+    g_err = "nb_search_configure: unsupported parameters (2 <= num_samples <= 5, max_nodes >= 64, 1 <= ecap < 32768)";
+    return NB_ERR_ARG;
+  }
+  h->sp = *sp;
+  h->sp_set = 1;
+  return NB_OK;
+}
+
+extern "C" int nb_set_static_longest(nb_handle* h, const double* longest)
+{
+  if (!h) return NB_ERR_ARG;
+  const int M = h->par.num_static;
+  if (M == 0) return NB_OK;
+  if (!longest) return NB_ERR_ARG;
+  NB_CUDA(cudaSetDevice(h->device));
+  if (!h->d_st_longest) NB_CUDA(cudaMalloc(&h->d_st_longest, sizeof(double) * 2 * M));
+  NB_CUDA(cudaMemcpy(h->d_st_longest, longest, sizeof(double) * 2 * M, cudaMemcpyHostToDevice));
+  return NB_OK;
+}
+
+namespace
+{
+template <typename T>
+int sstage_in(nb_handle* h, int slot, int space, const T* src, size_t count, cudaStream_t st, const T** dst)
+{
+  if (space == NB_DEVICE || src == nullptr || count == 0)
+  {
+    *dst = src;
+    return NB_OK;
+  }
+  if (h->sin[slot].ensure(count * sizeof(T)))
+  {
+    g_err = "cudaMalloc failed while staging search inputs";
+    return NB_ERR_CUDA;
+  }
+  NB_CUDA(cudaMemcpyAsync(h->sin[slot].p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+  *dst = (const T*)h->sin[slot].p;
+  return NB_OK;
+}
+template <typename T>
+int sstage_out(nb_handle* h, int slot, int space, T* user, size_t count, T** dst)
+{
+  if (space == NB_DEVICE)
+  {
+    *dst = user;
+    return NB_OK;
+  }
+  if (h->sout[slot].ensure(count * sizeof(T)))
+  {
+    g_err = "cudaMalloc failed while staging search outputs";
+    return NB_ERR_CUDA;
+  }
+  *dst = (T*)h->sout[slot].p;
+  return NB_OK;
+}
+}  // namespace
+
+extern "C" int nb_search_batch(nb_handle* h, const nb_search_args* u, void* stream)
+{
+  if (!h || !u || u->B < 0) return NB_ERR_ARG;
+  if (u->B == 0) return NB_OK;
+  if (!h->sp_set)
+  {
+    g_err = "nb_search_batch before nb_search_configure";
+    return NB_ERR_ARG;
+  }
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const nb_search_params& sp = h->sp;
+  const int B = u->B, N = h->par.num_agents, M = h->par.num_static, NA = N + M, S = h->par.samples, np = h->par.num_pol;
+  const int cap = h->par.ent_cap, space = u->space, G = u->group ? u->n_groups : B;
+  if (M > 0 && (!h->d_strep || !h->d_st_longest || !h->d_st_xy))
+  {
+    g_err = "nb_search_batch with static obstacles needs nb_set_static(strep) and nb_set_static_longest first";
+    return NB_ERR_ARG;
+  }
+  NbSearchArgs a;
+  memset(&a, 0, sizeof(a));
+  NbSearchPar& p = a.p;
+  nb_search_fill_par(h->par, sp, h->cs, &p);
+  int rc;
+  if ((rc = sstage_in(h, 0, space, u->agent_id, (size_t)B, st, &a.agent_id))) return rc;
+  if ((rc = sstage_in(h, 1, space, u->init, (size_t)B * 6, st, &a.init))) return rc;
+  if ((rc = sstage_in(h, 2, space, u->goal, (size_t)B * 2, st, &a.goal))) return rc;
+  if ((rc = sstage_in(h, 3, space, u->coeffs_z, (size_t)B * NB_NPOL * 4, st, &a.coeffs_z))) return rc;
+  if ((rc = sstage_in(h, 4, space, u->group, (size_t)B, st, &a.group))) return rc;
+  if ((rc = sstage_in(h, 5, space, u->hull_xy, (size_t)G * N * NB_NPOL * NB_HULL_STRIDE * 2, st, &a.hull_xy))) return rc;
+  if ((rc = sstage_in(h, 6, space, u->hull_cnt, (size_t)G * N * NB_NPOL, st, &a.hull_cnt))) return rc;
+  if ((rc = sstage_in(h, 7, space, u->samp, (size_t)G * N * np * (S + 1) * 2, st, &a.samp))) return rc;
+  if ((rc = sstage_in(h, 8, space, u->known, (size_t)B * N, st, &a.known))) return rc;
+  if ((rc = sstage_in(h, 9, space, (const int32_t*)u->es.cnt, (size_t)B * 2, st, (const int32_t**)&a.es.cnt))) return rc;
+  if ((rc = sstage_in(h, 10, space, (const int32_t*)u->es.alpha, (size_t)B * cap * 2, st, (const int32_t**)&a.es.alpha))) return rc;
+  if ((rc = sstage_in(h, 11, space, (const double*)u->es.beta, (size_t)B * cap, st, (const double**)&a.es.beta))) return rc;
+  if ((rc = sstage_in(h, 12, space, (const int32_t*)u->es.bend, (size_t)B * cap, st, (const int32_t**)&a.es.bend))) return rc;
+  if ((rc = sstage_in(h, 13, space, (const int32_t*)u->es.active, (size_t)B * NA, st, (const int32_t**)&a.es.active))) return rc;
+  if ((rc = sstage_in(h, 14, space, u->bp_cnt, (size_t)N, st, &a.bp_cnt))) return rc;
+  if ((rc = sstage_in(h, 15, space, u->bp_xy, (size_t)N * h->par.bp_max * 2, st, &a.bp_xy))) return rc;
+  if ((rc = sstage_in(h, 16, space, u->comb, (size_t)(u->comb_shared ? 1 : B) * p.nchild, st, &a.comb))) return rc;
+  a.comb_shared = u->comb_shared;
+  a.st_ptr = h->d_st_ptr, a.st_xy = h->d_st_xy, a.strep = h->d_strep, a.st_longest = h->d_st_longest, a.pb = h->d_pb;
+  const size_t ns9 = (size_t)B * 9;
+  if ((rc = sstage_out(h, 0, space, u->status, (size_t)B, &a.status))) return rc;
+  if ((rc = sstage_out(h, 1, space, u->solved, (size_t)B, &a.solved))) return rc;
+  if ((rc = sstage_out(h, 2, space, u->n_int, (size_t)B, &a.n_int))) return rc;
+  if ((rc = sstage_out(h, 3, space, u->coeff, (size_t)B * 3 * NB_NPOL * 4, &a.coeff))) return rc;
+  if ((rc = sstage_out(h, 4, space, u->esv.cnt, ns9 * 2, &a.esv.cnt))) return rc;
+  if ((rc = sstage_out(h, 5, space, u->esv.alpha, ns9 * cap * 2, &a.esv.alpha))) return rc;
+  if ((rc = sstage_out(h, 6, space, u->esv.beta, ns9 * cap, &a.esv.beta))) return rc;
+  if ((rc = sstage_out(h, 7, space, u->esv.bend, ns9 * cap, &a.esv.bend))) return rc;
+  if ((rc = sstage_out(h, 8, space, u->esv.active, ns9 * NA, &a.esv.active))) return rc;
+  if ((rc = sstage_out(h, 9, space, u->stats, (size_t)B * 4, &a.stats))) return rc;
+  if ((rc = sstage_out(h, 10, space, u->cost, (size_t)B, &a.cost))) return rc;
+  // workspace
+  const size_t mn = (size_t)sp.max_nodes;
+  const size_t ch_stride = (size_t)nb_search_ch_stride(p);
+  bool bad = false;
+  bad |= h->sw_meta.ensure(B * mn * sizeof(NbInt4)) != 0;
+  bad |= h->sw_kin.ensure(B * mn * NB_SEARCH_KIN * sizeof(double)) != 0;
+  bad |= h->sw_alpha.ensure(B * mn * p.ecap * 2 * sizeof(int)) != 0;
+  bad |= h->sw_beta.ensure(B * mn * p.ecap * sizeof(double)) != 0;
+  bad |= h->sw_bend.ensure(B * mn * p.ecap * sizeof(int)) != 0;
+  bad |= h->sw_hash.ensure((size_t)B * p.hcap * sizeof(NbInt4)) != 0;
+  // global homes of everything the kernel tries to keep in shared memory (used when it does not fit)
+  bad |= h->sw_heap.ensure(B * mn * sizeof(int)) != 0;
+  bad |= h->sw_gh.ensure(B * mn * 2 * sizeof(double)) != 0;
+  bad |= h->sw_chi.ensure((size_t)B * (p.nchild * ch_stride + NA) * sizeof(int)) != 0;
+  bad |= h->sw_chd.ensure((size_t)B * p.nchild * p.ecap * sizeof(double)) != 0;
+  if (bad)
+  {
+    g_err = "cudaMalloc failed for the search workspace";
+    return NB_ERR_CUDA;
+  }
+  a.nd_meta = (NbInt4*)h->sw_meta.p, a.nd_kin = (double*)h->sw_kin.p, a.nd_alpha = (int*)h->sw_alpha.p;
+  a.nd_beta = (double*)h->sw_beta.p, a.nd_bend = (int*)h->sw_bend.p, a.hash = (NbInt4*)h->sw_hash.p;
+  a.heap_g = (int*)h->sw_heap.p, a.gh_g = (double*)h->sw_gh.p, a.ch_int = (int*)h->sw_chi.p, a.ch_dbl = (double*)h->sw_chd.p;
+  a.err = (int*)h->err.p;
+  const char* etxt = nullptr;
+  if (nb_search_launch(&a, B, stream, &etxt))
+  {
+    g_err = std::string("k_search launch: ") + (etxt ? etxt : "?");
+    return NB_ERR_CUDA;
+  }
+  h->launches += 1;
+  if (space == NB_HOST)
+  {
+    NB_CUDA(cudaMemcpyAsync(u->status, a.status, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(u->solved, a.solved, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(u->n_int, a.n_int, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(u->coeff, a.coeff, (size_t)B * 96 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(u->esv.cnt, a.esv.cnt, ns9 * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(u->esv.alpha, a.esv.alpha, ns9 * cap * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(u->esv.beta, a.esv.beta, ns9 * cap * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(u->esv.bend, a.esv.bend, ns9 * cap * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(u->esv.active, a.esv.active, ns9 * NA * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(u->stats, a.stats, (size_t)B * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(u->cost, a.cost, (size_t)B * sizeof(double), cudaMemcpyDeviceToHost, st));
+    int err = 0;
+    NB_CUDA(cudaMemcpyAsync(&err, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaStreamSynchronize(st));
+    if (err)
+    {
+      NB_CUDA(cudaMemsetAsync(h->err.p, 0, sizeof(int), st));
+      g_err = "front-end search: a node's alphas list exceeded search ecap / ent_cap";
+      return NB_ERR_CAPACITY;
+    }
+  }
   return NB_OK;
 }

@@ -1,0 +1,938 @@
+// nb_search.cuh -- K0: the front end of a replan, KinodynamicSearch (reference
+// neptune/src/kinodynamic_search.cpp), one CTA per planning agent.  SURVEY.md section 8(f) #1.
+//
+// Replaces
+//   KinodynamicSearch::setUp (entangle form)                   kinodynamic_search.cpp:190-249
+//   KinodynamicSearch::run                                     :1629-1827
+//   KinodynamicSearch::expandAndAddToQueue (root / node)       :1240-1385 / :1045-1228
+//   KinodynamicSearch::entanglesWithOtherAgents                :805-895
+//   eu::getTetherLength, eu::getBendPt2dwIdx                   entangle_utils.cpp:1724-1743, :1681-1707
+//   KinodynamicSearch::collidesWithObstacles2dSolve            :1514-1580
+//   KinodynamicSearch::collidesWithBases2d                     :1583-1627
+//   recoverPwpOut, recoverEntStateVector                       :521-553, :582-603
+//   getIz, power_int, CompareCost                              :2006-2031, kinodynamic_search.hpp:163-179
+//
+// Mapping onto the SM.  A best-first search is a sequential chain of pops, but every pop fans out:
+//   * the popped node is tested against the N-1 window hulls, the M static obstacles and the N bases
+//     (GJK, one thread per obstacle, __syncthreads_or);
+//   * its 25 jerk children are evaluated by 25 warps at once: each warp runs the S-step entanglement
+//     chain of its child with the lanes spread over the N+M tethers (ballot-ordered appends, the
+//     list automaton on lane 0), then the tether-length test and the voxel key;
+//   * one thread then replays the reference's sequential loop over the children in all_combinations_
+//     order -- hash lookup, the "better node" replacement rule with its ran_trigger parity, node
+//     allocation, push_heap -- so node numbering, heap layout and therefore the pop order are identical
+//     to a sequential run.
+// The open list (heap of node ids) and the (g, h) keys its comparisons read live in shared memory when
+// max_nodes * 20 B fits (it does for the defaults), otherwise in global scratch: the sift loops then run at
+// shared-memory latency.  Node payloads (kinematics, entanglement lists) stay in global memory; a node's
+// active_cases array is not stored: active = active_A - count_A(id) + count_node(id) because every change of
+// active_cases is paired with an append/erase of alphas (entangle_utils.cpp:1402-1534).
+//
+// std::priority_queue is restated as libstdc++'s __push_heap / __adjust_heap (CompareCost is not a strict
+// weak order, so the pop order depends on the sift algorithm).  Compiled with --fmad=false: every FP64
+// result feeds a discrete decision (voxel keys, cost ties, admissibility tests), so products and sums are
+// rounded separately, as in the CPU build of the reference.
+//
+// Non-deterministic reference state is injected: the order of the jerk samples (comb) and the number of
+// pops that stands in for the wall-clock budget (max_exp).
+#pragma once
+#include <float.h>
+
+#include "../../include/neptune_b200.h"
+#include "nb_common.cuh"
+#include "nb_entangle.cuh"
+#include "nb_hull.cuh"
+
+#define NB_SEARCH_MAXCHILD 25
+#define NB_SEARCH_KIN 14  // end[6], coeff_x[4], coeff_y[4]
+
+struct NbInt4
+{
+  int x, y, z, w;
+};
+
+struct NbSearchPar
+{
+  int N, M, num_pol, S, ns, nchild;
+  double T, x_min, x_max, y_min, y_max, v_max, a_max, j_max, voxel, bias, goal_size, tether;
+  int enable_entangle, use_not_reaching, max_nodes, max_exp, ecap, out_cap, es_cap, bp_max, hcap, tcap;
+  double Ainv[16], V[9];
+};
+
+struct NbSearchArgs
+{
+  NbSearchPar p;
+  // inputs
+  const int* agent_id;
+  const double* init;      // [B][6]
+  const double* goal;      // [B][2]
+  const double* coeffs_z;  // [B][8][4]
+  const int* group;        // [B] or null
+  const double* hull_xy;   // [G][N][8][24][2]
+  const int* hull_cnt;     // [G][N][8]
+  const double* samp;      // [G][N][num_pol][S+1][2]
+  const uint8_t* known;    // [B][N]
+  const int64_t* st_ptr;
+  const double* st_xy;
+  const double* strep;
+  const double* st_longest;
+  const double* pb;
+  const int* bp_cnt;
+  const double* bp_xy;
+  nb_ent_state es;  // entangle_state_A, stride es_cap
+  const uint8_t* comb;
+  int comb_shared;
+  // outputs
+  int* status;
+  int* solved;
+  int* n_int;
+  double* coeff;     // [B][3][8][4]
+  nb_ent_state esv;  // [B][9], stride out_cap
+  int* stats;        // [B][4]
+  double* cost;      // [B]
+  // workspace, per agent
+  NbInt4* nd_meta;   // [max_nodes]: prev, index, state, n_alpha | n_bend << 16
+  double* nd_kin;    // [max_nodes][14]
+  int* nd_alpha;     // [max_nodes][ecap][2]
+  double* nd_beta;   // [max_nodes][ecap]
+  int* nd_bend;      // [max_nodes][ecap]
+  NbInt4* hash;      // [hcap]: ix, iy, iz, id + 1
+  int* heap_g;       // [max_nodes] when the open list does not fit in shared memory
+  double* gh_g;      // [max_nodes][2]
+  int* ch_int;       // [nchild][2 tcap + 2 NA + 3 ecap] + [NA] parent active
+  double* ch_dbl;    // [nchild][ecap]
+  int* err;
+};
+
+// parameters of one launch from the ABI structs (host side; shared by nb_capi.cu and the test emulation)
+inline void nb_search_fill_par(const nb_params& par, const nb_search_params& sp, const NbConsts& cs, NbSearchPar* p)
+{
+  const int NA = par.num_agents + par.num_static;
+  p->N = par.num_agents, p->M = par.num_static, p->num_pol = par.num_pol, p->S = par.samples;
+  p->ns = sp.num_samples, p->nchild = sp.num_samples * sp.num_samples;
+  p->T = par.T_span;
+  p->x_min = par.lim_min[0], p->x_max = par.lim_max[0], p->y_min = par.lim_min[1], p->y_max = par.lim_max[1];
+  p->v_max = par.v_max, p->a_max = par.a_max, p->j_max = sp.j_max, p->voxel = sp.voxel_size, p->bias = sp.bias;
+  p->goal_size = sp.goal_size, p->tether = par.tether_length;
+  p->enable_entangle = sp.enable_entangle_check, p->use_not_reaching = sp.use_not_reaching_soln;
+  p->max_nodes = sp.max_nodes, p->max_exp = sp.max_expansions, p->ecap = sp.ecap;
+  p->out_cap = par.ent_cap, p->es_cap = par.ent_cap, p->bp_max = par.bp_max;
+  p->hcap = 64;
+  while (p->hcap < 2 * sp.max_nodes) p->hcap *= 2;
+  p->tcap = NA + 32;
+  for (int k = 0; k < 16; k++) p->Ainv[k] = cs.Ainv[k];
+  for (int k = 0; k < 9; k++) p->V[k] = cs.V[k];
+}
+
+// shared-memory arena: per-agent working sets are placed in shared memory in priority order while they fit,
+// and stay in global memory (same code, generic pointers) when they do not (large N + M)
+struct NbArena
+{
+  unsigned char* p;
+  size_t left;
+  NB_HD void* take(size_t bytes)
+  {
+    bytes = (bytes + 15) & ~(size_t)15;
+    if (!p || bytes > left) return nullptr;
+    void* r = p;
+    p += bytes;
+    left -= bytes;
+    return r;
+  }
+};
+
+// ints of scratch per child: toadd [2 tcap] | (id, old active) pairs [2 tcap] | active [NA] | alpha [2 ecap] | bend [ecap]
+NB_HD int nb_search_ch_stride(const NbSearchPar& p) { return 4 * p.tcap + (p.N + p.M) + 3 * p.ecap; }
+
+// one evaluated child of the node being expanded
+struct NbChildRec
+{
+  int valid, ix, iy, iz, n_alpha, n_bend, accept_id, found, f_state, f_index;
+  double kin[NB_SEARCH_KIN], g, h;
+};
+
+struct NbSearchCtl
+{
+  int done, status, cur, best, closest, n_used, heap_n, pops, ran_trigger, goal_occupied, first_new, overflow;
+  double smallest;
+  int flag[NB_SEARCH_MAXCHILD][4];
+};
+
+struct NbSearchShared
+{
+  NbSearchCtl ctl;
+  NbChildRec rec[NB_SEARCH_MAXCHILD];
+};
+
+// per-agent view of the arguments
+struct NbSearchCtx
+{
+  const NbSearchPar* p;
+  int b, self, NA;
+  double init[6], goal[2];
+  const double* hull_xy;
+  const int* hull_cnt;
+  const double* samp;
+  const uint8_t* known;
+  const uint8_t* comb;
+  const int64_t* st_ptr;
+  const double* st_xy;
+  const double* st_longest;
+  NbEntCtx ecx;
+  // entangle_state_A
+  int a_na, a_nb;
+  const int* a_alpha;
+  const double* a_beta;
+  const int* a_bend;
+  const int* a_active;
+  // pool
+  NbInt4* meta;
+  double* kin;
+  int* alpha;
+  double* beta;
+  int* bend;
+  NbInt4* hash;
+  int* heap;
+  double* gh;
+  int* ch_int;
+  double* ch_dbl;
+  int* par_act;
+  int ch_stride;
+};
+
+NB_HD double nb_norm2(double x, double y) { return sqrt(x * x + y * y); }
+
+NB_HD int nb_hull_count(const NbSearchCtx& c, int o, int i)
+{
+  if (o == c.self || !c.known[o]) return 0;
+  return c.hull_cnt[o * NB_NPOL + i];
+}
+
+// CompareCost (kinodynamic_search.hpp:163-179): true when l has lower priority than r
+NB_HD bool nb_cmp_cost(const NbSearchCtx& c, int l, int r)
+{
+  const double cl = c.gh[2 * l] + c.p->bias * c.gh[2 * l + 1];
+  const double cr = c.gh[2 * r] + c.p->bias * c.gh[2 * r + 1];
+  if (fabs(cl - cr) < 1e-5) return c.gh[2 * l + 1] > c.gh[2 * r + 1];
+  return cl > cr;
+}
+
+// libstdc++ std::__push_heap
+NB_HD void nb_heap_push_at(const NbSearchCtx& c, int hole, int top, int value)
+{
+  int parent = (hole - 1) / 2;
+  while (hole > top && nb_cmp_cost(c, c.heap[parent], value))
+  {
+    c.heap[hole] = c.heap[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  c.heap[hole] = value;
+}
+
+// top() + pop(): std::pop_heap (= __pop_heap, __adjust_heap) + pop_back
+NB_HD int nb_heap_pop(const NbSearchCtx& c, int& heap_n)
+{
+  const int top = c.heap[0];
+  if (heap_n > 1)
+  {
+    const int last = heap_n - 1;
+    const int value = c.heap[last];
+    c.heap[last] = c.heap[0];
+    const int len = last;
+    int hole = 0, child = 0;
+    while (child < (len - 1) / 2)
+    {
+      child = 2 * (child + 1);
+      if (nb_cmp_cost(c, c.heap[child], c.heap[child - 1])) child--;
+      c.heap[hole] = c.heap[child];
+      hole = child;
+    }
+    if ((len & 1) == 0 && child == (len - 2) / 2)
+    {
+      child = 2 * (child + 1);
+      c.heap[hole] = c.heap[child - 1];
+      hole = child - 1;
+    }
+    nb_heap_push_at(c, hole, 0, value);
+  }
+  heap_n--;
+  return top;
+}
+
+NB_HD uint32_t nb_hash3(int ix, int iy, int iz)
+{
+  uint32_t h = (uint32_t)ix * 0x9E3779B1u;
+  h ^= (uint32_t)iy * 0x85EBCA77u + (h << 6) + (h >> 2);
+  h ^= (uint32_t)iz * 0xC2B2AE3Du + (h << 6) + (h >> 2);
+  return h;
+}
+
+NB_HD int nb_hash_find(const NbSearchCtx& c, int ix, int iy, int iz)
+{
+  const uint32_t mask = (uint32_t)(c.p->hcap - 1);
+  uint32_t q = nb_hash3(ix, iy, iz) & mask;
+  for (;;)
+  {
+    const NbInt4 e = c.hash[q];
+    if (e.w == 0) return -1;
+    if (e.x == ix && e.y == iy && e.z == iz) return e.w - 1;
+    q = (q + 1) & mask;
+  }
+}
+
+// unordered_map::insert keeps an existing mapping
+NB_HD void nb_hash_insert(const NbSearchCtx& c, int ix, int iy, int iz, int id)
+{
+  const uint32_t mask = (uint32_t)(c.p->hcap - 1);
+  uint32_t q = nb_hash3(ix, iy, iz) & mask;
+  for (;;)
+  {
+    const NbInt4 e = c.hash[q];
+    if (e.w == 0)
+    {
+      NbInt4 n;
+      n.x = ix, n.y = iy, n.z = iz, n.w = id + 1;
+      c.hash[q] = n;
+      return;
+    }
+    if (e.x == ix && e.y == iy && e.z == iz) return;
+    q = (q + 1) & mask;
+  }
+}
+
+// KinodynamicSearch::power_int (:2016-2031)
+NB_HD uint32_t nb_power_int(uint32_t base, uint32_t exponent)
+{
+  if (exponent == 0) return 1;
+  if (base < 2) return base;
+  uint32_t result = 1;
+  for (uint32_t term = base;; term = term * term)
+  {
+    if (exponent % 2 != 0) result *= term;
+    exponent /= 2;
+    if (exponent == 0) break;
+  }
+  return result;
+}
+
+// unsigned int ix = round(x / voxel), then Eigen::Vector2i(ix, iy): two's-complement wrap
+NB_HD int nb_voxel_index(double x, double voxel) { return (int)(uint32_t)(long long)round(x / voxel); }
+
+// eu::getTetherLength (entangle_utils.cpp:1724-1743)
+NB_HD double nb_tether_length(const NbSearchCtx& c, const NbEntState& es, const double* pk1)
+{
+  const int N = c.ecx.N;
+  double length = 0.0;
+  double prev[2] = { c.ecx.pb[2 * c.self], c.ecx.pb[2 * c.self + 1] };
+  for (int i = 0; i < es.n_bend; i++)
+  {
+    const int q = es.bend[i];
+    const int id = es.alpha[2 * q], cs = es.alpha[2 * q + 1];
+    double bp[2], comp = 0.0;
+    if (id <= N)
+      bp[0] = c.ecx.pb[2 * (id - 1)], bp[1] = c.ecx.pb[2 * (id - 1) + 1];
+    else
+    {
+      bp[0] = c.ecx.strep[4 * (id - N - 1) + 2 * cs], bp[1] = c.ecx.strep[4 * (id - N - 1) + 2 * cs + 1];
+      comp = c.st_longest[2 * (id - N - 1) + cs];
+    }
+    length += nb_norm2(bp[0] - prev[0], bp[1] - prev[1]) + 2 * comp;
+    prev[0] = bp[0], prev[1] = bp[1];
+  }
+  length += nb_norm2(pk1[0] - prev[0], pk1[1] - prev[1]);
+  return length;
+}
+
+// KinodynamicSearch::entanglesWithOtherAgents (:805-895) for one child, group-cooperative.
+// es works on the child's scratch lists / active array.  Returns 1 entangles, 0 fine, -1 storage overflow.
+template <int NL>
+NB_HD int nb_search_entangles(const Group<NL>& g, const NbSearchCtx& c, NbEntState& es, const double* kin, int index,
+                              int* toadd, int* act_old, int* flag, double* arc_length)
+{
+  const NbSearchPar& p = *c.p;
+  const int N = p.N, NA = c.NA, S = p.S, num_pol = p.num_pol;
+  const double* cx = kin + 6;
+  const double* cy = kin + 10;
+  double pk[2] = { cx[3], cy[3] }, pk1[2] = { cx[3], cy[3] };
+  double arc = 0.0;
+  const int stride = num_pol * (S + 1) * 2;
+  for (int j = 1; j <= S; j++)
+  {
+    if (j < S)
+    {
+      const double t = p.T * j / S;
+      const double t3 = t * t * t, t2 = t * t;
+      pk1[0] = cx[0] * t3 + cx[1] * t2 + cx[2] * t + cx[3];
+      pk1[1] = cy[0] * t3 + cy[1] * t2 + cy[2] * t + cy[3];
+    }
+    else
+      pk1[0] = kin[0], pk1[1] = kin[1];
+    arc += nb_norm2(pk1[0] - pk[0], pk1[1] - pk[1]);
+    const double *pik, *pik1;
+    if (index > num_pol)
+    {
+      pik = c.samp + ((size_t)(num_pol - 1) * (S + 1) + S) * 2;
+      pik1 = pik;
+    }
+    else
+    {
+      pik = c.samp + ((size_t)(index - 1) * (S + 1) + (j - 1)) * 2;
+      pik1 = c.samp + ((size_t)(index - 1) * (S + 1) + j) * 2;
+    }
+    const int nadd = nb_collect_toadd<NL>(g, c.ecx, pk, nullptr, pk1, pik, stride, pik1, stride, c.known, toadd, p.tcap);
+    if (nadd < 0) return 1;  // more crossings than tcap >= N+M: over the list bound of :844-848 in any case
+    if (g.lane == 0)
+    {
+      int r = 0;
+      if (es.n_alpha + nadd > NA)
+        r = 1;
+      else
+      {
+        // active_cases_old (:813, :880) is only compared where active_cases can have grown, i.e. at the ids of
+        // alphasToAdd: remember (id, value before) for those instead of copying the whole array every step
+        for (int i = 0; i < nadd; i++) act_old[2 * i] = toadd[2 * i], act_old[2 * i + 1] = es.active[toadd[2 * i] - 1];
+        if (nb_add_alpha_beta(toadd, nadd, es, pk, c.ecx))
+          r = -1;
+        else
+        {
+          for (int i = 0; i < nadd; i++)
+          {
+            const int a = act_old[2 * i] - 1, was = act_old[2 * i + 1];
+            if (a >= N) continue;
+            if (was < 2 && es.active[a] >= 2) r = 1;
+            if (was >= 2 && es.active[a] > was) r = 1;
+          }
+          if (r == 0) nb_update_bend_pts(es, pk1, c.ecx);
+        }
+      }
+      flag[0] = r;
+      flag[1] = es.n_alpha;
+      flag[2] = es.n_bend;
+    }
+    g.sync();
+    const int r = flag[0];
+    es.n_alpha = flag[1];
+    es.n_bend = flag[2];
+    g.sync();
+    if (r != 0) return r;
+    pk[0] = pk1[0], pk[1] = pk1[1];
+  }
+  *arc_length = arc;
+  if (nb_tether_length(c, es, pk1) > p.tether) return 1;  // :884-891
+  return 0;
+}
+
+// kinematics and admissibility of one jerk sample (:1071-1155 node form, :1260-1339 root form)
+NB_HD bool nb_search_primitive(const NbSearchCtx& c, const double* ist, int comb, bool root, double* kin, double* Q)
+{
+  const NbSearchPar& p = *c.p;
+  const double tau = p.T, j_max = p.j_max, j_min = -p.j_max, a_max = p.a_max, a_min = -p.a_max;
+  const double v_max = p.v_max, v_min = -p.v_max;
+  const double delta_x = (j_max - j_min) / (p.ns - 1);
+  const int jx = comb / p.ns, jy = comb % p.ns;
+  const double ji[2] = { j_min + jx * delta_x, j_min + jy * delta_x };
+  double* e = kin;
+  for (int d = 0; d < 2; d++)
+  {
+    e[d] = ist[d] + ist[2 + d] * tau + ist[4 + d] * tau * tau / 2 + ji[d] * tau * tau * tau / 6;
+    e[2 + d] = ist[2 + d] + ist[4 + d] * tau + ji[d] * tau * tau / 2;
+    e[4 + d] = ist[4 + d] + ji[d] * tau;
+  }
+  double n2 = 0;
+  for (int k = 0; k < 6; k++) n2 += (e[k] - ist[k]) * (e[k] - ist[k]);
+  if (sqrt(n2) < 0.00001) return false;
+  if (e[5] > a_max || e[5] < a_min || e[4] > a_max || e[4] < a_min) return false;
+  double* cx = kin + 6;
+  double* cy = kin + 10;
+  cx[0] = ji[0] / 6, cx[1] = ist[4] / 2, cx[2] = ist[2], cx[3] = ist[0];
+  cy[0] = ji[1] / 6, cy[1] = ist[5] / 2, cy[2] = ist[3], cy[3] = ist[1];
+  for (int i = 0; i < 4; i++)
+  {
+    double qx = 0, qy = 0;
+    for (int k = 0; k < 4; k++) qx += cx[k] * p.Ainv[k * 4 + i], qy += cy[k] * p.Ainv[k * 4 + i];
+    Q[i] = qx, Q[4 + i] = qy;
+  }
+  const double bx = c.ecx.pb[2 * c.self], by = c.ecx.pb[2 * c.self + 1];
+  for (int i = 0; i < 4; i++)
+  {
+    if (Q[i] < p.x_min || Q[i] > p.x_max || Q[4 + i] < p.y_min || Q[4 + i] > p.y_max ||
+        nb_norm2(Q[i] - bx, Q[4 + i] - by) > p.tether)
+      return false;
+  }
+  if (!root)
+  {
+    for (int i = 0; i < 3; i++)
+    {
+      double vx = 0, vy = 0;
+      for (int k = 0; k < 3; k++) vx += cx[k] * p.V[k * 3 + i], vy += cy[k] * p.V[k * 3 + i];
+      if (vx < v_min || vx > v_max || vy < v_min || vy > v_max) return false;
+    }
+  }
+  if (e[4] > 0 && e[2] - 0.5 * e[4] * e[4] / j_min > v_max) return false;
+  else if (e[4] < 0 && e[2] - 0.5 * e[4] * e[4] / j_max < v_min) return false;
+  if (e[5] > 0 && e[3] - 0.5 * e[5] * e[5] / j_min > v_max) return false;
+  else if (e[5] < 0 && e[3] - 0.5 * e[5] * e[5] / j_max < v_min) return false;
+  return true;
+}
+
+// position control points of a node from its coefficients (Q = P * A_rest_pos_basis_inverse_, :1108)
+NB_HD void nb_search_ctrl(const NbSearchPar& p, const double* kin, double* cps /*[4][2]*/)
+{
+  const double* cx = kin + 6;
+  const double* cy = kin + 10;
+  for (int i = 0; i < 4; i++)
+  {
+    double qx = 0, qy = 0;
+    for (int k = 0; k < 4; k++) qx += cx[k] * p.Ainv[k * 4 + i], qy += cy[k] * p.Ainv[k * 4 + i];
+    cps[2 * i] = qx, cps[2 * i + 1] = qy;
+  }
+}
+
+// child c of the node `cur` (cur < 0: root), evaluated by one group; result in rec
+template <int NL>
+NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchShared* sh, int cur, int ch, const double* ist,
+                           int par_index, double par_g, const int* par_alpha, const double* par_beta, const int* par_bend,
+                           int par_na, int par_nb)
+{
+  const NbSearchPar& p = *c.p;
+  NbChildRec& rec = sh->rec[ch];
+  if (g.lane == 0) rec.valid = 0, rec.accept_id = -1;
+  double kin[NB_SEARCH_KIN], Q[8];
+  const bool root = cur < 0;
+  if (!nb_search_primitive(c, ist, c.comb[ch], root, kin, Q)) return;
+  const int index = par_index + 1;
+  int* ci = c.ch_int + (size_t)ch * c.ch_stride;
+  int* toadd = ci;
+  int* act_old = ci + 2 * p.tcap;
+  int* act = act_old + 2 * p.tcap;
+  NbEntState es;
+  es.alpha = act + c.NA;
+  es.bend = es.alpha + 2 * p.ecap;
+  es.beta = c.ch_dbl + (size_t)ch * p.ecap;
+  es.active = act;
+  es.n_alpha = par_na, es.n_bend = par_nb;
+  for (int q = g.lane; q < par_na; q += NL)
+  {
+    es.alpha[2 * q] = par_alpha[2 * q], es.alpha[2 * q + 1] = par_alpha[2 * q + 1];
+    es.beta[q] = par_beta[q];
+  }
+  for (int q = g.lane; q < par_nb; q += NL) es.bend[q] = par_bend[q];
+  for (int q = g.lane; q < c.NA; q += NL) act[q] = c.par_act[q];
+  g.sync();
+  double arc = 0.0;
+  if (p.enable_entangle)
+  {
+    const int r = nb_search_entangles<NL>(g, c, es, kin, index, toadd, act_old, sh->ctl.flag[ch], &arc);
+    if (r < 0 && g.lane == 0) sh->ctl.overflow = 1;
+    if (r != 0) return;
+  }
+  else
+    arc = nb_norm2(kin[0] - ist[0], kin[1] - ist[1]);
+  if (g.lane == 0)
+  {
+    uint32_t iz = 0;  // getIz (:2006-2014)
+    for (int i = 0; i < es.n_alpha; i++) iz += (uint32_t)(i + 1) * nb_power_int((uint32_t)es.alpha[2 * i], (uint32_t)es.alpha[2 * i + 1]);
+    rec.iz = (int)iz;
+    rec.ix = nb_voxel_index(kin[0], p.voxel);
+    rec.iy = nb_voxel_index(kin[1], p.voxel);
+    rec.n_alpha = es.n_alpha, rec.n_bend = es.n_bend;
+    for (int k = 0; k < NB_SEARCH_KIN; k++) rec.kin[k] = kin[k];
+    rec.g = par_g + arc;
+    rec.h = nb_norm2(kin[0] - c.goal[0], kin[1] - c.goal[1]) + 0.3 * (double)es.n_alpha + 1.0 * (double)es.n_bend;
+    // node-map lookup against the map as it is BEFORE this expansion (all children in parallel); the
+    // sequential pass adds the siblings accepted ahead of this child
+    rec.found = root ? -1 : nb_hash_find(c, rec.ix, rec.iy, rec.iz);
+    if (rec.found >= 0)
+    {
+      const NbInt4 m = c.meta[rec.found];
+      rec.f_state = m.z, rec.f_index = m.y;
+    }
+    rec.valid = 1;
+  }
+}
+
+// the sequential half of expandAndAddToQueue: children in all_combinations_ order (one thread)
+NB_HD void nb_search_resolve(const NbSearchCtx& c, NbSearchShared* sh, int cur, int par_index)
+{
+  const NbSearchPar& p = *c.p;
+  NbSearchCtl& ctl = sh->ctl;
+  const bool root = cur < 0;
+  ctl.first_new = ctl.n_used;
+  for (int ch = 0; ch < p.nchild; ch++)
+  {
+    if (!root && ctl.n_used == p.max_nodes - 1) break;  // "run out of memory" (:1060-1064)
+    if (root && ctl.n_used >= p.max_nodes) break;        // storage guard (the reference would overrun its pool)
+    NbChildRec& rec = sh->rec[ch];
+    if (!rec.valid) continue;
+    if (!root)
+    {
+      int f = rec.found, f_state = rec.f_state, f_index = rec.f_index;
+      if (f < 0)
+        for (int s = 0; s < ch; s++)
+          if (sh->rec[s].accept_id >= 0 && sh->rec[s].ix == rec.ix && sh->rec[s].iy == rec.iy && sh->rec[s].iz == rec.iz)
+          {  // a sibling accepted a moment ago holds this voxel
+            f = sh->rec[s].accept_id, f_state = 1, f_index = par_index + 1;
+            break;
+          }
+      if (f >= 0)
+      {
+        if (f_state == 1 && f_index == par_index + 1)
+        {
+          if (rec.g + p.bias * rec.h < c.gh[2 * f] + p.bias * c.gh[2 * f + 1] && ctl.ran_trigger % 2 == 0)
+          {  // :1193-1205: kinematics replaced; entangle state, index and heap position kept
+            c.gh[2 * f] = rec.g, c.gh[2 * f + 1] = rec.h;
+            if (f >= ctl.first_new)
+            {
+              for (int s = 0; s < ch; s++)
+                if (sh->rec[s].accept_id == f)
+                  for (int k = 0; k < NB_SEARCH_KIN; k++) sh->rec[s].kin[k] = rec.kin[k];
+            }
+            else
+            {
+              c.meta[f].x = cur;
+              for (int k = 0; k < NB_SEARCH_KIN; k++) c.kin[(size_t)f * NB_SEARCH_KIN + k] = rec.kin[k];
+            }
+          }
+          ctl.ran_trigger++;
+        }
+        continue;
+      }
+    }
+    const int id = ctl.n_used;
+    rec.accept_id = id;
+    c.gh[2 * id] = rec.g, c.gh[2 * id + 1] = rec.h;
+    c.heap[ctl.heap_n++] = id;
+    nb_heap_push_at(c, ctl.heap_n - 1, 0, id);
+    nb_hash_insert(c, rec.ix, rec.iy, rec.iz, id);
+    ctl.n_used++;
+  }
+}
+
+// the CTA-wide search of one agent.  Cta: tid, nthreads, warp, nwarps, lane, sync(), any(int)
+// bytes of shared memory that hold every per-agent working set (the launcher clamps to what the SM has)
+inline size_t nb_search_arena_wanted(const NbSearchPar& p)
+{
+  const size_t NA = (size_t)p.N + p.M, mn = (size_t)p.max_nodes;
+  auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+  size_t t = 0;
+  t += r16(((size_t)p.nchild * nb_search_ch_stride(p) + NA) * 4) + r16((size_t)p.nchild * p.ecap * 8);
+  t += r16(mn * 16) + r16(mn * 4);
+  t += r16((size_t)p.N * 16) + r16((size_t)p.N * 4) + r16((size_t)p.N * p.bp_max * 16) + r16((size_t)p.N) + r16(NA * 4);
+  t += r16((size_t)p.M * 32) + r16((size_t)p.M * 16) + r16((size_t)p.N * NB_NPOL * 4);
+  t += r16((size_t)p.N * p.num_pol * (p.S + 1) * 16);
+  return t;
+}
+
+template <class Cta, typename T>
+NB_HD const T* nb_search_stage(Cta& cta, NbArena& ar, const T* src, size_t count)
+{
+  if (!src || count == 0) return src;
+  T* d = (T*)ar.take(count * sizeof(T));
+  if (!d) return src;
+  for (size_t q = cta.tid; q < count; q += cta.nthreads) d[q] = src[q];
+  return d;
+}
+
+template <class Cta, int NL>
+NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared* sh, unsigned char* arena, size_t arena_bytes)
+{
+  const NbSearchPar& p = a.p;
+  const int N = p.N, M = p.M, NA = N + M, S = p.S;
+  NbSearchCtx c;
+  c.p = &p, c.b = b, c.self = a.agent_id[b] - 1, c.NA = NA;
+  for (int k = 0; k < 6; k++) c.init[k] = a.init[(size_t)b * 6 + k];
+  c.goal[0] = a.goal[2 * b], c.goal[1] = a.goal[2 * b + 1];
+  const int grp = a.group ? a.group[b] : b;
+  c.hull_xy = a.hull_xy + (size_t)grp * N * NB_NPOL * NB_HMAX * 2;
+  c.hull_cnt = a.hull_cnt + (size_t)grp * N * NB_NPOL;
+  c.samp = a.samp + (size_t)grp * N * p.num_pol * (S + 1) * 2;
+  c.known = a.known + (size_t)b * N;
+  c.comb = a.comb + (a.comb_shared ? 0 : (size_t)b * p.nchild);
+  c.st_ptr = a.st_ptr, c.st_xy = a.st_xy, c.st_longest = a.st_longest;
+  c.ecx.N = N, c.ecx.M = M, c.ecx.self = c.self, c.ecx.cap = p.ecap, c.ecx.bp_max = p.bp_max;
+  c.ecx.pb = a.pb, c.ecx.strep = a.strep, c.ecx.bp_cnt = a.bp_cnt, c.ecx.bp_xy = a.bp_xy;
+  c.a_na = a.es.cnt[2 * b], c.a_nb = a.es.cnt[2 * b + 1];
+  c.a_alpha = a.es.alpha + (size_t)b * p.es_cap * 2, c.a_beta = a.es.beta + (size_t)b * p.es_cap;
+  c.a_bend = a.es.bend + (size_t)b * p.es_cap, c.a_active = a.es.active + (size_t)b * NA;
+  c.meta = a.nd_meta + (size_t)b * p.max_nodes;
+  c.kin = a.nd_kin + (size_t)b * p.max_nodes * NB_SEARCH_KIN;
+  c.alpha = a.nd_alpha + (size_t)b * p.max_nodes * p.ecap * 2;
+  c.beta = a.nd_beta + (size_t)b * p.max_nodes * p.ecap;
+  c.bend = a.nd_bend + (size_t)b * p.max_nodes * p.ecap;
+  c.hash = a.hash + (size_t)b * p.hcap;
+  c.ch_stride = nb_search_ch_stride(p);
+  NbArena ar;
+  ar.p = arena, ar.left = arena_bytes;
+  {  // priority 1: the children's scratch (crossing lists, working entanglement state); 2: the open list and
+     // its keys; 3: read-only per-agent inputs of the entanglement chain
+    int* ci = (int*)ar.take(((size_t)p.nchild * c.ch_stride + NA) * sizeof(int));
+    c.ch_int = ci ? ci : a.ch_int + (size_t)b * (p.nchild * c.ch_stride + NA);
+    double* cd = (double*)ar.take((size_t)p.nchild * p.ecap * sizeof(double));
+    c.ch_dbl = cd ? cd : a.ch_dbl + (size_t)b * p.nchild * p.ecap;
+    double* gh = (double*)ar.take((size_t)p.max_nodes * 2 * sizeof(double));
+    c.gh = gh ? gh : a.gh_g + (size_t)b * p.max_nodes * 2;
+    int* hp = (int*)ar.take((size_t)p.max_nodes * sizeof(int));
+    c.heap = hp ? hp : a.heap_g + (size_t)b * p.max_nodes;
+    c.ecx.pb = nb_search_stage(cta, ar, c.ecx.pb, (size_t)N * 2);
+    c.ecx.bp_cnt = nb_search_stage(cta, ar, c.ecx.bp_cnt, (size_t)N);
+    c.ecx.bp_xy = nb_search_stage(cta, ar, c.ecx.bp_xy, (size_t)N * p.bp_max * 2);
+    c.known = nb_search_stage(cta, ar, c.known, (size_t)N);
+    c.a_active = nb_search_stage(cta, ar, c.a_active, (size_t)NA);
+    c.ecx.strep = nb_search_stage(cta, ar, c.ecx.strep, (size_t)M * 4);
+    c.st_longest = nb_search_stage(cta, ar, c.st_longest, (size_t)M * 2);
+    c.hull_cnt = nb_search_stage(cta, ar, c.hull_cnt, (size_t)N * NB_NPOL);
+    c.samp = nb_search_stage(cta, ar, c.samp, (size_t)N * p.num_pol * (S + 1) * 2);
+  }
+  c.par_act = c.ch_int + (size_t)p.nchild * c.ch_stride;
+  cta.sync();  // staged copies visible to every thread
+  NbSearchCtl& ctl = sh->ctl;
+  Group<NL> g(cta.lane);
+
+  // ---- setUp: clear the node map; is the goal occupied by another agent's last hull? (:213-229)
+  for (int q = cta.tid; q < p.hcap; q += cta.nthreads)
+  {
+    NbInt4 z;
+    z.x = z.y = z.z = z.w = 0;
+    c.hash[q] = z;
+  }
+  int occ = 0;
+  {
+    const double r = 0.5, gx = c.goal[0], gy = c.goal[1];
+    const double ghull[8] = { gx + r, gy + r, gx + r, gy - r, gx - r, gy + r, gx - r, gy - r };
+    for (int o = cta.tid; o < N; o += cta.nthreads)
+    {
+      const int hn = nb_hull_count(c, o, p.num_pol - 1);
+      if (hn > 0 && nb_gjk_collision(c.hull_xy + ((size_t)(o * NB_NPOL + p.num_pol - 1) * NB_HMAX) * 2, hn, ghull, 4)) occ = 1;
+    }
+  }
+  occ = cta.any(occ);
+  if (cta.tid == 0)
+  {
+    ctl.done = 0, ctl.status = 2, ctl.cur = -1, ctl.best = -1, ctl.closest = -1, ctl.n_used = 0, ctl.heap_n = 0;
+    ctl.pops = 0, ctl.ran_trigger = 0, ctl.goal_occupied = occ, ctl.first_new = 0, ctl.overflow = 0;
+    ctl.smallest = DBL_MAX;
+  }
+  for (int q = cta.tid; q < NA; q += cta.nthreads) c.par_act[q] = c.a_active[q];
+  cta.sync();
+  if (c.a_na > p.ecap || c.a_nb > p.ecap)
+  {  // entangle_state_A does not fit a search node
+    if (cta.tid == 0)
+    {
+      *a.err = 5;
+      a.status[b] = 2, a.solved[b] = 0, a.n_int[b] = 0;
+      a.stats[4 * b] = a.stats[4 * b + 1] = a.stats[4 * b + 2] = 0, a.stats[4 * b + 3] = occ;
+      a.cost[b] = 0.0;
+    }
+    return;
+  }
+
+  int cur = -1;
+  for (;;)
+  {
+    // ---- expandAndAddToQueue(cur)
+    double ist[6];
+    int par_index, par_na, par_nb;
+    double par_g;
+    const int *par_alpha, *par_bend;
+    const double* par_beta;
+    if (cur < 0)
+    {
+      for (int k = 0; k < 6; k++) ist[k] = c.init[k];
+      par_index = 0, par_g = 0.0, par_na = c.a_na, par_nb = c.a_nb;
+      par_alpha = c.a_alpha, par_beta = c.a_beta, par_bend = c.a_bend;
+    }
+    else
+    {
+      for (int k = 0; k < 6; k++) ist[k] = c.kin[(size_t)cur * NB_SEARCH_KIN + k];
+      const NbInt4 m = c.meta[cur];
+      par_index = m.y, par_na = m.w & 0xffff, par_nb = m.w >> 16;
+      par_g = c.gh[2 * cur];
+      par_alpha = c.alpha + (size_t)cur * p.ecap * 2, par_beta = c.beta + (size_t)cur * p.ecap;
+      par_bend = c.bend + (size_t)cur * p.ecap;
+    }
+    for (int ch = cta.warp; ch < p.nchild; ch += cta.nwarps)
+      nb_search_child<NL>(g, c, sh, cur, ch, ist, par_index, par_g, par_alpha, par_beta, par_bend, par_na, par_nb);
+    cta.sync();
+    if (cta.tid == 0) nb_search_resolve(c, sh, cur, par_index);
+    cta.sync();
+    for (int ch = cta.warp; ch < p.nchild; ch += cta.nwarps)
+    {  // accepted children: payload into the pool
+      const NbChildRec& rec = sh->rec[ch];
+      const int id = rec.accept_id;
+      if (id < 0) continue;
+      const int* ci = c.ch_int + (size_t)ch * c.ch_stride + 4 * p.tcap + NA;
+      const double* cb = c.ch_dbl + (size_t)ch * p.ecap;
+      for (int q = g.lane; q < rec.n_alpha; q += NL)
+      {
+        c.alpha[((size_t)id * p.ecap + q) * 2] = ci[2 * q], c.alpha[((size_t)id * p.ecap + q) * 2 + 1] = ci[2 * q + 1];
+        c.beta[(size_t)id * p.ecap + q] = cb[q];
+      }
+      for (int q = g.lane; q < rec.n_bend; q += NL) c.bend[(size_t)id * p.ecap + q] = ci[2 * p.ecap + q];
+      for (int q = g.lane; q < NB_SEARCH_KIN; q += NL) c.kin[(size_t)id * NB_SEARCH_KIN + q] = rec.kin[q];
+      if (g.lane == 0)
+      {
+        NbInt4 m;
+        m.x = cur, m.y = par_index + 1, m.z = 1, m.w = rec.n_alpha | (rec.n_bend << 16);
+        c.meta[id] = m;
+      }
+    }
+    cta.sync();
+
+    // ---- next node of the open list that survives the collision tests (:1642-1676)
+    for (;;)
+    {
+      if (cta.tid == 0)
+      {
+        if (ctl.heap_n == 0)
+          ctl.done = 1, ctl.status = 2;
+        else if (ctl.pops >= p.max_exp)
+          ctl.done = 1, ctl.status = 0;
+        else
+        {
+          ctl.pops++;
+          ctl.cur = nb_heap_pop(c, ctl.heap_n);
+          c.meta[ctl.cur].z = -1;
+        }
+      }
+      cta.sync();
+      if (ctl.done) break;
+      cur = ctl.cur;
+      double nk[NB_SEARCH_KIN], cps[8];
+      for (int k = 0; k < NB_SEARCH_KIN; k++) nk[k] = c.kin[(size_t)cur * NB_SEARCH_KIN + k];
+      const NbInt4 m = c.meta[cur];
+      nb_search_ctrl(p, nk, cps);
+      int hi = m.y > p.num_pol ? p.num_pol : m.y;
+      int hit = 0;
+      const double radius = 0.7, safe_dist = p.T * p.v_max * 2;
+      for (int it = cta.tid; it < 2 * N + M && !hit; it += cta.nthreads)
+      {
+        if (it < N)
+        {  // collidesWithObstacles2dSolve: other agents' hulls of window index-1
+          const int hn = nb_hull_count(c, it, hi - 1);
+          if (hn > 0 && nb_gjk_collision(c.hull_xy + ((size_t)(it * NB_NPOL + hi - 1) * NB_HMAX) * 2, hn, cps, 4)) hit = 1;
+        }
+        else if (it < N + M)
+        {  // static obstacles
+          const int64_t p0 = c.st_ptr[it - N], p1 = c.st_ptr[it - N + 1];
+          if (nb_gjk_collision(c.st_xy + 2 * p0, (int)(p1 - p0), cps, 4)) hit = 1;
+        }
+        else if (p.enable_entangle)
+        {  // collidesWithBases2d
+          const int ag = it - N - M;
+          if (ag == c.self) continue;
+          const double bx = c.ecx.pb[2 * ag], by = c.ecx.pb[2 * ag + 1];
+          if (nb_norm2(cps[0] - bx, cps[1] - by) > safe_dist) continue;
+          const double sq[8] = { bx + radius, by + radius, bx + radius, by - radius, bx - radius, by - radius, bx - radius, by + radius };
+          if (nb_gjk_collision(sq, 4, cps, 4)) hit = 1;
+        }
+      }
+      hit = cta.any(hit);
+      if (hit) continue;
+      // active_cases of the node: active_A - count_A + count_node
+      for (int q = cta.tid; q < NA; q += cta.nthreads)
+      {
+        int v = c.a_active[q];
+        for (int k = 0; k < c.a_na; k++) v -= (c.a_alpha[2 * k] == q + 1);
+        const int na = m.w & 0xffff;
+        const int* al = c.alpha + (size_t)cur * p.ecap * 2;
+        for (int k = 0; k < na; k++) v += (al[2 * k] == q + 1);
+        c.par_act[q] = v;
+      }
+      cta.sync();
+      int invalid = 0;
+      for (int q = cta.tid; q < N; q += cta.nthreads)
+        if (c.par_act[q] > 1) invalid = 1;
+      invalid = cta.any(invalid);
+      if (cta.tid == 0)
+      {
+        const double dist = nb_norm2(nk[0] - c.goal[0], nk[1] - c.goal[1]);
+        const double dist_init = nb_norm2(nk[0] - c.init[0], nk[1] - c.init[1]);
+        const double dcmp = ctl.goal_occupied ? dist * dist : dist_init;
+        const double dti = dcmp * (double)m.y;
+        if (dti < ctl.smallest && !invalid)
+        {
+          ctl.smallest = dti;
+          ctl.closest = cur;
+        }
+        if (dist < p.goal_size && !invalid) ctl.done = 1, ctl.status = 1;
+      }
+      cta.sync();
+      break;
+    }
+    if (ctl.done) break;
+  }
+
+  // ---- choose the result (:1753-1826), recoverPwpOut (:521-553), recoverEntStateVector (:582-603)
+  int best = -1;
+  if (ctl.status == 1)
+    best = ctl.cur;
+  else if (ctl.closest >= 0 && p.use_not_reaching)
+    best = ctl.closest;
+  int n = 0;
+  int path[NB_NPOL];
+  if (best >= 0)
+  {
+    for (int t = best; t >= 0; t = c.meta[t].x)
+    {
+      const int idx = c.meta[t].y;
+      if (idx <= p.num_pol)
+      {
+        path[idx - 1] = t;
+        if (idx > n) n = idx;
+      }
+    }
+  }
+  if (cta.tid == 0)
+  {
+    a.status[b] = ctl.status;
+    a.solved[b] = best >= 0;
+    a.n_int[b] = n;
+    a.stats[4 * b] = ctl.n_used, a.stats[4 * b + 1] = ctl.pops, a.stats[4 * b + 2] = best >= 0 ? c.meta[best].y : 0;
+    a.stats[4 * b + 3] = ctl.goal_occupied;
+    a.cost[b] = best >= 0 ? c.gh[2 * best] : 0.0;
+    if (ctl.overflow) *a.err = 5;
+  }
+  double* co = a.coeff + (size_t)b * 3 * NB_NPOL * 4;
+  for (int q = cta.tid; q < 3 * NB_NPOL * 4; q += cta.nthreads)
+  {
+    const int ax = q / (NB_NPOL * 4), i = (q / 4) % NB_NPOL, k = q % 4;
+    double v = 0.0;
+    if (i < n) v = ax == 2 ? a.coeffs_z[((size_t)b * NB_NPOL + i) * 4 + k] : c.kin[(size_t)path[i] * NB_SEARCH_KIN + 6 + 4 * ax + k];
+    co[q] = v;
+  }
+  if (best < 0) return;
+  const int ocap = p.out_cap;
+  for (int i = 0; i <= NB_NPOL; i++)
+  {
+    const int src = i == 0 ? -1 : path[(i <= n ? i : n) - 1];
+    const int na = src < 0 ? c.a_na : (c.meta[src].w & 0xffff), nbd = src < 0 ? c.a_nb : (c.meta[src].w >> 16);
+    const int* al = src < 0 ? c.a_alpha : c.alpha + (size_t)src * p.ecap * 2;
+    const double* be = src < 0 ? c.a_beta : c.beta + (size_t)src * p.ecap;
+    const int* bd = src < 0 ? c.a_bend : c.bend + (size_t)src * p.ecap;
+    const size_t o = (size_t)b * 9 + i;
+    if (cta.tid == 0)
+    {
+      a.esv.cnt[2 * o] = na, a.esv.cnt[2 * o + 1] = nbd;
+      if (na > ocap || nbd > ocap) *a.err = 5;
+    }
+    for (int q = cta.tid; q < ocap; q += cta.nthreads)
+    {
+      const bool in = q < na && na <= ocap;
+      a.esv.alpha[(o * ocap + q) * 2] = in ? al[2 * q] : 0;
+      a.esv.alpha[(o * ocap + q) * 2 + 1] = in ? al[2 * q + 1] : 0;
+      a.esv.beta[o * ocap + q] = in ? be[q] : 0.0;
+      a.esv.bend[o * ocap + q] = (q < nbd && nbd <= ocap) ? bd[q] : 0;
+    }
+    for (int q = cta.tid; q < NA; q += cta.nthreads)
+    {
+      int v = c.a_active[q];
+      if (src >= 0)
+      {
+        for (int k = 0; k < c.a_na; k++) v -= (c.a_alpha[2 * k] == q + 1);
+        for (int k = 0; k < na; k++) v += (al[2 * k] == q + 1);
+      }
+      a.esv.active[o * NA + q] = v;
+    }
+  }
+}

@@ -1,0 +1,11 @@
+// nb_search_launch.h -- host-side interface between nb_capi.cu (ABI) and nb_search.cu (kernel TU)
+#pragma once
+#include <stddef.h>
+
+struct NbSearchArgs;
+
+#define NB_SEARCH_THREADS 800            // 25 warps: one per jerk sample of the 5x5 lattice
+#define NB_SEARCH_SMEM_MAX (220 * 1024)  // dynamic shared memory the search kernel may ask for
+
+// returns 0, or -1 with *err = CUDA error text
+int nb_search_launch(const NbSearchArgs* a, int B, void* stream, const char** err);

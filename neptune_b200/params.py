@@ -37,6 +37,15 @@ class Params:
     runtime_opt: float = 0.08
     use_linear_constraints: bool = True
     enable_entangle_check: bool = True
+    # front end (KinodynamicSearch), neptune_multi_obstacle.yaml:9, :43-44, :127; setBias(1.1) neptune.cpp:97
+    goal_radius: float = 0.5
+    a_star_samp_x: int = 5
+    a_star_fraction_voxel_size: float = 0.2
+    a_star_bias: float = 1.1
+    use_not_reaching_soln: bool = True
+    search_max_nodes: int = 4096      # node_num_max_ (the reference: 15 * area / voxel^2, kinodynamic_search.cpp:370)
+    search_max_expansions: int = 600  # open-list pops allowed: stands in for the wall-clock max_runtime_ (:1646)
+    search_ecap: int = 24             # entries an alphas list of a search node can hold (semantic bound N+M)
     # storage capacities of this implementation (the reference uses std::vector)
     ent_cap: int = 48                # entries an alphas list can hold (semantic bound stays 3(N+M))
     bp_max: int = 8                  # bend points per agent list, base included

@@ -218,6 +218,10 @@ class Scene:
     esA_beta: np.ndarray | None = None
     esA_bend: np.ndarray | None = None
     esA_active: np.ndarray | None = None
+    group: np.ndarray | None = None        # [B] window group (index into the distinct t_start values)
+    hull_g_xy: np.ndarray | None = None    # [G][N][8][24][2] inflated hulls per window group (fixed stride)
+    hull_g_cnt: np.ndarray | None = None   # [G][N][8]
+    samp_g: np.ndarray | None = None       # [G][N][num_pol][S+1][2]
 
 
 def _static_obstacles(par: Params, rng, pb):
@@ -258,7 +262,7 @@ def _static_rep(poly, theta):
 
 def make_scene(par: Params, seed: int, *, n_fixed: int | None = None, sync: bool = True,
                ent_backend=None, agents: np.ndarray | None = None, spread: float | None = None,
-               pack_hulls: bool = True) -> Scene:
+               pack_hulls: bool = True, group_hulls: bool = False) -> Scene:
     """Build one replan cycle's inputs for the planning agents `agents` (0-based, default all).
     pack_hulls=False skips the host-side packed hull arrays (large worlds: the device builds the hulls
     from the committed-trajectory records, K1)."""
@@ -407,10 +411,53 @@ def make_scene(par: Params, seed: int, *, n_fixed: int | None = None, sync: bool
                state_A=state_A, es0_cnt=np.zeros((B, 2), np.int32), es0_alpha=np.zeros((B, cap, 2), np.int32),
                es0_beta=np.zeros((B, cap)), es0_bend=np.zeros((B, cap), np.int32),
                es0_active=np.zeros((B, NA), np.int32))
+    if group_hulls:  # fixed-stride hulls / samples per window group: the front-end search's view
+        G = len(uniq)
+        sc.group = np.array([uniq.index(float(t)) for t in t_start], np.int32)
+        sc.hull_g_xy = np.zeros((G, N, NPOL, 24, 2))
+        sc.hull_g_cnt = np.zeros((G, N, NPOL), np.int32)
+        sc.samp_g = np.zeros((G, N, par.num_pol, S + 1, 2))
+        for gi, ts in enumerate(uniq):
+            for j in range(N):
+                for i in range(par.num_pol):
+                    hj = hull_cache[(ts, j)][i][0]
+                    sc.hull_g_cnt[gi, j, i] = len(hj)
+                    sc.hull_g_xy[gi, j, i, :len(hj)] = hj
+                sc.samp_g[gi, j] = samp_cache[(ts, j)]
     if ent_backend is not None:
         fill_entangle(sc, ent_backend, rng)
     batch.validate()
     return sc
+
+
+def make_search_batch(sc: Scene, seed: int, per_agent_order: bool = False):
+    """Inputs of KinodynamicSearch::setUp / run for every planning agent of a scene built with
+    ``group_hulls=True`` and an ``ent_backend`` (``neptune.cpp:1437-1453``)."""
+    from .search import SearchBatch, jerk_order, static_longest_dist
+
+    par, b = sc.par, sc.batch
+    assert sc.hull_g_xy is not None and sc.esA_cnt is not None
+    B = b.B
+    init = np.zeros((B, 6))
+    init[:, 0:2], init[:, 2:4], init[:, 4:6] = sc.state_A[:, 0, :2], sc.state_A[:, 1, :2], sc.state_A[:, 2, :2]
+    agents = b.agent_id - 1
+    goal = np.ascontiguousarray(sc.goals[agents, :2])
+    cz = np.stack([initial_z_pwp(par, sc.state_A[bi, 0, 2], sc.state_A[bi, 1, 2], sc.state_A[bi, 2, 2],
+                                 sc.goals[agents[bi], 2]) for bi in range(B)])
+    coeffs_z = np.zeros((B, NPOL, 4))
+    coeffs_z[:, :par.num_pol] = cz
+    M = par.num_of_static_obst
+    strep = np.ascontiguousarray(sc.strep, np.float64).reshape(M, 2, 2)
+    sb = SearchBatch(
+        par=par, agent_id=b.agent_id.copy(), init=init, goal=goal, coeffs_z=coeffs_z, group=sc.group.copy(),
+        hull_xy=sc.hull_g_xy, hull_cnt=sc.hull_g_cnt, samp=sc.samp_g, known=sc.known.copy(),
+        es_cnt=np.ascontiguousarray(sc.esA_cnt, np.int32), es_alpha=np.ascontiguousarray(sc.esA_alpha, np.int32),
+        es_beta=np.ascontiguousarray(sc.esA_beta, np.float64), es_bend=np.ascontiguousarray(sc.esA_bend, np.int32),
+        es_active=np.ascontiguousarray(sc.esA_active, np.int32), bp_cnt=b.bp_cnt, bp_xy=b.bp_xy,
+        comb=jerk_order(par, seed, B if per_agent_order else None), st_ptr=b.st_ptr, st_xy=b.st_xy, strep=strep,
+        st_longest=static_longest_dist(sc.static_raw, strep) if M else np.zeros((0, 2)))
+    sb.validate()
+    return sb
 
 
 def fill_entangle(sc: Scene, be, rng) -> None:

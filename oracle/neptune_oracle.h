@@ -206,6 +206,115 @@ int orc_cycle_batch(const orc_params* par, int B, const int* agent_id, const int
                     double delta, int do_entangle, double* coeff_out, double* obj, int* status, int* iters,
                     int* entangled, int* collide, int nthreads);
 
+/* ---- front end: KinodynamicSearch (kinodynamic_search.cpp), neptune_search.c ---- */
+#define ORC_SEARCH_HSTRIDE 24 /* vertices reserved per hull in the fixed-stride hull arrays */
+
+typedef struct orc_search_par
+{
+  int num_pol, N, M, S;
+  double T;
+  double x_min, x_max, y_min, y_max;
+  double v_max, a_max, j_max;
+  int num_samples;     /* a_star_samp_x: jerk samples per axis */
+  double voxel_size;   /* a_star_fraction_voxel_size */
+  double bias;         /* setBias(1.1), neptune.cpp:97 */
+  double goal_size;    /* goal_radius */
+  double tether;       /* tetherLength */
+  int enable_entangle; /* enable_entangle_check */
+  int use_not_reaching;/* use_not_reaching_soln */
+  int max_nodes;       /* node_num_max_ */
+  int max_expansions;  /* stands in for max_runtime_ */
+  int ecap;            /* storage capacity of a node's alphas list */
+  int out_cap;         /* stride of the esv_* outputs (= the back end's ent_cap) */
+  int bp_max;
+} orc_search_par;
+
+typedef struct orc_search_in
+{
+  int agent_id;            /* 1-based */
+  double init[6];          /* px py vx vy ax ay */
+  double goal[2];
+  const double* coeffs_z;  /* [8][4] getInitialZPwp */
+  const double* hull_xy;   /* [N][8][ORC_SEARCH_HSTRIDE][2] inflated hulls per window */
+  const int* hull_cnt;     /* [N][8], 0 = no hull (unknown agent or self) */
+  const double* samp;      /* [N][num_pol][S+1][2] */
+  const unsigned char* known; /* [N] */
+  const long long* st_ptr; /* [M+1] inflated static obstacles */
+  const double* st_xy;
+  const double* strep;     /* [M][2][2] */
+  const double* st_longest;/* [M][2] staticObsLongestDist */
+  const double* pb;        /* [N][2] */
+  const int* bp_cnt;       /* [N] */
+  const double* bp_xy;     /* [N][bp_max][2] */
+  const int* es_cnt;       /* [2] entangle_state_A */
+  const int* es_alpha;
+  const double* es_beta;
+  const int* es_bend;
+  const int* es_active;    /* [N+M] */
+  const unsigned char* comb; /* [num_samples^2] order of the jerk samples, value = jx*num_samples+jy */
+} orc_search_in;
+
+typedef struct orc_search_out
+{
+  int* status;     /* 0 runtime reached, 1 goal reached, 2 open list empty (kinodynamic_search.cpp:1637-1639) */
+  int* solved;     /* return value of run() */
+  int* n_int;      /* pieces of pwp_out_ */
+  double* coeff;   /* [3][8][4] */
+  int* esv_cnt;    /* [9][2] entStateVec */
+  int* esv_alpha;  /* [9][out_cap][2] */
+  double* esv_beta;/* [9][out_cap] */
+  int* esv_bend;   /* [9][out_cap] */
+  int* esv_active; /* [9][N+M] */
+  int* stats;      /* [4] nodes used, pops, index of the best node, goal_occupied */
+  double* cost;    /* g of the best node */
+} orc_search_out;
+
+int orc_search(const orc_search_par* par, const orc_search_in* in, orc_search_out* out);
+
+typedef struct orc_search_batch_t
+{
+  int B;
+  const int* agent_id;       /* [B] */
+  const double* init;        /* [B][6] */
+  const double* goal;        /* [B][2] */
+  const double* coeffs_z;    /* [B][8][4] */
+  const int* group;          /* [B] window group of each agent, NULL: group = b */
+  const double* hull_xy;     /* [G][N][8][24][2] */
+  const int* hull_cnt;       /* [G][N][8] */
+  const double* samp;        /* [G][N][num_pol][S+1][2] */
+  const unsigned char* known;/* [B][N] */
+  const long long* st_ptr;
+  const double* st_xy;
+  const double* strep;
+  const double* st_longest;
+  const double* pb;
+  const int* bp_cnt;
+  const double* bp_xy;
+  int es_cap;                /* stride of es_alpha / es_beta / es_bend */
+  const int* es_cnt;         /* [B][2] */
+  const int* es_alpha;       /* [B][es_cap][2] */
+  const double* es_beta;
+  const int* es_bend;
+  const int* es_active;      /* [B][N+M] */
+  int comb_shared;
+  const unsigned char* comb; /* [num_samples^2] or [B][num_samples^2] */
+  int* status;
+  int* solved;
+  int* n_int;
+  double* coeff;             /* [B][3][8][4] */
+  int* esv_cnt;              /* [B][9][2] */
+  int* esv_alpha;            /* [B][9][out_cap][2] */
+  double* esv_beta;
+  int* esv_bend;
+  int* esv_active;           /* [B][9][N+M] */
+  int* stats;                /* [B][4] */
+  double* cost;              /* [B] */
+} orc_search_batch_t;
+
+int orc_search_batch(const orc_search_par* par, const orc_search_batch_t* b, int nthreads);
+/* test hook: open-list script through the heap restatement (compared with the real std::priority_queue) */
+int orc_heap_replay(int n_ops, const int* ops, const double* vals, int n_ids, double bias, int* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,10 +18,8 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "neptune_oracle.c")
-    hdr = os.path.join(_HERE, "neptune_oracle.h")
-    stale = (not os.path.exists(_LIB_PATH)) or any(
-        os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in (src, hdr))
+    srcs = [os.path.join(_HERE, f) for f in ("neptune_oracle.c", "neptune_search.c", "neptune_oracle.h")]
+    stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
     return _LIB_PATH
@@ -342,3 +340,61 @@ def compose_records(t, dc, p1, p2):
     f.restype = C.c_int
     n = f(C.c_double(t), C.c_double(dc), _p(p1), _p(p2), _p(out))
     return n, out, p1, p2
+
+
+# --------------------------------------------------------------------------- front end (neptune_search.c)
+class OrcSearchPar(C.Structure):
+    _fields_ = [("num_pol", C.c_int), ("N", C.c_int), ("M", C.c_int), ("S", C.c_int), ("T", C.c_double),
+                ("x_min", C.c_double), ("x_max", C.c_double), ("y_min", C.c_double), ("y_max", C.c_double),
+                ("v_max", C.c_double), ("a_max", C.c_double), ("j_max", C.c_double), ("num_samples", C.c_int),
+                ("voxel_size", C.c_double), ("bias", C.c_double), ("goal_size", C.c_double), ("tether", C.c_double),
+                ("enable_entangle", C.c_int), ("use_not_reaching", C.c_int), ("max_nodes", C.c_int),
+                ("max_expansions", C.c_int), ("ecap", C.c_int), ("out_cap", C.c_int), ("bp_max", C.c_int)]
+
+
+class OrcSearchBatch(C.Structure):
+    _fields_ = [("B", C.c_int), ("agent_id", _P), ("init", _P), ("goal", _P), ("coeffs_z", _P), ("group", _P),
+                ("hull_xy", _P), ("hull_cnt", _P), ("samp", _P), ("known", _P), ("st_ptr", _P), ("st_xy", _P),
+                ("strep", _P), ("st_longest", _P), ("pb", _P), ("bp_cnt", _P), ("bp_xy", _P), ("es_cap", C.c_int),
+                ("es_cnt", _P), ("es_alpha", _P), ("es_beta", _P), ("es_bend", _P), ("es_active", _P),
+                ("comb_shared", C.c_int), ("comb", _P), ("status", _P), ("solved", _P), ("n_int", _P), ("coeff", _P),
+                ("esv_cnt", _P), ("esv_alpha", _P), ("esv_beta", _P), ("esv_bend", _P), ("esv_active", _P),
+                ("stats", _P), ("cost", _P)]
+
+
+def make_search_par(par) -> OrcSearchPar:
+    sp = OrcSearchPar()
+    sp.num_pol, sp.N, sp.M, sp.S, sp.T = par.num_pol, par.num_of_agents, par.num_of_static_obst, par.num_sample_per_interval, par.T_span
+    sp.x_min, sp.x_max, sp.y_min, sp.y_max = par.x_min, par.x_max, par.y_min, par.y_max
+    sp.v_max, sp.a_max, sp.j_max, sp.num_samples = par.v_max, par.a_max, par.j_max, par.a_star_samp_x
+    sp.voxel_size, sp.bias, sp.goal_size, sp.tether = par.a_star_fraction_voxel_size, par.a_star_bias, par.goal_radius, par.tetherLength
+    sp.enable_entangle, sp.use_not_reaching = int(par.enable_entangle_check), int(par.use_not_reaching_soln)
+    sp.max_nodes, sp.max_expansions, sp.ecap = par.search_max_nodes, par.search_max_expansions, par.search_ecap
+    sp.out_cap, sp.bp_max = par.ent_cap, par.bp_max
+    return sp
+
+
+def search_batch(sb, res, nthreads: int = 1) -> int:
+    """orc_search_batch over a neptune_b200.search.SearchBatch; fills a SearchResult."""
+    par = sb.par
+    sp = make_search_par(par)
+    M = par.num_of_static_obst
+    keep = dict(pb=_c(par.pb, np.float64), hull_cnt=_c(sb.hull_cnt, np.int32),
+                strep=_c(sb.strep, np.float64) if M else np.zeros((1, 2, 2)),
+                longest=_c(sb.st_longest, np.float64) if M else np.zeros((1, 2)),
+                st_ptr=_c(sb.st_ptr, np.int64), st_xy=_c(sb.st_xy, np.float64) if M else np.zeros((1, 2)))
+    b = OrcSearchBatch()
+    b.B = sb.B
+    b.agent_id, b.init, b.goal, b.coeffs_z, b.group = _p(sb.agent_id), _p(sb.init), _p(sb.goal), _p(sb.coeffs_z), _p(sb.group)
+    b.hull_xy, b.hull_cnt, b.samp, b.known = _p(sb.hull_xy), _p(keep["hull_cnt"]), _p(sb.samp), _p(sb.known)
+    b.st_ptr, b.st_xy, b.strep, b.st_longest = _p(keep["st_ptr"]), _p(keep["st_xy"]), _p(keep["strep"]), _p(keep["longest"])
+    b.pb, b.bp_cnt, b.bp_xy = _p(keep["pb"]), _p(sb.bp_cnt), _p(sb.bp_xy)
+    b.es_cap = par.ent_cap
+    b.es_cnt, b.es_alpha, b.es_beta, b.es_bend, b.es_active = _p(sb.es_cnt), _p(sb.es_alpha), _p(sb.es_beta), _p(sb.es_bend), _p(sb.es_active)
+    b.comb_shared, b.comb = int(sb.comb.ndim == 1), _p(sb.comb)
+    b.status, b.solved, b.n_int, b.coeff = _p(res.status), _p(res.solved), _p(res.n_int), _p(res.coeff)
+    b.esv_cnt, b.esv_alpha, b.esv_beta, b.esv_bend, b.esv_active = _p(res.esv_cnt), _p(res.esv_alpha), _p(res.esv_beta), _p(res.esv_bend), _p(res.esv_active)
+    b.stats, b.cost = _p(res.stats), _p(res.cost)
+    f = lib().orc_search_batch
+    f.restype = C.c_int
+    return f(C.byref(sp), C.byref(b), C.c_int(nthreads))

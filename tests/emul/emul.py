@@ -76,3 +76,24 @@ def compose(t, has_prev, prev, now):
     f.argtypes = [C.c_int] + [C.c_void_p] * 6
     f(len(arrs[0]), *[a.ctypes.data_as(C.c_void_p) for a in arrs], out.ctypes.data_as(C.c_void_p), npc.ctypes.data_as(C.c_void_p))
     return npc, out
+
+
+def search(sb):
+    """K0 front-end search, the device code on one host lane."""
+    from neptune_b200.capi import host_search_args, make_search_params
+    from neptune_b200.search import SearchResult
+    par = sb.par
+    res = SearchResult.empty(sb)
+    a = host_search_args(sb, res)
+    nbp, sp = make_nb_params(par), make_search_params(par)
+    pb = np.ascontiguousarray(par.pb, np.float64)
+    M = par.num_of_static_obst
+    strep = np.ascontiguousarray(sb.strep, np.float64) if M else np.zeros((1, 2, 2))
+    longest = np.ascontiguousarray(sb.st_longest, np.float64) if M else np.zeros((1, 2))
+    st_xy = np.ascontiguousarray(sb.st_xy, np.float64) if M else np.zeros((1, 2))
+    f = lib().emul_search_batch
+    f.argtypes = [C.c_void_p] * 8
+    rc = f(C.addressof(nbp), C.addressof(sp), pb.ctypes.data, sb.st_ptr.ctypes.data, st_xy.ctypes.data, strep.ctypes.data,
+           longest.ctypes.data, C.addressof(a))
+    assert rc == 0, rc
+    return res

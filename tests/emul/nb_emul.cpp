@@ -13,6 +13,7 @@
 #include "../../neptune_b200/csrc/nb_common.cuh"
 #include "../../neptune_b200/csrc/nb_lines.cuh"
 #include "../../neptune_b200/csrc/nb_qp.cuh"
+#include "../../neptune_b200/csrc/nb_search.cuh"
 #include "../../neptune_b200/csrc/nb_sep.cuh"
 #include "../../neptune_b200/csrc/nb_tables.h"
 
@@ -195,4 +196,51 @@ extern "C" int emul_compose(int B, const double* t, const uint8_t* has_prev, con
       n_pieces[b] = nb_compose_records(t[b], prev + (size_t)b * NB_REC, now + (size_t)b * NB_REC, out + (size_t)b * NB_REC);
   }
   return 0;
+}
+
+// ---- K0 front-end search with one host lane: the same nb_search_task the device runs with 25 warps
+struct EmulCta
+{
+  int tid = 0, nthreads = 1, warp = 0, nwarps = 1, lane = 0;
+  void sync() const {}
+  int any(int p) const { return p; }
+};
+
+extern "C" int emul_search_batch(const nb_params* par, const nb_search_params* sp, const double* pb, const int64_t* st_ptr,
+                                 const double* st_xy, const double* strep, const double* st_longest, const nb_search_args* u)
+{
+  NbConsts cs;
+  nb_build_consts(par, &cs);
+  NbSearchArgs a;
+  memset(&a, 0, sizeof(a));
+  nb_search_fill_par(*par, *sp, cs, &a.p);
+  const NbSearchPar& p = a.p;
+  const int NA = p.N + p.M;
+  a.agent_id = u->agent_id, a.init = u->init, a.goal = u->goal, a.coeffs_z = u->coeffs_z, a.group = u->group;
+  a.hull_xy = u->hull_xy, a.hull_cnt = u->hull_cnt, a.samp = u->samp, a.known = u->known;
+  a.st_ptr = st_ptr, a.st_xy = st_xy, a.strep = strep, a.st_longest = st_longest, a.pb = pb;
+  a.bp_cnt = u->bp_cnt, a.bp_xy = u->bp_xy, a.es = u->es, a.comb = u->comb, a.comb_shared = u->comb_shared;
+  a.status = u->status, a.solved = u->solved, a.n_int = u->n_int, a.coeff = u->coeff, a.esv = u->esv;
+  a.stats = u->stats, a.cost = u->cost;
+  const size_t mn = (size_t)p.max_nodes, chs = (size_t)nb_search_ch_stride(p);
+  std::vector<NbInt4> meta(mn), hash((size_t)p.hcap);
+  std::vector<double> kin(mn * NB_SEARCH_KIN), beta(mn * p.ecap), gh(mn * 2), chd((size_t)p.nchild * p.ecap);
+  std::vector<int> alpha(mn * p.ecap * 2), bend(mn * p.ecap), heap(mn), chi((size_t)p.nchild * chs + NA);
+  int err = 0;
+  a.nd_meta = meta.data(), a.nd_kin = kin.data(), a.nd_alpha = alpha.data(), a.nd_beta = beta.data(), a.nd_bend = bend.data();
+  a.hash = hash.data(), a.heap_g = heap.data(), a.gh_g = gh.data(), a.ch_int = chi.data(), a.ch_dbl = chd.data(), a.err = &err;
+  NbSearchShared* sh = new NbSearchShared();
+  // workspace pointers are per agent: run agents one at a time with b-relative offsets removed
+  for (int b = 0; b < u->B; b++)
+  {
+    NbSearchArgs ab = a;
+    ab.nd_meta -= (size_t)b * mn, ab.nd_kin -= (size_t)b * mn * NB_SEARCH_KIN, ab.nd_alpha -= (size_t)b * mn * p.ecap * 2;
+    ab.nd_beta -= (size_t)b * mn * p.ecap, ab.nd_bend -= (size_t)b * mn * p.ecap, ab.hash -= (size_t)b * p.hcap;
+    ab.heap_g -= (size_t)b * mn, ab.gh_g -= (size_t)b * mn * 2, ab.ch_int -= (size_t)b * (p.nchild * chs + NA);
+    ab.ch_dbl -= (size_t)b * p.nchild * p.ecap;
+    EmulCta cta;
+    nb_search_task<EmulCta, 1>(cta, ab, b, sh, nullptr, 0);
+  }
+  delete sh;
+  return err ? NB_ERR_CAPACITY : 0;
 }

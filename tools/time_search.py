@@ -1,0 +1,53 @@
+"""Times the front-end search kernel (K0) on one scene against the oracle; prints per-stage numbers.
+Measurement helper (not the bench): python tools/time_search.py [cfg] [seed] [max_expansions]"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from neptune_b200 import capi, config
+from neptune_b200.scenes import make_scene, make_search_batch
+from neptune_b200.search import SearchResult
+
+
+def main():
+    cfg = sys.argv[1] if len(sys.argv) > 1 else "grid64"
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 4004
+    par = config(cfg)
+    if len(sys.argv) > 3:
+        par.search_max_expansions = int(sys.argv[3])
+    s = capi.Solver(par, device=0)
+    sc = make_scene(par, seed, sync=False, ent_backend=capi.DeviceEntBackend(s), group_hulls=True)
+    sb = make_search_batch(sc, seed + 1, per_agent_order=True)
+    if par.num_of_static_obst:
+        s.set_static(sb.st_ptr, sb.st_xy, sb.strep)
+        s.set_static_longest(sb.st_longest)
+    s.search_configure()
+    got = s.search(sb)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        t = time.perf_counter()
+        got = s.search(sb)
+        ts.append(time.perf_counter() - t)
+    print(f"{cfg}: B={sb.B} gpu search (host buffers, e2e) best {min(ts) * 1e3:.3f} ms; pops total {int(got.stats[:, 1].sum())} "
+          f"max {int(got.stats[:, 1].max())}; nodes max {int(got.stats[:, 0].max())}; status {np.bincount(got.status, minlength=3).tolist()}")
+    print(f"  per pop of the slowest agent: {min(ts) * 1e6 / max(1, int(got.stats[:, 1].max())):.2f} us")
+    try:
+        from oracle import oracle as orc
+        ref = SearchResult.empty(sb)
+        nt = os.cpu_count() or 1
+        t = time.perf_counter()
+        orc.search_batch(sb, ref, nt)
+        dt = time.perf_counter() - t
+        same = all(np.array_equal(getattr(ref, f), getattr(got, f)) for f in ("status", "n_int", "coeff", "esv_alpha", "stats"))
+        print(f"  oracle ({nt} threads): {dt * 1e3:.2f} ms; identical: {same}")
+    except Exception as e:  # oracle is test infrastructure; this helper still reports the GPU side
+        print("  oracle unavailable:", e)
+
+
+if __name__ == "__main__":
+    main()
