@@ -156,6 +156,87 @@ def cpu_baseline(scene, budget_s: float, threads: int):
     return scene.batch.B * reps / el, reps, el, out
 
 
+def measure_front_end(par, agents, dev, scene, static, steps: int, with_cpu: bool):
+    """The front end (K0, KinodynamicSearch::run) measured on the same world: one more ReplanCycle object with
+    front_end=True, i.e. hulls -> predict -> SEARCH -> LPs + QP -> post-check -> commit, all device-resident.
+    Reported beside the headline (whose metric, SURVEY 8d, starts after the front end)."""
+    import torch
+
+    from neptune_b200 import capi
+    from neptune_b200.cycle import ReplanCycle
+    from neptune_b200.scenes import search_host_inputs
+    from neptune_b200.search import SearchBatch, SearchResult, static_longest_dist
+
+    cyc = ReplanCycle(par, agents, dev, static=static, world=1, front_end=True)
+    fe = search_host_inputs(scene, SEED + 1)
+    hin = cyc.host_inputs(scene, fe)
+    hout = cyc.host_outputs()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    B = cyc.B
+    cyc.upload(hin)
+    cyc.capture()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for it in range(2 + steps):
+        cyc.upload(hin)
+        flush.zero_()
+        if it >= 2:
+            ev[it - 2][0].record()
+        cyc.step()
+        if it >= 2:
+            ev[it - 2][1].record()
+    torch.cuda.synchronize()
+    cyc.check_errors()
+    full_ms = float(np.median([a.elapsed_time(b) for a, b in ev]))
+    cyc.profile = True
+    fe_ms = []
+    for it in range(3):
+        cyc.upload(hin)
+        flush.zero_()
+        cyc.step()
+        fe_ms.append(cyc.stage_ms["front_end"])
+    cyc.profile = False
+    t0 = time.perf_counter()
+    for it in range(steps):
+        cyc.step_from_host(hin, hout)
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+    o = cyc.o
+    stats = o["fe_stats"].cpu().numpy()
+    status = o["fe_status"].cpu().numpy()
+    out = {"kernel": "k_search", "agents": B, "ms_search": float(np.median(fe_ms)), "ms_full_cycle": full_ms,
+           "full_replans_per_s": B / (full_ms * 1e-3), "e2e_full_replans_per_s": B / (e2e_ms * 1e-3),
+           "pops": int(stats[:, 1].sum()), "pops_max": int(stats[:, 1].max()), "nodes_max": int(stats[:, 0].max()),
+           "pops_per_s": float(stats[:, 1].sum() / (np.median(fe_ms) * 1e-3)),
+           "status_hist": {"runtime": int((status == 0).sum()), "goal": int((status == 1).sum()), "empty": int((status == 2).sum())},
+           "solved": int(o["fe_solved"].sum().item()), "max_expansions": par.search_max_expansions,
+           "max_nodes": par.search_max_nodes}
+    if with_cpu:
+        from oracle import oracle as orc
+        M = par.num_of_static_obst
+        sb = SearchBatch(
+            par=par, agent_id=scene.batch.agent_id.copy(), init=fe["init"], goal=fe["goal"], coeffs_z=fe["coeffs_z"],
+            group=hin["group"].copy(), hull_xy=o["hull_xy_g"].cpu().numpy(), hull_cnt=o["hull_cnt_g"].cpu().numpy(),
+            samp=o["samp_g"].cpu().numpy(), known=scene.known.copy(), es_cnt=o["esA_cnt"].cpu().numpy(),
+            es_alpha=o["esA_alpha"].cpu().numpy(), es_beta=o["esA_beta"].cpu().numpy(), es_bend=o["esA_bend"].cpu().numpy(),
+            es_active=o["esA_active"].cpu().numpy(), bp_cnt=scene.batch.bp_cnt, bp_xy=scene.batch.bp_xy, comb=fe["comb"],
+            st_ptr=scene.batch.st_ptr, st_xy=scene.batch.st_xy, strep=np.asarray(scene.strep, np.float64).reshape(M, 2, 2),
+            st_longest=static_longest_dist(scene.static_raw, np.asarray(scene.strep).reshape(M, 2, 2)) if M else np.zeros((0, 2)))
+        ref = SearchResult.empty(sb)
+        nt = os.cpu_count() or 1
+        orc.search_batch(sb, ref, nt)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            orc.search_batch(sb, ref, nt)
+        cpu_ms = 1e3 * (time.perf_counter() - t0) / reps
+        same = (np.array_equal(ref.status, status) and np.array_equal(ref.n_int, o["fe_n_int"].cpu().numpy())
+                and np.array_equal(ref.coeff, o["fe_coeff"].cpu().numpy()) and np.array_equal(ref.stats, stats)
+                and np.array_equal(ref.esv_alpha, o["fe_esv_alpha"].cpu().numpy()))
+        out["cpu_oracle"] = {"ms_search": cpu_ms, "cores": nt, "kind": "port", "identical": bool(same),
+                             "sample": f"{B} searches x {reps}, oracle/neptune_search.c orc_search_batch"}
+    cyc.solver.close()
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -351,6 +432,8 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": v, "unit": "replans/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": f"{B} agents x {reps} whole cycles of scene 0 ({el:.1f} s), "
                                               "oracle/neptune_oracle.c orc_cycle_batch"}
+        if world == 1 and args.workload == "grid64" and not args.no_front_end:
+            line["front_end"] = measure_front_end(par, agents, dev, scenes[0], static, args.front_end_steps, not args.no_cpu)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -368,6 +451,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
+    ap.add_argument("--no-front-end", action="store_true", help="skip the front-end (K0 search) measurement")
+    ap.add_argument("--front-end-steps", type=int, default=10)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

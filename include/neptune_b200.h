@@ -350,6 +350,12 @@ typedef struct nb_search_args
 
 int nb_search_batch(nb_handle* h, const nb_search_args* args, void* stream);
 
+/* Measurement hook (no reference counterpart): with nb_set_profiling on, SM cycles thread 0 of every search CTA
+ * spent per phase in the last nb_search_batch, out [B][16]: [0] children, [1] sequential resolve, [2] pool copy,
+ * [3] open-list pop, [4] collision tests, [5] endpoint tests, [6] set-up; [8..14] child 0 only: primitive, state copy,
+ * entanglement chain, key + lookup, step geometry, crossing tests, list automaton. */
+int nb_search_phase_cycles(nb_handle* h, long long* out, int B);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,7 +75,9 @@ struct nb_handle
   // front-end search: configuration, staging and workspace
   nb_search_params sp;
   int sp_set = 0;
+  int sprof_B = 0;
   double* d_st_longest = nullptr;
+  DevBuf sprof;
   DevBuf sin[20], sout[12], sw_meta, sw_kin, sw_alpha, sw_beta, sw_bend, sw_hash, sw_heap, sw_gh, sw_chi, sw_chd;
   int qp_smem_set = 0;
   int profiling = 0;
@@ -514,6 +516,7 @@ extern "C" void nb_destroy(nb_handle* h)
   for (auto& b : h->sin) b.release();
   for (auto& b : h->sout) b.release();
   h->sw_meta.release(), h->sw_kin.release(), h->sw_alpha.release(), h->sw_beta.release(), h->sw_bend.release();
+  h->sprof.release();
   h->sw_hash.release(), h->sw_heap.release(), h->sw_gh.release(), h->sw_chi.release(), h->sw_chd.release();
   delete h;
 }
@@ -1311,6 +1314,11 @@ extern "C" int nb_search_batch(nb_handle* h, const nb_search_args* u, void* stre
   const nb_search_params& sp = h->sp;
   const int B = u->B, N = h->par.num_agents, M = h->par.num_static, NA = N + M, S = h->par.samples, np = h->par.num_pol;
   const int cap = h->par.ent_cap, space = u->space, G = u->group ? u->n_groups : B;
+  if (S > 8)
+  {
+    g_err = "nb_search_batch: num_sample_per_interval > 8 is not supported";
+    return NB_ERR_ARG;
+  }
   if (M > 0 && (!h->d_strep || !h->d_st_longest || !h->d_st_xy))
   {
     g_err = "nb_search_batch with static obstacles needs nb_set_static(strep) and nb_set_static_longest first";
@@ -1366,7 +1374,7 @@ extern "C" int nb_search_batch(nb_handle* h, const nb_search_args* u, void* stre
   bad |= h->sw_heap.ensure(B * mn * sizeof(int)) != 0;
   bad |= h->sw_gh.ensure(B * mn * 2 * sizeof(double)) != 0;
   bad |= h->sw_chi.ensure((size_t)B * (p.nchild * ch_stride + NA) * sizeof(int)) != 0;
-  bad |= h->sw_chd.ensure((size_t)B * p.nchild * p.ecap * sizeof(double)) != 0;
+  bad |= h->sw_chd.ensure((size_t)B * nb_search_chd_stride(p) * sizeof(double)) != 0;
   if (bad)
   {
     g_err = "cudaMalloc failed for the search workspace";
@@ -1376,6 +1384,18 @@ extern "C" int nb_search_batch(nb_handle* h, const nb_search_args* u, void* stre
   a.nd_beta = (double*)h->sw_beta.p, a.nd_bend = (int*)h->sw_bend.p, a.hash = (NbInt4*)h->sw_hash.p;
   a.heap_g = (int*)h->sw_heap.p, a.gh_g = (double*)h->sw_gh.p, a.ch_int = (int*)h->sw_chi.p, a.ch_dbl = (double*)h->sw_chd.p;
   a.err = (int*)h->err.p;
+  a.prof = nullptr;
+  if (h->profiling)
+  {
+    if (h->sprof.ensure((size_t)B * 16 * sizeof(long long)))
+    {
+      g_err = "cudaMalloc failed";
+      return NB_ERR_CUDA;
+    }
+    NB_CUDA(cudaMemsetAsync(h->sprof.p, 0, (size_t)B * 16 * sizeof(long long), st));
+    a.prof = (long long*)h->sprof.p;
+    h->sprof_B = B;
+  }
   const char* etxt = nullptr;
   if (nb_search_launch(&a, B, stream, &etxt))
   {
@@ -1406,5 +1426,17 @@ extern "C" int nb_search_batch(nb_handle* h, const nb_search_args* u, void* stre
       return NB_ERR_CAPACITY;
     }
   }
+  return NB_OK;
+}
+
+// Measurement hook: SM cycles thread 0 of every search CTA spent per phase in the last profiled nb_search_batch
+// (nb_set_profiling on): [0] children, [1] sequential resolve, [2] pool copy, [3] open-list pop, [4] collision
+// tests, [5] endpoint tests, [6] set-up.  out: [B][8].
+extern "C" int nb_search_phase_cycles(nb_handle* h, long long* out, int B)
+{
+  if (!h || !out || !h->sprof.p || B > h->sprof_B) return NB_ERR_ARG;
+  NB_CUDA(cudaSetDevice(h->device));
+  NB_CUDA(cudaDeviceSynchronize());
+  NB_CUDA(cudaMemcpy(out, h->sprof.p, (size_t)B * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return NB_OK;
 }

@@ -142,6 +142,69 @@ NB_HD int nb_hsig_agent(int* loc, const double* pk, const double* pk1, const dou
   return nadd;
 }
 
+// Same function without a per-thread entry buffer: the entries go straight to `out` (pairs) when out != nullptr,
+// otherwise they are only counted; the last two entries stay in registers for the cancellation rule (:1221-1227).
+// nb_collect_toadd calls it twice (count, then write at the scanned offset) so no thread keeps a stack array.
+NB_HD int nb_hsig_agent_stream(int* out, const double* pk, const double* pk1, const double* pik, const double* pik1,
+                               const double* pb_self, const double* bend, int nbend, int agent_id)
+{
+  int nadd = 0, last_cs = -1, prev_cs = -2;  // entries all carry agent_id: only the case numbers can differ
+  bool base_add = false;
+#define NB_HSIG_PUSH(cs_)                                   \
+  {                                                         \
+    if (out) out[2 * nadd] = agent_id, out[2 * nadd + 1] = (cs_); \
+    prev_cs = last_cs, last_cs = (cs_);                     \
+    nadd++;                                                 \
+  }
+  for (int i = 0; i < nbend; i++)
+  {
+    double ab[2], ac[2], c1, c2;
+    const double* bi = bend + 2 * i;
+    const bool last = (i == nbend - 1);
+    if (!last)
+    {
+      c1 = nb_wedge(pk, bend + 2 * (i + 1), bi, ab, ac);
+      c2 = nb_wedge(pk1, bend + 2 * (i + 1), bi, nullptr, nullptr);
+    }
+    else
+    {
+      c1 = nb_wedge(pk, pik, bi, ab, ac);
+      c2 = nb_wedge(pk1, pik1, bi, nullptr, nullptr);
+    }
+    if (last)
+    {
+      double fb[2], fc[2];
+      const double f1 = nb_wedge(pb_self, pik, bi, fb, fc);
+      const double f2 = nb_wedge(pb_self, pik1, bi, nullptr, nullptr);
+      if (nb_neg_product(f1, f2))
+      {
+        const double a = nb_cross_ratio(fb, fc);
+        if (a < 0)
+        {
+        }
+        else if (a < 1)
+          NB_HSIG_PUSH(1)
+        else if (i == 0)
+          NB_HSIG_PUSH(0)
+        base_add = true;
+      }
+    }
+    if (nb_neg_product(c1, c2))
+    {
+      const double a = nb_cross_ratio(ab, ac);
+      if (a < 0)
+        NB_HSIG_PUSH(i + 2)
+      else if (a < 1 && last)
+        NB_HSIG_PUSH(1)
+      else if (a >= 1 && i == 0)
+        NB_HSIG_PUSH(0)
+    }
+  }
+#undef NB_HSIG_PUSH
+  if (base_add && nadd >= 2 && last_cs == prev_cs) nadd -= 2;
+  return nadd;
+}
+
 // eu::entangleHSigToAddStatic (:1231-1277) for ONE static obstacle
 NB_HD int nb_hsig_static_one(int* loc, const double* pk, const double* pk1, const double* rep /*[2][2]*/, int id)
 {
@@ -180,7 +243,8 @@ NB_HD int nb_excl_scan(const Group<NL>& g, int v, int& total)
 
 // All crossing tests of one step pk -> pk+1: tethers of the known agents (positions pik -> pik+1 per
 // agent: pik_all[j], pik1_all[j]) then the static obstacles.  toadd: shared list [tcap][2].
-// Returns the number of entries, or -1 if tcap would be exceeded.
+// Returns the number of entries, or -1 if tcap would be exceeded.  Two passes per chunk of NL tethers: count,
+// then (only when the chunk has a crossing at all) a prefix sum and a second evaluation that writes in place.
 template <int NL>
 NB_HD int nb_collect_toadd(const Group<NL>& g, const NbEntCtx& cx, const double* pk, const double* pk_agents,
                            const double* pk1, const double* pik_all, int pik_stride, const double* pik1_all,
@@ -191,27 +255,29 @@ NB_HD int nb_collect_toadd(const Group<NL>& g, const NbEntCtx& cx, const double*
   for (int base = 0; base < cx.N + cx.M; base += NL)
   {
     const int j = base + g.lane;
-    int loc[2 * NB_ENT_LOCAL];
-    int cnt = 0;
-    if (j < cx.N)
+    int cnt = 0, nb = 0, st[2];
+    const bool agent = j < cx.N && j != cx.self && known[j];
+    if (agent)
     {
-      if (j != cx.self && known[j])
-      {
-        int nb = cx.bp_cnt[j];
-        if (nb > NB_ENT_LOCAL - 2) nb = NB_ENT_LOCAL - 2;
-        cnt = nb_hsig_agent(loc, pk_agents ? pk_agents + 2 * j : pk, pk1, pik_all + (size_t)j * pik_stride, pik1_all + (size_t)j * pik1_stride, pb_self,
-                            cx.bp_xy + (size_t)2 * cx.bp_max * j, nb, j + 1);
-      }
+      nb = cx.bp_cnt[j];
+      if (nb > NB_ENT_LOCAL - 2) nb = NB_ENT_LOCAL - 2;
+      cnt = nb_hsig_agent_stream(nullptr, pk_agents ? pk_agents + 2 * j : pk, pk1, pik_all + (size_t)j * pik_stride,
+                                 pik1_all + (size_t)j * pik1_stride, pb_self, cx.bp_xy + (size_t)2 * cx.bp_max * j, nb, j + 1);
     }
-    else if (j < cx.N + cx.M)
-      cnt = nb_hsig_static_one(loc, pk, pk1, cx.strep + 4 * (j - cx.N), j + 1);
+    else if (j >= cx.N && j < cx.N + cx.M)
+      cnt = nb_hsig_static_one(st, pk, pk1, cx.strep + 4 * (j - cx.N), j + 1);
+    if (!g.any(cnt > 0)) continue;  // no crossing in this chunk of tethers (the common case): nothing to place
     int total;
     const int off = nb_excl_scan<NL>(g, cnt, total);
     if (nadd + total > tcap) return -1;
-    for (int e = 0; e < cnt; e++)
+    if (cnt > 0)
     {
-      toadd[2 * (nadd + off + e)] = loc[2 * e];
-      toadd[2 * (nadd + off + e) + 1] = loc[2 * e + 1];
+      int* out = toadd + 2 * (nadd + off);
+      if (agent)
+        nb_hsig_agent_stream(out, pk_agents ? pk_agents + 2 * j : pk, pk1, pik_all + (size_t)j * pik_stride,
+                             pik1_all + (size_t)j * pik1_stride, pb_self, cx.bp_xy + (size_t)2 * cx.bp_max * j, nb, j + 1);
+      else
+        out[0] = st[0], out[1] = st[1];
     }
     nadd += total;
   }

@@ -311,10 +311,11 @@ NB_HD void nb_gjk_triple(const double* a, const double* b, const double* c, doub
   r[1] = NB_SUB(NB_MUL(b[1], ac), NB_MUL(a[1], bc));
 }
 
-// gjk::collision (gjk.cpp:76-148)
+// gjk::collision (gjk.cpp:76-148).  The simplex (at most three points, addressed by `index` in the reference)
+// is kept in named registers s0, s1, s2 so that no thread needs a stack array.
 NB_HD bool nb_gjk_collision(const double* v1, int n1, const double* v2, int n2)
 {
-  double simplex[3][2], a[2], b[2], c[2], d[2], ao[2], ab[2], ac[2], abp[2], acp[2];
+  double s0[2], s1[2] = { 0, 0 }, s2[2], a[2], d[2], ao[2], ab[2], ac[2], abp[2], acp[2];
   double p1[2] = { 0, 0 }, p2[2] = { 0, 0 };
   int index = 0;
   for (int i = 0; i < n1; i++) p1[0] = NB_ADD(p1[0], v1[2 * i]), p1[1] = NB_ADD(p1[1], v1[2 * i + 1]);
@@ -322,29 +323,29 @@ NB_HD bool nb_gjk_collision(const double* v1, int n1, const double* v2, int n2)
   d[0] = NB_SUB(p1[0] / n1, p2[0] / n2);
   d[1] = NB_SUB(p1[1] / n1, p2[1] / n2);
   if (d[0] == 0 && d[1] == 0) d[0] = 1.0;
-  nb_gjk_support(v1, n1, v2, n2, d[0], d[1], simplex[0]);
-  a[0] = simplex[0][0], a[1] = simplex[0][1];
+  nb_gjk_support(v1, n1, v2, n2, d[0], d[1], s0);
+  a[0] = s0[0], a[1] = s0[1];
   if (nb_dot2(a, d) <= 0) return false;
   d[0] = -a[0], d[1] = -a[1];
   for (int guard = 0; guard < 1000; guard++)
   {
-    ++index;
-    nb_gjk_support(v1, n1, v2, n2, d[0], d[1], simplex[index]);
-    a[0] = simplex[index][0], a[1] = simplex[index][1];
+    ++index;  // 1 or 2
+    nb_gjk_support(v1, n1, v2, n2, d[0], d[1], a);
+    if (index == 1)
+      s1[0] = a[0], s1[1] = a[1];
+    else
+      s2[0] = a[0], s2[1] = a[1];
     if (nb_dot2(a, d) <= 0) return false;
     ao[0] = -a[0], ao[1] = -a[1];
     if (index < 2)
     {
-      b[0] = simplex[0][0], b[1] = simplex[0][1];
-      ab[0] = NB_SUB(b[0], a[0]), ab[1] = NB_SUB(b[1], a[1]);
+      ab[0] = NB_SUB(s0[0], a[0]), ab[1] = NB_SUB(s0[1], a[1]);
       nb_gjk_triple(ab, ao, ab, d);
       if (sqrt(NB_ADD(NB_MUL(d[0], d[0]), NB_MUL(d[1], d[1]))) == 0) d[0] = ab[1], d[1] = -ab[0];
       continue;
     }
-    b[0] = simplex[1][0], b[1] = simplex[1][1];
-    c[0] = simplex[0][0], c[1] = simplex[0][1];
-    ab[0] = NB_SUB(b[0], a[0]), ab[1] = NB_SUB(b[1], a[1]);
-    ac[0] = NB_SUB(c[0], a[0]), ac[1] = NB_SUB(c[1], a[1]);
+    ab[0] = NB_SUB(s1[0], a[0]), ab[1] = NB_SUB(s1[1], a[1]);
+    ac[0] = NB_SUB(s0[0], a[0]), ac[1] = NB_SUB(s0[1], a[1]);
     nb_gjk_triple(ab, ac, ac, acp);
     if (nb_dot2(acp, ao) >= 0)
       d[0] = acp[0], d[1] = acp[1];
@@ -352,10 +353,10 @@ NB_HD bool nb_gjk_collision(const double* v1, int n1, const double* v2, int n2)
     {
       nb_gjk_triple(ac, ab, ab, abp);
       if (nb_dot2(abp, ao) < 0) return true;
-      simplex[0][0] = simplex[1][0], simplex[0][1] = simplex[1][1];
+      s0[0] = s1[0], s0[1] = s1[1];
       d[0] = abp[0], d[1] = abp[1];
     }
-    simplex[1][0] = simplex[2][0], simplex[1][1] = simplex[2][1];
+    s1[0] = s2[0], s1[1] = s2[1];
     --index;
   }
   return false;

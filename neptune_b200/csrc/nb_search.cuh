@@ -102,6 +102,7 @@ struct NbSearchArgs
   int* ch_int;       // [nchild][2 tcap + 2 NA + 3 ecap] + [NA] parent active
   double* ch_dbl;    // [nchild][ecap]
   int* err;
+  long long* prof;   // optional [B][16]: SM cycles thread 0 spent per phase (measurement hook)
 };
 
 // parameters of one launch from the ABI structs (host side; shared by nb_capi.cu and the test emulation)
@@ -144,6 +145,9 @@ struct NbArena
 // ints of scratch per child: toadd [2 tcap] | (id, old active) pairs [2 tcap] | active [NA] | alpha [2 ecap] | bend [ecap]
 NB_HD int nb_search_ch_stride(const NbSearchPar& p) { return 4 * p.tcap + (p.N + p.M) + 3 * p.ecap; }
 
+// doubles of scratch per agent: beta lists of the children, then the base squares [N][4][2]
+NB_HD size_t nb_search_chd_stride(const NbSearchPar& p) { return (size_t)p.nchild * p.ecap + (size_t)p.N * 8; }
+
 // one evaluated child of the node being expanded
 struct NbChildRec
 {
@@ -154,15 +158,21 @@ struct NbChildRec
 struct NbSearchCtl
 {
   int done, status, cur, best, closest, n_used, heap_n, pops, ran_trigger, goal_occupied, first_new, overflow;
+  int n_acc, acc[NB_SEARCH_MAXCHILD];  // children accepted so far in the expansion being resolved
   double smallest;
   int flag[NB_SEARCH_MAXCHILD][4];
 };
 
-struct NbSearchShared
+// per-launch constants that depend only on the parameters and the jerk order (built once by thread 0 with the
+// very expressions of the reference, so that the per-child chains start from them)
+struct NbSearchTab
 {
-  NbSearchCtl ctl;
-  NbChildRec rec[NB_SEARCH_MAXCHILD];
+  double j6[5], j2[5], jt[5], jc[5];  // ji*tau*tau*tau/6, ji*tau*tau/2, ji*tau, ji/6 for the ns jerk values
+  double tt[8][3];                    // sampled_time_vector_ (:116-127): t, t*t, t*t*t for j = 1..S-1
+  int cjx[NB_SEARCH_MAXCHILD], cjy[NB_SEARCH_MAXCHILD];
 };
+
+#define NB_SEARCH_NSTAGE 9
 
 // per-agent view of the arguments
 struct NbSearchCtx
@@ -197,10 +207,57 @@ struct NbSearchCtx
   int* ch_int;
   double* ch_dbl;
   int* par_act;
+  double* base_sq;  // [N][4][2] squares around the bases (collidesWithBases2d :1610-1612)
   int ch_stride;
+  long long* prof;
+};
+
+// Everything the threads of one search share lives here (shared memory on the device): parameters and the
+// per-agent context are read through it instead of per-thread copies, so the kernel keeps no stack frame --
+// with 800 threads per CTA any per-thread local memory would overflow the part of L1 left beside the arena.
+struct NbSearchShared
+{
+  NbSearchCtl ctl;
+  NbSearchTab tab;
+  NbSearchPar par;
+  NbSearchCtx cx;
+  const void* stage_src[NB_SEARCH_NSTAGE];
+  void* stage_dst[NB_SEARCH_NSTAGE];
+  size_t stage_bytes[NB_SEARCH_NSTAGE];
+  int path[NB_NPOL];
+  // the node being expanded (written by thread 0 after the pop): kinematics, control points, list views
+  double par_kin[NB_SEARCH_KIN], par_cps[8], par_g, goal_hull[8];
+  int par_index, par_na, par_nb;
+  const int *par_alpha, *par_bend;
+  const double* par_beta;
+  NbChildRec rec[NB_SEARCH_MAXCHILD];
 };
 
 NB_HD double nb_norm2(double x, double y) { return sqrt(x * x + y * y); }
+
+#if defined(__CUDA_ARCH__)
+#define NB_TICK(slot)                                        \
+  if (a.prof && cta.tid == 0)                                \
+  {                                                          \
+    const long long now_ = clock64();                        \
+    a.prof[(size_t)b * 16 + (slot)] += now_ - tick_;          \
+    tick_ = now_;                                            \
+  }
+#define NB_TICK_INIT long long tick_ = clock64();
+#define NB_CTICK(slot)                                       \
+  if (c.prof && ch == 0 && g.lane == 0)                      \
+  {                                                          \
+    const long long now_ = clock64();                        \
+    c.prof[(slot)] += now_ - ctick_;                         \
+    ctick_ = now_;                                           \
+  }
+#define NB_CTICK_INIT long long ctick_ = clock64();
+#else
+#define NB_CTICK(slot)
+#define NB_CTICK_INIT
+#define NB_TICK(slot)
+#define NB_TICK_INIT
+#endif
 
 NB_HD int nb_hull_count(const NbSearchCtx& c, int o, int i)
 {
@@ -348,8 +405,9 @@ NB_HD double nb_tether_length(const NbSearchCtx& c, const NbEntState& es, const 
 // es works on the child's scratch lists / active array.  Returns 1 entangles, 0 fine, -1 storage overflow.
 template <int NL>
 NB_HD int nb_search_entangles(const Group<NL>& g, const NbSearchCtx& c, NbEntState& es, const double* kin, int index,
-                              int* toadd, int* act_old, int* flag, double* arc_length)
+                              int* toadd, int* act_old, int* flag, double* arc_length, int ch, const double (*tt)[3])
 {
+  NB_CTICK_INIT
   const NbSearchPar& p = *c.p;
   const int N = p.N, NA = c.NA, S = p.S, num_pol = p.num_pol;
   const double* cx = kin + 6;
@@ -361,8 +419,7 @@ NB_HD int nb_search_entangles(const Group<NL>& g, const NbSearchCtx& c, NbEntSta
   {
     if (j < S)
     {
-      const double t = p.T * j / S;
-      const double t3 = t * t * t, t2 = t * t;
+      const double t = tt[j][0], t2 = tt[j][1], t3 = tt[j][2];
       pk1[0] = cx[0] * t3 + cx[1] * t2 + cx[2] * t + cx[3];
       pk1[1] = cy[0] * t3 + cy[1] * t2 + cy[2] * t + cy[3];
     }
@@ -380,7 +437,9 @@ NB_HD int nb_search_entangles(const Group<NL>& g, const NbSearchCtx& c, NbEntSta
       pik = c.samp + ((size_t)(index - 1) * (S + 1) + (j - 1)) * 2;
       pik1 = c.samp + ((size_t)(index - 1) * (S + 1) + j) * 2;
     }
+    NB_CTICK(12)
     const int nadd = nb_collect_toadd<NL>(g, c.ecx, pk, nullptr, pk1, pik, stride, pik1, stride, c.known, toadd, p.tcap);
+    NB_CTICK(13)
     if (nadd < 0) return 1;  // more crossings than tcap >= N+M: over the list bound of :844-848 in any case
     if (g.lane == 0)
     {
@@ -415,6 +474,7 @@ NB_HD int nb_search_entangles(const Group<NL>& g, const NbSearchCtx& c, NbEntSta
     es.n_alpha = flag[1];
     es.n_bend = flag[2];
     g.sync();
+    NB_CTICK(14)
     if (r != 0) return r;
     pk[0] = pk1[0], pk[1] = pk1[1];
   }
@@ -423,57 +483,77 @@ NB_HD int nb_search_entangles(const Group<NL>& g, const NbSearchCtx& c, NbEntSta
   return 0;
 }
 
-// kinematics and admissibility of one jerk sample (:1071-1155 node form, :1260-1339 root form)
-NB_HD bool nb_search_primitive(const NbSearchCtx& c, const double* ist, int comb, bool root, double* kin, double* Q)
+NB_HD void nb_search_build_tab(const NbSearchPar& p, const uint8_t* comb, NbSearchTab& tb)
+{
+  const double tau = p.T, j_max = p.j_max, j_min = -p.j_max;
+  const double delta_x = (j_max - j_min) / (p.ns - 1);  // :1053
+  for (int k = 0; k < p.ns; k++)
+  {
+    const double ji = j_min + k * delta_x;  // :1074
+    tb.j6[k] = ji * tau * tau * tau / 6, tb.j2[k] = ji * tau * tau / 2, tb.jt[k] = ji * tau, tb.jc[k] = ji / 6;
+  }
+  for (int ch = 0; ch < p.nchild; ch++) tb.cjx[ch] = comb[ch] / p.ns, tb.cjy[ch] = comb[ch] % p.ns;
+  for (int j = 1; j < p.S && j < 8; j++)
+  {
+    const double t = p.T * j / p.S;
+    tb.tt[j][0] = t, tb.tt[j][1] = t * t, tb.tt[j][2] = t * t * t;
+  }
+}
+
+// kinematics and admissibility of one jerk sample (:1071-1155 node form, :1260-1339 root form).
+// Everything that depends only on the jerk sample comes from the per-launch table (same expressions, evaluated
+// once); the tests are pure, so they are all evaluated and combined at the end (no branches between dependent
+// FP64 chains).
+NB_HD bool nb_search_primitive(const NbSearchCtx& c, const NbSearchTab& tb, const double* ist, int ch, bool root,
+                               double* kin)
 {
   const NbSearchPar& p = *c.p;
   const double tau = p.T, j_max = p.j_max, j_min = -p.j_max, a_max = p.a_max, a_min = -p.a_max;
   const double v_max = p.v_max, v_min = -p.v_max;
-  const double delta_x = (j_max - j_min) / (p.ns - 1);
-  const int jx = comb / p.ns, jy = comb % p.ns;
-  const double ji[2] = { j_min + jx * delta_x, j_min + jy * delta_x };
-  double* e = kin;
-  for (int d = 0; d < 2; d++)
-  {
-    e[d] = ist[d] + ist[2 + d] * tau + ist[4 + d] * tau * tau / 2 + ji[d] * tau * tau * tau / 6;
-    e[2 + d] = ist[2 + d] + ist[4 + d] * tau + ji[d] * tau * tau / 2;
-    e[4 + d] = ist[4 + d] + ji[d] * tau;
-  }
+  const int jx = tb.cjx[ch], jy = tb.cjy[ch];
+  const double i0 = ist[0], i1 = ist[1], i2 = ist[2], i3 = ist[3], i4 = ist[4], i5 = ist[5];
+  const double e0 = i0 + i2 * tau + i4 * tau * tau / 2 + tb.j6[jx];
+  const double e1 = i1 + i3 * tau + i5 * tau * tau / 2 + tb.j6[jy];
+  const double e2 = i2 + i4 * tau + tb.j2[jx];
+  const double e3 = i3 + i5 * tau + tb.j2[jy];
+  const double e4 = i4 + tb.jt[jx];
+  const double e5 = i5 + tb.jt[jy];
   double n2 = 0;
-  for (int k = 0; k < 6; k++) n2 += (e[k] - ist[k]) * (e[k] - ist[k]);
-  if (sqrt(n2) < 0.00001) return false;
-  if (e[5] > a_max || e[5] < a_min || e[4] > a_max || e[4] < a_min) return false;
-  double* cx = kin + 6;
-  double* cy = kin + 10;
-  cx[0] = ji[0] / 6, cx[1] = ist[4] / 2, cx[2] = ist[2], cx[3] = ist[0];
-  cy[0] = ji[1] / 6, cy[1] = ist[5] / 2, cy[2] = ist[3], cy[3] = ist[1];
+  n2 += (e0 - i0) * (e0 - i0), n2 += (e1 - i1) * (e1 - i1), n2 += (e2 - i2) * (e2 - i2);
+  n2 += (e3 - i3) * (e3 - i3), n2 += (e4 - i4) * (e4 - i4), n2 += (e5 - i5) * (e5 - i5);
+  bool ok = !(sqrt(n2) < 0.00001);
+  ok &= !(e5 > a_max || e5 < a_min || e4 > a_max || e4 < a_min);
+  const double cx0 = tb.jc[jx], cx1 = i4 / 2, cx2 = i2, cx3 = i0;
+  const double cy0 = tb.jc[jy], cy1 = i5 / 2, cy2 = i3, cy3 = i1;
+  const double bx = c.ecx.pb[2 * c.self], by = c.ecx.pb[2 * c.self + 1];
+#pragma unroll
   for (int i = 0; i < 4; i++)
   {
     double qx = 0, qy = 0;
-    for (int k = 0; k < 4; k++) qx += cx[k] * p.Ainv[k * 4 + i], qy += cy[k] * p.Ainv[k * 4 + i];
-    Q[i] = qx, Q[4 + i] = qy;
-  }
-  const double bx = c.ecx.pb[2 * c.self], by = c.ecx.pb[2 * c.self + 1];
-  for (int i = 0; i < 4; i++)
-  {
-    if (Q[i] < p.x_min || Q[i] > p.x_max || Q[4 + i] < p.y_min || Q[4 + i] > p.y_max ||
-        nb_norm2(Q[i] - bx, Q[4 + i] - by) > p.tether)
-      return false;
+    qx += cx0 * p.Ainv[i], qx += cx1 * p.Ainv[4 + i], qx += cx2 * p.Ainv[8 + i], qx += cx3 * p.Ainv[12 + i];
+    qy += cy0 * p.Ainv[i], qy += cy1 * p.Ainv[4 + i], qy += cy2 * p.Ainv[8 + i], qy += cy3 * p.Ainv[12 + i];
+    ok &= !(qx < p.x_min || qx > p.x_max || qy < p.y_min || qy > p.y_max || nb_norm2(qx - bx, qy - by) > p.tether);
   }
   if (!root)
   {
+#pragma unroll
     for (int i = 0; i < 3; i++)
     {
       double vx = 0, vy = 0;
-      for (int k = 0; k < 3; k++) vx += cx[k] * p.V[k * 3 + i], vy += cy[k] * p.V[k * 3 + i];
-      if (vx < v_min || vx > v_max || vy < v_min || vy > v_max) return false;
+      vx += cx0 * p.V[i], vx += cx1 * p.V[3 + i], vx += cx2 * p.V[6 + i];
+      vy += cy0 * p.V[i], vy += cy1 * p.V[3 + i], vy += cy2 * p.V[6 + i];
+      ok &= !(vx < v_min || vx > v_max || vy < v_min || vy > v_max);
     }
   }
-  if (e[4] > 0 && e[2] - 0.5 * e[4] * e[4] / j_min > v_max) return false;
-  else if (e[4] < 0 && e[2] - 0.5 * e[4] * e[4] / j_max < v_min) return false;
-  if (e[5] > 0 && e[3] - 0.5 * e[5] * e[5] / j_min > v_max) return false;
-  else if (e[5] < 0 && e[3] - 0.5 * e[5] * e[5] / j_max < v_min) return false;
-  return true;
+  // future violation of the velocity bound under maximum braking jerk (:1136-1155)
+  const double fx = e2 - 0.5 * e4 * e4 / (e4 > 0 ? j_min : j_max);
+  const double fy = e3 - 0.5 * e5 * e5 / (e5 > 0 ? j_min : j_max);
+  ok &= !((e4 > 0 && fx > v_max) || (e4 < 0 && fx < v_min));
+  ok &= !((e5 > 0 && fy > v_max) || (e5 < 0 && fy < v_min));
+  kin[0] = e0, kin[1] = e1, kin[2] = e2, kin[3] = e3, kin[4] = e4, kin[5] = e5;
+  kin[6] = cx0, kin[7] = cx1, kin[8] = cx2, kin[9] = cx3;
+  kin[10] = cy0, kin[11] = cy1, kin[12] = cy2, kin[13] = cy3;
+  return ok;
 }
 
 // position control points of a node from its coefficients (Q = P * A_rest_pos_basis_inverse_, :1108)
@@ -491,16 +571,21 @@ NB_HD void nb_search_ctrl(const NbSearchPar& p, const double* kin, double* cps /
 
 // child c of the node `cur` (cur < 0: root), evaluated by one group; result in rec
 template <int NL>
-NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchShared* sh, int cur, int ch, const double* ist,
-                           int par_index, double par_g, const int* par_alpha, const double* par_beta, const int* par_bend,
-                           int par_na, int par_nb)
+NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchShared* sh, int cur, int ch)
 {
+  const double* ist = sh->par_kin;
+  const int par_index = sh->par_index, par_na = sh->par_na, par_nb = sh->par_nb;
+  const int *par_alpha = sh->par_alpha, *par_bend = sh->par_bend;
+  const double* par_beta = sh->par_beta;
   const NbSearchPar& p = *c.p;
   NbChildRec& rec = sh->rec[ch];
   if (g.lane == 0) rec.valid = 0, rec.accept_id = -1;
-  double kin[NB_SEARCH_KIN], Q[8];
+  double kin[NB_SEARCH_KIN];
   const bool root = cur < 0;
-  if (!nb_search_primitive(c, ist, c.comb[ch], root, kin, Q)) return;
+  NB_CTICK_INIT
+  const bool prim_ok = nb_search_primitive(c, sh->tab, ist, ch, root, kin);
+  NB_CTICK(8)
+  if (!prim_ok) return;
   const int index = par_index + 1;
   int* ci = c.ch_int + (size_t)ch * c.ch_stride;
   int* toadd = ci;
@@ -520,10 +605,12 @@ NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchSha
   for (int q = g.lane; q < par_nb; q += NL) es.bend[q] = par_bend[q];
   for (int q = g.lane; q < c.NA; q += NL) act[q] = c.par_act[q];
   g.sync();
+  NB_CTICK(9)
   double arc = 0.0;
   if (p.enable_entangle)
   {
-    const int r = nb_search_entangles<NL>(g, c, es, kin, index, toadd, act_old, sh->ctl.flag[ch], &arc);
+    const int r = nb_search_entangles<NL>(g, c, es, kin, index, toadd, act_old, sh->ctl.flag[ch], &arc, ch, sh->tab.tt);
+    NB_CTICK(10)
     if (r < 0 && g.lane == 0) sh->ctl.overflow = 1;
     if (r != 0) return;
   }
@@ -538,7 +625,7 @@ NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchSha
     rec.iy = nb_voxel_index(kin[1], p.voxel);
     rec.n_alpha = es.n_alpha, rec.n_bend = es.n_bend;
     for (int k = 0; k < NB_SEARCH_KIN; k++) rec.kin[k] = kin[k];
-    rec.g = par_g + arc;
+    rec.g = sh->par_g + arc;
     rec.h = nb_norm2(kin[0] - c.goal[0], kin[1] - c.goal[1]) + 0.3 * (double)es.n_alpha + 1.0 * (double)es.n_bend;
     // node-map lookup against the map as it is BEFORE this expansion (all children in parallel); the
     // sequential pass adds the siblings accepted ahead of this child
@@ -550,6 +637,7 @@ NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchSha
     }
     rec.valid = 1;
   }
+  NB_CTICK(11)
 }
 
 // the sequential half of expandAndAddToQueue: children in all_combinations_ order (one thread)
@@ -559,6 +647,7 @@ NB_HD void nb_search_resolve(const NbSearchCtx& c, NbSearchShared* sh, int cur, 
   NbSearchCtl& ctl = sh->ctl;
   const bool root = cur < 0;
   ctl.first_new = ctl.n_used;
+  ctl.n_acc = 0;
   for (int ch = 0; ch < p.nchild; ch++)
   {
     if (!root && ctl.n_used == p.max_nodes - 1) break;  // "run out of memory" (:1060-1064)
@@ -569,12 +658,15 @@ NB_HD void nb_search_resolve(const NbSearchCtx& c, NbSearchShared* sh, int cur, 
     {
       int f = rec.found, f_state = rec.f_state, f_index = rec.f_index;
       if (f < 0)
-        for (int s = 0; s < ch; s++)
-          if (sh->rec[s].accept_id >= 0 && sh->rec[s].ix == rec.ix && sh->rec[s].iy == rec.iy && sh->rec[s].iz == rec.iz)
+        for (int k = 0; k < ctl.n_acc; k++)
+        {
+          const NbChildRec& sr = sh->rec[ctl.acc[k]];
+          if (sr.ix == rec.ix && sr.iy == rec.iy && sr.iz == rec.iz)
           {  // a sibling accepted a moment ago holds this voxel
-            f = sh->rec[s].accept_id, f_state = 1, f_index = par_index + 1;
+            f = sr.accept_id, f_state = 1, f_index = par_index + 1;
             break;
           }
+        }
       if (f >= 0)
       {
         if (f_state == 1 && f_index == par_index + 1)
@@ -584,9 +676,8 @@ NB_HD void nb_search_resolve(const NbSearchCtx& c, NbSearchShared* sh, int cur, 
             c.gh[2 * f] = rec.g, c.gh[2 * f + 1] = rec.h;
             if (f >= ctl.first_new)
             {
-              for (int s = 0; s < ch; s++)
-                if (sh->rec[s].accept_id == f)
-                  for (int k = 0; k < NB_SEARCH_KIN; k++) sh->rec[s].kin[k] = rec.kin[k];
+              NbChildRec& sr = sh->rec[ctl.acc[f - ctl.first_new]];
+              for (int k = 0; k < NB_SEARCH_KIN; k++) sr.kin[k] = rec.kin[k];
             }
             else
             {
@@ -601,6 +692,7 @@ NB_HD void nb_search_resolve(const NbSearchCtx& c, NbSearchShared* sh, int cur, 
     }
     const int id = ctl.n_used;
     rec.accept_id = id;
+    ctl.acc[ctl.n_acc++] = ch;
     c.gh[2 * id] = rec.g, c.gh[2 * id + 1] = rec.h;
     c.heap[ctl.heap_n++] = id;
     nb_heap_push_at(c, ctl.heap_n - 1, 0, id);
@@ -609,6 +701,106 @@ NB_HD void nb_search_resolve(const NbSearchCtx& c, NbSearchShared* sh, int cur, 
   }
 }
 
+#if defined(__CUDA_ARCH__)
+// The same sequential pass run by one warp: lane ch holds child ch in registers, the loop over the children is
+// warp-uniform (broadcasts by shuffle, sibling voxel matches by ballot), only the open-list sift stays on lane 0,
+// and the node-map inserts of the accepted children go in parallel afterwards (their keys are distinct).
+__device__ __forceinline__ void nb_search_resolve_warp(const NbSearchCtx& c, NbSearchShared* sh, int cur, int par_index, int lane)
+{
+  const NbSearchPar& p = *c.p;
+  NbSearchCtl& ctl = sh->ctl;
+  const unsigned FULL = 0xffffffffu;
+  const bool root = cur < 0;
+  const bool has = lane < p.nchild;
+  NbChildRec& mine = sh->rec[has ? lane : 0];
+  const int valid = has ? mine.valid : 0;
+  const int ix = mine.ix, iy = mine.iy, iz = mine.iz;
+  const int found = (valid && !root) ? mine.found : -1, fst = mine.f_state, fidx = mine.f_index;
+  const double gm = mine.g, hm = mine.h;
+  int n_used = ctl.n_used, heap_n = ctl.heap_n, ran = ctl.ran_trigger;
+  const int first_new = n_used;
+  int my_id = -1;
+  for (int ch = 0; ch < p.nchild; ch++)
+  {
+    if (!root && n_used == p.max_nodes - 1) break;  // "run out of memory" (:1060-1064)
+    if (root && n_used >= p.max_nodes) break;
+    if (!__shfl_sync(FULL, valid, ch)) continue;
+    int f = -1, f_state = 0, f_index = 0, sib = -1;
+    if (!root)
+    {
+      f = __shfl_sync(FULL, found, ch), f_state = __shfl_sync(FULL, fst, ch), f_index = __shfl_sync(FULL, fidx, ch);
+      if (f < 0)
+      {
+        const int kx = __shfl_sync(FULL, ix, ch), ky = __shfl_sync(FULL, iy, ch), kz = __shfl_sync(FULL, iz, ch);
+        const unsigned m = __ballot_sync(FULL, my_id >= 0 && ix == kx && iy == ky && iz == kz);
+        if (m)
+        {  // a sibling accepted a moment ago holds this voxel
+          sib = __ffs(m) - 1;
+          f = __shfl_sync(FULL, my_id, sib), f_state = 1, f_index = par_index + 1;
+        }
+      }
+    }
+    if (f >= 0)
+    {
+      if (f_state == 1 && f_index == par_index + 1)
+      {
+        const double gc = __shfl_sync(FULL, gm, ch), hc = __shfl_sync(FULL, hm, ch);
+        if (gc + p.bias * hc < c.gh[2 * f] + p.bias * c.gh[2 * f + 1] && ran % 2 == 0)
+        {  // :1193-1205: kinematics replaced; entangle state, index and heap position kept
+          __syncwarp();
+          if (lane == 0) c.gh[2 * f] = gc, c.gh[2 * f + 1] = hc;
+          if (sib >= 0)
+          {
+            if (lane < NB_SEARCH_KIN) sh->rec[sib].kin[lane] = sh->rec[ch].kin[lane];
+          }
+          else
+          {
+            if (lane == 0) c.meta[f].x = cur;
+            if (lane < NB_SEARCH_KIN) c.kin[(size_t)f * NB_SEARCH_KIN + lane] = sh->rec[ch].kin[lane];
+          }
+          __syncwarp();
+        }
+        ran++;
+      }
+      continue;
+    }
+    const int id = n_used;
+    if (lane == ch) my_id = id;
+    if (lane == 0)
+    {
+      c.gh[2 * id] = sh->rec[ch].g, c.gh[2 * id + 1] = sh->rec[ch].h;
+      c.heap[heap_n] = id;
+      nb_heap_push_at(c, heap_n, 0, id);
+    }
+    __syncwarp();
+    heap_n++, n_used++;
+  }
+  if (has) mine.accept_id = my_id;
+  if (root)
+  {  // the root form has no lookup: duplicates are pushed, the map keeps the first (:1377)
+    __syncwarp();
+    if (lane == 0)
+      for (int ch = 0; ch < p.nchild; ch++)
+        if (sh->rec[ch].accept_id >= 0) nb_hash_insert(c, sh->rec[ch].ix, sh->rec[ch].iy, sh->rec[ch].iz, sh->rec[ch].accept_id);
+  }
+  else if (my_id >= 0)
+  {
+    const uint32_t mask = (uint32_t)(p.hcap - 1);
+    uint32_t q = nb_hash3(ix, iy, iz) & mask;
+    for (;;)
+    {
+      if (atomicCAS(&c.hash[q].w, 0, my_id + 1) == 0)
+      {
+        c.hash[q].x = ix, c.hash[q].y = iy, c.hash[q].z = iz;
+        break;
+      }
+      q = (q + 1) & mask;
+    }
+  }
+  if (lane == 0) ctl.n_used = n_used, ctl.heap_n = heap_n, ctl.ran_trigger = ran, ctl.first_new = first_new;
+}
+#endif
+
 // the CTA-wide search of one agent.  Cta: tid, nthreads, warp, nwarps, lane, sync(), any(int)
 // bytes of shared memory that hold every per-agent working set (the launcher clamps to what the SM has)
 inline size_t nb_search_arena_wanted(const NbSearchPar& p)
@@ -616,7 +808,7 @@ inline size_t nb_search_arena_wanted(const NbSearchPar& p)
   const size_t NA = (size_t)p.N + p.M, mn = (size_t)p.max_nodes;
   auto r16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
   size_t t = 0;
-  t += r16(((size_t)p.nchild * nb_search_ch_stride(p) + NA) * 4) + r16((size_t)p.nchild * p.ecap * 8);
+  t += r16(((size_t)p.nchild * nb_search_ch_stride(p) + NA) * 4) + r16(nb_search_chd_stride(p) * 8);
   t += r16(mn * 16) + r16(mn * 4);
   t += r16((size_t)p.N * 16) + r16((size_t)p.N * 4) + r16((size_t)p.N * p.bp_max * 16) + r16((size_t)p.N) + r16(NA * 4);
   t += r16((size_t)p.M * 32) + r16((size_t)p.M * 16) + r16((size_t)p.N * NB_NPOL * 4);
@@ -624,68 +816,115 @@ inline size_t nb_search_arena_wanted(const NbSearchPar& p)
   return t;
 }
 
-template <class Cta, typename T>
-NB_HD const T* nb_search_stage(Cta& cta, NbArena& ar, const T* src, size_t count)
-{
-  if (!src || count == 0) return src;
-  T* d = (T*)ar.take(count * sizeof(T));
-  if (!d) return src;
-  for (size_t q = cta.tid; q < count; q += cta.nthreads) d[q] = src[q];
-  return d;
-}
-
 template <class Cta, int NL>
 NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared* sh, unsigned char* arena, size_t arena_bytes)
 {
-  const NbSearchPar& p = a.p;
-  const int N = p.N, M = p.M, NA = N + M, S = p.S;
-  NbSearchCtx c;
-  c.p = &p, c.b = b, c.self = a.agent_id[b] - 1, c.NA = NA;
-  for (int k = 0; k < 6; k++) c.init[k] = a.init[(size_t)b * 6 + k];
-  c.goal[0] = a.goal[2 * b], c.goal[1] = a.goal[2 * b + 1];
-  const int grp = a.group ? a.group[b] : b;
-  c.hull_xy = a.hull_xy + (size_t)grp * N * NB_NPOL * NB_HMAX * 2;
-  c.hull_cnt = a.hull_cnt + (size_t)grp * N * NB_NPOL;
-  c.samp = a.samp + (size_t)grp * N * p.num_pol * (S + 1) * 2;
-  c.known = a.known + (size_t)b * N;
-  c.comb = a.comb + (a.comb_shared ? 0 : (size_t)b * p.nchild);
-  c.st_ptr = a.st_ptr, c.st_xy = a.st_xy, c.st_longest = a.st_longest;
-  c.ecx.N = N, c.ecx.M = M, c.ecx.self = c.self, c.ecx.cap = p.ecap, c.ecx.bp_max = p.bp_max;
-  c.ecx.pb = a.pb, c.ecx.strep = a.strep, c.ecx.bp_cnt = a.bp_cnt, c.ecx.bp_xy = a.bp_xy;
-  c.a_na = a.es.cnt[2 * b], c.a_nb = a.es.cnt[2 * b + 1];
-  c.a_alpha = a.es.alpha + (size_t)b * p.es_cap * 2, c.a_beta = a.es.beta + (size_t)b * p.es_cap;
-  c.a_bend = a.es.bend + (size_t)b * p.es_cap, c.a_active = a.es.active + (size_t)b * NA;
-  c.meta = a.nd_meta + (size_t)b * p.max_nodes;
-  c.kin = a.nd_kin + (size_t)b * p.max_nodes * NB_SEARCH_KIN;
-  c.alpha = a.nd_alpha + (size_t)b * p.max_nodes * p.ecap * 2;
-  c.beta = a.nd_beta + (size_t)b * p.max_nodes * p.ecap;
-  c.bend = a.nd_bend + (size_t)b * p.max_nodes * p.ecap;
-  c.hash = a.hash + (size_t)b * p.hcap;
-  c.ch_stride = nb_search_ch_stride(p);
-  NbArena ar;
-  ar.p = arena, ar.left = arena_bytes;
-  {  // priority 1: the children's scratch (crossing lists, working entanglement state); 2: the open list and
-     // its keys; 3: read-only per-agent inputs of the entanglement chain
+  // ---- thread 0 builds the shared context: parameters, per-agent pointers, shared-memory placement
+  if (cta.tid == 0)
+  {
+    sh->par = a.p;
+    const NbSearchPar& p = sh->par;
+    const int N = p.N, M = p.M, NA = N + M, S = p.S;
+    NbSearchCtx& c = sh->cx;
+    c.p = &sh->par, c.b = b, c.self = a.agent_id[b] - 1, c.NA = NA;
+    c.prof = a.prof ? a.prof + (size_t)b * 16 : nullptr;
+    for (int k = 0; k < 6; k++) c.init[k] = a.init[(size_t)b * 6 + k];
+    c.goal[0] = a.goal[2 * b], c.goal[1] = a.goal[2 * b + 1];
+    const int grp = a.group ? a.group[b] : b;
+    c.hull_xy = a.hull_xy + (size_t)grp * N * NB_NPOL * NB_HMAX * 2;
+    c.hull_cnt = a.hull_cnt + (size_t)grp * N * NB_NPOL;
+    c.samp = a.samp + (size_t)grp * N * p.num_pol * (S + 1) * 2;
+    c.known = a.known + (size_t)b * N;
+    c.comb = a.comb + (a.comb_shared ? 0 : (size_t)b * p.nchild);
+    c.st_ptr = a.st_ptr, c.st_xy = a.st_xy, c.st_longest = a.st_longest;
+    c.ecx.N = N, c.ecx.M = M, c.ecx.self = c.self, c.ecx.cap = p.ecap, c.ecx.bp_max = p.bp_max;
+    c.ecx.pb = a.pb, c.ecx.strep = a.strep, c.ecx.bp_cnt = a.bp_cnt, c.ecx.bp_xy = a.bp_xy;
+    c.a_na = a.es.cnt[2 * b], c.a_nb = a.es.cnt[2 * b + 1];
+    c.a_alpha = a.es.alpha + (size_t)b * p.es_cap * 2, c.a_beta = a.es.beta + (size_t)b * p.es_cap;
+    c.a_bend = a.es.bend + (size_t)b * p.es_cap, c.a_active = a.es.active + (size_t)b * NA;
+    c.meta = a.nd_meta + (size_t)b * p.max_nodes;
+    c.kin = a.nd_kin + (size_t)b * p.max_nodes * NB_SEARCH_KIN;
+    c.alpha = a.nd_alpha + (size_t)b * p.max_nodes * p.ecap * 2;
+    c.beta = a.nd_beta + (size_t)b * p.max_nodes * p.ecap;
+    c.bend = a.nd_bend + (size_t)b * p.max_nodes * p.ecap;
+    c.hash = a.hash + (size_t)b * p.hcap;
+    c.ch_stride = nb_search_ch_stride(p);
+    NbArena ar;
+    ar.p = arena, ar.left = arena_bytes;
+    // priority 1: the children's scratch (crossing lists, working entanglement state); 2: the open list and
+    // its keys; 3: read-only per-agent inputs of the entanglement chain (copied in by all threads below)
     int* ci = (int*)ar.take(((size_t)p.nchild * c.ch_stride + NA) * sizeof(int));
     c.ch_int = ci ? ci : a.ch_int + (size_t)b * (p.nchild * c.ch_stride + NA);
-    double* cd = (double*)ar.take((size_t)p.nchild * p.ecap * sizeof(double));
-    c.ch_dbl = cd ? cd : a.ch_dbl + (size_t)b * p.nchild * p.ecap;
+    double* cd = (double*)ar.take(nb_search_chd_stride(p) * sizeof(double));
+    c.ch_dbl = cd ? cd : a.ch_dbl + (size_t)b * nb_search_chd_stride(p);
+    c.base_sq = c.ch_dbl + (size_t)p.nchild * p.ecap;
     double* gh = (double*)ar.take((size_t)p.max_nodes * 2 * sizeof(double));
     c.gh = gh ? gh : a.gh_g + (size_t)b * p.max_nodes * 2;
     int* hp = (int*)ar.take((size_t)p.max_nodes * sizeof(int));
     c.heap = hp ? hp : a.heap_g + (size_t)b * p.max_nodes;
-    c.ecx.pb = nb_search_stage(cta, ar, c.ecx.pb, (size_t)N * 2);
-    c.ecx.bp_cnt = nb_search_stage(cta, ar, c.ecx.bp_cnt, (size_t)N);
-    c.ecx.bp_xy = nb_search_stage(cta, ar, c.ecx.bp_xy, (size_t)N * p.bp_max * 2);
-    c.known = nb_search_stage(cta, ar, c.known, (size_t)N);
-    c.a_active = nb_search_stage(cta, ar, c.a_active, (size_t)NA);
-    c.ecx.strep = nb_search_stage(cta, ar, c.ecx.strep, (size_t)M * 4);
-    c.st_longest = nb_search_stage(cta, ar, c.st_longest, (size_t)M * 2);
-    c.hull_cnt = nb_search_stage(cta, ar, c.hull_cnt, (size_t)N * NB_NPOL);
-    c.samp = nb_search_stage(cta, ar, c.samp, (size_t)N * p.num_pol * (S + 1) * 2);
+    c.par_act = c.ch_int + (size_t)p.nchild * c.ch_stride;
+    sh->stage_src[0] = c.ecx.pb, sh->stage_bytes[0] = (size_t)N * 16;
+    sh->stage_src[1] = c.ecx.bp_cnt, sh->stage_bytes[1] = (size_t)N * 4;
+    sh->stage_src[2] = c.ecx.bp_xy, sh->stage_bytes[2] = (size_t)N * p.bp_max * 16;
+    sh->stage_src[3] = c.known, sh->stage_bytes[3] = (size_t)N;
+    sh->stage_src[4] = c.a_active, sh->stage_bytes[4] = (size_t)NA * 4;
+    sh->stage_src[5] = c.ecx.strep, sh->stage_bytes[5] = (size_t)M * 32;
+    sh->stage_src[6] = c.st_longest, sh->stage_bytes[6] = (size_t)M * 16;
+    sh->stage_src[7] = c.hull_cnt, sh->stage_bytes[7] = (size_t)N * NB_NPOL * 4;
+    sh->stage_src[8] = c.samp, sh->stage_bytes[8] = (size_t)N * p.num_pol * (S + 1) * 16;
+    for (int k = 0; k < NB_SEARCH_NSTAGE; k++)
+      sh->stage_dst[k] = (sh->stage_src[k] && sh->stage_bytes[k]) ? ar.take(sh->stage_bytes[k]) : nullptr;
+    {  // goal hull of setUp (:215-220)
+      const double r = 0.5, gx = c.goal[0], gy = c.goal[1];
+      double* gq = sh->goal_hull;
+      gq[0] = gx + r, gq[1] = gy + r, gq[2] = gx + r, gq[3] = gy - r, gq[4] = gx - r, gq[5] = gy + r, gq[6] = gx - r, gq[7] = gy - r;
+    }
   }
-  c.par_act = c.ch_int + (size_t)p.nchild * c.ch_stride;
-  cta.sync();  // staged copies visible to every thread
+  cta.sync();
+  for (int k = 0; k < NB_SEARCH_NSTAGE; k++)
+  {
+    if (!sh->stage_dst[k]) continue;
+    const size_t nb = sh->stage_bytes[k];
+    if ((nb & 3) == 0)
+    {
+      const int* s4 = (const int*)sh->stage_src[k];
+      int* d4 = (int*)sh->stage_dst[k];
+      for (size_t q = cta.tid; q < nb / 4; q += cta.nthreads) d4[q] = s4[q];
+    }
+    else
+    {
+      const unsigned char* s1 = (const unsigned char*)sh->stage_src[k];
+      unsigned char* d1 = (unsigned char*)sh->stage_dst[k];
+      for (size_t q = cta.tid; q < nb; q += cta.nthreads) d1[q] = s1[q];
+    }
+  }
+  cta.sync();
+  if (cta.tid == 0)
+  {
+    NbSearchCtx& c = sh->cx;
+    void** d = sh->stage_dst;
+    if (d[0]) c.ecx.pb = (const double*)d[0];
+    if (d[1]) c.ecx.bp_cnt = (const int*)d[1];
+    if (d[2]) c.ecx.bp_xy = (const double*)d[2];
+    if (d[3]) c.known = (const uint8_t*)d[3];
+    if (d[4]) c.a_active = (const int*)d[4];
+    if (d[5]) c.ecx.strep = (const double*)d[5];
+    if (d[6]) c.st_longest = (const double*)d[6];
+    if (d[7]) c.hull_cnt = (const int*)d[7];
+    if (d[8]) c.samp = (const double*)d[8];
+  }
+  cta.sync();
+  const NbSearchPar& p = sh->par;
+  const NbSearchCtx& c = sh->cx;
+  const int N = p.N, M = p.M, NA = N + M;
+  for (int ag = cta.tid; ag < N; ag += cta.nthreads)
+  {  // squares around the bases (:1610-1612)
+    const double radius = 0.7, bx = c.ecx.pb[2 * ag], by = c.ecx.pb[2 * ag + 1];
+    double* sq = c.base_sq + 8 * ag;
+    sq[0] = bx + radius, sq[1] = by + radius, sq[2] = bx + radius, sq[3] = by - radius;
+    sq[4] = bx - radius, sq[5] = by - radius, sq[6] = bx - radius, sq[7] = by + radius;
+  }
+  NB_TICK_INIT
   NbSearchCtl& ctl = sh->ctl;
   Group<NL> g(cta.lane);
 
@@ -697,14 +936,10 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     c.hash[q] = z;
   }
   int occ = 0;
+  for (int o = cta.tid; o < N; o += cta.nthreads)
   {
-    const double r = 0.5, gx = c.goal[0], gy = c.goal[1];
-    const double ghull[8] = { gx + r, gy + r, gx + r, gy - r, gx - r, gy + r, gx - r, gy - r };
-    for (int o = cta.tid; o < N; o += cta.nthreads)
-    {
-      const int hn = nb_hull_count(c, o, p.num_pol - 1);
-      if (hn > 0 && nb_gjk_collision(c.hull_xy + ((size_t)(o * NB_NPOL + p.num_pol - 1) * NB_HMAX) * 2, hn, ghull, 4)) occ = 1;
-    }
+    const int hn = nb_hull_count(c, o, p.num_pol - 1);
+    if (hn > 0 && nb_gjk_collision(c.hull_xy + ((size_t)(o * NB_NPOL + p.num_pol - 1) * NB_HMAX) * 2, hn, sh->goal_hull, 4)) occ = 1;
   }
   occ = cta.any(occ);
   if (cta.tid == 0)
@@ -712,6 +947,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     ctl.done = 0, ctl.status = 2, ctl.cur = -1, ctl.best = -1, ctl.closest = -1, ctl.n_used = 0, ctl.heap_n = 0;
     ctl.pops = 0, ctl.ran_trigger = 0, ctl.goal_occupied = occ, ctl.first_new = 0, ctl.overflow = 0;
     ctl.smallest = DBL_MAX;
+    nb_search_build_tab(p, c.comb, sh->tab);
   }
   for (int q = cta.tid; q < NA; q += cta.nthreads) c.par_act[q] = c.a_active[q];
   cta.sync();
@@ -728,33 +964,27 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
   }
 
   int cur = -1;
+  if (cta.tid == 0)
+  {
+    for (int k = 0; k < NB_SEARCH_KIN; k++) sh->par_kin[k] = k < 6 ? c.init[k] : 0.0;
+    sh->par_index = 0, sh->par_g = 0.0, sh->par_na = c.a_na, sh->par_nb = c.a_nb;
+    sh->par_alpha = c.a_alpha, sh->par_beta = c.a_beta, sh->par_bend = c.a_bend;
+  }
+  cta.sync();
+  NB_TICK(6)
   for (;;)
   {
-    // ---- expandAndAddToQueue(cur)
-    double ist[6];
-    int par_index, par_na, par_nb;
-    double par_g;
-    const int *par_alpha, *par_bend;
-    const double* par_beta;
-    if (cur < 0)
-    {
-      for (int k = 0; k < 6; k++) ist[k] = c.init[k];
-      par_index = 0, par_g = 0.0, par_na = c.a_na, par_nb = c.a_nb;
-      par_alpha = c.a_alpha, par_beta = c.a_beta, par_bend = c.a_bend;
-    }
-    else
-    {
-      for (int k = 0; k < 6; k++) ist[k] = c.kin[(size_t)cur * NB_SEARCH_KIN + k];
-      const NbInt4 m = c.meta[cur];
-      par_index = m.y, par_na = m.w & 0xffff, par_nb = m.w >> 16;
-      par_g = c.gh[2 * cur];
-      par_alpha = c.alpha + (size_t)cur * p.ecap * 2, par_beta = c.beta + (size_t)cur * p.ecap;
-      par_bend = c.bend + (size_t)cur * p.ecap;
-    }
-    for (int ch = cta.warp; ch < p.nchild; ch += cta.nwarps)
-      nb_search_child<NL>(g, c, sh, cur, ch, ist, par_index, par_g, par_alpha, par_beta, par_bend, par_na, par_nb);
+    // ---- expandAndAddToQueue(cur): the parent was published in shared memory by thread 0
+    const int par_index = sh->par_index;
+    for (int ch = cta.warp; ch < p.nchild; ch += cta.nwarps) nb_search_child<NL>(g, c, sh, cur, ch);
     cta.sync();
+    NB_TICK(0)
+#if defined(__CUDA_ARCH__)
+    if (cta.warp == 0) nb_search_resolve_warp(c, sh, cur, par_index, cta.lane);
+#else
     if (cta.tid == 0) nb_search_resolve(c, sh, cur, par_index);
+#endif
+    NB_TICK(1)
     cta.sync();
     for (int ch = cta.warp; ch < p.nchild; ch += cta.nwarps)
     {  // accepted children: payload into the pool
@@ -778,6 +1008,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
       }
     }
     cta.sync();
+    NB_TICK(2)
 
     // ---- next node of the open list that survives the collision tests (:1642-1676)
     for (;;)
@@ -791,20 +1022,27 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
         else
         {
           ctl.pops++;
-          ctl.cur = nb_heap_pop(c, ctl.heap_n);
-          c.meta[ctl.cur].z = -1;
+          const int nc = nb_heap_pop(c, ctl.heap_n);
+          ctl.cur = nc;
+          const NbInt4 m = c.meta[nc];
+          c.meta[nc].z = -1;
+          for (int k = 0; k < NB_SEARCH_KIN; k++) sh->par_kin[k] = c.kin[(size_t)nc * NB_SEARCH_KIN + k];
+          nb_search_ctrl(p, sh->par_kin, sh->par_cps);
+          sh->par_index = m.y, sh->par_na = m.w & 0xffff, sh->par_nb = m.w >> 16, sh->par_g = c.gh[2 * nc];
+          sh->par_alpha = c.alpha + (size_t)nc * p.ecap * 2, sh->par_beta = c.beta + (size_t)nc * p.ecap;
+          sh->par_bend = c.bend + (size_t)nc * p.ecap;
         }
       }
+      NB_TICK(3)
       cta.sync();
       if (ctl.done) break;
       cur = ctl.cur;
-      double nk[NB_SEARCH_KIN], cps[8];
-      for (int k = 0; k < NB_SEARCH_KIN; k++) nk[k] = c.kin[(size_t)cur * NB_SEARCH_KIN + k];
-      const NbInt4 m = c.meta[cur];
-      nb_search_ctrl(p, nk, cps);
-      int hi = m.y > p.num_pol ? p.num_pol : m.y;
+      const double* nk = sh->par_kin;
+      const double* cps = sh->par_cps;
+      const int node_index = sh->par_index, node_na = sh->par_na;
+      int hi = node_index > p.num_pol ? p.num_pol : node_index;
       int hit = 0;
-      const double radius = 0.7, safe_dist = p.T * p.v_max * 2;
+      const double safe_dist = p.T * p.v_max * 2;
       for (int it = cta.tid; it < 2 * N + M && !hit; it += cta.nthreads)
       {
         if (it < N)
@@ -823,19 +1061,19 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
           if (ag == c.self) continue;
           const double bx = c.ecx.pb[2 * ag], by = c.ecx.pb[2 * ag + 1];
           if (nb_norm2(cps[0] - bx, cps[1] - by) > safe_dist) continue;
-          const double sq[8] = { bx + radius, by + radius, bx + radius, by - radius, bx - radius, by - radius, bx - radius, by + radius };
-          if (nb_gjk_collision(sq, 4, cps, 4)) hit = 1;
+          if (nb_gjk_collision(c.base_sq + 8 * ag, 4, cps, 4)) hit = 1;
         }
       }
       hit = cta.any(hit);
+      NB_TICK(4)
       if (hit) continue;
       // active_cases of the node: active_A - count_A + count_node
       for (int q = cta.tid; q < NA; q += cta.nthreads)
       {
         int v = c.a_active[q];
         for (int k = 0; k < c.a_na; k++) v -= (c.a_alpha[2 * k] == q + 1);
-        const int na = m.w & 0xffff;
-        const int* al = c.alpha + (size_t)cur * p.ecap * 2;
+        const int na = node_na;
+        const int* al = sh->par_alpha;
         for (int k = 0; k < na; k++) v += (al[2 * k] == q + 1);
         c.par_act[q] = v;
       }
@@ -849,7 +1087,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
         const double dist = nb_norm2(nk[0] - c.goal[0], nk[1] - c.goal[1]);
         const double dist_init = nb_norm2(nk[0] - c.init[0], nk[1] - c.init[1]);
         const double dcmp = ctl.goal_occupied ? dist * dist : dist_init;
-        const double dti = dcmp * (double)m.y;
+        const double dti = dcmp * (double)node_index;
         if (dti < ctl.smallest && !invalid)
         {
           ctl.smallest = dti;
@@ -858,6 +1096,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
         if (dist < p.goal_size && !invalid) ctl.done = 1, ctl.status = 1;
       }
       cta.sync();
+      NB_TICK(5)
       break;
     }
     if (ctl.done) break;
@@ -869,20 +1108,24 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     best = ctl.cur;
   else if (ctl.closest >= 0 && p.use_not_reaching)
     best = ctl.closest;
-  int n = 0;
-  int path[NB_NPOL];
-  if (best >= 0)
+  int* path = sh->path;
+  if (cta.tid == 0)
   {
-    for (int t = best; t >= 0; t = c.meta[t].x)
-    {
-      const int idx = c.meta[t].y;
-      if (idx <= p.num_pol)
+    int nn = 0;
+    if (best >= 0)
+      for (int t = best; t >= 0; t = c.meta[t].x)
       {
-        path[idx - 1] = t;
-        if (idx > n) n = idx;
+        const int idx = c.meta[t].y;
+        if (idx <= p.num_pol)
+        {
+          path[idx - 1] = t;
+          if (idx > nn) nn = idx;
+        }
       }
-    }
+    ctl.best = nn;
   }
+  cta.sync();
+  const int n = ctl.best;
   if (cta.tid == 0)
   {
     a.status[b] = ctl.status;

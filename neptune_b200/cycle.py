@@ -4,8 +4,9 @@ back end, ``:1641-1647`` post-check) and of the inter-agent exchange (ROS topic 
 ``neptune_ros.cpp:172-179, :434-480``) as ONE all-gather of committed-trajectory records per cycle.
 
 PyTorch is used for device memory, streams and ``torch.distributed`` only; all math runs in
-libneptune_b200.so through the C-ABI with device pointers.  The front end (the kinodynamic search that
-produces ``pwp_init`` / ``entStateVec``) is out of scope: its outputs are inputs here.
+libneptune_b200.so through the C-ABI with device pointers.  With ``front_end=True`` the kinodynamic search
+(``KinodynamicSearch::run``, ``neptune.cpp:1453``; K0, SURVEY 8f #1) runs on the device too and its ``pwp_init`` /
+``entStateVec`` feed the back end in place; otherwise they are inputs of the cycle.
 """
 from __future__ import annotations
 
@@ -53,16 +54,22 @@ def gather_records(local, world: int, group=None, sizes=None):
 class ReplanCycle:
     """Device-resident state and launch sequence of one rank."""
 
-    def __init__(self, par: Params, agents: np.ndarray, device, static=None, world: int = 1, group=None):
+    def __init__(self, par: Params, agents: np.ndarray, device, static=None, world: int = 1, group=None,
+                 front_end: bool = False):
         import torch
         self.torch = torch
+        self.front_end = front_end
         self.par, self.agents, self.world, self.group = par, np.asarray(agents), world, group
         self.dev = torch.device(device)
         self.B, self.N = len(agents), par.num_of_agents
         self.solver = capi.Solver(par, device=self.dev.index or 0)
         if par.num_of_static_obst:
-            st_ptr, st_xy, strep = static
+            st_ptr, st_xy, strep = static[:3]
             self.solver.set_static(st_ptr, st_xy, strep)
+            if front_end:
+                self.solver.set_static_longest(static[3])
+        if front_end:
+            self.solver.search_configure()
         B, N, S, cap, NA = self.B, self.N, par.num_sample_per_interval, par.ent_cap, par.NA
         f64, i32, u8, i64 = torch.float64, torch.int32, torch.uint8, torch.int64
 
@@ -79,6 +86,9 @@ class ReplanCycle:
             es_cnt=((B, 2), i32), es_alpha=((B, cap, 2), i32), es_beta=((B, cap), f64), es_bend=((B, cap), i32),
             es_active=((B, NA), i32), prev_pos=((B, N + 1, 2), f64), prev_pos_agent=((B, N, 2), f64), cur=((B, 2), f64),
             t_group=(B, f64), group=(B, i32), t_now=(B, f64))
+        if front_end:   # start state A, goal, initial z polynomial, order of the jerk samples
+            spec.update(fe_init=((B, 6), f64), fe_goal=((B, 2), f64), fe_coeffs_z=((B, NPOL, 4), f64),
+                        fe_comb=((B, par.a_star_samp_x ** 2), u8))
         self.layout, off = {}, 0
         for k, (shape, dt) in spec.items():
             shape = (shape,) if isinstance(shape, int) else tuple(shape)
@@ -97,6 +107,11 @@ class ReplanCycle:
             esC_cnt=z((B, 2), i32), esC_alpha=z((B, cap, 2), i32), esC_beta=z((B, cap), f64), esC_bend=z((B, cap), i32),
             esC_active=z((B, NA), i32),
             new_recs=z((B, REC), f64), new_pieces=z(B, i32))
+        if front_end:   # outputs of the search, laid out like the back end's inputs
+            self.o.update(fe_status=z(B, i32), fe_solved=z(B, i32), fe_n_int=z(B, i32), fe_coeff=z((B, 3, NPOL, 4), f64),
+                          fe_esv_cnt=z((B, NPOL + 1, 2), i32), fe_esv_alpha=z((B, NPOL + 1, cap, 2), i32),
+                          fe_esv_beta=z((B, NPOL + 1, cap), f64), fe_esv_bend=z((B, NPOL + 1, cap), i32),
+                          fe_esv_active=z((B, NPOL + 1, NA), i32), fe_stats=z((B, 4), i32), fe_cost=z(B, f64))
         self.G = 0
         # packed outputs (one D2H copy)
         ospec = dict(coeff_out=((B, 3, NPOL, 4), f64), obj=(B, f64), status=(B, i32), iters=((B, 2), i32),
@@ -155,7 +170,7 @@ class ReplanCycle:
     DELTA_T_STEPS = 2   # t_start - time_now in units of dc (deltaT_ of neptune.cpp:1236-1262 for the synthetic world)
     OUT_KEYS = ("coeff_out", "obj", "status", "iters", "entangled", "collide")
 
-    def host_inputs(self, scene) -> dict:
+    def host_inputs(self, scene, fe: dict | None = None) -> dict:
         """Pinned host copy of everything a cycle needs from the planner core / front end, laid out exactly
         like the packed device buffer.  Returns {"buf": pinned uint8 tensor, "G": groups, <name>: numpy views}."""
         torch = self.torch
@@ -171,6 +186,8 @@ class ReplanCycle:
                    es_active=scene.es0_active, prev_pos=scene.prev_pos, prev_pos_agent=scene.prev_pos_agent,
                    cur=np.ascontiguousarray(scene.state_A[:, 0, :2]), t_group=tg, group=inv.astype(np.int32),
                    t_now=np.asarray(scene.t_start, np.float64) - self.DELTA_T_STEPS * self.par.dc)
+        if self.front_end:   # neptune_b200.scenes.search_host_inputs(scene, seed)
+            src.update(fe_init=fe["init"], fe_goal=fe["goal"], fe_coeffs_z=fe["coeffs_z"], fe_comb=fe["comb"])
         buf = torch.zeros(self.in_bytes, dtype=torch.uint8)
         if torch.cuda.is_available():
             buf = buf.pin_memory()
@@ -284,14 +301,44 @@ class ReplanCycle:
             for k in ("cnt", "alpha", "beta", "bend", "active"):   # copy for entangleCheckGivenPwp (works on a local)
                 o["esC_" + k].copy_(o["esA_" + k])
         mark("predict")
+        n_int_t, coeff_t = d["n_int"], d["coeff_init"]
+        esv_t = (d["esv_cnt"], d["esv_alpha"], d["esv_active"])
+        if self.front_end:
+            # KinodynamicSearch::setUp + run (neptune.cpp:1450-1453) from entangle_state_A and the shared hulls /
+            # samples; pwp_init and entStateVec stay on the device for the back end (:1509-1517)
+            if par_streams:
+                main.wait_stream(sB)
+            sa = capi.NbSearchArgs()
+            sa.B, sa.space = B, DEV
+            sa.agent_id, sa.init, sa.goal, sa.coeffs_z = (d[k].data_ptr() for k in ("agent_id", "fe_init", "fe_goal", "fe_coeffs_z"))
+            sa.n_groups, sa.group = G, d["group"].data_ptr()
+            sa.hull_xy, sa.hull_cnt, sa.samp, sa.known = o["hull_xy_g"].data_ptr(), o["hull_cnt_g"].data_ptr(), o["samp_g"].data_ptr(), d["known"].data_ptr()
+            sa.es = esA
+            sa.bp_cnt, sa.bp_xy, sa.comb, sa.comb_shared = d["bp_cnt"].data_ptr(), d["bp_xy"].data_ptr(), d["fe_comb"].data_ptr(), 0
+            sa.status, sa.solved, sa.n_int, sa.coeff = (o[k].data_ptr() for k in ("fe_status", "fe_solved", "fe_n_int", "fe_coeff"))
+            esv = capi.NbEntState()
+            esv.cnt, esv.alpha, esv.beta, esv.bend, esv.active = (p(o["fe_esv_" + k]) for k in ("cnt", "alpha", "beta", "bend", "active"))
+            sa.esv = esv
+            sa.stats, sa.cost = o["fe_stats"].data_ptr(), o["fe_cost"].data_ptr()
+            chk(L.nb_search_batch(h, C.byref(sa), st), "nb_search_batch")
+            # "returning with no solution" (neptune.cpp:1473-1478): the replan is rejected below; the back end
+            # still gets a well-formed (host-provided) path for those agents so that the batch stays dense
+            ok = o["fe_solved"] > 0
+            n_int_t = torch.where(ok, o["fe_n_int"], d["n_int"])
+            coeff_t = torch.where(ok[:, None, None, None], o["fe_coeff"], d["coeff_init"])
+            esv_t = (torch.where(ok[:, None, None], o["fe_esv_cnt"], d["esv_cnt"]),
+                     torch.where(ok[:, None, None, None], o["fe_esv_alpha"], d["esv_alpha"]),
+                     torch.where(ok[:, None, None], o["fe_esv_active"], d["esv_active"]))
+            self._fe_keep = (n_int_t, coeff_t, esv_t)   # referenced by the captured graph
+            mark("front_end")
         a = capi.NbReplanArgs()
         a.B, a.space, a.n_hull_slots = B, DEV, self.N
-        a.agent_id, a.n_int, a.coeff_init = d["agent_id"].data_ptr(), d["n_int"].data_ptr(), d["coeff_init"].data_ptr()
+        a.agent_id, a.n_int, a.coeff_init = d["agent_id"].data_ptr(), n_int_t.data_ptr(), coeff_t.data_ptr()
         # shared-window mode: the lines kernel reads hull (group[b], j, i) directly (own slot / unknown empty)
         a.hull_ptr, a.hull_xy, a.hull_cnt = None, o["hull_xy_g"].data_ptr(), o["hull_cnt_g"].data_ptr()
         a.hull_nvert = G * self.N * NPOL * HS
         a.nih0, a.nih0_group, a.hull_known = o["nih0_g"].data_ptr(), d["group"].data_ptr(), d["known"].data_ptr()
-        a.esv_cnt, a.esv_alpha, a.esv_active = d["esv_cnt"].data_ptr(), d["esv_alpha"].data_ptr(), d["esv_active"].data_ptr()
+        a.esv_cnt, a.esv_alpha, a.esv_active = (t.data_ptr() for t in esv_t)
         a.bp_cnt, a.bp_xy = d["bp_cnt"].data_ptr(), d["bp_xy"].data_ptr()
         a.coeff_out, a.obj, a.status, a.iters = (o[k].data_ptr() for k in ("coeff_out", "obj", "status", "iters"))
         a.lines, a.line_ok = None, None
@@ -301,19 +348,21 @@ class ReplanCycle:
         if par_streams:
             main.wait_stream(sC)
             main.wait_stream(sB)
-        chk(L.nb_postcheck_hulls_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["group"]), p(o["hull_xy_g_l"]),
+        chk(L.nb_postcheck_hulls_batch(h, B, DEV, p(n_int_t), p(o["coeff_out"]), p(d["group"]), p(o["hull_xy_g_l"]),
                                        p(o["hull_cnt_g_l"]), p(d["late"]), p(o["collide"]), st), "nb_postcheck_hulls_batch")
         if self.par.enable_entangle_check:
             esC = capi.NbEntState()
             esC.cnt, esC.alpha, esC.beta, esC.bend, esC.active = (p(o["esC_" + k]) for k in ("cnt", "alpha", "beta", "bend", "active"))
             samp_ptr, shared = (p(o["samp_g_l"]), 1) if G == 1 else (p(o["samp_b"]), 0)
             chk(L.nb_entangle_check_batch(h, B, DEV, p(d["agent_id"]), p(d["known"]), p(d["bp_cnt"]), p(d["bp_xy"]), esC,
-                                          p(d["n_int"]), p(o["coeff_out"]), samp_ptr, shared, p(o["entangled"]), st),
+                                          p(n_int_t), p(o["coeff_out"]), samp_ptr, shared, p(o["entangled"]), st),
                 "nb_entangle_check_batch")
+        if self.front_end:   # no front-end solution: replanFull returned before the back end (neptune.cpp:1473-1478)
+            o["collide"].add_(1 - o["fe_solved"])
         mark("postcheck")
         # tail of replanFull (neptune.cpp:1685-1699): pwp_out = composePieceWisePol(time_now, dc, pwp_prev, pwp_now);
         # an agent whose replan was rejected keeps publishing its previous trajectory
-        chk(L.nb_commit_compose_batch(h, B, DEV, p(d["n_int"]), p(o["coeff_out"]), p(d["t_start"]), p(d["t_now"]),
+        chk(L.nb_commit_compose_batch(h, B, DEV, p(n_int_t), p(o["coeff_out"]), p(d["t_start"]), p(d["t_now"]),
                                       p(d["recs"]), p(d["agent_id"]), None, p(o["status"]), p(o["entangled"]),
                                       p(o["collide"]), p(o["new_recs"]), p(o["new_pieces"]), st),
             "nb_commit_compose_batch")

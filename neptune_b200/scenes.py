@@ -430,6 +430,24 @@ def make_scene(par: Params, seed: int, *, n_fixed: int | None = None, sync: bool
     return sc
 
 
+def search_host_inputs(sc: Scene, seed: int) -> dict:
+    """Per-agent inputs of the front-end search that do not come from other kernels: start state A, goal,
+    initial z polynomial (getInitialZPwp) and a seeded order of the jerk samples."""
+    from .search import jerk_order
+
+    par, b = sc.par, sc.batch
+    B = b.B
+    init = np.zeros((B, 6))
+    init[:, 0:2], init[:, 2:4], init[:, 4:6] = sc.state_A[:, 0, :2], sc.state_A[:, 1, :2], sc.state_A[:, 2, :2]
+    agents = b.agent_id - 1
+    coeffs_z = np.zeros((B, NPOL, 4))
+    for bi in range(B):
+        coeffs_z[bi, :par.num_pol] = initial_z_pwp(par, sc.state_A[bi, 0, 2], sc.state_A[bi, 1, 2], sc.state_A[bi, 2, 2],
+                                                   sc.goals[agents[bi], 2])
+    return dict(init=init, goal=np.ascontiguousarray(sc.goals[agents, :2]), coeffs_z=coeffs_z,
+                comb=jerk_order(par, seed, B))
+
+
 def make_search_batch(sc: Scene, seed: int, per_agent_order: bool = False):
     """Inputs of KinodynamicSearch::setUp / run for every planning agent of a scene built with
     ``group_hulls=True`` and an ``ent_backend`` (``neptune.cpp:1437-1453``)."""

@@ -224,7 +224,7 @@ extern "C" int emul_search_batch(const nb_params* par, const nb_search_params* s
   a.stats = u->stats, a.cost = u->cost;
   const size_t mn = (size_t)p.max_nodes, chs = (size_t)nb_search_ch_stride(p);
   std::vector<NbInt4> meta(mn), hash((size_t)p.hcap);
-  std::vector<double> kin(mn * NB_SEARCH_KIN), beta(mn * p.ecap), gh(mn * 2), chd((size_t)p.nchild * p.ecap);
+  std::vector<double> kin(mn * NB_SEARCH_KIN), beta(mn * p.ecap), gh(mn * 2), chd(nb_search_chd_stride(p));
   std::vector<int> alpha(mn * p.ecap * 2), bend(mn * p.ecap), heap(mn), chi((size_t)p.nchild * chs + NA);
   int err = 0;
   a.nd_meta = meta.data(), a.nd_kin = kin.data(), a.nd_alpha = alpha.data(), a.nd_beta = beta.data(), a.nd_bend = bend.data();
@@ -237,7 +237,7 @@ extern "C" int emul_search_batch(const nb_params* par, const nb_search_params* s
     ab.nd_meta -= (size_t)b * mn, ab.nd_kin -= (size_t)b * mn * NB_SEARCH_KIN, ab.nd_alpha -= (size_t)b * mn * p.ecap * 2;
     ab.nd_beta -= (size_t)b * mn * p.ecap, ab.nd_bend -= (size_t)b * mn * p.ecap, ab.hash -= (size_t)b * p.hcap;
     ab.heap_g -= (size_t)b * mn, ab.gh_g -= (size_t)b * mn * 2, ab.ch_int -= (size_t)b * (p.nchild * chs + NA);
-    ab.ch_dbl -= (size_t)b * p.nchild * p.ecap;
+    ab.ch_dbl -= (size_t)b * nb_search_chd_stride(p);
     EmulCta cta;
     nb_search_task<EmulCta, 1>(cta, ab, b, sh, nullptr, 0);
   }

@@ -263,3 +263,58 @@ def test_gpu_search_feeds_back_end(capi, oracle):
     assert np.array_equal(out_gpu.status, out_ref.status)
     assert np.abs(out_gpu.coeff_out - out_ref.coeff_out).max() <= 1e-6 * max(1.0, np.abs(out_ref.coeff_out).max())
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,seed,sync", [("obst8", 3003, False), ("grid64", 4004, True)])
+def test_gpu_cycle_with_front_end(capi, oracle, cfg, seed, sync):
+    """ReplanCycle(front_end=True): hulls -> predict -> search -> LPs + QP -> post-check -> commit on the device.
+    The search inside the cycle equals the oracle's search on the cycle's own (device-built, separately tested)
+    hulls, samples and entangle_state_A; the back end then equals the oracle's back end on the search's output;
+    agents without a front-end solution are rejected (they keep their previous record)."""
+    import torch
+    from neptune_b200.batch import ReplanBatch, ReplanResult
+    from neptune_b200.cycle import ReplanCycle
+    from neptune_b200.scenes import search_host_inputs
+    from neptune_b200.search import SearchBatch, static_longest_dist
+
+    par = config(cfg)
+    par.search_max_expansions = 200
+    M = par.num_of_static_obst
+    sc = make_scene(par, seed, sync=sync, ent_backend=OracleEntBackend(oracle))
+    strep = np.asarray(sc.strep, np.float64).reshape(M, 2, 2)
+    longest = static_longest_dist(sc.static_raw, strep) if M else np.zeros((0, 2))
+    dev = torch.device("cuda", 0)
+    cyc = ReplanCycle(par, np.arange(par.num_of_agents), dev, static=(sc.batch.st_ptr, sc.batch.st_xy, sc.strep, longest),
+                      front_end=True)
+    fe = search_host_inputs(sc, seed + 5)
+    hin = cyc.host_inputs(sc, fe)
+    cyc.upload(hin)
+    cyc.step()
+    torch.cuda.synchronize()
+    cyc.check_errors()
+    o = {k: v.cpu().numpy() for k, v in cyc.o.items() if hasattr(v, "cpu")}
+    sb = SearchBatch(par=par, agent_id=sc.batch.agent_id.copy(), init=fe["init"], goal=fe["goal"], coeffs_z=fe["coeffs_z"],
+                     group=hin["group"].copy(), hull_xy=o["hull_xy_g"], hull_cnt=o["hull_cnt_g"], samp=o["samp_g"],
+                     known=sc.known.copy(), es_cnt=o["esA_cnt"], es_alpha=o["esA_alpha"], es_beta=o["esA_beta"],
+                     es_bend=o["esA_bend"], es_active=o["esA_active"], bp_cnt=sc.batch.bp_cnt, bp_xy=sc.batch.bp_xy,
+                     comb=fe["comb"], st_ptr=sc.batch.st_ptr, st_xy=sc.batch.st_xy, strep=strep, st_longest=longest)
+    sb.validate()
+    ref = _oracle_search(oracle, sb)
+    for name in ("status", "solved", "n_int", "coeff", "esv_cnt", "esv_alpha", "esv_beta", "esv_bend", "esv_active", "stats", "cost"):
+        assert np.array_equal(getattr(ref, name), o["fe_" + name]), name
+    ok = ref.solved > 0
+    assert ok.any()
+    # the back end on the search's output
+    bt = sc.batch
+    bt.n_int[ok] = ref.n_int[ok]
+    bt.coeff_init[ok] = ref.coeff[ok]
+    bt.esv_cnt[ok], bt.esv_alpha[ok], bt.esv_active[ok] = ref.esv_cnt[ok], ref.esv_alpha[ok], ref.esv_active[ok]
+    out_ref = ReplanResult.empty(bt)
+    assert oracle.replan_batch(bt, out_ref, 4) == 0
+    assert np.array_equal(o["status"], out_ref.status)
+    assert np.abs(o["coeff_out"] - out_ref.coeff_out).max() <= 1e-6 * max(1.0, np.abs(out_ref.coeff_out).max())
+    assert (o["collide"][~ok] >= 1).all()
+    recs_in = capi.make_records(sc.committed)
+    assert np.array_equal(o["new_recs"][~ok], recs_in[bt.agent_id[~ok] - 1])
+    cyc.solver.close()

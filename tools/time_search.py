@@ -36,6 +36,19 @@ def main():
     print(f"{cfg}: B={sb.B} gpu search (host buffers, e2e) best {min(ts) * 1e3:.3f} ms; pops total {int(got.stats[:, 1].sum())} "
           f"max {int(got.stats[:, 1].max())}; nodes max {int(got.stats[:, 0].max())}; status {np.bincount(got.status, minlength=3).tolist()}")
     print(f"  per pop of the slowest agent: {min(ts) * 1e6 / max(1, int(got.stats[:, 1].max())):.2f} us")
+    import ctypes as C
+    capi.lib().nb_set_profiling(s.handle, 1)
+    got = s.search(sb)
+    pc = np.zeros((sb.B, 16), np.int64)
+    capi.lib().nb_search_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    assert capi.lib().nb_search_phase_cycles(s.handle, pc.ctypes.data, sb.B) == 0
+    capi.lib().nb_set_profiling(s.handle, 0)
+    slow = int(np.argmax(got.stats[:, 1]))
+    names = ["children", "resolve", "copy", "pop", "collide", "endpoint", "setup", "-"]
+    pops = max(1, int(got.stats[slow, 1]))
+    print("  cycles per pop (slowest agent): " + ", ".join(f"{n} {pc[slow, i] / pops:.0f}" for i, n in enumerate(names[:7])))
+    cn = ["primitive", "state copy", "chain", "key+lookup", "step geometry", "crossing tests", "automaton"]
+    print("  child 0, cycles per pop: " + ", ".join(f"{n} {pc[slow, 8 + i] / pops:.0f}" for i, n in enumerate(cn)))
     try:
         from oracle import oracle as orc
         ref = SearchResult.empty(sb)
