@@ -78,7 +78,7 @@ struct nb_handle
   int sprof_B = 0;
   double* d_st_longest = nullptr;
   DevBuf sprof;
-  DevBuf sin[20], sout[12], sw_meta, sw_kin, sw_alpha, sw_beta, sw_bend, sw_hash, sw_heap, sw_gh, sw_chi, sw_chd;
+  DevBuf sin[20], sout[12], sw_meta, sw_kin, sw_alpha, sw_beta, sw_bend, sw_hash, sw_heap, sw_gh, sw_ng, sw_chi, sw_chd, sw_fcode;
   int qp_smem_set = 0;
   int profiling = 0;
   cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -517,6 +517,7 @@ extern "C" void nb_destroy(nb_handle* h)
   for (auto& b : h->sout) b.release();
   h->sw_meta.release(), h->sw_kin.release(), h->sw_alpha.release(), h->sw_beta.release(), h->sw_bend.release();
   h->sprof.release();
+  h->sw_ng.release(), h->sw_fcode.release();
   h->sw_hash.release(), h->sw_heap.release(), h->sw_gh.release(), h->sw_chi.release(), h->sw_chd.release();
   delete h;
 }
@@ -1373,8 +1374,10 @@ extern "C" int nb_search_batch(nb_handle* h, const nb_search_args* u, void* stre
   // global homes of everything the kernel tries to keep in shared memory (used when it does not fit)
   bad |= h->sw_heap.ensure(B * mn * sizeof(int)) != 0;
   bad |= h->sw_gh.ensure(B * mn * 2 * sizeof(double)) != 0;
+  bad |= h->sw_ng.ensure(B * mn * sizeof(double)) != 0;
   bad |= h->sw_chi.ensure((size_t)B * (p.nchild * ch_stride + NA) * sizeof(int)) != 0;
   bad |= h->sw_chd.ensure((size_t)B * nb_search_chd_stride(p) * sizeof(double)) != 0;
+  bad |= h->sw_fcode.ensure((size_t)B * nb_search_fcode_bytes(p)) != 0;
   if (bad)
   {
     g_err = "cudaMalloc failed for the search workspace";
@@ -1382,7 +1385,8 @@ extern "C" int nb_search_batch(nb_handle* h, const nb_search_args* u, void* stre
   }
   a.nd_meta = (NbInt4*)h->sw_meta.p, a.nd_kin = (double*)h->sw_kin.p, a.nd_alpha = (int*)h->sw_alpha.p;
   a.nd_beta = (double*)h->sw_beta.p, a.nd_bend = (int*)h->sw_bend.p, a.hash = (NbInt4*)h->sw_hash.p;
-  a.heap_g = (int*)h->sw_heap.p, a.gh_g = (double*)h->sw_gh.p, a.ch_int = (int*)h->sw_chi.p, a.ch_dbl = (double*)h->sw_chd.p;
+  a.heap_g = (int*)h->sw_heap.p, a.gh_g = (double*)h->sw_gh.p, a.nd_g = (double*)h->sw_ng.p, a.ch_int = (int*)h->sw_chi.p, a.ch_dbl = (double*)h->sw_chd.p;
+  a.fcode_g = (uint8_t*)h->sw_fcode.p;
   a.err = (int*)h->err.p;
   a.prof = nullptr;
   if (h->profiling)

@@ -8,11 +8,24 @@
 
 static __host__ __device__ inline size_t nb_search_shared_bytes() { return (sizeof(NbSearchShared) + 15) & ~(size_t)15; }
 
+// 25 "child" warps (one per jerk sample) + 7 auxiliary warps that run the collision tests of the popped node
+// while the children are evaluated.  sync_children is a named barrier over the child warps only.
 struct NbCtaDev
 {
-  int tid, nthreads, warp, nwarps, lane;
+  int tid, nthreads, warp, nwarps, lane, aux_tid, aux_n;
+  bool child, aux;
   __device__ __forceinline__ void sync() const { __syncthreads(); }
   __device__ __forceinline__ int any(int p) const { return __syncthreads_or(p); }
+  __device__ __forceinline__ void sync_children() const
+  {
+    __syncwarp();  // bar.sync is the aligned form: the lanes of a warp must arrive together
+    asm volatile("bar.sync 1, %0;" ::"r"(NB_SEARCH_CHILD_THREADS) : "memory");
+  }
+  __device__ __forceinline__ void sync_aux() const
+  {
+    __syncwarp();
+    asm volatile("bar.sync 2, %0;" ::"r"(NB_SEARCH_THREADS - NB_SEARCH_CHILD_THREADS) : "memory");
+  }
 };
 
 __global__ void __launch_bounds__(NB_SEARCH_THREADS, 1) k_search(NbSearchArgs a, unsigned arena_bytes)
@@ -21,8 +34,10 @@ __global__ void __launch_bounds__(NB_SEARCH_THREADS, 1) k_search(NbSearchArgs a,
   NbSearchShared* sh = reinterpret_cast<NbSearchShared*>(nb_search_smem);
   unsigned char* arena = reinterpret_cast<unsigned char*>(nb_search_smem) + nb_search_shared_bytes();
   NbCtaDev cta;
-  cta.tid = threadIdx.x, cta.nthreads = blockDim.x, cta.warp = threadIdx.x >> 5, cta.nwarps = blockDim.x >> 5;
+  cta.tid = threadIdx.x, cta.nthreads = blockDim.x, cta.warp = threadIdx.x >> 5, cta.nwarps = NB_SEARCH_CHILD_THREADS >> 5;
   cta.lane = threadIdx.x & 31;
+  cta.child = threadIdx.x < NB_SEARCH_CHILD_THREADS, cta.aux = !cta.child;
+  cta.aux_tid = threadIdx.x - NB_SEARCH_CHILD_THREADS, cta.aux_n = NB_SEARCH_THREADS - NB_SEARCH_CHILD_THREADS;
   nb_search_task<NbCtaDev, 32>(cta, a, blockIdx.x, sh, arena_bytes ? arena : nullptr, arena_bytes);
 }
 

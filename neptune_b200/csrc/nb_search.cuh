@@ -98,9 +98,11 @@ struct NbSearchArgs
   int* nd_bend;      // [max_nodes][ecap]
   NbInt4* hash;      // [hcap]: ix, iy, iz, id + 1
   int* heap_g;       // [max_nodes] when the open list does not fit in shared memory
-  double* gh_g;      // [max_nodes][2]
+  double* gh_g;      // [max_nodes][2] (f = g + bias h, h): the keys CompareCost reads
+  double* nd_g;      // [max_nodes] g of every node
   int* ch_int;       // [nchild][2 tcap + 2 NA + 3 ecap] + [NA] parent active
-  double* ch_dbl;    // [nchild][ecap]
+  double* ch_dbl;    // [nchild][ecap + 18] + base squares
+  uint8_t* fcode_g;  // [num_pol][8][N] per agent
   int* err;
   long long* prof;   // optional [B][16]: SM cycles thread 0 spent per phase (measurement hook)
 };
@@ -120,7 +122,7 @@ inline void nb_search_fill_par(const nb_params& par, const nb_search_params& sp,
   p->out_cap = par.ent_cap, p->es_cap = par.ent_cap, p->bp_max = par.bp_max;
   p->hcap = 64;
   while (p->hcap < 2 * sp.max_nodes) p->hcap *= 2;
-  p->tcap = NA + 32;
+  p->tcap = NA;  // a crossing list longer than N + M entangles in any case (:844-848)
   for (int k = 0; k < 16; k++) p->Ainv[k] = cs.Ainv[k];
   for (int k = 0; k < 9; k++) p->V[k] = cs.V[k];
 }
@@ -142,25 +144,30 @@ struct NbArena
   }
 };
 
-// ints of scratch per child: toadd [2 tcap] | (id, old active) pairs [2 tcap] | active [NA] | alpha [2 ecap] | bend [ecap]
-NB_HD int nb_search_ch_stride(const NbSearchPar& p) { return 4 * p.tcap + (p.N + p.M) + 3 * p.ecap; }
+// ints of scratch per child: S crossing lists [S][2 tcap] | (id, old active) pairs [2 tcap] | active [NA] | alpha [2 ecap] | bend [ecap]
+NB_HD int nb_search_ch_stride(const NbSearchPar& p) { return (2 * p.S + 2) * p.tcap + (p.N + p.M) + 3 * p.ecap; }
 
 // doubles of scratch per agent: beta lists of the children, then the base squares [N][4][2]
-NB_HD size_t nb_search_chd_stride(const NbSearchPar& p) { return (size_t)p.nchild * p.ecap + (size_t)p.N * 8; }
+#define NB_SEARCH_PTS 20  // sample positions of a child: (S + 1) points, S <= 8, and the arc length in the last slot
+NB_HD size_t nb_search_chd_stride(const NbSearchPar& p) { return (size_t)p.nchild * (p.ecap + NB_SEARCH_PTS) + (size_t)p.N * 8; }
+NB_HD size_t nb_search_fcode_bytes(const NbSearchPar& p) { return (size_t)p.num_pol * 8 * p.N; }
 
 // one evaluated child of the node being expanded
 struct NbChildRec
 {
   int valid, ix, iy, iz, n_alpha, n_bend, accept_id, found, f_state, f_index;
-  double kin[NB_SEARCH_KIN], g, h;
+  double kin[NB_SEARCH_KIN], g, h, f;
+  int prim_ok, pad2;
 };
 
 struct NbSearchCtl
 {
   int done, status, cur, best, closest, n_used, heap_n, pops, ran_trigger, goal_occupied, first_new, overflow;
   int n_acc, acc[NB_SEARCH_MAXCHILD];  // children accepted so far in the expansion being resolved
+  int cmax;                            // measurement: slowest child chain of the current expansion (cycles)
+  int hit[2], invalid;                 // the popped node: collides (flag per iteration parity) / has an active case above 1
   double smallest;
-  int flag[NB_SEARCH_MAXCHILD][4];
+  int flag[NB_SEARCH_MAXCHILD][12];  // per child: result, n_alpha, n_bend, -, entries of the S crossing lists
 };
 
 // per-launch constants that depend only on the parameters and the jerk order (built once by thread 0 with the
@@ -203,11 +210,15 @@ struct NbSearchCtx
   int* bend;
   NbInt4* hash;
   int* heap;
-  double* gh;
+  double* gh;   // (f, h) per node
+  double* ng;   // g per node
   int* ch_int;
   double* ch_dbl;
   int* par_act;
   double* base_sq;  // [N][4][2] squares around the bases (collidesWithBases2d :1610-1612)
+  uint8_t* fcode;      // [num_pol][8][N] base-crossing code of every (window, step, single-bend tether), built once
+  int multi_bend;      // some known tether has bend points besides its base: the generic chain is used
+  double* hull_stage;  // [N][24][2] shared-memory copy of the hulls of one window (null: read them from global)
   int ch_stride;
   long long* prof;
 };
@@ -266,10 +277,11 @@ NB_HD int nb_hull_count(const NbSearchCtx& c, int o, int i)
 }
 
 // CompareCost (kinodynamic_search.hpp:163-179): true when l has lower priority than r
+// The cost g + bias h of a node is evaluated once, when (g, h) are written, and stored beside h: the same
+// double the reference recomputes in every comparison.
 NB_HD bool nb_cmp_cost(const NbSearchCtx& c, int l, int r)
 {
-  const double cl = c.gh[2 * l] + c.p->bias * c.gh[2 * l + 1];
-  const double cr = c.gh[2 * r] + c.p->bias * c.gh[2 * r + 1];
+  const double cl = c.gh[2 * l], cr = c.gh[2 * r];
   if (fabs(cl - cr) < 1e-5) return c.gh[2 * l + 1] > c.gh[2 * r + 1];
   return cl > cr;
 }
@@ -483,6 +495,174 @@ NB_HD int nb_search_entangles(const Group<NL>& g, const NbSearchCtx& c, NbEntSta
   return 0;
 }
 
+// ---- the same chain with the wedge products shared between steps and between children (single-bend tethers).
+// For a tether whose only bend point is its base b (nbend == 1, the normal case):
+//   * the base-side test of eu::entangleHSigToAddAgentInd (:1145-1180) uses wedge(pb_self, sample, b): it does not
+//     depend on the node at all, only on (window, step, tether) -> its outcome is the code c.fcode, built once per
+//     search: 0 no crossing, 1 crossing without entry (a < 0), 2 entry case 1, 3 entry case 0;
+//   * the robot-side test uses c1 = wedge(P_{s-1}, sample_{s-1}, b), c2 = wedge(P_s, sample_s, b): c2 of step s is c1
+//     of step s+1 (same operands, same operation), so S + 1 products serve S steps.  Same for static obstacles.
+// Values and their order of evaluation are those of the generic path, so the lists are bit-identical.
+// Phase 1 (lanes over tethers) fills one crossing list per step; phase 2 (lane 0) runs the list automaton.
+NB_HD uint8_t nb_search_fcode_one(const double* pb_self, const double* pik, const double* pik1, const double* b)
+{
+  double fb[2], fc[2];
+  const double f1 = nb_wedge(pb_self, pik, b, fb, fc);
+  const double f2 = nb_wedge(pb_self, pik1, b, nullptr, nullptr);
+  if (!nb_neg_product(f1, f2)) return 0;
+  const double a = nb_cross_ratio(fb, fc);
+  return a < 0 ? 1 : (a < 1 ? 2 : 3);
+}
+
+template <int NL>
+NB_HD int nb_search_entangles_fast(const Group<NL>& g, const NbSearchCtx& c, NbEntState& es, const double* kin, int index,
+                                   int* toadd, int* act_old, int* flag, double* arc_length, int ch, const double (*tt)[3],
+                                   double* pts)
+{
+  NB_CTICK_INIT
+  const NbSearchPar& p = *c.p;
+  const int N = p.N, M = p.M, NA = c.NA, S = p.S, num_pol = p.num_pol;
+  const double* cx = kin + 6;
+  const double* cy = kin + 10;
+  // sample positions P_0 .. P_S of this child (:808, :818-819)
+  if (g.lane == 0)
+  {
+    pts[0] = cx[3], pts[1] = cy[3];
+    for (int j = 1; j < S; j++)
+    {
+      const double t = tt[j][0], t2 = tt[j][1], t3 = tt[j][2];
+      pts[2 * j] = cx[0] * t3 + cx[1] * t2 + cx[2] * t + cx[3];
+      pts[2 * j + 1] = cy[0] * t3 + cy[1] * t2 + cy[2] * t + cy[3];
+    }
+    pts[2 * S] = kin[0], pts[2 * S + 1] = kin[1];
+    for (int j = 1; j <= S; j++) flag[3 + j] = 0;  // entries of the crossing list of step j (-1: over tcap)
+  }
+  g.sync();
+  NB_CTICK(12)
+  const int stride = num_pol * (S + 1) * 2;
+  const bool past = index > num_pol;
+  const double* samp0 = past ? c.samp + ((size_t)(num_pol - 1) * (S + 1) + S) * 2 : c.samp + (size_t)(index - 1) * (S + 1) * 2;
+  const uint8_t* fcode = c.fcode + (size_t)(past ? 0 : index - 1) * 8 * N;
+  int* nlist = flag + 4;
+  for (int base = 0; base < NA; base += NL)
+  {
+    const int j = base + g.lane;
+    const bool agent = j < N && j != c.self && c.known[j];
+    const bool stat = j >= N && j < NA;
+    // per step: number of entries (0..2) and their cases, 6 bits per step
+    unsigned long long code = 0;
+    if (agent || stat)
+    {
+      const double* b = agent ? c.ecx.bp_xy + (size_t)2 * p.bp_max * j : c.ecx.strep + 4 * (j - N);
+      const double* tgt0 = agent ? samp0 + (size_t)j * stride : c.ecx.strep + 4 * (j - N) + 2;
+      double ab[2], ac[2];
+      double prev = nb_wedge(pts, tgt0, b, ab, ac);
+      for (int s = 1; s <= S; s++)
+      {
+        const double* tgt = (agent && !past) ? tgt0 + 2 * s : tgt0;
+        double ab1[2], ac1[2];
+        const double cur = nb_wedge(pts + 2 * s, tgt, b, ab1, ac1);
+        int cnt = 0, e0 = 0, e1 = 0;
+        bool base_add = false;
+        if (agent && !past)
+        {
+          const int fcd = fcode[(size_t)(s - 1) * N + j];
+          if (fcd)
+          {
+            base_add = true;
+            if (fcd == 2) e0 = 1, cnt = 1;
+            if (fcd == 3) e0 = 0, cnt = 1;
+          }
+        }
+        if (nb_neg_product(prev, cur))
+        {
+          const double a = nb_cross_ratio(ab, ac);
+          int cs = -1;
+          if (agent)
+            cs = a < 0 ? 2 : (a < 1 ? 1 : (a >= 1 ? 0 : -1));
+          else if (!(a < 0))
+            cs = a < 1 ? 1 : 0;
+          if (cs >= 0)
+          {
+            if (cnt == 0)
+              e0 = cs;
+            else
+              e1 = cs;
+            cnt++;
+          }
+        }
+        if (base_add && cnt == 2 && e0 == e1) cnt = 0;  // the cancellation rule (:1221-1227)
+        code |= (unsigned long long)(cnt | (e0 << 2) | (e1 << 4)) << (6 * (s - 1));
+        prev = cur, ab[0] = ab1[0], ab[1] = ab1[1], ac[0] = ac1[0], ac[1] = ac1[1];
+      }
+    }
+    if (!g.any(code != 0)) continue;
+    for (int s = 1; s <= S; s++)
+    {
+      const int f6 = (int)((code >> (6 * (s - 1))) & 63);
+      const int cnt = f6 & 3;
+      if (!g.any(cnt > 0)) continue;
+      int total;
+      const int off = nb_excl_scan<NL>(g, cnt, total);
+      const int nl = nlist[s - 1];
+      const bool over = nl < 0 || nl + total > p.tcap;
+      if (!over)
+      {
+        int* out = toadd + (size_t)(s - 1) * 2 * p.tcap + 2 * (nl + off);
+        if (cnt > 0) out[0] = j + 1, out[1] = (f6 >> 2) & 3;
+        if (cnt > 1) out[2] = j + 1, out[3] = (f6 >> 4) & 3;
+      }
+      g.sync();
+      if (g.lane == 0) nlist[s - 1] = over ? -1 : nl + total;
+      g.sync();
+    }
+  }
+  g.sync();
+  NB_CTICK(13)
+  // phase 2: the list automaton, step by step (lane 0)
+  if (g.lane == 0)
+  {
+    int r = 0;
+    double arc = 0.0;
+    for (int s = 1; s <= S && r == 0; s++)
+    {
+      const double* pk = pts + 2 * (s - 1);
+      const double* pk1 = pts + 2 * s;
+      arc += nb_norm2(pk1[0] - pk[0], pk1[1] - pk[1]);
+      const int nadd = nlist[s - 1];
+      int* ta = toadd + (size_t)(s - 1) * 2 * p.tcap;
+      if (nadd < 0 || es.n_alpha + nadd > NA)
+        r = 1;  // :844-848
+      else
+      {
+        for (int i = 0; i < nadd; i++) act_old[2 * i] = ta[2 * i], act_old[2 * i + 1] = es.active[ta[2 * i] - 1];
+        if (nb_add_alpha_beta(ta, nadd, es, pk, c.ecx))
+          r = -1;
+        else
+        {
+          for (int i = 0; i < nadd; i++)
+          {
+            const int a = act_old[2 * i] - 1, was = act_old[2 * i + 1];
+            if (a >= N) continue;
+            if (was < 2 && es.active[a] >= 2) r = 1;
+            if (was >= 2 && es.active[a] > was) r = 1;
+          }
+          if (r == 0) nb_update_bend_pts(es, pk1, c.ecx);
+        }
+      }
+    }
+    if (r == 0 && nb_tether_length(c, es, pts + 2 * S) > p.tether) r = 1;  // :884-891
+    flag[0] = r, flag[1] = es.n_alpha, flag[2] = es.n_bend;
+    pts[NB_SEARCH_PTS - 1] = arc;
+  }
+  g.sync();
+  const int r = flag[0];
+  es.n_alpha = flag[1], es.n_bend = flag[2];
+  *arc_length = pts[NB_SEARCH_PTS - 1];
+  NB_CTICK(14)
+  return r;
+}
+
 NB_HD void nb_search_build_tab(const NbSearchPar& p, const uint8_t* comb, NbSearchTab& tb)
 {
   const double tau = p.T, j_max = p.j_max, j_min = -p.j_max;
@@ -579,22 +759,20 @@ NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchSha
   const double* par_beta = sh->par_beta;
   const NbSearchPar& p = *c.p;
   NbChildRec& rec = sh->rec[ch];
-  if (g.lane == 0) rec.valid = 0, rec.accept_id = -1;
-  double kin[NB_SEARCH_KIN];
   const bool root = cur < 0;
   NB_CTICK_INIT
-  const bool prim_ok = nb_search_primitive(c, sh->tab, ist, ch, root, kin);
-  NB_CTICK(8)
-  if (!prim_ok) return;
+  if (!rec.prim_ok) return;  // primitive evaluated by nb_search_primitives (one lane per child)
+  const double* kin = rec.kin;
+
   const int index = par_index + 1;
   int* ci = c.ch_int + (size_t)ch * c.ch_stride;
   int* toadd = ci;
-  int* act_old = ci + 2 * p.tcap;
+  int* act_old = ci + 2 * p.S * p.tcap;
   int* act = act_old + 2 * p.tcap;
   NbEntState es;
   es.alpha = act + c.NA;
   es.bend = es.alpha + 2 * p.ecap;
-  es.beta = c.ch_dbl + (size_t)ch * p.ecap;
+  es.beta = c.ch_dbl + (size_t)ch * (p.ecap + NB_SEARCH_PTS);
   es.active = act;
   es.n_alpha = par_na, es.n_bend = par_nb;
   for (int q = g.lane; q < par_na; q += NL)
@@ -609,7 +787,9 @@ NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchSha
   double arc = 0.0;
   if (p.enable_entangle)
   {
-    const int r = nb_search_entangles<NL>(g, c, es, kin, index, toadd, act_old, sh->ctl.flag[ch], &arc, ch, sh->tab.tt);
+    const int r = c.multi_bend ? nb_search_entangles<NL>(g, c, es, kin, index, toadd, act_old, sh->ctl.flag[ch], &arc, ch, sh->tab.tt)
+                               : nb_search_entangles_fast<NL>(g, c, es, kin, index, toadd, act_old, sh->ctl.flag[ch], &arc, ch, sh->tab.tt,
+                                                              es.beta + p.ecap);
     NB_CTICK(10)
     if (r < 0 && g.lane == 0) sh->ctl.overflow = 1;
     if (r != 0) return;
@@ -624,9 +804,9 @@ NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchSha
     rec.ix = nb_voxel_index(kin[0], p.voxel);
     rec.iy = nb_voxel_index(kin[1], p.voxel);
     rec.n_alpha = es.n_alpha, rec.n_bend = es.n_bend;
-    for (int k = 0; k < NB_SEARCH_KIN; k++) rec.kin[k] = kin[k];
     rec.g = sh->par_g + arc;
     rec.h = nb_norm2(kin[0] - c.goal[0], kin[1] - c.goal[1]) + 0.3 * (double)es.n_alpha + 1.0 * (double)es.n_bend;
+    rec.f = rec.g + p.bias * rec.h;
     // node-map lookup against the map as it is BEFORE this expansion (all children in parallel); the
     // sequential pass adds the siblings accepted ahead of this child
     rec.found = root ? -1 : nb_hash_find(c, rec.ix, rec.iy, rec.iz);
@@ -638,6 +818,9 @@ NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchSha
     rec.valid = 1;
   }
   NB_CTICK(11)
+#if defined(__CUDA_ARCH__)
+  if (c.prof && g.lane == 0) atomicMax(&sh->ctl.cmax, (int)(clock64() - ctick_));
+#endif
 }
 
 // the sequential half of expandAndAddToQueue: children in all_combinations_ order (one thread)
@@ -671,9 +854,9 @@ NB_HD void nb_search_resolve(const NbSearchCtx& c, NbSearchShared* sh, int cur, 
       {
         if (f_state == 1 && f_index == par_index + 1)
         {
-          if (rec.g + p.bias * rec.h < c.gh[2 * f] + p.bias * c.gh[2 * f + 1] && ctl.ran_trigger % 2 == 0)
+          if (rec.f < c.gh[2 * f] && ctl.ran_trigger % 2 == 0)
           {  // :1193-1205: kinematics replaced; entangle state, index and heap position kept
-            c.gh[2 * f] = rec.g, c.gh[2 * f + 1] = rec.h;
+            c.gh[2 * f] = rec.f, c.gh[2 * f + 1] = rec.h, c.ng[f] = rec.g;
             if (f >= ctl.first_new)
             {
               NbChildRec& sr = sh->rec[ctl.acc[f - ctl.first_new]];
@@ -693,7 +876,7 @@ NB_HD void nb_search_resolve(const NbSearchCtx& c, NbSearchShared* sh, int cur, 
     const int id = ctl.n_used;
     rec.accept_id = id;
     ctl.acc[ctl.n_acc++] = ch;
-    c.gh[2 * id] = rec.g, c.gh[2 * id + 1] = rec.h;
+    c.gh[2 * id] = rec.f, c.gh[2 * id + 1] = rec.h, c.ng[id] = rec.g;
     c.heap[ctl.heap_n++] = id;
     nb_heap_push_at(c, ctl.heap_n - 1, 0, id);
     nb_hash_insert(c, rec.ix, rec.iy, rec.iz, id);
@@ -716,7 +899,7 @@ __device__ __forceinline__ void nb_search_resolve_warp(const NbSearchCtx& c, NbS
   const int valid = has ? mine.valid : 0;
   const int ix = mine.ix, iy = mine.iy, iz = mine.iz;
   const int found = (valid && !root) ? mine.found : -1, fst = mine.f_state, fidx = mine.f_index;
-  const double gm = mine.g, hm = mine.h;
+  const double fm = mine.f;
   int n_used = ctl.n_used, heap_n = ctl.heap_n, ran = ctl.ran_trigger;
   const int first_new = n_used;
   int my_id = -1;
@@ -744,11 +927,11 @@ __device__ __forceinline__ void nb_search_resolve_warp(const NbSearchCtx& c, NbS
     {
       if (f_state == 1 && f_index == par_index + 1)
       {
-        const double gc = __shfl_sync(FULL, gm, ch), hc = __shfl_sync(FULL, hm, ch);
-        if (gc + p.bias * hc < c.gh[2 * f] + p.bias * c.gh[2 * f + 1] && ran % 2 == 0)
+        const double fc = __shfl_sync(FULL, fm, ch);
+        if (fc < c.gh[2 * f] && ran % 2 == 0)
         {  // :1193-1205: kinematics replaced; entangle state, index and heap position kept
           __syncwarp();
-          if (lane == 0) c.gh[2 * f] = gc, c.gh[2 * f + 1] = hc;
+          if (lane == 0) c.gh[2 * f] = fc, c.gh[2 * f + 1] = sh->rec[ch].h, c.ng[f] = sh->rec[ch].g;
           if (sib >= 0)
           {
             if (lane < NB_SEARCH_KIN) sh->rec[sib].kin[lane] = sh->rec[ch].kin[lane];
@@ -768,7 +951,7 @@ __device__ __forceinline__ void nb_search_resolve_warp(const NbSearchCtx& c, NbS
     if (lane == ch) my_id = id;
     if (lane == 0)
     {
-      c.gh[2 * id] = sh->rec[ch].g, c.gh[2 * id + 1] = sh->rec[ch].h;
+      c.gh[2 * id] = sh->rec[ch].f, c.gh[2 * id + 1] = sh->rec[ch].h, c.ng[id] = sh->rec[ch].g;
       c.heap[heap_n] = id;
       nb_heap_push_at(c, heap_n, 0, id);
     }
@@ -813,6 +996,7 @@ inline size_t nb_search_arena_wanted(const NbSearchPar& p)
   t += r16((size_t)p.N * 16) + r16((size_t)p.N * 4) + r16((size_t)p.N * p.bp_max * 16) + r16((size_t)p.N) + r16(NA * 4);
   t += r16((size_t)p.M * 32) + r16((size_t)p.M * 16) + r16((size_t)p.N * NB_NPOL * 4);
   t += r16((size_t)p.N * p.num_pol * (p.S + 1) * 16);
+  t += r16(nb_search_fcode_bytes(p)) + r16((size_t)p.N * NB_HMAX * 16);
   return t;
 }
 
@@ -848,6 +1032,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     c.beta = a.nd_beta + (size_t)b * p.max_nodes * p.ecap;
     c.bend = a.nd_bend + (size_t)b * p.max_nodes * p.ecap;
     c.hash = a.hash + (size_t)b * p.hcap;
+    c.ng = a.nd_g + (size_t)b * p.max_nodes;
     c.ch_stride = nb_search_ch_stride(p);
     NbArena ar;
     ar.p = arena, ar.left = arena_bytes;
@@ -857,7 +1042,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     c.ch_int = ci ? ci : a.ch_int + (size_t)b * (p.nchild * c.ch_stride + NA);
     double* cd = (double*)ar.take(nb_search_chd_stride(p) * sizeof(double));
     c.ch_dbl = cd ? cd : a.ch_dbl + (size_t)b * nb_search_chd_stride(p);
-    c.base_sq = c.ch_dbl + (size_t)p.nchild * p.ecap;
+    c.base_sq = c.ch_dbl + (size_t)p.nchild * (p.ecap + NB_SEARCH_PTS);
     double* gh = (double*)ar.take((size_t)p.max_nodes * 2 * sizeof(double));
     c.gh = gh ? gh : a.gh_g + (size_t)b * p.max_nodes * 2;
     int* hp = (int*)ar.take((size_t)p.max_nodes * sizeof(int));
@@ -874,6 +1059,10 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     sh->stage_src[8] = c.samp, sh->stage_bytes[8] = (size_t)N * p.num_pol * (S + 1) * 16;
     for (int k = 0; k < NB_SEARCH_NSTAGE; k++)
       sh->stage_dst[k] = (sh->stage_src[k] && sh->stage_bytes[k]) ? ar.take(sh->stage_bytes[k]) : nullptr;
+    uint8_t* fcd = (uint8_t*)ar.take(nb_search_fcode_bytes(p));
+    c.fcode = fcd ? fcd : a.fcode_g + (size_t)b * nb_search_fcode_bytes(p);
+    c.multi_bend = 0;
+    c.hull_stage = (double*)ar.take((size_t)N * NB_HMAX * 2 * sizeof(double));
     {  // goal hull of setUp (:215-220)
       const double r = 0.5, gx = c.goal[0], gy = c.goal[1];
       double* gq = sh->goal_hull;
@@ -924,6 +1113,30 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     sq[0] = bx + radius, sq[1] = by + radius, sq[2] = bx + radius, sq[3] = by - radius;
     sq[4] = bx - radius, sq[5] = by - radius, sq[6] = bx - radius, sq[7] = by + radius;
   }
+  {  // tethers with bend points besides the base use the generic chain; otherwise build the base-crossing codes
+    int mb = 0;
+    for (int j = cta.tid; j < N; j += cta.nthreads)
+      if (j != c.self && c.known[j] && c.ecx.bp_cnt[j] != 1) mb = 1;
+    mb = cta.any(mb);
+    if (cta.tid == 0) sh->cx.multi_bend = mb;
+    if (!mb && p.enable_entangle)
+    {
+      const int S = p.S;
+      const double* pb_self = c.ecx.pb + 2 * c.self;
+      for (int q = cta.tid; q < p.num_pol * S * N; q += cta.nthreads)
+      {
+        const int i = q / (S * N), s0 = (q / N) % S, j = q % N;
+        uint8_t code = 0;
+        if (j != c.self && c.known[j])
+        {
+          const double* sp = c.samp + ((size_t)(j * p.num_pol + i) * (S + 1) + s0) * 2;
+          code = nb_search_fcode_one(pb_self, sp, sp + 2, c.ecx.bp_xy + (size_t)2 * p.bp_max * j);
+        }
+        c.fcode[((size_t)i * 8 + s0) * N + j] = code;
+      }
+    }
+    cta.sync();
+  }
   NB_TICK_INIT
   NbSearchCtl& ctl = sh->ctl;
   Group<NL> g(cta.lane);
@@ -969,86 +1182,61 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     for (int k = 0; k < NB_SEARCH_KIN; k++) sh->par_kin[k] = k < 6 ? c.init[k] : 0.0;
     sh->par_index = 0, sh->par_g = 0.0, sh->par_na = c.a_na, sh->par_nb = c.a_nb;
     sh->par_alpha = c.a_alpha, sh->par_beta = c.a_beta, sh->par_bend = c.a_bend;
+    ctl.hit[0] = ctl.hit[1] = 0, ctl.invalid = 0, ctl.cmax = 0;
   }
   cta.sync();
   NB_TICK(6)
+  int par = 0;  // iteration parity: the collision flag of one iteration is cleared during the next
+  // Every iteration handles one popped node `cur` (the first one: the root).  The reference tests the node
+  // (:1669-1737) and then expands it (:1739); neither depends on the other, so here the child warps evaluate the
+  // 25 children SPECULATIVELY while the remaining warps run the collision tests of `cur`; the sequential pass that
+  // creates nodes runs only if `cur` survived, so the open list, the node numbering and the result are unchanged.
   for (;;)
   {
-    // ---- expandAndAddToQueue(cur): the parent was published in shared memory by thread 0
-    const int par_index = sh->par_index;
-    for (int ch = cta.warp; ch < p.nchild; ch += cta.nwarps) nb_search_child<NL>(g, c, sh, cur, ch);
-    cta.sync();
-    NB_TICK(0)
-#if defined(__CUDA_ARCH__)
-    if (cta.warp == 0) nb_search_resolve_warp(c, sh, cur, par_index, cta.lane);
-#else
-    if (cta.tid == 0) nb_search_resolve(c, sh, cur, par_index);
-#endif
-    NB_TICK(1)
-    cta.sync();
-    for (int ch = cta.warp; ch < p.nchild; ch += cta.nwarps)
-    {  // accepted children: payload into the pool
-      const NbChildRec& rec = sh->rec[ch];
-      const int id = rec.accept_id;
-      if (id < 0) continue;
-      const int* ci = c.ch_int + (size_t)ch * c.ch_stride + 4 * p.tcap + NA;
-      const double* cb = c.ch_dbl + (size_t)ch * p.ecap;
-      for (int q = g.lane; q < rec.n_alpha; q += NL)
-      {
-        c.alpha[((size_t)id * p.ecap + q) * 2] = ci[2 * q], c.alpha[((size_t)id * p.ecap + q) * 2 + 1] = ci[2 * q + 1];
-        c.beta[(size_t)id * p.ecap + q] = cb[q];
-      }
-      for (int q = g.lane; q < rec.n_bend; q += NL) c.bend[(size_t)id * p.ecap + q] = ci[2 * p.ecap + q];
-      for (int q = g.lane; q < NB_SEARCH_KIN; q += NL) c.kin[(size_t)id * NB_SEARCH_KIN + q] = rec.kin[q];
-      if (g.lane == 0)
-      {
-        NbInt4 m;
-        m.x = cur, m.y = par_index + 1, m.z = 1, m.w = rec.n_alpha | (rec.n_bend << 16);
-        c.meta[id] = m;
-      }
-    }
-    cta.sync();
-    NB_TICK(2)
-
-    // ---- next node of the open list that survives the collision tests (:1642-1676)
-    for (;;)
+    if (cta.child)
     {
-      if (cta.tid == 0)
+      // the 25 jerk primitives: one LANE per child (a warp per child would run the same scalar FP64 chain on 32
+      // lanes 25 times over and saturate the SM's FP64 pipe), then one WARP per child for the entanglement chain
+      for (int ch = cta.tid; ch < p.nchild; ch += cta.nthreads)
       {
-        if (ctl.heap_n == 0)
-          ctl.done = 1, ctl.status = 2;
-        else if (ctl.pops >= p.max_exp)
-          ctl.done = 1, ctl.status = 0;
-        else
-        {
-          ctl.pops++;
-          const int nc = nb_heap_pop(c, ctl.heap_n);
-          ctl.cur = nc;
-          const NbInt4 m = c.meta[nc];
-          c.meta[nc].z = -1;
-          for (int k = 0; k < NB_SEARCH_KIN; k++) sh->par_kin[k] = c.kin[(size_t)nc * NB_SEARCH_KIN + k];
-          nb_search_ctrl(p, sh->par_kin, sh->par_cps);
-          sh->par_index = m.y, sh->par_na = m.w & 0xffff, sh->par_nb = m.w >> 16, sh->par_g = c.gh[2 * nc];
-          sh->par_alpha = c.alpha + (size_t)nc * p.ecap * 2, sh->par_beta = c.beta + (size_t)nc * p.ecap;
-          sh->par_bend = c.bend + (size_t)nc * p.ecap;
-        }
+        NbChildRec& rec = sh->rec[ch];
+        double kin[NB_SEARCH_KIN];
+        rec.prim_ok = nb_search_primitive(c, sh->tab, sh->par_kin, ch, cur < 0, kin) ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < NB_SEARCH_KIN; k++) rec.kin[k] = kin[k];
+        rec.valid = 0, rec.accept_id = -1;
       }
-      NB_TICK(3)
-      cta.sync();
-      if (ctl.done) break;
-      cur = ctl.cur;
-      const double* nk = sh->par_kin;
+      cta.sync_children();
+      NB_TICK(7)
+      for (int ch = cta.warp; ch < p.nchild; ch += cta.nwarps) nb_search_child<NL>(g, c, sh, cur, ch);
+    }
+    if (cta.aux && cur >= 0)
+    {  // collidesWithObstacles2dSolve (:1514-1580) and collidesWithBases2d (:1583-1627) of the popped node
+#if defined(__CUDA_ARCH__)
+      const long long aux_t0 = clock64();
+#endif
       const double* cps = sh->par_cps;
-      const int node_index = sh->par_index, node_na = sh->par_na;
-      int hi = node_index > p.num_pol ? p.num_pol : node_index;
-      int hit = 0;
+      const int node_index = sh->par_index;
+      const int hi = node_index > p.num_pol ? p.num_pol : node_index;
       const double safe_dist = p.T * p.v_max * 2;
-      for (int it = cta.tid; it < 2 * N + M && !hit; it += cta.nthreads)
+      int hit = 0;
+      if (c.hull_stage)
+      {  // the hulls of this window, copied once (coalesced) so that the GJK loops read shared memory
+        for (int q = cta.aux_tid; q < N * NB_HMAX * 2; q += cta.aux_n)
+        {
+          const int o = q / (NB_HMAX * 2), r = q % (NB_HMAX * 2);
+          if (r < 2 * nb_hull_count(c, o, hi - 1)) c.hull_stage[q] = c.hull_xy[((size_t)(o * NB_NPOL + hi - 1) * NB_HMAX) * 2 + r];
+        }
+        cta.sync_aux();
+      }
+      for (int it = cta.aux_tid; it < 2 * N + M && !hit; it += cta.aux_n)
       {
         if (it < N)
-        {  // collidesWithObstacles2dSolve: other agents' hulls of window index-1
+        {  // other agents' hulls of window index-1
           const int hn = nb_hull_count(c, it, hi - 1);
-          if (hn > 0 && nb_gjk_collision(c.hull_xy + ((size_t)(it * NB_NPOL + hi - 1) * NB_HMAX) * 2, hn, cps, 4)) hit = 1;
+          const double* hv = c.hull_stage ? c.hull_stage + (size_t)it * NB_HMAX * 2
+                                          : c.hull_xy + ((size_t)(it * NB_NPOL + hi - 1) * NB_HMAX) * 2;
+          if (hn > 0 && nb_gjk_collision(hv, hn, cps, 4)) hit = 1;
         }
         else if (it < N + M)
         {  // static obstacles
@@ -1056,7 +1244,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
           if (nb_gjk_collision(c.st_xy + 2 * p0, (int)(p1 - p0), cps, 4)) hit = 1;
         }
         else if (p.enable_entangle)
-        {  // collidesWithBases2d
+        {  // bases of the other agents
           const int ag = it - N - M;
           if (ag == c.self) continue;
           const double bx = c.ecx.pb[2 * ag], by = c.ecx.pb[2 * ag + 1];
@@ -1064,42 +1252,122 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
           if (nb_gjk_collision(c.base_sq + 8 * ag, 4, cps, 4)) hit = 1;
         }
       }
-      hit = cta.any(hit);
-      NB_TICK(4)
-      if (hit) continue;
-      // active_cases of the node: active_A - count_A + count_node
+      if (hit) ctl.hit[par] = 1;
+#if defined(__CUDA_ARCH__)
+      if (c.prof && cta.aux_tid == 0) c.prof[8] += clock64() - aux_t0;
+#endif
+    }
+    cta.sync();
+    NB_TICK(0)
+#if defined(__CUDA_ARCH__)
+    if (c.prof && cta.tid == 0) c.prof[15] += ctl.cmax, ctl.cmax = 0;
+#endif
+    bool expand = true;
+    if (cur >= 0)
+    {
+      if (ctl.hit[par])
+        expand = false;  // constraintViolated: continue (:1673, :1676)
+      else
+      {
+        if (cta.tid == 0)
+        {  // closest safe node so far and the goal test (:1694-1737)
+          const double* nk = sh->par_kin;
+          const int invalid = ctl.invalid;
+          const double dist = nb_norm2(nk[0] - c.goal[0], nk[1] - c.goal[1]);
+          const double dist_init = nb_norm2(nk[0] - c.init[0], nk[1] - c.init[1]);
+          const double dcmp = ctl.goal_occupied ? dist * dist : dist_init;
+          const double dti = dcmp * (double)sh->par_index;
+          if (dti < ctl.smallest && !invalid)
+          {
+            ctl.smallest = dti;
+            ctl.closest = cur;
+          }
+          if (dist < p.goal_size && !invalid) ctl.done = 1, ctl.status = 1;
+        }
+        cta.sync();
+        if (ctl.done) break;
+      }
+    }
+    NB_TICK(5)
+    if (expand)
+    {
+      // ---- the sequential half of expandAndAddToQueue(cur), then the accepted children's payload
+      const int par_index = sh->par_index;
+#if defined(__CUDA_ARCH__)
+      if (cta.warp == 0) nb_search_resolve_warp(c, sh, cur, par_index, cta.lane);
+#else
+      if (cta.tid == 0) nb_search_resolve(c, sh, cur, par_index);
+#endif
+      NB_TICK(1)
+      cta.sync();
+      for (int ch = cta.warp; ch < p.nchild; ch += cta.nwarps)
+      {
+        const NbChildRec& rec = sh->rec[ch];
+        const int id = rec.accept_id;
+        if (id < 0) continue;
+        const int* ci = c.ch_int + (size_t)ch * c.ch_stride + (2 * p.S + 2) * p.tcap + NA;
+        const double* cb = c.ch_dbl + (size_t)ch * (p.ecap + NB_SEARCH_PTS);
+        for (int q = g.lane; q < rec.n_alpha; q += NL)
+        {
+          c.alpha[((size_t)id * p.ecap + q) * 2] = ci[2 * q], c.alpha[((size_t)id * p.ecap + q) * 2 + 1] = ci[2 * q + 1];
+          c.beta[(size_t)id * p.ecap + q] = cb[q];
+        }
+        for (int q = g.lane; q < rec.n_bend; q += NL) c.bend[(size_t)id * p.ecap + q] = ci[2 * p.ecap + q];
+        for (int q = g.lane; q < NB_SEARCH_KIN; q += NL) c.kin[(size_t)id * NB_SEARCH_KIN + q] = rec.kin[q];
+        if (g.lane == 0)
+        {
+          NbInt4 m;
+          m.x = cur, m.y = par_index + 1, m.z = 1, m.w = rec.n_alpha | (rec.n_bend << 16);
+          c.meta[id] = m;
+        }
+      }
+      cta.sync();
+      NB_TICK(2)
+    }
+
+    // ---- next node of the open list (:1642-1656), published for every thread
+    par ^= 1;
+    if (cta.tid == 0)
+    {
+      ctl.hit[par] = 0;
+      if (ctl.heap_n == 0)
+        ctl.done = 1, ctl.status = 2;
+      else if (ctl.pops >= p.max_exp)
+        ctl.done = 1, ctl.status = 0;
+      else
+      {
+        ctl.pops++;
+        const int nc = nb_heap_pop(c, ctl.heap_n);
+        ctl.cur = nc;
+        const NbInt4 m = c.meta[nc];
+        c.meta[nc].z = -1;
+        for (int k = 0; k < NB_SEARCH_KIN; k++) sh->par_kin[k] = c.kin[(size_t)nc * NB_SEARCH_KIN + k];
+        nb_search_ctrl(p, sh->par_kin, sh->par_cps);
+        sh->par_index = m.y, sh->par_na = m.w & 0xffff, sh->par_nb = m.w >> 16, sh->par_g = c.ng[nc];
+        sh->par_alpha = c.alpha + (size_t)nc * p.ecap * 2, sh->par_beta = c.beta + (size_t)nc * p.ecap;
+        sh->par_bend = c.bend + (size_t)nc * p.ecap;
+      }
+    }
+    NB_TICK(3)
+    cta.sync();
+    if (ctl.done) break;
+    cur = ctl.cur;
+    {  // active_cases of the node: active_A - count_A + count_node; valid_endpoint (:1694-1702)
+      const int na = sh->par_na;
+      const int* al = sh->par_alpha;
+      int invalid = 0;
       for (int q = cta.tid; q < NA; q += cta.nthreads)
       {
         int v = c.a_active[q];
         for (int k = 0; k < c.a_na; k++) v -= (c.a_alpha[2 * k] == q + 1);
-        const int na = node_na;
-        const int* al = sh->par_alpha;
         for (int k = 0; k < na; k++) v += (al[2 * k] == q + 1);
         c.par_act[q] = v;
+        if (q < N && v > 1) invalid = 1;
       }
-      cta.sync();
-      int invalid = 0;
-      for (int q = cta.tid; q < N; q += cta.nthreads)
-        if (c.par_act[q] > 1) invalid = 1;
       invalid = cta.any(invalid);
-      if (cta.tid == 0)
-      {
-        const double dist = nb_norm2(nk[0] - c.goal[0], nk[1] - c.goal[1]);
-        const double dist_init = nb_norm2(nk[0] - c.init[0], nk[1] - c.init[1]);
-        const double dcmp = ctl.goal_occupied ? dist * dist : dist_init;
-        const double dti = dcmp * (double)node_index;
-        if (dti < ctl.smallest && !invalid)
-        {
-          ctl.smallest = dti;
-          ctl.closest = cur;
-        }
-        if (dist < p.goal_size && !invalid) ctl.done = 1, ctl.status = 1;
-      }
-      cta.sync();
-      NB_TICK(5)
-      break;
+      if (cta.tid == 0) ctl.invalid = invalid;
     }
-    if (ctl.done) break;
+    NB_TICK(4)
   }
 
   // ---- choose the result (:1753-1826), recoverPwpOut (:521-553), recoverEntStateVector (:582-603)
@@ -1133,7 +1401,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     a.n_int[b] = n;
     a.stats[4 * b] = ctl.n_used, a.stats[4 * b + 1] = ctl.pops, a.stats[4 * b + 2] = best >= 0 ? c.meta[best].y : 0;
     a.stats[4 * b + 3] = ctl.goal_occupied;
-    a.cost[b] = best >= 0 ? c.gh[2 * best] : 0.0;
+    a.cost[b] = best >= 0 ? c.ng[best] : 0.0;
     if (ctl.overflow) *a.err = 5;
   }
   double* co = a.coeff + (size_t)b * 3 * NB_NPOL * 4;

@@ -4,7 +4,8 @@
 
 struct NbSearchArgs;
 
-#define NB_SEARCH_THREADS 800            // 25 warps: one per jerk sample of the 5x5 lattice
+#define NB_SEARCH_THREADS 1024           // 25 child warps (one per jerk sample of the 5x5 lattice) + 7 auxiliary warps
+#define NB_SEARCH_CHILD_THREADS 800
 #define NB_SEARCH_SMEM_MAX (220 * 1024)  // dynamic shared memory the search kernel may ask for
 
 // returns 0, or -1 with *err = CUDA error text

@@ -201,8 +201,11 @@ extern "C" int emul_compose(int B, const double* t, const uint8_t* has_prev, con
 // ---- K0 front-end search with one host lane: the same nb_search_task the device runs with 25 warps
 struct EmulCta
 {
-  int tid = 0, nthreads = 1, warp = 0, nwarps = 1, lane = 0;
+  int tid = 0, nthreads = 1, warp = 0, nwarps = 1, lane = 0, aux_tid = 0, aux_n = 1;
+  bool child = true, aux = true;
   void sync() const {}
+  void sync_children() const {}
+  void sync_aux() const {}
   int any(int p) const { return p; }
 };
 
@@ -224,11 +227,12 @@ extern "C" int emul_search_batch(const nb_params* par, const nb_search_params* s
   a.stats = u->stats, a.cost = u->cost;
   const size_t mn = (size_t)p.max_nodes, chs = (size_t)nb_search_ch_stride(p);
   std::vector<NbInt4> meta(mn), hash((size_t)p.hcap);
-  std::vector<double> kin(mn * NB_SEARCH_KIN), beta(mn * p.ecap), gh(mn * 2), chd(nb_search_chd_stride(p));
+  std::vector<double> kin(mn * NB_SEARCH_KIN), beta(mn * p.ecap), gh(mn * 2), ng(mn), chd(nb_search_chd_stride(p));
+  std::vector<uint8_t> fcode(nb_search_fcode_bytes(p));
   std::vector<int> alpha(mn * p.ecap * 2), bend(mn * p.ecap), heap(mn), chi((size_t)p.nchild * chs + NA);
   int err = 0;
   a.nd_meta = meta.data(), a.nd_kin = kin.data(), a.nd_alpha = alpha.data(), a.nd_beta = beta.data(), a.nd_bend = bend.data();
-  a.hash = hash.data(), a.heap_g = heap.data(), a.gh_g = gh.data(), a.ch_int = chi.data(), a.ch_dbl = chd.data(), a.err = &err;
+  a.hash = hash.data(), a.heap_g = heap.data(), a.gh_g = gh.data(), a.nd_g = ng.data(), a.ch_int = chi.data(), a.ch_dbl = chd.data(), a.fcode_g = fcode.data(), a.err = &err;
   NbSearchShared* sh = new NbSearchShared();
   // workspace pointers are per agent: run agents one at a time with b-relative offsets removed
   for (int b = 0; b < u->B; b++)
@@ -236,8 +240,9 @@ extern "C" int emul_search_batch(const nb_params* par, const nb_search_params* s
     NbSearchArgs ab = a;
     ab.nd_meta -= (size_t)b * mn, ab.nd_kin -= (size_t)b * mn * NB_SEARCH_KIN, ab.nd_alpha -= (size_t)b * mn * p.ecap * 2;
     ab.nd_beta -= (size_t)b * mn * p.ecap, ab.nd_bend -= (size_t)b * mn * p.ecap, ab.hash -= (size_t)b * p.hcap;
-    ab.heap_g -= (size_t)b * mn, ab.gh_g -= (size_t)b * mn * 2, ab.ch_int -= (size_t)b * (p.nchild * chs + NA);
+    ab.heap_g -= (size_t)b * mn, ab.gh_g -= (size_t)b * mn * 2, ab.nd_g -= (size_t)b * mn, ab.ch_int -= (size_t)b * (p.nchild * chs + NA);
     ab.ch_dbl -= (size_t)b * nb_search_chd_stride(p);
+    ab.fcode_g -= (size_t)b * nb_search_fcode_bytes(p);
     EmulCta cta;
     nb_search_task<EmulCta, 1>(cta, ab, b, sh, nullptr, 0);
   }

@@ -23,12 +23,19 @@ from tests.ent_backends import OracleEntBackend
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _batch(oracle, cfg, seed, per_agent_order=True, **mods):
+def _batch(oracle, cfg, seed, per_agent_order=True, multi_bend=False, **mods):
     par = config(cfg)
     for k, v in mods.items():
         setattr(par, k, v)
     sc = make_scene(par, seed, sync=False, ent_backend=OracleEntBackend(oracle), group_hulls=True)
-    return sc, make_search_batch(sc, seed + 1, per_agent_order=per_agent_order)
+    sb = make_search_batch(sc, seed + 1, per_agent_order=per_agent_order)
+    if multi_bend:   # some tethers already wrap around a contact point: bendPtsForAgents_[j] = [base, point]
+        sb.bp_cnt, sb.bp_xy = sb.bp_cnt.copy(), sb.bp_xy.copy()
+        rng = np.random.default_rng(seed)
+        for j in range(0, par.num_of_agents, 2):
+            sb.bp_cnt[j] = 2
+            sb.bp_xy[j, 1] = sb.bp_xy[j, 0] + rng.normal(0, 2.0, size=2)
+    return sc, sb
 
 
 def _oracle_search(oracle, sb, expect_rc=0):
@@ -168,6 +175,7 @@ def test_oracle_search_jerk_order_matters_only_through_ties(oracle):
     ("mtlp5", 2002, {}), ("mtlp5", 2004, dict(search_max_nodes=128)), ("obst8", 3003, {}),
     ("obst8", 3005, dict(search_max_expansions=1500)), ("grid64", 4004, dict(search_max_expansions=150)),
     ("mtlp5", 2006, dict(enable_entangle_check=False)), ("obst8", 3006, dict(use_not_reaching_soln=False)),
+    ("mtlp5", 2007, dict(multi_bend=True)), ("obst8", 3007, dict(multi_bend=True)),
 ])
 def test_emulated_kernel_matches_oracle(oracle, cfg, seed, mods):
     from tests.emul import emul
@@ -203,6 +211,8 @@ def _gpu_solver(capi, sc, sb):
     ("mtlp5", range(2012, 2014), dict(enable_entangle_check=False)),
     ("obst8", range(3012, 3014), dict(use_not_reaching_soln=False)),
     ("mtlp5", range(2014, 2015), dict(search_max_expansions=0)),
+    ("obst8", range(3014, 3016), dict(multi_bend=True)),   # generic chain (tethers with contact points)
+    ("grid64", range(4006, 4007), dict(multi_bend=True, search_max_expansions=150)),
 ])
 def test_gpu_search_matches_oracle(capi, oracle, cfg, seeds, mods):
     for seed in seeds:

@@ -44,11 +44,11 @@ def main():
     assert capi.lib().nb_search_phase_cycles(s.handle, pc.ctypes.data, sb.B) == 0
     capi.lib().nb_set_profiling(s.handle, 0)
     slow = int(np.argmax(got.stats[:, 1]))
-    names = ["children", "resolve", "copy", "pop", "collide", "endpoint", "setup", "-"]
+    names = ["chains||collide", "resolve", "copy", "pop", "active", "endpoint", "setup", "primitives"]
     pops = max(1, int(got.stats[slow, 1]))
-    print("  cycles per pop (slowest agent): " + ", ".join(f"{n} {pc[slow, i] / pops:.0f}" for i, n in enumerate(names[:7])))
-    cn = ["primitive", "state copy", "chain", "key+lookup", "step geometry", "crossing tests", "automaton"]
-    print("  child 0, cycles per pop: " + ", ".join(f"{n} {pc[slow, 8 + i] / pops:.0f}" for i, n in enumerate(cn)))
+    print("  cycles per pop (slowest agent): " + ", ".join(f"{n} {pc[slow, i] / pops:.0f}" for i, n in enumerate(names[:8])))
+    cn = ["(aux collide path)", "state copy", "chain", "key+lookup", "step geometry", "crossing tests", "automaton"]
+    print("  child 0, cycles per pop: " + ", ".join(f"{n} {pc[slow, 8 + i] / pops:.0f}" for i, n in enumerate(cn)) + f", slowest child {pc[slow, 15] / pops:.0f}")
     try:
         from oracle import oracle as orc
         ref = SearchResult.empty(sb)
