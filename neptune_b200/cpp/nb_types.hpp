@@ -109,3 +109,10 @@ struct ent_state  // entangle_utils.hpp:23-29
   std::vector<int> active_cases;
 };
 }  // namespace eu
+
+namespace mt
+{
+typedef Eigen::Matrix<double, 2, Eigen::Dynamic> PointsofInterval;       // mader_types.hpp:22
+typedef std::vector<PointsofInterval> SampledPointsofIntervals;           // :26, one 2 x (S+1) matrix per interval
+typedef std::vector<SampledPointsofIntervals> SampledPointsofCurves;      // :30, indexed by agent id - 1, empty = unknown
+}  // namespace mt

@@ -328,3 +328,52 @@ def test_gpu_cycle_with_front_end(capi, oracle, cfg, seed, sync):
     recs_in = capi.make_records(sc.committed)
     assert np.array_equal(o["new_recs"][~ok], recs_in[bt.agent_id[~ok] - 1])
     cyc.solver.close()
+
+
+@pytest.mark.gpu
+def test_cpp_shim_kinodynamic_search(capi, oracle, tmp_path):
+    """The C++ drop-in class KinodynamicSearch (neptune_b200/cpp/kinodynamic_search_b200.hpp) driven like
+    neptune.cpp drives the reference's (:88-97, :1421-1453, :1509-1510): same status, pieces and entStateVec as
+    the oracle, coefficients bit-exact."""
+    exe = os.path.join(ROOT, "tests", "cpp", "_build", "test_shim_search")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "_build/test_shim_search"], check=True, capture_output=True)
+    sc, sb = _batch(oracle, "mtlp5", 2002, per_agent_order=True)
+    par = sb.par
+    ref = _oracle_search(oracle, sb)
+    N, S, np_ = par.num_of_agents, par.num_sample_per_interval, par.num_pol
+    for b in range(sb.B):
+        g = int(sb.group[b])
+        lines = [f"{N} {int(sb.agent_id[b])} {np_} {S} {par.a_star_samp_x} {par.search_max_expansions} {par.search_max_nodes}",
+                 " ".join(repr(float(v)) for v in (par.T_span, par.x_min, par.x_max, par.y_min, par.y_max, par.v_max, par.a_max, par.j_max,
+                                                   par.a_star_fraction_voxel_size, par.a_star_bias, par.goal_radius, par.tetherLength))]
+        lines += [f"{float(q[0])!r} {float(q[1])!r}" for q in par.pb]
+        lines.append(" ".join(str(int(v)) for v in sb.comb[b]))
+        lines.append(" ".join(repr(float(v)) for v in list(sb.init[b]) + list(sb.goal[b])))
+        lines += [" ".join(repr(float(v)) for v in sb.coeffs_z[b, i]) for i in range(np_)]
+        for j in range(N):
+            kn = int(sb.known[b, j])
+            lines.append(str(kn))
+            if not kn:
+                continue
+            for i in range(np_):
+                lines.append(" ".join(f"{float(sb.samp[g, j, i, s, 0])!r} {float(sb.samp[g, j, i, s, 1])!r}" for s in range(S + 1)))
+            for i in range(np_):
+                nv = int(sb.hull_cnt[g, j, i])
+                lines.append(f"{nv} " + " ".join(f"{float(sb.hull_xy[g, j, i, v, 0])!r} {float(sb.hull_xy[g, j, i, v, 1])!r}" for v in range(nv)))
+        na, nb_ = int(sb.es_cnt[b, 0]), int(sb.es_cnt[b, 1])
+        lines.append(f"{na} {nb_}")
+        lines += [f"{int(sb.es_alpha[b, q, 0])} {int(sb.es_alpha[b, q, 1])} {float(sb.es_beta[b, q])!r}" for q in range(na)]
+        lines.append(" ".join(str(int(v)) for v in sb.es_bend[b, :nb_]))
+        lines.append(" ".join(str(int(v)) for v in sb.es_active[b, :N]))
+        path = tmp_path / f"search_{b}.txt"
+        path.write_text("\n".join(lines) + "\n")
+        out = subprocess.run([exe, str(path)], capture_output=True, text=True, check=True).stdout.split("\n")
+        ok, status, n = (int(v) for v in out[0].split())
+        assert ok == ref.solved[b] and status == ref.status[b] and n == ref.n_int[b]
+        co = np.array([[float(v) for v in out[1 + k].split()] for k in range(3 * n)]).reshape(n, 3, 4)
+        assert np.array_equal(co.transpose(1, 0, 2), ref.coeff[b, :, :n])
+        for i in range(n + 1 if ok else 0):
+            vals = [int(v) for v in out[1 + 3 * n + i].split()]
+            assert vals[0] == ref.esv_cnt[b, i, 0]
+            assert vals[1:] == ref.esv_alpha[b, i, :vals[0]].reshape(-1).tolist()
