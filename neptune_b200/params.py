@@ -116,7 +116,8 @@ def config(name: str) -> Params:
         p.x_min = p.y_min = -half
         p.x_max = p.y_max = half
     elif name == "grid1024":    # config 5: builder-defined 32x32 grid, 200 static squares
-        p = Params(num_of_agents=1024, num_of_static_obst=200, tetherLength=25.0, ent_cap=1232)  # >= N + M
+        p = Params(num_of_agents=1024, num_of_static_obst=200, tetherLength=25.0, ent_cap=1232,  # >= N + M
+                   search_ecap=96)   # crowded world: longer signature words per search node
         p.pb = grid_bases(32)
         half = 15.5 * 8.0 + 12.0
         p.x_min = p.y_min = -half

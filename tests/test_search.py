@@ -183,6 +183,24 @@ def test_emulated_kernel_matches_oracle(oracle, cfg, seed, mods):
     _assert_same(_oracle_search(oracle, sb), emul.search(sb))
 
 
+def _big_world_batch(oracle):
+    """Four agents of BASELINE.json configs[4] (1024 agents / 200 static obstacles): N + M = 1224 tethers, so the
+    per-agent working sets no longer fit in shared memory and the kernel runs from global memory / L2."""
+    par = config("grid1024")
+    par.search_max_expansions = 60
+    sc = make_scene(par, 5005, sync=True, ent_backend=OracleEntBackend(oracle), group_hulls=True,
+                    agents=np.array([0, 17, 500, 1023]), pack_hulls=False)
+    return sc, make_search_batch(sc, 5006, per_agent_order=True)
+
+
+def test_emulated_kernel_matches_oracle_1024_agents(oracle):
+    from tests.emul import emul
+    _, sb = _big_world_batch(oracle)
+    ref = _oracle_search(oracle, sb)
+    assert (ref.stats[:, 1] > 0).all()
+    _assert_same(ref, emul.search(sb))
+
+
 # ------------------------------------------------------------------------------------------ GPU
 @pytest.fixture(scope="module")
 def capi():
@@ -222,6 +240,14 @@ def test_gpu_search_matches_oracle(capi, oracle, cfg, seeds, mods):
         _assert_same(_oracle_search(oracle, sb), got)
         assert s.launch_count() >= 1
         s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_search_matches_oracle_1024_agents(capi, oracle):
+    sc, sb = _big_world_batch(oracle)
+    s = _gpu_solver(capi, sc, sb)
+    _assert_same(_oracle_search(oracle, sb), s.search(sb))
+    s.close()
 
 
 @pytest.mark.gpu
