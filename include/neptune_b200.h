@@ -266,6 +266,19 @@ int nb_entangle_predict_batch(nb_handle* h, int32_t B, int32_t space, const int3
                               const int32_t* bp_cnt, const double* bp_xy, nb_ent_state st, const double* prev_pos,
                               const double* prev_pos_agent, const double* cur, const double* samp0, void* stream);
 
+/* Replaces NeptuneRos::updateEntStateStaticObs (neptune_ros.cpp:798-850), one odometry tick of the online tracker
+ * that maintains entangle_state_, with the 9-argument eu::entangleHSigToAddAgentInd (entangle_utils.cpp:820-1127:
+ * a bend point of the other tether added or released since the last check).  SURVEY section 8(f) "next #3".
+ * state, prev_pos [B][N+1][2] (previousCheckingPos_) and prev_pos_agent [B][N][2] (previousCheckingPosAgent_; x < -900 =
+ * no message from that agent yet) are updated in place; latest_pos_agent [B][N][2] = latestCheckingPosAgent_;
+ * bp_*_prev = bendPtsForAgents_prev_ (the caller sets prev = current after the call, :818); elapsed_ms [B] replaces
+ * the wall-clock timer of :803-804.  result [B]: 0 updated, 1 skipped by the gate, -k where the reference prints
+ * "stop k" and calls exit(-1). */
+int nb_entangle_track_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const int32_t* bp_cnt,
+                            const double* bp_xy, const int32_t* bp_cnt_prev, const double* bp_xy_prev, nb_ent_state st,
+                            double* prev_pos, double* prev_pos_agent, const double* latest_pos_agent, const double* cur,
+                            const double* elapsed_ms, int32_t* result, void* stream);
+
 /* Replaces the per-interval chain of KinodynamicSearch::entanglesWithOtherAgents
  * (kinodynamic_search.cpp:707-895; list bound N+M, tether-length test excluded) that produces
  * entStateVec (recoverEntStateVector :582-603).  in: state at A.  out: states after 0..n intervals,

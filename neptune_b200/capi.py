@@ -287,6 +287,23 @@ class Solver:
                  _np(arrs[4]), _np(arrs[5]), _np(arrs[6]), _np(arrs[7]), None), "nb_entangle_predict_batch")
         return st
 
+    def entangle_track(self, agent_id, bp_cnt, bp_xy, bp_cnt_prev, bp_xy_prev, state: EntArrays, prev_pos, prev_pos_agent,
+                       latest, cur, elapsed_ms):
+        """``NeptuneRos::updateEntStateStaticObs`` (one tick of the online tracker): returns
+        (result [B], entangle_state_, previousCheckingPos_, previousCheckingPosAgent_), inputs untouched."""
+        st = state.copy()
+        pp, ppa = np.ascontiguousarray(prev_pos, np.float64).copy(), np.ascontiguousarray(prev_pos_agent, np.float64).copy()
+        arrs = [np.ascontiguousarray(agent_id, np.int32), np.ascontiguousarray(bp_cnt, np.int32),
+                np.ascontiguousarray(bp_xy, np.float64), np.ascontiguousarray(bp_cnt_prev, np.int32),
+                np.ascontiguousarray(bp_xy_prev, np.float64), np.ascontiguousarray(latest, np.float64),
+                np.ascontiguousarray(cur, np.float64), np.ascontiguousarray(elapsed_ms, np.float64)]
+        res = np.zeros(len(arrs[0]), np.int32)
+        f = lib().nb_entangle_track_batch
+        f.argtypes = [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, NbEntState, _P, _P, _P, _P, _P, _P, _P]
+        _check(f(self._h, len(arrs[0]), NB_HOST, _np(arrs[0]), _np(arrs[1]), _np(arrs[2]), _np(arrs[3]), _np(arrs[4]), st.c(),
+                 _np(pp), _np(ppa), _np(arrs[5]), _np(arrs[6]), _np(arrs[7]), _np(res), None), "nb_entangle_track_batch")
+        return res, st, pp, ppa
+
     def entangle_rollout(self, agent_id, known, bp_cnt, bp_xy, state: EntArrays, n_int, coeff, samp, samp_shared=False):
         """Front-end chain along a path: (done [B], states after 0..n intervals as EntArrays [B][9])."""
         B = len(agent_id)

@@ -941,6 +941,44 @@ extern "C" int nb_entangle_predict_batch(nb_handle* h, int32_t B, int32_t space,
   return ent_finish(h, space, st);
 }
 
+extern "C" int nb_entangle_track_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const int32_t* bp_cnt,
+                                       const double* bp_xy, const int32_t* bp_cnt_prev, const double* bp_xy_prev,
+                                       nb_ent_state stt, double* prev_pos, double* prev_pos_agent,
+                                       const double* latest_pos_agent, const double* cur, const double* elapsed_ms,
+                                       int32_t* result, void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->par.num_agents;
+  NbEntArgs a;
+  int rc;
+  if ((rc = ent_common(h, &a, 3, B, space, agent_id, nullptr, bp_cnt, bp_xy, st))) return rc;
+  nb_ent_state d;
+  if ((rc = stage_state_in(h, 4, space, stt, (size_t)B, st, &d, true))) return rc;
+  a.st = d;
+  const double *pp = nullptr, *ppa = nullptr;
+  if ((rc = stage_in(h, 9, space, (const double*)prev_pos, (size_t)B * (N + 1) * 2, st, &pp))) return rc;
+  if ((rc = stage_in(h, 10, space, (const double*)prev_pos_agent, (size_t)B * N * 2, st, &ppa))) return rc;
+  a.prev_pos_rw = (double*)pp, a.prev_pos_agent_rw = (double*)ppa;
+  if ((rc = stage_in(h, 11, space, cur, (size_t)B * 2, st, &a.cur))) return rc;
+  if ((rc = stage_in(h, 12, space, latest_pos_agent, (size_t)B * N * 2, st, &a.latest))) return rc;
+  if ((rc = stage_in(h, 13, space, bp_cnt_prev, (size_t)N, st, &a.bp_cnt_prev))) return rc;
+  if ((rc = stage_in(h, 14, space, bp_xy_prev, (size_t)N * h->par.bp_max * 2, st, &a.bp_xy_prev))) return rc;
+  if ((rc = stage_in(h, 15, space, elapsed_ms, (size_t)B, st, &a.elapsed_ms))) return rc;
+  if ((rc = stage_out(h, 7, space, result, (size_t)B, &a.result))) return rc;
+  if ((rc = ent_launch(h, a, B, st))) return rc;
+  if ((rc = state_out(h, space, stt, d, (size_t)B, st))) return rc;
+  if (space == NB_HOST)
+  {
+    NB_CUDA(cudaMemcpyAsync(prev_pos, pp, (size_t)B * (N + 1) * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(prev_pos_agent, ppa, (size_t)B * N * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(result, a.result, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  return ent_finish(h, space, st);
+}
+
 extern "C" int nb_entangle_rollout_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id,
                                          const uint8_t* known, const int32_t* bp_cnt, const double* bp_xy,
                                          nb_ent_state in, const int32_t* n_int, const double* coeff, const double* samp,

@@ -22,6 +22,17 @@
 #define NB_NFEAT_AX 64   // features per axis: 8 intervals x (4 pos CP + 3 vel CP + 1 acc)
 #define NB_SEP_EPS 1e-9
 
+// explicitly rounded FP64 operations: no FMA contraction where a sign or a comparison decides an integer result
+#if defined(__CUDA_ARCH__)
+#define NB_MUL(a, b) __dmul_rn((a), (b))
+#define NB_ADD(a, b) __dadd_rn((a), (b))
+#define NB_SUB(a, b) __dsub_rn((a), (b))
+#else
+#define NB_MUL(a, b) ((a) * (b))
+#define NB_ADD(a, b) ((a) + (b))
+#define NB_SUB(a, b) ((a) - (b))
+#endif
+
 // ---------------------------------------------------------------- thread-group abstraction
 // NL = 1   : host emulation (one lane runs every phase sequentially)
 // NL = 32  : one warp (sync = __syncwarp, reductions by shuffles)

@@ -145,16 +145,18 @@ NB_HD int nb_hsig_agent(int* loc, const double* pk, const double* pk1, const dou
 // Same function without a per-thread entry buffer: the entries go straight to `out` (pairs) when out != nullptr,
 // otherwise they are only counted; the last two entries stay in registers for the cancellation rule (:1221-1227).
 // nb_collect_toadd calls it twice (count, then write at the scanned offset) so no thread keeps a stack array.
+// limit: entries the caller reserved room for (the final count of the counting pass): the cancellation rule drops
+// the LAST two entries, so on the writing pass everything from index `limit` on must not be stored.
 NB_HD int nb_hsig_agent_stream(int* out, const double* pk, const double* pk1, const double* pik, const double* pik1,
-                               const double* pb_self, const double* bend, int nbend, int agent_id)
+                               const double* pb_self, const double* bend, int nbend, int agent_id, int limit)
 {
   int nadd = 0, last_cs = -1, prev_cs = -2;  // entries all carry agent_id: only the case numbers can differ
   bool base_add = false;
-#define NB_HSIG_PUSH(cs_)                                   \
-  {                                                         \
-    if (out) out[2 * nadd] = agent_id, out[2 * nadd + 1] = (cs_); \
-    prev_cs = last_cs, last_cs = (cs_);                     \
-    nadd++;                                                 \
+#define NB_HSIG_PUSH(cs_)                                                   \
+  {                                                                         \
+    if (out && nadd < limit) out[2 * nadd] = agent_id, out[2 * nadd + 1] = (cs_); \
+    prev_cs = last_cs, last_cs = (cs_);                                     \
+    nadd++;                                                                 \
   }
   for (int i = 0; i < nbend; i++)
   {
@@ -198,6 +200,184 @@ NB_HD int nb_hsig_agent_stream(int* out, const double* pk, const double* pk1, co
         NB_HSIG_PUSH(1)
       else if (a >= 1 && i == 0)
         NB_HSIG_PUSH(0)
+    }
+  }
+#undef NB_HSIG_PUSH
+  if (base_add && nadd >= 2 && last_cs == prev_cs) nadd -= 2;
+  return nadd;
+}
+
+// eu::entangleHSigToAddAgentInd, 9-arg (:820-1127): the online tracker's form, aware of a bend point of the other
+// tether having been added or released since the last check.  Streams its entries like nb_hsig_agent_stream.
+// *stop = k where the reference prints "stop k" and calls exit(-1) (:917, :981, :1073, :1107).
+NB_HD int nb_hsig_agent9_stream(int* out, const double* pk, const double* pk1, const double* pik, const double* pik1,
+                                const double* pb_self, const double* bend, int nbend, const double* prev, int nprev,
+                                int agent_id, int* stop, int limit)
+{
+  if (nprev == nbend) return nb_hsig_agent_stream(out, pk, pk1, pik, pik1, pb_self, bend, nbend, agent_id, limit);
+  if (nbend == 0 || nprev == 0) return 0;  // "bendpts empty!" (:833-836)
+  int nadd = 0, last_cs = -1, prev_cs = -2;
+  bool base_add = false;
+#define NB_HSIG_PUSH(cs_)                                                         \
+  {                                                                               \
+    if (out && nadd < limit) out[2 * nadd] = agent_id, out[2 * nadd + 1] = (cs_); \
+    prev_cs = last_cs, last_cs = (cs_);                                           \
+    nadd++;                                                                       \
+  }
+  const double* pback = prev + 2 * (nprev - 1);
+  if (nbend < nprev)
+  {  // released from a bend point (:837-986)
+    const double* pback2 = prev + 2 * (nprev - 2);
+    for (int i = 0; i < nbend; i++)
+    {
+      double ab[2], ac[2], abp[2] = { 0, 0 }, acp[2] = { 0, 0 }, c1, c2, c1p = 0.0;
+      const double* bi = bend + 2 * i;
+      const bool last = (i == nbend - 1);
+      if (!last)
+      {
+        c1 = nb_wedge(pk, bend + 2 * (i + 1), bi, ab, ac);
+        c2 = nb_wedge(pk1, bend + 2 * (i + 1), bi, nullptr, nullptr);
+      }
+      else
+      {
+        c1 = nb_wedge(pk, pik, pback, ab, ac);
+        c2 = nb_wedge(pk1, pik1, bi, nullptr, nullptr);
+        c1p = nb_wedge(pk, pback, pback2, abp, acp);
+      }
+      if (last)
+      {
+        double fb[2], fc[2];
+        const double f1 = nb_wedge(pb_self, pik, pback, nullptr, nullptr);
+        const double f2 = nb_wedge(pb_self, pik1, bi, fb, fc);
+        double f1p = 0.0;
+        if (i == 0) f1p = nb_wedge(pb_self, pback, pback2, nullptr, nullptr);
+        if (nb_neg_product(f1, f2))
+        {
+          const double a = nb_cross_ratio(fb, fc);
+          if (a < 0)
+          {
+          }
+          else if (a < 1)
+            NB_HSIG_PUSH(1)
+          base_add = true;
+        }
+        if (i == 0 && nb_neg_product(f1p, f2))
+        {
+          const double a = nb_cross_ratio(fb, fc);
+          if (a < 0)
+          {
+          }
+          else if (a < 1)
+          {
+          }
+          else
+          {
+            NB_HSIG_PUSH(0)
+            *stop = 4;
+          }
+          base_add = true;
+        }
+      }
+      bool added_inbtw = false;
+      if (nb_neg_product(c1, c2))
+      {
+        const double a = nb_cross_ratio(ab, ac);
+        if (a < 0)
+        {
+          NB_HSIG_PUSH(i + 2)
+          added_inbtw = true;
+        }
+        else if (a < 1 && last)
+          NB_HSIG_PUSH(1)
+      }
+      if (last && nb_neg_product(c1p, c2))
+      {
+        const double a = nb_cross_ratio(abp, acp);
+        if (a < 0 && !added_inbtw)
+          NB_HSIG_PUSH(i + 2)
+        else if (a < 1 && last)
+        {
+        }
+        else if (a >= 1 && i == 0)
+        {
+          NB_HSIG_PUSH(0)
+          *stop = 3;
+        }
+      }
+    }
+  }
+  else
+  {  // a bend point was added (:987-1116)
+    for (int i = 0; i < nbend; i++)
+    {
+      double ab[2], ac[2], c1, c2;
+      const double* bi = bend + 2 * i;
+      if (i == nbend - 1)
+      {
+        c1 = nb_wedge(pk, pik, pback, nullptr, nullptr);
+        c2 = nb_wedge(pk1, pik1, bi, ab, ac);
+      }
+      else if (i == nbend - 2)
+      {
+        c1 = nb_wedge(pk, pik, pback, nullptr, nullptr);
+        c2 = nb_wedge(pk1, bend + 2 * (i + 1), bi, ab, ac);
+      }
+      else
+      {
+        c1 = nb_wedge(pk, bend + 2 * (i + 1), bi, ab, ac);
+        c2 = nb_wedge(pk1, bend + 2 * (i + 1), bi, nullptr, nullptr);
+      }
+      if (i == nbend - 1)
+      {
+        double fb[2], fc[2];
+        const double f1 = nb_wedge(pb_self, pik, pback, nullptr, nullptr);
+        const double f2 = nb_wedge(pb_self, pik1, bi, fb, fc);
+        if (nb_neg_product(f1, f2))
+        {
+          const double a = nb_cross_ratio(fb, fc);
+          if (a < 0)
+          {
+          }
+          else if (a < 1)
+            NB_HSIG_PUSH(1)
+          base_add = true;
+        }
+      }
+      if (i == 0 && nbend == 2)
+      {
+        double fb[2], fc[2];
+        const double f1 = nb_wedge(pb_self, pik, pback, nullptr, nullptr);
+        const double f2 = nb_wedge(pb_self, bend + 2 * (i + 1), bi, fb, fc);
+        if (nb_neg_product(f1, f2))
+        {
+          const double a = nb_cross_ratio(fb, fc);
+          if (a < 0)
+          {
+          }
+          else if (a < 1)
+          {
+          }
+          else
+          {
+            NB_HSIG_PUSH(0)
+            *stop = 2;
+          }
+          base_add = true;
+        }
+      }
+      if (nb_neg_product(c1, c2))
+      {
+        const double a = nb_cross_ratio(ab, ac);
+        if (a < 0)
+          NB_HSIG_PUSH(i + 2)
+        else if (a < 1 && i == nbend - 1)
+          NB_HSIG_PUSH(1)
+        else if (a >= 1 && i == 0)
+        {
+          NB_HSIG_PUSH(0)
+          *stop = 1;
+        }
+      }
     }
   }
 #undef NB_HSIG_PUSH
@@ -262,7 +442,7 @@ NB_HD int nb_collect_toadd(const Group<NL>& g, const NbEntCtx& cx, const double*
       nb = cx.bp_cnt[j];
       if (nb > NB_ENT_LOCAL - 2) nb = NB_ENT_LOCAL - 2;
       cnt = nb_hsig_agent_stream(nullptr, pk_agents ? pk_agents + 2 * j : pk, pk1, pik_all + (size_t)j * pik_stride,
-                                 pik1_all + (size_t)j * pik1_stride, pb_self, cx.bp_xy + (size_t)2 * cx.bp_max * j, nb, j + 1);
+                                 pik1_all + (size_t)j * pik1_stride, pb_self, cx.bp_xy + (size_t)2 * cx.bp_max * j, nb, j + 1, 0);
     }
     else if (j >= cx.N && j < cx.N + cx.M)
       cnt = nb_hsig_static_one(st, pk, pk1, cx.strep + 4 * (j - cx.N), j + 1);
@@ -275,11 +455,79 @@ NB_HD int nb_collect_toadd(const Group<NL>& g, const NbEntCtx& cx, const double*
       int* out = toadd + 2 * (nadd + off);
       if (agent)
         nb_hsig_agent_stream(out, pk_agents ? pk_agents + 2 * j : pk, pk1, pik_all + (size_t)j * pik_stride,
-                             pik1_all + (size_t)j * pik1_stride, pb_self, cx.bp_xy + (size_t)2 * cx.bp_max * j, nb, j + 1);
+                             pik1_all + (size_t)j * pik1_stride, pb_self, cx.bp_xy + (size_t)2 * cx.bp_max * j, nb, j + 1, cnt);
       else
         out[0] = st[0], out[1] = st[1];
     }
     nadd += total;
+  }
+  g.sync();
+  return nadd;
+}
+
+// Crossing tests of one tracker tick (NeptuneRos::updateEntStateStaticObs, neptune_ros.cpp:806-822): per known
+// agent its own previous checking position and the 9-argument test; then the static obstacles from
+// previousCheckingPos_[N].  Also advances previousCheckingPos_[i] / previousCheckingPosAgent_[i] (:814-815).
+template <int NL>
+NB_HD int nb_collect_track(const Group<NL>& g, const NbEntCtx& cx, const int* bp_cnt_prev, const double* bp_xy_prev,
+                           double* prev_pos, double* prev_pos_agent, const double* latest, const double* cur, int* toadd,
+                           int tcap, int* stop_out)
+{
+  int nadd = 0;
+  const double* pb_self = cx.pb + 2 * cx.self;
+  const double pkN[2] = { prev_pos[2 * cx.N], prev_pos[2 * cx.N + 1] };
+  for (int base = 0; base < cx.N + cx.M; base += NL)
+  {
+    const int j = base + g.lane;
+    int cnt = 0, nb = 0, np = 0, st[2], stop = 0;
+    double pk[2] = { 0, 0 }, pik[2] = { 0, 0 };
+    bool agent = j < cx.N && j != cx.self;
+    if (agent)
+    {
+      nb = cx.bp_cnt[j], np = bp_cnt_prev[j];
+      pik[0] = prev_pos_agent[2 * j], pik[1] = prev_pos_agent[2 * j + 1];
+      if (pik[0] < -900 || nb == 0) agent = false;  // agent msg not received yet (:811)
+    }
+    if (agent)
+    {
+      pk[0] = prev_pos[2 * j], pk[1] = prev_pos[2 * j + 1];
+      if (nb > NB_ENT_LOCAL - 2) nb = NB_ENT_LOCAL - 2;
+      cnt = nb_hsig_agent9_stream(nullptr, pk, cur, pik, latest + 2 * j, pb_self, cx.bp_xy + (size_t)2 * cx.bp_max * j, nb,
+                                  bp_xy_prev + (size_t)2 * cx.bp_max * j, np, j + 1, &stop, 0);
+    }
+    else if (j >= cx.N && j < cx.N + cx.M)
+      cnt = nb_hsig_static_one(st, pkN, cur, cx.strep + 4 * (j - cx.N), j + 1);
+    if (g.any(stop != 0))
+    {  // the sequential loop keeps the value assigned last: the highest tether index wins
+#if defined(__CUDA_ARCH__)
+      const unsigned m = __ballot_sync(0xffffffffu, stop != 0);
+      if (g.lane == 31 - __clz(m)) *stop_out = stop;
+#else
+      *stop_out = stop;
+#endif
+    }
+    if (g.any(cnt > 0))
+    {
+      int total;
+      const int off = nb_excl_scan<NL>(g, cnt, total);
+      if (nadd + total > tcap) return -1;
+      if (cnt > 0)
+      {
+        int* out = toadd + 2 * (nadd + off);
+        int dummy = 0;
+        if (agent)
+          nb_hsig_agent9_stream(out, pk, cur, pik, latest + 2 * j, pb_self, cx.bp_xy + (size_t)2 * cx.bp_max * j, nb,
+                                bp_xy_prev + (size_t)2 * cx.bp_max * j, np, j + 1, &dummy, cnt);
+        else
+          out[0] = st[0], out[1] = st[1];
+      }
+      nadd += total;
+    }
+    if (agent)
+    {
+      prev_pos[2 * j] = cur[0], prev_pos[2 * j + 1] = cur[1];
+      prev_pos_agent[2 * j] = latest[2 * j], prev_pos_agent[2 * j + 1] = latest[2 * j + 1];
+    }
   }
   g.sync();
   return nadd;
@@ -556,7 +804,14 @@ struct NbEntArgs
   const double* prev_pos_agent;
   const double* cur;
   const double* samp0;
-  int* result;           // done / entangled
+  // tracker (mode 3)
+  const int* bp_cnt_prev;
+  const double* bp_xy_prev;
+  double* prev_pos_rw;           // [B][N+1][2] in/out
+  double* prev_pos_agent_rw;     // [B][N][2] in/out
+  const double* latest;          // [B][N][2]
+  const double* elapsed_ms;      // [B]
+  int* result;           // done / entangled / tracker result
   int* act_old;          // [B][N+M] scratch
   int* err;
 };
@@ -614,6 +869,42 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
       }
       a.st.cnt[2 * b] = es.n_alpha;
       a.st.cnt[2 * b + 1] = es.n_bend;
+    }
+    g.sync();
+    if (!bad && flag[3]) bad = 1;
+  }
+  else if (a.mode == 3)
+  {  // NeptuneRos::updateEntStateStaticObs neptune_ros.cpp:798-850
+    double* pp = a.prev_pos_rw + (size_t)b * (a.N + 1) * 2;
+    double* ppa = a.prev_pos_agent_rw + (size_t)b * a.N * 2;
+    const double* cur = a.cur + 2 * b;
+    const double dx = NB_SUB(pp[2 * a.N], cur[0]), dy = NB_SUB(pp[2 * a.N + 1], cur[1]);
+    if (sqrt(NB_ADD(NB_MUL(dx, dx), NB_MUL(dy, dy))) < 0.05 && a.elapsed_ms[b] < 100)
+    {  // the gate of :803-804 (group-uniform)
+      if (g.lane == 0) a.result[b] = 1;
+      return;
+    }
+    if (g.lane == 0) flag[2] = 0;
+    g.sync();
+    const double pkN[2] = { pp[2 * a.N], pp[2 * a.N + 1] };
+    const int nadd = nb_collect_track<NL>(g, cx, a.bp_cnt_prev, a.bp_xy_prev, pp, ppa, a.latest + (size_t)b * a.N * 2, cur, toadd,
+                                          a.tcap, &flag[2]);
+    g.sync();
+    if (nadd < 0)
+      bad = 1;
+    else if (g.lane == 0)
+    {
+      if (nb_add_alpha_beta(toadd, nadd, es, pkN, cx))
+        flag[3] = 1;
+      else
+      {
+        flag[3] = 0;
+        nb_update_bend_pts(es, cur, cx);
+      }
+      pp[2 * a.N] = cur[0], pp[2 * a.N + 1] = cur[1];
+      a.st.cnt[2 * b] = es.n_alpha;
+      a.st.cnt[2 * b + 1] = es.n_bend;
+      a.result[b] = flag[2] ? -flag[2] : 0;
     }
     g.sync();
     if (!bad && flag[3]) bad = 1;

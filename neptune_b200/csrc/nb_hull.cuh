@@ -25,16 +25,6 @@ NB_HD int nb_rec_np(const double* rec) { return (int)rec[0]; }
 NB_HD const double* nb_rec_times(const double* rec) { return rec + 1; }
 NB_HD const double* nb_rec_coeff(const double* rec, int ax) { return rec + 1 + (NB_TP + 1) + ax * NB_TP * 4; }
 
-#if defined(__CUDA_ARCH__)
-#define NB_MUL(a, b) __dmul_rn((a), (b))
-#define NB_ADD(a, b) __dadd_rn((a), (b))
-#define NB_SUB(a, b) __dsub_rn((a), (b))
-#else
-#define NB_MUL(a, b) ((a) * (b))
-#define NB_ADD(a, b) ((a) + (b))
-#define NB_SUB(a, b) ((a) - (b))
-#endif
-
 NB_HD double nb_cross3(const double* o, const double* a, const double* b)
 {
   return NB_SUB(NB_MUL(NB_SUB(a[0], o[0]), NB_SUB(b[1], o[1])), NB_MUL(NB_SUB(a[1], o[1]), NB_SUB(b[0], o[0])));

@@ -759,6 +759,229 @@ int orc_hsig_agent(int* toadd, int nadd, const double pk[2], const double pk1[2]
   return nadd;
 }
 
+/* eu::entangleHSigToAddAgentInd, 9-arg (entangle_utils.cpp:820-1127): the online tracker's form, aware of a
+ * bend point of the other tether having been added or released since the last check.  *stop = k where the
+ * reference would print "stop k" and exit(-1) (:917, :981, :1073, :1107). */
+#define PUSH9(cs_)                   \
+  {                                  \
+    toadd[2 * nadd] = agent_id;      \
+    toadd[2 * nadd + 1] = (cs_);     \
+    nadd++;                          \
+  }
+int orc_hsig_agent9(int* toadd, int nadd, const double pk[2], const double pk1[2], const double pik[2],
+                    const double pik1[2], const double pb_self[2], const double* bend, int nbend, const double* prev,
+                    int nprev, int agent_id, int* stop)
+{
+  if (nprev == nbend) return orc_hsig_agent(toadd, nadd, pk, pk1, pik, pik1, pb_self, bend, nbend, agent_id); /* :826-830 */
+  int base_add = 0;
+  if (nbend == 0 || nprev == 0) return nadd; /* "bendpts empty!" :833-836 */
+  const double* pback = prev + 2 * (nprev - 1);
+  if (nbend < nprev)
+  { /* released from a bend point (:837-986) */
+    const double* pback2 = prev + 2 * (nprev - 2);
+    for (int i = 0; i < nbend; i++)
+    {
+      double ab[2], ac[2], abp[2], acp[2], c1, c2, c1p = 0.0;
+      const double* bi = bend + 2 * i;
+      const int last = (i == nbend - 1);
+      if (!last)
+      {
+        c1 = wedge2(pk, bend + 2 * (i + 1), bi, ab, ac);
+        c2 = wedge2(pk1, bend + 2 * (i + 1), bi, 0, 0);
+      }
+      else
+      {
+        c1 = wedge2(pk, pik, pback, ab, ac);
+        c2 = wedge2(pk1, pik1, bi, 0, 0);
+        c1p = wedge2(pk, pback, pback2, abp, acp);
+      }
+      if (last)
+      {
+        double fb[2], fc[2];
+        double f1 = wedge2(pb_self, pik, pback, 0, 0);
+        double f2 = wedge2(pb_self, pik1, bi, fb, fc);
+        double f1p = 0.0;
+        if (i == 0) f1p = wedge2(pb_self, pback, pback2, 0, 0);
+        if (f1 * f2 < 0)
+        {
+          double a = cross_ratio(fb, fc);
+          if (a < 0)
+          {
+          }
+          else if (a < 1)
+            PUSH9(1)
+          base_add = 1;
+        }
+        if (i == 0 && f1p * f2 < 0)
+        {
+          double a = cross_ratio(fb, fc);
+          if (a < 0)
+          {
+          }
+          else if (a < 1)
+          {
+          }
+          else
+          {
+            PUSH9(0)
+            *stop = 4;
+          }
+          base_add = 1;
+        }
+      }
+      int added_inbtw = 0;
+      if (c1 * c2 < 0)
+      {
+        double a = cross_ratio(ab, ac);
+        if (a < 0)
+        {
+          PUSH9(i + 2)
+          added_inbtw = 1;
+        }
+        else if (a < 1 && last)
+          PUSH9(1)
+      }
+      if (last && c1p * c2 < 0)
+      {
+        double a = cross_ratio(abp, acp);
+        if (a < 0 && !added_inbtw)
+          PUSH9(i + 2)
+        else if (a < 1 && last)
+        {
+        }
+        else if (a >= 1 && i == 0)
+        {
+          PUSH9(0)
+          *stop = 3;
+        }
+      }
+    }
+  }
+  else
+  { /* a bend point was added (:987-1116) */
+    for (int i = 0; i < nbend; i++)
+    {
+      double ab[2], ac[2], c1, c2;
+      const double* bi = bend + 2 * i;
+      if (i == nbend - 1)
+      {
+        c1 = wedge2(pk, pik, pback, 0, 0);
+        c2 = wedge2(pk1, pik1, bi, ab, ac);
+      }
+      else if (i == nbend - 2)
+      {
+        c1 = wedge2(pk, pik, pback, 0, 0);
+        c2 = wedge2(pk1, bend + 2 * (i + 1), bi, ab, ac);
+      }
+      else
+      {
+        c1 = wedge2(pk, bend + 2 * (i + 1), bi, ab, ac);
+        c2 = wedge2(pk1, bend + 2 * (i + 1), bi, 0, 0);
+      }
+      if (i == nbend - 1)
+      {
+        double fb[2], fc[2];
+        double f1 = wedge2(pb_self, pik, pback, 0, 0);
+        double f2 = wedge2(pb_self, pik1, bi, fb, fc);
+        if (f1 * f2 < 0)
+        {
+          double a = cross_ratio(fb, fc);
+          if (a < 0)
+          {
+          }
+          else if (a < 1)
+            PUSH9(1)
+          base_add = 1;
+        }
+      }
+      if (i == 0 && nbend == 2)
+      {
+        double fb[2], fc[2];
+        double f1 = wedge2(pb_self, pik, pback, 0, 0);
+        double f2 = wedge2(pb_self, bend + 2 * (i + 1), bi, fb, fc);
+        if (f1 * f2 < 0)
+        {
+          double a = cross_ratio(fb, fc);
+          if (a < 0)
+          {
+          }
+          else if (a < 1)
+          {
+          }
+          else
+          {
+            PUSH9(0)
+            *stop = 2;
+          }
+          base_add = 1;
+        }
+      }
+      if (c1 * c2 < 0)
+      {
+        double a = cross_ratio(ab, ac);
+        if (a < 0)
+          PUSH9(i + 2)
+        else if (a < 1 && i == nbend - 1)
+          PUSH9(1)
+        else if (a >= 1 && i == 0)
+        {
+          PUSH9(0)
+          *stop = 1;
+        }
+      }
+    }
+  }
+  if (base_add && nadd >= 2 && toadd[2 * (nadd - 1)] == toadd[2 * (nadd - 2)] &&
+      toadd[2 * (nadd - 1) + 1] == toadd[2 * (nadd - 2) + 1])
+    nadd -= 2;
+  return nadd;
+}
+
+/* NeptuneRos::updateEntStateStaticObs (neptune_ros.cpp:798-850): one odometry tick of the online tracker.
+ * es = entangle_state_ (in/out); prev_pos [N+1][2] = previousCheckingPos_ and prev_pos_agent [N][2] =
+ * previousCheckingPosAgent_ (both in/out); latest [N][2] = latestCheckingPosAgent_; elapsed_ms replaces the
+ * wall-clock timer of :803-804.  Returns 0 updated, 1 skipped by the gate, -k "stop k" (the reference exits),
+ * -100 storage overflow. */
+int orc_track(orc_ent* es, const orc_ectx* cx, const int* bp_cnt_prev, const double* bp_xy_prev, double* prev_pos,
+              double* prev_pos_agent, const double* latest, const double cur[2], double elapsed_ms)
+{
+  const int N = cx->N, tcap = 4 * (cx->N + cx->M) + 16;
+  {
+    const double dx = prev_pos[2 * N] - cur[0], dy = prev_pos[2 * N + 1] - cur[1];
+    if (sqrt(dx * dx + dy * dy) < 0.05 && elapsed_ms < 100) return 1;
+  }
+  int* toadd = (int*)malloc(sizeof(int) * 2 * tcap);
+  int nadd = 0, rc = 0, stop = 0;
+  for (int i = 0; i < N && !rc; i++)
+  {
+    if (i == cx->self) continue;
+    if (prev_pos_agent[2 * i] < -900 || cx->bp_cnt[i] == 0) continue; /* agent msg not received yet (:811) */
+    if (nadd + cx->bp_cnt[i] + 3 > tcap)
+    {
+      rc = -100;
+      break;
+    }
+    nadd = orc_hsig_agent9(toadd, nadd, prev_pos + 2 * i, cur, prev_pos_agent + 2 * i, latest + 2 * i, cx->pb + 2 * cx->self,
+                           cx->bp_xy + 2 * cx->bp_max * i, cx->bp_cnt[i], bp_xy_prev + 2 * cx->bp_max * i, bp_cnt_prev[i],
+                           i + 1, &stop);
+    prev_pos[2 * i] = cur[0], prev_pos[2 * i + 1] = cur[1];
+    prev_pos_agent[2 * i] = latest[2 * i], prev_pos_agent[2 * i + 1] = latest[2 * i + 1];
+  }
+  if (!rc && nadd + cx->M > tcap) rc = -100;
+  if (!rc)
+  {
+    nadd = orc_hsig_static(toadd, nadd, prev_pos + 2 * N, cur, cx->strep, cx->M, N);
+    if (orc_add_alpha_beta(toadd, nadd, es, prev_pos + 2 * N, cx))
+      rc = -100;
+    else
+      orc_update_bend_pts(es, cur, cx);
+    prev_pos[2 * N] = cur[0], prev_pos[2 * N + 1] = cur[1];
+  }
+  free(toadd);
+  if (stop) return -stop;
+  return rc;
+}
+
 /* eu::entangleHSigToAddStatic (entangle_utils.cpp:1231-1277) */
 int orc_hsig_static(int* toadd, int nadd, const double pk[2], const double pk1[2], const double* strep,
                     int M, int N)

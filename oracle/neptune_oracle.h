@@ -102,6 +102,13 @@ int orc_hsig_static(int* toadd, int nadd, const double pk[2], const double pk1[2
 int orc_add_alpha_beta(int* toadd, int nadd, orc_ent* es, const double pk[2], const orc_ectx* cx);
 void orc_update_bend_pts(orc_ent* es, const double pk1[2], const orc_ectx* cx);
 
+/* eu::entangleHSigToAddAgentInd, 9-arg (entangle_utils.cpp:820-1127) */
+int orc_hsig_agent9(int* toadd, int nadd, const double pk[2], const double pk1[2], const double pik[2],
+                    const double pik1[2], const double pb_self[2], const double* bend, int nbend, const double* prev,
+                    int nprev, int agent_id, int* stop);
+/* NeptuneRos::updateEntStateStaticObs neptune_ros.cpp:798-850 (one tick of the online tracker) */
+int orc_track(orc_ent* es, const orc_ectx* cx, const int* bp_cnt_prev, const double* bp_xy_prev, double* prev_pos,
+              double* prev_pos_agent, const double* latest, const double cur[2], double elapsed_ms);
 /* Neptune::PredictAlphasBetas neptune.cpp:976-1008 */
 int orc_predict(orc_ent* es, const orc_ectx* cx, const double* prev_pos /*[N+1][2]*/,
                 const double* prev_pos_agent /*[N][2]*/, const double cur[2],

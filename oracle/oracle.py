@@ -220,6 +220,20 @@ def predict(es: EntState, cx: EntCtx, prev_pos, prev_pos_agent, cur, samp0, know
     return rc
 
 
+def track(es: EntState, cx: EntCtx, bp_cnt_prev, bp_xy_prev, prev_pos, prev_pos_agent, latest, cur, elapsed_ms: float) -> int:
+    """orc_track: one tick of the online tracker; es, prev_pos, prev_pos_agent are updated in place (float64 arrays)."""
+    bp_cnt_prev, bp_xy_prev = _c(bp_cnt_prev, np.int32), _c(bp_xy_prev, np.float64)
+    latest, cur = _c(latest, np.float64), _c(cur, np.float64)
+    assert prev_pos.dtype == np.float64 and prev_pos.flags["C_CONTIGUOUS"] and prev_pos_agent.flags["C_CONTIGUOUS"]
+    e = es._c()
+    f = lib().orc_track
+    f.restype = C.c_int
+    rc = f(C.byref(e), C.byref(cx.c), _p(bp_cnt_prev), _p(bp_xy_prev), _p(prev_pos), _p(prev_pos_agent), _p(latest), _p(cur),
+           C.c_double(elapsed_ms))
+    es._back(e)
+    return rc
+
+
 def entangle_check_pwp(es: EntState, cx: EntCtx, n, cxy, samp, known) -> int:
     par = cx.par
     cxy, samp, known = _c(cxy, np.float64), _c(samp, np.float64), _c(known, np.uint8)

@@ -97,3 +97,26 @@ def search(sb):
            longest.ctypes.data, C.addressof(a))
     assert rc == 0, rc
     return res
+
+
+def track(par, strep, agent_id, bp_cnt, bp_xy, bp_cnt_prev, bp_xy_prev, state, prev_pos, prev_pos_agent, latest, cur, elapsed_ms):
+    """k_entangle mode 3 (online tracker tick) on one host lane; same return convention as Solver.entangle_track."""
+    nbp = make_nb_params(par)
+    st = state.copy()
+    pp, ppa = np.ascontiguousarray(prev_pos, np.float64).copy(), np.ascontiguousarray(prev_pos_agent, np.float64).copy()
+    arrs = [np.ascontiguousarray(par.pb, np.float64),
+            np.ascontiguousarray(strep, np.float64) if par.num_of_static_obst else np.zeros((1, 2, 2)),
+            np.ascontiguousarray(agent_id, np.int32), np.ascontiguousarray(bp_cnt, np.int32), np.ascontiguousarray(bp_xy, np.float64),
+            np.ascontiguousarray(bp_cnt_prev, np.int32), np.ascontiguousarray(bp_xy_prev, np.float64),
+            np.ascontiguousarray(latest, np.float64), np.ascontiguousarray(cur, np.float64), np.ascontiguousarray(elapsed_ms, np.float64)]
+    B = len(arrs[2])
+    res = np.zeros(B, np.int32)
+    from neptune_b200.capi import NbEntState
+    f = lib().emul_track_batch
+    P = C.c_void_p
+    f.argtypes = [P, P, P, C.c_int, P, P, P, P, P, NbEntState, P, P, P, P, P, P]
+    d = lambda x: x.ctypes.data_as(P)  # noqa: E731
+    rc = f(C.addressof(nbp), d(arrs[0]), d(arrs[1]), B, d(arrs[2]), d(arrs[3]), d(arrs[4]), d(arrs[5]), d(arrs[6]), st.c(),
+           d(pp), d(ppa), d(arrs[7]), d(arrs[8]), d(arrs[9]), d(res))
+    assert rc == 0, rc
+    return res, st, pp, ppa

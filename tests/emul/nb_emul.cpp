@@ -11,6 +11,7 @@
 
 #include "../../include/neptune_b200.h"
 #include "../../neptune_b200/csrc/nb_common.cuh"
+#include "../../neptune_b200/csrc/nb_entangle.cuh"
 #include "../../neptune_b200/csrc/nb_lines.cuh"
 #include "../../neptune_b200/csrc/nb_qp.cuh"
 #include "../../neptune_b200/csrc/nb_search.cuh"
@@ -247,5 +248,28 @@ extern "C" int emul_search_batch(const nb_params* par, const nb_search_params* s
     nb_search_task<EmulCta, 1>(cta, ab, b, sh, nullptr, 0);
   }
   delete sh;
+  return err ? NB_ERR_CAPACITY : 0;
+}
+
+// ---- one tick of the online tracker (k_entangle mode 3) with one host lane
+extern "C" int emul_track_batch(const nb_params* par, const double* pb, const double* strep, int B, const int32_t* agent_id,
+                                const int32_t* bp_cnt, const double* bp_xy, const int32_t* bp_cnt_prev, const double* bp_xy_prev,
+                                nb_ent_state st, double* prev_pos, double* prev_pos_agent, const double* latest,
+                                const double* cur, const double* elapsed_ms, int32_t* result)
+{
+  NbEntArgs a;
+  memset(&a, 0, sizeof(a));
+  const int N = par->num_agents, M = par->num_static;
+  a.mode = 3, a.N = N, a.M = M, a.cap = par->ent_cap, a.bp_max = par->bp_max, a.num_pol = par->num_pol, a.S = par->samples;
+  a.T = par->T_span, a.tcap = 4 * (N + M) + 16;
+  a.agent_id = agent_id, a.bp_cnt = bp_cnt, a.bp_xy = bp_xy, a.pb = pb, a.strep = strep, a.st = st;
+  a.bp_cnt_prev = bp_cnt_prev, a.bp_xy_prev = bp_xy_prev, a.prev_pos_rw = prev_pos, a.prev_pos_agent_rw = prev_pos_agent;
+  a.latest = latest, a.cur = cur, a.elapsed_ms = elapsed_ms, a.result = result;
+  std::vector<uint8_t> known((size_t)B * N, 1);
+  std::vector<int> act_old((size_t)B * (N + M)), toadd((size_t)2 * a.tcap);
+  int err = 0, flag[4];
+  a.known = known.data(), a.act_old = act_old.data(), a.err = &err;
+  Group<1> g(0);
+  for (int b = 0; b < B; b++) nb_entangle_task<1>(g, b, a, toadd.data(), flag);
   return err ? NB_ERR_CAPACITY : 0;
 }

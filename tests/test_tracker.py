@@ -1,0 +1,147 @@
+"""Online entanglement tracker (NeptuneRos::updateEntStateStaticObs, reference neptune/src/neptune_ros.cpp:798-850,
+with the 9-argument eu::entangleHSigToAddAgentInd, entangle_utils.cpp:820-1127).
+
+Integer outputs (the signature word, active cases, bend-point indices, result codes) and the copied FP64 state
+(previousCheckingPos_, betas) are compared bit for bit: device code on one host lane and the CUDA kernel through
+the C-ABI against the oracle, over multi-tick walks in which tethers gain and lose contact points."""
+import numpy as np
+import pytest
+
+from neptune_b200 import config
+from neptune_b200.capi import EntArrays
+from neptune_b200.scenes import make_scene
+
+
+def _walk(par, seed, ticks=40, p_toggle=0.15):
+    """A random multi-tick scenario: every agent random-walks, other tethers gain / lose a contact point now and
+    then, some agents are silent (x = -1000: no message yet), some ticks fall under the 5 cm / 100 ms gate."""
+    rng = np.random.default_rng(seed)
+    N, bpm = par.num_of_agents, par.bp_max
+    pb = np.asarray(par.pb, float)
+    pos = pb + rng.normal(0, 3.0, size=(N, 2))
+    bp_cnt = np.ones(N, np.int32)
+    bp_xy = np.zeros((N, bpm, 2))
+    bp_xy[:, 0] = pb
+    silent = rng.random(N) < 0.15
+    frames = []
+    for t in range(ticks):
+        prev_cnt, prev_xy = bp_cnt.copy(), bp_xy.copy()
+        for j in range(N):
+            if rng.random() < p_toggle:
+                if bp_cnt[j] > 1 and rng.random() < 0.5:
+                    bp_cnt[j] -= 1
+                elif bp_cnt[j] < 3:
+                    bp_xy[j, bp_cnt[j]] = 0.5 * (pb[j] + pos[j]) + rng.normal(0, 1.5, size=2)
+                    bp_cnt[j] += 1
+        tiny = rng.random(N) < 0.1
+        step = rng.normal(0, 0.6, size=(N, 2))
+        step[tiny] *= 0.01
+        pos = pos + step
+        elapsed = np.where(rng.random(N) < 0.5, 20.0, 150.0)
+        latest = pos.copy()
+        latest[silent] = -1000.0
+        frames.append(dict(bp_cnt=bp_cnt.copy(), bp_xy=bp_xy.copy(), bp_cnt_prev=prev_cnt, bp_xy_prev=prev_xy,
+                           cur=pos.copy(), latest=latest, elapsed=elapsed))
+    start = pb + rng.normal(0, 3.0, size=(N, 2))
+    return start, silent, frames
+
+
+def _init(par, start, silent):
+    N = par.num_of_agents
+    st = EntArrays(par, N)
+    prev_pos = np.repeat(start[:, None, :], N + 1, axis=1).copy()           # setUpCheckingPosAndStaticObs :854-857
+    prev_pos_agent = np.repeat(start[None, :, :], N, axis=0).copy()
+    prev_pos_agent[:, silent] = -1000.0
+    return st, np.ascontiguousarray(prev_pos), np.ascontiguousarray(prev_pos_agent)
+
+
+def _oracle_tick(oracle, par, strep, st, pp, ppa, fr):
+    N = par.num_of_agents
+    res = np.zeros(N, np.int32)
+    for b in range(N):
+        es = oracle.EntState(par.ent_cap, par.NA)
+        es.n_alpha, es.n_bend = int(st.cnt[b, 0]), int(st.cnt[b, 1])
+        es.alpha[:], es.beta[:], es.bend[:], es.active[:] = st.alpha[b], st.beta[b], st.bend[b], st.active[b]
+        cx = oracle.EntCtx(par, b, strep, fr["bp_cnt"], fr["bp_xy"])
+        latest_b = np.ascontiguousarray(fr["latest"])
+        res[b] = oracle.track(es, cx, fr["bp_cnt_prev"], fr["bp_xy_prev"], pp[b], ppa[b], latest_b, fr["cur"][b], float(fr["elapsed"][b]))
+        st.cnt[b] = [es.n_alpha, es.n_bend]
+        st.alpha[b], st.beta[b], st.bend[b], st.active[b] = es.alpha, es.beta, es.bend, es.active
+    return res
+
+
+def _run(oracle, par, strep, seed, device_tick):
+    start, silent, frames = _walk(par, seed)
+    N = par.num_of_agents
+    ids = np.arange(1, N + 1, dtype=np.int32)
+    st_o, pp_o, ppa_o = _init(par, start, silent)
+    st_d, pp_d, ppa_d = _init(par, start, silent)
+    seen = {0: 0, 1: 0, "neg": 0, "changed": 0}
+    for fr in frames:
+        latest = np.repeat(fr["latest"][None], N, axis=0)
+        res_o = _oracle_tick(oracle, par, strep, st_o, pp_o, ppa_o, fr)
+        res_d, st_d, pp_d, ppa_d = device_tick(ids, fr["bp_cnt"], fr["bp_xy"], fr["bp_cnt_prev"], fr["bp_xy_prev"], st_d,
+                                               pp_d, ppa_d, latest, fr["cur"], fr["elapsed"])
+        assert np.array_equal(res_o, res_d)
+        ok = res_o >= 0   # where the reference would have exited the state is no longer defined
+        assert np.array_equal(st_o.cnt[ok], st_d.cnt[ok])
+        for b in np.flatnonzero(ok):
+            na, nb = st_o.cnt[b]
+            assert np.array_equal(st_o.alpha[b, :na], st_d.alpha[b, :na]) and np.array_equal(st_o.beta[b, :na], st_d.beta[b, :na])
+            assert np.array_equal(st_o.bend[b, :nb], st_d.bend[b, :nb]) and np.array_equal(st_o.active[b], st_d.active[b])
+        assert np.array_equal(pp_o[ok], pp_d[ok]) and np.array_equal(ppa_o[ok], ppa_d[ok])
+        # keep both sides on the oracle's state (stop cases included) so that later ticks stay comparable
+        st_d, pp_d, ppa_d = st_o.copy(), pp_o.copy(), ppa_o.copy()
+        seen[0] += int((res_o == 0).sum()); seen[1] += int((res_o == 1).sum()); seen["neg"] += int((res_o < 0).sum())
+        seen["changed"] += int((fr["bp_cnt"] != fr["bp_cnt_prev"]).sum())
+    assert seen[0] > 50 and seen[1] > 5 and seen["changed"] > 10
+    assert int(st_o.cnt[:, 0].max()) >= 1    # the walks do cross tethers
+    return seen
+
+
+def _scene(oracle, cfg, seed):
+    par = config(cfg)
+    sc = make_scene(par, seed, sync=True)
+    return par, sc.strep
+
+
+def test_tracker_without_contact_changes_equals_predict(oracle):
+    """With bendPtsForAgents_ unchanged the 9-argument test is the 8-argument one (entangle_utils.cpp:826-830), so a
+    tracker tick equals PredictAlphasBetas (neptune.cpp:976-1008) on the same positions: two code paths of the oracle."""
+    par, strep = _scene(oracle, "obst8", 3003)
+    start, silent, frames = _walk(par, 5, ticks=25, p_toggle=0.0)
+    N = par.num_of_agents
+    st, pp, ppa = _init(par, start, silent)
+    for fr in frames:
+        fr["elapsed"][:] = 1000.0
+        st_p, pp_before, ppa_before = st.copy(), pp.copy(), ppa.copy()
+        _oracle_tick(oracle, par, strep, st, pp, ppa, fr)
+        for b in range(N):
+            es = oracle.EntState(par.ent_cap, par.NA)
+            es.n_alpha, es.n_bend = int(st_p.cnt[b, 0]), int(st_p.cnt[b, 1])
+            es.alpha[:], es.beta[:], es.bend[:], es.active[:] = st_p.alpha[b], st_p.beta[b], st_p.bend[b], st_p.active[b]
+            cx = oracle.EntCtx(par, b, strep, fr["bp_cnt"], fr["bp_xy"])
+            known = (ppa_before[b, :, 0] > -900).astype(np.uint8)
+            assert oracle.predict(es, cx, pp_before[b], ppa_before[b], fr["cur"][b], fr["latest"], known) == 0
+            assert (es.n_alpha, es.n_bend) == tuple(st.cnt[b])
+            assert np.array_equal(es.alpha[:es.n_alpha], st.alpha[b, :es.n_alpha]) and np.array_equal(es.active, st.active[b])
+
+
+@pytest.mark.parametrize("cfg,seed", [("obst8", 11), ("obst8", 12), ("mtlp5", 13)])
+def test_emulated_tracker_matches_oracle(oracle, cfg, seed):
+    from tests.emul import emul
+    par, strep = _scene(oracle, cfg, 3003)
+    _run(oracle, par, strep, seed, lambda *a: emul.track(par, strep, *a))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,seed", [("obst8", 21), ("obst8", 22), ("mtlp5", 23), ("grid64", 24)])
+def test_gpu_tracker_matches_oracle(oracle, cfg, seed):
+    from neptune_b200 import capi
+    par, strep = _scene(oracle, cfg, 3003)
+    s = capi.Solver(par)
+    if par.num_of_static_obst:
+        sc = make_scene(par, 3003, sync=True)
+        s.set_static(sc.batch.st_ptr, sc.batch.st_xy, sc.strep)
+    _run(oracle, par, strep, seed, lambda *a: s.entangle_track(*a))
+    s.close()
