@@ -321,6 +321,17 @@ typedef struct nb_search_params
 
 int nb_search_configure(nb_handle* h, const nb_search_params* sp);
 
+/*
+ * Replaces NeptuneRos::setUpCheckingPosAndStaticObs (neptune_ros.cpp:852-1019), the one-time choice of the two
+ * representative points of every static obstacle (staticObsRep_) and of staticObsLongestDist_ for ONE agent.  Host
+ * function (no device work, like the reference's).  poly_*: the raw (un-inflated) obstacles, CSR; base / pos: the
+ * agent's base and current position; voxel_size: a_star_fraction_voxel_size.  strep [M][2][2], longest [M][2].
+ * Returns NB_ERR_ARG where the reference prints "cannot find a feasible vertex representation" and exits.
+ * SURVEY section 8(f) "next #3".
+ */
+int nb_static_obst_rep(int32_t M, const int64_t* poly_ptr, const double* poly_xy, const double* base, const double* pos,
+                       double voxel_size, double* strep, double* longest);
+
 /* Second argument of KinodynamicSearch::setStaticObstRep (:385-390): staticObsLongestDist [M][2]. Host pointer. */
 int nb_set_static_longest(nb_handle* h, const double* longest);
 

@@ -319,6 +319,9 @@ typedef struct orc_search_batch_t
 } orc_search_batch_t;
 
 int orc_search_batch(const orc_search_par* par, const orc_search_batch_t* b, int nthreads);
+/* NeptuneRos::setUpCheckingPosAndStaticObs neptune_ros.cpp:852-1019 (static-obstacle representation of one agent) */
+int orc_static_obst_rep(int M, const long long* ptr, const double* xy, const double base[2], const double pos[2],
+                        double voxel, double* strep, double* longest);
 /* test hook: open-list script through the heap restatement (compared with the real std::priority_queue) */
 int orc_heap_replay(int n_ops, const int* ops, const double* vals, int n_ids, double bias, int* out);
 

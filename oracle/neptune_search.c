@@ -673,3 +673,99 @@ int orc_heap_replay(int n_ops, const int* ops, const double* vals, int n_ids, do
   free(s.pool), free(s.heap);
   return n_out;
 }
+
+/* NeptuneRos::setUpCheckingPosAndStaticObs (neptune_ros.cpp:852-1019): representative points of every static
+ * obstacle for one agent -- where a line through the obstacle's centre, at an angle found by a one-degree sweep that
+ * starts along base -> pos, leaves the polygon -- and staticObsLongestDist.  poly: raw (un-inflated) obstacles.
+ * Returns 0, or -1 where the reference prints "cannot find a feasible vertex representation" and exits. */
+int orc_static_obst_rep(int M, const long long* ptr, const double* xy, const double base[2], const double pos[2],
+                        double voxel, double* strep, double* longest)
+{
+  double* cen = (double*)malloc(sizeof(double) * 2 * (M > 0 ? M : 1));
+  for (int i = 0; i < M; i++)
+  {
+    double sx = 0.0, sy = 0.0;
+    const int nv = (int)(ptr[i + 1] - ptr[i]);
+    for (int j = 0; j < nv; j++) sx += xy[2 * (ptr[i] + j)], sy += xy[2 * (ptr[i] + j) + 1];
+    cen[2 * i] = sx / nv, cen[2 * i + 1] = sy / nv;
+  }
+  const double c11 = base[0], c22 = base[1], d11 = pos[0], d22 = pos[1];
+  double theta = atan2(d22 - c22, d11 - c11);
+  int ok = 0, rc = 0;
+  while (!ok)
+  {
+    if (theta > atan2(d22 - c22, d11 - c11) + 3.14)
+    {
+      rc = -1;
+      break;
+    }
+    const double m = tan(theta);
+    int fail = 0;
+    for (int i = 0; i < M && !fail; i++)
+    {
+      const double e1 = cen[2 * i + 1] - cen[2 * i] * m;
+      for (int j = i + 1; j < M; j++)
+      {
+        const double e2 = cen[2 * j + 1] - cen[2 * j] * m;
+        if (fabs(e1 - e2) / sqrt(1 + m * m) < voxel * 1.6) fail = 1;
+      }
+      if (fail) break;
+      const double e2 = base[1] - base[0] * m;
+      if (fabs(e1 - e2) / sqrt(1 + m * m) < voxel * 1.6)
+      {
+        fail = 1;
+        break;
+      }
+      const double a1 = cen[2 * i], a2 = cen[2 * i + 1], b1 = cen[2 * i] + 10, b2 = cen[2 * i + 1] + 10 * m;
+      const double den = (b2 - a2) * (d11 - c11) - (b1 - a1) * (d22 - c22);
+      const double y = ((c22 - a2) * (b1 - a1) - (b2 - a2) * (c11 - a1)) / den;
+      if (fabs(den) < 0.01 || y < 0 || y > 1.0)
+      {
+      }
+      else
+        fail = 1;
+    }
+    for (int i = 0; i < M && !fail; i++)
+    {
+      const int nv = (int)(ptr[i + 1] - ptr[i]);
+      const double* v = xy + 2 * ptr[i];
+      double x_max = -1e-5, x_min = 1e-5, maxv[2] = { 0, 0 }, minv[2] = { 0, 0 };
+      for (int j = 0; j < nv; j++)
+      {
+        const double a1 = cen[2 * i], a2 = cen[2 * i + 1], b1 = cen[2 * i] + 10, b2 = cen[2 * i + 1] + 10 * m;
+        const double c1 = v[2 * j], c2 = v[2 * j + 1], d1 = v[2 * ((j + 1) % nv)], d2 = v[2 * ((j + 1) % nv) + 1];
+        const double den = (b2 - a2) * (d1 - c1) - (b1 - a1) * (d2 - c2);
+        const double y = ((c2 - a2) * (b1 - a1) - (b2 - a2) * (c1 - a1)) / den;
+        if (fabs(den) < 0.01 || y < 0 || y > 1.0) continue;
+        double x;
+        if (fabs(b1 - a1) < 0.01)
+          x = (c2 - a2) / (b2 - a2) + y * (d2 - c2) / (b2 - a2);
+        else
+          x = (c1 - a1) / (b1 - a1) + y * (d1 - c1) / (b1 - a1);
+        if (x > x_max)
+          x_max = x, maxv[0] = c1 + y * (d1 - c1), maxv[1] = c2 + y * (d2 - c2);
+        else if (x < x_min)
+          x_min = x, minv[0] = c1 + y * (d1 - c1), minv[1] = c2 + y * (d2 - c2);
+      }
+      if (x_max < 0 || x_min > 0)
+      {
+        fail = 1;
+        break;
+      }
+      strep[4 * i] = minv[0], strep[4 * i + 1] = minv[1], strep[4 * i + 2] = maxv[0], strep[4 * i + 3] = maxv[1];
+      double l1 = 0, l2 = 0;
+      for (int j = 0; j < nv; j++)
+      {
+        const double q1 = sqrt((v[2 * j] - minv[0]) * (v[2 * j] - minv[0]) + (v[2 * j + 1] - minv[1]) * (v[2 * j + 1] - minv[1]));
+        const double q2 = sqrt((v[2 * j] - maxv[0]) * (v[2 * j] - maxv[0]) + (v[2 * j + 1] - maxv[1]) * (v[2 * j + 1] - maxv[1]));
+        if (q1 > l1) l1 = q1;
+        if (q2 > l2) l2 = q2;
+      }
+      longest[2 * i] = l1, longest[2 * i + 1] = l2;
+    }
+    if (!fail) ok = 1;
+    theta = theta + 1.0 / 180.0 * 3.1415927;
+  }
+  free(cen);
+  return rc;
+}

@@ -145,3 +145,67 @@ def test_gpu_tracker_matches_oracle(oracle, cfg, seed):
         s.set_static(sc.batch.st_ptr, sc.batch.st_xy, sc.strep)
     _run(oracle, par, strep, seed, lambda *a: s.entangle_track(*a))
     s.close()
+
+
+def test_static_obstacle_representation(oracle):
+    """NeptuneRos::setUpCheckingPosAndStaticObs (neptune_ros.cpp:852-1019): the product's host function against the
+    oracle (bit-exact: same libm on the same host) and against what the reference's construction guarantees -- both
+    points lie on the obstacle's boundary on a common-slope line through its centre, on opposite sides of it, the
+    parallel lines are at least 1.6 voxels apart, none cuts the straight tether."""
+    import ctypes as C
+    from neptune_b200 import capi
+    from neptune_b200.params import multi_obstacle_squares
+    lib = capi.lib()
+    f = lib.nb_static_obst_rep
+    f.argtypes = [C.c_int32] + [C.c_void_p] * 4 + [C.c_double] + [C.c_void_p] * 2
+    g = oracle.lib().orc_static_obst_rep
+    g.restype = C.c_int
+    rng = np.random.default_rng(3)
+    sq = np.array([[0.25, 0.25], [0.25, -0.25], [-0.25, -0.25], [-0.25, 0.25]])
+    n_ok = 0
+    for trial in range(40):
+        if trial == 0:
+            polys = multi_obstacle_squares()
+        else:
+            polys = []
+            while len(polys) < int(rng.integers(1, 12)):
+                c = rng.uniform(-12, 12, size=2)
+                if all(np.linalg.norm(c - q.mean(axis=0)) > 1.5 for q in polys):
+                    polys.append(c + sq * rng.uniform(0.6, 2.0) if rng.random() < 0.7 else
+                                 c + np.array([[0.4, 0.0], [0.0, 0.5], [-0.5, 0.1], [-0.1, -0.6]]))
+        M = len(polys)
+        ptr = np.concatenate([[0], np.cumsum([len(q) for q in polys])]).astype(np.int64)
+        xy = np.ascontiguousarray(np.concatenate(polys), np.float64)
+        base, pos = rng.uniform(-14, 14, size=2), rng.uniform(-14, 14, size=2)
+        out = [np.zeros((M, 2, 2)), np.zeros((M, 2)), np.zeros((M, 2, 2)), np.zeros((M, 2))]
+        rc_p = f(M, ptr.ctypes.data, xy.ctypes.data, base.ctypes.data, pos.ctypes.data, 0.2, out[0].ctypes.data, out[1].ctypes.data)
+        rc_o = g(C.c_int(M), ptr.ctypes.data_as(C.c_void_p), xy.ctypes.data_as(C.c_void_p), base.ctypes.data_as(C.c_void_p),
+                 pos.ctypes.data_as(C.c_void_p), C.c_double(0.2), out[2].ctypes.data_as(C.c_void_p), out[3].ctypes.data_as(C.c_void_p))
+        assert (rc_p == 0) == (rc_o == 0)
+        if rc_o != 0:
+            continue
+        n_ok += 1
+        assert np.array_equal(out[0], out[2]) and np.array_equal(out[1], out[3])
+        strep, longest = out[0], out[1]
+        d = strep[:, 1] - strep[:, 0]
+        ang = np.arctan2(d[:, 1], d[:, 0])
+        assert np.abs(np.sin(ang - ang[0])).max() < 1e-9                      # one common slope
+        nrm = np.array([-np.sin(ang[0]), np.cos(ang[0])])
+        cen = np.array([q.mean(axis=0) for q in polys])
+        off = cen @ nrm
+        assert np.abs((strep[:, 0] - cen) @ nrm).max() < 1e-9                 # through the centre
+        assert (((strep[:, 0] - cen) * (strep[:, 1] - cen)).sum(axis=1) < 0).all()   # on opposite sides of it
+        if M > 1:
+            gaps = np.abs(off[:, None] - off[None, :])[np.triu_indices(M, 1)]
+            assert gaps.min() >= 0.2 * 1.6 - 1e-9
+        assert np.abs(off - base @ nrm).min() >= 0.2 * 1.6 - 1e-9
+        for m in range(M):                                                    # on the boundary; longest distance is a vertex distance
+            for c in range(2):
+                q = polys[m]
+                def seg_dist(k):
+                    e, w = q[(k + 1) % len(q)] - q[k], strep[m, c] - q[k]
+                    return abs(e[0] * w[1] - e[1] * w[0]) / np.linalg.norm(e)
+                dist = min(seg_dist(k) for k in range(len(q)))
+                assert dist < 1e-9
+                assert abs(longest[m, c] - np.linalg.norm(q - strep[m, c], axis=1).max()) < 1e-12
+    assert n_ok >= 25
