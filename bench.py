@@ -44,7 +44,8 @@ def world_params(n_gpus: int, workload: str = "grid64"):
     gx, gy = np.meshgrid(xs, ys, indexing="ij")
     # ent_cap >= N + M: the front-end chain can then never overflow its storage (it declares a step
     # entangling before the word exceeds N + M entries, kinodynamic_search.cpp:844-848)
-    p = Params(num_of_agents=nx * ny, tetherLength=25.0, ent_cap=max(48, nx * ny + 8))
+    p = Params(num_of_agents=nx * ny, tetherLength=25.0, ent_cap=max(48, nx * ny + 8),
+               search_ecap=max(24, (nx * ny) // 2))   # signature words grow with the number of tethers around
     p.pb = np.stack([gx.ravel(), gy.ravel()], axis=1)
     p.x_min, p.x_max = xs[0] - 12.0, xs[-1] + 12.0
     p.y_min, p.y_max = ys[0] - 12.0, ys[-1] + 12.0

@@ -30,6 +30,7 @@ struct NbEntState
 struct NbEntCtx
 {
   int N, M, self, cap, bp_max;
+  int bp_stride;        // doubles between the bend-point lists of consecutive agents (2 bp_max, or padded in shared memory)
   const double* pb;     // [N][2]
   const double* strep;  // [M][2][2]
   const int* bp_cnt;    // [N]
@@ -442,7 +443,7 @@ NB_HD int nb_collect_toadd(const Group<NL>& g, const NbEntCtx& cx, const double*
       nb = cx.bp_cnt[j];
       if (nb > NB_ENT_LOCAL - 2) nb = NB_ENT_LOCAL - 2;
       cnt = nb_hsig_agent_stream(nullptr, pk_agents ? pk_agents + 2 * j : pk, pk1, pik_all + (size_t)j * pik_stride,
-                                 pik1_all + (size_t)j * pik1_stride, pb_self, cx.bp_xy + (size_t)2 * cx.bp_max * j, nb, j + 1, 0);
+                                 pik1_all + (size_t)j * pik1_stride, pb_self, cx.bp_xy + (size_t)cx.bp_stride * j, nb, j + 1, 0);
     }
     else if (j >= cx.N && j < cx.N + cx.M)
       cnt = nb_hsig_static_one(st, pk, pk1, cx.strep + 4 * (j - cx.N), j + 1);
@@ -455,7 +456,7 @@ NB_HD int nb_collect_toadd(const Group<NL>& g, const NbEntCtx& cx, const double*
       int* out = toadd + 2 * (nadd + off);
       if (agent)
         nb_hsig_agent_stream(out, pk_agents ? pk_agents + 2 * j : pk, pk1, pik_all + (size_t)j * pik_stride,
-                             pik1_all + (size_t)j * pik1_stride, pb_self, cx.bp_xy + (size_t)2 * cx.bp_max * j, nb, j + 1, cnt);
+                             pik1_all + (size_t)j * pik1_stride, pb_self, cx.bp_xy + (size_t)cx.bp_stride * j, nb, j + 1, cnt);
       else
         out[0] = st[0], out[1] = st[1];
     }
@@ -492,8 +493,8 @@ NB_HD int nb_collect_track(const Group<NL>& g, const NbEntCtx& cx, const int* bp
     {
       pk[0] = prev_pos[2 * j], pk[1] = prev_pos[2 * j + 1];
       if (nb > NB_ENT_LOCAL - 2) nb = NB_ENT_LOCAL - 2;
-      cnt = nb_hsig_agent9_stream(nullptr, pk, cur, pik, latest + 2 * j, pb_self, cx.bp_xy + (size_t)2 * cx.bp_max * j, nb,
-                                  bp_xy_prev + (size_t)2 * cx.bp_max * j, np, j + 1, &stop, 0);
+      cnt = nb_hsig_agent9_stream(nullptr, pk, cur, pik, latest + 2 * j, pb_self, cx.bp_xy + (size_t)cx.bp_stride * j, nb,
+                                  bp_xy_prev + (size_t)cx.bp_stride * j, np, j + 1, &stop, 0);
     }
     else if (j >= cx.N && j < cx.N + cx.M)
       cnt = nb_hsig_static_one(st, pkN, cur, cx.strep + 4 * (j - cx.N), j + 1);
@@ -516,8 +517,8 @@ NB_HD int nb_collect_track(const Group<NL>& g, const NbEntCtx& cx, const int* bp
         int* out = toadd + 2 * (nadd + off);
         int dummy = 0;
         if (agent)
-          nb_hsig_agent9_stream(out, pk, cur, pik, latest + 2 * j, pb_self, cx.bp_xy + (size_t)2 * cx.bp_max * j, nb,
-                                bp_xy_prev + (size_t)2 * cx.bp_max * j, np, j + 1, &dummy, cnt);
+          nb_hsig_agent9_stream(out, pk, cur, pik, latest + 2 * j, pb_self, cx.bp_xy + (size_t)cx.bp_stride * j, nb,
+                                bp_xy_prev + (size_t)cx.bp_stride * j, np, j + 1, &dummy, cnt);
         else
           out[0] = st[0], out[1] = st[1];
       }
@@ -821,7 +822,7 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
 {
   const int NA = a.N + a.M;
   NbEntCtx cx;
-  cx.N = a.N, cx.M = a.M, cx.self = a.agent_id[b] - 1, cx.cap = a.cap, cx.bp_max = a.bp_max;
+  cx.N = a.N, cx.M = a.M, cx.self = a.agent_id[b] - 1, cx.cap = a.cap, cx.bp_max = a.bp_max, cx.bp_stride = 2 * a.bp_max;
   cx.pb = a.pb, cx.strep = a.strep, cx.bp_cnt = a.bp_cnt, cx.bp_xy = a.bp_xy;
   const uint8_t* known = a.known + (size_t)b * a.N;
   int* act_old = a.act_old + (size_t)b * NA;

@@ -149,7 +149,13 @@ NB_HD int nb_search_ch_stride(const NbSearchPar& p) { return (2 * p.S + 2) * p.t
 
 // doubles of scratch per agent: beta lists of the children, then the base squares [N][4][2]
 #define NB_SEARCH_PTS 20  // sample positions of a child: (S + 1) points, S <= 8, and the arc length in the last slot
-NB_HD size_t nb_search_chd_stride(const NbSearchPar& p) { return (size_t)p.nchild * (p.ecap + NB_SEARCH_PTS) + (size_t)p.N * 8; }
+// Strides of the per-tether arrays that lanes read side by side are padded to an ODD number of doubles in shared
+// memory: with an even stride (64 doubles of samples, 16 of bend points, 48 of hull vertices) all 32 lanes of a
+// warp hit the same bank.
+#define NB_SEARCH_BSQ_STRIDE 9
+#define NB_SEARCH_HSTAGE_STRIDE (NB_HMAX * 2 + 1)
+NB_HD size_t nb_search_chd_stride(const NbSearchPar& p) { return (size_t)p.nchild * (p.ecap + NB_SEARCH_PTS) + (size_t)p.N * NB_SEARCH_BSQ_STRIDE; }
+NB_HD int nb_search_odd(int n) { return n | 1; }
 NB_HD size_t nb_search_fcode_bytes(const NbSearchPar& p) { return (size_t)p.num_pol * 8 * p.N; }
 
 // one evaluated child of the node being expanded
@@ -216,6 +222,8 @@ struct NbSearchCtx
   double* ch_dbl;
   int* par_act;
   double* base_sq;  // [N][4][2] squares around the bases (collidesWithBases2d :1610-1612)
+  int samp_stride;     // doubles between the sample blocks of consecutive agents (padded to an odd count in shared memory)
+  int hstage_stride, bsq_stride;
   uint8_t* fcode;      // [num_pol][8][N] base-crossing code of every (window, step, single-bend tether), built once
   int multi_bend;      // some known tether has bend points besides its base: the generic chain is used
   double* hull_stage;  // [N][24][2] shared-memory copy of the hulls of one window (null: read them from global)
@@ -235,6 +243,7 @@ struct NbSearchShared
   const void* stage_src[NB_SEARCH_NSTAGE];
   void* stage_dst[NB_SEARCH_NSTAGE];
   size_t stage_bytes[NB_SEARCH_NSTAGE];
+  int stage_rows[NB_SEARCH_NSTAGE], stage_src_stride[NB_SEARCH_NSTAGE], stage_dst_stride[NB_SEARCH_NSTAGE];  // row-wise re-pack (doubles)
   int path[NB_NPOL];
   // the node being expanded (written by thread 0 after the pop): kinematics, control points, list views
   double par_kin[NB_SEARCH_KIN], par_cps[8], par_g, goal_hull[8];
@@ -426,7 +435,7 @@ NB_HD int nb_search_entangles(const Group<NL>& g, const NbSearchCtx& c, NbEntSta
   const double* cy = kin + 10;
   double pk[2] = { cx[3], cy[3] }, pk1[2] = { cx[3], cy[3] };
   double arc = 0.0;
-  const int stride = num_pol * (S + 1) * 2;
+  const int stride = c.samp_stride;
   for (int j = 1; j <= S; j++)
   {
     if (j < S)
@@ -539,7 +548,7 @@ NB_HD int nb_search_entangles_fast(const Group<NL>& g, const NbSearchCtx& c, NbE
   }
   g.sync();
   NB_CTICK(12)
-  const int stride = num_pol * (S + 1) * 2;
+  const int stride = c.samp_stride;
   const bool past = index > num_pol;
   const double* samp0 = past ? c.samp + ((size_t)(num_pol - 1) * (S + 1) + S) * 2 : c.samp + (size_t)(index - 1) * (S + 1) * 2;
   const uint8_t* fcode = c.fcode + (size_t)(past ? 0 : index - 1) * 8 * N;
@@ -553,7 +562,7 @@ NB_HD int nb_search_entangles_fast(const Group<NL>& g, const NbSearchCtx& c, NbE
     unsigned long long code = 0;
     if (agent || stat)
     {
-      const double* b = agent ? c.ecx.bp_xy + (size_t)2 * p.bp_max * j : c.ecx.strep + 4 * (j - N);
+      const double* b = agent ? c.ecx.bp_xy + (size_t)c.ecx.bp_stride * j : c.ecx.strep + 4 * (j - N);
       const double* tgt0 = agent ? samp0 + (size_t)j * stride : c.ecx.strep + 4 * (j - N) + 2;
       double ab[2], ac[2];
       double prev = nb_wedge(pts, tgt0, b, ab, ac);
@@ -993,10 +1002,10 @@ inline size_t nb_search_arena_wanted(const NbSearchPar& p)
   size_t t = 0;
   t += r16(((size_t)p.nchild * nb_search_ch_stride(p) + NA) * 4) + r16(nb_search_chd_stride(p) * 8);
   t += r16(mn * 16) + r16(mn * 4);
-  t += r16((size_t)p.N * 16) + r16((size_t)p.N * 4) + r16((size_t)p.N * p.bp_max * 16) + r16((size_t)p.N) + r16(NA * 4);
+  t += r16((size_t)p.N * 16) + r16((size_t)p.N * 4) + r16((size_t)p.N * nb_search_odd(2 * p.bp_max) * 8) + r16((size_t)p.N) + r16(NA * 4);
   t += r16((size_t)p.M * 32) + r16((size_t)p.M * 16) + r16((size_t)p.N * NB_NPOL * 4);
-  t += r16((size_t)p.N * p.num_pol * (p.S + 1) * 16);
-  t += r16(nb_search_fcode_bytes(p)) + r16((size_t)p.N * NB_HMAX * 16);
+  t += r16((size_t)p.N * nb_search_odd(p.num_pol * (p.S + 1) * 2) * 8);
+  t += r16(nb_search_fcode_bytes(p)) + r16((size_t)p.N * NB_SEARCH_HSTAGE_STRIDE * 8);
   return t;
 }
 
@@ -1021,7 +1030,8 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     c.known = a.known + (size_t)b * N;
     c.comb = a.comb + (a.comb_shared ? 0 : (size_t)b * p.nchild);
     c.st_ptr = a.st_ptr, c.st_xy = a.st_xy, c.st_longest = a.st_longest;
-    c.ecx.N = N, c.ecx.M = M, c.ecx.self = c.self, c.ecx.cap = p.ecap, c.ecx.bp_max = p.bp_max;
+    c.ecx.N = N, c.ecx.M = M, c.ecx.self = c.self, c.ecx.cap = p.ecap, c.ecx.bp_max = p.bp_max, c.ecx.bp_stride = 2 * p.bp_max;
+    c.samp_stride = p.num_pol * (S + 1) * 2, c.bsq_stride = NB_SEARCH_BSQ_STRIDE, c.hstage_stride = NB_SEARCH_HSTAGE_STRIDE;
     c.ecx.pb = a.pb, c.ecx.strep = a.strep, c.ecx.bp_cnt = a.bp_cnt, c.ecx.bp_xy = a.bp_xy;
     c.a_na = a.es.cnt[2 * b], c.a_nb = a.es.cnt[2 * b + 1];
     c.a_alpha = a.es.alpha + (size_t)b * p.es_cap * 2, c.a_beta = a.es.beta + (size_t)b * p.es_cap;
@@ -1050,19 +1060,22 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     c.par_act = c.ch_int + (size_t)p.nchild * c.ch_stride;
     sh->stage_src[0] = c.ecx.pb, sh->stage_bytes[0] = (size_t)N * 16;
     sh->stage_src[1] = c.ecx.bp_cnt, sh->stage_bytes[1] = (size_t)N * 4;
-    sh->stage_src[2] = c.ecx.bp_xy, sh->stage_bytes[2] = (size_t)N * p.bp_max * 16;
+    for (int k = 0; k < NB_SEARCH_NSTAGE; k++) sh->stage_rows[k] = 0;
+    sh->stage_src[2] = c.ecx.bp_xy, sh->stage_bytes[2] = (size_t)N * nb_search_odd(2 * p.bp_max) * 8;
+    sh->stage_rows[2] = N, sh->stage_src_stride[2] = 2 * p.bp_max, sh->stage_dst_stride[2] = nb_search_odd(2 * p.bp_max);
     sh->stage_src[3] = c.known, sh->stage_bytes[3] = (size_t)N;
     sh->stage_src[4] = c.a_active, sh->stage_bytes[4] = (size_t)NA * 4;
     sh->stage_src[5] = c.ecx.strep, sh->stage_bytes[5] = (size_t)M * 32;
     sh->stage_src[6] = c.st_longest, sh->stage_bytes[6] = (size_t)M * 16;
     sh->stage_src[7] = c.hull_cnt, sh->stage_bytes[7] = (size_t)N * NB_NPOL * 4;
-    sh->stage_src[8] = c.samp, sh->stage_bytes[8] = (size_t)N * p.num_pol * (S + 1) * 16;
+    sh->stage_src[8] = c.samp, sh->stage_bytes[8] = (size_t)N * nb_search_odd(c.samp_stride) * 8;
+    sh->stage_rows[8] = N, sh->stage_src_stride[8] = c.samp_stride, sh->stage_dst_stride[8] = nb_search_odd(c.samp_stride);
     for (int k = 0; k < NB_SEARCH_NSTAGE; k++)
       sh->stage_dst[k] = (sh->stage_src[k] && sh->stage_bytes[k]) ? ar.take(sh->stage_bytes[k]) : nullptr;
     uint8_t* fcd = (uint8_t*)ar.take(nb_search_fcode_bytes(p));
     c.fcode = fcd ? fcd : a.fcode_g + (size_t)b * nb_search_fcode_bytes(p);
     c.multi_bend = 0;
-    c.hull_stage = (double*)ar.take((size_t)N * NB_HMAX * 2 * sizeof(double));
+    c.hull_stage = (double*)ar.take((size_t)N * NB_SEARCH_HSTAGE_STRIDE * sizeof(double));
     {  // goal hull of setUp (:215-220)
       const double r = 0.5, gx = c.goal[0], gy = c.goal[1];
       double* gq = sh->goal_hull;
@@ -1074,7 +1087,14 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
   {
     if (!sh->stage_dst[k]) continue;
     const size_t nb = sh->stage_bytes[k];
-    if ((nb & 3) == 0)
+    if (sh->stage_rows[k] > 0)
+    {
+      const double* s8 = (const double*)sh->stage_src[k];
+      double* d8 = (double*)sh->stage_dst[k];
+      const int ss = sh->stage_src_stride[k], ds = sh->stage_dst_stride[k];
+      for (size_t q = cta.tid; q < (size_t)sh->stage_rows[k] * ss; q += cta.nthreads) d8[(q / ss) * ds + q % ss] = s8[q];
+    }
+    else if ((nb & 3) == 0)
     {
       const int* s4 = (const int*)sh->stage_src[k];
       int* d4 = (int*)sh->stage_dst[k];
@@ -1094,13 +1114,13 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     void** d = sh->stage_dst;
     if (d[0]) c.ecx.pb = (const double*)d[0];
     if (d[1]) c.ecx.bp_cnt = (const int*)d[1];
-    if (d[2]) c.ecx.bp_xy = (const double*)d[2];
+    if (d[2]) c.ecx.bp_xy = (const double*)d[2], c.ecx.bp_stride = sh->stage_dst_stride[2];
     if (d[3]) c.known = (const uint8_t*)d[3];
     if (d[4]) c.a_active = (const int*)d[4];
     if (d[5]) c.ecx.strep = (const double*)d[5];
     if (d[6]) c.st_longest = (const double*)d[6];
     if (d[7]) c.hull_cnt = (const int*)d[7];
-    if (d[8]) c.samp = (const double*)d[8];
+    if (d[8]) c.samp = (const double*)d[8], c.samp_stride = sh->stage_dst_stride[8];
   }
   cta.sync();
   const NbSearchPar& p = sh->par;
@@ -1109,7 +1129,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
   for (int ag = cta.tid; ag < N; ag += cta.nthreads)
   {  // squares around the bases (:1610-1612)
     const double radius = 0.7, bx = c.ecx.pb[2 * ag], by = c.ecx.pb[2 * ag + 1];
-    double* sq = c.base_sq + 8 * ag;
+    double* sq = c.base_sq + c.bsq_stride * ag;
     sq[0] = bx + radius, sq[1] = by + radius, sq[2] = bx + radius, sq[3] = by - radius;
     sq[4] = bx - radius, sq[5] = by - radius, sq[6] = bx - radius, sq[7] = by + radius;
   }
@@ -1129,8 +1149,8 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
         uint8_t code = 0;
         if (j != c.self && c.known[j])
         {
-          const double* sp = c.samp + ((size_t)(j * p.num_pol + i) * (S + 1) + s0) * 2;
-          code = nb_search_fcode_one(pb_self, sp, sp + 2, c.ecx.bp_xy + (size_t)2 * p.bp_max * j);
+          const double* sp = c.samp + (size_t)j * c.samp_stride + ((size_t)i * (S + 1) + s0) * 2;
+          code = nb_search_fcode_one(pb_self, sp, sp + 2, c.ecx.bp_xy + (size_t)c.ecx.bp_stride * j);
         }
         c.fcode[((size_t)i * 8 + s0) * N + j] = code;
       }
@@ -1225,7 +1245,8 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
         for (int q = cta.aux_tid; q < N * NB_HMAX * 2; q += cta.aux_n)
         {
           const int o = q / (NB_HMAX * 2), r = q % (NB_HMAX * 2);
-          if (r < 2 * nb_hull_count(c, o, hi - 1)) c.hull_stage[q] = c.hull_xy[((size_t)(o * NB_NPOL + hi - 1) * NB_HMAX) * 2 + r];
+          if (r < 2 * nb_hull_count(c, o, hi - 1))
+            c.hull_stage[(size_t)o * c.hstage_stride + r] = c.hull_xy[((size_t)(o * NB_NPOL + hi - 1) * NB_HMAX) * 2 + r];
         }
         cta.sync_aux();
       }
@@ -1234,7 +1255,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
         if (it < N)
         {  // other agents' hulls of window index-1
           const int hn = nb_hull_count(c, it, hi - 1);
-          const double* hv = c.hull_stage ? c.hull_stage + (size_t)it * NB_HMAX * 2
+          const double* hv = c.hull_stage ? c.hull_stage + (size_t)it * c.hstage_stride
                                           : c.hull_xy + ((size_t)(it * NB_NPOL + hi - 1) * NB_HMAX) * 2;
           if (hn > 0 && nb_gjk_collision(hv, hn, cps, 4)) hit = 1;
         }
@@ -1249,7 +1270,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
           if (ag == c.self) continue;
           const double bx = c.ecx.pb[2 * ag], by = c.ecx.pb[2 * ag + 1];
           if (nb_norm2(cps[0] - bx, cps[1] - by) > safe_dist) continue;
-          if (nb_gjk_collision(c.base_sq + 8 * ag, 4, cps, 4)) hit = 1;
+          if (nb_gjk_collision(c.base_sq + c.bsq_stride * ag, 4, cps, 4)) hit = 1;
         }
       }
       if (hit) ctl.hit[par] = 1;

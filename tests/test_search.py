@@ -176,6 +176,7 @@ def test_oracle_search_jerk_order_matters_only_through_ties(oracle):
     ("obst8", 3005, dict(search_max_expansions=1500)), ("grid64", 4004, dict(search_max_expansions=150)),
     ("mtlp5", 2006, dict(enable_entangle_check=False)), ("obst8", 3006, dict(use_not_reaching_soln=False)),
     ("mtlp5", 2007, dict(multi_bend=True)), ("obst8", 3007, dict(multi_bend=True)),
+    ("single", 1001, {}),   # configs[0]: one agent, nothing to avoid
 ])
 def test_emulated_kernel_matches_oracle(oracle, cfg, seed, mods):
     from tests.emul import emul
@@ -221,6 +222,7 @@ def _gpu_solver(capi, sc, sb):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("cfg,seeds,mods", [
+    ("single", range(1001, 1003), {}),
     ("mtlp5", range(2002, 2008), {}),
     ("obst8", range(3003, 3007), {}),
     ("grid64", range(4004, 4006), {}),

@@ -16,7 +16,12 @@ from neptune_b200.search import SearchResult
 def main():
     cfg = sys.argv[1] if len(sys.argv) > 1 else "grid64"
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 4004
-    par = config(cfg)
+    if cfg.startswith("grid") and cfg not in ("grid64", "grid1024"):   # e.g. grid128: the 64-agents-per-GPU world of N GPUs on ONE GPU
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
+        par = bench.world_params(int(cfg[4:]) // 64)
+    else:
+        par = config(cfg)
     if len(sys.argv) > 3:
         par.search_max_expansions = int(sys.argv[3])
     s = capi.Solver(par, device=0)
