@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(NB_SEARCH_THREADS, 1) k_search(NbSearchArgs a,
   cta.lane = threadIdx.x & 31;
   cta.child = threadIdx.x < NB_SEARCH_CHILD_THREADS, cta.aux = !cta.child;
   cta.aux_tid = threadIdx.x - NB_SEARCH_CHILD_THREADS, cta.aux_n = NB_SEARCH_THREADS - NB_SEARCH_CHILD_THREADS;
-  nb_search_task<NbCtaDev, 32>(cta, a, blockIdx.x, sh, arena_bytes ? arena : nullptr, arena_bytes);
+  nb_search_task<NbCtaDev, 32>(cta, a, blockIdx.x, blockIdx.x, sh, arena_bytes ? arena : nullptr, arena_bytes);
 }
 
 int nb_search_launch(const NbSearchArgs* a, int B, void* stream, const char** err)

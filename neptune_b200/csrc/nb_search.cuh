@@ -257,7 +257,7 @@ NB_HD double nb_norm2(double x, double y) { return sqrt(x * x + y * y); }
 
 #if defined(__CUDA_ARCH__)
 #define NB_TICK(slot)                                        \
-  if (a.prof && cta.tid == 0)                                \
+  if (cta.tid == 0 && a.prof)                                \
   {                                                          \
     const long long now_ = clock64();                        \
     a.prof[(size_t)b * 16 + (slot)] += now_ - tick_;          \
@@ -1010,8 +1010,8 @@ inline size_t nb_search_arena_wanted(const NbSearchPar& p)
 }
 
 template <class Cta, int NL>
-NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared* sh, unsigned char* arena, size_t arena_bytes)
-{
+NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSearchShared* sh, unsigned char* arena, size_t arena_bytes)
+{  // b: agent of the batch; wb: which per-agent workspace block to use (= b on the device)
   // ---- thread 0 builds the shared context: parameters, per-agent pointers, shared-memory placement
   if (cta.tid == 0)
   {
@@ -1036,27 +1036,27 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     c.a_na = a.es.cnt[2 * b], c.a_nb = a.es.cnt[2 * b + 1];
     c.a_alpha = a.es.alpha + (size_t)b * p.es_cap * 2, c.a_beta = a.es.beta + (size_t)b * p.es_cap;
     c.a_bend = a.es.bend + (size_t)b * p.es_cap, c.a_active = a.es.active + (size_t)b * NA;
-    c.meta = a.nd_meta + (size_t)b * p.max_nodes;
-    c.kin = a.nd_kin + (size_t)b * p.max_nodes * NB_SEARCH_KIN;
-    c.alpha = a.nd_alpha + (size_t)b * p.max_nodes * p.ecap * 2;
-    c.beta = a.nd_beta + (size_t)b * p.max_nodes * p.ecap;
-    c.bend = a.nd_bend + (size_t)b * p.max_nodes * p.ecap;
-    c.hash = a.hash + (size_t)b * p.hcap;
-    c.ng = a.nd_g + (size_t)b * p.max_nodes;
+    c.meta = a.nd_meta + (size_t)wb * p.max_nodes;
+    c.kin = a.nd_kin + (size_t)wb * p.max_nodes * NB_SEARCH_KIN;
+    c.alpha = a.nd_alpha + (size_t)wb * p.max_nodes * p.ecap * 2;
+    c.beta = a.nd_beta + (size_t)wb * p.max_nodes * p.ecap;
+    c.bend = a.nd_bend + (size_t)wb * p.max_nodes * p.ecap;
+    c.hash = a.hash + (size_t)wb * p.hcap;
+    c.ng = a.nd_g + (size_t)wb * p.max_nodes;
     c.ch_stride = nb_search_ch_stride(p);
     NbArena ar;
     ar.p = arena, ar.left = arena_bytes;
     // priority 1: the children's scratch (crossing lists, working entanglement state); 2: the open list and
     // its keys; 3: read-only per-agent inputs of the entanglement chain (copied in by all threads below)
     int* ci = (int*)ar.take(((size_t)p.nchild * c.ch_stride + NA) * sizeof(int));
-    c.ch_int = ci ? ci : a.ch_int + (size_t)b * (p.nchild * c.ch_stride + NA);
+    c.ch_int = ci ? ci : a.ch_int + (size_t)wb * (p.nchild * c.ch_stride + NA);
     double* cd = (double*)ar.take(nb_search_chd_stride(p) * sizeof(double));
-    c.ch_dbl = cd ? cd : a.ch_dbl + (size_t)b * nb_search_chd_stride(p);
+    c.ch_dbl = cd ? cd : a.ch_dbl + (size_t)wb * nb_search_chd_stride(p);
     c.base_sq = c.ch_dbl + (size_t)p.nchild * (p.ecap + NB_SEARCH_PTS);
     double* gh = (double*)ar.take((size_t)p.max_nodes * 2 * sizeof(double));
-    c.gh = gh ? gh : a.gh_g + (size_t)b * p.max_nodes * 2;
+    c.gh = gh ? gh : a.gh_g + (size_t)wb * p.max_nodes * 2;
     int* hp = (int*)ar.take((size_t)p.max_nodes * sizeof(int));
-    c.heap = hp ? hp : a.heap_g + (size_t)b * p.max_nodes;
+    c.heap = hp ? hp : a.heap_g + (size_t)wb * p.max_nodes;
     c.par_act = c.ch_int + (size_t)p.nchild * c.ch_stride;
     sh->stage_src[0] = c.ecx.pb, sh->stage_bytes[0] = (size_t)N * 16;
     sh->stage_src[1] = c.ecx.bp_cnt, sh->stage_bytes[1] = (size_t)N * 4;
@@ -1073,7 +1073,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, NbSearchShared
     for (int k = 0; k < NB_SEARCH_NSTAGE; k++)
       sh->stage_dst[k] = (sh->stage_src[k] && sh->stage_bytes[k]) ? ar.take(sh->stage_bytes[k]) : nullptr;
     uint8_t* fcd = (uint8_t*)ar.take(nb_search_fcode_bytes(p));
-    c.fcode = fcd ? fcd : a.fcode_g + (size_t)b * nb_search_fcode_bytes(p);
+    c.fcode = fcd ? fcd : a.fcode_g + (size_t)wb * nb_search_fcode_bytes(p);
     c.multi_bend = 0;
     c.hull_stage = (double*)ar.take((size_t)N * NB_SEARCH_HSTAGE_STRIDE * sizeof(double));
     {  // goal hull of setUp (:215-220)

@@ -235,17 +235,11 @@ extern "C" int emul_search_batch(const nb_params* par, const nb_search_params* s
   a.nd_meta = meta.data(), a.nd_kin = kin.data(), a.nd_alpha = alpha.data(), a.nd_beta = beta.data(), a.nd_bend = bend.data();
   a.hash = hash.data(), a.heap_g = heap.data(), a.gh_g = gh.data(), a.nd_g = ng.data(), a.ch_int = chi.data(), a.ch_dbl = chd.data(), a.fcode_g = fcode.data(), a.err = &err;
   NbSearchShared* sh = new NbSearchShared();
-  // workspace pointers are per agent: run agents one at a time with b-relative offsets removed
+  // one workspace block, reused by every agent in turn (workspace index 0)
   for (int b = 0; b < u->B; b++)
   {
-    NbSearchArgs ab = a;
-    ab.nd_meta -= (size_t)b * mn, ab.nd_kin -= (size_t)b * mn * NB_SEARCH_KIN, ab.nd_alpha -= (size_t)b * mn * p.ecap * 2;
-    ab.nd_beta -= (size_t)b * mn * p.ecap, ab.nd_bend -= (size_t)b * mn * p.ecap, ab.hash -= (size_t)b * p.hcap;
-    ab.heap_g -= (size_t)b * mn, ab.gh_g -= (size_t)b * mn * 2, ab.nd_g -= (size_t)b * mn, ab.ch_int -= (size_t)b * (p.nchild * chs + NA);
-    ab.ch_dbl -= (size_t)b * nb_search_chd_stride(p);
-    ab.fcode_g -= (size_t)b * nb_search_fcode_bytes(p);
     EmulCta cta;
-    nb_search_task<EmulCta, 1>(cta, ab, b, sh, nullptr, 0);
+    nb_search_task<EmulCta, 1>(cta, a, b, 0, sh, nullptr, 0);
   }
   delete sh;
   return err ? NB_ERR_CAPACITY : 0;

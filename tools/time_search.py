@@ -25,7 +25,12 @@ def main():
     if len(sys.argv) > 3:
         par.search_max_expansions = int(sys.argv[3])
     s = capi.Solver(par, device=0)
-    sc = make_scene(par, seed, sync=False, ent_backend=capi.DeviceEntBackend(s), group_hulls=True)
+    agents = np.arange(int(sys.argv[4])) if len(sys.argv) > 4 else None   # a subset of the world's agents plans
+    if par.num_of_static_obst:   # the entanglement back end of the generator needs the static representation first
+        s0 = make_scene(par, seed, sync=True, agents=np.arange(1), pack_hulls=False)
+        s.set_static(s0.batch.st_ptr, s0.batch.st_xy, s0.strep)
+    sc = make_scene(par, seed, sync=(agents is not None), ent_backend=capi.DeviceEntBackend(s), group_hulls=True, agents=agents,
+                    pack_hulls=(par.num_of_agents <= 256))
     sb = make_search_batch(sc, seed + 1, per_agent_order=True)
     if par.num_of_static_obst:
         s.set_static(sb.st_ptr, sb.st_xy, sb.strep)
