@@ -75,6 +75,7 @@ struct nb_handle
   // front-end search: configuration, staging and workspace
   nb_search_params sp;
   int sp_set = 0;
+  int search_smem_set = 0;
   int sprof_B = 0;
   double* d_st_longest = nullptr;
   DevBuf sprof;
@@ -1439,7 +1440,7 @@ extern "C" int nb_search_batch(nb_handle* h, const nb_search_args* u, void* stre
     h->sprof_B = B;
   }
   const char* etxt = nullptr;
-  if (nb_search_launch(&a, B, stream, &etxt))
+  if (nb_search_launch(&a, B, stream, &h->search_smem_set, &etxt))
   {
     g_err = std::string("k_search launch: ") + (etxt ? etxt : "?");
     return NB_ERR_CUDA;

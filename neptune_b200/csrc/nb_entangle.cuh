@@ -668,9 +668,11 @@ NB_HD void nb_update_bend_pts(NbEntState& es, const double* pk1, const NbEntCtx&
   nb_bend_pt(bp, es, cx);
   int idx_new = -1;
   const int start = es.n_bend == 0 ? -1 : es.bend[es.n_bend - 1];
-  for (int i = start + 1; i < es.n_alpha; i++)
+  // agents: calculateBetaForCase returns 0, and 0 * beta < -1e-7 is never true -- without static obstacles no entry
+  // can become a bend point, so the scan is skipped altogether
+  for (int i = start + 1; i < es.n_alpha && cx.M > 0; i++)
   {
-    if (es.alpha[2 * i] <= cx.N) continue;  // agents: calculateBetaForCase returns 0, and 0 * beta < -1e-7 is never true
+    if (es.alpha[2 * i] <= cx.N) continue;
     const double beta = nb_beta_for_case(es.alpha[2 * i], es.alpha[2 * i + 1], pk1, bp, cx);
     if (nb_lt_prod(beta, es.beta[i], -1e-7)) idx_new = i;
   }

@@ -41,21 +41,20 @@ __global__ void __launch_bounds__(NB_SEARCH_THREADS, 1) k_search(NbSearchArgs a,
   nb_search_task<NbCtaDev, 32>(cta, a, blockIdx.x, blockIdx.x, sh, arena_bytes ? arena : nullptr, arena_bytes);
 }
 
-int nb_search_launch(const NbSearchArgs* a, int B, void* stream, const char** err)
+int nb_search_launch(const NbSearchArgs* a, int B, void* stream, int* smem_attr_set, const char** err)
 {
-  static int max_smem_set = 0;
   const size_t fixed = nb_search_shared_bytes();
   size_t arena = nb_search_arena_wanted(a->p);
   if (fixed + arena > NB_SEARCH_SMEM_MAX) arena = NB_SEARCH_SMEM_MAX - fixed;
-  if (!max_smem_set)
-  {
+  if (!*smem_attr_set)
+  {  // per device / context: remembered in the caller's handle
     cudaError_t e = cudaFuncSetAttribute(k_search, cudaFuncAttributeMaxDynamicSharedMemorySize, NB_SEARCH_SMEM_MAX);
     if (e != cudaSuccess)
     {
       *err = cudaGetErrorString(e);
       return -1;
     }
-    max_smem_set = 1;
+    *smem_attr_set = 1;
   }
   k_search<<<B, NB_SEARCH_THREADS, fixed + arena, (cudaStream_t)stream>>>(*a, (unsigned)arena);
   cudaError_t e = cudaGetLastError();

@@ -12,21 +12,24 @@
 //   recoverPwpOut, recoverEntStateVector                       :521-553, :582-603
 //   getIz, power_int, CompareCost                              :2006-2031, kinodynamic_search.hpp:163-179
 //
-// Mapping onto the SM.  A best-first search is a sequential chain of pops, but every pop fans out:
-//   * the popped node is tested against the N-1 window hulls, the M static obstacles and the N bases
-//     (GJK, one thread per obstacle, __syncthreads_or);
-//   * its 25 jerk children are evaluated by 25 warps at once: each warp runs the S-step entanglement
-//     chain of its child with the lanes spread over the N+M tethers (ballot-ordered appends, the
-//     list automaton on lane 0), then the tether-length test and the voxel key;
-//   * one thread then replays the reference's sequential loop over the children in all_combinations_
-//     order -- hash lookup, the "better node" replacement rule with its ran_trigger parity, node
-//     allocation, push_heap -- so node numbering, heap layout and therefore the pop order are identical
-//     to a sequential run.
-// The open list (heap of node ids) and the (g, h) keys its comparisons read live in shared memory when
-// max_nodes * 20 B fits (it does for the defaults), otherwise in global scratch: the sift loops then run at
-// shared-memory latency.  Node payloads (kinematics, entanglement lists) stay in global memory; a node's
-// active_cases array is not stored: active = active_A - count_A(id) + count_node(id) because every change of
-// active_cases is paired with an append/erase of alphas (entangle_utils.cpp:1402-1534).
+// Mapping onto the SM.  A best-first search is a sequential chain of pops, but every pop fans out.  One CTA of 32
+// warps per agent:
+//   * the 25 jerk primitives of the popped node (kinematics + admissibility) are evaluated one LANE per child from
+//     a per-launch table of everything that depends only on the jerk value;
+//   * each child's S-step entanglement chain runs on its own WARP, lanes over the N + M tethers: crossing lists by
+//     ballot-ordered append (wedge products shared between steps and, for the base-side test, between all nodes of
+//     the search), the list automaton on lane 0, then the tether-length test and the voxel key + node-map lookup;
+//   * the collision tests of the popped node (GJK against the N - 1 window hulls, the M static obstacles and the
+//     bases) run on the 7 remaining warps CONCURRENTLY with its speculatively evaluated children;
+//   * one warp then replays the reference's sequential loop over the children in all_combinations_ order -- the
+//     "better node" replacement rule with its ran_trigger parity, node allocation, push_heap -- with child ch in
+//     the registers of lane ch, so node numbering, heap layout and therefore the pop order are those of a
+//     sequential run; the accepted children's payloads are then copied to the node pool by the child warps.
+// The open list (heap of node ids), the (f = g + bias h, h) keys its comparisons read, the children's scratch and
+// the per-agent inputs of the chain live in shared memory while they fit (they do up to ~100 tethers) and in
+// global memory otherwise: same code, generic pointers.  Node payloads (kinematics, entanglement lists) stay in
+// global memory; a node's active_cases array is not stored: active = active_A - count_A(id) + count_node(id)
+// because every change of active_cases is paired with an append/erase of alphas (entangle_utils.cpp:1402-1534).
 //
 // std::priority_queue is restated as libstdc++'s __push_heap / __adjust_heap (CompareCost is not a strict
 // weak order, so the pop order depends on the sift algorithm).  Compiled with --fmad=false: every FP64
@@ -148,7 +151,7 @@ struct NbArena
 NB_HD int nb_search_ch_stride(const NbSearchPar& p) { return (2 * p.S + 2) * p.tcap + (p.N + p.M) + 3 * p.ecap; }
 
 // doubles of scratch per agent: beta lists of the children, then the base squares [N][4][2]
-#define NB_SEARCH_PTS 20  // sample positions of a child: (S + 1) points, S <= 8, and the arc length in the last slot
+#define NB_SEARCH_PTS 28  // per child: (S + 1) sample positions (S <= 8) [0..17], step lengths [18 + s], arc length [27]
 // Strides of the per-tether arrays that lanes read side by side are padded to an ODD number of doubles in shared
 // memory: with an even stride (64 doubles of samples, 16 of bend points, 48 of hull vertices) all 32 lanes of a
 // warp hit the same bank.
@@ -253,7 +256,23 @@ struct NbSearchShared
   NbChildRec rec[NB_SEARCH_MAXCHILD];
 };
 
-NB_HD double nb_norm2(double x, double y) { return sqrt(x * x + y * y); }
+// The kernel is latency-bound on short sequential phases that run once per pop, so its code size matters more than
+// call overhead: with everything inlined it was 277 KB of SASS, far beyond the instruction caches, and every phase
+// started with a run of instruction-fetch misses.  The multi-site helpers below are therefore real functions on the
+// device (one body each); on the host (single-lane emulation) they stay inline.
+#if defined(__CUDA_ARCH__)
+#define NB_OUTLINE __device__ __noinline__
+#else
+#define NB_OUTLINE inline
+#endif
+
+NB_OUTLINE double nb_norm2(double x, double y) { return sqrt(x * x + y * y); }
+NB_OUTLINE bool nb_s_gjk(const double* v1, int n1, const double* v2, int n2) { return nb_gjk_collision(v1, n1, v2, n2); }
+NB_OUTLINE int nb_s_add_alpha_beta(int* toadd, int nadd, NbEntState* es, const double* pk, const NbEntCtx* cx)
+{
+  return nb_add_alpha_beta(toadd, nadd, *es, pk, *cx);
+}
+NB_OUTLINE void nb_s_update_bend_pts(NbEntState* es, const double* pk1, const NbEntCtx* cx) { nb_update_bend_pts(*es, pk1, *cx); }
 
 #if defined(__CUDA_ARCH__)
 #define NB_TICK(slot)                                        \
@@ -472,7 +491,7 @@ NB_HD int nb_search_entangles(const Group<NL>& g, const NbSearchCtx& c, NbEntSta
         // active_cases_old (:813, :880) is only compared where active_cases can have grown, i.e. at the ids of
         // alphasToAdd: remember (id, value before) for those instead of copying the whole array every step
         for (int i = 0; i < nadd; i++) act_old[2 * i] = toadd[2 * i], act_old[2 * i + 1] = es.active[toadd[2 * i] - 1];
-        if (nb_add_alpha_beta(toadd, nadd, es, pk, c.ecx))
+        if (nb_s_add_alpha_beta(toadd, nadd, &es, pk, &c.ecx))
           r = -1;
         else
         {
@@ -483,7 +502,7 @@ NB_HD int nb_search_entangles(const Group<NL>& g, const NbSearchCtx& c, NbEntSta
             if (was < 2 && es.active[a] >= 2) r = 1;
             if (was >= 2 && es.active[a] > was) r = 1;
           }
-          if (r == 0) nb_update_bend_pts(es, pk1, c.ecx);
+          if (r == 0) nb_s_update_bend_pts(&es, pk1, &c.ecx);
         }
       }
       flag[0] = r;
@@ -547,6 +566,9 @@ NB_HD int nb_search_entangles_fast(const Group<NL>& g, const NbSearchCtx& c, NbE
     for (int j = 1; j <= S; j++) flag[3 + j] = 0;  // entries of the crossing list of step j (-1: over tcap)
   }
   g.sync();
+  // lengths of the S steps (:820), one lane each; lane 0 adds them up in step order below
+  for (int s2 = 1 + g.lane; s2 <= S; s2 += NL)
+    pts[18 + s2] = nb_norm2(pts[2 * s2] - pts[2 * (s2 - 1)], pts[2 * s2 + 1] - pts[2 * (s2 - 1) + 1]);
   NB_CTICK(12)
   const int stride = c.samp_stride;
   const bool past = index > num_pol;
@@ -637,7 +659,7 @@ NB_HD int nb_search_entangles_fast(const Group<NL>& g, const NbSearchCtx& c, NbE
     {
       const double* pk = pts + 2 * (s - 1);
       const double* pk1 = pts + 2 * s;
-      arc += nb_norm2(pk1[0] - pk[0], pk1[1] - pk[1]);
+      arc += pts[18 + s];
       const int nadd = nlist[s - 1];
       int* ta = toadd + (size_t)(s - 1) * 2 * p.tcap;
       if (nadd < 0 || es.n_alpha + nadd > NA)
@@ -645,7 +667,7 @@ NB_HD int nb_search_entangles_fast(const Group<NL>& g, const NbSearchCtx& c, NbE
       else
       {
         for (int i = 0; i < nadd; i++) act_old[2 * i] = ta[2 * i], act_old[2 * i + 1] = es.active[ta[2 * i] - 1];
-        if (nb_add_alpha_beta(ta, nadd, es, pk, c.ecx))
+        if (nb_s_add_alpha_beta(ta, nadd, &es, pk, &c.ecx))
           r = -1;
         else
         {
@@ -656,7 +678,7 @@ NB_HD int nb_search_entangles_fast(const Group<NL>& g, const NbSearchCtx& c, NbE
             if (was < 2 && es.active[a] >= 2) r = 1;
             if (was >= 2 && es.active[a] > was) r = 1;
           }
-          if (r == 0) nb_update_bend_pts(es, pk1, c.ecx);
+          if (r == 0) nb_s_update_bend_pts(&es, pk1, &c.ecx);
         }
       }
     }
@@ -805,10 +827,14 @@ NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchSha
   }
   else
     arc = nb_norm2(kin[0] - ist[0], kin[1] - ist[1]);
+  // getIz (:2006-2014): a sum of 32-bit terms (wrap-around), one term per lane
+  uint32_t iz = 0;
+  for (int i = g.lane; i < es.n_alpha; i += NL) iz += (uint32_t)(i + 1) * nb_power_int((uint32_t)es.alpha[2 * i], (uint32_t)es.alpha[2 * i + 1]);
+#if defined(__CUDA_ARCH__)
+  if (NL > 1) iz = __reduce_add_sync(0xffffffffu, iz);
+#endif
   if (g.lane == 0)
   {
-    uint32_t iz = 0;  // getIz (:2006-2014)
-    for (int i = 0; i < es.n_alpha; i++) iz += (uint32_t)(i + 1) * nb_power_int((uint32_t)es.alpha[2 * i], (uint32_t)es.alpha[2 * i + 1]);
     rec.iz = (int)iz;
     rec.ix = nb_voxel_index(kin[0], p.voxel);
     rec.iy = nb_voxel_index(kin[1], p.voxel);
@@ -1172,7 +1198,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
   for (int o = cta.tid; o < N; o += cta.nthreads)
   {
     const int hn = nb_hull_count(c, o, p.num_pol - 1);
-    if (hn > 0 && nb_gjk_collision(c.hull_xy + ((size_t)(o * NB_NPOL + p.num_pol - 1) * NB_HMAX) * 2, hn, sh->goal_hull, 4)) occ = 1;
+    if (hn > 0 && nb_s_gjk(c.hull_xy + ((size_t)(o * NB_NPOL + p.num_pol - 1) * NB_HMAX) * 2, hn, sh->goal_hull, 4)) occ = 1;
   }
   occ = cta.any(occ);
   if (cta.tid == 0)
@@ -1257,12 +1283,12 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
           const int hn = nb_hull_count(c, it, hi - 1);
           const double* hv = c.hull_stage ? c.hull_stage + (size_t)it * c.hstage_stride
                                           : c.hull_xy + ((size_t)(it * NB_NPOL + hi - 1) * NB_HMAX) * 2;
-          if (hn > 0 && nb_gjk_collision(hv, hn, cps, 4)) hit = 1;
+          if (hn > 0 && nb_s_gjk(hv, hn, cps, 4)) hit = 1;
         }
         else if (it < N + M)
         {  // static obstacles
           const int64_t p0 = c.st_ptr[it - N], p1 = c.st_ptr[it - N + 1];
-          if (nb_gjk_collision(c.st_xy + 2 * p0, (int)(p1 - p0), cps, 4)) hit = 1;
+          if (nb_s_gjk(c.st_xy + 2 * p0, (int)(p1 - p0), cps, 4)) hit = 1;
         }
         else if (p.enable_entangle)
         {  // bases of the other agents
@@ -1270,7 +1296,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
           if (ag == c.self) continue;
           const double bx = c.ecx.pb[2 * ag], by = c.ecx.pb[2 * ag + 1];
           if (nb_norm2(cps[0] - bx, cps[1] - by) > safe_dist) continue;
-          if (nb_gjk_collision(c.base_sq + c.bsq_stride * ag, 4, cps, 4)) hit = 1;
+          if (nb_s_gjk(c.base_sq + c.bsq_stride * ag, 4, cps, 4)) hit = 1;
         }
       }
       if (hit) ctl.hit[par] = 1;
@@ -1305,6 +1331,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
           }
           if (dist < p.goal_size && !invalid) ctl.done = 1, ctl.status = 1;
         }
+        NB_TICK(9)
         cta.sync();
         if (ctl.done) break;
       }

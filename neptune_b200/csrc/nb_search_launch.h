@@ -9,4 +9,5 @@ struct NbSearchArgs;
 #define NB_SEARCH_SMEM_MAX (220 * 1024)  // dynamic shared memory the search kernel may ask for
 
 // returns 0, or -1 with *err = CUDA error text
-int nb_search_launch(const NbSearchArgs* a, int B, void* stream, const char** err);
+// smem_attr_set: the caller's per-handle flag (the opt-in shared-memory attribute is per device)
+int nb_search_launch(const NbSearchArgs* a, int B, void* stream, int* smem_attr_set, const char** err);
