@@ -327,6 +327,23 @@ NB_HD void nb_heap_push_at(const NbSearchCtx& c, int hole, int top, int value)
   c.heap[hole] = value;
 }
 
+// the same sift with the keys (f, h) of `value` already in registers (two shared-memory loads less per level)
+NB_HD void nb_heap_push_at_keys(const NbSearchCtx& c, int hole, int top, int value, double fv, double hv)
+{
+  int parent = (hole - 1) / 2;
+  while (hole > top)
+  {
+    const int pid = c.heap[parent];
+    const double cl = c.gh[2 * pid];
+    const bool lower = fabs(cl - fv) < 1e-5 ? c.gh[2 * pid + 1] > hv : cl > fv;  // CompareCost(parent, value)
+    if (!lower) break;
+    c.heap[hole] = pid;
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  c.heap[hole] = value;
+}
+
 // top() + pop(): std::pop_heap (= __pop_heap, __adjust_heap) + pop_back
 NB_HD int nb_heap_pop(const NbSearchCtx& c, int& heap_n)
 {
@@ -351,7 +368,7 @@ NB_HD int nb_heap_pop(const NbSearchCtx& c, int& heap_n)
       c.heap[hole] = c.heap[child - 1];
       hole = child - 1;
     }
-    nb_heap_push_at(c, hole, 0, value);
+    nb_heap_push_at_keys(c, hole, 0, value, c.gh[2 * value], c.gh[2 * value + 1]);
   }
   heap_n--;
   return top;
@@ -938,11 +955,13 @@ __device__ __forceinline__ void nb_search_resolve_warp(const NbSearchCtx& c, NbS
   int n_used = ctl.n_used, heap_n = ctl.heap_n, ran = ctl.ran_trigger;
   const int first_new = n_used;
   int my_id = -1;
-  for (int ch = 0; ch < p.nchild; ch++)
+  unsigned todo = __ballot_sync(FULL, valid != 0);  // the invalid children only cost a `continue` in the reference
+  while (todo)
   {
+    const int ch = __ffs(todo) - 1;
+    todo &= todo - 1;
     if (!root && n_used == p.max_nodes - 1) break;  // "run out of memory" (:1060-1064)
     if (root && n_used >= p.max_nodes) break;
-    if (!__shfl_sync(FULL, valid, ch)) continue;
     int f = -1, f_state = 0, f_index = 0, sib = -1;
     if (!root)
     {
@@ -986,9 +1005,9 @@ __device__ __forceinline__ void nb_search_resolve_warp(const NbSearchCtx& c, NbS
     if (lane == ch) my_id = id;
     if (lane == 0)
     {
-      c.gh[2 * id] = sh->rec[ch].f, c.gh[2 * id + 1] = sh->rec[ch].h, c.ng[id] = sh->rec[ch].g;
-      c.heap[heap_n] = id;
-      nb_heap_push_at(c, heap_n, 0, id);
+      const double fv = sh->rec[ch].f, hv = sh->rec[ch].h;
+      c.gh[2 * id] = fv, c.gh[2 * id + 1] = hv, c.ng[id] = sh->rec[ch].g;
+      nb_heap_push_at_keys(c, heap_n, 0, id, fv, hv);
     }
     __syncwarp();
     heap_n++, n_used++;
@@ -1001,20 +1020,7 @@ __device__ __forceinline__ void nb_search_resolve_warp(const NbSearchCtx& c, NbS
       for (int ch = 0; ch < p.nchild; ch++)
         if (sh->rec[ch].accept_id >= 0) nb_hash_insert(c, sh->rec[ch].ix, sh->rec[ch].iy, sh->rec[ch].iz, sh->rec[ch].accept_id);
   }
-  else if (my_id >= 0)
-  {
-    const uint32_t mask = (uint32_t)(p.hcap - 1);
-    uint32_t q = nb_hash3(ix, iy, iz) & mask;
-    for (;;)
-    {
-      if (atomicCAS(&c.hash[q].w, 0, my_id + 1) == 0)
-      {
-        c.hash[q].x = ix, c.hash[q].y = iy, c.hash[q].z = iz;
-        break;
-      }
-      q = (q + 1) & mask;
-    }
-  }
+  // (node form: the accepted children's voxels go into the node map during the payload copy, in parallel)
   if (lane == 0) ctl.n_used = n_used, ctl.heap_n = heap_n, ctl.ran_trigger = ran, ctl.first_new = first_new;
 }
 #endif
@@ -1367,6 +1373,22 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
           NbInt4 m;
           m.x = cur, m.y = par_index + 1, m.z = 1, m.w = rec.n_alpha | (rec.n_bend << 16);
           c.meta[id] = m;
+#if defined(__CUDA_ARCH__)
+          if (cur >= 0)
+          {  // expanded_nodes_.insert (:1219): the accepted siblings have distinct voxels, so they insert concurrently
+            const uint32_t mask = (uint32_t)(p.hcap - 1);
+            uint32_t q = nb_hash3(rec.ix, rec.iy, rec.iz) & mask;
+            for (;;)
+            {
+              if (atomicCAS(&c.hash[q].w, 0, id + 1) == 0)
+              {
+                c.hash[q].x = rec.ix, c.hash[q].y = rec.iy, c.hash[q].z = rec.iz;
+                break;
+              }
+              q = (q + 1) & mask;
+            }
+          }
+#endif
         }
       }
       cta.sync();
