@@ -681,6 +681,10 @@ NB_HD int nb_search_entangles_fast(const Group<NL>& g, const NbSearchCtx& c, NbE
       int* ta = toadd + (size_t)(s - 1) * 2 * p.tcap;
       if (nadd < 0 || es.n_alpha + nadd > NA)
         r = 1;  // :844-848
+      else if (nadd == 0 && M == 0 && es.n_bend == 0)
+      {  // no crossing in this step, no static obstacle whose beta could change sign, no bend point to release:
+         // addAlphaBetaToList and updateBendPts leave the state as it is
+      }
       else
       {
         for (int i = 0; i < nadd; i++) act_old[2 * i] = ta[2 * i], act_old[2 * i + 1] = es.active[ta[2 * i] - 1];
@@ -853,8 +857,6 @@ NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchSha
   if (g.lane == 0)
   {
     rec.iz = (int)iz;
-    rec.ix = nb_voxel_index(kin[0], p.voxel);
-    rec.iy = nb_voxel_index(kin[1], p.voxel);
     rec.n_alpha = es.n_alpha, rec.n_bend = es.n_bend;
     rec.g = sh->par_g + arc;
     rec.h = nb_norm2(kin[0] - c.goal[0], kin[1] - c.goal[1]) + 0.3 * (double)es.n_alpha + 1.0 * (double)es.n_bend;
@@ -1257,6 +1259,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
 #pragma unroll
         for (int k = 0; k < NB_SEARCH_KIN; k++) rec.kin[k] = kin[k];
         rec.valid = 0, rec.accept_id = -1;
+        rec.ix = nb_voxel_index(kin[0], p.voxel), rec.iy = nb_voxel_index(kin[1], p.voxel);  // :1172-1173
       }
       cta.sync_children();
       NB_TICK(7)
@@ -1282,6 +1285,9 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
         }
         cta.sync_aux();
       }
+#if defined(__CUDA_ARCH__)
+      if (c.prof && cta.aux_tid == 0) c.prof[9] += clock64() - aux_t0;   // staging part of the auxiliary path
+#endif
       for (int it = cta.aux_tid; it < 2 * N + M && !hit; it += cta.aux_n)
       {
         if (it < N)
@@ -1337,7 +1343,6 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
           }
           if (dist < p.goal_size && !invalid) ctl.done = 1, ctl.status = 1;
         }
-        NB_TICK(9)
         cta.sync();
         if (ctl.done) break;
       }

@@ -57,7 +57,7 @@ def main():
     names = ["chains||collide", "resolve", "copy", "pop", "active", "endpoint", "setup", "primitives"]
     pops = max(1, int(got.stats[slow, 1]))
     print("  cycles per pop (slowest agent): " + ", ".join(f"{n} {pc[slow, i] / pops:.0f}" for i, n in enumerate(names[:8])))
-    cn = ["(aux collide path)", "(endpoint t0 work)", "chain", "key+lookup", "step geometry", "crossing tests", "automaton"]
+    cn = ["(aux collide path)", "(aux: hull staging)", "chain", "key+lookup", "step geometry", "crossing tests", "automaton"]
     print("  child 0, cycles per pop: " + ", ".join(f"{n} {pc[slow, 8 + i] / pops:.0f}" for i, n in enumerate(cn)) + f", slowest child {pc[slow, 15] / pops:.0f}")
     try:
         from oracle import oracle as orc
