@@ -271,11 +271,24 @@ NB_HD void nb_sample_points(const NbConsts& cs, const double* rec, double t_star
 }
 
 // ------------------------------------------------------------------------------------------ GJK
+// argmax of d . v over the vertices, first maximum wins (gjk.cpp:30-47).  The dot products of four vertices are
+// formed independently before the (sequential, order-preserving) comparisons, so that their latencies overlap.
 NB_HD int nb_gjk_furthest(const double* v, int n, double dx, double dy)
 {
   double best = NB_ADD(NB_MUL(dx, v[0]), NB_MUL(dy, v[1]));
-  int idx = 0;
-  for (int i = 1; i < n; i++)
+  int idx = 0, i = 1;
+  for (; i + 3 < n; i += 4)
+  {
+    const double pa = NB_ADD(NB_MUL(dx, v[2 * i]), NB_MUL(dy, v[2 * i + 1]));
+    const double pb = NB_ADD(NB_MUL(dx, v[2 * i + 2]), NB_MUL(dy, v[2 * i + 3]));
+    const double pc = NB_ADD(NB_MUL(dx, v[2 * i + 4]), NB_MUL(dy, v[2 * i + 5]));
+    const double pd = NB_ADD(NB_MUL(dx, v[2 * i + 6]), NB_MUL(dy, v[2 * i + 7]));
+    if (pa > best) best = pa, idx = i;
+    if (pb > best) best = pb, idx = i + 1;
+    if (pc > best) best = pc, idx = i + 2;
+    if (pd > best) best = pd, idx = i + 3;
+  }
+  for (; i < n; i++)
   {
     const double p = NB_ADD(NB_MUL(dx, v[2 * i]), NB_MUL(dy, v[2 * i + 1]));
     if (p > best)

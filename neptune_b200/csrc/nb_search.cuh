@@ -1027,6 +1027,24 @@ __device__ __forceinline__ void nb_search_resolve_warp(const NbSearchCtx& c, NbS
 }
 #endif
 
+// the jerk primitives of the node published in sh->par_*: one LANE per child (a warp per child would run the same
+// scalar FP64 chain on 32 lanes 25 times over), into the child records
+template <class Cta>
+NB_HD void nb_search_primitives(Cta& cta, const NbSearchCtx& c, NbSearchShared* sh, bool root)
+{
+  const NbSearchPar& p = *c.p;
+  for (int ch = cta.tid; ch < p.nchild; ch += cta.nthreads)
+  {
+    NbChildRec& rec = sh->rec[ch];
+    double kin[NB_SEARCH_KIN];
+    rec.prim_ok = nb_search_primitive(c, sh->tab, sh->par_kin, ch, root, kin) ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < NB_SEARCH_KIN; k++) rec.kin[k] = kin[k];
+    rec.valid = 0, rec.accept_id = -1;
+    rec.ix = nb_voxel_index(kin[0], p.voxel), rec.iy = nb_voxel_index(kin[1], p.voxel);  // :1172-1173
+  }
+}
+
 // the CTA-wide search of one agent.  Cta: tid, nthreads, warp, nwarps, lane, sync(), any(int)
 // bytes of shared memory that hold every per-agent working set (the launcher clamps to what the SM has)
 inline size_t nb_search_arena_wanted(const NbSearchPar& p)
@@ -1239,6 +1257,8 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
     ctl.hit[0] = ctl.hit[1] = 0, ctl.invalid = 0, ctl.cmax = 0;
   }
   cta.sync();
+  nb_search_primitives(cta, c, sh, true);
+  cta.sync();
   NB_TICK(6)
   int par = 0;  // iteration parity: the collision flag of one iteration is cleared during the next
   // Every iteration handles one popped node `cur` (the first one: the root).  The reference tests the node
@@ -1247,24 +1267,9 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
   // creates nodes runs only if `cur` survived, so the open list, the node numbering and the result are unchanged.
   for (;;)
   {
+    // one WARP per child for the entanglement chain (the primitives were evaluated when the node was published)
     if (cta.child)
-    {
-      // the 25 jerk primitives: one LANE per child (a warp per child would run the same scalar FP64 chain on 32
-      // lanes 25 times over and saturate the SM's FP64 pipe), then one WARP per child for the entanglement chain
-      for (int ch = cta.tid; ch < p.nchild; ch += cta.nthreads)
-      {
-        NbChildRec& rec = sh->rec[ch];
-        double kin[NB_SEARCH_KIN];
-        rec.prim_ok = nb_search_primitive(c, sh->tab, sh->par_kin, ch, cur < 0, kin) ? 1 : 0;
-#pragma unroll
-        for (int k = 0; k < NB_SEARCH_KIN; k++) rec.kin[k] = kin[k];
-        rec.valid = 0, rec.accept_id = -1;
-        rec.ix = nb_voxel_index(kin[0], p.voxel), rec.iy = nb_voxel_index(kin[1], p.voxel);  // :1172-1173
-      }
-      cta.sync_children();
-      NB_TICK(7)
       for (int ch = cta.warp; ch < p.nchild; ch += cta.nwarps) nb_search_child<NL>(g, c, sh, cur, ch);
-    }
     if (cta.aux && cur >= 0)
     {  // collidesWithObstacles2dSolve (:1514-1580) and collidesWithBases2d (:1583-1627) of the popped node
 #if defined(__CUDA_ARCH__)
@@ -1431,7 +1436,10 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
       const int na = sh->par_na;
       const int* al = sh->par_alpha;
       int invalid = 0;
-      for (int q = cta.tid; q < NA; q += cta.nthreads)
+      // the first warp evaluates the node's 25 jerk primitives meanwhile (they need neither list nor active cases)
+      const int t_first = cta.nthreads > 32 ? 32 : 0;
+      if (cta.tid < 32) nb_search_primitives(cta, c, sh, false);
+      for (int q = cta.tid - t_first; q >= 0 && q < NA; q += cta.nthreads - t_first)
       {
         int v = c.a_active[q];
         for (int k = 0; k < c.a_na; k++) v -= (c.a_alpha[2 * k] == q + 1);
