@@ -434,7 +434,16 @@ def run_ours(args):
                                     "sample": f"{B} agents x {reps} whole cycles of scene 0 ({el:.1f} s), "
                                               "oracle/neptune_oracle.c orc_cycle_batch"}
         if world == 1 and args.workload == "grid64" and not args.no_front_end:
-            line["front_end"] = measure_front_end(par, agents, dev, scenes[0], static, args.front_end_steps, not args.no_cpu)
+            if args.front_end_world > 1:   # the 64-agents-per-GPU world of K GPUs, searched (and replanned) by this one GPU
+                from neptune_b200.scenes import make_scene
+                par_fe = world_params(args.front_end_world)
+                agents_fe = np.arange(par_fe.num_of_agents)
+                gen = capi.Solver(par_fe, device=local_rank)
+                scene_fe = make_scene(par_fe, SEED, agents=agents_fe, ent_backend=capi.DeviceEntBackend(gen))
+                gen.close()
+                line["front_end"] = measure_front_end(par_fe, agents_fe, dev, scene_fe, None, args.front_end_steps, not args.no_cpu)
+            else:
+                line["front_end"] = measure_front_end(par, agents, dev, scenes[0], static, args.front_end_steps, not args.no_cpu)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -454,6 +463,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
     ap.add_argument("--no-front-end", action="store_true", help="skip the front-end (K0 search) measurement")
     ap.add_argument("--front-end-steps", type=int, default=10)
+    ap.add_argument("--front-end-world", type=int, default=1,
+                    help="front_end block on the world of K x 64 agents, all searched by ONE GPU (default 1 = the bench world)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -9,18 +9,13 @@
 static __host__ __device__ inline size_t nb_search_shared_bytes() { return (sizeof(NbSearchShared) + 15) & ~(size_t)15; }
 
 // 25 "child" warps (one per jerk sample) + 7 auxiliary warps that run the collision tests of the popped node
-// while the children are evaluated.  sync_children is a named barrier over the child warps only.
+// while the children are evaluated.  sync_aux is a named barrier over the auxiliary warps only.
 struct NbCtaDev
 {
   int tid, nthreads, warp, nwarps, lane, aux_tid, aux_n;
   bool child, aux;
   __device__ __forceinline__ void sync() const { __syncthreads(); }
   __device__ __forceinline__ int any(int p) const { return __syncthreads_or(p); }
-  __device__ __forceinline__ void sync_children() const
-  {
-    __syncwarp();  // bar.sync is the aligned form: the lanes of a warp must arrive together
-    asm volatile("bar.sync 1, %0;" ::"r"(NB_SEARCH_CHILD_THREADS) : "memory");
-  }
   __device__ __forceinline__ void sync_aux() const
   {
     __syncwarp();

@@ -171,7 +171,7 @@ struct NbChildRec
 
 struct NbSearchCtl
 {
-  int done, status, cur, best, closest, n_used, heap_n, pops, ran_trigger, goal_occupied, first_new, overflow;
+  int done, status, cur, n_path, closest, n_used, heap_n, pops, ran_trigger, goal_occupied, first_new, overflow;
   int n_acc, acc[NB_SEARCH_MAXCHILD];  // children accepted so far in the expansion being resolved
   int cmax;                            // measurement: slowest child chain of the current expansion (cycles)
   int hit[2], invalid;                 // the popped node: collides (flag per iteration parity) / has an active case above 1
@@ -1229,7 +1229,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
   occ = cta.any(occ);
   if (cta.tid == 0)
   {
-    ctl.done = 0, ctl.status = 2, ctl.cur = -1, ctl.best = -1, ctl.closest = -1, ctl.n_used = 0, ctl.heap_n = 0;
+    ctl.done = 0, ctl.status = 2, ctl.cur = -1, ctl.n_path = 0, ctl.closest = -1, ctl.n_used = 0, ctl.heap_n = 0;
     ctl.pops = 0, ctl.ran_trigger = 0, ctl.goal_occupied = occ, ctl.first_new = 0, ctl.overflow = 0;
     ctl.smallest = DBL_MAX;
     nb_search_build_tab(p, c.comb, sh->tab);
@@ -1473,10 +1473,10 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
           if (idx > nn) nn = idx;
         }
       }
-    ctl.best = nn;
+    ctl.n_path = nn;
   }
   cta.sync();
-  const int n = ctl.best;
+  const int n = ctl.n_path;
   if (cta.tid == 0)
   {
     a.status[b] = ctl.status;

@@ -205,7 +205,6 @@ struct EmulCta
   int tid = 0, nthreads = 1, warp = 0, nwarps = 1, lane = 0, aux_tid = 0, aux_n = 1;
   bool child = true, aux = true;
   void sync() const {}
-  void sync_children() const {}
   void sync_aux() const {}
   int any(int p) const { return p; }
 };

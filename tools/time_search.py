@@ -1,5 +1,6 @@
-"""Times the front-end search kernel (K0) on one scene against the oracle; prints per-stage numbers.
-Measurement helper (not the bench): python tools/time_search.py [cfg] [seed] [max_expansions]"""
+"""Times the front-end search kernel (K0) on one scene and prints the kernel's own per-phase cycle counters.
+Measurement helper (not the bench; the comparison with the oracle lives in bench.py's front_end block and in tests/):
+python tools/time_search.py [cfg] [seed] [max_expansions] [planning agents]"""
 import os
 import sys
 import time
@@ -10,7 +11,6 @@ import torch
 
 from neptune_b200 import capi, config
 from neptune_b200.scenes import make_scene, make_search_batch
-from neptune_b200.search import SearchResult
 
 
 def main():
@@ -59,17 +59,6 @@ def main():
     print("  cycles per pop (slowest agent): " + ", ".join(f"{n} {pc[slow, i] / pops:.0f}" for i, n in enumerate(names[:8])))
     cn = ["(aux collide path)", "(aux: hull staging)", "chain", "key+lookup", "step geometry", "crossing tests", "automaton"]
     print("  child 0, cycles per pop: " + ", ".join(f"{n} {pc[slow, 8 + i] / pops:.0f}" for i, n in enumerate(cn)) + f", slowest child {pc[slow, 15] / pops:.0f}")
-    try:
-        from oracle import oracle as orc
-        ref = SearchResult.empty(sb)
-        nt = os.cpu_count() or 1
-        t = time.perf_counter()
-        orc.search_batch(sb, ref, nt)
-        dt = time.perf_counter() - t
-        same = all(np.array_equal(getattr(ref, f), getattr(got, f)) for f in ("status", "n_int", "coeff", "esv_alpha", "stats"))
-        print(f"  oracle ({nt} threads): {dt * 1e3:.2f} ms; identical: {same}")
-    except Exception as e:  # oracle is test infrastructure; this helper still reports the GPU side
-        print("  oracle unavailable:", e)
 
 
 if __name__ == "__main__":
