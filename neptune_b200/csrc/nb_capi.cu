@@ -1359,6 +1359,34 @@ extern "C" int nb_search_batch(nb_handle* h, const nb_search_args* u, void* stre
     g_err = "nb_search_batch: num_sample_per_interval > 8 is not supported";
     return NB_ERR_ARG;
   }
+  if (!u->agent_id || !u->init || !u->goal || !u->coeffs_z || !u->hull_xy || !u->hull_cnt || !u->samp || !u->known ||
+      !u->es.cnt || !u->es.alpha || !u->es.beta || !u->es.bend || !u->es.active || !u->bp_cnt || !u->bp_xy || !u->comb ||
+      !u->status || !u->solved || !u->n_int || !u->coeff || !u->esv.cnt || !u->esv.alpha || !u->esv.beta || !u->esv.bend ||
+      !u->esv.active || !u->stats || !u->cost || (u->group && u->n_groups < 1))
+  {
+    g_err = "nb_search_batch: null argument";
+    return NB_ERR_ARG;
+  }
+  if (space == NB_HOST)
+  {  // host arrays can be checked before anything is launched
+    for (int b = 0; b < B; b++)
+    {
+      if (u->agent_id[b] < 1 || u->agent_id[b] > N || (u->group && (u->group[b] < 0 || u->group[b] >= u->n_groups)))
+      {
+        g_err = "nb_search_batch: agent_id or group out of range";
+        return NB_ERR_ARG;
+      }
+      const uint8_t* cb = u->comb + (u->comb_shared ? 0 : (size_t)b * sp.num_samples * sp.num_samples);
+      unsigned seen = 0;
+      for (int k = 0; k < sp.num_samples * sp.num_samples; k++)
+        if (cb[k] < 32) seen |= 1u << cb[k];
+      if (seen != (sp.num_samples * sp.num_samples >= 32 ? 0xffffffffu : (1u << (sp.num_samples * sp.num_samples)) - 1))
+      {
+        g_err = "nb_search_batch: comb is not a permutation of the jerk samples";
+        return NB_ERR_ARG;
+      }
+    }
+  }
   if (M > 0 && (!h->d_strep || !h->d_st_longest || !h->d_st_xy))
   {
     g_err = "nb_search_batch with static obstacles needs nb_set_static(strep) and nb_set_static_longest first";

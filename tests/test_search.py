@@ -405,3 +405,23 @@ def test_cpp_shim_kinodynamic_search(capi, oracle, tmp_path):
             vals = [int(v) for v in out[1 + 3 * n + i].split()]
             assert vals[0] == ref.esv_cnt[b, i, 0]
             assert vals[1:] == ref.esv_alpha[b, i, :vals[0]].reshape(-1).tolist()
+
+
+@pytest.mark.gpu
+def test_gpu_search_rejects_bad_arguments(capi, oracle):
+    """Argument errors are reported as NB_ERR_ARG before anything is launched (no exceptions cross the ABI)."""
+    sc, sb = _batch(oracle, "mtlp5", 2002)
+    s = _gpu_solver(capi, sc, sb)
+    bad = dataclasses.replace(sb, comb=sb.comb.copy())
+    bad.comb[0, 0] = bad.comb[0, 1]                      # not a permutation
+    with pytest.raises(capi.NbError, match="permutation"):
+        s.search(bad)
+    bad = dataclasses.replace(sb, group=sb.group + 7)     # group index out of range
+    with pytest.raises(capi.NbError, match="out of range"):
+        s.search(bad)
+    s2 = capi.Solver(sb.par)                              # search before nb_search_configure
+    with pytest.raises(capi.NbError, match="configure"):
+        s2.search(sb)
+    s2.close()
+    _assert_same(_oracle_search(oracle, sb), s.search(sb))   # the handle is still usable
+    s.close()

@@ -209,3 +209,53 @@ def test_static_obstacle_representation(oracle):
                 assert dist < 1e-9
                 assert abs(longest[m, c] - np.linalg.norm(q - strep[m, c], axis=1).max()) < 1e-12
     assert n_ok >= 25
+
+
+@pytest.mark.gpu
+def test_gpu_tracker_device_pointers(oracle):
+    """NB_DEVICE form of nb_entangle_track_batch (state and checking positions resident in HBM, asynchronous on the
+    stream) gives the same bits as the NB_HOST form."""
+    import ctypes as C
+    import torch
+    from neptune_b200 import capi
+    par, strep = _scene(oracle, "obst8", 3003)
+    sc = make_scene(par, 3003, sync=True)
+    s = capi.Solver(par)
+    s.set_static(sc.batch.st_ptr, sc.batch.st_xy, sc.strep)
+    start, silent, frames = _walk(par, 31, ticks=6)
+    N = par.num_of_agents
+    ids = np.arange(1, N + 1, dtype=np.int32)
+    st, pp, ppa = _init(par, start, silent)
+    dev = torch.device("cuda", 0)
+    to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    d_st = {k: to(getattr(st, k)) for k in ("cnt", "alpha", "beta", "bend", "active")}
+    d_pp, d_ppa, d_ids = to(pp), to(ppa), to(ids)
+    f = capi.lib().nb_entangle_track_batch
+    P = C.c_void_p
+    f.argtypes = [P, C.c_int32, C.c_int32, P, P, P, P, P, capi.NbEntState, P, P, P, P, P, P, P]
+    for fr in frames:
+        latest = np.repeat(fr["latest"][None], N, axis=0)
+        res_h, st, pp, ppa = s.entangle_track(ids, fr["bp_cnt"], fr["bp_xy"], fr["bp_cnt_prev"], fr["bp_xy_prev"], st, pp, ppa,
+                                              latest, fr["cur"], fr["elapsed"])
+        keep = [to(fr["bp_cnt"]), to(fr["bp_xy"]), to(fr["bp_cnt_prev"]), to(fr["bp_xy_prev"]), to(latest), to(fr["cur"]),
+                to(fr["elapsed"]), torch.zeros(N, dtype=torch.int32, device=dev)]
+        es = capi.NbEntState()
+        es.cnt, es.alpha, es.beta, es.bend, es.active = (P(d_st[k].data_ptr()) for k in ("cnt", "alpha", "beta", "bend", "active"))
+        p = lambda t: P(t.data_ptr())  # noqa: E731
+        rc = f(s.handle, N, capi.NB_DEVICE, p(d_ids), p(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]), es, p(d_pp), p(d_ppa),
+               p(keep[4]), p(keep[5]), p(keep[6]), p(keep[7]), P(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert np.array_equal(keep[7].cpu().numpy(), res_h)
+        ok = res_h >= 0
+        assert np.array_equal(d_st["cnt"].cpu().numpy()[ok], st.cnt[ok])
+        assert np.array_equal(d_pp.cpu().numpy()[ok], pp[ok]) and np.array_equal(d_ppa.cpu().numpy()[ok], ppa[ok])
+        for b in np.flatnonzero(ok):
+            na = st.cnt[b, 0]
+            assert np.array_equal(d_st["alpha"].cpu().numpy()[b, :na], st.alpha[b, :na])
+            assert np.array_equal(d_st["active"].cpu().numpy()[b], st.active[b])
+        # keep both sides on the same state where the reference would have exited
+        for k in d_st:
+            d_st[k].copy_(to(getattr(st, k)))
+        d_pp.copy_(to(pp)), d_ppa.copy_(to(ppa))
+    s.close()
