@@ -173,6 +173,7 @@ struct NbSearchCtl
 {
   int done, status, cur, n_path, closest, n_used, heap_n, pops, ran_trigger, goal_occupied, first_new, overflow;
   int n_acc, acc[NB_SEARCH_MAXCHILD];  // children accepted so far in the expansion being resolved
+  int ovf_iter;                        // storage overflow seen while evaluating the children of the current node
   int cmax;                            // measurement: slowest child chain of the current expansion (cycles)
   int hit[2], invalid;                 // the popped node: collides (flag per iteration parity) / has an active case above 1
   double smallest;
@@ -843,7 +844,7 @@ NB_HD void nb_search_child(const Group<NL>& g, const NbSearchCtx& c, NbSearchSha
                                : nb_search_entangles_fast<NL>(g, c, es, kin, index, toadd, act_old, sh->ctl.flag[ch], &arc, ch, sh->tab.tt,
                                                               es.beta + p.ecap);
     NB_CTICK(10)
-    if (r < 0 && g.lane == 0) sh->ctl.overflow = 1;
+    if (r < 0 && g.lane == 0) sh->ctl.ovf_iter = 1;  // counts only if this node is really expanded (speculation)
     if (r != 0) return;
   }
   else
@@ -1254,7 +1255,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
     for (int k = 0; k < NB_SEARCH_KIN; k++) sh->par_kin[k] = k < 6 ? c.init[k] : 0.0;
     sh->par_index = 0, sh->par_g = 0.0, sh->par_na = c.a_na, sh->par_nb = c.a_nb;
     sh->par_alpha = c.a_alpha, sh->par_beta = c.a_beta, sh->par_bend = c.a_bend;
-    ctl.hit[0] = ctl.hit[1] = 0, ctl.invalid = 0, ctl.cmax = 0;
+    ctl.hit[0] = ctl.hit[1] = 0, ctl.invalid = 0, ctl.cmax = 0, ctl.ovf_iter = 0;
   }
   cta.sync();
   nb_search_primitives(cta, c, sh, true);
@@ -1355,6 +1356,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
     NB_TICK(5)
     if (expand)
     {
+      if (cta.tid == 0 && ctl.ovf_iter) ctl.overflow = 1;
       // ---- the sequential half of expandAndAddToQueue(cur), then the accepted children's payload
       const int par_index = sh->par_index;
 #if defined(__CUDA_ARCH__)
@@ -1409,7 +1411,7 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
     par ^= 1;
     if (cta.tid == 0)
     {
-      ctl.hit[par] = 0;
+      ctl.hit[par] = 0, ctl.ovf_iter = 0;
       if (ctl.heap_n == 0)
         ctl.done = 1, ctl.status = 2;
       else if (ctl.pops >= p.max_exp)
