@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(32) k_entangle(NbEntArgs a)
 {
   extern __shared__ int smem_i[];
   Group<32> g(threadIdx.x);
-  nb_entangle_task<32>(g, blockIdx.x, a, smem_i, smem_i + 2 * a.tcap);
+  nb_entangle_task<32>(g, blockIdx.x, a, smem_i, smem_i + 4 * a.tcap);
 }
 
 // ---- K1 / K5 kernels
@@ -895,19 +895,13 @@ int ent_common(nb_handle* h, NbEntArgs* a, int mode, int B, int space, const int
   if ((rc = stage_in(h, 1, space, known, (size_t)B * N, st, &a->known))) return rc;
   if ((rc = stage_in(h, 2, space, bp_cnt, (size_t)N, st, &a->bp_cnt))) return rc;
   if ((rc = stage_in(h, 3, space, bp_xy, (size_t)N * h->par.bp_max * 2, st, &a->bp_xy))) return rc;
-  if (h->ent_scratch.ensure((size_t)B * (N + M) * sizeof(int)))  // own scratch: K3 may overlap K2/K4 on another stream
-  {
-    g_err = "cudaMalloc failed";
-    return NB_ERR_CUDA;
-  }
-  a->act_old = (int*)h->ent_scratch.p;
   a->err = (int*)h->err.p;
   return NB_OK;
 }
 
 int ent_launch(nb_handle* h, const NbEntArgs& a, int B, cudaStream_t st)
 {
-  const size_t sm = (size_t)(2 * a.tcap + 4) * sizeof(int);
+  const size_t sm = (size_t)(4 * a.tcap + 4) * sizeof(int);
   k_entangle<<<B, 32, sm, st>>>(a);
   h->launches += 1;
   NB_CUDA(cudaGetLastError());

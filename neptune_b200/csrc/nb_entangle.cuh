@@ -728,12 +728,9 @@ NB_HD void nb_eval_xy(const double* cxy /*[3][8][4] of agent*/, int i, double t,
 template <int NL>
 NB_HD int nb_ent_interval_pass(const Group<NL>& g, NbEntState& es, const NbEntCtx& cx, const double* cxy, int ii,
                                const double* samp, const unsigned char* known, int num_pol, int S, double T, int limit,
-                               int* toadd, int tcap, int* act_old, int* flag /*shared int*/)
+                               int* toadd, int tcap, int* pairs /*[tcap][2] shared*/, int* flag /*shared int*/)
 {
-  const int NA = cx.N + cx.M;
   double pk[2] = { cxy[4 * ii + 3], cxy[32 + 4 * ii + 3] }, pk1[2];
-  for (int q = g.lane; q < NA; q += NL) act_old[q] = es.active[q];
-  g.sync();
   for (int j = 1; j <= S; j++)
   {
     const double t = (j < S) ? T * j / S : T;
@@ -757,16 +754,25 @@ NB_HD int nb_ent_interval_pass(const Group<NL>& g, NbEntState& es, const NbEntCt
       int r = 0;
       if (es.n_alpha + nadd > limit)
         r = 1;
-      else if (nb_add_alpha_beta(toadd, nadd, es, pk, cx))
-        r = -1;
       else
       {
-        for (int a = 0; a < cx.N; a++)
+        // active_cases_old (kinodynamic_search.cpp:813, :880 / :909, :971) is only compared where active_cases can
+        // have grown, i.e. at the ids of alphasToAdd: remember (id, value before) for those instead of copying and
+        // scanning the whole array (N + M entries in global memory) every step
+        for (int i = 0; i < nadd; i++) pairs[2 * i] = toadd[2 * i], pairs[2 * i + 1] = es.active[toadd[2 * i] - 1];
+        if (nb_add_alpha_beta(toadd, nadd, es, pk, cx))
+          r = -1;
+        else
         {
-          if (act_old[a] < 2 && es.active[a] >= 2) r = 1;
-          if (act_old[a] >= 2 && es.active[a] > act_old[a]) r = 1;
+          for (int i = 0; i < nadd; i++)
+          {
+            const int a = pairs[2 * i] - 1, was = pairs[2 * i + 1];
+            if (a >= cx.N) continue;
+            if (was < 2 && es.active[a] >= 2) r = 1;
+            if (was >= 2 && es.active[a] > was) r = 1;
+          }
+          if (r == 0) nb_update_bend_pts(es, pk1, cx);
         }
-        if (r == 0) nb_update_bend_pts(es, pk1, cx);
       }
       flag[0] = r;
       flag[1] = es.n_alpha;
@@ -778,8 +784,6 @@ NB_HD int nb_ent_interval_pass(const Group<NL>& g, NbEntState& es, const NbEntCt
     es.n_bend = flag[2];
     g.sync();
     if (r != 0) return r;
-    for (int q = g.lane; q < NA; q += NL) act_old[q] = es.active[q];
-    g.sync();
     pk[0] = pk1[0];
     pk[1] = pk1[1];
   }
@@ -815,19 +819,18 @@ struct NbEntArgs
   const double* latest;          // [B][N][2]
   const double* elapsed_ms;      // [B]
   int* result;           // done / entangled / tracker result
-  int* act_old;          // [B][N+M] scratch
   int* err;
 };
 
 template <int NL>
-NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* toadd /*[tcap][2]*/, int* flag /*[4]*/)
+NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* toadd /*[2 tcap][2]: list, then pairs*/, int* flag /*[4]*/)
 {
   const int NA = a.N + a.M;
   NbEntCtx cx;
   cx.N = a.N, cx.M = a.M, cx.self = a.agent_id[b] - 1, cx.cap = a.cap, cx.bp_max = a.bp_max, cx.bp_stride = 2 * a.bp_max;
   cx.pb = a.pb, cx.strep = a.strep, cx.bp_cnt = a.bp_cnt, cx.bp_xy = a.bp_xy;
   const uint8_t* known = a.known + (size_t)b * a.N;
-  int* act_old = a.act_old + (size_t)b * NA;
+  int* pairs = toadd + 2 * a.tcap;  // shared: (id, active before) of the entries of one step
   NbEntState es;
   if (a.mode == 1)
   {  // work on slot 0 of the output, then replicate forward
@@ -916,7 +919,7 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
   {  // entangleCheckGivenPwp: interval 0 only (kinodynamic_search.cpp:899, :982-983)
     int r = 0;
     if (a.n_int[b] > 0)
-      r = nb_ent_interval_pass<NL>(g, es, cx, cxy, 0, samp, known, a.num_pol, a.S, a.T, 3 * NA, toadd, a.tcap, act_old, flag);
+      r = nb_ent_interval_pass<NL>(g, es, cx, cxy, 0, samp, known, a.num_pol, a.S, a.T, 3 * NA, toadd, a.tcap, pairs, flag);
     if (r < 0) bad = 1;
     if (g.lane == 0)
     {
@@ -950,7 +953,7 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
         if (i <= n && !bad)
         {
           const int r = nb_ent_interval_pass<NL>(g, es, cx, cxy, i - 1, samp, known, a.num_pol, a.S, a.T, NA, toadd,
-                                                 a.tcap, act_old, flag);
+                                                 a.tcap, pairs, flag);
           if (r < 0) bad = 1;
           if (r > 0 && done == n) done = i - 1;
         }

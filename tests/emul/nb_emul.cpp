@@ -123,12 +123,11 @@ extern "C" int emul_entangle(const nb_params* par, const double* pb, const doubl
   a.agent_id = agent_id, a.known = known, a.bp_cnt = bp_cnt, a.bp_xy = bp_xy, a.pb = pb, a.strep = strep;
   a.st = st, a.out = out, a.n_int = n_int, a.coeff = coeff, a.samp = samp, a.samp_shared = samp_shared;
   a.prev_pos = prev_pos, a.prev_pos_agent = prev_pos_agent, a.cur = cur, a.samp0 = samp0, a.result = result;
-  std::vector<int> act_old((size_t)B * (N + M)), toadd(2 * a.tcap + 8);
+  std::vector<int> toadd(4 * a.tcap + 8);
   int err = 0;
-  a.act_old = act_old.data();
   a.err = &err;
   Group<1> g(0);
-  for (int b = 0; b < B; b++) nb_entangle_task<1>(g, b, a, toadd.data(), toadd.data() + 2 * a.tcap);
+  for (int b = 0; b < B; b++) nb_entangle_task<1>(g, b, a, toadd.data(), toadd.data() + 4 * a.tcap);
   return err ? NB_ERR_CAPACITY : 0;
 }
 
@@ -259,9 +258,9 @@ extern "C" int emul_track_batch(const nb_params* par, const double* pb, const do
   a.bp_cnt_prev = bp_cnt_prev, a.bp_xy_prev = bp_xy_prev, a.prev_pos_rw = prev_pos, a.prev_pos_agent_rw = prev_pos_agent;
   a.latest = latest, a.cur = cur, a.elapsed_ms = elapsed_ms, a.result = result;
   std::vector<uint8_t> known((size_t)B * N, 1);
-  std::vector<int> act_old((size_t)B * (N + M)), toadd((size_t)2 * a.tcap);
+  std::vector<int> toadd((size_t)4 * a.tcap);
   int err = 0, flag[4];
-  a.known = known.data(), a.act_old = act_old.data(), a.err = &err;
+  a.known = known.data(), a.err = &err;
   Group<1> g(0);
   for (int b = 0; b < B; b++) nb_entangle_task<1>(g, b, a, toadd.data(), flag);
   return err ? NB_ERR_CAPACITY : 0;
