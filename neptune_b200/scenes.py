@@ -3,9 +3,11 @@
 This is the WORKLOAD GENERATOR: host-side numpy that produces the inputs the reference's planner
 core hands to its back end (``neptune/src/neptune.cpp:1426-1517``) -- committed trajectories of the
 other agents, start state A, a front-end path ``pwp_init``, hull/sample arrays, entanglement-state
-vectors.  It is neither the product's hot path nor the oracle.  The front end here is a greedy walk
-over the reference's 5x5 constant-jerk lattice (``kinodynamic_search.cpp:1045-1140`` primitives and
-admissibility tests), not the reference's A*: that search is SURVEY section 8(f) "next #1".
+vectors.  It is neither the product's hot path nor the oracle.  The ``pwp_init`` it produces comes from a
+greedy walk over the reference's 5x5 constant-jerk lattice (``kinodynamic_search.cpp:1045-1140`` primitives
+and admissibility tests): a cheap stand-in used for the previous plans of the other agents and as the back
+end's input when the search is not run.  The reference's search itself is the product's K0 kernel
+(``nb_search_batch``); ``make_search_batch`` / ``search_host_inputs`` below build its inputs.
 
 Entanglement states are filled through an ``ent_backend`` (the product's device kernels in bench.py,
 the oracle in tests/), so this module never touches oracle/.
