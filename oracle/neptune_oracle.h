@@ -6,10 +6,17 @@
  * cpu_baseline / --impl reference legs may load this library.  The product
  * (neptune_b200/) never links, imports or executes anything in oracle/.
  *
- * PARITY STATUS: "parity unpinned" against a recorded Gurobi/GLPK/CGAL run --
- * the reference ships no golden vectors and none of Gurobi 9.1.2, GLPK 4.65,
- * CGAL 4.14.2, Eigen3 or ROS exist in this image, so /root/reference cannot
- * be compiled (oracle/_ref is therefore absent).  The oracle is
+ * PARITY STATUS, by part:
+ *  - entanglement chain (crossing tests with 8 and 9 arguments and for static
+ *    obstacles, addAlphaBetaToList, updateBendPts, getLengthToContactPoints,
+ *    the per-interval loop around them) and gjk::collision: PINNED against the
+ *    reference's own entangle_utils.cpp and gjk.cpp, compiled where they lie
+ *    (oracle/Makefile target _ref, Eigen replaced by oracle/eigen_shim) --
+ *    tests/test_reference_pin.py, recorded vectors tests/golden/reference/ref_chain.npz.
+ *  - separating-line LP, trajectory QP, hulls: "parity unpinned" against a
+ *    recorded Gurobi/GLPK/CGAL run -- the reference ships no golden vectors
+ *    and none of Gurobi 9.1.2, GLPK 4.65, CGAL 4.14.2, Eigen3 or ROS exist in
+ *    this image.  These are
  * pinned instead by (i) the one known answer in the tree
  * (submodules/separator/src/test_separator.cpp:23-32 => Solved=1),
  * (ii) HiGHS (scipy) as an independent LP/QP solver on every golden scene,
@@ -322,6 +329,8 @@ int orc_search_batch(const orc_search_par* par, const orc_search_batch_t* b, int
 /* NeptuneRos::setUpCheckingPosAndStaticObs neptune_ros.cpp:852-1019 (static-obstacle representation of one agent) */
 int orc_static_obst_rep(int M, const long long* ptr, const double* xy, const double base[2], const double pos[2],
                         double voxel, double* strep, double* longest);
+/* eu::getTetherLength (entangle_utils.cpp:1724-1743) on an explicit state (test hook) */
+double orc_tether_length_state(const orc_ent* es, const orc_ectx* cx, const double* st_longest, const double pk1[2]);
 /* test hook: open-list script through the heap restatement (compared with the real std::priority_queue) */
 int orc_heap_replay(int n_ops, const int* ops, const double* vals, int n_ids, double bias, int* out);
 

@@ -769,3 +769,16 @@ int orc_static_obst_rep(int M, const long long* ptr, const double* xy, const dou
   free(cen);
   return rc;
 }
+
+/* eu::getTetherLength on an explicit state (test hook for tests/test_reference_pin.py) */
+double orc_tether_length_state(const orc_ent* es, const orc_ectx* cx, const double* st_longest, const double pk1[2])
+{
+  ksearch s;
+  orc_search_in in;
+  memset(&s, 0, sizeof(s));
+  memset(&in, 0, sizeof(in));
+  in.st_longest = st_longest;
+  s.in = &in;
+  s.cx = *cx;
+  return tether_length(&s, es, pk1);
+}

@@ -1,8 +1,9 @@
 """ctypes binding of the CPU ORACLE (oracle/neptune_oracle.c).
 
 TEST INFRASTRUCTURE ONLY.  May be imported from tests/, __graft_entry__.smoke() and bench.py's
-cpu_baseline / --impl reference legs; never from neptune_b200/.  Parity status: "parity unpinned"
-against Gurobi/GLPK (not installable here); pinned by HiGHS and known answers in tests/.
+cpu_baseline / --impl reference legs; never from neptune_b200/.  Parity status: the entanglement
+chain and GJK are pinned against the reference's own sources (oracle/_ref, tests/test_reference_pin.py); the LP/QP are
+"parity unpinned" against Gurobi/GLPK (not installable here) and pinned by HiGHS and known answers in tests/.
 """
 from __future__ import annotations
 

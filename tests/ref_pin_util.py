@@ -1,0 +1,78 @@
+"""ctypes access to oracle/_ref/libneptune_ref.so: the REFERENCE's own entangle_utils.cpp and gjk.cpp compiled where
+they lie against the Eigen stand-in (oracle/Makefile target _ref).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "oracle", "_ref", "libneptune_ref.so")
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(LIB) or os.path.isdir("/root/reference/neptune/src")
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if os.path.isdir("/root/reference/neptune/src"):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "_ref"], check=True, capture_output=True)
+        _lib = C.CDLL(LIB)
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+def gjk(v1, v2) -> bool:
+    v1, v2 = _c(v1, np.float64), _c(v2, np.float64)
+    return bool(lib().ref_gjk_collision(_p(v1), len(v1), _p(v2), len(v2)))
+
+
+def hsig_agent(pk, pk1, pik, pik1, pb, bend, agent_id, prev=None):
+    arrs = [_c(x, np.float64) for x in (pk, pk1, pik, pik1, pb, bend)]
+    out = np.zeros((64, 2), np.int32)
+    if prev is None:
+        n = lib().ref_hsig_agent(_p(out), 64, *[_p(a) for a in arrs], len(arrs[5]), agent_id)
+    else:
+        pv = _c(prev, np.float64)
+        n = lib().ref_hsig_agent9(_p(out), 64, *[_p(a) for a in arrs], len(arrs[5]), _p(pv), len(pv), agent_id)
+    return out[:n].copy()
+
+
+def hsig_static(pk, pk1, strep, N):
+    pk, pk1, strep = _c(pk, np.float64), _c(pk1, np.float64), _c(strep, np.float64)
+    out = np.zeros((len(strep) + 4, 2), np.int32)
+    n = lib().ref_hsig_static(_p(out), len(out), _p(pk), _p(pk1), _p(strep), len(strep), N)
+    return out[:n].copy()
+
+
+def chain(par, self_idx, strep, longest, bp_cnt, bp_xy, known, samp, n, cxy, cnt0, alpha0, beta0, bend0, active0):
+    """The reference's chain along a path: returns (done, cnt [n+1][2], alpha, beta, bend, active, tether lengths [n])."""
+    N, M, NA, cap = par.num_of_agents, par.num_of_static_obst, par.NA, par.ent_cap
+    S = par.num_sample_per_interval
+    arrs = dict(pb=_c(par.pb, np.float64), strep=_c(strep, np.float64) if M else np.zeros((1, 2, 2)),
+                longest=_c(longest, np.float64) if M else np.zeros((1, 2)), bp_cnt=_c(bp_cnt, np.int32),
+                bp_xy=_c(bp_xy, np.float64), known=_c(known, np.uint8), samp=_c(samp, np.float64), cxy=_c(cxy, np.float64),
+                cnt0=_c(cnt0, np.int32), alpha0=_c(alpha0, np.int32), beta0=_c(beta0, np.float64), bend0=_c(bend0, np.int32),
+                active0=_c(active0, np.int32))
+    cnt, alpha = np.zeros((n + 1, 2), np.int32), np.zeros((n + 1, cap, 2), np.int32)
+    beta, bend = np.zeros((n + 1, cap)), np.zeros((n + 1, cap), np.int32)
+    active, length = np.zeros((n + 1, NA), np.int32), np.zeros(max(n, 1))
+    f = lib().ref_chain
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] * 3 + [C.c_void_p] * 5 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int, C.c_int, C.c_double, C.c_int,
+                  C.c_void_p, C.c_int] + [C.c_void_p] * 11
+    done = f(N, M, self_idx, _p(arrs["pb"]), _p(arrs["strep"]), _p(arrs["longest"]), _p(arrs["bp_cnt"]), _p(arrs["bp_xy"]),
+             par.bp_max, _p(arrs["known"]), _p(arrs["samp"]), par.num_pol, S, par.T_span, n, _p(arrs["cxy"]), cap,
+             _p(arrs["cnt0"]), _p(arrs["alpha0"]), _p(arrs["beta0"]), _p(arrs["bend0"]), _p(arrs["active0"]), _p(cnt), _p(alpha),
+             _p(beta), _p(bend), _p(active), _p(length))
+    return done, cnt, alpha, beta, bend, active, length

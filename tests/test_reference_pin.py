@@ -1,0 +1,165 @@
+"""The oracle pinned against the REFERENCE'S OWN CODE: neptune/src/entangle_utils.cpp and neptune/src/gjk.cpp are the
+two reference sources that need nothing but Eigen; `make -C oracle _ref` compiles them unmodified, where they lie,
+against the Eigen stand-in of oracle/eigen_shim.  Here (a container with /root/reference) the restatement in
+oracle/neptune_oracle.c is compared with them on random inputs; on machines without /root/reference the same checks run
+against golden vectors recorded from that library (tests/golden/reference/ref_chain.npz, tests/golden/make_ref_golden.py).
+
+Bars: crossing lists, signature words, active cases, bend-point indices and GJK answers bit-exact (integers); betas
+and tether lengths bit-exact as FP64 (same operations in the same order)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from neptune_b200 import config
+from neptune_b200.scenes import make_scene
+from neptune_b200.search import static_longest_dist
+from tests import ref_pin_util as ref
+from tests.ent_walks import random_walks
+
+needs_ref = pytest.mark.skipif(not ref.available(), reason="no /root/reference and no prebuilt oracle/_ref")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference", "ref_chain.npz")
+
+
+@needs_ref
+@pytest.mark.timeout(300)
+def test_gjk_matches_reference(oracle):
+    """gjk::collision (gjk.cpp:76-148).  The reference loops `while (1)`, so only generic positions are drawn (the
+    oracle and the kernels bound the loop at 1000 iterations; no generic input comes near that)."""
+    rng = np.random.default_rng(1)
+    n_hit = 0
+    for trial in range(3000):
+        a = oracle.convex_hull(rng.normal(size=(rng.integers(3, 16), 2)) * rng.uniform(0.3, 2.0) + rng.normal(size=2) * 2)
+        b = rng.normal(size=(4, 2)) * rng.uniform(0.2, 1.5) + rng.normal(size=2) * 2
+        if trial % 7 == 0:   # a control polygon poking into / hovering next to a hull vertex
+            b = b - b.mean(axis=0) + a[rng.integers(len(a))] + rng.normal(size=2) * 0.3
+        r, o = ref.gjk(a, b), oracle.gjk_collision(a, b)
+        assert r == o, trial
+        n_hit += r
+    assert 300 < n_hit < 2700
+
+
+@needs_ref
+def test_crossing_tests_match_reference(oracle):
+    """entangleHSigToAddAgentInd (8- and 9-argument forms) and entangleHSigToAddStatic on random geometry."""
+    rng = np.random.default_rng(2)
+    L = oracle.lib()
+    n_entries = n9 = 0
+    for trial in range(6000):
+        sc = rng.uniform(0.5, 6.0)
+        pk, pik, pb = rng.normal(size=2) * sc, rng.normal(size=2) * sc, rng.normal(size=2) * sc
+        pk1, pik1 = pk + rng.normal(size=2) * sc * 0.5, pik + rng.normal(size=2) * sc * 0.5
+        nb = int(rng.integers(1, 4))
+        bend = rng.normal(size=(nb, 2)) * sc
+        out = np.zeros(128, np.int32)
+        n = L.orc_hsig_agent(out.ctypes.data_as(C.c_void_p), 0, *[np.ascontiguousarray(x).ctypes.data_as(C.c_void_p) for x in (pk, pk1, pik, pik1, pb, bend)], nb, 7)
+        got = ref.hsig_agent(pk, pk1, pik, pik1, pb, bend, 7)
+        assert np.array_equal(out[:2 * n].reshape(-1, 2), got), trial
+        n_entries += n
+        # 9-argument form: a bend point added or released since the last check
+        npv = nb + (1 if rng.random() < 0.5 else -1)
+        if npv >= 1:
+            prev = np.concatenate([bend[:min(nb, npv)], rng.normal(size=(max(0, npv - nb), 2)) * sc])[:npv]
+            stop = C.c_int(0)
+            out9 = np.zeros(128, np.int32)
+            n2 = L.orc_hsig_agent9(out9.ctypes.data_as(C.c_void_p), 0, *[np.ascontiguousarray(x).ctypes.data_as(C.c_void_p) for x in (pk, pk1, pik, pik1, pb, bend)],
+                                   nb, np.ascontiguousarray(prev).ctypes.data_as(C.c_void_p), npv, 7, C.byref(stop))
+            if stop.value == 0:   # the reference calls exit(-1) on the others
+                got9 = ref.hsig_agent(pk, pk1, pik, pik1, pb, bend, 7, prev=prev)
+                assert np.array_equal(out9[:2 * n2].reshape(-1, 2), got9), trial
+                n9 += 1
+        M = int(rng.integers(1, 6))
+        strep = rng.normal(size=(M, 2, 2)) * sc
+        outs = np.zeros(64, np.int32)
+        ns = L.orc_hsig_static(outs.ctypes.data_as(C.c_void_p), 0, pk.ctypes.data_as(C.c_void_p), pk1.ctypes.data_as(C.c_void_p),
+                               np.ascontiguousarray(strep).ctypes.data_as(C.c_void_p), M, 5)
+        assert np.array_equal(outs[:2 * ns].reshape(-1, 2), ref.hsig_static(pk, pk1, strep, 5)), trial
+    assert n_entries > 500 and n9 > 1500
+
+
+def _chain_cases(oracle):
+    """(par, scene, agent, n, cxy, state0) for planner paths and for random walks that wrap around obstacles."""
+    from tests.ent_backends import OracleEntBackend
+    cases = []
+    for cfg, seed in (("obst8", 3003), ("obst8", 3004), ("mtlp5", 2002), ("grid64", 4004)):
+        par = config(cfg)
+        sc = make_scene(par, seed, sync=False, ent_backend=OracleEntBackend(oracle))
+        rng = np.random.default_rng(seed)
+        walks = [sc.batch.coeff_init] + [random_walks(par, sc.batch.B, rng, s) for s in (3.0, 6.0, 6.0)]
+        for w, co in enumerate(walks):
+            for b in range(min(sc.batch.B, 8)):
+                n = int(sc.batch.n_int[b]) if w == 0 else 8
+                st0 = (sc.esA_cnt[b], sc.esA_alpha[b], sc.esA_beta[b], sc.esA_bend[b], sc.esA_active[b]) if w == 0 else \
+                    (np.zeros(2, np.int32), np.zeros((par.ent_cap, 2), np.int32), np.zeros(par.ent_cap), np.zeros(par.ent_cap, np.int32),
+                     np.zeros(par.NA, np.int32))
+                cases.append((par, sc, b, n, np.ascontiguousarray(co[b, :2, :n, :]), st0))
+    return cases
+
+
+def _oracle_chain(oracle, par, sc, b, n, cxy, st0, longest):
+    es = oracle.EntState(par.ent_cap, par.NA)
+    es.n_alpha, es.n_bend = int(st0[0][0]), int(st0[0][1])
+    es.alpha[:], es.beta[:], es.bend[:], es.active[:] = st0[1], st0[2], st0[3], st0[4]
+    cx = oracle.EntCtx(par, int(sc.batch.agent_id[b]) - 1, sc.strep, sc.batch.bp_cnt, sc.batch.bp_xy)
+    done, cnt, alpha, beta, bend, active = oracle.entangle_rollout(es, cx, n, cxy, sc.samp[b], sc.known[b])
+    f = oracle.lib().orc_tether_length_state
+    f.restype = C.c_double
+    lens = np.zeros(max(n, 1))
+    lg = np.ascontiguousarray(longest, np.float64) if par.num_of_static_obst else np.zeros((1, 2))
+    for i in range(done):
+        e = oracle.EntState(par.ent_cap, par.NA)
+        e.n_alpha, e.n_bend = int(cnt[i + 1, 0]), int(cnt[i + 1, 1])
+        e.alpha[:], e.beta[:], e.bend[:], e.active[:] = alpha[i + 1], beta[i + 1], bend[i + 1], active[i + 1]
+        t = par.T_span
+        end = np.array([cxy[0, i] @ [t ** 3, t ** 2, t, 1.0], cxy[1, i] @ [t ** 3, t ** 2, t, 1.0]])
+        t3, t2 = t * t * t, t * t
+        end = np.array([cxy[0, i, 0] * t3 + cxy[0, i, 1] * t2 + cxy[0, i, 2] * t + cxy[0, i, 3],
+                        cxy[1, i, 0] * t3 + cxy[1, i, 1] * t2 + cxy[1, i, 2] * t + cxy[1, i, 3]])
+        ec = e._c()
+        lens[i] = f(C.byref(ec), C.byref(cx.c), lg.ctypes.data_as(C.c_void_p), end.ctypes.data_as(C.c_void_p))
+    return done, cnt, alpha, beta, bend, active, lens
+
+
+def _same_chain(a, b):
+    done = a[0]
+    assert done == b[0]
+    assert np.array_equal(a[1][:done + 1], b[1][:done + 1])
+    for i in range(done + 1):
+        na, nb = a[1][i]
+        assert np.array_equal(a[2][i, :na], b[2][i, :na]) and np.array_equal(a[3][i, :na], b[3][i, :na])
+        assert np.array_equal(a[4][i, :nb], b[4][i, :nb]) and np.array_equal(a[5][i], b[5][i])
+    assert np.array_equal(a[6][:done], b[6][:done])
+
+
+@needs_ref
+def test_chain_matches_reference(oracle):
+    """addAlphaBetaToList, updateBendPts, getBendPt2d, calculateBetaForCase, breakcondition and getTetherLength through
+    the loop of entanglesWithOtherAgents: the oracle's chain against the reference's functions, interval by interval."""
+    mx_a = mx_b = n_cut = 0
+    for par, sc, b, n, cxy, st0 in _chain_cases(oracle):
+        M = par.num_of_static_obst
+        longest = static_longest_dist(sc.static_raw, np.asarray(sc.strep).reshape(M, 2, 2)) if M else np.zeros((0, 2))
+        r = ref.chain(par, int(sc.batch.agent_id[b]) - 1, sc.strep, longest, sc.batch.bp_cnt, sc.batch.bp_xy, sc.known[b], sc.samp[b],
+                      n, cxy, *st0)
+        o = _oracle_chain(oracle, par, sc, b, n, cxy, st0, longest)
+        _same_chain(r, o)
+        mx_a, mx_b, n_cut = max(mx_a, int(r[1][:, 0].max())), max(mx_b, int(r[1][:, 1].max())), n_cut + (r[0] < n)
+    assert mx_a >= 6 and mx_b >= 1 and n_cut >= 5   # long words, bend points and entangling steps all occurred
+
+
+def test_chain_matches_reference_golden(oracle):
+    """The same comparison against vectors recorded from the reference library (travels without /root/reference)."""
+    g = np.load(GOLDEN, allow_pickle=False)
+    k = 0
+    for par, sc, b, n, cxy, st0 in _chain_cases(oracle):
+        if par.num_of_agents > 8:
+            continue
+        M = par.num_of_static_obst
+        longest = static_longest_dist(sc.static_raw, np.asarray(sc.strep).reshape(M, 2, 2)) if M else np.zeros((0, 2))
+        o = _oracle_chain(oracle, par, sc, b, n, cxy, st0, longest)
+        assert np.array_equal(g[f"cxy_{k}"], cxy)           # the generator still produces the recorded inputs
+        r = (int(g[f"done_{k}"]), g[f"cnt_{k}"], g[f"alpha_{k}"], g[f"beta_{k}"], g[f"bend_{k}"], g[f"active_{k}"], g[f"len_{k}"])
+        _same_chain(r, o)
+        k += 1
+    assert k == int(g["n_cases"])
