@@ -7,6 +7,8 @@
  * (neptune_b200/) never links, imports or executes anything in oracle/.
  *
  * PARITY STATUS, by part:
+ *  - front-end search (neptune_search.c): PINNED against the reference's own
+ *    kinodynamic_search.cpp, whole runs compared field by field.
  *  - entanglement chain (crossing tests with 8 and 9 arguments and for static
  *    obstacles, addAlphaBetaToList, updateBendPts, getLengthToContactPoints,
  *    the per-interval loop around them) and gjk::collision: PINNED against the

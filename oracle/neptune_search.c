@@ -26,8 +26,10 @@
  *   max_expansions  pops of the open list allowed before "Max Runtime was reached" (:1646-1652 uses a
  *                   wall-clock timer); max_nodes is node_num_max_ (:370-371).
  *
- * PARITY STATUS: parity unpinned (no reference test or golden vector covers the search; the reference
- * cannot be compiled here).  Pinned by properties in tests/test_search_oracle.py.
+ * PARITY STATUS: PINNED against the reference's own kinodynamic_search.cpp, compiled unmodified into oracle/_ref
+ * (Eigen replaced by oracle/eigen_shim): tests/test_reference_pin.py::test_search_matches_reference compares whole
+ * runs field by field, bit for bit; recorded outputs in tests/golden/reference/ref_search.npz.  Also checked by
+ * properties and against the real std::priority_queue in tests/test_search.py.
  */
 #include <float.h>
 #include <math.h>

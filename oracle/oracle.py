@@ -389,8 +389,8 @@ def make_search_par(par) -> OrcSearchPar:
     return sp
 
 
-def search_batch(sb, res, nthreads: int = 1) -> int:
-    """orc_search_batch over a neptune_b200.search.SearchBatch; fills a SearchResult."""
+def search_batch_struct(sb, res):
+    """(orc_search_par, orc_search_batch_t, keep-alive) for a neptune_b200.search.SearchBatch / SearchResult pair."""
     par = sb.par
     sp = make_search_par(par)
     M = par.num_of_static_obst
@@ -410,6 +410,12 @@ def search_batch(sb, res, nthreads: int = 1) -> int:
     b.status, b.solved, b.n_int, b.coeff = _p(res.status), _p(res.solved), _p(res.n_int), _p(res.coeff)
     b.esv_cnt, b.esv_alpha, b.esv_beta, b.esv_bend, b.esv_active = _p(res.esv_cnt), _p(res.esv_alpha), _p(res.esv_beta), _p(res.esv_bend), _p(res.esv_active)
     b.stats, b.cost = _p(res.stats), _p(res.cost)
+    return sp, b, keep
+
+
+def search_batch(sb, res, nthreads: int = 1) -> int:
+    """orc_search_batch over a neptune_b200.search.SearchBatch; fills a SearchResult."""
+    sp, b, keep = search_batch_struct(sb, res)
     f = lib().orc_search_batch
     f.restype = C.c_int
     return f(C.byref(sp), C.byref(b), C.c_int(nthreads))

@@ -1,0 +1,233 @@
+// ref_wrap_search.cpp -- a C entry point around the REFERENCE's own KinodynamicSearch (TEST INFRASTRUCTURE).
+//
+// oracle/Makefile (target _ref) compiles neptune/src/kinodynamic_search.cpp where it lies under /root/reference,
+// unmodified, against the Eigen stand-in (oracle/eigen_shim) and the header stand-ins in oracle/ref_stubs (ROS clock,
+// utils.hpp, bspline_utils.hpp, exprtk.hpp: nothing of theirs is used by the search), together with this file.
+// ref_search() drives the class exactly as Neptune does (neptune.cpp:89-97 construction, :662 / :670 static obstacles,
+// :1310 clearProcess, :1419-1452 setRunTime / setInitZCoeffs / setUp / run, :1509-1510 getters) on the oracle's own
+// plain-array inputs and writes the oracle's output layout, so tests/test_reference_pin.py can compare field by field.
+//
+// The reference shuffles the jerk samples with a wall-clock seed inside run() (kinodynamic_search.cpp:1462-1463); the
+// order it drew is read back from the object afterwards (comb_out) and handed to the oracle as its `comb` input.  The
+// wall-clock budget is set far above what the test cases need, so the search ends by reaching the goal, by emptying the
+// open list or by exhausting the node pool (node_num_max_, returned in info[0], = the oracle's max_nodes).
+#include <queue>
+#include <sstream>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+#include <Eigen/Dense>
+#include "mader_types.hpp"
+
+// read-only access to all_combinations_, node_used_num_ and goal_occupied_ (no member is written from here)
+#define private public
+#include "kinodynamic_search.hpp"
+#undef private
+
+#include "neptune_oracle.h"
+
+// separator::Separator is only used by collidesWithObstaclesGivenVertexes, which run() never calls; GLPK is absent.
+namespace separator
+{
+struct Separator::PImpl
+{
+};
+Separator::Separator() {}
+Separator::~Separator() {}
+static bool unavailable()
+{
+  std::fprintf(stderr, "ref_wrap_search: separator::Separator needs GLPK and is not part of this build\n");
+  abort();
+  return false;
+}
+bool Separator::solveModel(Eigen::Vector3d&, double&, const std::vector<Eigen::Vector3d>&, const std::vector<Eigen::Vector3d>&) { return unavailable(); }
+bool Separator::solveModel(Eigen::Vector3d&, double&, const Eigen::Matrix<double, 3, Eigen::Dynamic>&,
+                           const Eigen::Matrix<double, 3, Eigen::Dynamic>&)
+{
+  return unavailable();
+}
+bool Separator::solveModel(const Eigen::Matrix<double, 2, Eigen::Dynamic>&, const Eigen::Matrix<double, 2, Eigen::Dynamic>&) { return unavailable(); }
+bool Separator::solveModel(Eigen::Vector3d&, const Eigen::Matrix<double, 2, Eigen::Dynamic>&, const Eigen::Matrix<double, 2, Eigen::Dynamic>&)
+{
+  return unavailable();
+}
+bool Separator::solveModel(Eigen::Vector3d&, const Eigen::Matrix<double, 2, Eigen::Dynamic>&, const Eigen::Matrix<double, 2, Eigen::Dynamic>&,
+                           const Eigen::Matrix<double, 2, Eigen::Dynamic>&)
+{
+  return unavailable();
+}
+}  // namespace separator
+
+typedef Eigen::Vector2d V2;
+
+static mt::Polygon_Std polygon(const double* xy, int n)
+{
+  mt::Polygon_Std p(2, n);
+  for (int i = 0; i < n; i++) p(0, i) = xy[2 * i], p(1, i) = xy[2 * i + 1];
+  return p;
+}
+
+// info[0] node_num_max_, info[1] node_used_num_, info[2] goal_occupied_
+extern "C" int ref_search(const orc_search_par* par, const orc_search_in* in, orc_search_out* out, unsigned char* comb_out, int* info)
+{
+  const int N = par->N, M = par->M, NA = N + M, S = par->S, np = par->num_pol, cap = par->out_cap;
+  std::vector<V2> pb;
+  for (int i = 0; i < N; i++) pb.push_back(V2(in->pb[2 * i], in->pb[2 * i + 1]));
+
+  std::streambuf* keep = std::cout.rdbuf();  // the reference prints progress lines; keep the test output readable
+  std::ostringstream sink;
+  std::cout.rdbuf(sink.rdbuf());
+
+  KinodynamicSearch ks(np, 3, in->agent_id, 1.0, par->T, S, pb, par->use_not_reaching != 0, par->enable_entangle != 0);
+  ks.setTetherLength(par->tether);
+  ks.setMaxValuesAndSamples(par->v_max, par->a_max, par->j_max, par->num_samples);
+  ks.setXYZMinMaxAndRa(par->x_min, par->x_max, par->y_min, par->y_max, -10.0, 10.0, 5.0, par->voxel_size);
+  ks.setBias(par->bias);
+  ks.setGoalSize(par->goal_size);
+
+  std::vector<mt::Polygon_Std> statics;
+  std::vector<Eigen::Matrix<double, 2, 2>> rep;
+  std::vector<V2> longest;
+  for (int m = 0; m < M; m++)
+  {
+    statics.push_back(polygon(in->st_xy + 2 * in->st_ptr[m], (int)(in->st_ptr[m + 1] - in->st_ptr[m])));
+    Eigen::Matrix<double, 2, 2> r;  // column c = representative point c (neptune_ros.cpp:961-983)
+    r(0, 0) = in->strep[4 * m + 0], r(1, 0) = in->strep[4 * m + 1], r(0, 1) = in->strep[4 * m + 2], r(1, 1) = in->strep[4 * m + 3];
+    rep.push_back(r);
+    longest.push_back(V2(in->st_longest[2 * m], in->st_longest[2 * m + 1]));
+  }
+  ks.setStaticObstVert(statics);
+  ks.setStaticObstRep(rep, longest);
+  info[0] = ks.node_num_max_;
+
+  ks.clearProcess();
+  ks.setRunTime(1.0e6);
+  std::vector<Eigen::Matrix<double, 4, 1>> cz;
+  for (int i = 0; i < ORC_NPOL_MAX; i++)
+    cz.push_back(Eigen::Matrix<double, 4, 1>(in->coeffs_z[4 * i], in->coeffs_z[4 * i + 1], in->coeffs_z[4 * i + 2], in->coeffs_z[4 * i + 3]));
+  ks.setInitZCoeffs(cz);
+
+  mt::state A;
+  A.setPos(in->init[0], in->init[1], 0.0);
+  A.setVel(in->init[2], in->init[3], 0.0);
+  A.setAccel(in->init[4], in->init[5], 0.0);
+  Eigen::Vector3d goal(in->goal[0], in->goal[1], 0.0);
+
+  mt::ConvexHullsOfCurves_Std2d hulls;  // one entry per KNOWN trajectory (neptune.cpp:1436-1441), intervals 0..num_pol-1
+  for (int o = 0; o < N; o++)
+  {
+    if (in->hull_cnt[o * ORC_NPOL_MAX] <= 0) continue;
+    mt::ConvexHullsOfCurve_Std2d one;
+    for (int i = 0; i < np; i++)
+      one.push_back(polygon(in->hull_xy + ((size_t)(o * ORC_NPOL_MAX + i) * ORC_SEARCH_HSTRIDE) * 2, in->hull_cnt[o * ORC_NPOL_MAX + i]));
+    hulls.push_back(one);
+  }
+  mt::SampledPointsofCurves spoc(N);  // indexed by agent id - 1, empty = unknown
+  for (int a = 0; a < N; a++)
+  {
+    if (!in->known[a]) continue;
+    for (int i = 0; i < np; i++) spoc[a].push_back(polygon(in->samp + ((size_t)(a * np + i) * (S + 1)) * 2, S + 1));
+  }
+  eu::ent_state es;
+  for (int i = 0; i < in->es_cnt[0]; i++)
+    es.alphas.push_back(Eigen::Vector2i(in->es_alpha[2 * i], in->es_alpha[2 * i + 1])), es.betas.push_back(in->es_beta[i]);
+  for (int i = 0; i < in->es_cnt[1]; i++) es.bendPointsIdx.push_back(in->es_bend[i]);
+  for (int i = 0; i < NA; i++) es.active_cases.push_back(in->es_active[i]);
+  std::vector<std::vector<V2>> bends(N);
+  for (int a = 0; a < N; a++)
+    for (int i = 0; i < in->bp_cnt[a]; i++)
+      bends[a].push_back(V2(in->bp_xy[((size_t)a * par->bp_max + i) * 2], in->bp_xy[((size_t)a * par->bp_max + i) * 2 + 1]));
+
+  ks.setUp(A, goal, hulls, spoc, es, bends);
+  std::vector<Eigen::Vector3d> path;
+  int status = -1;
+  const bool solved = ks.run(path, status);
+  std::cout.rdbuf(keep);
+
+  for (size_t i = 0; i < ks.all_combinations_.size(); i++)
+    comb_out[i] = (unsigned char)(std::get<0>(ks.all_combinations_[i]) * par->num_samples + std::get<1>(ks.all_combinations_[i]));
+  info[1] = ks.node_used_num_;
+  info[2] = ks.goal_occupied_ ? 1 : 0;
+
+  out->status[0] = status;
+  out->solved[0] = solved ? 1 : 0;
+  out->n_int[0] = 0;
+  if (solved)
+  {
+    mt::PieceWisePol pwp;
+    ks.getPwpOut_0tstart(pwp);
+    std::vector<eu::ent_state> esv;
+    ks.getEntStateVector(esv);
+    const int n = (int)pwp.coeff_x.size();
+    out->n_int[0] = n;
+    for (int i = 0; i < n && i < ORC_NPOL_MAX; i++)
+      for (int k = 0; k < 4; k++)
+      {
+        out->coeff[(0 * ORC_NPOL_MAX + i) * 4 + k] = pwp.coeff_x[i](k);
+        out->coeff[(1 * ORC_NPOL_MAX + i) * 4 + k] = pwp.coeff_y[i](k);
+        out->coeff[(2 * ORC_NPOL_MAX + i) * 4 + k] = pwp.coeff_z[i](k);
+      }
+    info[3] = (int)esv.size();
+    for (size_t s = 0; s < esv.size() && s <= ORC_NPOL_MAX; s++)
+    {
+      const eu::ent_state& e = esv[s];
+      out->esv_cnt[2 * s] = (int)e.alphas.size(), out->esv_cnt[2 * s + 1] = (int)e.bendPointsIdx.size();
+      for (size_t i = 0; i < e.alphas.size() && (int)i < cap; i++)
+      {
+        out->esv_alpha[(s * cap + i) * 2] = e.alphas[i](0), out->esv_alpha[(s * cap + i) * 2 + 1] = e.alphas[i](1);
+        out->esv_beta[s * cap + i] = e.betas[i];
+      }
+      for (size_t i = 0; i < e.bendPointsIdx.size() && (int)i < cap; i++) out->esv_bend[s * cap + i] = e.bendPointsIdx[i];
+      for (int i = 0; i < NA && i < (int)e.active_cases.size(); i++) out->esv_active[s * NA + i] = e.active_cases[i];
+    }
+    out->cost[0] = ks.best_node_ptr_ ? ks.best_node_ptr_->g : 0.0;  // getCost() is declared but never defined
+  }
+  return 0;
+}
+
+// The same slicing of a batch into per-agent inputs as orc_search_batch (oracle/neptune_search.c), one reference search
+// per agent.  comb_out [B][num_samples^2], info [B][4].
+extern "C" int ref_search_batch(const orc_search_par* par, const orc_search_batch_t* b, unsigned char* comb_out, int* info)
+{
+  const int N = par->N, M = par->M, NA = N + M, S = par->S, np = par->num_pol, ocap = par->out_cap;
+  const int nchild = par->num_samples * par->num_samples;
+  for (int i = 0; i < b->B; i++)
+  {
+    orc_search_in in;
+    orc_search_out out;
+    const int g = b->group ? b->group[i] : i;
+    in.agent_id = b->agent_id[i];
+    for (int k = 0; k < 6; k++) in.init[k] = b->init[6 * (size_t)i + k];
+    in.goal[0] = b->goal[2 * i], in.goal[1] = b->goal[2 * i + 1];
+    in.coeffs_z = b->coeffs_z + (size_t)i * ORC_NPOL_MAX * 4;
+    std::vector<int> hc(b->hull_cnt + (size_t)g * N * ORC_NPOL_MAX, b->hull_cnt + (size_t)(g + 1) * N * ORC_NPOL_MAX);
+    const unsigned char* known = b->known + (size_t)i * N;
+    for (int o = 0; o < N; o++)
+      if (o == in.agent_id - 1 || !known[o])
+        for (int k = 0; k < ORC_NPOL_MAX; k++) hc[o * ORC_NPOL_MAX + k] = 0;
+    in.hull_cnt = hc.data();
+    in.hull_xy = b->hull_xy + (size_t)g * N * ORC_NPOL_MAX * ORC_SEARCH_HSTRIDE * 2;
+    in.samp = b->samp + (size_t)g * N * np * (S + 1) * 2;
+    in.known = known;
+    in.st_ptr = b->st_ptr, in.st_xy = b->st_xy, in.strep = b->strep, in.st_longest = b->st_longest;
+    in.pb = b->pb, in.bp_cnt = b->bp_cnt, in.bp_xy = b->bp_xy;
+    in.es_cnt = b->es_cnt + 2 * (size_t)i;
+    in.es_alpha = b->es_alpha + (size_t)i * 2 * b->es_cap;
+    in.es_beta = b->es_beta + (size_t)i * b->es_cap;
+    in.es_bend = b->es_bend + (size_t)i * b->es_cap;
+    in.es_active = b->es_active + (size_t)i * NA;
+    in.comb = 0;
+    out.status = b->status + i, out.solved = b->solved + i, out.n_int = b->n_int + i;
+    out.coeff = b->coeff + (size_t)i * 3 * ORC_NPOL_MAX * 4;
+    out.esv_cnt = b->esv_cnt + (size_t)i * 9 * 2;
+    out.esv_alpha = b->esv_alpha + (size_t)i * 9 * 2 * ocap;
+    out.esv_beta = b->esv_beta + (size_t)i * 9 * ocap;
+    out.esv_bend = b->esv_bend + (size_t)i * 9 * ocap;
+    out.esv_active = b->esv_active + (size_t)i * 9 * NA;
+    out.stats = b->stats + 4 * (size_t)i;
+    out.cost = b->cost + i;
+    ref_search(par, &in, &out, comb_out + (size_t)i * nchild, info + 4 * (size_t)i);
+  }
+  return 0;
+}

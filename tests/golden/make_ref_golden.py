@@ -1,5 +1,6 @@
-"""Records golden vectors of the entanglement chain from the REFERENCE library (oracle/_ref/libneptune_ref.so: the
-reference's entangle_utils.cpp compiled against the Eigen stand-in) for tests/test_reference_pin.py.
+"""Records golden vectors of the entanglement chain and of whole front-end searches from the REFERENCE library
+(oracle/_ref/libneptune_ref.so: the reference's entangle_utils.cpp, gjk.cpp and kinodynamic_search.cpp compiled against the
+Eigen stand-in) for tests/test_reference_pin.py.
 Run in a container that has /root/reference:  python tests/golden/make_ref_golden.py"""
 import os
 import sys
@@ -12,7 +13,7 @@ sys.path.insert(0, ROOT)
 from neptune_b200.search import static_longest_dist  # noqa: E402
 from oracle import oracle as orc  # noqa: E402
 from tests import ref_pin_util as ref  # noqa: E402
-from tests.test_reference_pin import _chain_cases  # noqa: E402
+from tests.test_reference_pin import SEARCH_CASES, _chain_cases, _reference_search, _search_case  # noqa: E402
 
 
 def main():
@@ -31,6 +32,17 @@ def main():
     out["n_cases"] = np.int32(k)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reference", "ref_chain.npz"), **out)
     print("wrote", k, "cases")
+
+    out = {"n_cases": np.int32(len(SEARCH_CASES))}
+    for k, (cfg, seed, mods, mb) in enumerate(SEARCH_CASES):
+        par, sb = _search_case(orc, cfg, seed, mods, mb)
+        g = _reference_search(sb)
+        mx = max(1, int(g["esv_cnt"][:, :, 0].max()), int(g["esv_cnt"][:, :, 1].max()))
+        for f in ("esv_alpha", "esv_beta", "esv_bend"):
+            g[f] = g[f][:, :, :mx]
+        out.update({f"{f}_{k}": v for f, v in g.items()})
+        print(cfg, seed, "status", g["status"].tolist(), "nodes", g["nodes"].tolist())
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reference", "ref_search.npz"), **out)
 
 
 if __name__ == "__main__":

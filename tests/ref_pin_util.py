@@ -76,3 +76,17 @@ def chain(par, self_idx, strep, longest, bp_cnt, bp_xy, known, samp, n, cxy, cnt
              _p(arrs["cnt0"]), _p(arrs["alpha0"]), _p(arrs["beta0"]), _p(arrs["bend0"]), _p(arrs["active0"]), _p(cnt), _p(alpha),
              _p(beta), _p(bend), _p(active), _p(length))
     return done, cnt, alpha, beta, bend, active, length
+
+
+def search(sb, res):
+    """The reference's own KinodynamicSearch on every agent of a SearchBatch (oracle/ref_wrap_search.cpp).
+    Returns (comb [B][ns^2] the jerk order each search drew, info [B][4]: node_num_max_, node_used_num_, goal_occupied_,
+    states in entStateVec)."""
+    from oracle import oracle
+    sp, b, keep = oracle.search_batch_struct(sb, res)
+    ns2 = sb.par.a_star_samp_x ** 2
+    comb, info = np.zeros((sb.B, ns2), np.uint8), np.zeros((sb.B, 4), np.int32)
+    f = lib().ref_search_batch
+    f.restype = C.c_int
+    f(C.byref(sp), C.byref(b), _p(comb), _p(info))
+    return comb, info

@@ -1,6 +1,6 @@
-"""The oracle pinned against the REFERENCE'S OWN CODE: neptune/src/entangle_utils.cpp and neptune/src/gjk.cpp are the
-two reference sources that need nothing but Eigen; `make -C oracle _ref` compiles them unmodified, where they lie,
-against the Eigen stand-in of oracle/eigen_shim.  Here (a container with /root/reference) the restatement in
+"""The oracle pinned against the REFERENCE'S OWN CODE: neptune/src/kinodynamic_search.cpp, neptune/src/entangle_utils.cpp
+and neptune/src/gjk.cpp are the reference sources on the path that need nothing but Eigen and a clock; `make -C oracle
+_ref` compiles them unmodified, where they lie, against the Eigen stand-in of oracle/eigen_shim (+ oracle/ref_stubs).  Here (a container with /root/reference) the restatement in
 oracle/neptune_oracle.c is compared with them on random inputs; on machines without /root/reference the same checks run
 against golden vectors recorded from that library (tests/golden/reference/ref_chain.npz, tests/golden/make_ref_golden.py).
 
@@ -163,3 +163,122 @@ def test_chain_matches_reference_golden(oracle):
         _same_chain(r, o)
         k += 1
     assert k == int(g["n_cases"])
+
+
+# ---------------------------------------------------------------------------- the front-end search, whole runs
+GOLDEN_SEARCH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference", "ref_search.npz")
+
+# (config, seed, parameter overrides, some tethers start wrapped around a contact point)
+SEARCH_CASES = [
+    ("single", 5, {}, False),
+    ("mtlp5", 11, {}, False),            # one goal occupied: the open list runs empty after 64 796 nodes (status 2)
+    ("mtlp5", 12, {}, False),
+    ("mtlp5", 13, {}, True),
+    ("mtlp5", 14, {"tetherLength": 9.0}, False),           # the tether constraint prunes most of the lattice
+    ("mtlp5", 15, {"use_not_reaching_soln": False}, False),
+    ("mtlp5", 16, {"a_star_samp_x": 3, "a_star_bias": 1.0}, False),
+    ("obst8", 3, {}, False),             # nine static obstacles: crossing signatures and collisions of both kinds
+    ("obst8", 6, {"x_min": -7.0, "x_max": 7.0, "y_min": -7.0, "y_max": 7.0}, True),   # a small world: the node pool runs out
+]
+
+
+def _search_case(oracle, cfg, seed, mods, multi_bend):
+    """Inputs of one reference-sized run: node_num_max_ from the world size (kinodynamic_search.cpp:370-371), no pop
+    budget (the reference's wall-clock limit is set far away), so a search ends by reaching the goal, by emptying the
+    open list or by exhausting the node pool."""
+    import math
+
+    from neptune_b200.scenes import make_search_batch
+    from tests.ent_backends import OracleEntBackend
+    par = config(cfg)
+    for k, v in mods.items():
+        setattr(par, k, v)
+    par.search_max_nodes = math.ceil((par.x_max - par.x_min) * (par.y_max - par.y_min) / (par.a_star_fraction_voxel_size ** 2) * 15)
+    par.search_max_expansions = 2 ** 30
+    sc = make_scene(par, seed, sync=False, ent_backend=OracleEntBackend(oracle), group_hulls=True)
+    sb = make_search_batch(sc, seed + 1, per_agent_order=True)
+    if multi_bend:
+        sb.bp_cnt, sb.bp_xy = sb.bp_cnt.copy(), sb.bp_xy.copy()
+        rng = np.random.default_rng(seed)
+        for j in range(0, par.num_of_agents, 2):
+            sb.bp_cnt[j] = 2
+            sb.bp_xy[j, 1] = sb.bp_xy[j, 0] + rng.normal(0, 2.0, size=2)
+    return par, sb
+
+
+def _reference_search(sb):
+    """{field: array} of the reference's run on every agent of the batch, entStateVec trimmed to the states it returned."""
+    from neptune_b200.search import SearchResult
+    r = SearchResult.empty(sb)
+    comb, info = ref.search(sb, r)
+    return dict(comb=comb, node_num_max=info[:, 0].copy(), nodes=info[:, 1].copy(), goal_occupied=info[:, 2].copy(),
+                n_states=info[:, 3].copy() * r.solved, status=r.status, solved=r.solved, n_int=r.n_int, coeff=r.coeff, cost=r.cost,
+                esv_cnt=r.esv_cnt, esv_alpha=r.esv_alpha, esv_beta=r.esv_beta, esv_bend=r.esv_bend, esv_active=r.esv_active)
+
+
+def _check_oracle_search(oracle, par, sb, g):
+    """Run the oracle with the jerk order the reference drew and compare every output, bit for bit."""
+    from neptune_b200.search import SearchResult
+    assert np.all(g["node_num_max"] == par.search_max_nodes)
+    sb.comb = np.ascontiguousarray(g["comb"], np.uint8)
+    o = SearchResult.empty(sb)
+    assert oracle.search_batch(sb, o, 4) == 0
+    assert np.array_equal(o.status, g["status"]) and np.array_equal(o.solved, g["solved"]) and np.array_equal(o.n_int, g["n_int"])
+    assert np.array_equal(o.stats[:, 0], g["nodes"]), "node_used_num_"
+    assert np.array_equal(o.stats[:, 3], g["goal_occupied"])
+    assert np.array_equal(o.coeff, g["coeff"]), "pwp_out_ coefficients (FP64, bit-exact)"
+    assert np.array_equal(o.cost, g["cost"])
+    for b in range(sb.B):
+        ns = int(g["n_states"][b])
+        assert ns == (int(o.n_int[b]) + 1 if o.solved[b] else 0)
+        assert np.array_equal(o.esv_cnt[b, :ns], g["esv_cnt"][b, :ns])
+        for s in range(ns):
+            na, nb = o.esv_cnt[b, s]
+            assert np.array_equal(o.esv_alpha[b, s, :na], g["esv_alpha"][b, s, :na])
+            assert np.array_equal(o.esv_beta[b, s, :na], g["esv_beta"][b, s, :na])
+            assert np.array_equal(o.esv_bend[b, s, :nb], g["esv_bend"][b, s, :nb])
+            assert np.array_equal(o.esv_active[b, s], g["esv_active"][b, s])
+        for s in range(ns, o.esv_cnt.shape[1]):   # layout convention of the oracle / product: later slots repeat the last state
+            if ns:
+                assert np.array_equal(o.esv_cnt[b, s], o.esv_cnt[b, ns - 1]) and np.array_equal(o.esv_active[b, s], o.esv_active[b, ns - 1])
+    return o
+
+
+@needs_ref
+@pytest.mark.timeout(600)
+@pytest.mark.skipif(not os.path.isdir("/root/reference/neptune/src"), reason="live run needs the reference sources")
+def test_search_matches_reference(oracle):
+    """KinodynamicSearch::run of the reference itself (kinodynamic_search.cpp compiled unmodified into oracle/_ref) against
+    the oracle: status, return value, pieces, coefficients, entStateVec with betas, nodes used, goal_occupied and cost,
+    on searches of 50 to 65 000 nodes that end in all three ways."""
+    seen, most = set(), 0
+    for cfg, seed, mods, mb in SEARCH_CASES:
+        par, sb = _search_case(oracle, cfg, seed, mods, mb)
+        g = _reference_search(sb)
+        o = _check_oracle_search(oracle, par, sb, g)
+        seen |= set(o.status.tolist())
+        most = max(most, int(o.stats[:, 0].max()))
+    assert {1, 2} <= seen and most > 10000
+
+
+def test_search_matches_reference_golden(oracle):
+    """The same comparison against outputs recorded from the reference library (tests/golden/make_ref_golden.py); the
+    inputs are regenerated from the seeds.  Runs where /root/reference is absent."""
+    g = np.load(GOLDEN_SEARCH)
+    assert int(g["n_cases"]) == len(SEARCH_CASES)
+    for k, (cfg, seed, mods, mb) in enumerate(SEARCH_CASES):
+        par, sb = _search_case(oracle, cfg, seed, mods, mb)
+        _check_oracle_search(oracle, par, sb, {f: g[f"{f}_{k}"] for f in (
+            "comb", "node_num_max", "nodes", "goal_occupied", "n_states", "status", "solved", "n_int", "coeff", "cost", "esv_cnt",
+            "esv_alpha", "esv_beta", "esv_bend", "esv_active")})
+
+
+@needs_ref
+@pytest.mark.skipif(not os.path.isdir("/root/reference/neptune/src") or not os.environ.get("NB_LONG_TESTS"),
+                    reason="minutes of CPU: set NB_LONG_TESTS=1 (needs the reference sources)")
+def test_search_matches_reference_long(oracle):
+    """Full-size obstacle world: searches of 80 000 to 337 499 nodes, one of which exhausts the node pool
+    (node_used_num_ == node_num_max_ - 1, kinodynamic_search.cpp:1060-1064)."""
+    par, sb = _search_case(oracle, "obst8", 6, {}, True)
+    o = _check_oracle_search(oracle, par, sb, _reference_search(sb))
+    assert int(o.stats[:, 0].max()) >= par.search_max_nodes - 1
