@@ -216,13 +216,17 @@ def _reference_search(sb):
                 esv_cnt=r.esv_cnt, esv_alpha=r.esv_alpha, esv_beta=r.esv_beta, esv_bend=r.esv_bend, esv_active=r.esv_active)
 
 
-def _check_oracle_search(oracle, par, sb, g):
-    """Run the oracle with the jerk order the reference drew and compare every output, bit for bit."""
+def _check_oracle_search(oracle, par, sb, g, run=None):
+    """Run the oracle (or `run`: the product / its host emulation) with the jerk order the reference drew and compare
+    every output with the reference's, bit for bit."""
     from neptune_b200.search import SearchResult
     assert np.all(g["node_num_max"] == par.search_max_nodes)
     sb.comb = np.ascontiguousarray(g["comb"], np.uint8)
-    o = SearchResult.empty(sb)
-    assert oracle.search_batch(sb, o, 4) == 0
+    if run is None:
+        o = SearchResult.empty(sb)
+        assert oracle.search_batch(sb, o, 4) == 0
+    else:
+        o = run(sb)
     assert np.array_equal(o.status, g["status"]) and np.array_equal(o.solved, g["solved"]) and np.array_equal(o.n_int, g["n_int"])
     assert np.array_equal(o.stats[:, 0], g["nodes"]), "node_used_num_"
     assert np.array_equal(o.stats[:, 3], g["goal_occupied"])
@@ -261,6 +265,10 @@ def test_search_matches_reference(oracle):
     assert {1, 2} <= seen and most > 10000
 
 
+_GOLDEN_FIELDS = ("comb", "node_num_max", "nodes", "goal_occupied", "n_states", "status", "solved", "n_int", "coeff", "cost", "esv_cnt",
+                  "esv_alpha", "esv_beta", "esv_bend", "esv_active")
+
+
 def test_search_matches_reference_golden(oracle):
     """The same comparison against outputs recorded from the reference library (tests/golden/make_ref_golden.py); the
     inputs are regenerated from the seeds.  Runs where /root/reference is absent."""
@@ -268,9 +276,39 @@ def test_search_matches_reference_golden(oracle):
     assert int(g["n_cases"]) == len(SEARCH_CASES)
     for k, (cfg, seed, mods, mb) in enumerate(SEARCH_CASES):
         par, sb = _search_case(oracle, cfg, seed, mods, mb)
-        _check_oracle_search(oracle, par, sb, {f: g[f"{f}_{k}"] for f in (
-            "comb", "node_num_max", "nodes", "goal_occupied", "n_states", "status", "solved", "n_int", "coeff", "cost", "esv_cnt",
-            "esv_alpha", "esv_beta", "esv_bend", "esv_active")})
+        _check_oracle_search(oracle, par, sb, {f: g[f"{f}_{k}"] for f in _GOLDEN_FIELDS})
+
+
+def test_emulated_kernel_matches_reference_golden(oracle):
+    """The product's search kernel source, compiled for the host (tests/emul), against the REFERENCE's recorded runs --
+    no oracle in between (searches of up to 66 000 nodes)."""
+    from tests.emul import emul
+    g = np.load(GOLDEN_SEARCH)
+    n = 0
+    for k, (cfg, seed, mods, mb) in enumerate(SEARCH_CASES):
+        if int(g[f"nodes_{k}"].max()) > 100000:
+            continue
+        par, sb = _search_case(oracle, cfg, seed, mods, mb)
+        _check_oracle_search(oracle, par, sb, {f: g[f"{f}_{k}"] for f in _GOLDEN_FIELDS}, run=emul.search)
+        n += 1
+    assert n >= 8
+
+
+@pytest.mark.gpu
+def test_gpu_search_matches_reference_golden(oracle):
+    """k_search on the GPU against the REFERENCE's recorded runs, at the reference's own budgets (node pool of
+    node_num_max_ nodes per agent, no pop limit): searches of up to 66 000 nodes, every output field bit for bit."""
+    from neptune_b200 import capi
+    g = np.load(GOLDEN_SEARCH)
+    for k, (cfg, seed, mods, mb) in enumerate(SEARCH_CASES):
+        par, sb = _search_case(oracle, cfg, seed, mods, mb)
+        s = capi.Solver(par)
+        if par.num_of_static_obst:
+            s.set_static(sb.st_ptr, sb.st_xy, sb.strep)
+            s.set_static_longest(sb.st_longest)
+        s.search_configure()
+        _check_oracle_search(oracle, par, sb, {f: g[f"{f}_{k}"] for f in _GOLDEN_FIELDS}, run=s.search)
+        s.close()
 
 
 @needs_ref
