@@ -20,7 +20,8 @@
 #include <Eigen/Dense>
 #include "mader_types.hpp"
 
-// read-only access to all_combinations_, node_used_num_ and goal_occupied_ (no member is written from here)
+// access to all_combinations_, node_used_num_, goal_occupied_ and best_node_ptr_ (read only); the one member written from
+// here is num_of_static_obst_ in ref_entangle_check_pwp, which setStaticObstVert would set together with a node pool
 #define private public
 #include "kinodynamic_search.hpp"
 #undef private
@@ -230,4 +231,61 @@ extern "C" int ref_search_batch(const orc_search_par* par, const orc_search_batc
     ref_search(par, &in, &out, comb_out + (size_t)i * nchild, info + 4 * (size_t)i);
   }
   return 0;
+}
+
+// KinodynamicSearch::entangleCheckGivenPwp (kinodynamic_search.cpp:897-985) called on a real object: the post-check of
+// an optimised trajectory.  State in / out as in ref_chain (oracle/ref_wrap.cpp); returns the reference's answer.
+extern "C" int ref_entangle_check_pwp(int N, int M, int self, const double* pb, const double* strep, const int* bp_cnt,
+                                      const double* bp_xy, int bp_max, const unsigned char* known, const double* samp, int num_pol,
+                                      int S, double T, int n, const double* cxy /*[2][n][4]*/, int cap, int* cnt, int* alpha,
+                                      double* beta, int* bend, int* active)
+{
+  std::vector<V2> vpb;
+  for (int i = 0; i < N; i++) vpb.push_back(V2(pb[2 * i], pb[2 * i + 1]));
+  std::streambuf* keep = std::cout.rdbuf();
+  std::ostringstream sink;
+  std::cout.rdbuf(sink.rdbuf());
+  KinodynamicSearch ks(num_pol, 3, self + 1, 1.0, T, S, vpb, true, true);
+  std::vector<Eigen::Matrix<double, 2, 2>> rep;
+  std::vector<V2> longest(M, V2(0.0, 0.0));
+  for (int m = 0; m < M; m++)
+  {
+    Eigen::Matrix<double, 2, 2> r;
+    r(0, 0) = strep[4 * m + 0], r(1, 0) = strep[4 * m + 1], r(0, 1) = strep[4 * m + 2], r(1, 1) = strep[4 * m + 3];
+    rep.push_back(r);
+  }
+  ks.setStaticObstRep(rep, longest);
+  ks.num_of_static_obst_ = M;  // normally set by setStaticObstVert (:367), which also allocates the node pool
+  mt::SampledPointsofCurves spoc(N);
+  for (int a = 0; a < N; a++)
+  {
+    if (!known[a]) continue;
+    for (int i = 0; i < num_pol; i++) spoc[a].push_back(polygon(samp + ((size_t)(a * num_pol + i) * (S + 1)) * 2, S + 1));
+  }
+  std::vector<std::vector<V2>> bends(N);
+  for (int a = 0; a < N; a++)
+    for (int i = 0; i < bp_cnt[a]; i++) bends[a].push_back(V2(bp_xy[((size_t)a * bp_max + i) * 2], bp_xy[((size_t)a * bp_max + i) * 2 + 1]));
+  eu::ent_state es;
+  for (int i = 0; i < cnt[0]; i++) es.alphas.push_back(Eigen::Vector2i(alpha[2 * i], alpha[2 * i + 1])), es.betas.push_back(beta[i]);
+  for (int i = 0; i < cnt[1]; i++) es.bendPointsIdx.push_back(bend[i]);
+  for (int i = 0; i < N + M; i++) es.active_cases.push_back(active[i]);
+  mt::state A;
+  Eigen::Vector3d goal(0.0, 0.0, 0.0);
+  mt::ConvexHullsOfCurves_Std2d no_hulls;
+  eu::ent_state es_setup = es;
+  ks.setUp(A, goal, no_hulls, spoc, es_setup, bends);
+
+  mt::PieceWisePol pwp;
+  for (int i = 0; i < n; i++)
+  {
+    pwp.coeff_x.push_back(Eigen::Matrix<double, 4, 1>(cxy[4 * i], cxy[4 * i + 1], cxy[4 * i + 2], cxy[4 * i + 3]));
+    pwp.coeff_y.push_back(Eigen::Matrix<double, 4, 1>(cxy[4 * (n + i)], cxy[4 * (n + i) + 1], cxy[4 * (n + i) + 2], cxy[4 * (n + i) + 3]));
+  }
+  const bool ent = n > 0 ? ks.entangleCheckGivenPwp(pwp, es) : false;  // with no piece the reference falls off the end (no return value)
+  std::cout.rdbuf(keep);
+  cnt[0] = (int)es.alphas.size(), cnt[1] = (int)es.bendPointsIdx.size();
+  for (size_t i = 0; i < es.alphas.size() && (int)i < cap; i++) alpha[2 * i] = es.alphas[i](0), alpha[2 * i + 1] = es.alphas[i](1), beta[i] = es.betas[i];
+  for (size_t i = 0; i < es.bendPointsIdx.size() && (int)i < cap; i++) bend[i] = es.bendPointsIdx[i];
+  for (int i = 0; i < N + M; i++) active[i] = es.active_cases[i];
+  return ent ? 1 : 0;
 }

@@ -90,3 +90,19 @@ def search(sb, res):
     f.restype = C.c_int
     f(C.byref(sp), C.byref(b), _p(comb), _p(info))
     return comb, info
+
+
+def entangle_check_pwp(par, self_idx, strep, bp_cnt, bp_xy, known, samp, n, cxy, cnt0, alpha0, beta0, bend0, active0):
+    """The reference's KinodynamicSearch::entangleCheckGivenPwp on a real object: (entangled, cnt, alpha, beta, bend, active)."""
+    N, M, cap = par.num_of_agents, par.num_of_static_obst, par.ent_cap
+    a = dict(pb=_c(par.pb, np.float64), strep=_c(strep, np.float64) if M else np.zeros((1, 2, 2)), bp_cnt=_c(bp_cnt, np.int32),
+             bp_xy=_c(bp_xy, np.float64), known=_c(known, np.uint8), samp=_c(samp, np.float64), cxy=_c(cxy, np.float64))
+    cnt, alpha, beta = np.array(cnt0, np.int32).copy(), np.array(alpha0, np.int32).copy(), np.array(beta0, np.float64).copy()
+    bend, active = np.array(bend0, np.int32).copy(), np.array(active0, np.int32).copy()
+    f = lib().ref_entangle_check_pwp
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 2 + [C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p,
+                  C.c_int] + [C.c_void_p] * 5
+    ent = f(N, M, self_idx, _p(a["pb"]), _p(a["strep"]), _p(a["bp_cnt"]), _p(a["bp_xy"]), par.bp_max, _p(a["known"]), _p(a["samp"]),
+            par.num_pol, par.num_sample_per_interval, par.T_span, n, _p(a["cxy"]), cap, _p(cnt), _p(alpha), _p(beta), _p(bend), _p(active))
+    return ent, cnt, alpha, beta, bend, active

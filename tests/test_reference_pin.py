@@ -320,3 +320,29 @@ def test_search_matches_reference_long(oracle):
     par, sb = _search_case(oracle, "obst8", 6, {}, True)
     o = _check_oracle_search(oracle, par, sb, _reference_search(sb))
     assert int(o.stats[:, 0].max()) >= par.search_max_nodes - 1
+
+
+@needs_ref
+@pytest.mark.skipif(not os.path.isdir("/root/reference/neptune/src"), reason="live run needs the reference sources")
+def test_post_check_matches_reference(oracle):
+    """KinodynamicSearch::entangleCheckGivenPwp called on a real object of the reference (:897-985, including its return
+    inside the interval loop: only interval 0 is looked at) against orc_entangle_check_pwp: answer and updated state."""
+    n_ent = n_all = 0
+    for par, sc, b, n, cxy, st0 in _chain_cases(oracle):
+        if n == 0:
+            continue
+        es = oracle.EntState(par.ent_cap, par.NA)
+        es.n_alpha, es.n_bend = int(st0[0][0]), int(st0[0][1])
+        es.alpha[:], es.beta[:], es.bend[:], es.active[:] = st0[1], st0[2], st0[3], st0[4]
+        cx = oracle.EntCtx(par, int(sc.batch.agent_id[b]) - 1, sc.strep, sc.batch.bp_cnt, sc.batch.bp_xy)
+        o = oracle.entangle_check_pwp(es, cx, n, cxy, sc.samp[b], sc.known[b])
+        r, cnt, alpha, beta, bend, active = ref.entangle_check_pwp(par, int(sc.batch.agent_id[b]) - 1, sc.strep, sc.batch.bp_cnt,
+                                                                  sc.batch.bp_xy, sc.known[b], sc.samp[b], n, cxy, *st0)
+        assert r == o, (par.num_of_agents, b)
+        n_ent += r
+        n_all += 1
+        if not r:   # after a rejection the reference leaves the state half-updated; callers drop it (neptune.cpp:750-757)
+            assert (es.n_alpha, es.n_bend) == (cnt[0], cnt[1])
+            assert np.array_equal(es.alpha[:cnt[0]], alpha[:cnt[0]]) and np.array_equal(es.beta[:cnt[0]], beta[:cnt[0]])
+            assert np.array_equal(es.bend[:cnt[1]], bend[:cnt[1]]) and np.array_equal(es.active, active)
+    assert n_all > 80 and 0 < n_ent < n_all
