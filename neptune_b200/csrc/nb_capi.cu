@@ -232,7 +232,9 @@ __global__ void k_separate(int L, const int64_t* a_ptr, const double* a_xy, cons
   out_ok[l] = ok ? 1 : 0;
 }
 
-// PolySolverGurobi::generatePwpOut sampling loop (solver_gurobi_poly.cpp:911-934)
+// PolySolverGurobi::generatePwpOut sampling loop (solver_gurobi_poly.cpp:911-934).  Operation order as written there
+// (power vectors first, then coefficients times powers summed from the left), every operation rounded on its own, so the
+// samples are bit-identical to the reference's.
 __global__ void k_traj(int B, const int* n_int, const double* coeff, double T, double dc, int max_states, double* states,
                        int* n_states)
 {
@@ -244,19 +246,21 @@ __global__ void k_traj(int B, const int* n_int, const double* coeff, double T, d
   int i = 0, cnt = 0;
   while (i < n && cnt < max_states)
   {
-    const double dt = t - i * T;
+    const double dt = NB_SUB(t, NB_MUL((double)i, T));
+    const double tp1 = NB_MUL(dt, dt), tp0 = NB_MUL(tp1, dt);
+    const double tv0 = NB_MUL(NB_MUL(3.0, dt), dt), tv1 = NB_MUL(2.0, dt), ta0 = NB_MUL(6.0, dt);
     double* st = states + ((size_t)b * max_states + cnt) * 12;
     for (int ax = 0; ax < 3; ax++)
     {
       const double* c = cf + ax * 32 + 4 * i;
-      st[ax] = c[0] * dt * dt * dt + c[1] * dt * dt + c[2] * dt + c[3];
-      st[3 + ax] = c[0] * 3 * dt * dt + c[1] * 2 * dt + c[2];
-      st[6 + ax] = c[0] * 6 * dt + c[1] * 2;
-      st[9 + ax] = c[0] * 6;
+      st[ax] = NB_ADD(NB_ADD(NB_ADD(NB_MUL(c[0], tp0), NB_MUL(c[1], tp1)), NB_MUL(c[2], dt)), c[3]);
+      st[3 + ax] = NB_ADD(NB_ADD(NB_MUL(c[0], tv0), NB_MUL(c[1], tv1)), c[2]);
+      st[6 + ax] = NB_ADD(NB_MUL(c[0], ta0), NB_MUL(c[1], 2.0));
+      st[9 + ax] = NB_MUL(c[0], 6.0);
     }
     cnt++;
-    t += dc;
-    if (t > (i + 1) * T) i++;
+    t = NB_ADD(t, dc);
+    if (t > NB_MUL((double)(i + 1), T)) i++;
   }
   n_states[b] = cnt;
 }

@@ -2257,21 +2257,26 @@ int orc_export_qp(const orc_params* par, const orc_replan_in* in, int fallback, 
   return m;
 }
 
-/* PolySolverGurobi::generatePwpOut sampling loop (:911-934): states[k] = pos(3) vel(3) acc(3) jerk(3) */
+/* PolySolverGurobi::generatePwpOut sampling loop (:911-934): states[k] = pos(3) vel(3) acc(3) jerk(3).
+ * Operation order as written there: the power vectors tp = (dt^3, dt^2, dt, 1), tv = (3 dt^2, 2 dt, 1), ta = (6 dt, 2)
+ * are formed first, then each state is a row of coefficients times that vector, summed from the left.
+ * KinodynamicSearch::generatePwpOut (kinodynamic_search.cpp:621-668) is the same code; tests/test_reference_pin.py
+ * compares this function with it bit for bit. */
 int orc_generate_traj(const double* coeff, int n, double T, double dc, double* states, int max_states)
 {
   double t = 0;
   int i = 0, cnt = 0;
   while (i < n && cnt < max_states)
   {
-    double dt = t - i * T;
+    const double dt = t - i * T;
+    const double tp0 = dt * dt * dt, tp1 = dt * dt, tv0 = 3 * dt * dt, tv1 = 2 * dt, ta0 = 6 * dt;
     double* st = states + 12 * cnt;
     for (int ax = 0; ax < 3; ax++)
     {
       const double* c = coeff + ax * 32 + 4 * i;
-      st[ax] = c[0] * dt * dt * dt + c[1] * dt * dt + c[2] * dt + c[3];
-      st[3 + ax] = c[0] * 3 * dt * dt + c[1] * 2 * dt + c[2];
-      st[6 + ax] = c[0] * 6 * dt + c[1] * 2;
+      st[ax] = c[0] * tp0 + c[1] * tp1 + c[2] * dt + c[3];
+      st[3 + ax] = c[0] * tv0 + c[1] * tv1 + c[2];
+      st[6 + ax] = c[0] * ta0 + c[1] * 2;
       st[9 + ax] = c[0] * 6;
     }
     cnt++;

@@ -21,7 +21,8 @@
 #include "mader_types.hpp"
 
 // access to all_combinations_, node_used_num_, goal_occupied_ and best_node_ptr_ (read only); the one member written from
-// here is num_of_static_obst_ in ref_entangle_check_pwp, which setStaticObstVert would set together with a node pool
+// here are num_of_static_obst_ in ref_entangle_check_pwp (setStaticObstVert would set it together with a node pool) and
+// pwp_out_ in ref_generate_traj (recoverPwpOut would, after a search)
 #define private public
 #include "kinodynamic_search.hpp"
 #undef private
@@ -288,4 +289,39 @@ extern "C" int ref_entangle_check_pwp(int N, int M, int self, const double* pb, 
   for (size_t i = 0; i < es.bendPointsIdx.size() && (int)i < cap; i++) bend[i] = es.bendPointsIdx[i];
   for (int i = 0; i < N + M; i++) active[i] = es.active_cases[i];
   return ent ? 1 : 0;
+}
+
+// KinodynamicSearch::generatePwpOut (kinodynamic_search.cpp:621-668), the same code as PolySolverGurobi::generatePwpOut
+// (solver_gurobi_poly.cpp:889-936, which needs Gurobi to compile): pwp_out_ is set here the way recoverPwpOut leaves it
+// (n pieces, n + 1 knots at multiples of T), then the reference samples it every dc.  states [max_states][12].
+extern "C" int ref_generate_traj(const double* coeff /*[3][8][4]*/, int n, double T, double dc, double t_start, double* states, int max_states,
+                                 double* times_out /*[n+1]*/)
+{
+  std::vector<V2> vpb(1, V2(0.0, 0.0));
+  std::streambuf* keep = std::cout.rdbuf();
+  std::ostringstream sink;
+  std::cout.rdbuf(sink.rdbuf());
+  KinodynamicSearch ks(ORC_NPOL_MAX, 3, 1, 1.0, T, 10, vpb, true, true);
+  ks.pwp_out_.clear();
+  for (int i = 0; i <= n; i++) ks.pwp_out_.times.push_back(i * T);
+  for (int i = 0; i < n; i++)
+  {
+    const double *x = coeff + 4 * i, *y = coeff + 32 + 4 * i, *z = coeff + 64 + 4 * i;
+    ks.pwp_out_.coeff_x.push_back(Eigen::Matrix<double, 4, 1>(x[0], x[1], x[2], x[3]));
+    ks.pwp_out_.coeff_y.push_back(Eigen::Matrix<double, 4, 1>(y[0], y[1], y[2], y[3]));
+    ks.pwp_out_.coeff_z.push_back(Eigen::Matrix<double, 4, 1>(z[0], z[1], z[2], z[3]));
+  }
+  mt::PieceWisePol pwp;
+  std::vector<mt::state> traj;
+  ks.generatePwpOut(pwp, traj, t_start, dc);
+  std::cout.rdbuf(keep);
+  for (size_t k = 0; k < pwp.times.size() && (int)k <= n; k++) times_out[k] = pwp.times[k];
+  int cnt = 0;
+  for (size_t k = 0; k < traj.size() && cnt < max_states; k++, cnt++)
+    for (int a = 0; a < 3; a++)
+    {
+      states[12 * k + a] = traj[k].pos(a), states[12 * k + 3 + a] = traj[k].vel(a);
+      states[12 * k + 6 + a] = traj[k].accel(a), states[12 * k + 9 + a] = traj[k].jerk(a);
+    }
+  return (int)traj.size();
 }

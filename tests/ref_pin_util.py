@@ -106,3 +106,15 @@ def entangle_check_pwp(par, self_idx, strep, bp_cnt, bp_xy, known, samp, n, cxy,
     ent = f(N, M, self_idx, _p(a["pb"]), _p(a["strep"]), _p(a["bp_cnt"]), _p(a["bp_xy"]), par.bp_max, _p(a["known"]), _p(a["samp"]),
             par.num_pol, par.num_sample_per_interval, par.T_span, n, _p(a["cxy"]), cap, _p(cnt), _p(alpha), _p(beta), _p(bend), _p(active))
     return ent, cnt, alpha, beta, bend, active
+
+
+def generate_traj(coeff, n, T, dc, t_start=0.0, max_states=4096):
+    """The reference's generatePwpOut (KinodynamicSearch's copy of the code): (states [K][12], shifted knot times)."""
+    coeff = _c(coeff, np.float64)
+    st, times = np.zeros((max_states, 12)), np.zeros(n + 1)
+    f = lib().ref_generate_traj
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p]
+    k = f(_p(coeff), n, T, dc, t_start, _p(st), max_states, _p(times))
+    assert k <= max_states
+    return st[:k].copy(), times

@@ -346,3 +346,20 @@ def test_post_check_matches_reference(oracle):
             assert np.array_equal(es.alpha[:cnt[0]], alpha[:cnt[0]]) and np.array_equal(es.beta[:cnt[0]], beta[:cnt[0]])
             assert np.array_equal(es.bend[:cnt[1]], bend[:cnt[1]]) and np.array_equal(es.active, active)
     assert n_all > 80 and 0 < n_ent < n_all
+
+
+@needs_ref
+@pytest.mark.skipif(not os.path.isdir("/root/reference/neptune/src"), reason="live run needs the reference sources")
+def test_generate_traj_matches_reference(oracle):
+    """generatePwpOut: PolySolverGurobi's copy (solver_gurobi_poly.cpp:889-936) needs Gurobi, KinodynamicSearch's copy
+    (kinodynamic_search.cpp:621-668) is the same text and compiles -- samples every dc, bit for bit, and the shifted knots."""
+    rng = np.random.default_rng(9)
+    for trial in range(60):
+        n = int(rng.integers(1, 9))
+        coeff = np.zeros((3, 8, 4))
+        coeff[:, :n] = rng.normal(size=(3, n, 4)) * rng.uniform(0.1, 10.0)
+        T, dc = float(rng.choice([0.5, 0.625, 1.0, 0.3])), float(rng.choice([0.01, 0.02, 0.013]))
+        st, times = ref.generate_traj(coeff, n, T, dc, t_start=12.5)
+        o = oracle.generate_traj(coeff, n, T, dc)
+        assert len(o) == len(st) and np.array_equal(o, st), trial
+        assert np.array_equal(times, np.arange(n + 1) * T + 12.5)
