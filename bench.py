@@ -345,9 +345,10 @@ def run_ours(args):
     sampler, l0 = None, 0
     for it in range(args.warmup + args.steps):
         k = it - args.warmup
+        if it == 0:
+            sampler = ClockSampler(local_rank)   # started with the warm-up (same load): nvidia-smi needs ~50 ms to come up
         if k == 0:
             barrier()
-            sampler = ClockSampler(local_rank)
             l0 = cyc.solver.launch_count()
         cyc.upload(hins[it % len(hins)])       # untimed: this leg measures with inputs already in HBM
         flush.zero_()
@@ -358,7 +359,24 @@ def run_ours(args):
             ev[k][1].record()
     barrier()
     launches = (cyc.solver.launch_count() - l0) if getattr(cyc, "graph", None) is None else args.steps * cyc.launches_per_cycle
+    # a short run (K x 0.4 ms) can end before the first 20 ms sample: keep the same cycle running, untimed, until there
+    # are three samples under load (bounded at 2 s)
+    extra, t_extra = 0, time.time()
+    if world == 1:
+        while len(sampler.rows) < 3 and sampler.proc is not None and time.time() - t_extra < 2.0:
+            flush.zero_()
+            cyc.step()
+            extra += 1
+            if extra % 16 == 0:
+                torch.cuda.synchronize()
+    else:   # a cycle ends in an all-gather: every rank must run the same number of extra cycles
+        for _ in range(max(0, 400 - args.steps)):
+            flush.zero_()
+            cyc.step()
+            extra += 1
+    torch.cuda.synchronize()
     clocks = sampler.stop()
+    clocks["extra_untimed_steps_for_sampling"] = extra
     cyc.check_errors()
     step_ms = np.array([e0.elapsed_time(e1) for e0, e1 in ev])
     total_ms = float(step_ms.sum())
