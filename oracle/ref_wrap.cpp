@@ -160,3 +160,51 @@ extern "C" int ref_chain(int N, int M, int self, const double* pb, const double*
   }
   return done;
 }
+
+// One tick of the online tracker: the loop of NeptuneRos::updateEntStateStaticObs (neptune_ros.cpp:798-850, a ROS file that
+// cannot be compiled) replayed around the reference's own functions -- the 9-argument entangleHSigToAddAgentInd,
+// entangleHSigToAddStatic, addAlphaBetaToList, updateBendPts.  elapsed_ms stands for the wall-clock timer of :803-804.
+// Returns 0 updated, 1 skipped by the gate; where the reference calls exit(-1) this process exits too (the test forks).
+extern "C" int ref_track(int N, int M, int self, const double* pb, const double* strep, const int* bp_cnt, const double* bp_xy,
+                         const int* bp_cnt_prev, const double* bp_xy_prev, int bp_max, int cap, int* cnt, int* alpha, double* beta,
+                         int* bend, int* active, double* prev_pos /*[N+1][2]*/, double* prev_pos_agent /*[N][2]*/,
+                         const double* latest /*[N][2]*/, const double* cur, double elapsed_ms)
+{
+  V2 pk1(cur[0], cur[1]);
+  {
+    V2 last(prev_pos[2 * N], prev_pos[2 * N + 1]);
+    if ((last - pk1).norm() < 0.05 && elapsed_ms < 100) return 1;
+  }
+  std::vector<V2> vpb = pts(pb, N);
+  std::vector<Eigen::Matrix<double, 2, 2>> rep = reps(strep, M);
+  std::vector<std::vector<V2>> bends(N), bends_prev(N);
+  for (int j = 0; j < N; j++) bends[j] = pts(bp_xy + (size_t)2 * bp_max * j, bp_cnt[j]);
+  for (int j = 0; j < N; j++) bends_prev[j] = pts(bp_xy_prev + (size_t)2 * bp_max * j, bp_cnt_prev[j]);
+  eu::ent_state st;
+  for (int i = 0; i < cnt[0]; i++) st.alphas.push_back(Eigen::Vector2i(alpha[2 * i], alpha[2 * i + 1])), st.betas.push_back(beta[i]);
+  for (int i = 0; i < cnt[1]; i++) st.bendPointsIdx.push_back(bend[i]);
+  for (int i = 0; i < N + M; i++) st.active_cases.push_back(active[i]);
+
+  std::vector<Eigen::Vector2i> add;
+  for (int i = 0; i < N; i++)
+  {
+    if (i == self) continue;
+    if (prev_pos_agent[2 * i] < -900 || bends[i].empty()) continue;
+    V2 lat(latest[2 * i], latest[2 * i + 1]);
+    eu::entangleHSigToAddAgentInd(add, V2(prev_pos[2 * i], prev_pos[2 * i + 1]), pk1, V2(prev_pos_agent[2 * i], prev_pos_agent[2 * i + 1]),
+                                  lat, vpb[self], bends[i], bends_prev[i], i + 1);
+    prev_pos[2 * i] = cur[0], prev_pos[2 * i + 1] = cur[1];
+    prev_pos_agent[2 * i] = latest[2 * i], prev_pos_agent[2 * i + 1] = latest[2 * i + 1];
+  }
+  V2 last(prev_pos[2 * N], prev_pos[2 * N + 1]);
+  eu::entangleHSigToAddStatic(add, last, pk1, rep, N);
+  eu::addAlphaBetaToList(add, st, last, vpb, vpb[self], rep, N, bends);
+  eu::updateBendPts(st, pk1, vpb, vpb[self], rep, N);
+  prev_pos[2 * N] = cur[0], prev_pos[2 * N + 1] = cur[1];
+
+  cnt[0] = (int)st.alphas.size(), cnt[1] = (int)st.bendPointsIdx.size();
+  for (size_t i = 0; i < st.alphas.size() && (int)i < cap; i++) alpha[2 * i] = st.alphas[i](0), alpha[2 * i + 1] = st.alphas[i](1), beta[i] = st.betas[i];
+  for (size_t i = 0; i < st.bendPointsIdx.size() && (int)i < cap; i++) bend[i] = st.bendPointsIdx[i];
+  for (int i = 0; i < N + M; i++) active[i] = st.active_cases[i];
+  return 0;
+}

@@ -118,3 +118,20 @@ def generate_traj(coeff, n, T, dc, t_start=0.0, max_states=4096):
     k = f(_p(coeff), n, T, dc, t_start, _p(st), max_states, _p(times))
     assert k <= max_states
     return st[:k].copy(), times
+
+
+def track(par, self_idx, strep, bp_cnt, bp_xy, bp_cnt_prev, bp_xy_prev, cnt, alpha, beta, bend, active, prev_pos, prev_pos_agent,
+          latest, cur, elapsed_ms):
+    """One tracker tick through the reference's functions; the state arrays and positions are updated in place."""
+    N, M = par.num_of_agents, par.num_of_static_obst
+    a = dict(pb=_c(par.pb, np.float64), strep=_c(strep, np.float64) if M else np.zeros((1, 2, 2)), bp_cnt=_c(bp_cnt, np.int32),
+             bp_xy=_c(bp_xy, np.float64), bp_cnt_prev=_c(bp_cnt_prev, np.int32), bp_xy_prev=_c(bp_xy_prev, np.float64),
+             latest=_c(latest, np.float64), cur=_c(cur, np.float64))
+    for x in (cnt, alpha, beta, bend, active, prev_pos, prev_pos_agent):
+        assert x.flags["C_CONTIGUOUS"]
+    f = lib().ref_track
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] * 3 + [C.c_void_p] * 6 + [C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_double]
+    return f(N, M, self_idx, _p(a["pb"]), _p(a["strep"]), _p(a["bp_cnt"]), _p(a["bp_xy"]), _p(a["bp_cnt_prev"]), _p(a["bp_xy_prev"]),
+             par.bp_max, par.ent_cap, _p(cnt), _p(alpha), _p(beta), _p(bend), _p(active), _p(prev_pos), _p(prev_pos_agent),
+             _p(a["latest"]), _p(a["cur"]), float(elapsed_ms))

@@ -363,3 +363,61 @@ def test_generate_traj_matches_reference(oracle):
         o = oracle.generate_traj(coeff, n, T, dc)
         assert len(o) == len(st) and np.array_equal(o, st), trial
         assert np.array_equal(times, np.arange(n + 1) * T + 12.5)
+
+
+def _exits_in_child(fn):
+    """Run fn() in a forked child; True when the child ended through exit(-1) (status 255), as the reference does."""
+    pid = os.fork()
+    if pid == 0:
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        os.dup2(devnull, 2)
+        try:
+            fn()
+        finally:
+            os._exit(0)
+    _, status = os.waitpid(pid, 0)
+    return os.WIFEXITED(status) and os.WEXITSTATUS(status) == 255
+
+
+@needs_ref
+def test_tracker_matches_reference(oracle):
+    """The online tracker (NeptuneRos::updateEntStateStaticObs, neptune_ros.cpp:798-850): its loop lives in a ROS file, so it
+    is replayed (oracle/ref_wrap.cpp::ref_track) around the reference's own 9-argument crossing test, static crossing test,
+    addAlphaBetaToList and updateBendPts, over multi-tick walks in which tethers gain and lose contact points.  Where the
+    oracle reports "stop k" the reference must end the process with exit(-1) -- checked in a forked child."""
+    from tests.test_tracker import _init, _walk
+    n_upd = n_gate = n_stop = 0
+    for cfg, seed in (("obst8", 21), ("mtlp5", 22), ("obst8", 23)):
+        par = config(cfg)
+        sc = make_scene(par, seed, sync=True)
+        N = par.num_of_agents
+        start, silent, frames = _walk(par, seed)
+        st, pp, ppa = _init(par, start, silent)
+        for fr in frames:
+            for b in range(N):
+                es = oracle.EntState(par.ent_cap, par.NA)
+                es.n_alpha, es.n_bend = int(st.cnt[b, 0]), int(st.cnt[b, 1])
+                es.alpha[:], es.beta[:], es.bend[:], es.active[:] = st.alpha[b], st.beta[b], st.bend[b], st.active[b]
+                cx = oracle.EntCtx(par, b, sc.strep, fr["bp_cnt"], fr["bp_xy"])
+                r_cnt, r_alpha, r_beta = st.cnt[b].copy(), st.alpha[b].copy(), st.beta[b].copy()
+                r_bend, r_active, r_pp, r_ppa = st.bend[b].copy(), st.active[b].copy(), pp[b].copy(), ppa[b].copy()
+                args = (par, b, sc.strep, fr["bp_cnt"], fr["bp_xy"], fr["bp_cnt_prev"], fr["bp_xy_prev"], r_cnt, r_alpha, r_beta, r_bend,
+                        r_active, r_pp, r_ppa, fr["latest"], fr["cur"][b], float(fr["elapsed"][b]))
+                o = oracle.track(es, cx, fr["bp_cnt_prev"], fr["bp_xy_prev"], pp[b], ppa[b], np.ascontiguousarray(fr["latest"]), fr["cur"][b],
+                                 float(fr["elapsed"][b]))
+                if o < 0:
+                    assert o > -100 and _exits_in_child(lambda: ref.track(*args)), (cfg, b, o)
+                    n_stop += 1
+                else:
+                    assert ref.track(*args) == o
+                    assert (es.n_alpha, es.n_bend) == (r_cnt[0], r_cnt[1])
+                    assert np.array_equal(es.alpha[:r_cnt[0]], r_alpha[:r_cnt[0]]) and np.array_equal(es.beta[:r_cnt[0]], r_beta[:r_cnt[0]])
+                    assert np.array_equal(es.bend[:r_cnt[1]], r_bend[:r_cnt[1]]) and np.array_equal(es.active, r_active)
+                    assert np.array_equal(pp[b], r_pp) and np.array_equal(ppa[b], r_ppa)
+                    n_upd += o == 0
+                    n_gate += o == 1
+                st.cnt[b] = [es.n_alpha, es.n_bend]
+                st.alpha[b], st.beta[b], st.bend[b], st.active[b] = es.alpha, es.beta, es.bend, es.active
+    assert n_upd > 300 and n_gate > 5
+    print("tracker ticks: updated", n_upd, "gated", n_gate, "reference exits", n_stop)
