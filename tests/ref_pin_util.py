@@ -135,3 +135,32 @@ def track(par, self_idx, strep, bp_cnt, bp_xy, bp_cnt_prev, bp_xy_prev, cnt, alp
     return f(N, M, self_idx, _p(a["pb"]), _p(a["strep"]), _p(a["bp_cnt"]), _p(a["bp_xy"]), _p(a["bp_cnt_prev"]), _p(a["bp_xy_prev"]),
              par.bp_max, par.ent_cap, _p(cnt), _p(alpha), _p(beta), _p(bend), _p(active), _p(prev_pos), _p(prev_pos_agent),
              _p(a["latest"]), _p(a["cur"]), float(elapsed_ms))
+
+
+def _count_exits(path):
+    """Script mode: fork once per pickled ref.track argument tuple; print how many children ended with exit status 255."""
+    import pickle
+    import sys
+    sys.path.insert(0, ROOT)
+    with open(path, "rb") as f:
+        cases = pickle.load(f)
+    lib()
+    n = 0
+    for args in cases:
+        pid = os.fork()
+        if pid == 0:
+            devnull = os.open(os.devnull, os.O_WRONLY)
+            os.dup2(devnull, 1)
+            os.dup2(devnull, 2)
+            try:
+                track(*args)
+            finally:
+                os._exit(0)
+        _, status = os.waitpid(pid, 0)
+        n += os.WIFEXITED(status) and os.WEXITSTATUS(status) == 255
+    print(n)
+
+
+if __name__ == "__main__":
+    import sys
+    _count_exits(sys.argv[1])

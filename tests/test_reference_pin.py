@@ -365,19 +365,22 @@ def test_generate_traj_matches_reference(oracle):
         assert np.array_equal(times, np.arange(n + 1) * T + 12.5)
 
 
-def _exits_in_child(fn):
-    """Run fn() in a forked child; True when the child ended through exit(-1) (status 255), as the reference does."""
-    pid = os.fork()
-    if pid == 0:
-        devnull = os.open(os.devnull, os.O_WRONLY)
-        os.dup2(devnull, 1)
-        os.dup2(devnull, 2)
-        try:
-            fn()
-        finally:
-            os._exit(0)
-    _, status = os.waitpid(pid, 0)
-    return os.WIFEXITED(status) and os.WEXITSTATUS(status) == 255
+def _reference_exits(cases):
+    """How many of the tracker ticks in `cases` (argument tuples of ref.track) end the process through exit(-1), as the
+    reference does at its "stop" sites.  Runs in a fresh single-threaded interpreter that forks once per case
+    (tests/ref_pin_util.py as a script), so nothing here forks a process that has OpenMP / torch threads."""
+    import pickle
+    import subprocess
+    import sys
+    import tempfile
+    with tempfile.NamedTemporaryFile(suffix=".pkl", delete=False) as f:
+        pickle.dump(cases, f)
+    try:
+        out = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "ref_pin_util.py"), f.name],
+                             capture_output=True, text=True, check=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    finally:
+        os.unlink(f.name)
+    return int(out.stdout.strip().splitlines()[-1])
 
 
 @needs_ref
@@ -385,9 +388,10 @@ def test_tracker_matches_reference(oracle):
     """The online tracker (NeptuneRos::updateEntStateStaticObs, neptune_ros.cpp:798-850): its loop lives in a ROS file, so it
     is replayed (oracle/ref_wrap.cpp::ref_track) around the reference's own 9-argument crossing test, static crossing test,
     addAlphaBetaToList and updateBendPts, over multi-tick walks in which tethers gain and lose contact points.  Where the
-    oracle reports "stop k" the reference must end the process with exit(-1) -- checked in a forked child."""
+    oracle reports "stop k" the reference must end the process with exit(-1) -- checked in forked children of a helper process."""
     from tests.test_tracker import _init, _walk
-    n_upd = n_gate = n_stop = 0
+    n_upd = n_gate = 0
+    stops = []
     for cfg, seed in (("obst8", 21), ("mtlp5", 22), ("obst8", 23)):
         par = config(cfg)
         sc = make_scene(par, seed, sync=True)
@@ -407,8 +411,8 @@ def test_tracker_matches_reference(oracle):
                 o = oracle.track(es, cx, fr["bp_cnt_prev"], fr["bp_xy_prev"], pp[b], ppa[b], np.ascontiguousarray(fr["latest"]), fr["cur"][b],
                                  float(fr["elapsed"][b]))
                 if o < 0:
-                    assert o > -100 and _exits_in_child(lambda: ref.track(*args)), (cfg, b, o)
-                    n_stop += 1
+                    assert o > -100, (cfg, b, o)
+                    stops.append(args)
                 else:
                     assert ref.track(*args) == o
                     assert (es.n_alpha, es.n_bend) == (r_cnt[0], r_cnt[1])
@@ -419,5 +423,6 @@ def test_tracker_matches_reference(oracle):
                     n_gate += o == 1
                 st.cnt[b] = [es.n_alpha, es.n_bend]
                 st.alpha[b], st.beta[b], st.bend[b], st.active[b] = es.alpha, es.beta, es.bend, es.active
-    assert n_upd > 300 and n_gate > 5
-    print("tracker ticks: updated", n_upd, "gated", n_gate, "reference exits", n_stop)
+    assert n_upd > 300 and n_gate > 5 and len(stops) > 10
+    assert _reference_exits(stops) == len(stops)
+    print("tracker ticks: updated", n_upd, "gated", n_gate, "reference exits", len(stops))
