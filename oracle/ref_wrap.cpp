@@ -208,3 +208,38 @@ extern "C" int ref_track(int N, int M, int self, const double* pb, const double*
   for (int i = 0; i < N + M; i++) active[i] = st.active_cases[i];
   return 0;
 }
+
+// Neptune::PredictAlphasBetas (neptune.cpp:976-1008; neptune.cpp needs CGAL, Gurobi and ROS) replayed around the reference's
+// own 8-argument crossing test, static crossing test, addAlphaBetaToList and updateBendPts.  samp0 [N][2] is
+// SampledPointsForAll[i][0].col(0), known[i] == 0 an empty SampledPointsForAll[i].  State in / out as in ref_track.
+extern "C" int ref_predict(int N, int M, int self, const double* pb, const double* strep, const int* bp_cnt, const double* bp_xy,
+                           int bp_max, int cap, int* cnt, int* alpha, double* beta, int* bend, int* active, const double* prev_pos,
+                           const double* prev_pos_agent, const double* cur, const double* samp0, const unsigned char* known)
+{
+  V2 pk1(cur[0], cur[1]);
+  std::vector<V2> vpb = pts(pb, N);
+  std::vector<Eigen::Matrix<double, 2, 2>> rep = reps(strep, M);
+  std::vector<std::vector<V2>> bends(N);
+  for (int j = 0; j < N; j++) bends[j] = pts(bp_xy + (size_t)2 * bp_max * j, bp_cnt[j]);
+  eu::ent_state st;
+  for (int i = 0; i < cnt[0]; i++) st.alphas.push_back(Eigen::Vector2i(alpha[2 * i], alpha[2 * i + 1])), st.betas.push_back(beta[i]);
+  for (int i = 0; i < cnt[1]; i++) st.bendPointsIdx.push_back(bend[i]);
+  for (int i = 0; i < N + M; i++) st.active_cases.push_back(active[i]);
+  std::vector<Eigen::Vector2i> add;
+  for (int i = 0; i < N; i++)
+  {
+    if (i == self || !known[i]) continue;
+    V2 pik1(samp0[2 * i], samp0[2 * i + 1]);
+    eu::entangleHSigToAddAgentInd(add, V2(prev_pos[2 * i], prev_pos[2 * i + 1]), pk1, V2(prev_pos_agent[2 * i], prev_pos_agent[2 * i + 1]), pik1,
+                                  vpb[self], bends[i], i + 1);
+  }
+  V2 last(prev_pos[2 * N], prev_pos[2 * N + 1]);
+  eu::entangleHSigToAddStatic(add, last, pk1, rep, N);
+  eu::addAlphaBetaToList(add, st, last, vpb, vpb[self], rep, N, bends);
+  eu::updateBendPts(st, pk1, vpb, vpb[self], rep, N);
+  cnt[0] = (int)st.alphas.size(), cnt[1] = (int)st.bendPointsIdx.size();
+  for (size_t i = 0; i < st.alphas.size() && (int)i < cap; i++) alpha[2 * i] = st.alphas[i](0), alpha[2 * i + 1] = st.alphas[i](1), beta[i] = st.betas[i];
+  for (size_t i = 0; i < st.bendPointsIdx.size() && (int)i < cap; i++) bend[i] = st.bendPointsIdx[i];
+  for (int i = 0; i < N + M; i++) active[i] = st.active_cases[i];
+  return 0;
+}

@@ -164,3 +164,16 @@ def _count_exits(path):
 if __name__ == "__main__":
     import sys
     _count_exits(sys.argv[1])
+
+
+def predict(par, self_idx, strep, bp_cnt, bp_xy, cnt, alpha, beta, bend, active, prev_pos, prev_pos_agent, cur, samp0, known):
+    """PredictAlphasBetas through the reference's functions; cnt / alpha / beta / bend / active are updated in place."""
+    N, M = par.num_of_agents, par.num_of_static_obst
+    a = dict(pb=_c(par.pb, np.float64), strep=_c(strep, np.float64) if M else np.zeros((1, 2, 2)), bp_cnt=_c(bp_cnt, np.int32),
+             bp_xy=_c(bp_xy, np.float64), pp=_c(prev_pos, np.float64), ppa=_c(prev_pos_agent, np.float64), cur=_c(cur, np.float64),
+             samp0=_c(samp0, np.float64), known=_c(known, np.uint8))
+    f = lib().ref_predict
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 10
+    return f(N, M, self_idx, _p(a["pb"]), _p(a["strep"]), _p(a["bp_cnt"]), _p(a["bp_xy"]), par.bp_max, par.ent_cap, _p(cnt), _p(alpha),
+             _p(beta), _p(bend), _p(active), _p(a["pp"]), _p(a["ppa"]), _p(a["cur"]), _p(a["samp0"]), _p(a["known"]))

@@ -426,3 +426,46 @@ def test_tracker_matches_reference(oracle):
     assert n_upd > 300 and n_gate > 5 and len(stops) > 10
     assert _reference_exits(stops) == len(stops)
     print("tracker ticks: updated", n_upd, "gated", n_gate, "reference exits", len(stops))
+
+
+@needs_ref
+def test_predict_matches_reference(oracle):
+    """Neptune::PredictAlphasBetas (neptune.cpp:976-1008) replayed around the reference's own functions against orc_predict,
+    from the states a tracker walk passes through (signature words of several entries, wrapped tethers)."""
+    from tests.test_tracker import _init, _walk
+    n = longest = 0
+    for cfg, seed in (("obst8", 31), ("mtlp5", 32)):
+        par = config(cfg)
+        sc = make_scene(par, seed, sync=True)
+        N = par.num_of_agents
+        start, silent, frames = _walk(par, seed)
+        st, pp, ppa = _init(par, start, silent)
+        rng = np.random.default_rng(seed)
+        for fr in frames:
+            for b in range(N):
+                cx = oracle.EntCtx(par, b, sc.strep, fr["bp_cnt"], fr["bp_xy"])
+                es = oracle.EntState(par.ent_cap, par.NA)
+                es.n_alpha, es.n_bend = int(st.cnt[b, 0]), int(st.cnt[b, 1])
+                es.alpha[:], es.beta[:], es.bend[:], es.active[:] = st.alpha[b], st.beta[b], st.bend[b], st.active[b]
+                # the prediction from the current tracker state to where the agent will be at the start of its plan
+                ahead = fr["cur"][b] + rng.normal(0, 0.8, size=2)
+                samp0 = fr["latest"] + rng.normal(0, 0.5, size=(N, 2))
+                known = (~silent).astype(np.uint8)
+                e2 = oracle.EntState(par.ent_cap, par.NA)
+                e2.n_alpha, e2.n_bend = es.n_alpha, es.n_bend
+                e2.alpha[:], e2.beta[:], e2.bend[:], e2.active[:] = es.alpha, es.beta, es.bend, es.active
+                rc = oracle.predict(e2, cx, pp[b], ppa[b], ahead, samp0, known)
+                r = [st.cnt[b].copy(), st.alpha[b].copy(), st.beta[b].copy(), st.bend[b].copy(), st.active[b].copy()]
+                if rc == 0:
+                    ref.predict(par, b, sc.strep, fr["bp_cnt"], fr["bp_xy"], *r, pp[b], ppa[b], ahead, samp0, known)
+                    assert (e2.n_alpha, e2.n_bend) == (r[0][0], r[0][1])
+                    assert np.array_equal(e2.alpha[:r[0][0]], r[1][:r[0][0]]) and np.array_equal(e2.beta[:r[0][0]], r[2][:r[0][0]])
+                    assert np.array_equal(e2.bend[:r[0][1]], r[3][:r[0][1]]) and np.array_equal(e2.active, r[4])
+                    n += 1
+                    longest = max(longest, e2.n_alpha)
+                # advance the tracker itself with the oracle (pinned by test_tracker_matches_reference)
+                o = oracle.track(es, cx, fr["bp_cnt_prev"], fr["bp_xy_prev"], pp[b], ppa[b], np.ascontiguousarray(fr["latest"]), fr["cur"][b],
+                                 float(fr["elapsed"][b]))
+                st.cnt[b] = [es.n_alpha, es.n_bend]
+                st.alpha[b], st.beta[b], st.bend[b], st.active[b] = es.alpha, es.beta, es.bend, es.active
+    assert n > 400 and longest >= 2
