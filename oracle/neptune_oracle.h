@@ -8,7 +8,9 @@
  *
  * PARITY STATUS, by part:
  *  - front-end search (neptune_search.c): PINNED against the reference's own
- *    kinodynamic_search.cpp, whole runs compared field by field.
+ *    kinodynamic_search.cpp, whole runs compared field by field; trajectory
+ *    sampling and composePieceWisePol: PINNED against kinodynamic_search.cpp /
+ *    utils.cpp.
  *  - entanglement chain (crossing tests with 8 and 9 arguments and for static
  *    obstacles, addAlphaBetaToList, updateBendPts, getLengthToContactPoints,
  *    the per-interval loop around them) and gjk::collision: PINNED against the

@@ -1,7 +1,10 @@
-// Stand-in for <ros/ros.h> (TEST INFRASTRUCTURE): the reference's timer.hpp reads ros::Time::now(); nothing else of ROS is
-// touched by the sources compiled into oracle/_ref.
+// Stand-in for <ros/ros.h> (TEST INFRASTRUCTURE): a clock for the reference's timer.hpp and utils.cpp, and the two names
+// utils.hpp mentions in a template (NodeHandle, ROS_ERROR).  Nothing else of ROS is touched by the sources compiled into
+// oracle/_ref.
 #pragma once
 #include <chrono>
+#include <cstdio>
+#include <string>
 namespace ros
 {
 struct Time
@@ -14,4 +17,14 @@ struct Time
   double toSec() const { return s; }
 };
 typedef Time WallTime;
+struct NodeHandle
+{
+  template <typename T>
+  bool getParam(const std::string&, T&) const
+  {
+    return false;
+  }
+  std::string resolveName(const std::string& n, bool = true) const { return n; }
+};
 }  // namespace ros
+#define ROS_ERROR(...) std::fprintf(stderr, __VA_ARGS__)

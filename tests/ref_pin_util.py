@@ -177,3 +177,14 @@ def predict(par, self_idx, strep, bp_cnt, bp_xy, cnt, alpha, beta, bend, active,
     f.argtypes = [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_void_p] * 10
     return f(N, M, self_idx, _p(a["pb"]), _p(a["strep"]), _p(a["bp_cnt"]), _p(a["bp_xy"]), par.bp_max, par.ent_cap, _p(cnt), _p(alpha),
              _p(beta), _p(bend), _p(active), _p(a["pp"]), _p(a["ppa"]), _p(a["cur"]), _p(a["samp0"]), _p(a["known"]))
+
+
+def compose_records(t, dc, p1, p2):
+    """The reference's mu::composePieceWisePol on two records: (n_pieces, times [n+1], coeff [3][n][4], p1 times, p2 times)."""
+    p1, p2 = _c(p1, np.float64), _c(p2, np.float64)
+    times, coeff, t1, t2 = np.zeros(64), np.zeros((3, 64, 4)), np.zeros(17), np.zeros(17)
+    f = lib().ref_compose_records
+    f.restype = C.c_int
+    f.argtypes = [C.c_double, C.c_double] + [C.c_void_p] * 6
+    n = f(t, dc, _p(p1), _p(p2), _p(times), _p(coeff), _p(t1), _p(t2))
+    return n, times[:n + 1].copy() if n else times[:0], coeff[:, :n].copy(), t1, t2

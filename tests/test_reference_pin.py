@@ -469,3 +469,29 @@ def test_predict_matches_reference(oracle):
                 st.cnt[b] = [es.n_alpha, es.n_bend]
                 st.alpha[b], st.beta[b], st.bend[b], st.active[b] = es.alpha, es.beta, es.bend, es.active
     assert n > 400 and longest >= 2
+
+
+@needs_ref
+def test_compose_matches_reference(oracle):
+    """mu::composePieceWisePol of the reference's own utils.cpp (:318-402) against orc_compose_records on every branch: the
+    composed knots and coefficients, the empty "dummy" result, and the in-place adjustment of the arguments' first knots."""
+    from tests import compose_util as cu
+    rng = np.random.default_rng(6)
+    seen = set()
+    for it in range(1400):
+        kind = cu.KINDS[it % len(cu.KINDS)]
+        t, p1, p2 = cu.random_case(rng, kind)
+        if int(p1[0]) < 1 or int(p2[0]) < 1:   # empty pwp: the reference reads .back() of an empty vector
+            continue
+        n, out, q1, q2 = oracle.compose_records(t, 0.05, p1, p2)
+        rn, rt, rc, t1, t2 = ref.compose_records(t, 0.05, p1, p2)
+        if n < 0:   # more than 16 pieces: the record cannot hold it, the reference has no bound
+            assert rn > 16
+            continue
+        assert n == rn, (kind, it)
+        assert np.array_equal(q1[1:2 + int(p1[0])], t1[:1 + int(p1[0])]) and np.array_equal(q2[1:2 + int(p2[0])], t2[:1 + int(p2[0])])
+        if n:
+            ot, oc = cu.rec_to(out)
+            assert np.array_equal(np.array(ot), rt) and np.array_equal(oc, rc)
+        seen.add((kind, n > 0))
+    assert len(seen) >= len(cu.KINDS) and (("stale", False) in seen)
