@@ -1,8 +1,8 @@
 // ref_wrap_search.cpp -- a C entry point around the REFERENCE's own KinodynamicSearch (TEST INFRASTRUCTURE).
 //
 // oracle/Makefile (target _ref) compiles neptune/src/kinodynamic_search.cpp where it lies under /root/reference,
-// unmodified, against the Eigen stand-in (oracle/eigen_shim) and the header stand-ins in oracle/ref_stubs (ROS clock,
-// utils.hpp, bspline_utils.hpp, exprtk.hpp: nothing of theirs is used by the search), together with this file.
+// unmodified, against the Eigen stand-in (oracle/eigen_shim) and the header stand-ins in oracle/ref_stubs (ROS clock and
+// message structs, bspline_utils.hpp, exprtk.hpp, glpk.h: nothing of theirs is used by the search), together with this file.
 // ref_search() drives the class exactly as Neptune does (neptune.cpp:89-97 construction, :662 / :670 static obstacles,
 // :1310 clearProcess, :1419-1452 setRunTime / setInitZCoeffs / setUp / run, :1509-1510 getters) on the oracle's own
 // plain-array inputs and writes the oracle's output layout, so tests/test_reference_pin.py can compare field by field.
@@ -28,38 +28,6 @@
 #undef private
 
 #include "neptune_oracle.h"
-
-// separator::Separator is only used by collidesWithObstaclesGivenVertexes, which run() never calls; GLPK is absent.
-namespace separator
-{
-struct Separator::PImpl
-{
-};
-Separator::Separator() {}
-Separator::~Separator() {}
-static bool unavailable()
-{
-  std::fprintf(stderr, "ref_wrap_search: separator::Separator needs GLPK and is not part of this build\n");
-  abort();
-  return false;
-}
-bool Separator::solveModel(Eigen::Vector3d&, double&, const std::vector<Eigen::Vector3d>&, const std::vector<Eigen::Vector3d>&) { return unavailable(); }
-bool Separator::solveModel(Eigen::Vector3d&, double&, const Eigen::Matrix<double, 3, Eigen::Dynamic>&,
-                           const Eigen::Matrix<double, 3, Eigen::Dynamic>&)
-{
-  return unavailable();
-}
-bool Separator::solveModel(const Eigen::Matrix<double, 2, Eigen::Dynamic>&, const Eigen::Matrix<double, 2, Eigen::Dynamic>&) { return unavailable(); }
-bool Separator::solveModel(Eigen::Vector3d&, const Eigen::Matrix<double, 2, Eigen::Dynamic>&, const Eigen::Matrix<double, 2, Eigen::Dynamic>&)
-{
-  return unavailable();
-}
-bool Separator::solveModel(Eigen::Vector3d&, const Eigen::Matrix<double, 2, Eigen::Dynamic>&, const Eigen::Matrix<double, 2, Eigen::Dynamic>&,
-                           const Eigen::Matrix<double, 2, Eigen::Dynamic>&)
-{
-  return unavailable();
-}
-}  // namespace separator
 
 typedef Eigen::Vector2d V2;
 

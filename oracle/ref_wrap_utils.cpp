@@ -42,3 +42,42 @@ extern "C" int ref_compose_records(double t, double dc, const double* p1, const 
       out_coeff[(0 * 64 + i) * 4 + k] = p.coeff_x[i](k), out_coeff[(1 * 64 + i) * 4 + k] = p.coeff_y[i](k), out_coeff[(2 * 64 + i) * 4 + k] = p.coeff_z[i](k);
   return n;
 }
+
+// separator::Separator of the reference's own separator_glpk.cpp (submodules/separator), 2-D variants, with the LP engine
+// supplied by the test through ref_stubs/glpk.h.  variant 0: solveModel(A, B) (:500-604); 1: solveModel(n, A, B)
+// (:248-373); 2: solveModel(n, A, Aplus, B) (:375-498).  Points are [n][2].
+#include "separator.hpp"
+static Eigen::Matrix<double, 2, Eigen::Dynamic> points2(const double* p, int n)
+{
+  Eigen::Matrix<double, 2, Eigen::Dynamic> m(2, n);
+  for (int i = 0; i < n; i++) m(0, i) = p[2 * i], m(1, i) = p[2 * i + 1];
+  return m;
+}
+extern "C" int ref_separator_solve(int variant, const double* A, int nA, const double* Aplus, int nAp, const double* B, int nB, double* n_out)
+{
+  separator::Separator sep;
+  Eigen::Vector3d n(0.0, 0.0, 0.0);
+  bool ok;
+  if (variant == 0)
+    ok = sep.solveModel(points2(A, nA), points2(B, nB));
+  else if (variant == 1)
+    ok = sep.solveModel(n, points2(A, nA), points2(B, nB));
+  else
+    ok = sep.solveModel(n, points2(A, nA), points2(Aplus, nAp), points2(B, nB));
+  n_out[0] = n(0), n_out[1] = n(1), n_out[2] = n(2);
+  return ok ? 1 : 0;
+}
+
+// The 3-D entry point the reference's own test_separator.cpp drives (solveModel(n, d, pointsA, pointsB), :53-62 -> :64-246).
+extern "C" int ref_separator_solve3d(const double* A, int nA, const double* B, int nB, double* n_out /*[4]: n, d*/)
+{
+  separator::Separator sep;
+  std::vector<Eigen::Vector3d> a, b;
+  for (int i = 0; i < nA; i++) a.push_back(Eigen::Vector3d(A[3 * i], A[3 * i + 1], A[3 * i + 2]));
+  for (int i = 0; i < nB; i++) b.push_back(Eigen::Vector3d(B[3 * i], B[3 * i + 1], B[3 * i + 2]));
+  Eigen::Vector3d n(0.0, 0.0, 0.0);
+  double d = 0.0;
+  const bool ok = sep.solveModel(n, d, a, b);
+  n_out[0] = n(0), n_out[1] = n(1), n_out[2] = n(2), n_out[3] = d;
+  return ok ? 1 : 0;
+}

@@ -188,3 +188,63 @@ def compose_records(t, dc, p1, p2):
     f.argtypes = [C.c_double, C.c_double] + [C.c_void_p] * 6
     n = f(t, dc, _p(p1), _p(p2), _p(times), _p(coeff), _p(t1), _p(t2))
     return n, times[:n + 1].copy() if n else times[:0], coeff[:, :n].copy(), t1, t2
+
+
+_LP_CB = None
+LP_MODELS = []   # (G rows as the reference built them, lower, upper) of every LP solved since the last clear
+
+
+def _install_highs():
+    """Give the GLPK stand-in an LP engine: HiGHS (scipy) on exactly the model the reference's separator built."""
+    global _LP_CB
+    if _LP_CB is not None:
+        return
+    from scipy.optimize import linprog
+    I, D = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    proto = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, I, D, D, I, D, D, D, C.c_int, C.c_int, I, I, D, D)
+
+    def solve(rows, cols, rt, rlb, rub, ct, clb, cub, obj, direction, ne, ia, ja, ar, x):
+        G = np.zeros((rows, cols))
+        for k in range(ne):
+            G[ia[k] - 1, ja[k] - 1] += ar[k]
+        lo = np.array([rlb[i] if rt[i] in (2, 4, 5) else -np.inf for i in range(rows)])
+        up = np.array([rub[i] if rt[i] in (3, 4) else (rlb[i] if rt[i] == 5 else np.inf) for i in range(rows)])
+        LP_MODELS.append((G, lo, up))
+        A_ub = np.vstack([G[np.isfinite(up)], -G[np.isfinite(lo)]])
+        b_ub = np.concatenate([up[np.isfinite(up)], -lo[np.isfinite(lo)]])
+        bounds = [(clb[j] if ct[j] in (2, 4, 5) else None, cub[j] if ct[j] in (3, 4) else (clb[j] if ct[j] == 5 else None)) for j in range(cols)]
+        c = np.array([obj[j] for j in range(cols)]) * (-1.0 if direction == 2 else 1.0)
+        r = linprog(c, A_ub=A_ub if len(A_ub) else None, b_ub=b_ub if len(b_ub) else None, bounds=bounds, method="highs")
+        if r.status == 0:
+            for j in range(cols):
+                x[j] = r.x[j]
+            return 5    # GLP_OPT
+        return 6 if r.status == 3 else 4   # GLP_UNBND / GLP_NOFEAS
+
+    _LP_CB = proto(solve)
+    lib().ref_set_lp_solver(_LP_CB)
+
+
+def separator_solve(variant, A, B, Aplus=None):
+    """The reference's separator::Separator::solveModel (2-D variants) with HiGHS as its LP engine: (solved, n[3])."""
+    _install_highs()
+    A, B = _c(A, np.float64), _c(B, np.float64)
+    Ap = _c(Aplus, np.float64) if Aplus is not None else np.zeros((0, 2))
+    n = np.zeros(3)
+    f = lib().ref_separator_solve
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    ok = f(variant, _p(A), len(A), _p(Ap) if len(Ap) else None, len(Ap), _p(B), len(B), _p(n))
+    return bool(ok), n
+
+
+def separator_solve3d(A, B):
+    """The 3-D solveModel that the reference's test_separator.cpp calls: (solved, n[3], d)."""
+    _install_highs()
+    A, B = _c(A, np.float64), _c(B, np.float64)
+    out = np.zeros(4)
+    f = lib().ref_separator_solve3d
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    ok = f(_p(A), len(A), _p(B), len(B), _p(out))
+    return bool(ok), out[:3].copy(), float(out[3])

@@ -495,3 +495,38 @@ def test_compose_matches_reference(oracle):
             assert np.array_equal(np.array(ot), rt) and np.array_equal(oc, rc)
         seen.add((kind, n > 0))
     assert len(seen) >= len(cu.KINDS) and (("stale", False) in seen)
+
+
+@needs_ref
+def test_separator_matches_reference(oracle):
+    """separator::Separator::solveModel of the reference's own separator_glpk.cpp (2-D variants :500-604, :248-373,
+    :375-498) with HiGHS standing in for GLPK as the LP engine (oracle/ref_stubs/glpk.h records the model the reference
+    builds and hands it to scipy): the solved flag equals the oracle's on every case, the model is the one the oracle
+    documents (rows [x y 1], >= 1 for A and A+, <= -1 for B, free columns, zero objective on d), and the line the
+    reference returns separates.  The known answer of the reference's own test (test_separator.cpp:23-32 -> "Solved= 1")
+    is reproduced through its 3-D entry point."""
+    rng = np.random.default_rng(12)
+    n_sep = 0
+    for t in range(600):
+        A = rng.normal(size=(rng.integers(1, 10), 2)) * 1.5 + rng.normal(size=2) * 2
+        B = rng.normal(size=(4, 2)) + rng.normal(size=2) * 2
+        variant = t % 3
+        Ap = (A + rng.normal(size=A.shape) * 0.3) if variant == 2 else None
+        allA = np.vstack([A, Ap]) if Ap is not None else A
+        ok, _ = oracle.separate(allA, B)
+        del ref.LP_MODELS[:]
+        r, n = ref.separator_solve(variant, A, B, Ap)
+        assert r == ok, (t, variant)
+        G, lo, up = ref.LP_MODELS[-1]
+        assert np.array_equal(G, np.c_[np.vstack([allA, B]), np.ones(len(allA) + len(B))])
+        assert np.array_equal(lo[:len(allA)], np.ones(len(allA))) and np.all(np.isinf(up[:len(allA)]))
+        assert np.array_equal(up[len(allA):], -np.ones(len(B))) and np.all(np.isinf(lo[len(allA):]))
+        if r and variant:
+            assert (allA @ n[:2] + n[2] >= 1 - 1e-7).all() and (B @ n[:2] + n[2] <= -1 + 1e-7).all()
+        n_sep += r
+    assert 150 < n_sep < 550
+    A3 = np.array([[-3.50, 21, 1.4], [-2.71, 2.13, 1.6], [0.53, 0.51, 1.4], [-3.50, 0.21, 0.3]])
+    B3 = np.array([[-2.3, 4.69, 6.2], [3.7, 2.13, 65.6], [6.5, 2.93, 2.8], [0.3, 4.8, 9.2], [1.5, 6.7, 2.9]])
+    ok, n3, d3 = ref.separator_solve3d(A3, B3)
+    assert ok and oracle.lp_separable(A3, B3)
+    assert (A3 @ n3 + d3 > 0).all() and (B3 @ n3 + d3 < 0).all()
