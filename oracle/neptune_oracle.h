@@ -17,14 +17,17 @@
  *    reference's own entangle_utils.cpp and gjk.cpp, compiled where they lie
  *    (oracle/Makefile target _ref, Eigen replaced by oracle/eigen_shim) --
  *    tests/test_reference_pin.py, recorded vectors tests/golden/reference/ref_chain.npz.
- *  - separating-line LP, trajectory QP, hulls: "parity unpinned" against a
- *    recorded Gurobi/GLPK/CGAL run -- the reference ships no golden vectors
- *    and none of Gurobi 9.1.2, GLPK 4.65, CGAL 4.14.2, Eigen3 or ROS exist in
- *    this image.  These are
- * pinned instead by (i) the one known answer in the tree
- * (submodules/separator/src/test_separator.cpp:23-32 => Solved=1),
- * (ii) HiGHS (scipy) as an independent LP/QP solver on every golden scene,
- * (iii) analytic cases.  tests/test_oracle_*.py hold those checks.
+ *  - separating-line LP: model and solved flag PINNED against the reference's
+ *    own separator_glpk.cpp run with HiGHS as its LP engine (GLPK is absent;
+ *    oracle/ref_stubs/glpk.h records the model); the vertex GLPK would return
+ *    for the zero objective is "parity unpinned" (oracle and product return the
+ *    minimum-norm line).
+ *  - trajectory QP, hull order: "parity unpinned" against a recorded
+ *    Gurobi / CGAL run -- the reference ships no golden vectors and none of
+ *    Gurobi 9.1.2, CGAL 4.14.2, GLPK 4.65, Eigen3 or ROS exist in this image
+ *    (see DESIGN.md).  These are checked instead by HiGHS (scipy) as an
+ *    independent QP solver on every golden scene and by analytic cases
+ *    (tests/test_oracle.py).
  *
  * Every function cites the reference file:line it restates (paths relative
  * to /root/reference).
