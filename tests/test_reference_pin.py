@@ -530,3 +530,40 @@ def test_separator_matches_reference(oracle):
     ok, n3, d3 = ref.separator_solve3d(A3, B3)
     assert ok and oracle.lp_separable(A3, B3)
     assert (A3 @ n3 + d3 > 0).all() and (B3 @ n3 + d3 < 0).all()
+
+
+def test_eigen_stand_in_semantics():
+    """The Eigen stand-in the reference sources are compiled against (oracle/eigen_shim) behaves like Eigen where those
+    sources depend on it: tests/cpp/eigen_shim_check.cpp against numpy."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "tests", "cpp"), "_build/eigen_shim_check"], check=True, capture_output=True)
+    out = subprocess.run([os.path.join(root, "tests", "cpp", "_build", "eigen_shim_check")], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for line in out.strip().splitlines():
+        f = line.split()
+        if f[0] == "norm":
+            got["norm"], got["dot"] = float(f[1]), float(f[3])
+        else:
+            got[f[0]] = np.array([float(x) for x in f[1:]])
+    A = np.array([[4, -2, 1, 0.5], [3, 6, -4, 2], [2, 1, 8, -1], [0.25, -3, 2, 5]])   # filled row by row
+    V = np.array([[2, 0.5, -1], [1, 3, 0.25], [-2, 1, 4]])
+    P = np.array([[1, 2, 3, 4], [-1, 0.5, 2, -3]])
+    t = np.array([0.125, 0.25, 0.5, 1])
+    assert np.array_equal(got["A"], A.ravel()) and np.array_equal(got["A_data"], A.T.ravel())   # column-major storage
+    assert np.allclose(got["A_inv"], np.linalg.inv(A).ravel(), rtol=1e-13, atol=1e-15)
+    assert np.allclose(got["V_inv"], np.linalg.inv(V).ravel(), rtol=1e-13, atol=1e-15)
+    assert np.array_equal(got["P_A"], (P @ A).ravel()) and np.array_equal(got["P_blk_V"], (P[:, :3] @ V).ravel())
+    assert np.array_equal(got["A_T"], A.T.ravel()) and np.array_equal(got["P_t"], P @ t)
+    assert got["colT_t"][0] == A[:, 1] @ t
+    e = np.array([1, 2, 3, 4, 5, 6.0])
+    e[:2] = e[:2] + e[2:4] * 0.5 + e[4:] * 0.25
+    e[4:] = e[4:] - e[:2]
+    assert np.array_equal(got["e"], e)
+    Q = np.zeros((2, 4))
+    Q[0] = t
+    Q[1] = 3 * Q[0]
+    Q[:, 3] = Q[:, 0]
+    assert np.array_equal(got["Q"], Q.ravel())
+    assert np.array_equal(got["D_last"], [3, 6]) and np.array_equal(got["D_mean"], [2, 5]) and np.array_equal(got["g2"], [1, 2])
+    assert got["norm"] == np.sqrt(18.0) and got["dot"] == 4.0 and got["abs"][0] == 0.75
