@@ -123,6 +123,7 @@ struct NbQpArgs
   double* obj;
   int* status;
   int* iters;
+  int* err;             // device error latch (5 = n_int out of range in a device-resident batch)
 };
 
 #define NB_QP_SMEM_LINES 160
@@ -151,6 +152,16 @@ __global__ void __launch_bounds__(NT) k_qp(NbConsts cs, const NbQpTable* tables,
   Group<NT> g(threadIdx.x, sm->red);
   const int n = a.n_int[b];
   const double* ci = a.coeff_init + (size_t)b * 96;
+  if (n < 1 || n > NB_NPOL)
+  {  // device-resident batch with a corrupt n_int: nothing is indexed with it; reported by nb_check_async_errors
+    for (int q = threadIdx.x; q < 96; q += NT) a.coeff_out[(size_t)b * 96 + q] = ci[q];
+    if (threadIdx.x == 0)
+    {
+      *a.err = 5;
+      a.obj[b] = 0.0, a.status[b] = NB_STATUS_FAILED, a.iters[2 * b] = 0, a.iters[2 * b + 1] = 0;
+    }
+    return;
+  }
   const uint8_t* keep = a.keep + (size_t)b * NB_NPOL * a.LS;
   const int nkeep = nb_count_lines<NT>(g, n, a.LS, keep);
   const bool in_smem = nkeep <= NB_QP_SMEM_LINES;
@@ -490,22 +501,32 @@ extern "C" int nb_create(const nb_params* par, const double* pb, int device, nb_
         delete h;
         return NB_ERR_ARG;
       }
-  NB_CUDA(cudaMalloc(&h->d_tables, sizeof(NbQpTable) * tabs.size()));
-  NB_CUDA(cudaMemcpy(h->d_tables, tabs.data(), sizeof(NbQpTable) * tabs.size(), cudaMemcpyHostToDevice));
-  NB_CUDA(cudaMalloc(&h->d_pb, sizeof(double) * 2 * par->num_agents));
-  NB_CUDA(cudaMemcpy(h->d_pb, pb, sizeof(double) * 2 * par->num_agents, cudaMemcpyHostToDevice));
+  h->d_tables = nullptr;
+  h->d_pb = nullptr;
   h->d_st_ptr = nullptr;
   h->d_st_xy = nullptr;
   h->d_strep = nullptr;
   h->st_nvert = 0;
-  NB_CUDA(cudaMalloc(&h->d_st_ptr, sizeof(int64_t) * (par->num_static + 1)));
-  NB_CUDA(cudaMemset(h->d_st_ptr, 0, sizeof(int64_t) * (par->num_static + 1)));
-  if (h->err.ensure(sizeof(int)))
-  {
-    g_err = "cudaMalloc failed";
-    return NB_ERR_CUDA;
+  const int rc = [&]() -> int {
+    NB_CUDA(cudaMalloc(&h->d_tables, sizeof(NbQpTable) * tabs.size()));
+    NB_CUDA(cudaMemcpy(h->d_tables, tabs.data(), sizeof(NbQpTable) * tabs.size(), cudaMemcpyHostToDevice));
+    NB_CUDA(cudaMalloc(&h->d_pb, sizeof(double) * 2 * par->num_agents));
+    NB_CUDA(cudaMemcpy(h->d_pb, pb, sizeof(double) * 2 * par->num_agents, cudaMemcpyHostToDevice));
+    NB_CUDA(cudaMalloc(&h->d_st_ptr, sizeof(int64_t) * (par->num_static + 1)));
+    NB_CUDA(cudaMemset(h->d_st_ptr, 0, sizeof(int64_t) * (par->num_static + 1)));
+    if (h->err.ensure(sizeof(int)))
+    {
+      g_err = "cudaMalloc failed";
+      return NB_ERR_CUDA;
+    }
+    NB_CUDA(cudaMemset(h->err.p, 0, sizeof(int)));
+    return NB_OK;
+  }();
+  if (rc != NB_OK)
+  {  // nothing leaks on a failed construction
+    nb_destroy(h);
+    return rc;
   }
-  NB_CUDA(cudaMemset(h->err.p, 0, sizeof(int)));
   *out = h;
   return NB_OK;
 }
@@ -568,6 +589,11 @@ extern "C" int nb_check_async_errors(nb_handle* h, void* stream)
   NB_CUDA(cudaMemcpyAsync(&err, h->err.p, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   NB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   NB_CUDA(cudaMemsetAsync(h->err.p, 0, sizeof(int), (cudaStream_t)stream));
+  if (err == 5)
+  {
+    g_err = "nb_replan_batch: n_int out of range (1..8) in a device-resident batch";
+    return NB_ERR_ARG;
+  }
   if (err)
   {
     g_err = "a fixed-capacity list overflowed in an asynchronous call (ent_slots, ent_cap or a 16-piece record)";
@@ -651,6 +677,27 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   const int B = a->B, N = h->par.num_agents, M = h->par.num_static, NA = N + M, cap = h->par.ent_cap;
   const int NH = a->n_hull_slots, LS = nb_line_slots(h, NH);
   const int sp = a->space;
+  if (!a->agent_id || !a->n_int || !a->coeff_init || !a->coeff_out || !a->obj || !a->status || !a->iters)
+  {
+    g_err = "nb_replan_batch: null argument";
+    return NB_ERR_ARG;
+  }
+  if (sp == NB_HOST)
+  {  // host arrays are checked before anything is launched; device arrays are checked by k_lines / k_qp (h->err)
+    for (int b = 0; b < B; b++)
+    {
+      if (a->n_int[b] < 1 || a->n_int[b] > h->par.num_pol)
+      {
+        g_err = "nb_replan_batch: n_int out of range (1..num_pol)";
+        return NB_ERR_ARG;
+      }
+      if (a->agent_id[b] < 1 || a->agent_id[b] > N)
+      {
+        g_err = "nb_replan_batch: agent_id out of range (1..num_agents)";
+        return NB_ERR_ARG;
+      }
+    }
+  }
   int rc;
   NbLinesIn in;
   in.NH = NH;
@@ -706,6 +753,7 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   q.cl = (double*)h->cl.p;
   q.rows = (double*)h->rows.p;
   q.RS = RS;
+  q.err = (int*)h->err.p;
   if ((rc = stage_out(h, 0, sp, a->coeff_out, (size_t)B * 96, &q.coeff_out))) return rc;
   if ((rc = stage_out(h, 1, sp, a->obj, (size_t)B, &q.obj))) return rc;
   if ((rc = stage_out(h, 2, sp, a->status, (size_t)B, &q.status))) return rc;

@@ -199,6 +199,82 @@ def test_ent_slot_overflow_is_loud(capi):
     s.close()
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_non_entangling_lines_match_oracle(capi, oracle, variant):
+    """addEntangleConstraintForIJCase (solver_gurobi_poly.cpp:620-642, :715-784) on the GPU: the crafted state of
+    tests/crafted.py fires >= 10 tether LPs (ray beyond the agent, bend-point segments, the k == case_id skip, the
+    distance gate, case id 0); flags bit-exact, lines <= 1e-9, coefficients <= 1e-6 against the oracle, whose LP
+    set is itself checked against an independent reading of the reference's loops and against HiGHS
+    (tests/test_crafted_branches.py)."""
+    from tests import crafted
+    par, b = crafted.ent_lp_batch(variant)
+    s = capi.Solver(par)
+    res = s.replan(b)
+    ref = ReplanResult.empty(b)
+    assert oracle.replan_batch(b, ref, 1) == 0
+    e0 = b.n_hull_slots + par.num_of_agents + par.num_of_static_obst
+    assert (ref.line_ok[:, :, e0:] == 1).sum() >= 8 and (ref.line_ok[:, :, e0:] == 2).sum() >= 1
+    assert np.array_equal(res.line_ok, ref.line_ok) and np.array_equal(res.status, ref.status)
+    m = ref.line_ok == 1
+    assert np.abs(res.lines[m] - ref.lines[m]).max() <= 1e-9 * max(1.0, np.abs(ref.lines[m]).max())
+    assert np.abs(res.coeff_out - ref.coeff_out).max() <= 1e-6 * max(1.0, np.abs(ref.coeff_out).max())
+    assert np.abs(res.obj - ref.obj).max() <= 1e-8 * max(1.0, np.abs(ref.obj).max())
+    _check_solution_properties(par, b, res)
+    s.close()
+
+
+@pytest.mark.parametrize("kind", ["box", "vel", "n2box"])
+def test_both_solves_infeasible_is_status_2(capi, oracle, kind):
+    """optimize()'s failure path (solver_gurobi_poly.cpp:856-859): start state outside the box / above v_max (and the
+    n == 2 single-point case) => status 2 on GPU == oracle, coeff_out == coeff_init bit for bit, objective 0.
+    HiGHS calls the same models infeasible in tests/test_crafted_branches.py."""
+    from tests import crafted
+    par, b = crafted.infeasible_batch(kind)
+    s = capi.Solver(par)
+    res = s.replan(b)
+    ref = ReplanResult.empty(b)
+    assert oracle.replan_batch(b, ref, 1) == 0
+    assert (ref.status == 2).all() and np.array_equal(res.status, ref.status)
+    assert np.array_equal(res.line_ok, ref.line_ok)
+    assert np.array_equal(res.coeff_out, b.coeff_init) and (res.obj == 0).all()
+    s.close()
+
+
+def test_golden_fixtures_through_the_abi(capi):
+    """Every committed fixture (tests/golden/*.npz, crafted branches included) through nb_replan_batch against the
+    outputs recorded from the oracle -- no oracle call at run time."""
+    from tests.golden_util import golden_files, load
+    files = golden_files()
+    assert len(files) >= 10
+    for path in files:
+        par, b, z = load(path)
+        s = capi.Solver(par)
+        if par.num_of_static_obst:
+            s.set_static(b.st_ptr, b.st_xy, z["strep"])
+        res = s.replan(b)
+        assert np.array_equal(res.line_ok, z["orc_line_ok"]), path
+        m = z["orc_line_ok"] == 1
+        assert np.abs(res.lines[m] - z["orc_lines"][m]).max(initial=0) <= 1e-9 * max(1.0, np.abs(z["orc_lines"][m]).max(initial=0))
+        assert np.array_equal(res.status, z["orc_status"]), path
+        assert np.abs(res.coeff_out - z["orc_coeff"]).max() <= 1e-6 * max(1.0, np.abs(z["orc_coeff"]).max())
+        assert np.abs(res.obj - z["orc_obj"]).max() <= 1e-8 * max(1.0, np.abs(z["orc_obj"]).max())
+        s.close()
+
+
+def test_invalid_n_int_and_agent_id_are_rejected(capi):
+    """nb_replan_batch validates n_int (1..num_pol) and agent_id (1..N) for host arguments."""
+    par = config("mtlp5")
+    sc = make_scene(par, 2002, sync=False)
+    s = capi.Solver(par)
+    for field, bad in (("n_int", 0), ("n_int", 9), ("agent_id", 0), ("agent_id", par.num_of_agents + 1)):
+        arr = getattr(sc.batch, field).copy()
+        arr[1] = bad
+        with pytest.raises(capi.NbError, match=field):
+            s.replan(dataclasses.replace(sc.batch, **{field: arr}))
+    s.replan(sc.batch)   # the handle stays usable
+    s.close()
+
+
 def test_separate_degenerate_sets(capi, oracle):
     par = config("mtlp5")
     s = capi.Solver(par)
