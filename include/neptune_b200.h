@@ -380,6 +380,12 @@ int nb_search_batch(nb_handle* h, const nb_search_args* args, void* stream);
  * entanglement chain, key + lookup, step geometry, crossing tests, list automaton. */
 int nb_search_phase_cycles(nb_handle* h, long long* out, int B);
 
+/* Measurement hook (no reference counterpart): with nb_set_profiling on, SM cycles lane 0 of every QP warp spent per
+ * phase in the last nb_replan_batch, out [B][16]: [0] set-up, [1] residual sweep, [2] dual residual + stopping test,
+ * [3] normal-matrix assembly, [4] factorisation, [5] predictor solve, [6] predictor sweep, [7] corrector solve,
+ * [8] final sweep. */
+int nb_qp_phase_cycles(nb_handle* h, long long* out, int B);
+
 #ifdef __cplusplus
 }
 #endif

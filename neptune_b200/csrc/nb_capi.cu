@@ -71,14 +71,15 @@ struct nb_handle
   // staging of NB_HOST arguments
   DevBuf in[16], out[8];
   // scratch
-  DevBuf lines, line_ok, keep, cl, rows, err, ent_scratch;
+  DevBuf lines, line_ok, keep, cl, ncl, rows, err, ent_scratch;
   // front-end search: configuration, staging and workspace
   nb_search_params sp;
   int sp_set = 0;
   int search_smem_set = 0;
   int sprof_B = 0;
   double* d_st_longest = nullptr;
-  DevBuf sprof;
+  DevBuf sprof, qprof;
+  int qprof_B = 0;
   DevBuf sin[20], sout[12], sw_meta, sw_kin, sw_alpha, sw_beta, sw_bend, sw_hash, sw_heap, sw_gh, sw_ng, sw_chi, sw_chd, sw_fcode;
   int qp_smem_set = 0;
   int num_sms = 148;
@@ -89,7 +90,7 @@ struct nb_handle
 // ------------------------------------------------------------------------------------------ kernels
 
 __global__ void __launch_bounds__(128) k_lines(NbConsts cs, NbLinesIn in, int LS, double* lines, uint8_t* ok,
-                                               uint8_t* keep, int* err)
+                                               uint8_t* keep, int* err, double* cl, int* ncl)
 {
   extern __shared__ double smem_d[];
   NbPruneShared ps;
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(128) k_lines(NbConsts cs, NbLinesIn in, int LS
   ps.valid = (uint8_t*)(ps.misc + 8);
   const int b = blockIdx.x / NB_NPOL, i = blockIdx.x % NB_NPOL;
   nb_lines_task<128>(threadIdx.x, b, i, cs, in, lines + (size_t)blockIdx.x * LS * 3, ok + (size_t)blockIdx.x * LS,
-                     keep + (size_t)blockIdx.x * LS, ps, err);
+                     keep + (size_t)blockIdx.x * LS, ps, err, cl + (size_t)blockIdx.x * LS * 3, ncl + blockIdx.x);
 }
 
 static size_t lines_smem_bytes(int LS)
@@ -113,92 +114,148 @@ struct NbQpArgs
 {
   const int* n_int;
   const double* coeff_init;
-  const double* lines;  // [B][8][LS][3]
-  const uint8_t* keep;  // [B][8][LS]
+  const double* cl;     // [B][8][LS][3] kept lines of every (agent, interval), compact (k_lines)
+  const int* ncl;       // [B][8] their number
   int LS;
-  double* cl;           // [B][8*LS][3]   (only used when an agent keeps more than NB_QP_SMEM_LINES lines)
-  double* rows;         // [B][5][RS]     (same)
+  double* rows;         // [B][5][RS]     (only used when an agent keeps more than NB_QP_SMEM_LINES lines)
   int RS;
   double* coeff_out;
   double* obj;
   int* status;
   int* iters;
   int* err;             // device error latch (5 = n_int out of range in a device-resident batch)
+  long long* prof;      // optional [B][16] phase cycles (nb_set_profiling)
 };
 
-#define NB_QP_SMEM_LINES 160
-#define NB_QP_THREADS 128        // one CTA of four warps per agent when the batch fills the GPU
-#define NB_QP_THREADS_WIDE 256   // eight warps per agent when it does not (B <= number of SMs): wider row sweeps
-#define NB_QP_SMEM_ROWS (6 * NB_NFEAT_AX + 4 * NB_QP_SMEM_LINES)
+#define NB_QP_SMEM_LINES 160     // kept lines whose rows live in shared memory; more: rows in global scratch
+#define NB_QP_SMEM_ROWS (NB_ROW_LINE0 + 4 * NB_QP_SMEM_LINES)
 
+#define NB_QP_THREADS 128
 struct NbQpSmem
 {
+  NbQpTable tb;  // first: destination of the bulk copy (16-byte aligned)
   NbQpShared sh;
-  NbQpTable tb;
+  double red[8 * NB_QP_THREADS / 32];
   double rows[5 * NB_QP_SMEM_ROWS];
   double cl[3 * NB_QP_SMEM_LINES];
   double xout[96];
-  double red[8 * NB_QP_THREADS_WIDE / 32];
+  unsigned long long mbar;
+  const double* clb[NB_NPOL];
   int lstart[12];
-  int nl;
+  unsigned char l2i[NB_QP_SMEM_LINES];
 };
 
-template <int NT>
-__global__ void __launch_bounds__(NT) k_qp(NbConsts cs, const NbQpTable* tables, NbQpArgs a)
+// ---- bulk asynchronous copy global -> shared (TMA unit, no tensor map: cp.async.bulk) completing on an mbarrier
+NB_DEV unsigned nb_smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+NB_DEV void nb_mbar_init(unsigned long long* bar, int count)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(nb_smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+NB_DEV void nb_bulk_load(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(nb_smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   nb_smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(nb_smem_addr(bar))
+               : "memory");
+}
+NB_DEV void nb_mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "NB_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra NB_DONE_%=;\n"
+      "bra NB_WAIT_%=;\n"
+      "NB_DONE_%=:\n"
+      "}\n" ::"r"(nb_smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// K4: one CTA of four warps per agent.  The (n, mode) table (32 KB) is staged by one bulk copy that overlaps the
+// gathering of the agent's lines (nb_qp.cuh has the solver).
+__global__ void __launch_bounds__(NB_QP_THREADS) k_qp(NbConsts cs, const NbQpTable* tables, NbQpArgs a)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   NbQpSmem* sm = reinterpret_cast<NbQpSmem*>(smem_raw);
-  const int b = blockIdx.x;
-  Group<NT> g(threadIdx.x, sm->red);
+  const int b = blockIdx.x, lane = threadIdx.x;
+  Group<NB_QP_THREADS> g(lane, sm->red);
   const int n = a.n_int[b];
   const double* ci = a.coeff_init + (size_t)b * 96;
   if (n < 1 || n > NB_NPOL)
   {  // device-resident batch with a corrupt n_int: nothing is indexed with it; reported by nb_check_async_errors
-    for (int q = threadIdx.x; q < 96; q += NT) a.coeff_out[(size_t)b * 96 + q] = ci[q];
-    if (threadIdx.x == 0)
+    for (int q = lane; q < 96; q += NB_QP_THREADS) a.coeff_out[(size_t)b * 96 + q] = ci[q];
+    if (lane == 0)
     {
       *a.err = 5;
       a.obj[b] = 0.0, a.status[b] = NB_STATUS_FAILED, a.iters[2 * b] = 0, a.iters[2 * b + 1] = 0;
     }
     return;
   }
-  const uint8_t* keep = a.keep + (size_t)b * NB_NPOL * a.LS;
-  const int nkeep = nb_count_lines<NT>(g, n, a.LS, keep);
-  const bool in_smem = nkeep <= NB_QP_SMEM_LINES;
-  double* cl = in_smem ? sm->cl : a.cl + (size_t)b * NB_NPOL * a.LS * 3;
-  if (threadIdx.x < 32)
-  {  // ordered compaction of the kept lines by warp 0 (ballot prefix)
-    Group<32> gw(threadIdx.x);
-    const int nl0 = nb_compact_lines<32>(gw, n, a.LS, a.lines + (size_t)b * NB_NPOL * a.LS * 3, keep, cl, sm->lstart);
-    if (threadIdx.x == 0) sm->nl = nl0;
+  if (lane == 0)
+  {
+    nb_mbar_init(&sm->mbar, 1);
+    nb_bulk_load(&sm->tb, tables + (n - 1), (unsigned)sizeof(NbQpTable), &sm->mbar);
   }
+  // line runs of the intervals: exclusive prefix of the counts (lanes 0..7 hold one interval each)
+  int cnt = (lane < n) ? a.ncl[(size_t)b * NB_NPOL + lane] : 0;
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1)
+  {
+    const int up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane <= NB_NPOL) sm->lstart[lane] = 0;
   __syncthreads();
-  const int nl = sm->nl;
+  if (lane < n) sm->lstart[lane + 1] = incl;
+  __syncthreads();
+  const int nl = sm->lstart[n];
+  const bool in_smem = nl <= NB_QP_SMEM_LINES;
   NbQpRows R;
   const size_t rs = in_smem ? NB_QP_SMEM_ROWS : a.RS;
   double* rb = in_smem ? sm->rows : a.rows + (size_t)b * 5 * a.RS;
-  R.s = rb;
-  R.lam = rb + rs;
-  R.dsa = rb + 2 * rs;
-  R.dla = rb + 3 * rs;
-  R.inv = rb + 4 * rs;
-  R.cl = cl;
+  R.s = rb, R.lam = rb + rs, R.dsa = rb + 2 * rs, R.dla = rb + 3 * rs, R.inv = rb + 4 * rs;
   R.lstart = sm->lstart;
+  for (int i = 0; i < NB_NPOL; i++)
+  {
+    const double* src = a.cl + ((size_t)b * NB_NPOL + i) * a.LS * 3;
+    const int l0 = i < n ? sm->lstart[i] : 0, l1 = i < n ? sm->lstart[i + 1] : 0;
+    if (in_smem)
+    {
+      for (int q = lane; q < 3 * (l1 - l0); q += NB_QP_THREADS) sm->cl[3 * l0 + q] = src[q];
+      for (int q = lane; q < l1 - l0; q += NB_QP_THREADS) sm->l2i[l0 + q] = (unsigned char)i;
+      if (lane == 0) sm->clb[i] = sm->cl;
+    }
+    else if (lane == 0)
+      sm->clb[i] = src - 3 * (ptrdiff_t)l0;
+  }
+  R.clb = sm->clb;
+  R.l2i = in_smem ? sm->l2i : nullptr;
+  __syncthreads();
   int status = NB_STATUS_FAILED, it0 = 0, it1 = 0;
   double obj = 0.0;
   bool ok = false;
   for (int mode = 0; mode < 2 && !ok; mode++)
   {
-    // stage the (n, mode) table in shared memory
-    const double* src = reinterpret_cast<const double*>(tables + mode * NB_NPOL + (n - 1));
-    double* dst = reinterpret_cast<double*>(&sm->tb);
-    g.sync();
-    for (int q = threadIdx.x; q < (int)(sizeof(NbQpTable) / sizeof(double)); q += NT) dst[q] = src[q];
-    g.sync();
-    ok = nb_qp_solve<NT>(g, cs, &sm->tb, &sm->sh, R, ci, nl, sm->xout, mode == 0 ? &it0 : &it1, &obj);
+    if (mode == 1)
+    {  // fallback table: the first one is not read any more; order those reads before the asynchronous overwrite
+      __syncthreads();
+      if (lane == 0)
+      {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        nb_bulk_load(&sm->tb, tables + NB_NPOL + (n - 1), (unsigned)sizeof(NbQpTable), &sm->mbar);
+      }
+    }
+    nb_mbar_wait(&sm->mbar, (unsigned)mode);
+    ok = nb_qp_solve<NB_QP_THREADS>(g, cs, &sm->tb, &sm->sh, R, ci, nl, sm->xout, mode == 0 ? &it0 : &it1, &obj,
+                         a.prof ? a.prof + (size_t)b * 16 : nullptr);
     if (ok) status = mode == 0 ? NB_STATUS_OK : NB_STATUS_FALLBACK;
   }
-  g.sync();
+  __syncthreads();
   // copy the solution (:866-876) or keep the initial path (:858); z override (:879-880)
   const double T = cs.T;
   double pfx = 0, pfy = 0;
@@ -213,14 +270,14 @@ __global__ void __launch_bounds__(NT) k_qp(NbConsts cs, const NbQpTable* tables,
   const double dx = ci[3] - pfx, dy = ci[32 + 3] - pfy;
   const bool keep_z = sqrt(dx * dx + dy * dy) < 1.0;
   double* co = a.coeff_out + (size_t)b * 96;
-  for (int q = threadIdx.x; q < 96; q += NT)
+  for (int q = lane; q < 96; q += NB_QP_THREADS)
   {
     const int ax = q / 32, r = q % 32;
     double v = ci[q];
     if (ok && r < 4 * n && !(ax == 2 && keep_z)) v = sm->xout[q];
     co[q] = v;
   }
-  if (threadIdx.x == 0)
+  if (lane == 0)
   {
     a.obj[b] = ok ? obj : 0.0;
     a.status[b] = status;
@@ -544,12 +601,12 @@ extern "C" void nb_destroy(nb_handle* h)
   for (auto& b : h->out) b.release();
   for (auto& e : h->ev)
     if (e) cudaEventDestroy(e);
-  h->lines.release(), h->line_ok.release(), h->keep.release(), h->cl.release(), h->rows.release(), h->err.release(), h->ent_scratch.release();
+  h->lines.release(), h->line_ok.release(), h->keep.release(), h->cl.release(), h->ncl.release(), h->rows.release(), h->err.release(), h->ent_scratch.release();
   cudaFree(h->d_st_longest);
   for (auto& b : h->sin) b.release();
   for (auto& b : h->sout) b.release();
   h->sw_meta.release(), h->sw_kin.release(), h->sw_alpha.release(), h->sw_beta.release(), h->sw_bend.release();
-  h->sprof.release();
+  h->sprof.release(), h->qprof.release();
   h->sw_ng.release(), h->sw_fcode.release();
   h->sw_hash.release(), h->sw_heap.release(), h->sw_gh.release(), h->sw_chi.release(), h->sw_chd.release();
   delete h;
@@ -735,9 +792,9 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   }
   // scratch
   const size_t nslots = (size_t)B * NB_NPOL * LS;
-  const int RS = 6 * NB_NFEAT_AX + 4 * NB_NPOL * LS;
+  const int RS = NB_ROW_LINE0 + 4 * NB_NPOL * LS;
   if (h->lines.ensure(nslots * 3 * sizeof(double)) || h->line_ok.ensure(nslots) ||
-      h->cl.ensure(nslots * 3 * sizeof(double)) || h->keep.ensure(nslots) ||
+      h->cl.ensure(nslots * 3 * sizeof(double)) || h->keep.ensure(nslots) || h->ncl.ensure((size_t)B * NB_NPOL * sizeof(int)) ||
       h->rows.ensure((size_t)B * 5 * RS * sizeof(double)) || h->err.ensure(sizeof(int)))
   {
     g_err = "cudaMalloc failed for scratch buffers";
@@ -747,13 +804,24 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   NbQpArgs q;
   q.n_int = in.n_int;
   q.coeff_init = in.coeff_init;
-  q.lines = (const double*)h->lines.p;
-  q.keep = (const uint8_t*)h->keep.p;
+  q.cl = (const double*)h->cl.p;
+  q.ncl = (const int*)h->ncl.p;
   q.LS = LS;
-  q.cl = (double*)h->cl.p;
   q.rows = (double*)h->rows.p;
   q.RS = RS;
   q.err = (int*)h->err.p;
+  q.prof = nullptr;
+  if (h->profiling)
+  {
+    if (h->qprof.ensure((size_t)B * 16 * sizeof(long long)))
+    {
+      g_err = "cudaMalloc failed";
+      return NB_ERR_CUDA;
+    }
+    NB_CUDA(cudaMemsetAsync(h->qprof.p, 0, (size_t)B * 16 * sizeof(long long), st));
+    q.prof = (long long*)h->qprof.p;
+    h->qprof_B = B;
+  }
   if ((rc = stage_out(h, 0, sp, a->coeff_out, (size_t)B * 96, &q.coeff_out))) return rc;
   if ((rc = stage_out(h, 1, sp, a->obj, (size_t)B, &q.obj))) return rc;
   if ((rc = stage_out(h, 2, sp, a->status, (size_t)B, &q.status))) return rc;
@@ -763,8 +831,7 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   const size_t lsm = lines_smem_bytes(LS);
   if (!h->qp_smem_set)
   {
-    NB_CUDA(cudaFuncSetAttribute(k_qp<NB_QP_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NbQpSmem)));
-    NB_CUDA(cudaFuncSetAttribute(k_qp<NB_QP_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NbQpSmem)));
+    NB_CUDA(cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NbQpSmem)));
     NB_CUDA(cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     h->qp_smem_set = 1;
   }
@@ -774,14 +841,9 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
     return NB_ERR_CAPACITY;
   }
   k_lines<<<B * NB_NPOL, 128, lsm, st>>>(h->cs, in, LS, (double*)h->lines.p, (uint8_t*)h->line_ok.p,
-                                         (uint8_t*)h->keep.p, (int*)h->err.p);
+                                         (uint8_t*)h->keep.p, (int*)h->err.p, (double*)h->cl.p, (int*)h->ncl.p);
   if (h->profiling) cudaEventRecord(h->ev[1], st);
-  // a batch that leaves SMs idle gets eight warps per agent (wider row sweeps, 0.29 -> 0.27 ms at 64 agents); a batch
-  // that fills the GPU gets four (more agents in flight: 1.6 ms against 2.2 ms at 1024 agents)
-  if (B <= h->num_sms)
-    k_qp<NB_QP_THREADS_WIDE><<<B, NB_QP_THREADS_WIDE, sizeof(NbQpSmem), st>>>(h->cs, h->d_tables, q);
-  else
-    k_qp<NB_QP_THREADS><<<B, NB_QP_THREADS, sizeof(NbQpSmem), st>>>(h->cs, h->d_tables, q);
+  k_qp<<<B, NB_QP_THREADS, sizeof(NbQpSmem), st>>>(h->cs, h->d_tables, q);
   if (h->profiling) cudaEventRecord(h->ev[2], st);
   h->launches += 2;
   NB_CUDA(cudaGetLastError());
@@ -1568,5 +1630,17 @@ extern "C" int nb_search_phase_cycles(nb_handle* h, long long* out, int B)
   NB_CUDA(cudaSetDevice(h->device));
   NB_CUDA(cudaDeviceSynchronize());
   NB_CUDA(cudaMemcpy(out, h->sprof.p, (size_t)B * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return NB_OK;
+}
+
+// Measurement hook: SM cycles lane 0 of every QP warp spent per phase in the last profiled nb_replan_batch, out [B][16]:
+// [0] set-up, [1] residual sweep, [2] dual residual + stopping test, [3] normal-matrix assembly, [4] factorisation,
+// [5] predictor solve, [6] predictor sweep, [7] corrector solve, [8] final sweep.
+extern "C" int nb_qp_phase_cycles(nb_handle* h, long long* out, int B)
+{
+  if (!h || !out || !h->qprof.p || B > h->qprof_B) return NB_ERR_ARG;
+  NB_CUDA(cudaSetDevice(h->device));
+  NB_CUDA(cudaDeviceSynchronize());
+  NB_CUDA(cudaMemcpy(out, h->qprof.p, (size_t)B * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return NB_OK;
 }

@@ -107,6 +107,48 @@ struct Group
       __syncthreads();
     }
   }
+  // (sum, max) and (max, sum, sum) at once: as many shuffles as values, one shared-memory exchange
+  NB_DEV void reduce_sum_max(double& s0, double& mx) const
+  {
+    constexpr int W = NL < 32 ? NL : 32;
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1)
+    {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (NL > 32)
+    {
+      const int w = lane >> 5;
+      if ((lane & 31) == 0) red[2 * w] = s0, red[2 * w + 1] = mx;
+      __syncthreads();
+      s0 = red[0], mx = red[1];
+#pragma unroll
+      for (int q = 1; q < NL / 32; q++) s0 += red[2 * q], mx = fmax(mx, red[2 * q + 1]);
+      __syncthreads();
+    }
+  }
+  NB_DEV void reduce_max_sum_sum(double& mx, double& s0, double& s1) const
+  {
+    constexpr int W = NL < 32 ? NL : 32;
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1)
+    {
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (NL > 32)
+    {
+      const int w = lane >> 5;
+      if ((lane & 31) == 0) red[3 * w] = mx, red[3 * w + 1] = s0, red[3 * w + 2] = s1;
+      __syncthreads();
+      mx = red[0], s0 = red[1], s1 = red[2];
+#pragma unroll
+      for (int q = 1; q < NL / 32; q++) mx = fmax(mx, red[3 * q]), s0 += red[3 * q + 1], s1 += red[3 * q + 2];
+      __syncthreads();
+    }
+  }
   // sum over the SUB adjacent lanes that share an item
   NB_DEV double sub_sum(double v) const
   {
@@ -121,6 +163,8 @@ struct Group
   double max(double v) const { return v; }
   double min(double v) const { return v; }
   void reduce5(double&, double&, double&, double&, double&) const {}
+  void reduce_sum_max(double&, double&) const {}
+  void reduce_max_sum_sum(double&, double&, double&) const {}
   double sub_sum(double v) const { return v; }
   int any(int p) const { return p; }
 #endif
@@ -131,19 +175,24 @@ struct Group
 // solver_gurobi_poly.cpp:660-678), mode 1: dropped and penalised (fallback, :838-847).
 // Per axis the equalities E1-E3 leave x_ax = Pm * init3 + Z * w with
 // dof = n-2 (mode 0) or n (mode 1) free parameters; Z has orthonormal columns.
+#define NB_NPAIR (NB_DOF_MAX * (NB_DOF_MAX + 1) / 2)  // lower-triangle pairs (ca >= cb) of one axis block
 struct NbQpTable
 {
   int n, mode, dof, has_resid;
   double Z[4 * NB_NPOL][NB_DOF_MAX];       // [interval*4 + coeff][dof]
   double Pm[4 * NB_NPOL][3];               // particular solution map on (b0, c0, d0)
   double C[NB_NFEAT_AX][NB_DOF_MAX];       // feature rows: [interval*8 + j], j: 0-3 pos CP, 4-6 vel CP, 7 acc
+  double Ct[NB_DOF_MAX][NB_NFEAT_AX];      // the same, transposed (lanes over features read it conflict-free)
   double c0[NB_NFEAT_AX][3];
   double Hr[NB_DOF_MAX][NB_DOF_MAX];       // reduced objective Hessian (per axis)
   double Gr[NB_DOF_MAX][3];                // reduced gradient at w = 0: Gr * init3 + gpf * pf
   double gpf[NB_DOF_MAX];
   double tq[NB_DOF_MAX], tq0[3];           // terminal position error: tq.w + tq0.init3 - pf
+  double pad0;
   double Rres[2][3];                       // n = 1, mode 0: equality consistency residual map
+  double PP[NB_NFEAT_AX][NB_NPAIR];        // C[f][ca] * C[f][cb], pair p = ca (ca + 1) / 2 + cb: normal-matrix assembly
 };
+static_assert(sizeof(NbQpTable) % 16 == 0, "NbQpTable is staged with cp.async.bulk (16-byte granules)");
 
 struct NbConsts
 {

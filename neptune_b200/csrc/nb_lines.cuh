@@ -57,9 +57,50 @@ NB_HD void nb_ctrl_pts(const NbConsts& cs, const double* ci /*[3][8][4] of agent
 
 // Threads tid, tid+NT, ... of the group handle slots; tid 0 additionally walks the (few)
 // non-entangling constraints.  lines: [LS][3], ok: [LS] of this (b, i).  Sets *err on overflow.
+// Ordered compaction of the lines the QP must see: cl_out[q] = (n0, n1, 1 - d) of the q-th slot with flag[s] == 1,
+// *ncl_out = their number.  This is the list K4 reads (one contiguous run per interval, no slot scan there).
+template <int NT>
+NB_HD void nb_emit_kept(const Cta<NT>& cta, int LS, const double* lines, const uint8_t* flag, int* red, double* cl_out,
+                        int* ncl_out)
+{
+  int total = 0;
+  for (int base = 0; base < LS; base += NT)
+  {
+    const int s = base + cta.tid;
+    const int mine = (s < LS) && (flag[s] == 1);
+    int pos = 0, cnt = mine;
+#if defined(__CUDA_ARCH__)
+    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+    const int lane = cta.tid & 31, w = cta.tid >> 5;
+    if (lane == 0) red[w] = __popc(bal);
+    cta.sync();
+    pos = __popc(bal & ((1u << lane) - 1u));
+    cnt = 0;
+    for (int q = 0; q < (NT + 31) / 32; q++)
+    {
+      if (q < w) pos += red[q];
+      cnt += red[q];
+    }
+#endif
+    if (mine)
+    {
+      const double* l = lines + (size_t)3 * s;
+      double* o = cl_out + (size_t)3 * (total + pos);
+      o[0] = l[0];
+      o[1] = l[1];
+      o[2] = 1.0 - l[2];
+    }
+    total += cnt;
+    cta.sync();
+  }
+  if (cta.tid == 0) *ncl_out = total;
+}
+
+// prune == false keeps every solved line (test hook of the host emulation: pruned == unpruned optimum)
 template <int NT>
 NB_HD void nb_lines_task(int tid, int b, int i, const NbConsts& cs, const NbLinesIn& in, double* lines,
-                         uint8_t* ok, uint8_t* keep, const NbPruneShared& ps, int* err)
+                         uint8_t* ok, uint8_t* keep, const NbPruneShared& ps, int* err, double* cl_out, int* ncl_out,
+                         bool prune = true)
 {
   const int N = cs.N, M = cs.M, NH = in.NH;
   const int LS = NH + N + M + cs.ent_slots;
@@ -71,6 +112,7 @@ NB_HD void nb_lines_task(int tid, int b, int i, const NbConsts& cs, const NbLine
       ok[s] = 0;
       keep[s] = 0;
     }
+    if (tid == 0) *ncl_out = 0;
     return;
   }
   double cp[8];
@@ -214,51 +256,6 @@ NB_HD void nb_lines_task(int tid, int b, int i, const NbConsts& cs, const NbLine
   Cta<NT> cta(tid);
   cta.sync();
   nb_prune_lines<NT>(cta, LS, lines, ok, cp, ps, keep);
-}
-
-// Gather the solved lines of one agent, interval by interval, into the compact list the QP reads:
-// cl[l] = (n0, n1, 1 - d).  Group-cooperative; returns the total number of lines.
-template <int NL>
-NB_HD int nb_count_lines(const Group<NL>& g, int n, int LS, const uint8_t* keep /*[8][LS]*/)
-{
-  double c = 0.0;
-  for (int q = g.lane; q < n * LS; q += NL) c += (keep[q] == 1) ? 1.0 : 0.0;
-  return (int)(g.sum(c) + 0.5);
-}
-
-template <int NL>
-NB_HD int nb_compact_lines(const Group<NL>& g, int n, int LS, const double* lines /*[8][LS][3]*/,
-                           const uint8_t* ok /*[8][LS] keep flags*/, double* cl, int* lstart)
-{
-  int total = 0;
-  for (int i = 0; i < n; i++)
-  {
-    if (g.lane == 0) lstart[i] = total;
-    for (int base = 0; base < LS; base += NL)
-    {
-      const int s = base + g.lane;
-      const int mine = (s < LS) && (ok[i * LS + s] == 1);
-      int pos, cnt;
-#if defined(__CUDA_ARCH__)
-      const unsigned bal = __ballot_sync(0xffffffffu, mine);
-      pos = __popc(bal & ((1u << g.lane) - 1u));
-      cnt = __popc(bal);
-#else
-      pos = 0;
-      cnt = mine;
-#endif
-      if (mine)
-      {
-        const double* l = lines + ((size_t)i * LS + s) * 3;
-        double* o = cl + 3 * (size_t)(total + pos);
-        o[0] = l[0];
-        o[1] = l[1];
-        o[2] = 1.0 - l[2];
-      }
-      total += cnt;
-    }
-  }
-  if (g.lane == 0) lstart[n] = total;
-  g.sync();
-  return total;
+  cta.sync();
+  nb_emit_kept<NT>(cta, LS, lines, prune ? keep : ok, ps.red, cl_out, ncl_out);
 }

@@ -1,4 +1,4 @@
-// nb_qp.cuh -- K4: batched trajectory QP, one agent per warp-group.
+// nb_qp.cuh -- K4: batched trajectory QP, ONE AGENT PER WARP.
 //
 // Replaces PolySolverGurobi::optimize's two m_.optimize() calls and the model they are run on
 // (reference neptune/src/solver_gurobi_poly.cpp:322-383 addObjective, :385-471 + :659-708
@@ -10,34 +10,59 @@
 // rows :485-489, :546-550, :587-591, :754-758), so the normal matrix is assembled as
 // Hr + C^T W C with W diagonal plus one 2x2 coupling per control point -- no per-row outer products.
 //
-// Lane-strided SPMD phases over shared memory (vectors, K, per-row s / lambda; global scratch only when an
-// agent keeps more lines than fit); compiles with NL = 128 (one CTA per agent) on the device and NL = 1 in
-// the host emulation.
+// Execution model: one CTA of four warps per agent.  The data-parallel phases (row sweeps, feature products, the
+// assembly of the normal matrix) are lane-strided over the 128 threads with at most two rows per thread; the inherently
+// sequential part -- factorisation and triangular solves -- runs on warp 0 alone with the matrix rows in REGISTERS
+// and pivots travelling by shuffle, so it costs no block barrier.  The normal matrix is block diagonal, an (x,y) block
+// of 2 dof <= 16 rows and a z block of dof <= 8 rows (the separating lines couple x with y only); the two blocks
+// are factorised (L D L^T) and solved IN LOCKSTEP by disjoint lanes, which shortens the sequential pivot chain
+// from 3 dof to 2 dof columns.  The quadratic terminal row (:697-702), which couples all three axes through a
+// rank-one term, enters by the Sherman-Morrison formula.  The corrector's right-hand side is obtained from two
+// per-feature sums gathered during the predictor sweep, so an iteration makes three sweeps over the rows
+// (residual, predictor direction, final direction).
+//
+// Lane-strided SPMD phases; compiles with NL = 128 (one CTA) on the device and NL = 1 in the host emulation.
 #pragma once
 #include "nb_common.cuh"
 
+#define NB_KLD 25                      // row stride of the normal matrix in shared memory (odd: conflict-free rows)
+#define NB_NF3 (3 * NB_NFEAT_AX)       // features of the three axes
+#define NB_ROW_LINE0 (2 * NB_NF3)      // first separating-line row: upper bound rows [0, 192), lower [192, 384)
+#define NB_NELEM (2 * NB_DOF_MAX * (2 * NB_DOF_MAX - 1) / 2 + NB_DOF_MAX * (NB_DOF_MAX - 1) / 2)  // 120 + 28
+
 struct NbQpShared
 {
-  double y[3 * NB_NFEAT_AX];   // feature values
-  double dy[3 * NB_NFEAT_AX];  // feature values of a direction
-  double om[3 * NB_NFEAT_AX];  // diagonal weights  sum lambda/s
-  double La[3 * NB_NFEAT_AX];  // per-feature load of a row vector (G^T v reduced to features)
-  double Sxy[4 * NB_NPOL];     // x-y coupling weight of control point (i,k)
-  double K[NB_NV_MAX * NB_NV_MAX];
-  double w[NB_NV_MAX], dw[NB_NV_MAX], rd[NB_NV_MAX], rhs[NB_NV_MAX], g0[NB_NV_MAX], gq[NB_NV_MAX];
-  double gobj[NB_NV_MAX], invd[NB_NV_MAX];
-  double init3[3][3], pf[3], e3[3];
+  double y[NB_NF3];    // feature values
+  double dy[NB_NF3];   // feature values of a direction
+  double du[NB_NF3];   // dual load per feature (G^T lambda reduced to features), for r_d
+  double La[NB_NF3];   // primal load per feature of the predictor right-hand side
+  double A1[NB_NF3];   // corrector: sum of ds_aff dl_aff / s per feature
+  double A2[NB_NF3];   // corrector: sum of 1 / s per feature
+  double omv[NB_NFEAT_AX * 4];  // weights per feature [f][0..2] = axis x, y, z; [f][3] = x-y coupling (position CPs)
+  double K[NB_NV_MAX * NB_KLD];
+  double col[NB_NV_MAX], invd[NB_NV_MAX];
+  double w[NB_NV_MAX], dw[NB_NV_MAX], rd[NB_NV_MAX], g0[NB_NV_MAX], gq[NB_NV_MAX], gobj[NB_NV_MAX], uq[NB_NV_MAX];
+  double init3[3][3], pf[3];
   double xin[3][4 * NB_NPOL];
-  double blo[24], bhi[24];                     // bounds of feature kind (axis, j)
+  double blo[24], bhi[24];                          // bounds of feature kind (axis, j)
   unsigned char ax_of[NB_NV_MAX], c_of[NB_NV_MAX];  // variable a -> (axis, column)
-  unsigned char pa[NB_NV_MAX * (NB_NV_MAX + 1) / 2], pb[NB_NV_MAX * (NB_NV_MAX + 1) / 2];  // lower-triangle pairs
-  int npairs;
+  unsigned char pca[NB_NPAIR], pcb[NB_NPAIR];       // pair p -> (ca, cb), ca >= cb
+  unsigned char ei[NB_NELEM], ej[NB_NELEM];         // strictly-lower elements (i > j) of the two diagonal blocks
+  int nelem;
 };
 
+// Reciprocal for the interior-point algebra (pivots, 1 / s): hardware seed (MUFU.RCP64H, ~20 bits) and two Newton
+// steps -- full double precision to within an ulp or two, a third of the instructions of the correctly rounded
+// __drcp_rn and no slow-path branch.  Arguments are never zero, denormal or infinite here.
 NB_HD double nb_rcp(double x)
 {
 #if defined(__CUDA_ARCH__)
-  return __drcp_rn(x);  // correctly rounded reciprocal == 1.0 / x, without the division slow path
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
 #else
   return 1.0 / x;
 #endif
@@ -50,8 +75,10 @@ struct NbQpRows  // per-agent row state (shared memory when it fits, else global
   double* dsa;
   double* dla;
   double* inv;  // 1/s of the current iterate (written by the RESID pass)
-  const double* cl;  // [L][3] compact kept lines: n0, n1, c = 1 - d
-  const int* lstart; // [n+1] first line of each interval
+  const double* const* clb;    // [8] kept lines (n0, n1, c = 1 - d): line l of interval i is clb[i] + 3 l, for
+                               // lstart[i] <= l < lstart[i+1] (one contiguous list, or one run per interval)
+  const int* lstart;           // [n+1] first line of each interval
+  const unsigned char* l2i;    // optional [L]: interval of line l (shared-memory path)
 };
 
 NB_HD void nb_feat_bounds(const NbConsts& cs, int ax, int j, double& lo, double& hi)
@@ -73,31 +100,31 @@ NB_HD void nb_feat_bounds(const NbConsts& cs, int ax, int j, double& lo, double&
   }
 }
 
-// y = c0 . init3 + C w  (with_const) or dy = C dw
+// y = c0 . init3 + C w  (with_const) or dy = C dw.  Lanes over features: C is read transposed.
 template <int NL>
 NB_HD void nb_qp_features(const Group<NL>& g, const NbQpTable* tb, const NbQpShared* sh_c, double* out,
                           const double* vec, bool with_const)
 {
   const int n = tb->n, dof = tb->dof;
-  for (int q = g.lane; q < 3 * NB_NFEAT_AX; q += NL)
+  for (int q = g.lane; q < NB_NF3; q += NL)
   {
     const int ax = q >> 6, fl = q & 63;
     if (fl >= 8 * n) continue;
     double v = 0.0;
     if (with_const)
       v = tb->c0[fl][0] * sh_c->init3[ax][0] + tb->c0[fl][1] * sh_c->init3[ax][1] + tb->c0[fl][2] * sh_c->init3[ax][2];
-    for (int c = 0; c < dof; c++) v += tb->C[fl][c] * vec[ax * dof + c];
-    out[ax * NB_NFEAT_AX + fl] = v;
+#pragma unroll
+    for (int c = 0; c < NB_DOF_MAX; c++)
+      if (c < dof) v += tb->Ct[c][fl] * vec[ax * dof + c];
+    out[q] = v;
   }
 }
 
 enum
 {
   NB_PASS_RESID = 0,  // residuals, weights, predictor load; sums mu, |rp|max
-  NB_PASS_DIR_PRED,   // predictor direction: ds, dl -> scratch; step length, mu_aff sums
-  NB_PASS_LOAD_CORR,  // corrector load with rc = s lam + dsa dla - sigma mu
+  NB_PASS_DIR_PRED,   // predictor direction: ds, dl -> scratch; step length, mu_aff sums; corrector sums A1
   NB_PASS_DIR_CORR,   // final direction: ds, dl -> scratch; step length
-  NB_PASS_UPDATE,     // s += a ds, lam += a dl
   NB_PASS_START       // Nocedal-Wright start: s = max(1,|s+ds|), lam likewise
 };
 
@@ -106,26 +133,29 @@ struct NbPassAcc
   double sum_sl, rp_max, rmax, sum_cross, sum_dd;  // rmax = max over rows of (-ds/s, -dl/lam): alpha_max = 1/rmax
 };
 
-// one inequality row: v = row value (<= 0 wanted), gd = row . direction.  Returns the load tau that
-// this row puts on its feature(s) (for RESID / LOAD_CORR), and the diagonal weight in `wgt`.
+// One inequality row r: v = row value (<= 0 wanted), gd = row . direction.
+//   RESID   : applies the pending step, returns the predictor load tau = (lam rp - s lam) / s, wgt = lam / s, iv = 1 / s
+//   DIR_PRED: returns ds_aff dl_aff / s (the corrector's second-order term)
 template <int MODE>
-NB_HD double nb_row(double* s_, double* lam_, double* dsa_, double* dla_, double* inv_, double v, double gd,
-                    double sigmu, double alpha, NbPassAcc& acc, double& wgt)
+NB_HD double nb_row(const NbQpRows& R, int r, double v, double gd, double sigmu, double alpha, NbPassAcc& acc,
+                    double& wgt, double& iv)
 {
-  double s = *s_, lam = *lam_;
+  double s = R.s[r], lam = R.lam[r];
   wgt = 0.0;
+  iv = 0.0;
   if (MODE == NB_PASS_RESID)
   {
     if (alpha != 0.0)
     {  // pending step of the previous iteration (s, lam) += alpha (ds, dl); v already is at the new point
-      s += alpha * (*dsa_);
-      lam += alpha * (*dla_);
-      *s_ = s;
-      *lam_ = lam;
+      s += alpha * R.dsa[r];
+      lam += alpha * R.dla[r];
+      R.s[r] = s;
+      R.lam[r] = lam;
     }
     const double rp = v + s;
     const double inv = nb_rcp(s);
-    *inv_ = inv;
+    R.inv[r] = inv;
+    iv = inv;
     wgt = lam * inv;
     acc.sum_sl += s * lam;
     acc.rp_max = fmax(acc.rp_max, fabs(rp));
@@ -133,66 +163,51 @@ NB_HD double nb_row(double* s_, double* lam_, double* dsa_, double* dla_, double
   }
   if (MODE == NB_PASS_DIR_PRED)
   {
-    const double inv = *inv_;
+    const double inv = R.inv[r];
     const double ds = -(v + s) - gd;
     const double dl = (-s * lam - lam * ds) * inv;
     acc.rmax = fmax(acc.rmax, -ds * inv);       // -ds/s
     acc.rmax = fmax(acc.rmax, 1.0 + ds * inv);  // -dl/lam = (s + ds)/s for the predictor
     acc.sum_cross += s * dl + lam * ds;
     acc.sum_dd += ds * dl;
-    *dsa_ = ds;
-    *dla_ = dl;
-    return 0.0;
+    R.dsa[r] = ds;
+    R.dla[r] = dl;
+    return ds * dl * inv;
   }
   if (MODE == NB_PASS_DIR_CORR)
   {
-    const double inv = *inv_;
-    const double rc = s * lam + (*dsa_) * (*dla_) - sigmu;
+    const double inv = R.inv[r];
+    const double rc = s * lam + R.dsa[r] * R.dla[r] - sigmu;
     const double ds = -(v + s) - gd;
     const double dl = (-rc - lam * ds) * inv;
     acc.rmax = fmax(acc.rmax, -ds * inv);
     acc.rmax = fmax(acc.rmax, -dl * nb_rcp(lam));
-    *dsa_ = ds;
-    *dla_ = dl;
-    return 0.0;
-  }
-  if (MODE == NB_PASS_LOAD_CORR)
-  {
-    const double rp = v + s;
-    const double rc = s * lam + (*dsa_) * (*dla_) - sigmu;
-    return (lam * rp - rc) * (*inv_);
-  }
-  if (MODE == NB_PASS_UPDATE)
-  {
-    *s_ = s + alpha * (*dsa_);
-    *lam_ = lam + alpha * (*dla_);
+    R.dsa[r] = ds;
+    R.dla[r] = dl;
     return 0.0;
   }
   // NB_PASS_START
   {
-    const double a = fabs(s + *dsa_), b = fabs(lam + *dla_);
-    *s_ = a > 1.0 ? a : 1.0;
-    *lam_ = b > 1.0 ? b : 1.0;
+    const double a = fabs(s + R.dsa[r]), b = fabs(lam + R.dla[r]);
+    R.s[r] = a > 1.0 ? a : 1.0;
+    R.lam[r] = b > 1.0 ? b : 1.0;
   }
   return 0.0;
 }
 
 // One sweep over every inequality row.  Bound rows are visited feature by feature (both sides of a
-// feature by the same lane), line rows control point by control point: item (interval i, control
-// point k, sub-lane) where the SUB adjacent lanes of an item split its lines and combine by shuffle.
+// feature by the same lane), line rows control point by control point (item = interval i, control point k).
 // All per-feature accumulations are conflict-free and in a fixed order.
 template <int NL, int MODE>
-NB_HD void nb_qp_pass(const Group<NL>& g, const NbConsts& cs, const NbQpTable* tb, NbQpShared* sh,
-                      const NbQpRows& R, double sigmu, double alpha, NbPassAcc& acc)
+NB_HD void nb_qp_pass(const Group<NL>& g, const NbQpTable* tb, NbQpShared* sh, const NbQpRows& R, int nlines, double sigmu,
+                      double alpha, NbPassAcc& acc)
 {
-  constexpr int SUB = Group<NL>::SUB;
   const int n = tb->n;
-  const bool loads = (MODE == NB_PASS_RESID || MODE == NB_PASS_LOAD_CORR);
-  for (int q = g.lane; q < 3 * NB_NFEAT_AX; q += NL)
+  for (int q = g.lane; q < NB_NF3; q += NL)
   {
     const int ax = q >> 6, fl = q & 63, f = q;
     if (fl >= 8 * n) continue;
-    double w_u, w_l;
+    double w_u, w_l, i_u, i_l;
     const double lo = sh->blo[ax * 8 + (fl & 7)], hi = sh->bhi[ax * 8 + (fl & 7)];
     double yv = sh->y[f];
     const double dv = sh->dy[f];
@@ -201,90 +216,107 @@ NB_HD void nb_qp_pass(const Group<NL>& g, const NbConsts& cs, const NbQpTable* t
       yv += alpha * dv;
       sh->y[f] = yv;
     }
-    const int rs = 2 * f;
-    const double t_u = nb_row<MODE>(R.s + rs, R.lam + rs, R.dsa + rs, R.dla + rs, R.inv + rs, yv - hi, dv, sigmu, alpha,
-                                    acc, w_u);
-    const double t_l = nb_row<MODE>(R.s + rs + 1, R.lam + rs + 1, R.dsa + rs + 1, R.dla + rs + 1, R.inv + rs + 1,
-                                    lo - yv, -dv, sigmu, alpha, acc, w_l);
-    if (loads)
+    const double t_u = nb_row<MODE>(R, f, yv - hi, dv, sigmu, alpha, acc, w_u, i_u);
+    const double t_l = nb_row<MODE>(R, NB_NF3 + f, lo - yv, -dv, sigmu, alpha, acc, w_l, i_l);
+    if (MODE == NB_PASS_RESID)
     {
       sh->La[f] = t_u - t_l;
-      if (MODE == NB_PASS_RESID)
-      {
-        sh->om[f] = w_u + w_l;
-        sh->dy[f] = R.lam[rs] - R.lam[rs + 1];  // dual load for r_d, parked in dy during RESID
-      }
+      sh->A2[f] = i_u - i_l;
+      sh->omv[fl * 4 + ax] = w_u + w_l;
+      sh->du[f] = R.lam[f] - R.lam[NB_NF3 + f];
     }
+    if (MODE == NB_PASS_DIR_PRED) sh->A1[f] = t_u - t_l;
   }
   g.sync();
-  const int items = 4 * n * SUB;  // <= NL for SUB > 1, so every lane reaches the shuffles below
-  for (int base = 0; base < items; base += NL)
+  // separating-line rows, one row per lane and step: row (l, k) is line l on control point k of its interval
+  for (int q = g.lane; q < 4 * nlines; q += NL)
   {
-    const int q = base + g.lane;
-    const bool on = q < items;
-    const int gq = on ? q / SUB : 0, sub = q % SUB;
-    const int i = gq >> 2, k = gq & 3;
-    const int fx = i * 8 + k, fy = NB_NFEAT_AX + i * 8 + k;
-    const double yx = sh->y[fx], yy = sh->y[fy];
-    const double dx = (MODE == NB_PASS_RESID) ? 0.0 : sh->dy[fx], dyv = (MODE == NB_PASS_RESID) ? 0.0 : sh->dy[fy];
-    double sxx = 0, sxy = 0, syy = 0, lx = 0, ly = 0, dlx = 0, dly = 0;
-    if (on)
-      for (int l = R.lstart[i] + sub; l < R.lstart[i + 1]; l += SUB)
-      {
-        const double n0 = R.cl[3 * l], n1 = R.cl[3 * l + 1], c = R.cl[3 * l + 2];
-        const int rs = 6 * NB_NFEAT_AX + 4 * l + k;
-        double wgt;
-        const double t = nb_row<MODE>(R.s + rs, R.lam + rs, R.dsa + rs, R.dla + rs, R.inv + rs, n0 * yx + n1 * yy - c,
-                                      n0 * dx + n1 * dyv, sigmu, alpha, acc, wgt);
-        if (loads)
-        {
-          lx += t * n0;
-          ly += t * n1;
-          if (MODE == NB_PASS_RESID)
-          {
-            sxx += wgt * n0 * n0;
-            sxy += wgt * n0 * n1;
-            syy += wgt * n1 * n1;
-            const double lam = R.lam[rs];
-            dlx += lam * n0;
-            dly += lam * n1;
-          }
-        }
-      }
-    if (loads)
+    const int l = q >> 2, k = q & 3;
+    int i;
+    if (R.l2i)
+      i = R.l2i[l];
+    else
     {
-      lx = g.sub_sum(lx), ly = g.sub_sum(ly);
+      i = 0;
+      for (int j = 1; j < n; j++) i += (l >= R.lstart[j]) ? 1 : 0;
+    }
+    const double* cl = R.clb[i] + 3 * l;
+    const double n0 = cl[0], n1 = cl[1], c = cl[2];
+    const int fl = i * 8 + k;
+    const double yx = sh->y[fl], yy = sh->y[NB_NFEAT_AX + fl];
+    const double dx = (MODE == NB_PASS_RESID) ? 0.0 : sh->dy[fl], dyv = (MODE == NB_PASS_RESID) ? 0.0 : sh->dy[NB_NFEAT_AX + fl];
+    const int r = NB_ROW_LINE0 + q;
+    double wgt, iv;
+    const double t = nb_row<MODE>(R, r, n0 * yx + n1 * yy - c, n0 * dx + n1 * dyv, sigmu, alpha, acc, wgt, iv);
+    if (MODE == NB_PASS_RESID)
+    {  // parked for the sums below (the pending step has consumed dsa / dla of this row already)
+      R.dsa[r] = t;
+      R.dla[r] = wgt;
+    }
+  }
+  if (MODE != NB_PASS_RESID && MODE != NB_PASS_DIR_PRED) return;
+  g.sync();
+  // per control point (i, k): what its line rows load on the x and y features
+  for (int q = g.lane; q < 4 * n; q += NL)
+  {
+    const int i = q >> 2, k = q & 3;
+    const int fl = i * 8 + k, fx = fl, fy = NB_NFEAT_AX + fl;
+    const double* cl = R.clb[i];
+    double sxx = 0, sxy = 0, syy = 0, lx = 0, ly = 0, dlx = 0, dly = 0, ax_ = 0, ay_ = 0;
+    for (int l = R.lstart[i]; l < R.lstart[i + 1]; l++)
+    {
+      const double n0 = cl[3 * l], n1 = cl[3 * l + 1];
+      const int r = NB_ROW_LINE0 + 4 * l + k;
       if (MODE == NB_PASS_RESID)
       {
-        sxx = g.sub_sum(sxx), sxy = g.sub_sum(sxy), syy = g.sub_sum(syy), dlx = g.sub_sum(dlx), dly = g.sub_sum(dly);
+        const double t = R.dsa[r], wgt = R.dla[r], iv = R.inv[r], lam = R.lam[r];
+        lx += t * n0;
+        ly += t * n1;
+        ax_ += iv * n0;
+        ay_ += iv * n1;
+        sxx += wgt * n0 * n0;
+        sxy += wgt * n0 * n1;
+        syy += wgt * n1 * n1;
+        dlx += lam * n0;
+        dly += lam * n1;
       }
-      if (on && sub == 0)
+      else
       {
-        sh->La[fx] += lx;
-        sh->La[fy] += ly;
-        if (MODE == NB_PASS_RESID)
-        {
-          sh->om[fx] += sxx;
-          sh->om[fy] += syy;
-          sh->Sxy[gq] = sxy;
-          sh->dy[fx] += dlx;
-          sh->dy[fy] += dly;
-        }
+        const double t = R.dsa[r] * R.dla[r] * R.inv[r];
+        lx += t * n0;
+        ly += t * n1;
       }
+    }
+    if (MODE == NB_PASS_RESID)
+    {
+      sh->La[fx] += lx;
+      sh->La[fy] += ly;
+      sh->A2[fx] += ax_;
+      sh->A2[fy] += ay_;
+      sh->omv[fl * 4 + 0] += sxx;
+      sh->omv[fl * 4 + 1] += syy;
+      sh->omv[fl * 4 + 3] = sxy;
+      sh->du[fx] += dlx;
+      sh->du[fy] += dly;
+    }
+    else
+    {
+      sh->A1[fx] += lx;
+      sh->A1[fy] += ly;
     }
   }
   g.sync();
 }
 
-// out[a] = sum_f C[f][c] * vecF[ax*64+f]   (a = ax*dof + c): C^T applied to a per-feature vector, then
-// dst[a] = bsign * base[a] + sign * that + es * extra[a]; item (a, sub-lane) with shuffle combine
+// dst[a] = bsign * base[a] + sign * (C^T vecF)[a] + es * extra[a]   (a = ax*dof + c); item (a, sub-lane): the SUB
+// adjacent lanes of a variable split its features and combine by shuffle
 template <int NL>
 NB_HD void nb_qp_ct_all(const Group<NL>& g, const NbQpTable* tb, const NbQpShared* sh_t, const double* vecF, double* dst,
                         const double* base, double bsign, double sign, const double* extra, double es)
 {
   constexpr int SUB = Group<NL>::SUB;
   const int n = tb->n, dof = tb->dof, nv = 3 * dof;
-  const int items = nv * SUB;
+  const int items = nv * SUB;  // <= NL for SUB > 1, so every lane reaches the shuffles below
   for (int b0 = 0; b0 < items; b0 += NL)
   {
     const int q = b0 + g.lane;
@@ -308,66 +340,153 @@ NB_HD void nb_qp_ct_all(const Group<NL>& g, const NbQpTable* tb, const NbQpShare
   }
 }
 
-// Factorisation K = L D L^T of the nv x nv matrix in sh->K (lower triangle, row-major, ld = nv):
-// afterwards K[i][k] (i > k) = L[i][k] and invd[k] = 1 / D[k].  sh->rhs is used as a column scratch.
+// Normal matrix K0 = Hr + C^T W C + lam_q Hess(c) (lower triangles of the (x,y) block and of the z block; the
+// rank-one term of the quadratic row is NOT included, see nb_qp_solve_blocks).  Items = (block, pair): blocks 0..2 are
+// the same-axis blocks, block 3 the y-x coupling (symmetric: both axes share C), all through the products PP.
 template <int NL>
-NB_HD void nb_qp_factor(const Group<NL>& g, NbQpShared* sh, int nv)
+NB_HD void nb_qp_assemble(const Group<NL>& g, const NbQpTable* tb, NbQpShared* sh, bool has_qc, double lam_q)
+{
+  const int n = tb->n, dof = tb->dof, np = dof * (dof + 1) / 2;
+  for (int q = g.lane; q < 4 * np; q += NL)
+  {
+    const int blk = q / np, p = q - blk * np;
+    const int ca = sh->pca[p], cb = sh->pcb[p];
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+#pragma unroll 2
+    for (int fl = 0; fl < 8 * n; fl += 4)
+    {
+      v0 += sh->omv[fl * 4 + blk] * tb->PP[fl][p];
+      v1 += sh->omv[fl * 4 + 4 + blk] * tb->PP[fl + 1][p];
+      v2 += sh->omv[fl * 4 + 8 + blk] * tb->PP[fl + 2][p];
+      v3 += sh->omv[fl * 4 + 12 + blk] * tb->PP[fl + 3][p];
+    }
+    double v = (v0 + v1) + (v2 + v3);
+    if (blk < 3)
+    {
+      v += tb->Hr[ca][cb];
+      if (has_qc) v += lam_q * 2.0 * tb->tq[ca] * tb->tq[cb];
+      sh->K[(blk * dof + ca) * NB_KLD + blk * dof + cb] = v;
+    }
+    else
+    {
+      sh->K[(dof + ca) * NB_KLD + cb] = v;
+      sh->K[(dof + cb) * NB_KLD + ca] = v;
+    }
+  }
+  g.sync();
+}
+
+// Factorisation K = L D L^T of the two diagonal blocks [0, nxy) and [nxy, nxy + nz) in lockstep, element-parallel:
+// lane e owns the strictly-lower element (i, j); at step t the elements right of column t (of their block) take the
+// rank-one update with the UNSCALED column, K[i][j] -= K[i][k] K[j][k] / K[k][k], so column k and the pivot are only
+// read during the step and one barrier per column suffices.  Diagonal entries are updated by the lanes j == i of a
+// second list range.  Afterwards K[i][k] (i > k) = L[i][k] and invd[k] = 1 / D[k].
+template <int NL>
+NB_HD void nb_qp_factor_blocks(const Group<NL>& g, NbQpShared* sh, int nxy, int nz)
 {
   double* K = sh->K;
-  double* col = sh->rhs;
-  for (int k = 0; k < nv; k++)
+  const int nv = nxy + nz, ne = sh->nelem;
+  for (int t = 0; t < nxy; t++)
   {
-    double d = K[k * nv + k];
-    d = d > 1e-300 ? d : 1e-300;  // rank-deficiency guard (K is positive definite by construction)
-    const double ip = nb_rcp(d);
-    if (g.lane == 0) sh->invd[k] = ip;
-    for (int i = k + 1 + g.lane; i < nv; i += NL)
+    for (int e = g.lane; e < ne + nv; e += NL)
     {
-      const double t = K[i * nv + k];
-      col[i] = t;
-      K[i * nv + k] = t * ip;
-    }
-    g.sync();
-    for (int q = g.lane; q < sh->npairs; q += NL)
-    {
-      const int i = sh->pa[q], j = sh->pb[q];
-      if (j > k) K[i * nv + j] -= K[i * nv + k] * col[j];
+      const int i = e < ne ? sh->ei[e] : e - ne, j = e < ne ? sh->ej[e] : e - ne;
+      const bool second = i >= nxy;
+      const int k = second ? nxy + t : t;
+      if ((second && t >= nz) || j <= k) continue;
+      double d = K[k * NB_KLD + k];
+      d = d > 1e-300 ? d : 1e-300;  // rank-deficiency guard (K is positive definite by construction)
+      K[i * NB_KLD + j] -= K[i * NB_KLD + k] * K[j * NB_KLD + k] * nb_rcp(d);
     }
     g.sync();
   }
+  for (int k = g.lane; k < nv; k += NL)
+  {
+    double d = K[k * NB_KLD + k];
+    d = d > 1e-300 ? d : 1e-300;
+    sh->invd[k] = nb_rcp(d);
+  }
+  g.sync();
+  for (int e = g.lane; e < ne; e += NL) K[sh->ei[e] * NB_KLD + sh->ej[e]] *= sh->invd[sh->ej[e]];
+  g.sync();
 }
 
-// Solve L D L^T x = b in place.  Device: one warp, x in registers, broadcasts by shuffle (no block
-// barriers); host emulation: plain loops in the same summation order.
-template <int NL>
-NB_HD void nb_qp_solve_ldl(const Group<NL>& g, NbQpShared* sh, int nv, double* b)
+#if defined(__CUDA_ARCH__)
+// x_i of K0 x = b (lane i of warp 0), both blocks in lockstep: 2 nxy dependent shuffle + FMA steps.  Row i and column i
+// of L are fetched into registers first (static indices: the loops are fully unrolled); one copy of the code serves
+// every solve of an iteration.
+__device__ __noinline__ double nb_warp_solve(const double* K, const double* invd, int nxy, int nz, int lane, double x)
 {
-  const double* K = sh->K;
+  constexpr int W = 2 * NB_DOF_MAX;
+  const bool second = lane >= nxy;
+  const int base = second ? nxy : 0, nb = second ? nz : nxy, il = lane - base;
+  const bool mine = il < nb;
+  double L[W], Lt[W];
+#pragma unroll
+  for (int t = 0; t < W; t++)
+  {
+    L[t] = (mine && t < il) ? K[lane * NB_KLD + base + t] : 0.0;
+    Lt[t] = (mine && t > il && t < nb) ? K[(base + t) * NB_KLD + lane] : 0.0;
+  }
+  const double id = mine ? invd[lane] : 0.0;
+#pragma unroll
+  for (int t = 0; t < W; t++)
+    if (t < nxy)
+    {
+      const double xk = __shfl_sync(0xffffffffu, x, (base + t) & 31);
+      x -= L[t] * xk;
+    }
+  x *= id;
+#pragma unroll
+  for (int t = W - 1; t >= 0; t--)
+    if (t < nxy)
+    {
+      const double xk = __shfl_sync(0xffffffffu, x, (base + t) & 31);
+      x -= Lt[t] * xk;
+    }
+  return mine ? x : 0.0;
+}
+#endif
+
+// Solve K x = b in place, K = K0 (factorised blocks) + dq g g^T by Sherman-Morrison when dq != 0 (u = K0^-1 g and
+// gu = g . u precomputed in sh->uq).  Device: x in registers, pivots broadcast by shuffle, the two blocks in lockstep.
+template <int NL>
+NB_HD void nb_qp_solve_blocks(const Group<NL>& g, NbQpShared* sh, int nxy, int nz, double* b, double dq, double gu)
+{
+  const int nv = nxy + nz;
   g.sync();
 #if defined(__CUDA_ARCH__)
   if (g.lane < 32)
   {
     const int i = g.lane;
-    double x = i < nv ? b[i] : 0.0;
-    for (int k = 0; k < nv; k++)
-    {  // forward: unit lower
-      const double xk = __shfl_sync(0xffffffffu, x, k);
-      if (i > k && i < nv) x -= K[i * nv + k] * xk;
+    const bool mine = i < nv;
+    double x = nb_warp_solve(sh->K, sh->invd, nxy, nz, i, mine ? b[i] : 0.0);
+    if (dq != 0.0)
+    {
+      double gy = mine ? sh->gq[i] * x : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) gy += __shfl_xor_sync(0xffffffffu, gy, o);
+      if (mine) x -= sh->uq[i] * (dq * gy / (1.0 + dq * gu));
     }
-    if (i < nv) x *= sh->invd[i];
-    for (int k = nv - 1; k >= 0; k--)
-    {  // backward: L^T
-      const double xk = __shfl_sync(0xffffffffu, x, k);
-      if (i < k) x -= K[k * nv + i] * xk;
-    }
-    if (i < nv) b[i] = x;
+    if (mine) b[i] = x;
   }
 #else
-  for (int k = 0; k < nv; k++)
-    for (int i = k + 1; i < nv; i++) b[i] -= K[i * nv + k] * b[k];
-  for (int i = 0; i < nv; i++) b[i] *= sh->invd[i];
-  for (int k = nv - 1; k >= 0; k--)
-    for (int i = 0; i < k; i++) b[i] -= K[k * nv + i] * b[k];
+  const double* K = sh->K;
+  for (int blk = 0; blk < 2; blk++)
+  {
+    const int lo = blk ? nxy : 0, hi = blk ? nv : nxy;
+    for (int k = lo; k < hi; k++)
+      for (int i = k + 1; i < hi; i++) b[i] -= K[i * NB_KLD + k] * b[k];
+    for (int i = lo; i < hi; i++) b[i] *= sh->invd[i];
+    for (int k = hi - 1; k >= lo; k--)
+      for (int i = lo; i < k; i++) b[i] -= K[k * NB_KLD + i] * b[k];
+  }
+  if (dq != 0.0)
+  {
+    double gy = 0.0;
+    for (int i = 0; i < nv; i++) gy += sh->gq[i] * b[i];
+    for (int i = 0; i < nv; i++) b[i] -= sh->uq[i] * (dq * gy / (1.0 + dq * gu));
+  }
 #endif
   g.sync();
 }
@@ -397,9 +516,23 @@ NB_HD double nb_objective(const NbConsts& cs, int n, int mode, const double* x /
 template <int NL>
 NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* tb, NbQpShared* sh,
                        const NbQpRows& R, const double* coeff_init, int nlines, double* x_out, int* iters_out,
-                       double* obj_out)
+                       double* obj_out, long long* prof = nullptr)
 {
+  // measurement hook (nb_set_profiling): SM cycles lane 0 spends per phase, summed over the iterations
+#if defined(__CUDA_ARCH__)
+  long long pt[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }, pc = prof ? clock64() : 0;
+#define NB_QP_TICK(k)                     \
+  if (prof)                               \
+  {                                       \
+    const long long now_ = clock64();     \
+    pt[k] += now_ - pc;                   \
+    pc = now_;                            \
+  }
+#else
+#define NB_QP_TICK(k)
+#endif
   const int n = tb->n, dof = tb->dof, nv = 3 * dof, mode = tb->mode;
+  const int nxy = 2 * dof, nz = dof;
   const double T = cs.T;
   const double qp[4] = { T * T * T, T * T, T, 1.0 };
   *iters_out = 0;
@@ -411,18 +544,25 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
     sh->ax_of[a] = (unsigned char)(a / (dof > 0 ? dof : 1));
     sh->c_of[a] = (unsigned char)(a - (a / (dof > 0 ? dof : 1)) * dof);
   }
-  if (g.lane == 0)
-  {
-    int q = 0;
-    for (int a = 0; a < nv; a++)
-      for (int b = 0; b <= a; b++)
-      {
-        sh->pa[q] = (unsigned char)a;
-        sh->pb[q] = (unsigned char)b;
-        q++;
-      }
-    sh->npairs = q;
+  for (int ca = g.lane; ca < dof; ca += NL)
+    for (int cb = 0; cb <= ca; cb++)
+    {
+      sh->pca[ca * (ca + 1) / 2 + cb] = (unsigned char)ca;
+      sh->pcb[ca * (ca + 1) / 2 + cb] = (unsigned char)cb;
+    }
+  {  // strictly-lower elements of the (x,y) block, then of the z block, row by row
+    const int na = nxy * (nxy - 1) / 2, nb = nz * (nz - 1) / 2;
+    for (int e = g.lane; e < na + nb; e += NL)
+    {
+      const int q = e < na ? e : e - na, off = e < na ? 0 : nxy;
+      int i = 1;
+      while (i * (i + 1) / 2 <= q) i++;
+      sh->ei[e] = (unsigned char)(off + i);
+      sh->ej[e] = (unsigned char)(off + q - i * (i - 1) / 2);
+    }
+    if (g.lane == 0) sh->nelem = na + nb;
   }
+  for (int q = g.lane; q < NB_NFEAT_AX * 4; q += NL) sh->omv[q] = 0.0;
   for (int q = g.lane; q < 3 * 4 * n; q += NL)
   {
     const int ax = q / (4 * n), r = q - ax * 4 * n;
@@ -449,7 +589,8 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
   hn = fmax(hn, fmax(cs.v_max, cs.a_max));
   {
     double hl = 0.0;
-    for (int l = g.lane; l < nlines; l += NL) hl = fmax(hl, fabs(R.cl[3 * l + 2]));
+    for (int i = 0; i < n; i++)
+      for (int l = R.lstart[i] + g.lane; l < R.lstart[i + 1]; l += NL) hl = fmax(hl, fabs(R.clb[i][3 * l + 2]));
     hn = fmax(hn, g.max(hl));
   }
   if (tb->has_resid)
@@ -505,7 +646,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
   if (dof == 0)
   {  // the equalities leave a single point: feasible iff every row holds there
     double worst = -1e300;
-    for (int q = g.lane; q < 3 * NB_NFEAT_AX; q += NL)
+    for (int q = g.lane; q < NB_NF3; q += NL)
     {
       const int ax = q >> 6, fl = q & 63;
       if (fl >= 8 * n) continue;
@@ -516,8 +657,9 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
     for (int q = g.lane; q < 4 * n; q += NL)
     {
       const int i = q >> 2, k = q & 3;
+      const double* cl = R.clb[i];
       for (int l = R.lstart[i]; l < R.lstart[i + 1]; l++)
-        worst = fmax(worst, R.cl[3 * l] * sh->y[i * 8 + k] + R.cl[3 * l + 1] * sh->y[NB_NFEAT_AX + i * 8 + k] - R.cl[3 * l + 2]);
+        worst = fmax(worst, cl[3 * l] * sh->y[i * 8 + k] + cl[3 * l + 1] * sh->y[NB_NFEAT_AX + i * 8 + k] - cl[3 * l + 2]);
     }
     worst = g.max(worst);
     bool ok = !(worst > 1e-9 * (1.0 + hn));
@@ -532,26 +674,29 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
   else
   {
     // ---- start: s = max(h - G w, 1), lam = 1
-    for (int q = g.lane; q < 3 * NB_NFEAT_AX; q += NL)
+    for (int q = g.lane; q < NB_NF3; q += NL)
     {
       const int ax = q >> 6, fl = q & 63, f = q;
       if (fl >= 8 * n) continue;
       const double lo = sh->blo[ax * 8 + (fl & 7)], hi = sh->bhi[ax * 8 + (fl & 7)];
       const double yv = sh->y[f];
-      R.s[2 * f] = fmax(hi - yv, 1.0);
-      R.s[2 * f + 1] = fmax(yv - lo, 1.0);
-      R.lam[2 * f] = 1.0;
-      R.lam[2 * f + 1] = 1.0;
+      R.s[f] = fmax(hi - yv, 1.0);
+      R.s[NB_NF3 + f] = fmax(yv - lo, 1.0);
+      R.lam[f] = 1.0;
+      R.lam[NB_NF3 + f] = 1.0;
+      sh->dy[f] = 0.0;
     }
-    for (int q = g.lane; q < 4 * nlines; q += NL)
+    for (int q = g.lane; q < 4 * n; q += NL)
     {
-      const int l = q >> 2, k = q & 3;
-      int i = 0;
-      while (l >= R.lstart[i + 1]) i++;
-      const int rs = 6 * NB_NFEAT_AX + q;
-      const double v = R.cl[3 * l + 2] - R.cl[3 * l] * sh->y[i * 8 + k] - R.cl[3 * l + 1] * sh->y[NB_NFEAT_AX + i * 8 + k];
-      R.s[rs] = fmax(v, 1.0);
-      R.lam[rs] = 1.0;
+      const int i = q >> 2, k = q & 3;
+      const double* cl = R.clb[i];
+      for (int l = R.lstart[i]; l < R.lstart[i + 1]; l++)
+      {
+        const int r = NB_ROW_LINE0 + 4 * l + k;
+        const double v = cl[3 * l + 2] - cl[3 * l] * sh->y[i * 8 + k] - cl[3 * l + 1] * sh->y[NB_NFEAT_AX + i * 8 + k];
+        R.s[r] = fmax(v, 1.0);
+        R.lam[r] = 1.0;
+      }
     }
     double s_q = 1.0, lam_q = 1.0, dsa_q = 0.0, dla_q = 0.0;
     if (has_qc)
@@ -562,6 +707,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
     }
     g.sync();
 
+    NB_QP_TICK(0);
     int it = 0;
     double al_pending = 0.0;  // step of the previous iteration, applied to (s, lam, y) by the next RESID sweep
     for (it = 0; it <= cs.max_iter; it++)
@@ -569,18 +715,19 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       const bool init_pass = (it == 0);
       // ---- residuals and weights
       NbPassAcc acc = { 0.0, 0.0, 0.0, 0.0, 0.0 };
-      nb_qp_pass<NL, NB_PASS_RESID>(g, cs, tb, sh, R, 0.0, al_pending, acc);
+      nb_qp_pass<NL, NB_PASS_RESID>(g, tb, sh, R, nlines, 0.0, al_pending, acc);
       al_pending = 0.0;
+      NB_QP_TICK(1);
       double cval = 0.0, rp_q = 0.0;
       if (has_qc)
       {
         NB_QC_EVAL(cval);
         rp_q = cval + s_q;
       }
-      double d0 = 0.0, d1 = 0.0;
-      g.reduce5(acc.sum_sl, acc.rp_max, acc.rmax, d0, d1);
-      const double mu = (acc.sum_sl + (has_qc ? s_q * lam_q : 0.0)) / mq;
-      double rpn = acc.rp_max;
+      double sum_sl = acc.sum_sl, rp_max = acc.rp_max;
+      g.reduce_sum_max(sum_sl, rp_max);
+      const double mu = (sum_sl + (has_qc ? s_q * lam_q : 0.0)) / mq;
+      double rpn = rp_max;
       if (has_qc) rpn = fmax(rpn, fabs(rp_q));
       // gobj = Hr w + g0 ; r_d = gobj + C^T(lambda load) + lam_q grad c
       for (int a = g.lane; a < nv; a += NL)
@@ -592,15 +739,22 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
         sh->gq[a] = has_qc ? 2.0 * e3[ax] * tb->tq[c] : 0.0;
       }
       g.sync();
-      nb_qp_ct_all<NL>(g, tb, sh, sh->dy, sh->rd, sh->gobj, 1.0, 1.0, sh->gq, has_qc ? lam_q : 0.0);
+      nb_qp_ct_all<NL>(g, tb, sh, sh->du, sh->rd, sh->gobj, 1.0, 1.0, sh->gq, has_qc ? lam_q : 0.0);
       g.sync();
-      double rdn = 0.0, gn = 0.0, fobj = fconst;
-      for (int a = 0; a < nv; a++)
+      double rdn = 0.0, gn = 0.0, fsum = 0.0;
+      for (int a = g.lane; a < nv; a += NL)
       {
         rdn = fmax(rdn, fabs(sh->rd[a]));
         gn = fmax(gn, fabs(sh->gobj[a]));
-        fobj += 0.5 * (sh->g0[a] + sh->gobj[a]) * sh->w[a];
+        fsum += 0.5 * (sh->g0[a] + sh->gobj[a]) * sh->w[a];
       }
+      {  // gn enters as a "sum" of one lane's value: every lane recomputes it from shared memory below
+        double e1 = 0.0;
+        g.reduce_max_sum_sum(rdn, fsum, e1);
+        gn = 0.0;
+        for (int a = 0; a < nv; a++) gn = fmax(gn, fabs(sh->gobj[a]));
+      }
+      const double fobj = fconst + fsum;
       if (!init_pass)
       {
         if (rpn <= cs.tol * (1.0 + hn) && rdn <= cs.tol * (1.0 + gn) && mu * mq <= cs.tol * (1.0 + fabs(fobj)))
@@ -611,52 +765,34 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
         if (it == cs.max_iter) break;
         if (!(mu == mu) || !(rpn == rpn) || !(rdn == rdn)) break;
       }
-      // ---- K = Hobj + C^T W C (+ quadratic-constraint terms), lower triangle
+      NB_QP_TICK(2);
+      // ---- K0 = Hobj + C^T W C (+ Hessian of the quadratic row), factorised block by block
+      nb_qp_assemble<NL>(g, tb, sh, has_qc, lam_q);
+      NB_QP_TICK(3);
+      nb_qp_factor_blocks<NL>(g, sh, nxy, nz);
+      NB_QP_TICK(4);
       const double d_q = has_qc ? lam_q / s_q : 0.0;
-      for (int q = g.lane; q < sh->npairs; q += NL)
-      {
-        const int a = sh->pa[q], b = sh->pb[q];
-        const int axa = sh->ax_of[a], ca = sh->c_of[a], axb = sh->ax_of[b], cb = sh->c_of[b];
-        double v = 0.0;
-        if (axa == axb)
-        {
-          const double* om = sh->om + axa * NB_NFEAT_AX;
-          double v0 = tb->Hr[ca][cb], v1 = 0.0;
-          for (int fl = 0; fl < 8 * n; fl += 2)
-          {
-            v0 += om[fl] * tb->C[fl][ca] * tb->C[fl][cb];
-            v1 += om[fl + 1] * tb->C[fl + 1][ca] * tb->C[fl + 1][cb];
-          }
-          v = v0 + v1;
-          if (has_qc) v += lam_q * 2.0 * tb->tq[ca] * tb->tq[cb];
-        }
-        else if (axa == 1 && axb == 0)
-        {
-          double v0 = 0.0, v1 = 0.0;
-          for (int i = 0; i < n; i++)
-          {
-            v0 += sh->Sxy[i * 4] * tb->C[i * 8][ca] * tb->C[i * 8][cb] +
-                  sh->Sxy[i * 4 + 2] * tb->C[i * 8 + 2][ca] * tb->C[i * 8 + 2][cb];
-            v1 += sh->Sxy[i * 4 + 1] * tb->C[i * 8 + 1][ca] * tb->C[i * 8 + 1][cb] +
-                  sh->Sxy[i * 4 + 3] * tb->C[i * 8 + 3][ca] * tb->C[i * 8 + 3][cb];
-          }
-          v = v0 + v1;
-        }
-        if (has_qc) v += d_q * sh->gq[a] * sh->gq[b];
-        sh->K[a * nv + b] = v;
+      double gu = 0.0;
+      if (has_qc)
+      {  // Sherman-Morrison for the rank-one term d_q gq gq^T: u = K0^-1 gq
+        for (int a = g.lane; a < nv; a += NL) sh->uq[a] = sh->gq[a];
+        nb_qp_solve_blocks<NL>(g, sh, nxy, nz, sh->uq, 0.0, 0.0);
+        double t = 0.0;
+        for (int a = g.lane; a < nv; a += NL) t += sh->gq[a] * sh->uq[a];
+        gu = g.sum(t);
       }
-      g.sync();
-      nb_qp_factor<NL>(g, sh, nv);
       // ---- predictor
       const double tau_q = has_qc ? (lam_q * rp_q - s_q * lam_q) / s_q : 0.0;
       nb_qp_ct_all<NL>(g, tb, sh, sh->La, sh->dw, sh->rd, -1.0, -1.0, sh->gq, -tau_q);
-      nb_qp_solve_ldl<NL>(g, sh, nv, sh->dw);
+      nb_qp_solve_blocks<NL>(g, sh, nxy, nz, sh->dw, d_q, gu);
       nb_qp_features<NL>(g, tb, sh, sh->dy, sh->dw, false);
       g.sync();
+      NB_QP_TICK(5);
       acc = NbPassAcc{ 0.0, 0.0, 0.0, 0.0, 0.0 };
-      nb_qp_pass<NL, NB_PASS_DIR_PRED>(g, cs, tb, sh, R, 0.0, 0.0, acc);
-      g.reduce5(d0, acc.rmax, d1, acc.sum_cross, acc.sum_dd);
+      nb_qp_pass<NL, NB_PASS_DIR_PRED>(g, tb, sh, R, nlines, 0.0, 0.0, acc);
       double rmax = acc.rmax, scross = acc.sum_cross, sdd = acc.sum_dd;
+      g.reduce_max_sum_sum(rmax, scross, sdd);
+      NB_QP_TICK(6);
       if (has_qc)
       {
         double gd = 0.0;
@@ -669,7 +805,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       }
       if (init_pass)
       {  // Nocedal-Wright starting-point correction
-        nb_qp_pass<NL, NB_PASS_START>(g, cs, tb, sh, R, 0.0, 0.0, acc);
+        nb_qp_pass<NL, NB_PASS_START>(g, tb, sh, R, nlines, 0.0, 0.0, acc);
         if (has_qc)
         {
           s_q = fmax(fabs(s_q + dsa_q), 1.0);
@@ -684,17 +820,21 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       // do not drive the complementarity below a tenth of what the stopping test needs: at mu ~ 1e-12 the
       // normal matrix is too ill-conditioned for the dual residual to reach its tolerance
       sigmu = fmax(sigmu, 0.1 * cs.tol * (1.0 + fabs(fobj)) / mq);
-      // ---- corrector
-      nb_qp_pass<NL, NB_PASS_LOAD_CORR>(g, cs, tb, sh, R, sigmu, 0.0, acc);
+      // ---- corrector: load = predictor load - ds_aff dl_aff / s + sigma mu / s, per feature
+      for (int q = g.lane; q < NB_NF3; q += NL)
+        if ((q & 63) < 8 * n) sh->La[q] += sigmu * sh->A2[q] - sh->A1[q];
+      g.sync();
       const double rc_q = s_q * lam_q + dsa_q * dla_q - sigmu;
       const double tau_q2 = has_qc ? (lam_q * rp_q - rc_q) / s_q : 0.0;
       nb_qp_ct_all<NL>(g, tb, sh, sh->La, sh->dw, sh->rd, -1.0, -1.0, sh->gq, -tau_q2);
-      nb_qp_solve_ldl<NL>(g, sh, nv, sh->dw);
+      nb_qp_solve_blocks<NL>(g, sh, nxy, nz, sh->dw, d_q, gu);
       nb_qp_features<NL>(g, tb, sh, sh->dy, sh->dw, false);
       g.sync();
+      NB_QP_TICK(7);
       acc = NbPassAcc{ 0.0, 0.0, 0.0, 0.0, 0.0 };
-      nb_qp_pass<NL, NB_PASS_DIR_CORR>(g, cs, tb, sh, R, sigmu, 0.0, acc);
+      nb_qp_pass<NL, NB_PASS_DIR_CORR>(g, tb, sh, R, nlines, sigmu, 0.0, acc);
       rmax = g.max(acc.rmax);
+      NB_QP_TICK(8);
       double ds_q = 0.0, dl_q = 0.0;
       if (has_qc)
       {
@@ -718,6 +858,11 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
     }
     *iters_out = it;
   }
+#if defined(__CUDA_ARCH__)
+  if (prof && g.lane == 0)
+    for (int k = 0; k < 10; k++) prof[k] += pt[k];
+#endif
+#undef NB_QP_TICK
 #undef NB_QC_EVAL
   if (converged)
   {

@@ -293,6 +293,12 @@ bool nb_build_table(const NbConsts* cs, int n, int mode, NbQpTable* t)
         for (int c = 0; c < 3; c++) t->c0[i * 8 + j][c] += row[q] * t->Pm[4 * i + q][c];
       }
     }
+  for (int f = 0; f < 8 * n; f++)
+  {
+    for (int c = 0; c < dof; c++) t->Ct[c][f] = t->C[f][c];
+    for (int ca = 0; ca < dof; ca++)
+      for (int cb = 0; cb <= ca; cb++) t->PP[f][ca * (ca + 1) / 2 + cb] = t->C[f][ca] * t->C[f][cb];
+  }
   // objective (:322-380): 36 T sum a_i^2 + W (qp.x_last - pf)^2 [+ W ((qv.x_last)^2 + (qa.x_last)^2)]
   double tv[NB_DOF_MAX] = { 0 }, ta[NB_DOF_MAX] = { 0 }, tv0[3] = { 0 }, ta0[3] = { 0 };
   for (int q = 0; q < 4; q++)

@@ -41,7 +41,7 @@ extern "C" int emul_replan_batch(const nb_params* par, const double* pb, const i
       if (!nb_build_table(&cs, n, mode, &tabs[mode * NB_NPOL + n - 1])) return -2;
   const int B = a->B, N = par->num_agents, M = par->num_static, NH = a->n_hull_slots;
   const int LS = NH + N + M + par->ent_slots;
-  const int RS = 6 * NB_NFEAT_AX + 4 * NB_NPOL * LS;
+  const int RS = NB_ROW_LINE0 + 4 * NB_NPOL * LS;
   NbLinesIn in;
   in.agent_id = a->agent_id, in.n_int = a->n_int, in.coeff_init = a->coeff_init, in.NH = NH;
   in.hull_ptr = a->hull_ptr, in.hull_cnt = a->hull_cnt, in.hull_xy = a->hull_xy, in.nih0 = a->nih0, in.nih0_group = a->nih0_group, in.hull_known = a->hull_known, in.st_ptr = st_ptr, in.st_xy = st_xy;
@@ -53,22 +53,30 @@ extern "C" int emul_replan_batch(const nb_params* par, const double* pb, const i
   int red[1], hull[NB_PRUNE_KMAX + 1], misc[8];
   NbPruneShared ps;
   ps.px = px.data(), ps.py = py.data(), ps.valid = valid.data(), ps.red = red, ps.hull = hull, ps.misc = misc;
-  int lstart[9], err = 0;
+  int lstart[9], ncl[NB_NPOL], err = 0;
+  const double* clb[NB_NPOL];
   NbQpShared* sh = new NbQpShared();
   Group<1> g(0);
   for (int b = 0; b < B; b++)
   {
     for (int i = 0; i < NB_NPOL; i++)
       nb_lines_task<1>(0, b, i, cs, in, lines.data() + (size_t)i * LS * 3, ok.data() + (size_t)i * LS,
-                       keep.data() + (size_t)i * LS, ps, &err);
+                       keep.data() + (size_t)i * LS, ps, &err, cl.data() + (size_t)i * LS * 3, &ncl[i], prune != 0);
     if (a->lines) memcpy(a->lines + (size_t)b * NB_NPOL * LS * 3, lines.data(), sizeof(double) * lines.size());
     if (a->line_ok) memcpy(a->line_ok + (size_t)b * NB_NPOL * LS, ok.data(), ok.size());
     const int n = a->n_int[b];
     const double* ci = a->coeff_init + (size_t)b * 96;
-    const int nl = nb_compact_lines<1>(g, n, LS, lines.data(), prune ? keep.data() : ok.data(), cl.data(), lstart);
+    int nl = 0;
+    for (int i = 0; i < NB_NPOL; i++)
+    {  // one run of kept lines per interval, as the kernel's global-row path addresses them
+      lstart[i] = nl;
+      clb[i] = cl.data() + (size_t)i * LS * 3 - (size_t)3 * nl;
+      if (i < n) nl += ncl[i];
+    }
+    for (int i = n; i <= NB_NPOL; i++) lstart[i] = nl;
     if (n_lines_out) n_lines_out[b] = nl;
     NbQpRows R;
-    R.s = rows.data(), R.lam = R.s + RS, R.dsa = R.lam + RS, R.dla = R.dsa + RS, R.inv = R.dla + RS, R.cl = cl.data(), R.lstart = lstart;
+    R.s = rows.data(), R.lam = R.s + RS, R.dsa = R.lam + RS, R.dla = R.dsa + RS, R.inv = R.dla + RS, R.clb = clb, R.lstart = lstart, R.l2i = nullptr;
     double xout[96], obj = 0;
     int it0 = 0, it1 = 0, status = NB_STATUS_FAILED;
     bool okq = nb_qp_solve<1>(g, cs, &tabs[n - 1], sh, R, ci, nl, xout, &it0, &obj);
