@@ -43,6 +43,29 @@ def main():
         out.update({f"{f}_{k}": v for f, v in g.items()})
         print(cfg, seed, "status", g["status"].tolist(), "nodes", g["nodes"].tolist())
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reference", "ref_search.npz"), **out)
+    make_qp_golden(orc)
+
+
+def make_qp_golden(orc):
+    """Outputs of the reference's own PolySolverGurobi (solver_gurobi_poly.cpp, HiGHS under a recording Gurobi stand-in,
+    canonical lines from its separator) on every agent of every fixture in tests/golden/: status path, pwp_out, objective.
+    The recorded models are checked against the oracle's restatement while recording (tests/test_reference_pin.py)."""
+    from neptune_b200.batch import ReplanResult
+    from tests.golden_util import golden_files, load
+    from tests.test_reference_pin import run_reference_qp
+    ref.install_qp_hooks(orc)
+    out = {}
+    for path in golden_files():
+        name = os.path.basename(path)[:-4]
+        par, b, z = load(path)
+        res = ReplanResult.empty(b)
+        assert orc.replan_batch(b, res, 2) == 0
+        st, co, ob = np.zeros(b.B, np.int32), np.zeros((b.B, 3, 8, 4)), np.zeros(b.B)
+        for a in range(b.B):
+            st[a], co[a], ob[a] = run_reference_qp(orc, b, a, res)
+        out[name + "/status"], out[name + "/coeff"], out[name + "/obj"] = st, co, ob
+        print(name, "reference status", st.tolist(), "oracle", res.status.tolist(), "max|dcoeff|", np.abs(co - res.coeff_out).max())
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reference", "ref_qp.npz"), **out)
 
 
 if __name__ == "__main__":

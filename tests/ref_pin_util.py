@@ -248,3 +248,158 @@ def separator_solve3d(A, B):
     f.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     ok = f(_p(A), len(A), _p(B), len(B), _p(out))
     return bool(ok), out[:3].copy(), float(out[3])
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# The reference's own PolySolverGurobi (neptune/src/solver_gurobi_poly.cpp) with recording stand-ins underneath
+class RefQpModel(C.Structure):
+    """ref_qp_model of oracle/ref_stubs/gurobi_c++.h"""
+    _D, _S = C.POINTER(C.c_double), C.POINTER(C.c_char)
+    _fields_ = [("nvar", C.c_int), ("lb", _D), ("ub", _D), ("Q", _D), ("c", _D), ("c0", C.c_double),
+                ("nlin", C.c_int), ("A", _D), ("sense", _S), ("rhs", _D),
+                ("nquad", C.c_int), ("Qc", _D), ("qc", _D), ("qsense", _S), ("qrhs", _D),
+                ("time_limit", C.c_double), ("non_convex", C.c_int)]
+
+
+QP_MODELS = []    # one dict per GRBModel::optimize() call of the reference since the last clear
+_QP_CB = None
+_LP_CANON_CB = None
+
+
+def _arr(ptr, shape):
+    n = int(np.prod(shape))
+    if n == 0:
+        return np.zeros(shape)
+    return np.ctypeslib.as_array(ptr, shape=(n,)).reshape(shape).copy()
+
+
+def _solve_recorded(m):
+    """Solve one recorded model: HiGHS (convex QP); with the quadratic terminal row, SLSQP on the reduced space.
+    Returns (GRB status, x)."""
+    from tests.highs_util import qp_highs
+    nv = m["nvar"]
+    used = (np.abs(m["Q"]).sum(0) + np.abs(m["Q"]).sum(1) + np.abs(m["c"]) + np.abs(m["A"]).sum(0)) > 0
+    if m["nquad"]:
+        used |= (np.abs(m["Qc"]).sum((0, 1)) + np.abs(m["Qc"]).sum((0, 2)) + np.abs(m["qc"]).sum(0)) > 0
+    idx = np.flatnonzero(used)
+    P = (m["Q"] + m["Q"].T)[np.ix_(idx, idx)]
+    q = m["c"][idx]
+    A = m["A"][:, idx]
+    eq = m["sense"] == b"="
+    le, ge = m["sense"] == b"<", m["sense"] == b">"
+    G = np.vstack([A[le], -A[ge]])
+    h = np.concatenate([m["rhs"][le], -m["rhs"][ge]])
+    x = np.zeros(nv)
+    if m["nquad"] == 0:
+        st, xs, _ = qp_highs(P, q, A[eq], m["rhs"][eq], G, h)
+        if st != "Optimal":
+            return 3, x
+        x[idx] = xs
+        return 2, x
+    # quadratic row(s): eliminate the equalities, then SLSQP from the solution without the quadratic row
+    from scipy.optimize import minimize
+    Aeq, beq = A[eq], m["rhs"][eq]
+    U, sv, Vt = np.linalg.svd(Aeq, full_matrices=True)
+    rank = int((sv > 1e-10 * sv[0]).sum())
+    xp = Vt[:rank].T @ ((U[:, :rank].T @ beq) / sv[:rank])
+    if np.abs(Aeq @ xp - beq).max() > 1e-8 * (1 + np.abs(beq).max()):
+        return 3, x
+    Z = Vt[rank:].T
+    Qc = [(m["Qc"][k] + m["Qc"][k].T)[np.ix_(idx, idx)] * 0.5 for k in range(m["nquad"])]
+    qc = [m["qc"][k][idx] for k in range(m["nquad"])]
+
+    def full(w):
+        return xp + Z @ w
+    if Z.shape[1] == 0:
+        xs = xp
+        ok = (G @ xs - h).max(initial=-1) <= 1e-7 and all(xs @ Qc[k] @ xs + qc[k] @ xs <= m["qrhs"][k] + 1e-9 for k in range(m["nquad"]))
+        x[idx] = xs
+        return (2 if ok else 3), x
+    cons = [{"type": "ineq", "fun": lambda w: h - G @ full(w), "jac": lambda w: -G @ Z}]
+    for k in range(m["nquad"]):
+        cons.append({"type": "ineq", "fun": (lambda w, k=k: m["qrhs"][k] - full(w) @ Qc[k] @ full(w) - qc[k] @ full(w)),
+                     "jac": (lambda w, k=k: -(2 * Qc[k] @ full(w) + qc[k]) @ Z)})
+    st0, x0, _ = qp_highs(P, q, Aeq, beq, G, h)
+    w0 = Z.T @ (x0 - xp) if st0 == "Optimal" else np.zeros(Z.shape[1])
+    best = None
+    for scale in (1.0, 0.0):
+        r = minimize(lambda w: 0.5 * full(w) @ P @ full(w) + q @ full(w), w0 * scale, jac=lambda w: Z.T @ (P @ full(w) + q),
+                     constraints=cons, method="SLSQP", options={"ftol": 1e-15, "maxiter": 500})
+        xs = full(r.x)
+        feas = (G @ xs - h).max(initial=-1) <= 1e-7 and all(xs @ Qc[k] @ xs + qc[k] @ xs <= m["qrhs"][k] + 1e-8 for k in range(m["nquad"]))
+        if feas and (best is None or r.fun < best[0]):
+            best = (r.fun, xs)
+    if best is None:
+        return 3, x
+    x[idx] = best[1]
+    return 2, x
+
+
+def install_qp_hooks(oracle):
+    """Engines for the reference's two third-party solvers: the separator's LP returns the canonical (minimum-norm) line
+    of the oracle -- with a zero objective any feasible vertex is a legitimate GLPK answer, and this one makes the QP
+    rows comparable with the oracle's -- and GRBModel::optimize records the model and solves it with HiGHS."""
+    global _QP_CB, _LP_CANON_CB, _LP_CB
+    I, D = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    lp_proto = C.CFUNCTYPE(C.c_int, C.c_int, C.c_int, I, D, D, I, D, D, D, C.c_int, C.c_int, I, I, D, D)
+
+    def lp_solve(rows, cols, rt, rlb, rub, ct, clb, cub, obj, direction, ne, ia, ja, ar, x):
+        G = np.zeros((rows, cols))
+        for k in range(ne):
+            G[ia[k] - 1, ja[k] - 1] += ar[k]
+        isA = np.array([rt[i] == 2 for i in range(rows)])      # GLP_LO: n.a + d >= 1
+        A, B = G[isA][:, :2], G[~isA][:, :2]
+        assert cols == 3 and np.all(G[:, 2] == 1.0)
+        ok, line = oracle.separate(A, B)
+        if not ok:
+            return 4
+        for j in range(3):
+            x[j] = line[j]
+        return 5
+    _LP_CANON_CB = lp_proto(lp_solve)
+    _LP_CB = None        # a later separator_solve() re-installs HiGHS
+    lib().ref_set_lp_solver(_LP_CANON_CB)
+    qp_proto = C.CFUNCTYPE(C.c_int, C.POINTER(RefQpModel), D, I, C.c_void_p)
+
+    def qp_solve(mp, x, sol_count, user):
+        m = mp.contents
+        nv, nl, nq = m.nvar, m.nlin, m.nquad
+        rec = dict(nvar=nv, nlin=nl, nquad=nq, Q=_arr(m.Q, (nv, nv)), c=_arr(m.c, (nv,)), c0=m.c0, A=_arr(m.A, (nl, nv)),
+                   sense=np.array([m.sense[i] for i in range(nl)]), rhs=_arr(m.rhs, (nl,)),
+                   Qc=_arr(m.Qc, (nq, nv, nv)), qc=_arr(m.qc, (nq, nv)), qsense=np.array([m.qsense[i] for i in range(nq)]),
+                   qrhs=_arr(m.qrhs, (nq,)), lb=_arr(m.lb, (nv,)), ub=_arr(m.ub, (nv,)), time_limit=m.time_limit)
+        status, xs = _solve_recorded(rec)
+        rec["status"], rec["x"] = status, xs
+        QP_MODELS.append(rec)
+        for j in range(nv):
+            x[j] = xs[j]
+        sol_count[0] = 1 if status == 2 else 0
+        return status
+    _QP_CB = qp_proto(qp_solve)
+    lib().ref_set_qp_solver.argtypes = [qp_proto, C.c_void_p]
+    lib().ref_set_qp_solver(_QP_CB, None)
+
+
+def qp_replan(batch, a: int, replans: int = 1, t_start: float = 1.25):
+    """The reference's PolySolverGurobi on agent `a` of a ReplanBatch, driven as Neptune drives it.
+    Returns (ok, coeff_out [3][8][4], times [n+1], objective, n_states); the models of every optimize() are in QP_MODELS."""
+    par = batch.par
+    N, M, NH, cap = par.num_of_agents, par.num_of_static_obst, batch.n_hull_slots, par.ent_cap
+    n = int(batch.n_int[a])
+    hp = _c(batch.hull_ptr[a * NH * 8:(a + 1) * NH * 8 + 1], np.int64)
+    arrs = dict(pb=_c(par.pb, np.float64), lim=_c([par.x_min, par.x_max, par.y_min, par.y_max, par.z_min, par.z_max], np.float64),
+                st_ptr=_c(batch.st_ptr, np.int64), st_xy=_c(batch.st_xy if len(batch.st_xy) else np.zeros((1, 2)), np.float64),
+                ci=_c(batch.coeff_init[a], np.float64), hxy=_c(batch.hull_xy if len(batch.hull_xy) else np.zeros((1, 2)), np.float64),
+                nih0=_c(batch.nih0[a], np.float64), ecnt=_c(batch.esv_cnt[a], np.int32), ealpha=_c(batch.esv_alpha[a], np.int32),
+                eact=_c(batch.esv_active[a], np.int32), bpc=_c(batch.bp_cnt, np.int32), bpx=_c(batch.bp_xy, np.float64))
+    co, times, obj, ns = np.zeros((3, 8, 4)), np.zeros(9), C.c_double(0), C.c_int(0)
+    f = lib().ref_qp_replan
+    f.restype = C.c_int
+    P, D, Ic = C.c_void_p, C.c_double, C.c_int
+    f.argtypes = [Ic, Ic, Ic, D, D, P, P, D, D, D, D, D, Ic, P, P, Ic, P, Ic, P, P, P, P, P, P, Ic, P, P, Ic, Ic, D, D, P, P,
+                  C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    ok = f(N, int(batch.agent_id[a]), par.num_pol, par.T_span, par.weight, _p(arrs["pb"]), _p(arrs["lim"]), par.v_max, par.a_max,
+           par.j_max, par.runtime_opt, par.tetherLength, M, _p(arrs["st_ptr"]), _p(arrs["st_xy"]), n, _p(arrs["ci"]), NH, _p(hp),
+           _p(arrs["hxy"]), _p(arrs["nih0"]), _p(arrs["ecnt"]), _p(arrs["ealpha"]), _p(arrs["eact"]), cap, _p(arrs["bpc"]),
+           _p(arrs["bpx"]), par.bp_max, replans, t_start, par.dc, _p(co), _p(times), C.byref(obj), C.byref(ns))
+    return bool(ok), co, times[:n + 1].copy(), obj.value, ns.value

@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 from neptune_b200 import config
+from neptune_b200.batch import ReplanResult
 from neptune_b200.scenes import make_scene
 from neptune_b200.search import static_longest_dist
 from tests import ref_pin_util as ref
@@ -567,3 +568,177 @@ def test_eigen_stand_in_semantics():
     assert np.array_equal(got["Q"], Q.ravel())
     assert np.array_equal(got["D_last"], [3, 6]) and np.array_equal(got["D_mean"], [2, 5]) and np.array_equal(got["g2"], [1, 2])
     assert got["norm"] == np.sqrt(18.0) and got["dot"] == 4.0 and got["abs"][0] == 0.75
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# The trajectory QP: the reference's own solver_gurobi_poly.cpp, model recorded through a Gurobi stand-in
+GOLDEN_QP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference", "ref_qp.npz")
+
+
+def _match_rows(Rr, Ro):
+    """Multiset comparison of constraint rows [a | rhs]: greedy nearest-row matching, returns the worst distance."""
+    assert Rr.shape == Ro.shape, (Rr.shape, Ro.shape)
+    used, worst = np.zeros(len(Ro), bool), 0.0
+    for r in Rr:
+        d = np.abs(Ro - r).max(axis=1)
+        d[used] = np.inf
+        k = int(np.argmin(d))
+        worst, used[k] = max(worst, d[k]), True
+    return worst / max(1.0, np.abs(Ro).max(initial=0.0))
+
+
+def check_recorded_model(oracle, b, a, rec, fallback, lines, line_ok, par):
+    """One GRBModel::optimize() of the reference against the oracle's restatement of the same model
+    (orc_export_qp): objective, every equality row in order, the inequality rows as a multiset, the quadratic row."""
+    n = int(b.n_int[a])
+    nv = 12 * n
+    mdl = oracle.export_qp(b, a, fallback, lines, line_ok)
+    # reference order: axis, interval, coefficient (setInitTrajectory :200-224); oracle order: interval, axis, coefficient
+    perm = np.array([ax * 4 * n + 4 * i + j for i in range(n) for ax in range(3) for j in range(4)])
+    # the 3 n O plane variables setHulls creates (:258-278) take part in nothing in linear mode
+    assert np.abs(rec["Q"][nv:]).max(initial=0) == 0 and np.abs(rec["Q"][:, nv:]).max(initial=0) == 0
+    assert np.abs(rec["A"][:, nv:]).max(initial=0) == 0 and np.abs(rec["c"][nv:]).max(initial=0) == 0
+    assert (rec["lb"] <= -1e100).all() and (rec["ub"] >= 1e100).all()             # free variables (:207-214)
+    Q = rec["Q"][:nv, :nv][np.ix_(perm, perm)]
+    scale = np.abs(mdl["P"]).max()
+    assert np.abs(Q + Q.T - mdl["P"]).max() <= 1e-12 * scale
+    assert np.abs(rec["c"][:nv][perm] - mdl["q"]).max() <= 1e-12 * max(1.0, np.abs(mdl["q"]).max())
+    assert abs(rec["c0"] - mdl["c0"]) <= 1e-12 * max(1.0, abs(mdl["c0"]))
+    A = rec["A"][:, :nv][:, perm]
+    eq, le, ge = rec["sense"] == b"=", rec["sense"] == b"<", rec["sense"] == b">"
+    Er, Eo = np.c_[A[eq], rec["rhs"][eq]], np.c_[mdl["Aeq"], mdl["beq"]]
+    assert Er.shape == Eo.shape == (9 * n + (0 if fallback else 6), nv + 1)
+    assert np.abs(Er - Eo).max() <= 1e-12 * max(1.0, np.abs(Eo).max())            # same rows in the same order
+    Gr = np.vstack([np.c_[A[le], rec["rhs"][le]], np.c_[-A[ge], -rec["rhs"][ge]]])
+    Go = np.c_[mdl["G"], mdl["h"]]
+    assert Gr.shape[0] == 48 * n + 4 * int((line_ok[:n] == 1).sum())
+    assert _match_rows(Gr, Go) <= 1e-11
+    # quadratic terminal row (:681-702): ||p_end - final_pos||^2 - 0.01 <= 0 iff the start is within 1 m of it
+    assert rec["nquad"] == int(mdl["has_qc"])
+    if rec["nquad"]:
+        T = par.T_span
+        qp = np.array([T ** 3, T * T, T, 1.0])
+        Qw, qw, cw = np.zeros((nv, nv)), np.zeros(nv), -0.01
+        for ax in range(3):
+            pf = float(qp @ b.coeff_init[a, ax, n - 1])
+            sl = slice(12 * (n - 1) + 4 * ax, 12 * (n - 1) + 4 * ax + 4)
+            Qw[sl, sl] += np.outer(qp, qp)
+            qw[sl] += -2.0 * pf * qp
+            cw += pf * pf
+        Qr = rec["Qc"][0][:nv, :nv][np.ix_(perm, perm)]
+        assert rec["qsense"][0] == b"<"
+        assert np.abs(0.5 * (Qr + Qr.T) - Qw).max() <= 1e-12 * np.abs(Qw).max()
+        assert np.abs(rec["qc"][0][:nv][perm] - qw).max() <= 1e-12 * max(1.0, np.abs(qw).max())
+        assert abs(-rec["qrhs"][0] - cw) <= 1e-12 * max(1.0, abs(cw))
+    assert abs(rec["time_limit"] - par.runtime_opt) < 1e-12                         # setMaxRuntime -> "TimeLimit" (:812)
+
+
+def run_reference_qp(oracle, b, a, ref, replans=1):
+    """The reference's solver on agent a: model checks on every optimize(), then (status, coeff, objective)."""
+    from tests import ref_pin_util as rp
+    rp.QP_MODELS.clear()
+    ok, co, times, obj, ns = rp.qp_replan(b, a, replans=replans)
+    per = len(rp.QP_MODELS) // replans
+    assert per in (1, 2) and per * replans == len(rp.QP_MODELS)
+    for k, rec in enumerate(rp.QP_MODELS):
+        check_recorded_model(oracle, b, a, rec, (k % per) == 1, ref.lines[a], ref.line_ok[a], b.par)
+    status = 0 if per == 1 else (1 if ok else 2)
+    n = int(b.n_int[a])
+    assert np.allclose(times, 1.25 + b.par.T_span * np.arange(n + 1)) and abs(ns - n * b.par.T_span / b.par.dc) <= 1.5
+    return status, co, obj
+
+
+QP_LIVE = ["single_1001", "mtlp5_2002", "obst8_3003", "mtlp5_crafted-ent0", "mtlp5_crafted-box", "mtlp5_crafted-n2box"]
+
+
+@needs_ref
+@pytest.mark.parametrize("name", QP_LIVE)
+def test_qp_model_matches_reference(oracle, name):
+    """PolySolverGurobi of the reference's own solver_gurobi_poly.cpp (setInitTrajectory :187-244, addObjective :322-383,
+    addConstraints :385-710, addEntangleConstraintForIJCase :715-784, optimize :804-887, generatePwpOut :889-936),
+    compiled unmodified with a recording Gurobi stand-in and driven as Neptune drives it (neptune.cpp:102-107,
+    :1514-1527): the model of every optimize() equals the oracle's restatement row for row (both solves, the quadratic
+    row, the tether rows of the crafted scenes), the status path (first solve / fallback / pwp_out = pwp_init) and the
+    optimiser's coefficients equal the oracle's."""
+    from tests import ref_pin_util as rp
+    from tests.golden_util import load
+    rp.install_qp_hooks(oracle)
+    par, b, z = load(os.path.join(os.path.dirname(GOLDEN_QP), "..", name + ".npz"))
+    ref = ReplanResult.empty(b)
+    assert oracle.replan_batch(b, ref, 2) == 0
+    agents = range(b.B) if b.B <= 5 else (0, 1, 4, 7)
+    for a in agents:
+        status, co, obj = run_reference_qp(oracle, b, a, ref)
+        assert status == ref.status[a], (name, a, status, ref.status[a])
+        n = int(b.n_int[a])
+        tol = (1e-6 if not z["has_qc"][a] else 1e-5) * max(1.0, np.abs(ref.coeff_out[a]).max())
+        assert np.abs(co[:, :n] - ref.coeff_out[a, :, :n]).max() <= tol, (name, a)
+        if status == 2:
+            assert np.array_equal(co[:, :n], b.coeff_init[a, :, :n])        # pwp_out_ = pwp_init_ (:858)
+        else:
+            assert abs(obj - ref.obj[a]) <= 1e-6 * max(1.0, abs(ref.obj[a]))
+
+
+@needs_ref
+def test_qp_reference_object_is_reusable(oracle):
+    """The solver object lives as long as the agent: a second replan on the same object builds the same model again --
+    resetCompleteModel (solver_gurobi_utils.hpp) removes the previous replan's variables and rows and, by Gurobi's lazy
+    update, not the ones setInitTrajectory / setHulls have just added."""
+    from tests import ref_pin_util as rp
+    from tests.golden_util import load
+    rp.install_qp_hooks(oracle)
+    par, b, z = load(os.path.join(os.path.dirname(GOLDEN_QP), "..", "mtlp5_2002.npz"))
+    ref = ReplanResult.empty(b)
+    assert oracle.replan_batch(b, ref, 2) == 0
+    for a in (1, 4):
+        status, co, obj = run_reference_qp(oracle, b, a, ref, replans=3)
+        assert status == ref.status[a]
+        n = int(b.n_int[a])
+        assert np.abs(co[:, :n] - ref.coeff_out[a, :, :n]).max() <= 1e-6 * max(1.0, np.abs(ref.coeff_out[a]).max())
+
+
+def test_qp_matches_reference_golden(oracle):
+    """The same comparison against outputs recorded from the reference's solver (tests/golden/make_ref_golden.py),
+    for machines without /root/reference: status path, coefficients, objective of every agent of every fixture."""
+    from tests.golden_util import golden_files, load
+    g = np.load(GOLDEN_QP)
+    n_agents = 0
+    for path in golden_files():
+        name = os.path.basename(path)[:-4]
+        par, b, z = load(path)
+        ref = ReplanResult.empty(b)
+        assert oracle.replan_batch(b, ref, 2) == 0
+        st, co, ob = g[name + "/status"], g[name + "/coeff"], g[name + "/obj"]
+        assert np.array_equal(st, ref.status), name
+        for a in range(b.B):
+            n = int(b.n_int[a])
+            tol = (1e-6 if not z["has_qc"][a] else 1e-5) * max(1.0, np.abs(co[a]).max())
+            assert np.abs(co[a, :, :n] - ref.coeff_out[a, :, :n]).max() <= tol, (name, a)
+            if st[a] < 2:
+                assert abs(ob[a] - ref.obj[a]) <= 1e-6 * max(1.0, abs(ob[a]))
+            n_agents += 1
+    assert n_agents >= 50
+
+
+@pytest.mark.gpu
+def test_gpu_qp_matches_reference_golden():
+    """The PRODUCT against the recordings of the reference's own solver, no oracle in between."""
+    from neptune_b200 import capi
+    from tests.golden_util import golden_files, load
+    g = np.load(GOLDEN_QP)
+    for path in golden_files():
+        name = os.path.basename(path)[:-4]
+        par, b, z = load(path)
+        s = capi.Solver(par)
+        if par.num_of_static_obst:
+            s.set_static(b.st_ptr, b.st_xy, z["strep"])
+        res = s.replan(b)
+        st, co, ob = g[name + "/status"], g[name + "/coeff"], g[name + "/obj"]
+        assert np.array_equal(res.status, st), name
+        for a in range(b.B):
+            n = int(b.n_int[a])
+            tol = (1e-6 if not z["has_qc"][a] else 1e-5) * max(1.0, np.abs(co[a]).max())
+            assert np.abs(res.coeff_out[a, :, :n] - co[a, :, :n]).max() <= tol, (name, a)
+            if st[a] < 2:
+                assert abs(res.obj[a] - ob[a]) <= 1e-6 * max(1.0, abs(ob[a]))
+        s.close()
