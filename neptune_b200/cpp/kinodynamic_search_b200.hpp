@@ -11,7 +11,13 @@
 // Two extensions replace non-deterministic state of the reference: setJerkOrder (the reference shuffles
 // all_combinations_ with a wall-clock seed, kinodynamic_search.cpp:321, :1462) and setMaxExpansions (open-list pops
 // that stand in for the wall-clock budget of setRunTime, :1646).
+//
+// Like poly_solver_b200.hpp this header defines the include guard of the reference's kinodynamic_search.hpp, so that
+// seen first (`g++ -include kinodynamic_search_b200.hpp`) it takes the reference class's place in neptune.cpp.
 #pragma once
+#ifndef KINODYNAMIC_SEARCH_HPP
+#define KINODYNAMIC_SEARCH_HPP  // include guard of the reference's header
+#endif
 #include <numeric>
 
 #include "poly_solver_b200.hpp"
@@ -26,7 +32,7 @@ public:
     par_ = nb_params();
     par_.num_pol = num_pol, par_.deg_pol = deg_pol, par_.num_agents = (int)pb.size(), par_.num_static = 0;
     par_.samples = num_sample_per_interval, par_.use_linear_constraints = 1, par_.T_span = T_span, par_.weight = 1.0;
-    par_.ent_cap = 48, par_.bp_max = 8, par_.ent_slots = 16, par_.ipm_max_iter = 60, par_.ipm_tol = 1e-9;
+    par_.ent_cap = 3 * (int)pb.size() + 16, par_.bp_max = 8, par_.ent_slots = 16, par_.ipm_max_iter = 60, par_.ipm_tol = 1e-9;
     sp_ = nb_search_params();
     sp_.num_samples = 5, sp_.j_max = 5.0, sp_.voxel_size = 0.2, sp_.bias = 1.0, sp_.goal_size = 0.5;
     sp_.enable_entangle_check = enable_entangle_check ? 1 : 0, sp_.use_not_reaching_soln = use_not_reaching_soln ? 1 : 0;
@@ -105,7 +111,124 @@ public:
     initial_ = initial_state, goal_ = goal, hulls_ = hulls, SPoC_ = SPoC, es_ = entangle_state, bend_ = bendPtsForAgents;
   }
 
+  // run() of the reference never throws; a library error (no device, a list beyond its storage) is reported as
+  // "no solution" (status 0, false) with the text kept in lastError()
   bool run(std::vector<Eigen::Vector3d>& result, int& status)
+  {
+    last_error_.clear();
+    try
+    {
+      return runImpl(result, status);
+    }
+    catch (const std::exception& e)
+    {
+      last_error_ = e.what();
+      std::fprintf(stderr, "KinodynamicSearch (neptune_b200): %s -- no solution returned\n", e.what());
+      status = 0;
+      pwp_out_.clear();
+      entStateVec_.clear();
+      return false;
+    }
+  }
+  const std::string& lastError() const { return last_error_; }
+  void clearProcess() {}  // the node pool lives in the library's workspace and is reset by every search (:1829-1858)
+
+  // KinodynamicSearch::generatePwpOut (kinodynamic_search.cpp:605-655): same sampling loop as the back end's
+  void generatePwpOut(mt::PieceWisePol& pwp_out, std::vector<mt::state>& traj_out, double t_start, double dc)
+  {
+    pwp_out = pwp_out_;
+    const int nt = (int)pwp_out.times.size(), n = nt - 1;
+    for (int i = 0; i < nt; i++) pwp_out.times[i] += t_start;
+    traj_out.clear();
+    double t = 0;
+    int i = 0;
+    while (i < n)
+    {
+      const double dt = t - i * par_.T_span;
+      mt::state st;
+      const Eigen::Matrix<double, 4, 1>* c[3] = { &pwp_out.coeff_x[i], &pwp_out.coeff_y[i], &pwp_out.coeff_z[i] };
+      for (int ax = 0; ax < 3; ax++)
+      {
+        const Eigen::Matrix<double, 4, 1>& q = *c[ax];
+        st.pos(ax) = q(0) * dt * dt * dt + q(1) * dt * dt + q(2) * dt + q(3);
+        st.vel(ax) = q(0) * 3 * dt * dt + q(1) * 2 * dt + q(2);
+        st.accel(ax) = q(0) * 6 * dt + q(1) * 2;
+        st.jerk(ax) = q(0) * 6;
+      }
+      traj_out.push_back(st);
+      t += dc;
+      if (t > (i + 1) * par_.T_span) i++;
+    }
+  }
+
+  // KinodynamicSearch::updateSPocAndbendPtsForAgent (:987-993): a late trajectory replaces the samples and the bend
+  // points the planner holds for that agent (Neptune::safetyCheckAfterReplan, neptune.cpp:737-742)
+  void updateSPocAndbendPtsForAgent(int idx, mt::SampledPointsofIntervals& SampledPtsForOne, std::vector<Eigen::Vector2d>& bendPtsForAgent)
+  {
+    if (idx >= (int)SPoC_.size()) SPoC_.resize(idx + 1);
+    if (idx >= (int)bend_.size()) bend_.resize(idx + 1);
+    SPoC_[idx] = SampledPtsForOne;
+    bend_[idx] = bendPtsForAgent;
+  }
+
+  // KinodynamicSearch::entangleCheckGivenPwp (:897-985), on the samples and bend points the planner holds; the state
+  // is advanced in place like the reference's argument.  A library error counts as "entangled" (the replan is dropped).
+  bool entangleCheckGivenPwp(mt::PieceWisePol& pwp, eu::ent_state& ent_state_begin)
+  {
+    try
+    {
+      ensure();
+      const int N = par_.num_agents, M = par_.num_static, NA = N + M, cap = par_.ent_cap, S = par_.samples, np = par_.num_pol;
+      const int n = (int)pwp.coeff_x.size();
+      if (n < 1 || n > NB_NPOL || (int)ent_state_begin.alphas.size() > cap) throw std::runtime_error("entangleCheckGivenPwp: input beyond storage");
+      std::vector<double> co(96, 0.0), samp((size_t)N * np * (S + 1) * 2, 0.0), bp_xy((size_t)N * par_.bp_max * 2, 0.0), beta(cap, 0.0);
+      std::vector<int32_t> cnt(2, 0), alpha((size_t)cap * 2, 0), bend(cap, 0), active(NA, 0), bp_cnt(N, 0);
+      std::vector<uint8_t> known(N, 0);
+      for (int i = 0; i < n; i++)
+        for (int r = 0; r < 4; r++)
+          co[4 * i + r] = pwp.coeff_x[i](r), co[32 + 4 * i + r] = pwp.coeff_y[i](r), co[64 + 4 * i + r] = pwp.coeff_z[i](r);
+      for (int j = 0; j < N && j < (int)SPoC_.size(); j++)
+        if (j != id_ - 1 && !SPoC_[j].empty())
+        {
+          known[j] = 1;
+          for (int i = 0; i < np && i < (int)SPoC_[j].size(); i++)
+            for (int s2 = 0; s2 <= S && s2 < SPoC_[j][i].cols(); s2++)
+              samp[(((size_t)j * np + i) * (S + 1) + s2) * 2] = SPoC_[j][i](0, s2), samp[(((size_t)j * np + i) * (S + 1) + s2) * 2 + 1] = SPoC_[j][i](1, s2);
+        }
+      for (int j = 0; j < N && j < (int)bend_.size(); j++)
+      {
+        if ((int)bend_[j].size() > par_.bp_max) throw std::runtime_error("bend-point list longer than bp_max");
+        bp_cnt[j] = (int)bend_[j].size();
+        for (int q = 0; q < bp_cnt[j]; q++) bp_xy[((size_t)j * par_.bp_max + q) * 2] = bend_[j][q](0), bp_xy[((size_t)j * par_.bp_max + q) * 2 + 1] = bend_[j][q](1);
+      }
+      eu::ent_state& e = ent_state_begin;
+      cnt[0] = (int)e.alphas.size(), cnt[1] = (int)e.bendPointsIdx.size();
+      for (size_t q = 0; q < e.alphas.size(); q++) alpha[2 * q] = e.alphas[q](0), alpha[2 * q + 1] = e.alphas[q](1);
+      for (size_t q = 0; q < e.betas.size() && q < (size_t)cap; q++) beta[q] = e.betas[q];
+      for (size_t q = 0; q < e.bendPointsIdx.size(); q++) bend[q] = e.bendPointsIdx[q];
+      for (int q = 0; q < NA && q < (int)e.active_cases.size(); q++) active[q] = e.active_cases[q];
+      int32_t agent_id = id_, n_int = n, entangled = 0;
+      nb_ent_state st;
+      st.cnt = cnt.data(), st.alpha = alpha.data(), st.beta = beta.data(), st.bend = bend.data(), st.active = active.data();
+      nb_detail::check(nb_entangle_check_batch(h_, 1, NB_HOST, &agent_id, known.data(), bp_cnt.data(), bp_xy.data(), st, &n_int,
+                                               co.data(), samp.data(), 1, &entangled, nullptr),
+                       "nb_entangle_check_batch");
+      e.alphas.clear(), e.betas.clear(), e.bendPointsIdx.clear();
+      for (int q = 0; q < cnt[0]; q++) e.alphas.push_back(Eigen::Vector2i(alpha[2 * q], alpha[2 * q + 1])), e.betas.push_back(beta[q]);
+      for (int q = 0; q < cnt[1]; q++) e.bendPointsIdx.push_back(bend[q]);
+      e.active_cases.assign(active.begin(), active.end());
+      return entangled != 0;
+    }
+    catch (const std::exception& ex)
+    {
+      last_error_ = ex.what();
+      std::fprintf(stderr, "KinodynamicSearch (neptune_b200): %s -- reported as entangled\n", ex.what());
+      return true;
+    }
+  }
+
+private:
+  bool runImpl(std::vector<Eigen::Vector3d>& result, int& status)
   {
     ensure();
     result.clear();
@@ -194,6 +317,8 @@ public:
     return true;
   }
 
+
+public:
   void getPwpOut_0tstart(mt::PieceWisePol& pwp_out) { pwp_out = pwp_out_; }
   void getEntStateVector(std::vector<eu::ent_state>& entStateVec) { entStateVec = entStateVec_; }
   void getRuntime(double& runtime_this_round, double& time_spent_contact_pt, int& node_used_num)
@@ -229,6 +354,7 @@ private:
   nb_search_params sp_;
   nb_handle* h_ = nullptr;
   bool configured_ = false;
+  std::string last_error_;
   int id_, node_used_num_ = 0;
   double max_runtime_ = 0.5;
   std::vector<Eigen::Vector2d> pb_;

@@ -1,19 +1,28 @@
 // nb_types.hpp -- the reference's value types on the back-end boundary.
 //
-// With Eigen available (<Eigen/Dense>) these are exactly the reference's typedefs
-// (neptune/include/mader_types.hpp:20-30, :462-548; neptune/include/entangle_utils.hpp:23-29), so
-// neptune.cpp recompiles unchanged against poly_solver_b200.hpp.  Without Eigen (this build image has
-// none) a minimal stand-in with the same member access syntax is used so the shim can be compiled
-// and tested.
+// Three build situations, chosen by what is on the include path:
+//  1. the reference's own headers (neptune/include/mader_types.hpp, entangle_utils.hpp) are reachable: they are
+//     included and NOTHING they define is defined here -- this is the drop-in build of neptune.cpp;
+//  2. only Eigen (<Eigen/Dense>) is reachable: the reference's typedefs are restated on real Eigen
+//     (mader_types.hpp:20-30, :462-548; entangle_utils.hpp:23-29);
+//  3. neither (this build image): a minimal Eigen stand-in with the same member access syntax, so that the shim can be
+//     compiled and tested.
 #pragma once
 #include <vector>
 
 #if defined(__has_include)
+#if __has_include("mader_types.hpp") && __has_include("entangle_utils.hpp")
+#define NB_HAVE_REFERENCE_TYPES 1
+#endif
 #if __has_include(<Eigen/Dense>)
 #define NB_HAVE_EIGEN 1
 #endif
 #endif
 
+#ifdef NB_HAVE_REFERENCE_TYPES
+#include "mader_types.hpp"      // mt::PieceWisePol, mt::state, hull and sample typedefs
+#include "entangle_utils.hpp"   // eu::ent_state
+#else
 #ifdef NB_HAVE_EIGEN
 #include <Eigen/Dense>
 #else
@@ -116,3 +125,4 @@ typedef Eigen::Matrix<double, 2, Eigen::Dynamic> PointsofInterval;       // made
 typedef std::vector<PointsofInterval> SampledPointsofIntervals;           // :26, one 2 x (S+1) matrix per interval
 typedef std::vector<SampledPointsofIntervals> SampledPointsofCurves;      // :30, indexed by agent id - 1, empty = unknown
 }  // namespace mt
+#endif  // NB_HAVE_REFERENCE_TYPES

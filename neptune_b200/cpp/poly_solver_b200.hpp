@@ -8,9 +8,19 @@
 // and error behaviour: optimize() returns false and leaves pwp_out = pwp_init when both solves fail;
 // solveModel() returns false for inseparable sets.  The header leaks no Gurobi types, so it is source-
 // not ABI-compatible: relink neptune_test_node against libneptune_b200.so.
+//
+// Coexistence with the reference's tree: this header defines the include guard of neptune/include/solver_gurobi_poly.hpp
+// and is meant to be seen first (`g++ -include poly_solver_b200.hpp`, or one edited #include in neptune.hpp), so the
+// reference's own header -- and with it gurobi_c++.h -- drops out without touching a reference file; separator.hpp
+// (#pragma once, found through the include path) is shadowed by neptune_b200/cpp/dropin/separator.hpp.
 #pragma once
+#ifndef SOLVER_GUROBI_POLY_HPP
+#define SOLVER_GUROBI_POLY_HPP  // include guard of the reference's header: keeps it out of the translation unit
+#endif
+#include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -37,7 +47,9 @@ public:
     par_.num_pol = num_pol, par_.deg_pol = deg_pol, par_.num_agents = (int)pb.size(), par_.num_static = 0;
     par_.samples = 3, par_.use_linear_constraints = use_linear_constraints ? 1 : 0;
     par_.T_span = T_span, par_.weight = weight_term;
-    par_.ent_cap = 48, par_.bp_max = 8, par_.ent_slots = 16, par_.ipm_max_iter = 60, par_.ipm_tol = 1e-9;
+    // storage capacities follow the semantic bounds of the reference's vectors and grow on demand (optimize):
+    // an alphas list holds at most 3 (N + M) entries (kinodynamic_search.cpp:938-942)
+    par_.ent_cap = 3 * (int)pb.size() + 16, par_.bp_max = 8, par_.ent_slots = 16, par_.ipm_max_iter = 60, par_.ipm_tol = 1e-9;
     par_.drone_radius = 0.0, par_.tether_length = 0.0;
     (void)rad_term;  // rad_term_ is stored but unused by the reference in linear mode (:701-706)
   }
@@ -48,7 +60,19 @@ public:
   PolySolverGurobi(const PolySolverGurobi&) = delete;
   PolySolverGurobi& operator=(const PolySolverGurobi&) = delete;
 
-  void setMaxRuntime(double runtime) { max_runtime_ = runtime; }  // the IPM is capped by iterations instead
+  // Gurobi "TimeLimit" (:811-812).  The interior-point kernel is capped by iterations: an iteration costs about 20 us
+  // on a B200, so the 60-iteration cap (1.2 ms) is inside every budget the shipped YAMLs set (15 - 80 ms); a smaller
+  // budget lowers the cap proportionally.  Like a barrier solve that hits TimeLimit before its first incumbent
+  // (SolCount == 0, :832-836), a solve that hits the cap counts as failed.
+  void setMaxRuntime(double runtime)
+  {
+    max_runtime_ = runtime;
+    const int cap = (int)(runtime / 20e-6);
+    const int it = cap < 5 ? 5 : (cap > 60 ? 60 : cap);
+    if (it != par_.ipm_max_iter) par_.ipm_max_iter = it, reset();
+  }
+  // stored and never read by the reference's linear mode either (solver_gurobi_poly.cpp:290-305, :786-801)
+  void setBetasVector(std::vector<std::vector<Eigen::Vector3d>>& vecOfAgents) { vecOfAgentsBetas_ = vecOfAgents; }
   void setMaxValues(double x_min, double x_max, double y_min, double y_max, double z_min, double z_max, double v_max,
                     double a_max, double j_max)
   {
@@ -72,6 +96,7 @@ public:
       st_ptr_.push_back((int64_t)st_xy_.size() / 2);
     }
     par_.num_static = (int)convexHullOfStaticObs.size();
+    par_.ent_cap = 3 * (par_.num_agents + par_.num_static) + 16;
     reset();
   }
   void setInitTrajectory(mt::PieceWisePol pwp_init)
@@ -87,7 +112,53 @@ public:
     bendPtsForAgents_ = bendPtsForAgents;
   }
 
+  // Failure behaviour of the reference: optimize() == false with pwp_out_ = pwp_init_, nothing thrown (:856-859; the
+  // caller flies the front-end path, neptune.cpp:1519-1527).  Library errors (no device, out of memory) take the same
+  // exit, with the text kept in lastError(); invalid input (n outside 1..8) is reported the same way.
   bool optimize(double& objective_value)
+  {
+    last_error_.clear();
+    try
+    {
+      return optimizeImpl(objective_value);
+    }
+    catch (const std::exception& e)
+    {
+      last_error_ = e.what();
+      std::fprintf(stderr, "PolySolverGurobi (neptune_b200): %s -- returning the initial trajectory\n", e.what());
+      pwp_out_ = pwp_init_;
+      last_status_ = NB_STATUS_FAILED;
+      total_replannings_++;
+      return false;
+    }
+  }
+  const std::string& lastError() const { return last_error_; }
+
+private:
+  bool optimizeImpl(double& objective_value)
+  {
+    const int n = (int)pwp_init_.coeff_x.size();
+    if (n < 1 || n > NB_NPOL) throw std::runtime_error("pwp_init with " + std::to_string(n) + " intervals (1..8 supported)");
+    for (auto& bl : bendPtsForAgents_)   // lists longer than the current storage: rebuild the handle once, larger
+      if ((int)bl.size() > par_.bp_max) par_.bp_max = 2 * (int)bl.size(), reset();
+    for (auto& e : entStateVec_)
+      if ((int)e.alphas.size() > par_.ent_cap) par_.ent_cap = 2 * (int)e.alphas.size(), reset();
+    for (int attempt = 0;; attempt++)
+    {
+      const int rc = replanOnce(objective_value);
+      if (rc == NB_OK) break;
+      if (rc == NB_ERR_CAPACITY && attempt < 4)
+      {  // more tether constraints in one interval than LP slots: the reference's vectors just grow
+        par_.ent_slots *= 2, reset();
+        continue;
+      }
+      throw std::runtime_error(std::string("nb_replan_batch: ") + nb_last_error());
+    }
+    if (last_status_ == NB_STATUS_FAILED) return false;  // pwp_out_ == pwp_init_ (:856-859)
+    solutions_found_++;
+    return true;
+  }
+  int replanOnce(double& objective_value)
   {
     ensure();
     const int N = par_.num_agents, M = par_.num_static, NA = N + M, cap = par_.ent_cap;
@@ -121,7 +192,6 @@ public:
     for (int i = 0; i <= n && i < (int)entStateVec_.size(); i++)
     {
       const eu::ent_state& e = entStateVec_[i];
-      if ((int)e.alphas.size() > cap) throw std::runtime_error("ent_state longer than ent_cap");
       esv_cnt[2 * i] = (int)e.alphas.size(), esv_cnt[2 * i + 1] = (int)e.bendPointsIdx.size();
       for (size_t q = 0; q < e.alphas.size(); q++)
         esv_alpha[((size_t)i * cap + q) * 2] = e.alphas[q](0), esv_alpha[((size_t)i * cap + q) * 2 + 1] = e.alphas[q](1);
@@ -129,7 +199,6 @@ public:
     }
     for (int j = 0; j < N && j < (int)bendPtsForAgents_.size(); j++)
     {
-      if ((int)bendPtsForAgents_[j].size() > par_.bp_max) throw std::runtime_error("bend-point list longer than bp_max");
       bp_cnt[j] = (int)bendPtsForAgents_[j].size();
       for (int q = 0; q < bp_cnt[j]; q++)
         bp_xy[((size_t)j * par_.bp_max + q) * 2] = bendPtsForAgents_[j][q](0),
@@ -143,7 +212,8 @@ public:
     a.hull_cnt = nullptr, a.nih0 = nih0.data(), a.esv_cnt = esv_cnt.data(), a.esv_alpha = esv_alpha.data();
     a.esv_active = esv_active.data(), a.bp_cnt = bp_cnt.data(), a.bp_xy = bp_xy.data();
     a.coeff_out = co, a.obj = &obj, a.status = &status, a.iters = iters, a.lines = nullptr, a.line_ok = nullptr;
-    nb_detail::check(nb_replan_batch(h_, &a, nullptr), "nb_replan_batch");
+    const int rc = nb_replan_batch(h_, &a, nullptr);
+    if (rc != NB_OK) return rc;
     total_replannings_++;
     pwp_out_ = pwp_init_;
     for (int i = 0; i < n; i++)
@@ -153,11 +223,11 @@ public:
       pwp_out_.coeff_z[i] = Eigen::Matrix<double, 4, 1>(co[64 + 4 * i], co[64 + 4 * i + 1], co[64 + 4 * i + 2], co[64 + 4 * i + 3]);
     }
     last_status_ = status;
-    if (status == NB_STATUS_FAILED) return false;  // pwp_out_ == pwp_init_ (:856-859)
-    solutions_found_++;
-    objective_value = obj;
-    return true;
+    if (status != NB_STATUS_FAILED) objective_value = obj;
+    return NB_OK;
   }
+
+public:
 
   // solver_gurobi_poly.cpp:889-936
   void generatePwpOut(mt::PieceWisePol& pwp_out, std::vector<mt::state>& traj_out, double t_start, double dc)
@@ -213,6 +283,8 @@ private:
   mt::ConvexHullsOfCurves_Std2d hulls_, hullsNoInflation_;
   std::vector<eu::ent_state> entStateVec_;
   std::vector<std::vector<Eigen::Vector2d>> bendPtsForAgents_;
+  std::vector<std::vector<Eigen::Vector3d>> vecOfAgentsBetas_;
+  std::string last_error_;
   double max_runtime_ = 0.05;
   int total_replannings_ = 0, solutions_found_ = 0, last_status_ = -1;
 };
@@ -251,10 +323,12 @@ public:
     return run(n, pointsA, nullptr, pointsB);
   }
   long int getNumOfLPsRun() { return num_; }
+  double meanSolveTimeMs() { return num_ > 0 ? total_ms_ / (double)num_ : 0.0; }  // separator.hpp:41
 
 private:
   bool run(Eigen::Vector3d& out, const mt::Polygon_Std& A, const mt::Polygon_Std* Ap, const mt::Polygon_Std& B)
   {
+    const auto t0 = std::chrono::steady_clock::now();
     std::vector<double> a, b;
     for (int c = 0; c < A.cols(); c++) a.push_back(A(0, c)), a.push_back(A(1, c));
     if (Ap)
@@ -263,12 +337,19 @@ private:
     const int64_t ap[2] = { 0, (int64_t)a.size() / 2 }, bp[2] = { 0, (int64_t)b.size() / 2 };
     double line[3];
     uint8_t ok = 0;
-    nb_detail::check(nb_separate_batch(h_, 1, NB_HOST, ap, a.data(), bp, b.data(), 0, line, &ok, nullptr), "nb_separate_batch");
+    const int rc = nb_separate_batch(h_, 1, NB_HOST, ap, a.data(), bp, b.data(), 0, line, &ok, nullptr);
     num_++;
+    total_ms_ += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (rc != NB_OK)
+    {  // the reference reports an LP it cannot solve as "not separable" (separator_glpk.cpp:340-346); so does a library error
+      std::fprintf(stderr, "separator::Separator (neptune_b200): %s\n", nb_last_error());
+      return false;
+    }
     out(0) = line[0], out(1) = line[1], out(2) = line[2];
     return ok != 0;
   }
   nb_handle* h_ = nullptr;
   long int num_ = 0;
+  double total_ms_ = 0.0;
 };
 }  // namespace separator

@@ -43,15 +43,53 @@ int main(int argc, char** argv)
         if (fscanf(f, "%lf %lf", &p(0, c), &p(1, c)) != 2) return 2;
       hulls[s].push_back(p);
     }
+  // optional section "ENT": entStateVec (alphas + active cases per interval), bend points per agent and column 0 of
+  // hullsNoInflation -- the inputs of addEntangleConstraintForIJCase (solver_gurobi_poly.cpp:620-642, :715-784)
+  std::vector<eu::ent_state> esv(n + 1);
+  for (auto& e : esv) e.active_cases.assign(N, 0);
+  std::vector<std::vector<Eigen::Vector2d>> bend(N);
+  for (int j = 0; j < N; j++) bend[j].push_back(pb[j]);
+  char tag[8] = { 0 };
+  if (fscanf(f, "%7s", tag) == 1 && tag[0] == 'E')
+  {
+    for (int i = 0; i <= n; i++)
+    {
+      int na;
+      if (fscanf(f, "%d", &na) != 1) return 2;
+      for (int q = 0; q < na; q++)
+      {
+        int a0, a1;
+        if (fscanf(f, "%d %d", &a0, &a1) != 2) return 2;
+        esv[i].alphas.push_back(Eigen::Vector2i(a0, a1));
+        esv[i].betas.push_back(0.0);
+      }
+      for (int j = 0; j < N; j++)
+        if (fscanf(f, "%d", &esv[i].active_cases[j]) != 1) return 2;
+    }
+    for (int j = 0; j < N; j++)
+    {
+      int nb;
+      if (fscanf(f, "%d", &nb) != 1) return 2;
+      bend[j].assign(nb, Eigen::Vector2d(0, 0));
+      for (int q = 0; q < nb; q++)
+        if (fscanf(f, "%lf %lf", &bend[j][q](0), &bend[j][q](1)) != 2) return 2;
+    }
+    for (int j = 0; j < N; j++)
+      for (int i = 0; i < n; i++)
+      {
+        int has;
+        double x = 0, y = 0;
+        if (fscanf(f, "%d %lf %lf", &has, &x, &y) != 3) return 2;
+        mt::Polygon_Std p(2, has ? 1 : 0);
+        if (has) p(0, 0) = x, p(1, 0) = y;
+        nih[j].push_back(p);
+      }
+  }
   fclose(f);
   PolySolverGurobi solver(8, 3, id, T, pb, W, 0.5, true);
   solver.setMaxValues(lim[0], lim[1], lim[2], lim[3], lim[4], lim[5], vmax, amax, 5.0);
   solver.setMaxRuntime(0.05);
   solver.setTetherLength(40.0);
-  std::vector<eu::ent_state> esv(n + 1);
-  for (auto& e : esv) e.active_cases.assign(N, 0);
-  std::vector<std::vector<Eigen::Vector2d>> bend(N);
-  for (int j = 0; j < N; j++) bend[j].push_back(pb[j]);
   solver.setInitTrajectory(pwp);
   solver.setHulls(hulls);
   solver.setHullsNoInflation(nih);

@@ -229,48 +229,110 @@ def test_replan_cycle_matches_oracle_composite(capi, oracle, cfg, seed):
     torch.cuda.synchronize()
 
 
-def test_cpp_shim_polysolvergurobi_and_separator(capi, oracle, tmp_path):
-    """The C++ drop-in classes (PolySolverGurobi / separator::Separator with the reference's method
-    names and call order) through the C-ABI, against the oracle on the same agent."""
+def _shim_input(par, b, a, with_ent):
+    """Text input of tests/cpp/test_shim.cpp for agent a of a batch."""
+    n, N, NH = int(b.n_int[a]), par.num_of_agents, b.n_hull_slots
+    lines = [f"{N} {int(b.agent_id[a])} {n} {NH} {par.T_span!r} {par.weight!r}",
+             " ".join(repr(float(v)) for v in (par.x_min, par.x_max, par.y_min, par.y_max, par.z_min, par.z_max)),
+             f"{par.v_max!r} {par.a_max!r}"]
+    lines += [f"{float(p[0])!r} {float(p[1])!r}" for p in np.asarray(par.pb, float)]
+    for ax in range(3):
+        for i in range(n):
+            lines.append(" ".join(repr(float(v)) for v in b.coeff_init[a, ax, i]))
+    for s in range(NH):
+        for i in range(n):
+            k = (a * NH + s) * 8 + i
+            pts = b.hull_xy[b.hull_ptr[k]:b.hull_ptr[k + 1]]
+            lines.append(str(len(pts)) + " " + " ".join(f"{float(p[0])!r} {float(p[1])!r}" for p in pts))
+    if with_ent:
+        lines.append("ENT")
+        for i in range(n + 1):
+            na = int(b.esv_cnt[a, i, 0])
+            lines.append(str(na) + " " + " ".join(f"{int(x)} {int(y)}" for x, y in b.esv_alpha[a, i, :na]))
+            lines.append(" ".join(str(int(v)) for v in b.esv_active[a, i, :N]))
+        for j in range(N):
+            nb = int(b.bp_cnt[j])
+            lines.append(str(nb) + " " + " ".join(f"{float(p[0])!r} {float(p[1])!r}" for p in b.bp_xy[j, :nb]))
+        for j in range(N):
+            for i in range(n):
+                x, y = b.nih0[a, j, i]
+                lines.append("0 0 0" if np.isnan(x) else f"1 {float(x)!r} {float(y)!r}")
+    return "\n".join(lines) + "\n"
+
+
+def _shim_binaries():
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = os.path.join(root, "tests", "cpp", "_build", "test_shim")
-    if not os.path.exists(exe):
+    bd = os.path.join(root, "tests", "cpp", "_build")
+    if not os.path.exists(os.path.join(bd, "test_shim")):
         subprocess.run(["make", "-C", os.path.join(root, "tests", "cpp")], check=True, capture_output=True)
+    # test_shim_ref: the same program compiled BESIDE the reference's own headers (tests/cpp/compile_against_reference.cpp);
+    # built where /root/reference exists and shipped with the tree
+    return [os.path.join(bd, x) for x in ("test_shim", "test_shim_ref") if os.path.exists(os.path.join(bd, x))]
+
+
+def _run_shim(exe, text, tmp_path, tag):
+    import subprocess
+    fn = tmp_path / f"{tag}.txt"
+    fn.write_text(text)
+    return subprocess.run([exe, str(fn)], check=True, capture_output=True, text=True).stdout.split("\n")
+
+
+def test_cpp_shim_polysolvergurobi_and_separator(capi, oracle, tmp_path):
+    """The C++ drop-in classes (PolySolverGurobi / separator::Separator with the reference's method
+    names and call order) through the C-ABI, against the oracle on the same agent -- with the repo's stand-in types and,
+    where the binary was built, with the reference's own mader_types.hpp / entangle_utils.hpp in the translation unit."""
     par = config("mtlp5")
     sc = make_scene(par, 2002, sync=False)
     b = sc.batch
     ref = ReplanResult.empty(b)
     assert oracle.replan_batch(b, ref, 1) == 0
-    for a in (0, 2):
-        n, N, NH = int(b.n_int[a]), par.num_of_agents, b.n_hull_slots
-        lines = [f"{N} {int(b.agent_id[a])} {n} {NH} {par.T_span!r} {par.weight!r}",
-                 " ".join(repr(float(v)) for v in (par.x_min, par.x_max, par.y_min, par.y_max, par.z_min, par.z_max)),
-                 f"{par.v_max!r} {par.a_max!r}"]
-        lines += [f"{float(p[0])!r} {float(p[1])!r}" for p in np.asarray(par.pb, float)]
-        for ax in range(3):
-            for i in range(n):
-                lines.append(" ".join(repr(float(v)) for v in b.coeff_init[a, ax, i]))
-        for s in range(NH):
-            for i in range(n):
-                k = (a * NH + s) * 8 + i
-                pts = b.hull_xy[b.hull_ptr[k]:b.hull_ptr[k + 1]]
-                lines.append(str(len(pts)) + " " + " ".join(f"{float(p[0])!r} {float(p[1])!r}" for p in pts))
-        fn = tmp_path / f"agent{a}.txt"
-        fn.write_text("\n".join(lines) + "\n")
-        out = subprocess.run([exe, str(fn)], check=True, capture_output=True, text=True).stdout.split("\n")
-        ok, status, obj, ntraj = out[0].split()
-        assert int(status) == ref.status[a] and int(ok) == int(ref.status[a] != 2)
+    exes = _shim_binaries()
+    assert exes
+    for exe in exes:
+        for a in (0, 2):
+            n, NH = int(b.n_int[a]), b.n_hull_slots
+            out = _run_shim(exe, _shim_input(par, b, a, False), tmp_path, f"agent{a}")
+            ok, status, obj, ntraj = out[0].split()
+            assert int(status) == ref.status[a] and int(ok) == int(ref.status[a] != 2)
+            co = np.array([[float(v) for v in ln.split()] for ln in out[1:1 + 3 * n]]).reshape(3, n, 4)
+            assert np.abs(co - ref.coeff_out[a, :, :n]).max() <= 1e-6 * max(1.0, np.abs(ref.coeff_out[a]).max())
+            assert abs(float(obj) - ref.obj[a]) <= 1e-8 * max(1.0, abs(ref.obj[a]))
+            assert abs(int(ntraj) - n * par.T_span / par.dc) <= 1.5
+            s_ok = int(out[1 + 3 * n].split()[0])      # separator::Separator::solveModel on hulls[0][0]
+            k0 = a * NH * 8
+            first = b.hull_xy[b.hull_ptr[k0]:b.hull_ptr[k0 + 1]]
+            far = np.array([[100.0, 100.0], [101.0, 100.0], [101.0, 101.0], [100.0, 101.0]])
+            assert s_ok == int(len(first) > 0 and oracle.separate(first, far)[0])
+
+
+def test_cpp_shim_tether_constraints_and_failure_path(capi, oracle, tmp_path):
+    """Through the C++ drop-in: the crafted tether-constraint scene (addEntangleConstraintForIJCase) equals the oracle,
+    and an infeasible replan returns optimize() == false with pwp_out == pwp_init (solver_gurobi_poly.cpp:856-859)."""
+    from tests import crafted
+    for exe in _shim_binaries():
+        par, b = crafted.ent_lp_batch(0)
+        ref = ReplanResult.empty(b)
+        assert oracle.replan_batch(b, ref, 1) == 0
+        plain = ReplanResult.empty(b)
+        import dataclasses
+        no_ent = dataclasses.replace(b, esv_active=np.zeros_like(b.esv_active), esv_cnt=np.zeros_like(b.esv_cnt))
+        assert oracle.replan_batch(no_ent, plain, 1) == 0
+        a, n = 0, int(b.n_int[0])
+        out = _run_shim(exe, _shim_input(par, b, a, True), tmp_path, "ent")
+        ok, status, obj, _ = out[0].split()
         co = np.array([[float(v) for v in ln.split()] for ln in out[1:1 + 3 * n]]).reshape(3, n, 4)
+        assert int(ok) == 1 and int(status) == ref.status[a]
         assert np.abs(co - ref.coeff_out[a, :, :n]).max() <= 1e-6 * max(1.0, np.abs(ref.coeff_out[a]).max())
-        assert abs(float(obj) - ref.obj[a]) <= 1e-8 * max(1.0, abs(ref.obj[a]))
-        assert abs(int(ntraj) - n * par.T_span / par.dc) <= 1.5
-        s_ok = int(out[1 + 3 * n].split()[0])      # separator::Separator::solveModel on hulls[0][0]
-        k0 = a * NH * 8
-        first = b.hull_xy[b.hull_ptr[k0]:b.hull_ptr[k0 + 1]]
-        far = np.array([[100.0, 100.0], [101.0, 100.0], [101.0, 101.0], [100.0, 101.0]])
-        assert s_ok == int(len(first) > 0 and oracle.separate(first, far)[0])
+        # the tether rows matter in this scene: without them the optimum is a different one
+        assert np.abs(ref.coeff_out[a] - plain.coeff_out[a]).max() > 1e-4
+        par, b = crafted.infeasible_batch("box")
+        out = _run_shim(exe, _shim_input(par, b, 2, False), tmp_path, "box")
+        ok, status, obj, _ = out[0].split()
+        n = int(b.n_int[2])
+        co = np.array([[float(v) for v in ln.split()] for ln in out[1:1 + 3 * n]]).reshape(3, n, 4)
+        assert int(ok) == 0 and int(status) == 2 and np.array_equal(co, b.coeff_init[2, :, :n])
 
 
 def test_entangle_random_walks_bend_points(capi, oracle):
