@@ -192,6 +192,6 @@ def test_dropin_headers_compile_beside_the_reference():
     assert r.returncode == 0, r.stdout + r.stderr
     assert os.path.exists(exe)
     syms = subprocess.run(["nm", "-C", exe], capture_output=True, text=True).stdout
-    for needle in ("PolySolverGurobi::optimize", "KinodynamicSearch::run", "separator::Separator::", "nb_replan_batch"):
+    for needle in ("PolySolverGurobi::optimize", "KinodynamicSearch::run", "nb_separate_batch", "nb_replan_batch", "nb_search_batch"):
         assert needle in syms, needle
     assert "GRBModel" not in syms and "glp_" not in syms     # neither Gurobi nor GLPK is referenced any more
