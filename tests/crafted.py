@@ -25,7 +25,12 @@ def ent_lp_batch(variant: int = 0, ent_slots: int = 16):
                1, 2 and 3 so that every skip rule (k == case_id) is exercised;
     variant 1: the same for EVERY planning agent, tethers with 2..4 bend points, one tether far away (distance gate
                :743-745 rejects its segments) and one agent with case id 0 ("not our concern", :632).
+    variant 2: ONE tether (agent 1, case id 5, bend points base -> P1 -> P2) whose segment P1-P2 lies where agent 0's
+               unconstrained optimum wants to go (found by search, hard-coded): its rows are ACTIVE at the optimum, the
+               optimiser's answer moves by ~0.5 m -- the test that the tether rows really enter the QP.
     Returns (par, batch)."""
+    if variant == 2:
+        return _binding_tether_batch(ent_slots)
     par = dataclasses.replace(config("mtlp5"), ent_slots=ent_slots)
     par.pb = config("mtlp5").pb
     sc = make_scene(par, 2002, sync=False)
@@ -61,6 +66,29 @@ def ent_lp_batch(variant: int = 0, ent_slots: int = 16):
                               nih0=np.ascontiguousarray(nih0))
     out.validate()
     return par, out
+
+
+def _binding_tether_batch(ent_slots: int):
+    par, b = ent_lp_batch(0, ent_slots)      # positions (nih0) of the other agents as in variant 0
+    a, me = 0, int(b.agent_id[0]) - 1
+    j = [jj for jj in range(par.num_of_agents) if jj != me][0]
+    bp_cnt, bp_xy = b.bp_cnt.copy(), b.bp_xy.copy()
+    c, dv = np.array([3.24255028, -7.07521061]), np.array([1.16518879, 0.90327916])
+    bp_cnt[j] = 3
+    bp_xy[j, 1], bp_xy[j, 2] = c + dv, c - dv
+    act, cnt, alpha = b.esv_active.copy(), b.esv_cnt.copy(), b.esv_alpha.copy()
+    act[a] = 0
+    act[a, :, j] = 1
+    cnt[a, :, 0] = 1
+    alpha[a, :, 0] = [j + 1, 5]
+    out = dataclasses.replace(b, par=par, esv_active=act, esv_cnt=cnt, esv_alpha=alpha, bp_cnt=bp_cnt, bp_xy=bp_xy)
+    out.validate()
+    return par, out
+
+
+def without_tether_rows(b):
+    """The same batch with every active case cleared (no addEntangleConstraintForIJCase call)."""
+    return dataclasses.replace(b, esv_active=np.zeros_like(b.esv_active), esv_cnt=np.zeros_like(b.esv_cnt))
 
 
 def infeasible_batch(kind: str):

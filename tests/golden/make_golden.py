@@ -24,7 +24,7 @@ CASES = [("single", 1001, dict(n_fixed=3)), ("mtlp5", 2002, dict(sync=False)), (
          ("obst8", 3003, dict(sync=False)), ("obst8", 3004, dict(sync=False)),
          # crafted inputs (tests/crafted.py) for the branches no generated scene reaches: non-entangling lines
          # (solver_gurobi_poly.cpp:715-784) and the failure path pwp_out = pwp_init (:856-859)
-         ("mtlp5", "crafted-ent0", None), ("mtlp5", "crafted-ent1", None),
+         ("mtlp5", "crafted-ent0", None), ("mtlp5", "crafted-ent1", None), ("mtlp5", "crafted-ent2", None),
          ("mtlp5", "crafted-box", None), ("mtlp5", "crafted-vel", None), ("mtlp5", "crafted-n2box", None)]
 BATCH_KEYS = ("agent_id", "n_int", "coeff_init", "hull_ptr", "hull_xy", "nih0", "st_ptr", "st_xy", "esv_cnt",
               "esv_alpha", "esv_active", "bp_cnt", "bp_xy")

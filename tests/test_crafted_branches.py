@@ -99,6 +99,32 @@ def test_non_entangling_lines_oracle_emulation_highs(oracle, variant):
     assert n_checked >= 2
 
 
+def test_tether_rows_bind_at_the_optimum(oracle):
+    """Variant 2: the tether segment lies where the unconstrained optimum goes -- with the rows the optimiser's answer
+    moves by decimetres, every row holds, and HiGHS on the exported rows (tether rows included) agrees."""
+    from tests.emul import emul
+    par, b = crafted.ent_lp_batch(2)
+    ref, plain = ReplanResult.empty(b), ReplanResult.empty(b)
+    assert oracle.replan_batch(b, ref, 1) == 0
+    assert oracle.replan_batch(crafted.without_tether_rows(b), plain, 1) == 0
+    e0 = b.n_hull_slots + par.num_of_agents + par.num_of_static_obst
+    assert (ref.line_ok[0, :, e0:] == 1).sum() >= 3 and ref.status[0] == 0 and plain.status[0] == 0
+    assert np.abs(ref.coeff_out[0] - plain.coeff_out[0]).max() > 0.1
+    assert ref.obj[0] > plain.obj[0] * (1 + 1e-6)            # a tighter feasible set costs something
+    got = emul.replan(b)
+    assert np.array_equal(got.line_ok, ref.line_ok) and np.array_equal(got.status, ref.status)
+    assert np.abs(got.coeff_out - ref.coeff_out).max() <= 1e-6 * max(1.0, np.abs(ref.coeff_out).max())
+    mdl = oracle.export_qp(b, 0, False, ref.lines[0], ref.line_ok[0])
+    st, x, f = qp_highs(mdl["P"], mdl["q"], mdl["Aeq"], mdl["beq"], mdl["G"], mdl["h"])
+    n = mdl["n"]
+    xo = np.concatenate([ref.coeff_out[0, ax, i] for i in range(n) for ax in range(3)])
+    assert st == "Optimal" and np.abs(xo - x).max() <= 1e-6 * max(1.0, np.abs(x).max())
+    # some row is active at the optimum that is inactive at the optimum without the tether rows
+    xp = np.concatenate([plain.coeff_out[0, ax, i] for i in range(n) for ax in range(3)])
+    assert (mdl["G"] @ xp - mdl["h"]).max() > 1e-3            # the unconstrained optimum violates a tether row
+    assert (mdl["G"] @ xo - mdl["h"]).max() <= 1e-6
+
+
 @pytest.mark.parametrize("kind", ["box", "vel", "n2box"])
 def test_both_solves_infeasible_is_status_2(oracle, kind):
     from tests.emul import emul

@@ -199,7 +199,7 @@ def test_ent_slot_overflow_is_loud(capi):
     s.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_non_entangling_lines_match_oracle(capi, oracle, variant):
     """addEntangleConstraintForIJCase (solver_gurobi_poly.cpp:620-642, :715-784) on the GPU: the crafted state of
     tests/crafted.py fires >= 10 tether LPs (ray beyond the agent, bend-point segments, the k == case_id skip, the
@@ -213,7 +213,12 @@ def test_non_entangling_lines_match_oracle(capi, oracle, variant):
     ref = ReplanResult.empty(b)
     assert oracle.replan_batch(b, ref, 1) == 0
     e0 = b.n_hull_slots + par.num_of_agents + par.num_of_static_obst
-    assert (ref.line_ok[:, :, e0:] == 1).sum() >= 8 and (ref.line_ok[:, :, e0:] == 2).sum() >= 1
+    if variant < 2:
+        assert (ref.line_ok[:, :, e0:] == 1).sum() >= 8 and (ref.line_ok[:, :, e0:] == 2).sum() >= 1
+    else:   # the binding tether: the rows move the optimum (checked against the oracle below)
+        plain = ReplanResult.empty(b)
+        assert oracle.replan_batch(crafted.without_tether_rows(b), plain, 1) == 0
+        assert np.abs(ref.coeff_out[0] - plain.coeff_out[0]).max() > 0.1
     assert np.array_equal(res.line_ok, ref.line_ok) and np.array_equal(res.status, ref.status)
     m = ref.line_ok == 1
     assert np.abs(res.lines[m] - ref.lines[m]).max() <= 1e-9 * max(1.0, np.abs(ref.lines[m]).max())

@@ -312,13 +312,11 @@ def test_cpp_shim_tether_constraints_and_failure_path(capi, oracle, tmp_path):
     and an infeasible replan returns optimize() == false with pwp_out == pwp_init (solver_gurobi_poly.cpp:856-859)."""
     from tests import crafted
     for exe in _shim_binaries():
-        par, b = crafted.ent_lp_batch(0)
+        par, b = crafted.ent_lp_batch(2)
         ref = ReplanResult.empty(b)
         assert oracle.replan_batch(b, ref, 1) == 0
         plain = ReplanResult.empty(b)
-        import dataclasses
-        no_ent = dataclasses.replace(b, esv_active=np.zeros_like(b.esv_active), esv_cnt=np.zeros_like(b.esv_cnt))
-        assert oracle.replan_batch(no_ent, plain, 1) == 0
+        assert oracle.replan_batch(crafted.without_tether_rows(b), plain, 1) == 0
         a, n = 0, int(b.n_int[0])
         out = _run_shim(exe, _shim_input(par, b, a, True), tmp_path, "ent")
         ok, status, obj, _ = out[0].split()
@@ -326,7 +324,7 @@ def test_cpp_shim_tether_constraints_and_failure_path(capi, oracle, tmp_path):
         assert int(ok) == 1 and int(status) == ref.status[a]
         assert np.abs(co - ref.coeff_out[a, :, :n]).max() <= 1e-6 * max(1.0, np.abs(ref.coeff_out[a]).max())
         # the tether rows matter in this scene: without them the optimum is a different one
-        assert np.abs(ref.coeff_out[a] - plain.coeff_out[a]).max() > 1e-4
+        assert np.abs(ref.coeff_out[a] - plain.coeff_out[a]).max() > 0.1
         par, b = crafted.infeasible_batch("box")
         out = _run_shim(exe, _shim_input(par, b, 2, False), tmp_path, "box")
         ok, status, obj, _ = out[0].split()

@@ -648,7 +648,7 @@ def run_reference_qp(oracle, b, a, ref, replans=1):
     return status, co, obj
 
 
-QP_LIVE = ["single_1001", "mtlp5_2002", "obst8_3003", "mtlp5_crafted-ent0", "mtlp5_crafted-box", "mtlp5_crafted-n2box"]
+QP_LIVE = ["single_1001", "mtlp5_2002", "obst8_3003", "mtlp5_crafted-ent0", "mtlp5_crafted-ent2", "mtlp5_crafted-box", "mtlp5_crafted-n2box"]
 
 
 @needs_ref
