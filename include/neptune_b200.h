@@ -160,12 +160,23 @@ int nb_generate_traj_batch(nb_handle* h, int32_t B, int32_t space, const int32_t
                            double dc, int32_t max_states, double* states, int32_t* n_states, void* stream);
 
 /*
- * Committed-trajectory record: the fixed-stride payload of the per-cycle all-gather (the batched
- * form of mader_msgs/DynTraj.msg + PieceWisePolTraj.msg): NB_REC_DOUBLES doubles per agent,
- *   [0] n_pieces (<= 16), [1..17] times, [18..209] coeff[3][16][4] ([a b c d] per axis and piece).
+ * Committed-trajectory record: the fixed-stride payload of the per-cycle exchange, the batched form of
+ * mader_msgs/msg/DynTraj.msg:1-9 + PieceWisePolTraj.msg (what NeptuneRos::publishOwnTraj sends, neptune_ros.cpp:436-480,
+ * and NeptuneRos::trajCB reads, :379-432): NB_REC_DOUBLES = 256 doubles (2 KB) per agent,
+ *   [0] n_pieces (<= 16), [1..17] times, [18..209] coeff[3][16][4] ([a b c d] per axis and piece)   -- pwp
+ *   [210] id, [211] is_agent, [212..214] bbox, [215..217] pos, [218] bendpt.size(), [219..234] bendpt[8] (x, y),
+ *   [235] sequence number of the commit, [236..255] reserved (zero).
  */
 #define NB_REC_PIECES 16
-#define NB_REC_DOUBLES (1 + (NB_REC_PIECES + 1) + 3 * NB_REC_PIECES * 4)
+#define NB_REC_PWP_DOUBLES (1 + (NB_REC_PIECES + 1) + 3 * NB_REC_PIECES * 4)
+#define NB_REC_DOUBLES 256
+#define NB_REC_OFF_ID 210
+#define NB_REC_OFF_ISAGENT 211
+#define NB_REC_OFF_BBOX 212
+#define NB_REC_OFF_POS 215
+#define NB_REC_OFF_NBEND 218
+#define NB_REC_OFF_BEND 219
+#define NB_REC_OFF_SEQ 235
 #define NB_HULL_STRIDE 24 /* vertices reserved per hull in nb_hulls_batch output */
 
 /*
@@ -297,6 +308,53 @@ int nb_entangle_check_batch(nb_handle* h, int32_t B, int32_t space, const int32_
                             void* stream);
 
 /*
+ * Entanglement half of Neptune::safetyCheckAfterReplan (neptune.cpp:735-752), faithful to its gating: for an agent with
+ * at least one late trajectory (late[b][j] != 0: received after time_init_opt_), SampledPointsForAll[j] of every late j
+ * is re-sampled from late_recs over [t_start, t_start + n T] (SamplePointsOfIntervals, :737-738), the front end's copy
+ * of j's bend points becomes the late message's (updateSPocAndbendPtsForAgent :740-741; bp_*_late), PredictAlphasBetas
+ * is re-run from entangle_state_ `st` (read only; :747-749) and entangleCheckGivenPwp decides (:750).  Agents without
+ * a late trajectory: entangled = 0 (need_to_rerun_entanglecheck stays false).  samp: the planning-time samples,
+ * [B][N][num_pol][S+1][2], or shared / group-indexed like nb_entangle_check_batch (samp_group [B], device only).
+ */
+int nb_postcheck_entangle_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const uint8_t* known,
+                                const uint8_t* late, const int32_t* bp_cnt, const double* bp_xy, const int32_t* bp_cnt_late,
+                                const double* bp_xy_late, nb_ent_state st, const double* prev_pos, const double* prev_pos_agent,
+                                const double* cur, const int32_t* n_int, const double* coeff, const double* t_start,
+                                const double* samp, int32_t samp_shared, const int32_t* samp_group, const double* late_recs,
+                                int32_t* entangled, void* stream);
+
+/*
+ * Replaces the bookkeeping of NeptuneRos::trajCB besides updateTrajObstacles (neptune_ros.cpp:413-431) for all N
+ * records at once: bendPtsForAgents_[j] = msg.bendpt -> bp_cnt [N], bp_xy [N][bp_max][2]; latestCheckingPosAgent_[j] =
+ * msg.pos -> latest_pos [N][2] (nullable).  SURVEY section 8(f) #2.
+ */
+int nb_unpack_records_batch(nb_handle* h, int32_t space, const double* recs, int32_t* bp_cnt, double* bp_xy,
+                            double* latest_pos, void* stream);
+
+/*
+ * Replaces the tail of Neptune::replanFull (neptune.cpp:1685-1699) followed by NeptuneRos::publishOwnTraj
+ * (neptune_ros.cpp:436-480): nb_commit_compose_batch plus the DynTraj header -- id, is_agent, bbox (3 x `bbox`), pos =
+ * start of the composed trajectory, bendpt[] = the tether base and the contact point of every entry of
+ * entangle_state_.bendPointsIdx (`es`, [B] states; es.cnt == NULL: base only), `seq` in the sequence slot.
+ * fe_solved (nullable): 0 = the front end returned no path, the replan is rejected (neptune.cpp:1473-1478).  t_now NULL:
+ * no composition (recs_out = pwp_now + header).  Device pointers only.
+ */
+int nb_publish_records_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const int32_t* n_int,
+                             const double* coeff, const double* t_start, const double* t_now, const double* prev,
+                             const uint8_t* has_prev, const int32_t* status, const int32_t* entangled, const int32_t* collide,
+                             const int32_t* fe_solved, nb_ent_state es, double bbox, double seq, double* recs_out,
+                             int32_t* n_pieces, void* stream);
+
+/*
+ * Every reference process derives its own staticObsRep_ / staticObsLongestDist_ from its base and start position
+ * (NeptuneRos::setUpCheckingPosAndStaticObs, neptune_ros.cpp:852-1019; nb_static_obst_rep computes one agent's).  This
+ * call gives the batched kernels one representation PER AGENT: strep_all [N][M][2][2], longest_all [N][M][2] (nullable
+ * when the front end is not used), indexed by agent id - 1.  It replaces the `strep` of nb_set_static, which stays the
+ * shared-representation form.  Host pointers.
+ */
+int nb_set_static_rep_per_agent(nb_handle* h, const double* strep_all, const double* longest_all);
+
+/*
  * ---- Front end: KinodynamicSearch (neptune/src/kinodynamic_search.cpp), SURVEY.md section 8(f) #1 ----
  *
  * Replaces the one-time setters of KinodynamicSearch (setMaxValuesAndSamples :272-327, setXYZMinMaxAndRa
@@ -379,6 +437,83 @@ int nb_search_batch(nb_handle* h, const nb_search_args* args, void* stream);
  * [3] open-list pop, [4] collision tests, [5] endpoint tests, [6] set-up; [8..14] child 0 only: primitive, state copy,
  * entanglement chain, key + lookup, step geometry, crossing tests, list automaton. */
 int nb_search_phase_cycles(nb_handle* h, long long* out, int B);
+
+/*
+ * ---- The replan cycle of one rank, resident on the device --------------------------------------------------------------
+ *
+ * Host side of the hot part of Neptune::replanFull for the B agents a rank plans (neptune.cpp:1430-1448 hulls, samples,
+ * PredictAlphasBetas; :1450-1510 front end; :1512-1529 back end; :1641-1647 safetyCheckAfterReplan; :1685-1699 compose) and
+ * of the message exchange around it (publishOwnTraj / trajCB, neptune_ros.cpp:379-480), as one stream-ordered launch
+ * sequence owned by the library: side streams for the independent stages, the whole sequence captured in CUDA graphs,
+ * committed-trajectory records kept in a three-slot ring on the device (slot k % 3 receives the records committed in
+ * cycle k; cycle k plans against the records of cycle k - 2 and post-checks against those of cycle k - 1, i.e. every
+ * other agent's newest trajectory arrives while this agent optimises).  With world > 1 the commit kernel stores every
+ * record into the ring of EVERY rank over NVLink (peer memory opened from CUDA IPC handles) and raises a flag there; the
+ * cycle ends when the flags of all peers for this cycle are up -- the all-gather of the reference's /trajs topic fused
+ * into the commit, no collective call and no host in the loop.
+ *
+ * Per-cycle inputs travel in ONE packed pinned host buffer -> ONE device buffer (nb_cycle_upload), results likewise
+ * (nb_cycle_download); nb_cycle_layout tells where each array lives.  Records never travel through the host once seeded.
+ */
+typedef struct nb_cycle nb_cycle;
+
+typedef struct nb_cycle_desc
+{
+  int32_t B;                 /* agents planned by this rank */
+  const int32_t* agent_id;   /* [B] 1-based ids (ctor argument id of each agent's solver) */
+  int32_t front_end;         /* 1: KinodynamicSearch::run inside the cycle (nb_search_configure must have been called) */
+  int32_t rank, world;       /* position of this rank in the exchange (world == 1: no peers) */
+  const uint8_t* planned;    /* [num_agents] 1 = some rank plans this agent (its ring slot is written by a commit every
+                                cycle); 0 = nobody does (its record is carried forward).  NULL: all planned by this rank
+                                when world == 1 */
+  double bbox;               /* DynTraj bbox edge of every agent (2 drone_radius, neptune_ros.cpp:447-449) */
+  double delta;              /* hull inflation bbox / 2 + drone_radius (neptune.cpp:340) */
+} nb_cycle_desc;
+
+/* byte offsets of the arrays inside the packed buffers (-1: absent) */
+typedef struct nb_cycle_layout
+{
+  /* inputs */
+  int64_t n_int, coeff_init, t_start, t_now, t_group, group, known, late, esv_cnt, esv_alpha, esv_active;
+  int64_t es_cnt, es_alpha, es_beta, es_bend, es_active, prev_pos, prev_pos_agent, cur;
+  int64_t fe_init, fe_goal, fe_coeffs_z, fe_comb;
+  int64_t in_bytes;
+  /* outputs */
+  int64_t coeff_out, obj, status, iters, entangled, collide, n_pieces, fe_status, fe_solved, fe_n_int, fe_stats;
+  int64_t out_bytes;
+} nb_cycle_layout;
+
+int nb_cycle_create(nb_handle* h, const nb_cycle_desc* d, nb_cycle** out);
+void nb_cycle_destroy(nb_cycle* c);
+int nb_cycle_layout_get(const nb_cycle* c, nb_cycle_layout* out);
+void* nb_cycle_host_in(nb_cycle* c);    /* pinned, in_bytes */
+void* nb_cycle_host_out(nb_cycle* c);   /* pinned, out_bytes */
+/* records the agents know when cycle k starts and those that arrive during it: host [num_agents][NB_REC_DOUBLES] each */
+int nb_cycle_seed_records(nb_cycle* c, const double* known_recs, const double* late_recs, void* stream);
+int nb_cycle_upload(nb_cycle* c, int32_t n_groups, void* stream);    /* packed inputs host -> device */
+int nb_cycle_step(nb_cycle* c, void* stream);                         /* one cycle (graph replay once captured) */
+int nb_cycle_download(nb_cycle* c, void* stream);                     /* packed results device -> host */
+/* the same with caller-owned PINNED buffers of in_bytes / out_bytes (several prepared input sets, nb_pinned_alloc) */
+int nb_cycle_upload_from(nb_cycle* c, const void* host_in, int32_t n_groups, void* stream);
+int nb_cycle_download_to(nb_cycle* c, void* host_out, void* stream);
+void* nb_pinned_alloc(int64_t bytes);   /* page-locked host memory, zeroed; NULL on failure */
+void nb_pinned_free(void* p);
+/* runs ONE real cycle (k advances), then captures the launch sequence for the current grouping in three CUDA graphs (one
+ * per ring phase); needs a non-default stream.  With world > 1 every rank must call it at the same cycle. */
+int nb_cycle_capture(nb_cycle* c, void* stream);
+/* one cycle on a single stream with an event after every stage; ms [8]: late hulls, hulls + samples, predict, front end,
+ * lines + QP, post-check, commit, exchange wait */
+int nb_cycle_step_profiled(nb_cycle* c, void* stream, double* ms);
+long long nb_cycle_launches_per_step(const nb_cycle* c);             /* kernels one step launches */
+long long nb_cycle_index(const nb_cycle* c);                          /* k: cycles completed */
+/* copy a device array of the cycle to the host (tests, diagnostics): "ring_new", "ring_late", "ring_known" (records,
+ * [num_agents][NB_REC_DOUBLES], as of the LAST completed cycle for ring_new), "esA_cnt", "esA_alpha", "esA_beta",
+ * "esA_bend", "esA_active", "hull_cnt", "samp", "bp_cnt", "bp_xy", "latest_pos" */
+int nb_cycle_fetch(nb_cycle* c, const char* name, void* dst, int64_t bytes, void* stream);
+/* exchange set-up for world > 1: every rank exports one IPC handle (64 bytes) of its ring; after an all-gather of the
+ * handles (the caller's job: torch.distributed, MPI ...) every rank opens its peers' rings */
+int nb_cycle_ipc_handle(nb_cycle* c, void* handle64);
+int nb_cycle_open_peers(nb_cycle* c, const void* handles /* [world][64] */);
 
 /* Measurement hook (no reference counterpart): with nb_set_profiling on, SM cycles lane 0 of every QP warp spent per
  * phase in the last nb_replan_batch, out [B][16]: [0] set-up, [1] residual sweep, [2] dual residual + stopping test,

@@ -335,20 +335,71 @@ class Solver:
         return ent, st
 
 
-NB_REC_DOUBLES = 1 + 17 + 3 * 16 * 4
+def solver_postcheck_entangle(self, agent_id, known, late, bp_cnt, bp_xy, bp_cnt_late, bp_xy_late, state: EntArrays, prev_pos,
+                             prev_pos_agent, cur, n_int, coeff, t_start, samp, late_recs):
+    """Entanglement half of ``Neptune::safetyCheckAfterReplan`` (nb_postcheck_entangle_batch): entangled [B]."""
+    arrs = [np.ascontiguousarray(x, dt) for x, dt in
+            ((agent_id, np.int32), (known, np.uint8), (late, np.uint8), (bp_cnt, np.int32), (bp_xy, np.float64),
+             (bp_cnt_late, np.int32), (bp_xy_late, np.float64), (prev_pos, np.float64), (prev_pos_agent, np.float64),
+             (cur, np.float64), (n_int, np.int32), (coeff, np.float64), (t_start, np.float64), (samp, np.float64),
+             (late_recs, np.float64))]
+    B = len(arrs[0])
+    ent = np.zeros(B, np.int32)
+    f = lib().nb_postcheck_entangle_batch
+    f.argtypes = [_P, C.c_int32, C.c_int32] + [_P] * 7 + [NbEntState] + [_P] * 7 + [C.c_int32, _P, _P, _P, _P]
+    p = [_np(a) for a in arrs]
+    _check(f(self._h, B, NB_HOST, p[0], p[1], p[2], p[3], p[4], p[5], p[6], state.c(), p[7], p[8], p[9], p[10], p[11], p[12],
+             p[13], 0, None, p[14], _np(ent), None), "nb_postcheck_entangle_batch")
+    return ent
+
+
+def solver_unpack_records(self, recs):
+    """``NeptuneRos::trajCB`` bookkeeping for all records: (bp_cnt [N], bp_xy [N][bp_max][2], latest_pos [N][2])."""
+    recs = np.ascontiguousarray(recs, np.float64)
+    N, bm = self.par.num_of_agents, self.par.bp_max
+    cnt, xy, pos = np.zeros(N, np.int32), np.zeros((N, bm, 2)), np.zeros((N, 2))
+    f = lib().nb_unpack_records_batch
+    f.argtypes = [_P, C.c_int32, _P, _P, _P, _P, _P]
+    _check(f(self._h, NB_HOST, _np(recs), _np(cnt), _np(xy), _np(pos), None), "nb_unpack_records_batch")
+    return cnt, xy, pos
+
+
+def solver_set_static_rep_per_agent(self, strep_all, longest_all=None):
+    """One staticObsRep_ (and staticObsLongestDist_) per agent: [N][M][2][2], [N][M][2]."""
+    sa = np.ascontiguousarray(strep_all, np.float64)
+    la = None if longest_all is None else np.ascontiguousarray(longest_all, np.float64)
+    f = lib().nb_set_static_rep_per_agent
+    f.argtypes = [_P, _P, _P]
+    _check(f(self._h, _np(sa), _np(la)), "nb_set_static_rep_per_agent")
+
+
+NB_REC_PWP_DOUBLES = 1 + 17 + 3 * 16 * 4   # trajectory part of a record
+NB_REC_DOUBLES = 256                         # record stride: trajectory + DynTraj header (include/neptune_b200.h)
+REC_ID, REC_ISAGENT, REC_BBOX, REC_POS, REC_NBEND, REC_BEND, REC_SEQ = 210, 211, 212, 215, 218, 219, 235
 NB_HULL_STRIDE = 24
 
 
-def make_records(committed) -> np.ndarray:
-    """Committed-trajectory records (the all-gather payload) from (times, cx, cy, cz) tuples."""
+def make_records(committed, par: Params | None = None, bp_cnt=None, bp_xy=None, seq: int = 0) -> np.ndarray:
+    """Committed-trajectory records (the payload of the per-cycle exchange) from (times, cx, cy, cz) tuples; with
+    `par` the DynTraj header is filled as NeptuneRos::publishOwnTraj fills the message (neptune_ros.cpp:436-480):
+    id, is_agent, bbox = 2 drone_radius, pos = first point of the trajectory, bendpt[] = the agent's tether."""
     recs = np.zeros((len(committed), NB_REC_DOUBLES))
     for j, (tm, cx, cy, cz) in enumerate(committed):
         n = len(cx)
         assert n <= 16
         recs[j, 0] = n
         recs[j, 1:2 + n] = tm
-        co = recs[j, 18:].reshape(3, 16, 4)
+        co = recs[j, 18:NB_REC_PWP_DOUBLES].reshape(3, 16, 4)
         co[0, :n], co[1, :n], co[2, :n] = cx, cy, cz
+        if par is not None:
+            recs[j, REC_ID], recs[j, REC_ISAGENT], recs[j, REC_SEQ] = j + 1, 1.0, seq
+            recs[j, REC_BBOX:REC_BBOX + 3] = 2.0 * par.drone_radius
+            recs[j, REC_POS:REC_POS + 3] = [cx[0][3], cy[0][3], cz[0][3]]
+            if bp_cnt is not None:
+                nb = int(bp_cnt[j])
+                assert nb <= 8
+                recs[j, REC_NBEND] = nb
+                recs[j, REC_BEND:REC_BEND + 2 * nb] = np.asarray(bp_xy[j, :nb], np.float64).reshape(-1)
     return recs
 
 
@@ -388,7 +439,7 @@ def solver_postcheck(self, n_int, coeff, t_start, recs, late, delta):
 
 
 def solver_compose(self, t, has_prev, prev, now):
-    """``mu::composePieceWisePol`` on committed-trajectory records -> (n_pieces [B], out [B][210])."""
+    """``mu::composePieceWisePol`` on committed-trajectory records -> (n_pieces [B], out [B][256])."""
     arrs = [np.ascontiguousarray(t, np.float64), np.ascontiguousarray(has_prev, np.uint8),
             np.ascontiguousarray(prev, np.float64), np.ascontiguousarray(now, np.float64)]
     out, npc = np.zeros_like(arrs[3]), np.zeros(len(arrs[0]), np.int32)
@@ -399,6 +450,9 @@ def solver_compose(self, t, has_prev, prev, now):
     return npc, out
 
 
+Solver.postcheck_entangle = solver_postcheck_entangle
+Solver.unpack_records = solver_unpack_records
+Solver.set_static_rep_per_agent = solver_set_static_rep_per_agent
 Solver.compose = solver_compose
 Solver.hulls = solver_hulls
 Solver.postcheck = solver_postcheck

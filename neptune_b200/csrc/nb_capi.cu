@@ -13,6 +13,7 @@
 #include "nb_entangle.cuh"
 #include "nb_hull.cuh"
 #include "nb_lines.cuh"
+#include "nb_publish.cuh"
 #include "nb_qp.cuh"
 #include "nb_search.cuh"
 #include "nb_search_launch.h"
@@ -21,6 +22,7 @@
 
 static thread_local std::string g_err;
 extern "C" const char* nb_last_error(void) { return g_err.c_str(); }
+void nb_set_error(const char* text) { g_err = text; }  // internal (nb_cycle.cu)
 
 #define NB_CUDA(call)                                                                         \
   do                                                                                          \
@@ -33,59 +35,7 @@ extern "C" const char* nb_last_error(void) { return g_err.c_str(); }
     }                                                                                         \
   } while (0)
 
-struct DevBuf
-{
-  void* p = nullptr;
-  size_t cap = 0;
-  int ensure(size_t bytes)
-  {
-    if (bytes <= cap) return 0;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-    size_t want = bytes + bytes / 4 + 256;
-    if (cudaMalloc(&p, want) != cudaSuccess) return -1;
-    cap = want;
-    return 0;
-  }
-  void release()
-  {
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
-  }
-};
-
-struct nb_handle
-{
-  nb_params par;
-  NbConsts cs;
-  int device;
-  long long launches;
-  NbQpTable* d_tables;  // [2][NB_NPOL] : mode-major
-  double* d_pb;
-  int64_t* d_st_ptr;
-  double* d_st_xy;
-  double* d_strep;
-  int64_t st_nvert;
-  // staging of NB_HOST arguments
-  DevBuf in[16], out[8];
-  // scratch
-  DevBuf lines, line_ok, keep, cl, ncl, rows, err, ent_scratch;
-  // front-end search: configuration, staging and workspace
-  nb_search_params sp;
-  int sp_set = 0;
-  int search_smem_set = 0;
-  int sprof_B = 0;
-  double* d_st_longest = nullptr;
-  DevBuf sprof, qprof;
-  int qprof_B = 0;
-  DevBuf sin[20], sout[12], sw_meta, sw_kin, sw_alpha, sw_beta, sw_bend, sw_hash, sw_heap, sw_gh, sw_ng, sw_chi, sw_chd, sw_fcode;
-  int qp_smem_set = 0;
-  int num_sms = 148;
-  int profiling = 0;
-  cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
-};
+#include "nb_handle.h"
 
 // ------------------------------------------------------------------------------------------ kernels
 
@@ -463,62 +413,39 @@ __global__ void k_compose(int B, const double* t, const uint8_t* has_prev, const
   n_pieces[b] = np;
 }
 
-// pwp_now of generatePwpOut (times shifted by t_start, solver_gurobi_poly.cpp:892-907) and, when t_now is
-// given, pwp_out = composePieceWisePol(time_now, dc, pwp_prev, pwp_now) of Neptune::replanFull
-// (neptune.cpp:1689-1699).  An agent whose replan failed, ended entangled or collides in the post-check keeps
-// its previous record (replanFull returns before pwp_out is touched).
 __global__ void k_commit(int B, const int* n_int, const double* coeff, const double* t_start, double T, double* recs,
                          const double* t_now, const double* prev, const int* prev_agent, const uint8_t* has_prev,
-                         const int* status, const int* entangled, const int* collide, int* n_pieces, int* err)
+                         const int* status, const int* entangled, const int* collide, const int* fe_solved, int* n_pieces,
+                         NbPublishHdr hd, int* err)
 {
   __shared__ double now[NB_REC];
   const int b = blockIdx.x;
   if (b >= B) return;
-  double* r = recs + (size_t)b * NB_REC;
-  const int n = n_int[b];
-  const bool compose = t_now != nullptr;
-  for (int q = threadIdx.x; q < NB_REC; q += blockDim.x)
+  nb_commit_one(b, n_int, coeff, t_start, T, recs + (size_t)b * NB_REC, now, t_now, prev, prev_agent, has_prev, status, entangled,
+                collide, fe_solved, n_pieces, hd, err);
+}
+
+// NeptuneRos::trajCB (neptune_ros.cpp:379-432), the bookkeeping a received DynTraj triggers besides
+// Neptune::updateTrajObstacles: bendPtsForAgents_[id-1] = msg.bendpt, latestCheckingPosAgent_[id-1] = msg.pos.
+// One thread per record.  bp_cnt [N], bp_xy [N][bp_max][2], latest_pos [N][2] (nullable).
+__global__ void k_unpack_records(int N, int bp_max, const double* recs, int* bp_cnt, double* bp_xy, double* latest_pos, int* err)
+{
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const double* r = recs + (size_t)j * NB_REC;
+  int nb = (int)r[NB_REC_NBEND];
+  if (nb > bp_max)
   {
-    double v = 0.0;
-    if (q == 0)
-      v = (double)n;
-    else if (q <= NB_TP + 1)
-    {
-      const int k = q - 1;
-      v = k <= n ? NB_ADD(t_start[b], NB_MUL((double)k, T)) : 0.0;  // pwp_out.times[i] += t_start (:898)
-    }
-    else
-    {
-      const int e = q - (NB_TP + 2), ax = e / (NB_TP * 4), rem = e % (NB_TP * 4), piece = rem / 4, c = rem % 4;
-      v = piece < n ? coeff[(size_t)b * 96 + ax * 32 + piece * 4 + c] : 0.0;
-    }
-    if (compose)
-      now[q] = v;
-    else
-      r[q] = v;
+    *err = 6;
+    nb = bp_max;
   }
-  if (!compose) return;
-  __syncthreads();
-  const double* pv = prev + (size_t)(prev_agent ? prev_agent[b] - 1 : b) * NB_REC;
-  const bool hp = has_prev == nullptr || has_prev[b];
-  const bool ok = !((status && status[b] >= 2) || (entangled && entangled[b]) || (collide && collide[b]));
-  if (!ok || !hp)
+  bp_cnt[j] = nb;
+  for (int q = 0; q < bp_max; q++)
   {
-    const double* src = (!ok && hp) ? pv : now;  // failed without a previous plan: nothing better to publish than pwp_now
-    for (int q = threadIdx.x; q < NB_REC; q += blockDim.x) r[q] = src[q];
-    if (threadIdx.x == 0 && n_pieces) n_pieces[b] = (int)src[0];
-    return;
+    bp_xy[((size_t)j * bp_max + q) * 2] = q < nb ? r[NB_REC_BEND + 2 * q] : 0.0;
+    bp_xy[((size_t)j * bp_max + q) * 2 + 1] = q < nb ? r[NB_REC_BEND + 2 * q + 1] : 0.0;
   }
-  if (threadIdx.x == 0)
-  {
-    int np = nb_compose_records(t_now[b], pv, now, r);
-    if (np < 0)
-    {
-      *err = 4;
-      np = 0;
-    }
-    if (n_pieces) n_pieces[b] = np;
-  }
+  if (latest_pos) latest_pos[2 * j] = r[NB_REC_POS], latest_pos[2 * j + 1] = r[NB_REC_POS + 1];
 }
 
 // ------------------------------------------------------------------------------------------ ABI
@@ -651,6 +578,16 @@ extern "C" int nb_check_async_errors(nb_handle* h, void* stream)
     g_err = "nb_replan_batch: n_int out of range (1..8) in a device-resident batch";
     return NB_ERR_ARG;
   }
+  if (err == 6)
+  {
+    g_err = "a tether has more bend points than a record (8) or bp_max can hold";
+    return NB_ERR_CAPACITY;
+  }
+  if (err == 7)
+  {
+    g_err = "nb_cycle: the records of a peer rank did not arrive (exchange timeout)";
+    return NB_ERR_CUDA;
+  }
   if (err)
   {
     g_err = "a fixed-capacity list overflowed in an asynchronous call (ent_slots, ent_cap or a 16-piece record)";
@@ -679,11 +616,34 @@ extern "C" int nb_set_static(nb_handle* h, const int64_t* st_ptr, const double* 
   NB_CUDA(cudaMemcpy(h->d_st_ptr, st_ptr, sizeof(int64_t) * (M + 1), cudaMemcpyHostToDevice));
   NB_CUDA(cudaMalloc(&h->d_st_xy, sizeof(double) * 2 * h->st_nvert));
   NB_CUDA(cudaMemcpy(h->d_st_xy, st_xy, sizeof(double) * 2 * h->st_nvert, cudaMemcpyHostToDevice));
+  h->strep_per_agent = 0;
   if (strep)
   {
     NB_CUDA(cudaMalloc(&h->d_strep, sizeof(double) * 4 * M));
     NB_CUDA(cudaMemcpy(h->d_strep, strep, sizeof(double) * 4 * M, cudaMemcpyHostToDevice));
   }
+  return NB_OK;
+}
+
+extern "C" int nb_set_static_rep_per_agent(nb_handle* h, const double* strep_all, const double* longest_all)
+{
+  if (!h) return NB_ERR_ARG;
+  const int M = h->par.num_static, N = h->par.num_agents;
+  if (M == 0) return NB_OK;
+  if (!strep_all) return NB_ERR_ARG;
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaFree(h->d_strep);
+  h->d_strep = nullptr;
+  NB_CUDA(cudaMalloc(&h->d_strep, sizeof(double) * 4 * M * N));
+  NB_CUDA(cudaMemcpy(h->d_strep, strep_all, sizeof(double) * 4 * M * N, cudaMemcpyHostToDevice));
+  if (longest_all)
+  {
+    cudaFree(h->d_st_longest);
+    h->d_st_longest = nullptr;
+    NB_CUDA(cudaMalloc(&h->d_st_longest, sizeof(double) * 2 * M * N));
+    NB_CUDA(cudaMemcpy(h->d_st_longest, longest_all, sizeof(double) * 2 * M * N, cudaMemcpyHostToDevice));
+  }
+  h->strep_per_agent = 1;
   return NB_OK;
 }
 
@@ -999,6 +959,7 @@ int ent_common(nb_handle* h, NbEntArgs* a, int mode, int B, int space, const int
   a->tcap = tcap > 1024 ? 1024 : tcap;
   a->pb = h->d_pb;
   a->strep = h->d_strep;
+  a->strep_per_agent = h->strep_per_agent;
   if (M > 0 && !h->d_strep)
   {
     g_err = "entanglement call with static obstacles but nb_set_static(strep) was never called";
@@ -1061,6 +1022,21 @@ extern "C" int nb_entangle_predict_batch(nb_handle* h, int32_t B, int32_t space,
   if ((rc = ent_launch(h, a, B, st))) return rc;
   if ((rc = state_out(h, space, stt, d, (size_t)B, st))) return rc;
   return ent_finish(h, space, st);
+}
+
+// internal (nb_cycle.cu): PredictAlphasBetas with SampledPointsForAll[j][0].col(0) read in place from the group-shaped
+// samples of nb_hulls_batch (agent b looks at block group[b]); device pointers
+int nb_internal_predict_grouped(nb_handle* h, int B, const int32_t* agent_id, const uint8_t* known, const int32_t* bp_cnt,
+                                const double* bp_xy, nb_ent_state stt, const double* prev_pos, const double* prev_pos_agent,
+                                const double* cur, const double* samp_g, const int32_t* group, cudaStream_t st)
+{
+  NbEntArgs a;
+  int rc;
+  if ((rc = ent_common(h, &a, 0, B, NB_DEVICE, agent_id, known, bp_cnt, bp_xy, st))) return rc;
+  a.st = stt;
+  a.prev_pos = prev_pos, a.prev_pos_agent = prev_pos_agent, a.cur = cur;
+  a.samp0 = samp_g, a.samp_group = group, a.samp0_stride = h->par.num_pol * (h->par.samples + 1) * 2;
+  return ent_launch(h, a, B, st);
 }
 
 extern "C" int nb_entangle_track_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const int32_t* bp_cnt,
@@ -1276,8 +1252,10 @@ extern "C" int nb_commit_records_batch(nb_handle* h, int32_t B, int32_t space, c
   if ((rc = stage_in(h, 1, space, coeff, (size_t)B * 96, st, &dc))) return rc;
   if ((rc = stage_in(h, 2, space, t_start, (size_t)B, st, &dt))) return rc;
   if ((rc = stage_out(h, 0, space, recs_out, (size_t)B * NB_REC, &dr))) return rc;
+  NbPublishHdr hd;
+  memset(&hd, 0, sizeof(hd));
   k_commit<<<B, 64, 0, st>>>(B, dn, dc, dt, h->cs.T, dr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                             (int*)h->err.p);
+                             nullptr, hd, (int*)h->err.p);
   h->launches += 1;
   NB_CUDA(cudaGetLastError());
   if (space == NB_HOST)
@@ -1390,11 +1368,148 @@ extern "C" int nb_commit_compose_batch(nb_handle* h, int32_t B, int32_t space, c
   }
   NB_CUDA(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
+  NbPublishHdr hd;
+  memset(&hd, 0, sizeof(hd));
   k_commit<<<B, 64, 0, st>>>(B, n_int, coeff, t_start, h->cs.T, recs_out, t_now, prev, prev_agent, has_prev, status, entangled,
-                             collide, n_pieces, (int*)h->err.p);
+                             collide, nullptr, n_pieces, hd, (int*)h->err.p);
   h->launches += 1;
   NB_CUDA(cudaGetLastError());
   return NB_OK;
+}
+
+extern "C" int nb_unpack_records_batch(nb_handle* h, int32_t space, const double* recs, int32_t* bp_cnt, double* bp_xy,
+                                       double* latest_pos, void* stream)
+{
+  if (!h || !recs || !bp_cnt || !bp_xy) return NB_ERR_ARG;
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->par.num_agents, bm = h->par.bp_max;
+  const double* dr;
+  int* dc;
+  double *dx, *dl;
+  int rc;
+  if ((rc = stage_in(h, 0, space, recs, (size_t)N * NB_REC, st, &dr))) return rc;
+  if ((rc = stage_out(h, 0, space, bp_cnt, (size_t)N, &dc))) return rc;
+  if ((rc = stage_out(h, 1, space, bp_xy, (size_t)N * bm * 2, &dx))) return rc;
+  if ((rc = stage_out(h, 2, space, latest_pos, (size_t)N * 2, &dl))) return rc;
+  k_unpack_records<<<(N + 127) / 128, 128, 0, st>>>(N, bm, dr, dc, dx, dl, (int*)h->err.p);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
+  if (space == NB_HOST)
+  {
+    NB_CUDA(cudaMemcpyAsync(bp_cnt, dc, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, st));
+    NB_CUDA(cudaMemcpyAsync(bp_xy, dx, (size_t)N * bm * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (latest_pos) NB_CUDA(cudaMemcpyAsync(latest_pos, dl, (size_t)N * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return ent_finish(h, space, st);
+  }
+  return NB_OK;
+}
+
+extern "C" int nb_publish_records_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const int32_t* n_int,
+                                        const double* coeff, const double* t_start, const double* t_now, const double* prev,
+                                        const uint8_t* has_prev, const int32_t* status, const int32_t* entangled,
+                                        const int32_t* collide, const int32_t* fe_solved, nb_ent_state es, double bbox,
+                                        double seq, double* recs_out, int32_t* n_pieces, void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  if (space != NB_DEVICE)
+  {
+    g_err = "nb_publish_records_batch: device pointers only (it runs inside the resident replan cycle)";
+    return NB_ERR_ARG;
+  }
+  if (!agent_id || !n_int || !coeff || !t_start || !recs_out || (t_now && !prev))
+  {
+    g_err = "nb_publish_records_batch: null argument";
+    return NB_ERR_ARG;
+  }
+  if (h->par.num_static > 0 && es.cnt && !h->d_strep)
+  {
+    g_err = "nb_publish_records_batch: static obstacles without nb_set_static(strep)";
+    return NB_ERR_ARG;
+  }
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  NbPublishHdr hd;
+  hd.on = 1, hd.N = h->par.num_agents, hd.M = h->par.num_static, hd.cap = h->par.ent_cap, hd.bbox = bbox, hd.pb = h->d_pb;
+  hd.strep = h->d_strep, hd.strep_per_agent = h->strep_per_agent, hd.es = es, hd.seq = seq;
+  k_commit<<<B, 64, 0, st>>>(B, n_int, coeff, t_start, h->cs.T, recs_out, t_now, prev, agent_id, has_prev, status, entangled,
+                             collide, fe_solved, n_pieces, hd, (int*)h->err.p);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+extern "C" int nb_postcheck_entangle_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const uint8_t* known,
+                                           const uint8_t* late, const int32_t* bp_cnt, const double* bp_xy,
+                                           const int32_t* bp_cnt_late, const double* bp_xy_late, nb_ent_state st_in,
+                                           const double* prev_pos, const double* prev_pos_agent, const double* cur,
+                                           const int32_t* n_int, const double* coeff, const double* t_start, const double* samp,
+                                           int32_t samp_shared, const int32_t* samp_group, const double* late_recs,
+                                           int32_t* entangled, void* stream)
+{
+  if (!h || B < 0) return NB_ERR_ARG;
+  if (B == 0) return NB_OK;
+  if (!agent_id || !known || !late || !bp_cnt || !bp_xy || !bp_cnt_late || !bp_xy_late || !st_in.cnt || !prev_pos ||
+      !prev_pos_agent || !cur || !n_int || !coeff || !t_start || !samp || !late_recs || !entangled)
+  {
+    g_err = "nb_postcheck_entangle_batch: null argument";
+    return NB_ERR_ARG;
+  }
+  if (space == NB_HOST && samp_group)
+  {
+    g_err = "nb_postcheck_entangle_batch: samp_group is only supported with device pointers";
+    return NB_ERR_ARG;
+  }
+  NB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h->par.num_agents, S = h->par.samples, cap = h->par.ent_cap, NA = N + h->par.num_static;
+  NbEntArgs a;
+  int rc;
+  if ((rc = ent_common(h, &a, 4, B, space, agent_id, known, bp_cnt, bp_xy, st))) return rc;
+  nb_ent_state d;
+  if ((rc = stage_state_in(h, 4, space, st_in, (size_t)B, st, &d, true))) return rc;
+  a.st = d;
+  if ((rc = stage_in(h, 9, space, n_int, (size_t)B, st, &a.n_int))) return rc;
+  if ((rc = stage_in(h, 10, space, coeff, (size_t)B * 96, st, &a.coeff))) return rc;
+  if ((rc = stage_in(h, 11, space, samp, (size_t)(samp_shared ? 1 : B) * N * h->par.num_pol * (S + 1) * 2, st, &a.samp))) return rc;
+  a.samp_shared = samp_shared;
+  a.samp_group = samp_group;
+  if ((rc = stage_in(h, 12, space, prev_pos, (size_t)B * (N + 1) * 2, st, &a.prev_pos))) return rc;
+  if ((rc = stage_in(h, 13, space, prev_pos_agent, (size_t)B * N * 2, st, &a.prev_pos_agent))) return rc;
+  if ((rc = stage_in(h, 14, space, cur, (size_t)B * 2, st, &a.cur))) return rc;
+  if ((rc = stage_in(h, 15, space, late, (size_t)B * N, st, &a.late))) return rc;
+  // further inputs and the scratch live in one library buffer: late records, late bend points, t_start | work states,
+  // per-agent samples of interval 0, per-agent known flags
+  const size_t o_rec = 0, o_bpc = o_rec + (size_t)N * NB_REC * 8, o_bpx = o_bpc + (((size_t)N * 4 + 7) & ~(size_t)7);
+  const size_t o_ts = o_bpx + (size_t)N * h->par.bp_max * 16, o_cnt = o_ts + (size_t)B * 8;
+  const size_t o_alpha = o_cnt + (size_t)B * 8, o_beta = o_alpha + (size_t)B * cap * 8, o_bend = o_beta + (size_t)B * cap * 8;
+  const size_t o_act = o_bend + (((size_t)B * cap * 4 + 7) & ~(size_t)7), o_ps = o_act + (((size_t)B * NA * 4 + 7) & ~(size_t)7);
+  const size_t o_pk = o_ps + (size_t)B * N * (S + 1) * 16, total = o_pk + (size_t)B * N + 16;
+  if (h->ent_scratch.ensure(total))
+  {
+    g_err = "cudaMalloc failed for the post-check scratch";
+    return NB_ERR_CUDA;
+  }
+  char* base = (char*)h->ent_scratch.p;
+  if (space == NB_HOST)
+  {
+    NB_CUDA(cudaMemcpyAsync(base + o_rec, late_recs, (size_t)N * NB_REC * 8, cudaMemcpyHostToDevice, st));
+    NB_CUDA(cudaMemcpyAsync(base + o_bpc, bp_cnt_late, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    NB_CUDA(cudaMemcpyAsync(base + o_bpx, bp_xy_late, (size_t)N * h->par.bp_max * 16, cudaMemcpyHostToDevice, st));
+    NB_CUDA(cudaMemcpyAsync(base + o_ts, t_start, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    a.late_recs = (const double*)(base + o_rec), a.bp_cnt_late = (const int*)(base + o_bpc);
+    a.bp_xy_late = (const double*)(base + o_bpx), a.t_start = (const double*)(base + o_ts);
+  }
+  else
+    a.late_recs = late_recs, a.bp_cnt_late = bp_cnt_late, a.bp_xy_late = bp_xy_late, a.t_start = t_start;
+  a.out.cnt = (int32_t*)(base + o_cnt), a.out.alpha = (int32_t*)(base + o_alpha), a.out.beta = (double*)(base + o_beta);
+  a.out.bend = (int32_t*)(base + o_bend), a.out.active = (int32_t*)(base + o_act);
+  a.psamp = (double*)(base + o_ps), a.pknown = (unsigned char*)(base + o_pk);
+  if ((rc = stage_out(h, 7, space, entangled, (size_t)B, &a.result))) return rc;
+  if ((rc = ent_launch(h, a, B, st))) return rc;
+  if (space == NB_HOST) NB_CUDA(cudaMemcpyAsync(entangled, a.result, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return ent_finish(h, space, st);
 }
 
 // ------------------------------------------------------------------------------------------ K0 ABI (front end)
@@ -1537,6 +1652,7 @@ extern "C" int nb_search_batch(nb_handle* h, const nb_search_args* u, void* stre
   if ((rc = sstage_in(h, 16, space, u->comb, (size_t)(u->comb_shared ? 1 : B) * p.nchild, st, &a.comb))) return rc;
   a.comb_shared = u->comb_shared;
   a.st_ptr = h->d_st_ptr, a.st_xy = h->d_st_xy, a.strep = h->d_strep, a.st_longest = h->d_st_longest, a.pb = h->d_pb;
+  a.strep_per_agent = h->strep_per_agent;
   const size_t ns9 = (size_t)B * 9;
   if ((rc = sstage_out(h, 0, space, u->status, (size_t)B, &a.status))) return rc;
   if ((rc = sstage_out(h, 1, space, u->solved, (size_t)B, &a.solved))) return rc;

@@ -15,6 +15,7 @@
 #pragma once
 #include "../../include/neptune_b200.h"
 #include "nb_common.cuh"
+#include "nb_hull.cuh"
 
 #define NB_ENT_LOCAL 24  // entries one tether can add in one step: bp_max + 2 <= 24 pairs... (ints = 2x)
 
@@ -35,7 +36,18 @@ struct NbEntCtx
   const double* strep;  // [M][2][2]
   const int* bp_cnt;    // [N]
   const double* bp_xy;  // [N][bp_max][2]
+  // post-check only (Neptune::safetyCheckAfterReplan): agents whose trajectory arrived late are seen with the bend
+  // points of that late message (trajCB, neptune_ros.cpp:418-424); nullptr elsewhere
+  const unsigned char* use_alt;  // [N]
+  const int* bp_cnt_alt;
+  const double* bp_xy_alt;
 };
+
+NB_HD int nb_bp_cnt(const NbEntCtx& cx, int j) { return (cx.use_alt && cx.use_alt[j]) ? cx.bp_cnt_alt[j] : cx.bp_cnt[j]; }
+NB_HD const double* nb_bp_xy(const NbEntCtx& cx, int j)
+{
+  return ((cx.use_alt && cx.use_alt[j]) ? cx.bp_xy_alt : cx.bp_xy) + (size_t)cx.bp_stride * j;
+}
 
 // eu::vectorWedge2 (:16-27): (b-a) x (c-a); ab, ac returned when asked for
 NB_HD double nb_wedge(const double* a, const double* b, const double* c, double* ab, double* ac)
@@ -440,10 +452,10 @@ NB_HD int nb_collect_toadd(const Group<NL>& g, const NbEntCtx& cx, const double*
     const bool agent = j < cx.N && j != cx.self && known[j];
     if (agent)
     {
-      nb = cx.bp_cnt[j];
+      nb = nb_bp_cnt(cx, j);
       if (nb > NB_ENT_LOCAL - 2) nb = NB_ENT_LOCAL - 2;
       cnt = nb_hsig_agent_stream(nullptr, pk_agents ? pk_agents + 2 * j : pk, pk1, pik_all + (size_t)j * pik_stride,
-                                 pik1_all + (size_t)j * pik1_stride, pb_self, cx.bp_xy + (size_t)cx.bp_stride * j, nb, j + 1, 0);
+                                 pik1_all + (size_t)j * pik1_stride, pb_self, nb_bp_xy(cx, j), nb, j + 1, 0);
     }
     else if (j >= cx.N && j < cx.N + cx.M)
       cnt = nb_hsig_static_one(st, pk, pk1, cx.strep + 4 * (j - cx.N), j + 1);
@@ -456,7 +468,7 @@ NB_HD int nb_collect_toadd(const Group<NL>& g, const NbEntCtx& cx, const double*
       int* out = toadd + 2 * (nadd + off);
       if (agent)
         nb_hsig_agent_stream(out, pk_agents ? pk_agents + 2 * j : pk, pk1, pik_all + (size_t)j * pik_stride,
-                             pik1_all + (size_t)j * pik1_stride, pb_self, cx.bp_xy + (size_t)cx.bp_stride * j, nb, j + 1, cnt);
+                             pik1_all + (size_t)j * pik1_stride, pb_self, nb_bp_xy(cx, j), nb, j + 1, cnt);
       else
         out[0] = st[0], out[1] = st[1];
     }
@@ -585,7 +597,7 @@ NB_HD int nb_add_alpha_beta(int* toadd, int nadd, NbEntState& es, const double* 
     for (int i = 0; i < nadd && !have; i++)
     {
       const int aid = toadd[2 * i], acs = toadd[2 * i + 1];
-      const int nb = (aid <= N) ? cx.bp_cnt[aid - 1] : 0;
+      const int nb = (aid <= N) ? nb_bp_cnt(cx, aid - 1) : 0;
       for (int j = es.n_alpha - 1; j >= 0; j--)
       {
         const int lid = es.alpha[2 * j], lcs = es.alpha[2 * j + 1];
@@ -805,8 +817,20 @@ struct NbEntArgs
   nb_ent_state out;      // rollout: [B][9][...]
   const int* n_int;
   const double* coeff;   // [B][3][8][4]
-  const double* samp;    // [B or 1][N][8][S+1][2]
+  const double* samp;    // [B or 1][N][8][S+1][2], or [G][...] with samp_group
   int samp_shared;
+  const int* samp_group; // optional [B]: agent b reads block samp_group[b] of samp (shared-window groups)
+  int samp0_stride;      // doubles between the first samples of consecutive agents in samp0 (2: packed [B][N][2];
+                         // num_pol (S+1) 2: samp0 points into a samples array and is group-indexed like samp)
+  int strep_per_agent;   // 1: strep is [N][M][2][2], indexed by the planning agent's id - 1
+  // post-check (mode 4, Neptune::safetyCheckAfterReplan neptune.cpp:735-752)
+  const unsigned char* late;     // [B][N] trajectory of j received after time_init_opt_
+  const double* late_recs;       // [N][NB_REC] those trajectories
+  const double* t_start;         // [B]
+  const int* bp_cnt_late;        // [N] bend points carried by the late messages
+  const double* bp_xy_late;      // [N][bp_max][2]
+  double* psamp;                 // scratch [B][N][S+1][2]: interval-0 samples per planning agent
+  unsigned char* pknown;         // scratch [B][N]
   const double* prev_pos;        // predict
   const double* prev_pos_agent;
   const double* cur;
@@ -828,13 +852,24 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
   const int NA = a.N + a.M;
   NbEntCtx cx;
   cx.N = a.N, cx.M = a.M, cx.self = a.agent_id[b] - 1, cx.cap = a.cap, cx.bp_max = a.bp_max, cx.bp_stride = 2 * a.bp_max;
-  cx.pb = a.pb, cx.strep = a.strep, cx.bp_cnt = a.bp_cnt, cx.bp_xy = a.bp_xy;
+  cx.pb = a.pb, cx.strep = a.strep + (a.strep_per_agent ? (size_t)cx.self * 4 * a.M : 0), cx.bp_cnt = a.bp_cnt, cx.bp_xy = a.bp_xy;
+  cx.use_alt = nullptr, cx.bp_cnt_alt = nullptr, cx.bp_xy_alt = nullptr;
   const uint8_t* known = a.known + (size_t)b * a.N;
   int* pairs = toadd + 2 * a.tcap;  // shared: (id, active before) of the entries of one step
   NbEntState es;
-  if (a.mode == 1)
-  {  // work on slot 0 of the output, then replicate forward
-    const size_t o = (size_t)b * 9;
+  if (a.mode == 4)
+  {  // post-check: nothing to do without a late trajectory (need_to_rerun_entanglecheck, neptune.cpp:722, :743)
+    int mine = 0;
+    for (int j = g.lane; j < a.N; j += NL) mine |= (j != cx.self && a.late[(size_t)b * a.N + j]) ? 1 : 0;
+    if (!g.any(mine))
+    {
+      if (g.lane == 0) a.result[b] = 0;
+      return;
+    }
+  }
+  if (a.mode == 1 || a.mode == 4)
+  {  // work on slot 0 of the output (mode 4: on a scratch copy, the reference's local ent_state_begin)
+    const size_t o = (size_t)b * (a.mode == 1 ? 9 : 1);
     es.alpha = a.out.alpha + o * a.cap * 2, es.beta = a.out.beta + o * a.cap, es.bend = a.out.bend + o * a.cap;
     es.active = a.out.active + o * NA;
     for (int q = g.lane; q < a.cap; q += NL)
@@ -853,15 +888,19 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
   es.n_alpha = a.st.cnt[2 * b];
   es.n_bend = a.st.cnt[2 * b + 1];
   g.sync();
-  const double* samp = a.samp ? a.samp + (a.samp_shared ? 0 : (size_t)b * a.N * a.num_pol * (a.S + 1) * 2) : nullptr;
+  const size_t samp_blk = (size_t)a.N * a.num_pol * (a.S + 1) * 2;
+  const double* samp = a.samp ? a.samp + (a.samp_group ? (size_t)a.samp_group[b] * samp_blk : (a.samp_shared ? 0 : (size_t)b * samp_blk))
+                              : nullptr;
   const double* cxy = a.coeff ? a.coeff + (size_t)b * 96 : nullptr;
   int bad = 0;
   if (a.mode == 0)
   {  // Neptune::PredictAlphasBetas neptune.cpp:976-1008
     const double* pp = a.prev_pos + (size_t)b * (a.N + 1) * 2;
     const double* cur = a.cur + 2 * b;
-    const int nadd = nb_collect_toadd<NL>(g, cx, pp + 2 * a.N, pp, cur, a.prev_pos_agent + (size_t)b * a.N * 2, 2,
-                                          a.samp0 + (size_t)b * a.N * 2, 2, known, toadd, a.tcap);
+    const int s0 = a.samp0_stride > 0 ? a.samp0_stride : 2;
+    const double* samp0 = a.samp0 + (a.samp_group && s0 != 2 ? (size_t)a.samp_group[b] * samp_blk : (size_t)b * a.N * s0);
+    const int nadd = nb_collect_toadd<NL>(g, cx, pp + 2 * a.N, pp, cur, a.prev_pos_agent + (size_t)b * a.N * 2, 2, samp0, s0,
+                                          known, toadd, a.tcap);
     if (nadd < 0)
       bad = 1;
     else if (g.lane == 0)
@@ -914,6 +953,56 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
     }
     g.sync();
     if (!bad && flag[3]) bad = 1;
+  }
+  else if (a.mode == 4)
+  {  // Neptune::safetyCheckAfterReplan, entanglement half (neptune.cpp:735-752)
+    const int S1 = a.S + 1, n = a.n_int[b];
+    double* ps = a.psamp + (size_t)b * a.N * S1 * 2;
+    unsigned char* pk = a.pknown + (size_t)b * a.N;
+    const unsigned char* late = a.late + (size_t)b * a.N;
+    // SampledPointsForAll[j]: re-sampled over [times.front(), times.back()] of pwp_optimized for the late agents
+    // (SamplePointsOfIntervals, :737-738: deltaT = n T / num_pol), the planning-time samples for the others; only
+    // interval 0 is ever read (PredictAlphasBetas :986, entangleCheckGivenPwp :899 / :982)
+    const double t0 = a.t_start[b], t1 = NB_ADD(t0, NB_MUL((double)n, a.T));
+    for (int j = g.lane; j < a.N; j += NL)
+    {
+      const bool lt = j != cx.self && late[j];
+      pk[j] = (known[j] || lt) ? 1 : 0;
+      if (lt)
+        nb_sample_interval(a.late_recs + (size_t)j * NB_REC, t0, t1, a.num_pol, a.S, 0, ps + (size_t)j * S1 * 2);
+      else
+        for (int q = 0; q < S1 * 2; q++) ps[(size_t)j * S1 * 2 + q] = samp ? samp[(size_t)j * a.num_pol * S1 * 2 + q] : 0.0;
+    }
+    g.sync();
+    cx.use_alt = late, cx.bp_cnt_alt = a.bp_cnt_late, cx.bp_xy_alt = a.bp_xy_late;
+    const double* pp = a.prev_pos + (size_t)b * (a.N + 1) * 2;
+    const double* cur = a.cur + 2 * b;
+    int r = 0;
+    // PredictAlphasBetas on the updated samples (:747-749)
+    const int nadd = nb_collect_toadd<NL>(g, cx, pp + 2 * a.N, pp, cur, a.prev_pos_agent + (size_t)b * a.N * 2, 2, ps, S1 * 2, pk,
+                                          toadd, a.tcap);
+    if (nadd < 0)
+      bad = 1;
+    else
+    {
+      if (g.lane == 0)
+      {
+        if (nb_add_alpha_beta(toadd, nadd, es, pp + 2 * a.N, cx))
+          flag[3] = 1;
+        else
+        {
+          flag[3] = 0;
+          nb_update_bend_pts(es, cur, cx);
+        }
+      }
+      g.sync();
+      if (flag[3])
+        bad = 1;
+      else if (n > 0)  // entangleCheckGivenPwp (:750), interval 0 only; the scratch samples hold one interval per agent
+        r = nb_ent_interval_pass<NL>(g, es, cx, cxy, 0, ps, pk, 1, a.S, a.T, 3 * NA, toadd, a.tcap, pairs, flag);
+      if (r < 0) bad = 1;
+    }
+    if (g.lane == 0) a.result[b] = r > 0 ? 1 : 0;
   }
   else if (a.mode == 2)
   {  // entangleCheckGivenPwp: interval 0 only (kinodynamic_search.cpp:899, :982-983)

@@ -16,11 +16,22 @@
 #include "nb_common.cuh"
 
 #define NB_TP 16                           // pieces a committed trajectory can hold
-#define NB_REC (1 + (NB_TP + 1) + 3 * NB_TP * 4)  // doubles per committed-trajectory record
+#define NB_REC_PWP (1 + (NB_TP + 1) + 3 * NB_TP * 4)  // doubles of the trajectory part of a record (210)
+#define NB_REC 256                         // doubles per committed-trajectory record (2 KB): trajectory + DynTraj header
+// DynTraj header of a record (mader_msgs/msg/DynTraj.msg:3-9), after the trajectory part
+#define NB_REC_ID 210       // id (1-based)
+#define NB_REC_ISAGENT 211  // is_agent
+#define NB_REC_BBOX 212     // bbox[3]
+#define NB_REC_POS 215      // pos[3]: position of the publisher when it published
+#define NB_REC_NBEND 218    // bendpt.size() (tether base included)
+#define NB_REC_BEND 219     // bendpt[8][2]
+#define NB_REC_BEND_MAX 8
+#define NB_REC_SEQ 235      // cycle in which the record was committed (stands in for time_received)
 #define NB_HMAX 24                         // vertices of an inflated hull (<= 4 + control points)
 #define NB_HPCS 4                          // pieces one window may overlap
 
-// committed-trajectory record (the all-gather payload): [0] n_pieces, [1..17] times, then coeff[3][16][4]
+// committed-trajectory record (the payload of the per-cycle exchange): [0] n_pieces, [1..17] times, coeff[3][16][4],
+// then the DynTraj header above
 NB_HD int nb_rec_np(const double* rec) { return (int)rec[0]; }
 NB_HD const double* nb_rec_times(const double* rec) { return rec + 1; }
 NB_HD const double* nb_rec_coeff(const double* rec, int ax) { return rec + 1 + (NB_TP + 1) + ax * NB_TP * 4; }
@@ -227,47 +238,56 @@ NB_HD int nb_hull_of_window(const NbConsts& cs, const double* rec, double t0, do
   return nb_chain_sorted(pts, np, hull, NB_HMAX);
 }
 
-// Neptune::SamplePointsOfIntervals (neptune.cpp:500-566): out [num_pol][S+1][2], idx [num_pol][S+1]
-NB_HD void nb_sample_points(const NbConsts& cs, const double* rec, double t_start, double t_end, double* out, int* idx_out)
+// One interval of Neptune::SamplePointsOfIntervals (neptune.cpp:500-566): the S+1 samples of interval i when
+// [t_start, t_end] is cut into num_pol intervals; out [S+1][2], idx [S+1] (optional)
+NB_HD void nb_sample_interval(const double* rec, double t_start, double t_end, int num_pol, int S, int i, double* out,
+                              int* idx_out = nullptr)
 {
-  const int np = nb_rec_np(rec), nt = np + 1, S = cs.S;
+  const int np = nb_rec_np(rec), nt = np + 1;
   const double* times = nb_rec_times(rec);
   const double* cx = nb_rec_coeff(rec, 0);
   const double* cy = nb_rec_coeff(rec, 1);
-  const double deltaT = NB_SUB(t_end, t_start) / (1.0 * cs.num_pol);
-  for (int i = 0; i < cs.num_pol; i++)
-    for (int j = 0; j <= S; j++)
+  const double deltaT = NB_SUB(t_end, t_start) / (1.0 * num_pol);
+  for (int j = 0; j <= S; j++)
+  {
+    const double ts = NB_ADD(NB_ADD(t_start, NB_MUL(deltaT, (double)i)), NB_MUL(deltaT / S, (double)j));
+    const int low = nb_upper_bound(times, nt, ts);
+    int ii;
+    double te;
+    if (low != nt)
     {
-      const double ts = NB_ADD(NB_ADD(t_start, NB_MUL(deltaT, (double)i)), NB_MUL(deltaT / S, (double)j));
-      const int low = nb_upper_bound(times, nt, ts);
-      int ii;
-      double te;
-      if (low != nt)
-      {
-        ii = nb_sat(low - 1, 0, np - 1);
-        te = NB_SUB(ts, times[ii]);
-        if (te < 0)
-          te = 0;
-        else if (te > deltaT)
-          te = deltaT;
-      }
-      else
-      {
-        const int k = low - 1;
-        te = NB_SUB(times[k], times[k - 1]);
-        ii = k - 1;
-      }
-      const double tv[4] = { NB_MUL(NB_MUL(te, te), te), NB_MUL(te, te), te, 1.0 };
-      double x = 0, y = 0;
-      for (int r = 0; r < 4; r++)
-      {
-        x = NB_ADD(x, NB_MUL(cx[4 * ii + r], tv[r]));
-        y = NB_ADD(y, NB_MUL(cy[4 * ii + r], tv[r]));
-      }
-      out[(i * (S + 1) + j) * 2] = x;
-      out[(i * (S + 1) + j) * 2 + 1] = y;
-      if (idx_out) idx_out[i * (S + 1) + j] = ii;
+      ii = nb_sat(low - 1, 0, np - 1);
+      te = NB_SUB(ts, times[ii]);
+      if (te < 0)
+        te = 0;
+      else if (te > deltaT)
+        te = deltaT;
     }
+    else
+    {
+      const int k = low - 1;
+      te = NB_SUB(times[k], times[k - 1]);
+      ii = k - 1;
+    }
+    const double tv[4] = { NB_MUL(NB_MUL(te, te), te), NB_MUL(te, te), te, 1.0 };
+    double x = 0, y = 0;
+    for (int r = 0; r < 4; r++)
+    {
+      x = NB_ADD(x, NB_MUL(cx[4 * ii + r], tv[r]));
+      y = NB_ADD(y, NB_MUL(cy[4 * ii + r], tv[r]));
+    }
+    out[2 * j] = x;
+    out[2 * j + 1] = y;
+    if (idx_out) idx_out[j] = ii;
+  }
+}
+
+// Neptune::SamplePointsOfIntervals (neptune.cpp:500-566): out [num_pol][S+1][2], idx [num_pol][S+1]
+NB_HD void nb_sample_points(const NbConsts& cs, const double* rec, double t_start, double t_end, double* out, int* idx_out)
+{
+  for (int i = 0; i < cs.num_pol; i++)
+    nb_sample_interval(rec, t_start, t_end, cs.num_pol, cs.S, i, out + (size_t)i * (cs.S + 1) * 2,
+                       idx_out ? idx_out + i * (cs.S + 1) : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------ GJK
@@ -455,5 +475,6 @@ NB_HD int nb_compose_records(double t, const double* p1_in, const double* p2_in,
       out[1 + np] = t2[i];
     }
   out[0] = (double)np;
+  for (int q = NB_REC_PWP; q < NB_REC; q++) out[q] = p2_in[q];  // the message header is the new publication's
   return np;
 }

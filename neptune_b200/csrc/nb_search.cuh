@@ -79,6 +79,7 @@ struct NbSearchArgs
   const double* st_xy;
   const double* strep;
   const double* st_longest;
+  int strep_per_agent;   // 1: strep is [N][M][2][2] and st_longest [N][M][2], indexed by the planning agent's id - 1
   const double* pb;
   const int* bp_cnt;
   const double* bp_xy;
@@ -1082,10 +1083,11 @@ NB_HD void nb_search_task(Cta& cta, const NbSearchArgs& a, int b, int wb, NbSear
     c.samp = a.samp + (size_t)grp * N * p.num_pol * (S + 1) * 2;
     c.known = a.known + (size_t)b * N;
     c.comb = a.comb + (a.comb_shared ? 0 : (size_t)b * p.nchild);
-    c.st_ptr = a.st_ptr, c.st_xy = a.st_xy, c.st_longest = a.st_longest;
+    c.st_ptr = a.st_ptr, c.st_xy = a.st_xy, c.st_longest = a.st_longest + (a.strep_per_agent ? (size_t)c.self * 2 * M : 0);
     c.ecx.N = N, c.ecx.M = M, c.ecx.self = c.self, c.ecx.cap = p.ecap, c.ecx.bp_max = p.bp_max, c.ecx.bp_stride = 2 * p.bp_max;
     c.samp_stride = p.num_pol * (S + 1) * 2, c.bsq_stride = NB_SEARCH_BSQ_STRIDE, c.hstage_stride = NB_SEARCH_HSTAGE_STRIDE;
-    c.ecx.pb = a.pb, c.ecx.strep = a.strep, c.ecx.bp_cnt = a.bp_cnt, c.ecx.bp_xy = a.bp_xy;
+    c.ecx.pb = a.pb, c.ecx.strep = a.strep + (a.strep_per_agent ? (size_t)c.self * 4 * M : 0), c.ecx.bp_cnt = a.bp_cnt, c.ecx.bp_xy = a.bp_xy;
+    c.ecx.use_alt = nullptr, c.ecx.bp_cnt_alt = nullptr, c.ecx.bp_xy_alt = nullptr;
     c.a_na = a.es.cnt[2 * b], c.a_nb = a.es.cnt[2 * b + 1];
     c.a_alpha = a.es.alpha + (size_t)b * p.es_cap * 2, c.a_beta = a.es.beta + (size_t)b * p.es_cap;
     c.a_bend = a.es.bend + (size_t)b * p.es_cap, c.a_active = a.es.active + (size_t)b * NA;

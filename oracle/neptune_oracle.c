@@ -2340,7 +2340,8 @@ int orc_replan_batch(const orc_params* par, const orc_batch* b, int nthreads)
  * CPU baseline that bench.py times next to the device-resident cycle.
  */
 #define ORC_REC_TP 16
-#define ORC_REC (1 + (ORC_REC_TP + 1) + 3 * ORC_REC_TP * 4)
+#define ORC_REC_PWP (1 + (ORC_REC_TP + 1) + 3 * ORC_REC_TP * 4) /* trajectory part of a record */
+#define ORC_REC 256 /* record stride: trajectory + DynTraj header (include/neptune_b200.h) */
 
 int orc_cycle_batch(const orc_params* par, int B, const int* agent_id, const int* n_int, const double* coeff_init,
                     const double* t_start, const double* recs, const unsigned char* known, const double* pb,
@@ -2525,6 +2526,7 @@ int orc_compose_records(double t, double dc, double* p1, double* p2, double* out
     }
 #undef COPY_PIECE
   out[0] = (double)np;
+  memcpy(out + ORC_REC_PWP, p2 + ORC_REC_PWP, sizeof(double) * (ORC_REC - ORC_REC_PWP)); /* header of the new publication */
   return np;
 }
 

@@ -338,7 +338,7 @@ def cycle_batch(scene, recs, nthreads: int = 1, do_entangle: bool = True, t_now=
            C.c_int(int(do_entangle)), _p(out["coeff_out"]), _p(out["obj"]), _p(out["status"]), _p(out["iters"]),
            _p(out["entangled"]), _p(out["collide"]), C.c_int(nthreads))
     if rc == 0 and t_now is not None:
-        out["new_recs"], out["new_pieces"] = np.zeros((B, 210)), np.zeros(B, np.int32)
+        out["new_recs"], out["new_pieces"] = np.zeros((B, 256)), np.zeros(B, np.int32)
         g = lib().orc_commit_compose_batch
         g.restype = C.c_int
         rc = g(C.byref(op), C.c_int(B), _p(arrs["agent_id"]), _p(arrs["n_int"]), _p(out["coeff_out"]), _p(arrs["t_start"]),

@@ -2,23 +2,23 @@
 cross-check the C oracle, plus random committed-trajectory records for the compose tests."""
 import numpy as np
 
-TP, REC = 16, 210
+TP, REC, REC_PWP = 16, 256, 210
 
 
 def rec_from(times, coeff):
-    """times [n+1], coeff [3][n][4] -> 210-double record."""
+    """times [n+1], coeff [3][n][4] -> record (256 doubles, header left zero)."""
     n = len(times) - 1
     r = np.zeros(REC)
     r[0] = n
     r[1:2 + n] = times
-    c = r[1 + TP + 1:].reshape(3, TP, 4)
+    c = r[1 + TP + 1:REC_PWP].reshape(3, TP, 4)
     c[:, :n] = coeff
     return r
 
 
 def rec_to(r):
     n = int(r[0])
-    return list(r[1:2 + n]), r[1 + TP + 1:].reshape(3, TP, 4)[:, :n].copy()
+    return list(r[1:2 + n]), r[1 + TP + 1:REC_PWP].reshape(3, TP, 4)[:, :n].copy()
 
 
 def compose_lists(t, p1, p2):

@@ -120,3 +120,25 @@ def track(par, strep, agent_id, bp_cnt, bp_xy, bp_cnt_prev, bp_xy_prev, state, p
            d(pp), d(ppa), d(arrs[7]), d(arrs[8]), d(arrs[9]), d(res))
     assert rc == 0, rc
     return res, st, pp, ppa
+
+
+def postcheck_entangle(par, strep, agent_id, known, late, bp_cnt, bp_xy, bp_cnt_late, bp_xy_late, state, prev_pos, prev_pos_agent,
+                       cur, n_int, coeff, t_start, samp, late_recs):
+    """k_entangle mode 4 (entanglement half of Neptune::safetyCheckAfterReplan) on one host lane: entangled [B]."""
+    nbp = make_nb_params(par)
+    arrs = [np.ascontiguousarray(x, dt) for x, dt in
+            ((par.pb, np.float64), (strep if par.num_of_static_obst else np.zeros((1, 2, 2)), np.float64), (agent_id, np.int32),
+             (known, np.uint8), (late, np.uint8), (bp_cnt, np.int32), (bp_xy, np.float64), (bp_cnt_late, np.int32),
+             (bp_xy_late, np.float64), (prev_pos, np.float64), (prev_pos_agent, np.float64), (cur, np.float64),
+             (n_int, np.int32), (coeff, np.float64), (t_start, np.float64), (samp, np.float64), (late_recs, np.float64))]
+    B = len(arrs[2])
+    ent = np.zeros(B, np.int32)
+    from neptune_b200.capi import NbEntState
+    f = lib().emul_postcheck_entangle
+    P = C.c_void_p
+    f.argtypes = [P, P, P, C.c_int] + [P] * 7 + [NbEntState] + [P] * 9
+    d = [a.ctypes.data_as(P) for a in arrs]
+    rc = f(C.addressof(nbp), d[0], d[1], B, d[2], d[3], d[4], d[5], d[6], d[7], d[8], state.c(), d[9], d[10], d[11], d[12], d[13],
+           d[14], d[15], d[16], ent.ctypes.data_as(P))
+    assert rc == 0, rc
+    return ent

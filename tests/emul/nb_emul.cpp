@@ -139,6 +139,37 @@ extern "C" int emul_entangle(const nb_params* par, const double* pb, const doubl
   return err ? NB_ERR_CAPACITY : 0;
 }
 
+// k_entangle mode 4 (Neptune::safetyCheckAfterReplan, entanglement half) on one host lane
+extern "C" int emul_postcheck_entangle(const nb_params* par, const double* pb, const double* strep, int B, const int32_t* agent_id,
+                                       const uint8_t* known, const uint8_t* late, const int32_t* bp_cnt, const double* bp_xy,
+                                       const int32_t* bp_cnt_late, const double* bp_xy_late, nb_ent_state st,
+                                       const double* prev_pos, const double* prev_pos_agent, const double* cur,
+                                       const int32_t* n_int, const double* coeff, const double* t_start, const double* samp,
+                                       const double* late_recs, int32_t* entangled)
+{
+  NbEntArgs a;
+  memset(&a, 0, sizeof(a));
+  const int N = par->num_agents, M = par->num_static, NA = N + M, cap = par->ent_cap, S = par->samples;
+  a.mode = 4, a.N = N, a.M = M, a.cap = cap, a.bp_max = par->bp_max, a.num_pol = par->num_pol, a.S = S, a.T = par->T_span;
+  int tcap = 4 * NA + 16;
+  a.tcap = tcap > 1024 ? 1024 : tcap;
+  a.agent_id = agent_id, a.known = known, a.bp_cnt = bp_cnt, a.bp_xy = bp_xy, a.pb = pb, a.strep = strep;
+  a.st = st, a.n_int = n_int, a.coeff = coeff, a.samp = samp, a.prev_pos = prev_pos, a.prev_pos_agent = prev_pos_agent, a.cur = cur;
+  a.late = late, a.late_recs = late_recs, a.t_start = t_start, a.bp_cnt_late = bp_cnt_late, a.bp_xy_late = bp_xy_late;
+  a.result = entangled;
+  std::vector<int32_t> wc((size_t)B * 2), wa((size_t)B * cap * 2), wb((size_t)B * cap), wact((size_t)B * NA);
+  std::vector<double> wbeta((size_t)B * cap), ps((size_t)B * N * (S + 1) * 2);
+  std::vector<uint8_t> pk((size_t)B * N);
+  a.out.cnt = wc.data(), a.out.alpha = wa.data(), a.out.beta = wbeta.data(), a.out.bend = wb.data(), a.out.active = wact.data();
+  a.psamp = ps.data(), a.pknown = pk.data();
+  std::vector<int> toadd(4 * a.tcap + 8);
+  int err = 0;
+  a.err = &err;
+  Group<1> g(0);
+  for (int b = 0; b < B; b++) nb_entangle_task<1>(g, b, a, toadd.data(), toadd.data() + 4 * a.tcap);
+  return err ? NB_ERR_CAPACITY : 0;
+}
+
 #include "../../neptune_b200/csrc/nb_hull.cuh"
 
 extern "C" int emul_hulls(const nb_params* par, int B, const double* t_start, const double* recs, const uint8_t* known,

@@ -174,24 +174,40 @@ def test_hulls_samples_postcheck_bit_exact(capi, oracle, cfg, seed):
     s.close()
 
 
-@pytest.mark.parametrize("cfg,seed", [("mtlp5", 2005), ("obst8", 3004)])
-def test_replan_cycle_matches_oracle_composite(capi, oracle, cfg, seed):
-    """The whole device-resident cycle (K1 -> K3 predict -> K2/K4 -> K5 + K3 check -> commit) against
-    the same chain executed by the oracle."""
-    import torch
+def _cycle_fetch_states(cyc, par):
+    B, cap, NA = cyc.B, par.ent_cap, par.NA
+    return dict(cnt=cyc.fetch("esA_cnt", (B, 2), np.int32), alpha=cyc.fetch("esA_alpha", (B, cap, 2), np.int32),
+                beta=cyc.fetch("esA_beta", (B, cap), np.float64), bend=cyc.fetch("esA_bend", (B, cap), np.int32),
+                active=cyc.fetch("esA_active", (B, NA), np.int32))
+
+
+@pytest.mark.parametrize("cfg,seed,all_late", [("mtlp5", 2005, True), ("obst8", 3004, True), ("obst8", 3003, False)])
+def test_replan_cycle_matches_oracle_composite(capi, oracle, cfg, seed, all_late):
+    """The whole device-resident cycle of the C++ library (nb_cycle_*: K1 -> K3 predict -> K2/K4 -> K5 + gated K3
+    post-check -> commit with DynTraj header into the record ring) against the same chain executed by the oracle.  The
+    third case has late != known: a random subset of the trajectories arrives during the optimisation, changed."""
     from neptune_b200.cycle import ReplanCycle
+    from tests import postcheck_util as pu
     from tests.ent_backends import OracleEntBackend
     par = config(cfg)
     ob = OracleEntBackend(oracle)
     sc = make_scene(par, seed, sync=False, ent_backend=ob)
     b = sc.batch
-    cyc = ReplanCycle(par, b.agent_id - 1, "cuda:0", static=(b.st_ptr, b.st_xy, sc.strep))
-    hin, hout = cyc.host_inputs(sc), cyc.host_outputs()
+    cyc = ReplanCycle(par, b.agent_id - 1, "cuda:0", static=(b.st_ptr, b.st_xy, sc.strep), planned=np.ones(par.num_of_agents, np.uint8))
+    known_recs = cyc.records_of(sc, seq=0)
+    if all_late:
+        late, late_committed, late_recs, bc_l, bx_l = sc.known, sc.committed, known_recs, b.bp_cnt, b.bp_xy
+    else:
+        late, late_committed, late_recs, bc_l, bx_l = next(pu.late_cases(par, sc, np.random.default_rng(seed), 1))
+    cyc.seed_records(known_recs, late_recs)
+    hin, hout = cyc.host_inputs(sc, late=late), cyc.host_outputs()
     cyc.step_from_host(hin, hout)
     cyc.check_errors()
-    o = {k: v.cpu().numpy() for k, v in cyc.o.items()}
+    esA = _cycle_fetch_states(cyc, par)
     for k in ("cnt", "alpha", "beta", "bend", "active"):
-        assert np.array_equal(o["esA_" + k], getattr(sc, "esA_" + k)), k
+        assert np.array_equal(esA[k], getattr(sc, "esA_" + k)), k
+    # trajCB bookkeeping from the record headers
+    assert np.array_equal(cyc.fetch("bp_cnt", (par.num_of_agents,), np.int32), b.bp_cnt)
     ref = ReplanResult.empty(b)
     assert oracle.replan_batch(b, ref, 2) == 0
     assert np.array_equal(hout["status"], ref.status)
@@ -200,33 +216,82 @@ def test_replan_cycle_matches_oracle_composite(capi, oracle, cfg, seed):
     want_col = np.zeros(b.B, np.int32)
     for bi in range(b.B):
         for j in range(par.num_of_agents):
-            if sc.known[bi, j]:
-                tm, cx, cy, _ = sc.committed[j]
+            if late[bi, j] and j != int(b.agent_id[bi]) - 1:
+                tm, cx, cy, _ = late_committed[j]
                 if oracle.pwp_collides(ref.coeff_out[bi], int(b.n_int[bi]), sc.t_start[bi], par.T_span, tm, cx, cy, [delta] * 3):
                     want_col[bi] = 1
     assert np.array_equal(hout["collide"], want_col)
-    ent = ob.check_batch(par, b.agent_id, b.n_int, ref.coeff_out, sc.samp, sc.known, sc.strep, b.bp_cnt, b.bp_xy,
-                         sc.esA_cnt, sc.esA_alpha, sc.esA_beta, sc.esA_bend, sc.esA_active)[0]
+    # safetyCheckAfterReplan, entanglement half: gated on late arrivals, fresh PredictAlphasBetas on the updated samples
+    es0 = (sc.es0_cnt, sc.es0_alpha, sc.es0_beta, sc.es0_bend, sc.es0_active)
+    ent = pu.oracle_postcheck_entangle(oracle, par, sc.strep, b.agent_id, sc.known, late, b.bp_cnt, b.bp_xy, bc_l, bx_l, es0,
+                                       sc.prev_pos, sc.prev_pos_agent, sc.state_A[:, 0, :2], b.n_int, ref.coeff_out, sc.t_start,
+                                       sc.samp, late_committed)
     assert np.array_equal(hout["entangled"], ent)
     # published records: pwp_now (times shifted by t_start, generatePwpOut :898) composed with the agent's previous
-    # record at time_now (replanFull neptune.cpp:1689-1699); a rejected replan keeps the previous record
-    rec, recs_in = o["new_recs"], capi.make_records(sc.committed)
+    # record at time_now (replanFull neptune.cpp:1689-1699) + the DynTraj header; a rejected replan keeps the previous one
+    rec = cyc.records("new")
+    PW = capi.NB_REC_PWP_DOUBLES
     for bi in range(b.B):
-        n = int(b.n_int[bi])
-        now = np.zeros(210)
+        n, me = int(b.n_int[bi]), int(b.agent_id[bi]) - 1
+        now = np.zeros(capi.NB_REC_DOUBLES)
         now[0] = n
         now[1:2 + n] = sc.t_start[bi] + par.T_span * np.arange(n + 1)
-        now[18:].reshape(3, 16, 4)[:, :n] = o["coeff_out"][bi, :, :n]
-        prev = recs_in[int(b.agent_id[bi]) - 1]
+        now[18:PW].reshape(3, 16, 4)[:, :n] = hout["coeff_out"][bi, :, :n]
+        prev = late_recs[me]
         if hout["status"][bi] >= 2 or hout["entangled"][bi] or hout["collide"][bi]:
-            assert np.array_equal(rec[bi], prev)
+            assert np.array_equal(rec[me], prev)
             continue
         npc, want, _, _ = oracle.compose_records(hin["t_now"][bi], par.dc, prev, now)
-        assert npc == o["new_pieces"][bi] and npc >= n
-        assert np.array_equal(rec[bi], want)
-        assert rec[bi, 1] == hin["t_now"][bi] and rec[bi, 1 + npc] == now[1 + n]
-    del cyc
-    torch.cuda.synchronize()
+        assert npc == hout["n_pieces"][bi] and npc >= n
+        assert np.array_equal(rec[me, :PW], want[:PW])
+        assert rec[me, 1] == hin["t_now"][bi] and rec[me, 1 + npc] == now[1 + n]
+        # header (publishOwnTraj, neptune_ros.cpp:436-480)
+        assert rec[me, capi.REC_ID] == me + 1 and rec[me, capi.REC_ISAGENT] == 1 and rec[me, capi.REC_SEQ] == 0
+        assert (rec[me, capi.REC_BBOX:capi.REC_BBOX + 3] == 2 * par.drone_radius).all()
+        assert np.array_equal(rec[me, capi.REC_POS:capi.REC_POS + 3], want[18:PW].reshape(3, 16, 4)[:, 0, 3])
+        nb = int(rec[me, capi.REC_NBEND])
+        exp_bend = [np.asarray(par.pb[me], float)]
+        for q in range(int(sc.es0_cnt[bi, 1])):
+            aid, cs = sc.es0_alpha[bi, sc.es0_bend[bi, q]]
+            exp_bend.append(np.asarray(par.pb[aid - 1], float) if aid <= par.num_of_agents
+                            else np.asarray(sc.strep, float).reshape(-1, 2, 2)[aid - par.num_of_agents - 1, cs])
+        assert nb == len(exp_bend) and np.array_equal(rec[me, capi.REC_BEND:capi.REC_BEND + 2 * nb].reshape(nb, 2), np.stack(exp_bend))
+    assert cyc.index == 1
+    cyc.close()
+
+
+def test_replan_cycle_feedback_and_graph(capi, oracle):
+    """Records fed back through the ring: cycle k plans against the records of cycle k - 2 and post-checks against
+    those of k - 1, identically with plain launches and with CUDA-graph replay."""
+    from neptune_b200.cycle import ReplanCycle
+    par = config("obst8")
+    sc = make_scene(par, 3003, sync=False, ent_backend=capi.DeviceEntBackend(_solver(capi, par, make_scene(par, 3003, sync=False))))
+    b = sc.batch
+    runs = []
+    for graph in (False, True):
+        cyc = ReplanCycle(par, b.agent_id - 1, "cuda:0", static=(b.st_ptr, b.st_xy, sc.strep), planned=np.ones(par.num_of_agents, np.uint8))
+        cyc.seed_records(cyc.records_of(sc))
+        hin, hout = cyc.host_inputs(sc), cyc.host_outputs()
+        cyc.upload(hin)
+        outs = []
+        for k in range(6):
+            if graph and k == 1:
+                cyc.capture()          # runs cycle 1 itself, then captures
+            else:
+                cyc.step()
+            cyc.download(hout)
+            cyc.stream.synchronize()
+            outs.append((hout["coeff_out"].copy(), hout["status"].copy(), cyc.records("new").copy()))
+        cyc.check_errors()
+        assert cyc.index == 6
+        runs.append(outs)
+        cyc.close()
+    for (c0, s0, r0), (c1, s1, r1) in zip(*runs):
+        assert np.array_equal(c0, c1) and np.array_equal(s0, s1) and np.array_equal(r0, r1)
+    # the feedback matters: later cycles plan against different records than the first
+    assert not np.array_equal(runs[0][0][2], runs[0][3][2])
+    seq = runs[0][5][2][:, capi.REC_SEQ]      # committed in cycle 5, or an older record of a rejected replan
+    assert (seq <= 5).all() and (seq == 5).sum() >= par.num_of_agents // 2
 
 
 def _shim_input(par, b, a, with_ent):

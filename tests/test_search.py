@@ -326,12 +326,23 @@ def test_gpu_cycle_with_front_end(capi, oracle, cfg, seed, sync):
     cyc = ReplanCycle(par, np.arange(par.num_of_agents), dev, static=(sc.batch.st_ptr, sc.batch.st_xy, sc.strep, longest),
                       front_end=True)
     fe = search_host_inputs(sc, seed + 5)
-    hin = cyc.host_inputs(sc, fe)
-    cyc.upload(hin)
-    cyc.step()
-    torch.cuda.synchronize()
+    recs_in = cyc.records_of(sc)
+    cyc.seed_records(recs_in)
+    hin, hout = cyc.host_inputs(sc, fe), cyc.host_outputs()
+    cyc.step_from_host(hin, hout)
     cyc.check_errors()
-    o = {k: v.cpu().numpy() for k, v in cyc.o.items() if hasattr(v, "cpu")}
+    B, N, cap, NA, S = cyc.B, par.num_of_agents, par.ent_cap, par.NA, par.num_sample_per_interval
+    G = hin.G
+    o = dict(hull_xy_g=cyc.fetch("hull_xy", (G, N, 8, 24, 2), np.float64), hull_cnt_g=cyc.fetch("hull_cnt", (G, N, 8), np.int32),
+             samp_g=cyc.fetch("samp", (G, N, par.num_pol, S + 1, 2), np.float64),
+             esA_cnt=cyc.fetch("esA_cnt", (B, 2), np.int32), esA_alpha=cyc.fetch("esA_alpha", (B, cap, 2), np.int32),
+             esA_beta=cyc.fetch("esA_beta", (B, cap), np.float64), esA_bend=cyc.fetch("esA_bend", (B, cap), np.int32),
+             esA_active=cyc.fetch("esA_active", (B, NA), np.int32),
+             fe_coeff=cyc.fetch("fe_coeff", (B, 3, 8, 4), np.float64), fe_esv_cnt=cyc.fetch("fe_esv_cnt", (B, 9, 2), np.int32),
+             fe_esv_alpha=cyc.fetch("fe_esv_alpha", (B, 9, cap, 2), np.int32), fe_esv_beta=cyc.fetch("fe_esv_beta", (B, 9, cap), np.float64),
+             fe_esv_bend=cyc.fetch("fe_esv_bend", (B, 9, cap), np.int32), fe_esv_active=cyc.fetch("fe_esv_active", (B, 9, NA), np.int32),
+             fe_cost=cyc.fetch("fe_cost", (B,), np.float64), fe_n_int=cyc.fetch("fe_n_int", (B,), np.int32),
+             fe_status=hout["fe_status"], fe_solved=hout["fe_solved"], fe_stats=hout["fe_stats"])
     sb = SearchBatch(par=par, agent_id=sc.batch.agent_id.copy(), init=fe["init"], goal=fe["goal"], coeffs_z=fe["coeffs_z"],
                      group=hin["group"].copy(), hull_xy=o["hull_xy_g"], hull_cnt=o["hull_cnt_g"], samp=o["samp_g"],
                      known=sc.known.copy(), es_cnt=o["esA_cnt"], es_alpha=o["esA_alpha"], es_beta=o["esA_beta"],
@@ -339,10 +350,15 @@ def test_gpu_cycle_with_front_end(capi, oracle, cfg, seed, sync):
                      comb=fe["comb"], st_ptr=sc.batch.st_ptr, st_xy=sc.batch.st_xy, strep=strep, st_longest=longest)
     sb.validate()
     ref = _oracle_search(oracle, sb)
-    for name in ("status", "solved", "n_int", "coeff", "esv_cnt", "esv_alpha", "esv_beta", "esv_bend", "esv_active", "stats", "cost"):
-        assert np.array_equal(getattr(ref, name), o["fe_" + name]), name
     ok = ref.solved > 0
     assert ok.any()
+    for name in ("status", "solved", "stats"):
+        assert np.array_equal(getattr(ref, name), o["fe_" + name]), name
+    # per-agent outputs of the search: identical where a path was found (the others carry the host-provided path into the
+    # back end, "returning with no solution" neptune.cpp:1473-1478, and are rejected in the commit)
+    for name in ("n_int", "coeff", "esv_cnt", "esv_alpha", "esv_beta", "esv_bend", "esv_active", "cost"):
+        assert np.array_equal(getattr(ref, name)[ok], o["fe_" + name][ok]), name
+    assert np.array_equal(hout["fe_n_int"][ok], ref.n_int[ok])
     # the back end on the search's output
     bt = sc.batch
     bt.n_int[ok] = ref.n_int[ok]
@@ -350,12 +366,11 @@ def test_gpu_cycle_with_front_end(capi, oracle, cfg, seed, sync):
     bt.esv_cnt[ok], bt.esv_alpha[ok], bt.esv_active[ok] = ref.esv_cnt[ok], ref.esv_alpha[ok], ref.esv_active[ok]
     out_ref = ReplanResult.empty(bt)
     assert oracle.replan_batch(bt, out_ref, 4) == 0
-    assert np.array_equal(o["status"], out_ref.status)
-    assert np.abs(o["coeff_out"] - out_ref.coeff_out).max() <= 1e-6 * max(1.0, np.abs(out_ref.coeff_out).max())
-    assert (o["collide"][~ok] >= 1).all()
-    recs_in = capi.make_records(sc.committed)
-    assert np.array_equal(o["new_recs"][~ok], recs_in[bt.agent_id[~ok] - 1])
-    cyc.solver.close()
+    assert np.array_equal(hout["status"], out_ref.status)
+    assert np.abs(hout["coeff_out"] - out_ref.coeff_out).max() <= 1e-6 * max(1.0, np.abs(out_ref.coeff_out).max())
+    new = cyc.records("new")
+    assert np.array_equal(new[bt.agent_id[~ok] - 1], recs_in[bt.agent_id[~ok] - 1])      # no path: the previous record stays
+    cyc.close()
 
 
 @pytest.mark.gpu
