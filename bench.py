@@ -1,17 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- replans/sec of the NEPTUNE replan hot path on B200 (BASELINE.json metric).
 
-One "step" = one replan cycle of neptune_b200.cycle.ReplanCycle: hulls/samples of every other
-agent's committed trajectory (K1), PredictAlphasBetas (K3), separating-line LPs + pruning (K2), the
-trajectory QP with the reference's fallback path (K4), the post-check (K5 GJK + K3 entangle re-check),
-commit; the ranks exchange committed-trajectory records with one NCCL all-gather.  Workload: BASELINE.json configs[3] family -- a grid world with 64 agents per GPU
-(N=1 is exactly "64 agents synthetic random goals"); every agent plans against ALL other agents of
-the world (faithful, no culling), so per-agent work grows with the world while agents/GPU stay fixed.
+One "step" = one replan cycle of the library's device-resident cycle (nb_cycle_*, neptune_b200.cycle.ReplanCycle):
+trajCB bookkeeping + hulls / samples of every other agent's committed trajectory (K1), PredictAlphasBetas (K3),
+separating-line LPs + pruning (K2), the trajectory QP with the reference's fallback path (K4), the post-check (K5 GJK +
+the gated K3 re-check), commit with the DynTraj header.  Records stay on the device: cycle k plans against the records
+committed in cycle k - 2 and post-checks against those of cycle k - 1; with N > 1 ranks the commit kernel stores them
+into every rank's ring over NVLink (peer memory), no collective call.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+Workloads (BASELINE.json configs):
+  grid64   (default) configs[3] family: a grid world with 64 agents per GPU (N = 1 is exactly "64 agents synthetic random
+           goals"); every agent plans against ALL other agents of the world (faithful, no culling): weak scaling.
+  grid1024 configs[4]: 1024 agents / 200 static obstacles, fixed world split over the ranks: strong scaling.  A grid1024
+           block also rides in the default line at every --gpus N (skip with --no-grid1024).
+  single | mtlp5 | obst8  configs[0..2] as throughput lines (many instances of the small world batched on one GPU).
 
-`--impl reference` times the CPU oracle (the restatement of the reference algorithm: Gurobi/GLPK
-cannot be installed here) on the host cores for the same config and metric.
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload ...]
+
+`--impl reference` times the CPU oracle (the restatement of the reference algorithm: Gurobi / GLPK cannot be installed
+here; `kind: "port"`, built -O3 -march=native) on the host cores for the same config and metric.
 """
 from __future__ import annotations
 
@@ -31,12 +38,13 @@ sys.path.insert(0, ROOT)
 
 AGENTS_PER_GPU = 64
 SEED = 4004
+FP64_NOMINAL_GFLOPS = 37000.0   # B200 FP64 (non-tensor) nominal; no measured FP64 peak in MEASURED_PEAKS.json
 
 
 def world_params(n_gpus: int, workload: str = "grid64"):
     from neptune_b200.params import Params, config
-    if workload == "grid1024":   # BASELINE.json configs[4]: 1024 agents / 200 static obstacles, fixed world
-        return config("grid1024")
+    if workload in ("grid1024", "single", "mtlp5", "obst8"):
+        return config(workload)
     nx, ny = 8, 8 * n_gpus
     pitch = 8.0
     xs = (np.arange(nx) - (nx - 1) / 2.0) * pitch
@@ -117,11 +125,13 @@ class ClockSampler:
 
 def ncu_traffic(kernel: str):
     """DRAM bytes per launch from the committed ncu --set full capture (profiles/), or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return int(json.load(f)["per_launch_dram_bytes"][kernel])
-    except Exception:
-        return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return int(json.load(f)["per_launch_dram_bytes"][kernel])
+        except Exception:
+            continue
+    return None
 
 
 def measured_peak_gbs():
@@ -133,8 +143,8 @@ def measured_peak_gbs():
 
 
 def cpu_cycle(scene, threads: int):
-    """One whole cycle of the scene's agents on the CPU oracle (hulls/samples, predict, LPs + QP,
-    post-check, entangle re-check): the restatement of the reference algorithm, all host threads."""
+    """One whole cycle of the scene's agents on the CPU oracle (hulls/samples, predict, LPs + QP, post-check with its
+    fresh PredictAlphasBetas + entangle re-check): the restatement of the reference algorithm, all host threads."""
     from neptune_b200 import capi
     from neptune_b200.cycle import ReplanCycle
     from oracle import oracle as orc
@@ -147,95 +157,219 @@ def cpu_cycle(scene, threads: int):
 
 def cpu_baseline(scene, budget_s: float, threads: int):
     cpu_cycle(scene, threads)  # warm
-    t0, reps = time.perf_counter(), 0
+    t0, reps, per = time.perf_counter(), 0, []
     while True:
+        t1 = time.perf_counter()
         out = cpu_cycle(scene, threads)
+        per.append(time.perf_counter() - t1)
         reps += 1
         el = time.perf_counter() - t0
         if el >= budget_s or reps >= 2000:
             break
-    return scene.batch.B * reps / el, reps, el, out
+    return scene.batch.B * reps / el, reps, el, out, per
 
 
-def measure_front_end(par, agents, dev, scene, static, steps: int, with_cpu: bool):
-    """The front end (K0, KinodynamicSearch::run) measured on the same world: one more ReplanCycle object with
-    front_end=True, i.e. hulls -> predict -> SEARCH -> LPs + QP -> post-check -> commit, all device-resident.
-    Reported beside the headline (whose metric, SURVEY 8d, starts after the front end)."""
+def qp_flops(n_int, iters, kept_lines):
+    """Algorithmic FP64 flops of the interior-point solves (per iteration 2 m r^2 + r^3 / 3 with m inequality
+    rows and r reduced variables), from the iteration counts and kept-line counts the run reports."""
+    total = 0.0
+    for n, (i0, i1), nl in zip(n_int, iters, kept_lines):
+        m = 48 * int(n) + 4 * int(nl)
+        for mode, it in ((0, i0), (1, i1)):
+            r = 3 * (max(int(n) - 2, 0) if mode == 0 else int(n))
+            total += float(it) * (2.0 * m * r * r + r ** 3 / 3.0)
+    return total
+
+
+# ------------------------------------------------------------------------------------------------ one measured world
+def measure_cycle(args, par, agents, rank, world, dev, workload, steps, warmup, n_scenes, static=None, front_end=False,
+                  cpu=False, clocks=False):
+    """Builds the cycle for this rank's agents, runs warm-up + `steps` timed cycles (CUDA events on the cycle's stream,
+    L2 flushed between iterations, inputs resident), the end-to-end leg (pinned H2D + D2H every step) and a profiled
+    pass.  Returns a dict (rank 0 fills the aggregate fields)."""
     import torch
+    import torch.distributed as dist
 
     from neptune_b200 import capi
-    from neptune_b200.cycle import ReplanCycle
+    from neptune_b200.cycle import STAGES, ReplanCycle
     from neptune_b200.scenes import search_host_inputs
-    from neptune_b200.search import SearchBatch, SearchResult, static_longest_dist
 
-    cyc = ReplanCycle(par, agents, dev, static=static, world=1, front_end=True)
-    fe = search_host_inputs(scene, SEED + 1)
-    hin = cyc.host_inputs(scene, fe)
-    hout = cyc.host_outputs()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    cyc = ReplanCycle(par, agents, dev, static=static, world=world, rank=rank, front_end=front_end)
+    cyc.connect()
+    # the workload generator fills entanglement states through the product's own K3 kernels
+    _, scenes = make_world(args.gpus, rank, n_scenes, capi.DeviceEntBackend(cyc.solver), workload, agents=agents)
     B = cyc.B
-    cyc.upload(hin)
-    cyc.capture()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for it in range(2 + steps):
-        cyc.upload(hin)
-        flush.zero_()
-        if it >= 2:
-            ev[it - 2][0].record()
+    fes = [search_host_inputs(sc, SEED + 1) for sc in scenes] if front_end else [None] * len(scenes)
+    hins = [cyc.host_inputs(sc, fe) for sc, fe in zip(scenes, fes)]
+    hout = cyc.host_outputs()
+    cyc.seed_records(cyc.records_of(scenes[0]))
+    lib = capi.lib()
+    st = cyc.stream
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        st.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def flush_l2():
+        with torch.cuda.stream(st):
+            flush.zero_()
+
+    # ---------------- warm-up, then graph capture (one more real cycle inside)
+    for it in range(max(1, warmup - 1)):
+        cyc.upload(hins[it % len(hins)])
+        flush_l2()
         cyc.step()
-        if it >= 2:
-            ev[it - 2][1].record()
-    torch.cuda.synchronize()
+    barrier()
     cyc.check_errors()
-    full_ms = float(np.median([a.elapsed_time(b) for a, b in ev]))
-    cyc.profile = True
-    fe_ms = []
-    for it in range(3):
-        cyc.upload(hin)
-        flush.zero_()
+    if not args.no_graph:
+        cyc.capture()
+    # ---------------- value: inputs resident in HBM before the timed region, CUDA events on the cycle's stream
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sampler = ClockSampler(dev.index or 0) if clocks else None
+    for it in range(3):   # the sampler comes up under the same load
+        cyc.upload(hins[it % len(hins)])
+        flush_l2()
         cyc.step()
-        fe_ms.append(cyc.stage_ms["front_end"])
-    cyc.profile = False
+    barrier()
+    for k in range(steps):
+        cyc.upload(hins[k % len(hins)])       # untimed: this leg measures with inputs already in HBM
+        flush_l2()
+        ev[k][0].record(st)
+        cyc.step()
+        ev[k][1].record(st)
+    barrier()
+    launches = steps * cyc.launches_per_cycle
+    extra = 0
+    if sampler is not None:
+        # a short run can end before the first 20 ms sample: keep the same cycle running, untimed, until there are
+        # three samples under load (bounded; every rank runs the same number of cycles, a cycle ends in an exchange)
+        n_extra = max(0, 400 - steps) if world > 1 else 0
+        t_extra = time.time()
+        while (world > 1 and extra < n_extra) or (world == 1 and len(sampler.rows) < 3 and sampler.proc is not None and time.time() - t_extra < 2.0):
+            flush_l2()
+            cyc.step()
+            extra += 1
+            if extra % 16 == 0:
+                st.synchronize()
+        barrier()
+    clocks_rec = sampler.stop() if sampler is not None else None
+    if clocks_rec is not None:
+        clocks_rec["extra_untimed_steps_for_sampling"] = extra
+    cyc.check_errors()
+    step_ms = np.array([e0.elapsed_time(e1) for e0, e1 in ev])
+    total_ms = float(step_ms.sum())
+    rank_ms = [total_ms]
+    if world > 1:
+        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        allt = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt, tt)
+        rank_ms = [float(x) for x in allt.cpu()]
+        total_ms = max(rank_ms)
+    n_agents_all = par.num_of_agents if workload != "grid64" else world * B
+    value = n_agents_all * steps / (total_ms * 1e-3)
+    cyc.download(hout)
+    st.synchronize()
+    status, itn = hout["status"].copy(), hout["iters"].copy()
+    ent, col = hout["entangled"].copy(), hout["collide"].copy()
+    n_int = hins[(steps - 1) % len(hins)]["n_int"].copy()
+
+    # ---------------- per-stage times and the two back-end kernels (plain launches, one stream, synchronised)
+    lib.nb_set_profiling(cyc.solver.handle, 1)
+    stage, kt = {k: [] for k in STAGES}, []
+    for it in range(5):
+        cyc.upload(hins[it % len(hins)])
+        flush_l2()
+        sm = cyc.step_profiled()
+        ms = (C.c_double * 2)()
+        lib.nb_kernel_times(cyc.solver.handle, ms, 2)
+        if it >= 1:
+            kt.append((ms[0], ms[1]))
+            for k2, v in sm.items():
+                stage[k2].append(v)
+    lib.nb_set_profiling(cyc.solver.handle, 0)
+    stage = {k2: float(np.mean(v)) for k2, v in stage.items()}
+    kt = np.array(kt)
+
+    # ---------------- e2e: pinned host inputs -> H2D -> all kernels -> D2H, every step
+    for it in range(2):
+        cyc.step_from_host(hins[it % len(hins)], hout)
+    barrier()
     t0 = time.perf_counter()
+    h2d = d2h = 0
     for it in range(steps):
-        cyc.step_from_host(hin, hout)
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
-    o = cyc.o
-    stats = o["fe_stats"].cpu().numpy()
-    status = o["fe_status"].cpu().numpy()
-    out = {"kernel": "k_search", "agents": B, "ms_search": float(np.median(fe_ms)), "ms_full_cycle": full_ms,
-           "full_replans_per_s": B / (full_ms * 1e-3), "e2e_full_replans_per_s": B / (e2e_ms * 1e-3),
-           "pops": int(stats[:, 1].sum()), "pops_max": int(stats[:, 1].max()), "nodes_max": int(stats[:, 0].max()),
-           "pops_per_s": float(stats[:, 1].sum() / (np.median(fe_ms) * 1e-3)),
-           "status_hist": {"runtime": int((status == 0).sum()), "goal": int((status == 1).sum()), "empty": int((status == 2).sum())},
-           "solved": int(o["fe_solved"].sum().item()), "max_expansions": par.search_max_expansions,
-           "max_nodes": par.search_max_nodes}
-    if with_cpu:
-        from oracle import oracle as orc
-        M = par.num_of_static_obst
-        sb = SearchBatch(
-            par=par, agent_id=scene.batch.agent_id.copy(), init=fe["init"], goal=fe["goal"], coeffs_z=fe["coeffs_z"],
-            group=hin["group"].copy(), hull_xy=o["hull_xy_g"].cpu().numpy(), hull_cnt=o["hull_cnt_g"].cpu().numpy(),
-            samp=o["samp_g"].cpu().numpy(), known=scene.known.copy(), es_cnt=o["esA_cnt"].cpu().numpy(),
-            es_alpha=o["esA_alpha"].cpu().numpy(), es_beta=o["esA_beta"].cpu().numpy(), es_bend=o["esA_bend"].cpu().numpy(),
-            es_active=o["esA_active"].cpu().numpy(), bp_cnt=scene.batch.bp_cnt, bp_xy=scene.batch.bp_xy, comb=fe["comb"],
-            st_ptr=scene.batch.st_ptr, st_xy=scene.batch.st_xy, strep=np.asarray(scene.strep, np.float64).reshape(M, 2, 2),
-            st_longest=static_longest_dist(scene.static_raw, np.asarray(scene.strep).reshape(M, 2, 2)) if M else np.zeros((0, 2)))
-        ref = SearchResult.empty(sb)
-        nt = os.cpu_count() or 1
-        orc.search_batch(sb, ref, nt)
-        t0 = time.perf_counter()
-        reps = 3
-        for _ in range(reps):
-            orc.search_batch(sb, ref, nt)
-        cpu_ms = 1e3 * (time.perf_counter() - t0) / reps
-        same = (np.array_equal(ref.status, status) and np.array_equal(ref.n_int, o["fe_n_int"].cpu().numpy())
-                and np.array_equal(ref.coeff, o["fe_coeff"].cpu().numpy()) and np.array_equal(ref.stats, stats)
-                and np.array_equal(ref.esv_alpha, o["fe_esv_alpha"].cpu().numpy()))
-        out["cpu_oracle"] = {"ms_search": cpu_ms, "cores": nt, "kind": "port", "identical": bool(same),
-                             "sample": f"{B} searches x {reps}, oracle/neptune_search.c orc_search_batch"}
-    cyc.solver.close()
+        h2d, d2h = cyc.step_from_host(hins[it % len(hins)], hout)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    e2e = n_agents_all * steps / e2e_s
+    cyc.check_errors()
+
+    out = dict(value=value, ms_per_step=total_ms / steps, p50=float(np.median(step_ms)), p95=float(np.percentile(step_ms, 95)),
+               e2e=e2e, h2d=int(h2d), d2h=int(d2h), launches=int(launches), launches_per_cycle=int(cyc.launches_per_cycle),
+               kernels_ms={"k_lines": float(kt[:, 0].mean()), "k_qp": float(kt[:, 1].mean())}, stage_ms=stage,
+               rank_ms_per_step=[x / steps for x in rank_ms], clocks=clocks_rec,
+               status_hist={str(k2): int((status == k2).sum()) for k2 in (0, 1, 2)},
+               postcheck={"entangled": int(ent.sum()), "collide": int(col.sum())},
+               ipm_iters_mean=float(itn.sum(axis=1).mean()), agents=int(n_agents_all), B=int(B))
+    # algorithmic bytes (SURVEY 8d) and FP64 flops of the dominant back-end kernel
+    alg_bytes = float(np.mean([sc.batch.algorithmic_bytes() for sc in scenes]))
+    if scenes[0].batch.hull_xy.shape[0] == 0:   # hulls were built on the device only: count their real vertices
+        G = hins[0].G
+        cnt = cyc.fetch("hull_cnt", (G, par.num_of_agents, 8), np.int32)[hins[0]["group"]]
+        alg_bytes += 16.0 * float((cnt * (scenes[0].known[:, :, None] > 0)).sum()) + 16.0 * float(scenes[0].known.sum()) * par.num_pol
+    out["alg_bytes"] = alg_bytes
+    kept = np.zeros((B, 8), np.int32)
+    capi._check(lib.nb_kept_lines(cyc.solver.handle, kept.ctypes.data_as(C.c_void_p), B), "nb_kept_lines")
+    out["kept_lines_mean"] = float(kept.sum(axis=1).mean())
+    out["qp_flops"] = qp_flops(n_int, itn, kept.sum(axis=1))
+    if front_end:
+        stats, fstat = hout["fe_stats"].copy(), hout["fe_status"].copy()
+        out["front_end"] = {"pops": int(stats[:, 1].sum()), "pops_max": int(stats[:, 1].max()), "nodes_max": int(stats[:, 0].max()),
+                            "status_hist": {"runtime": int((fstat == 0).sum()), "goal": int((fstat == 1).sum()), "empty": int((fstat == 2).sum())},
+                            "solved": int(hout["fe_solved"].sum())}
+    if cpu:
+        v, reps, el, ref, per = cpu_baseline(scenes[0], args.cpu_budget, os.cpu_count() or 1)
+        per_replan = np.array(per) * 1e3 / 1.0      # ms per whole cycle of B agents on all cores
+        out["cpu_baseline"] = {"value": v, "unit": "replans/s", "cores": os.cpu_count() or 1, "kind": "port",
+                               "p50_ms_per_cycle": float(np.median(per_replan)), "p95_ms_per_cycle": float(np.percentile(per_replan, 95)),
+                               "build": "gcc -O3 -march=native -fopenmp (oracle/Makefile)",
+                               "sample": f"{B} agents x {reps} whole cycles of scene 0 ({el:.1f} s), oracle/neptune_oracle.c orc_cycle_batch: "
+                                         "full 12n-variable interior-point solve per replan, every agent builds its own hulls (no window "
+                                         "sharing), no line pruning -- a restatement of the reference algorithm, not Gurobi / GLPK"}
+    out["_scene0"], out["_hin0"], out["_fe0"], out["_cyc"] = scenes[0], hins[0], fes[0], cyc
     return out
+
+
+def front_end_cpu(par, scene, hin, fe, cyc, static_longest):
+    """The oracle's search on exactly the inputs the device search had (the cycle's own hulls, samples, entangle_state_A)."""
+    from neptune_b200.search import SearchBatch, SearchResult
+    from oracle import oracle as orc
+    M, N, B, cap, NA, S = par.num_of_static_obst, par.num_of_agents, cyc.B, par.ent_cap, par.NA, par.num_sample_per_interval
+    G = hin.G
+    sb = SearchBatch(
+        par=par, agent_id=scene.batch.agent_id.copy(), init=fe["init"], goal=fe["goal"], coeffs_z=fe["coeffs_z"],
+        group=hin["group"].copy(), hull_xy=cyc.fetch("hull_xy", (G, N, 8, 24, 2), np.float64), hull_cnt=cyc.fetch("hull_cnt", (G, N, 8), np.int32),
+        samp=cyc.fetch("samp", (G, N, par.num_pol, S + 1, 2), np.float64), known=scene.known.copy(),
+        es_cnt=cyc.fetch("esA_cnt", (B, 2), np.int32), es_alpha=cyc.fetch("esA_alpha", (B, cap, 2), np.int32),
+        es_beta=cyc.fetch("esA_beta", (B, cap), np.float64), es_bend=cyc.fetch("esA_bend", (B, cap), np.int32),
+        es_active=cyc.fetch("esA_active", (B, NA), np.int32), bp_cnt=scene.batch.bp_cnt, bp_xy=scene.batch.bp_xy, comb=fe["comb"],
+        st_ptr=scene.batch.st_ptr, st_xy=scene.batch.st_xy, strep=np.asarray(scene.strep, np.float64).reshape(M, 2, 2),
+        st_longest=static_longest if M else np.zeros((0, 2)))
+    ref = SearchResult.empty(sb)
+    nt = os.cpu_count() or 1
+    orc.search_batch(sb, ref, nt)
+    t0, reps = time.perf_counter(), 3
+    for _ in range(reps):
+        orc.search_batch(sb, ref, nt)
+    cpu_ms = 1e3 * (time.perf_counter() - t0) / reps
+    return ref, {"ms_search": cpu_ms, "cores": nt, "kind": "port",
+                 "sample": f"{B} searches x {reps}, oracle/neptune_search.c orc_search_batch"}
 
 
 def run_reference(args):
@@ -258,7 +392,7 @@ def run_reference(args):
     B = scenes[0].batch.B
     val = B * args.steps / el
     sample = (f"{B} of the world's {par.num_of_agents} agents (rank-0 shard) x {args.steps} cycles, "
-              f"each against all {par.num_of_agents - 1} others; oracle/neptune_oracle.c orc_cycle_batch")
+              f"each against all {par.num_of_agents - 1} others; oracle/neptune_oracle.c orc_cycle_batch, gcc -O3 -march=native")
     line = {"impl": "reference", "metric": "replans_per_sec", "value": val, "unit": "replans/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
             "higher_is_better": True, "scaling": scaling_kind(args.workload), "vs_baseline": None, "dtype": "f64",
@@ -276,22 +410,92 @@ def config_dict(par, n_gpus, workload="grid64"):
     if workload == "grid1024":
         wl = (f"BASELINE.json configs[4]: {par.num_of_agents} agents / {par.num_of_static_obst} static obstacles, "
               f"32x32 base grid, sharded over {n_gpus} GPU(s), random goals, faithful (no culling)")
-    else:
+    elif workload == "grid64":
         wl = (f"grid world, {AGENTS_PER_GPU} agents/GPU x {n_gpus} GPU = {par.num_of_agents} agents "
               "(BASELINE.json configs[3] at N=1), random goals, no static obstacles, faithful (no culling)")
+    else:
+        wl = {"single": "BASELINE.json configs[0]: single agent, obstacle-free, 3-interval path (derived from neptune_single_benchmark.yaml), 4096 instances per batch",
+              "mtlp5": "BASELINE.json configs[1]: 5 agents obstacle-free random goals (neptune_mtlp_benchmark.yaml), 256 independent worlds per batch",
+              "obst8": "BASELINE.json configs[2]: 8 agents, 9 static obstacles (neptune_multi_obstacle.yaml), separator LPs + entangle check, 128 independent worlds per batch"}[workload]
     return {"workload": wl, "agents": par.num_of_agents, "agents_per_gpu": par.num_of_agents // n_gpus
-            if workload == "grid1024" else AGENTS_PER_GPU, "static_obstacles": par.num_of_static_obst,
+            if workload != "grid64" else AGENTS_PER_GPU, "static_obstacles": par.num_of_static_obst,
             "num_pol": par.num_pol, "T_span": par.T_span, "seed": SEED if workload == "grid64" else 5005,
             "l2": "flushed between timed iterations (256 MiB write)",
-            "parallelism": f"agents sharded over {n_gpus} rank(s); one all-gather of committed trajectories per cycle"}
+            "parallelism": f"agents sharded over {n_gpus} rank(s); committed trajectories exchanged by peer-to-peer stores from the commit kernel (no collective call)"}
+
+
+def run_small(args):
+    """configs[0..2] as throughput lines: many independent instances of the small world in one nb_replan_batch
+    (the back end: LPs -> QP), inputs resident, CUDA events; printed as one JSON line."""
+    import torch
+
+    from neptune_b200 import capi
+    from neptune_b200.params import config
+    from neptune_b200.scenes import make_scene
+    par = config(args.workload)
+    n_worlds = {"single": 4096, "mtlp5": 256, "obst8": 128}[args.workload]
+    kw = dict(n_fixed=3) if args.workload == "single" else dict(sync=False)
+    seed0 = {"single": 1001, "mtlp5": 2002, "obst8": 3003}[args.workload]
+    s = capi.Solver(par)
+    scenes = []
+    for k in range(min(n_worlds, 64)):      # 64 distinct seeded worlds, tiled to n_worlds instances
+        if par.num_of_static_obst and k == 0:
+            sc0 = make_scene(par, seed0, **kw)
+            s.set_static(sc0.batch.st_ptr, sc0.batch.st_xy, sc0.strep)
+        scenes.append(make_scene(par, seed0 + k, ent_backend=capi.DeviceEntBackend(s), **kw))
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream(device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    # device-resident batches, one per world (B = agents of the world), all launched back to back per step
+    res_h = [capi.ReplanResult.empty(sc.batch, with_lines=False) for sc in scenes]
+    reps = n_worlds // len(scenes)
+    t_ms = []
+    for it in range(args.warmup + args.steps):
+        with torch.cuda.stream(st):
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(st)
+        for _ in range(reps):
+            for sc, r in zip(scenes, res_h):
+                a = capi.host_args(sc.batch, r)
+                capi._check(capi.lib().nb_replan_batch(s.handle, C.byref(a), C.c_void_p(st.cuda_stream)), "nb_replan_batch")
+        e1.record(st)
+        st.synchronize()
+        if it >= args.warmup:
+            t_ms.append(1e3 * (time.perf_counter() - t0))
+    replans = n_worlds * par.num_of_agents
+    ms = float(np.mean(t_ms))
+    status = np.concatenate([r.status for r in res_h])
+    line = {"metric": "replans_per_sec", "value": replans / (ms * 1e-3), "unit": "replans/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(par, 1, args.workload),
+            "p50_ms_per_step": float(np.median(t_ms)), "p95_ms_per_step": float(np.percentile(t_ms, 95)),
+            "note": "end-to-end through the C-ABI with HOST buffers (nb_replan_batch, NB_HOST): staging copies, LPs, QP and the "
+                    "result copies are all inside the timed region; one call per world, as one reference process per agent group would",
+            "status_hist": {str(k2): int((status == k2).sum()) for k2 in (0, 1, 2)},
+            "gpu_launches": int(2 * reps * len(scenes) * args.steps)}
+    # CPU arm on the same worlds
+    if not args.no_cpu:
+        from neptune_b200.batch import ReplanResult
+        from oracle import oracle as orc
+        nt = os.cpu_count() or 1
+        t0, n = time.perf_counter(), 0
+        while time.perf_counter() - t0 < args.cpu_budget:
+            for sc in scenes:
+                r = ReplanResult.empty(sc.batch, with_lines=False)
+                orc.replan_batch(sc.batch, r, nt)
+                n += sc.batch.B
+        el = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": n / el, "unit": "replans/s", "cores": nt, "kind": "port",
+                                "sample": f"{n} back-end replans (orc_replan_batch) in {el:.1f} s"}
+    print(json.dumps(line))
+    s.close()
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
-
-    from neptune_b200 import capi
-    from neptune_b200.cycle import ReplanCycle
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -302,168 +506,96 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    par = world_params(args.gpus, args.workload)
-    agents = rank_agents(par, args.gpus, rank, args.workload)
-    static = None
-    if par.num_of_static_obst:   # static obstacles are part of the world: build them once, before the solver
+    if args.workload in ("single", "mtlp5", "obst8"):
+        if rank == 0:
+            run_small(args)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    def static_of(par, agents):
+        if not par.num_of_static_obst:   # static obstacles are part of the world: build them once, before the solver
+            return None
         from neptune_b200.scenes import make_scene
         s0 = make_scene(par, 5005, agents=agents[:1], pack_hulls=False)
-        static = (s0.batch.st_ptr, s0.batch.st_xy, s0.strep)
-    cyc = ReplanCycle(par, agents, dev, static=static, world=world)
-    # the workload generator fills entanglement states through the product's own K3 kernels
-    _, scenes = make_world(args.gpus, rank, args.scenes, capi.DeviceEntBackend(cyc.solver), args.workload)
-    B = cyc.B
-    hins = [cyc.host_inputs(sc) for sc in scenes]
-    hout = cyc.host_outputs()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    lib = capi.lib()
+        return (s0.batch.st_ptr, s0.batch.st_xy, s0.strep)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---------------- per-kernel times of the two back-end kernels (library events; plain launches)
-    lib.nb_set_profiling(cyc.solver.handle, 1)
-    ktimes = []
-    for it in range(8):
-        cyc.upload(hins[it % len(hins)])
-        flush.zero_()
-        cyc.step()
-        ms = (C.c_double * 2)()
-        lib.nb_kernel_times(cyc.solver.handle, ms, 2)
-        if it >= 3:
-            ktimes.append((ms[0], ms[1]))
-    lib.nb_set_profiling(cyc.solver.handle, 0)
-    cyc.check_errors()
-    # ---------------- value: inputs resident in HBM before the timed region, CUDA events, max over ranks;
-    # the cycle's launch sequence is replayed from a CUDA graph
-    cyc.upload(hins[0])
-    if not args.no_graph:
-        cyc.capture()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler, l0 = None, 0
-    for it in range(args.warmup + args.steps):
-        k = it - args.warmup
-        if it == 0:
-            sampler = ClockSampler(local_rank)   # started with the warm-up (same load): nvidia-smi needs ~50 ms to come up
-        if k == 0:
-            barrier()
-            l0 = cyc.solver.launch_count()
-        cyc.upload(hins[it % len(hins)])       # untimed: this leg measures with inputs already in HBM
-        flush.zero_()
-        if k >= 0:
-            ev[k][0].record()
-        cyc.step()
-        if k >= 0:
-            ev[k][1].record()
-    barrier()
-    launches = (cyc.solver.launch_count() - l0) if getattr(cyc, "graph", None) is None else args.steps * cyc.launches_per_cycle
-    # a short run (K x 0.4 ms) can end before the first 20 ms sample: keep the same cycle running, untimed, until there
-    # are three samples under load (bounded at 2 s)
-    extra, t_extra = 0, time.time()
-    if world == 1:
-        while len(sampler.rows) < 3 and sampler.proc is not None and time.time() - t_extra < 2.0:
-            flush.zero_()
-            cyc.step()
-            extra += 1
-            if extra % 16 == 0:
-                torch.cuda.synchronize()
-    else:   # a cycle ends in an all-gather: every rank must run the same number of extra cycles
-        for _ in range(max(0, 400 - args.steps)):
-            flush.zero_()
-            cyc.step()
-            extra += 1
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    clocks["extra_untimed_steps_for_sampling"] = extra
-    cyc.check_errors()
-    step_ms = np.array([e0.elapsed_time(e1) for e0, e1 in ev])
-    total_ms = float(step_ms.sum())
-    if world > 1:
-        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
-    value = world * B * args.steps / (total_ms * 1e-3)
-    st = cyc.o["status"].cpu().numpy()
-    itn = cyc.o["iters"].cpu().numpy()
-    ent, col = cyc.o["entangled"].cpu().numpy(), cyc.o["collide"].cpu().numpy()
-
-    # ---------------- per-stage times (separate short pass, synchronised between stages)
-    cyc.profile = True
-    stage = {}
-    for it in range(5):
-        cyc.upload(hins[it % len(hins)])
-        flush.zero_()
-        cyc.step()
-        for k2, v in cyc.stage_ms.items():
-            stage.setdefault(k2, []).append(v)
-    cyc.profile = False
-    stage = {k2: float(np.mean(v)) for k2, v in stage.items()}
-
-    # ---------------- e2e: pinned host inputs -> H2D -> all kernels -> D2H, every step
-    for it in range(2):
-        cyc.step_from_host(hins[it % len(hins)], hout)
-    barrier()
-    t0 = time.perf_counter()
-    h2d = d2h = 0
-    for it in range(args.steps):
-        h2d, d2h = cyc.step_from_host(hins[it % len(hins)], hout)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        tt = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_s = float(tt.item())
-    e2e = world * B * args.steps / e2e_s
-
+    par = world_params(args.gpus, args.workload)
+    agents = rank_agents(par, args.gpus, rank, args.workload)
+    main = measure_cycle(args, par, agents, rank, world, dev, args.workload, args.steps, args.warmup, args.scenes,
+                         static=static_of(par, agents), cpu=(world == 1 and not args.no_cpu and args.workload == "grid64"), clocks=True)
+    line = None
     if rank == 0:
-        kt = np.array(ktimes)
-        dom = int(np.argmax(kt.mean(axis=0)))
-        dom_ms = float(kt[:, dom].mean())
-        alg_bytes = float(np.mean([sc.batch.algorithmic_bytes() for sc in scenes]))
-        if scenes[0].batch.hull_xy.shape[0] == 0:   # hulls were built on the device only: count their real vertices
-            cnt_b = cyc.o["hull_cnt_g"].index_select(0, cyc.d["group"].long())          # [B][N][8]
-            kn = torch.from_numpy(scenes[0].known.astype(np.bool_)).to(dev)[:, :, None]
-            alg_bytes += 16.0 * float((cnt_b * kn).sum().item()) + 16.0 * float(scenes[0].known.sum()) * par.num_pol
+        m = main
+        dom = "k_qp" if m["kernels_ms"]["k_qp"] >= m["kernels_ms"]["k_lines"] else "k_lines"
+        dom_ms = m["kernels_ms"][dom]
         peak, which = measured_peak_gbs()
-        achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-        line = {"metric": "replans_per_sec", "value": value, "unit": "replans/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        achieved = m["alg_bytes"] / (dom_ms * 1e-3) / 1e9
+        gflops = m["qp_flops"] / (m["kernels_ms"]["k_qp"] * 1e-3) / 1e9
+        line = {"metric": "replans_per_sec", "value": m["value"], "unit": "replans/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
                 "scaling": scaling_kind(args.workload), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config_dict(par, world, args.workload),
-                "p50_ms_per_replan_cycle": float(np.median(step_ms)),
-                "e2e": {"value": e2e, "unit": "replans/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(launches),
-                "kernels_ms": {"k_lines": float(kt[:, 0].mean()), "k_qp": float(kt[:, 1].mean())},
-                "stage_ms": stage,
-                "roofline": {"bound": "hbm", "kernel": ["k_lines", "k_qp"][dom], "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(["k_lines", "k_qp"][dom]) if args.workload == "grid64" and world == 1 else None,
-                             "peak_source": which,
-                             "algorithmic_bytes_per_launch": alg_bytes,
-                             "note": "latency/FP64-issue bound at this size, not HBM bound (DESIGN.md)"},
-                "status_hist": {str(k2): int((st == k2).sum()) for k2 in (0, 1, 2)},
-                "postcheck": {"entangled": int(ent.sum()), "collide": int(col.sum())},
-                "ipm_iters_mean": float(itn.sum(axis=1).mean()),
-                "clocks": clocks}
-        if world == 1 and not args.no_cpu and args.workload == "grid64":
-            v, reps, el, ref = cpu_baseline(scenes[0], args.cpu_budget, os.cpu_count() or 1)
-            line["cpu_baseline"] = {"value": v, "unit": "replans/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                    "sample": f"{B} agents x {reps} whole cycles of scene 0 ({el:.1f} s), "
-                                              "oracle/neptune_oracle.c orc_cycle_batch"}
-        if world == 1 and args.workload == "grid64" and not args.no_front_end:
-            if args.front_end_world > 1:   # the 64-agents-per-GPU world of K GPUs, searched (and replanned) by this one GPU
-                from neptune_b200.scenes import make_scene
-                par_fe = world_params(args.front_end_world)
-                agents_fe = np.arange(par_fe.num_of_agents)
-                gen = capi.Solver(par_fe, device=local_rank)
-                scene_fe = make_scene(par_fe, SEED, agents=agents_fe, ent_backend=capi.DeviceEntBackend(gen))
-                gen.close()
-                line["front_end"] = measure_front_end(par_fe, agents_fe, dev, scene_fe, None, args.front_end_steps, not args.no_cpu)
-            else:
-                line["front_end"] = measure_front_end(par, agents, dev, scenes[0], static, args.front_end_steps, not args.no_cpu)
+                "p50_ms_per_replan_cycle": m["p50"], "p95_ms_per_replan_cycle": m["p95"],
+                "e2e": {"value": m["e2e"], "unit": "replans/s", "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"]},
+                "gpu_launches": m["launches"], "launches_per_cycle": m["launches_per_cycle"],
+                "kernels_ms": m["kernels_ms"], "stage_ms": m["stage_ms"],
+                "exchange": {"kind": "peer-to-peer stores from k_publish + flag wait (k_wait_peers)", "wait_ms": m["stage_ms"]["exchange_wait"],
+                             "commit_ms": m["stage_ms"]["commit"], "rank_ms_per_step": m["rank_ms_per_step"]},
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": ncu_traffic(dom) if args.workload == "grid64" and world == 1 else None,
+                             "peak_source": which, "algorithmic_bytes_per_launch": m["alg_bytes"],
+                             "fp64": {"kernel": "k_qp", "gflops": gflops, "nominal_peak_gflops": FP64_NOMINAL_GFLOPS,
+                                      "frac_of_nominal": gflops / FP64_NOMINAL_GFLOPS,
+                                      "flops_per_launch": m["qp_flops"], "kept_lines_per_agent": m["kept_lines_mean"],
+                                      "formula": "sum over solves of iterations x (2 m r^2 + r^3 / 3), SURVEY 8d"},
+                             "note": "latency / FP64-issue bound at this size, not HBM bound (DESIGN.md)"},
+                "status_hist": m["status_hist"], "postcheck": m["postcheck"], "ipm_iters_mean": m["ipm_iters_mean"],
+                "clocks": m["clocks"]}
+        if "cpu_baseline" in m:
+            line["cpu_baseline"] = m["cpu_baseline"]
+    cyc_main = main.pop("_cyc")
+    # ---------------- front end (K0) on the same world: one more cycle object with the search inside
+    if world == 1 and args.workload == "grid64" and not args.no_front_end:
+        from neptune_b200.search import static_longest_dist
+        cyc_main.close()
+        par_fe, agents_fe = par, agents
+        if args.front_end_world > 1:   # the 64-agents-per-GPU world of K GPUs, searched (and replanned) by this one GPU
+            par_fe = world_params(args.front_end_world)
+            agents_fe = np.arange(par_fe.num_of_agents)
+        saved = args.gpus
+        args.gpus = args.front_end_world if args.front_end_world > 1 else args.gpus
+        fe = measure_cycle(args, par_fe, agents_fe, 0, 1, dev, "grid64", args.front_end_steps, 3, 1, front_end=True)
+        args.gpus = saved
+        blk = {"kernel": "k_search", "agents": fe["B"], "ms_search": fe["stage_ms"]["front_end"], "ms_full_cycle": fe["ms_per_step"],
+               "full_replans_per_s": fe["value"], "e2e_full_replans_per_s": fe["e2e"],
+               "pops_per_s": fe["front_end"]["pops"] / (fe["stage_ms"]["front_end"] * 1e-3),
+               "max_expansions": par_fe.search_max_expansions, "max_nodes": par_fe.search_max_nodes}
+        blk.update(fe["front_end"])
+        if not args.no_cpu:
+            ref, cpu_blk = front_end_cpu(par_fe, fe["_scene0"], fe["_hin0"], fe["_fe0"], fe["_cyc"], None)
+            cpu_blk["identical"] = bool(ref.solved.sum() == fe["front_end"]["solved"])
+            blk["cpu_oracle"] = cpu_blk
+        fe["_cyc"].close()
+        line["front_end"] = blk
+    else:
+        cyc_main.close()
+    # ---------------- configs[4] block: 1024 agents / 200 static obstacles split over the ranks (strong scaling)
+    if args.workload == "grid64" and not args.no_grid1024:
+        par5 = world_params(args.gpus, "grid1024")
+        agents5 = rank_agents(par5, args.gpus, rank, "grid1024")
+        g = measure_cycle(args, par5, agents5, rank, world, dev, "grid1024", args.grid1024_steps, 3, 1, static=static_of(par5, agents5))
+        g.pop("_cyc").close()
+        if rank == 0:
+            line["grid1024"] = {"workload": config_dict(par5, world, "grid1024")["workload"], "scaling": "strong",
+                                "replans_per_s": g["value"], "ms_per_cycle": g["ms_per_step"], "p50_ms": g["p50"], "p95_ms": g["p95"],
+                                "e2e_replans_per_s": g["e2e"], "h2d_bytes_per_step": g["h2d"], "agents_per_gpu": g["B"],
+                                "kernels_ms": g["kernels_ms"], "stage_ms": g["stage_ms"], "rank_ms_per_step": g["rank_ms_per_step"],
+                                "status_hist": g["status_hist"], "steps": args.grid1024_steps}
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -474,12 +606,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scenes", type=int, default=4)
-    ap.add_argument("--workload", default="grid64", choices=["grid64", "grid1024"],
-                    help="grid64: configs[3] family, 64 agents per GPU (default); grid1024: configs[4], fixed world")
+    ap.add_argument("--workload", default="grid64", choices=["grid64", "grid1024", "single", "mtlp5", "obst8"],
+                    help="grid64: configs[3] family, 64 agents per GPU (default); grid1024: configs[4], fixed world; "
+                         "single / mtlp5 / obst8: configs[0..2] as back-end throughput lines")
     ap.add_argument("--cpu-budget", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
     ap.add_argument("--no-front-end", action="store_true", help="skip the front-end (K0 search) measurement")
+    ap.add_argument("--no-grid1024", action="store_true", help="skip the configs[4] block of the default line")
+    ap.add_argument("--grid1024-steps", type=int, default=20)
     ap.add_argument("--front-end-steps", type=int, default=10)
     ap.add_argument("--front-end-world", type=int, default=1,
                     help="front_end block on the world of K x 64 agents, all searched by ONE GPU (default 1 = the bench world)")

@@ -136,6 +136,9 @@ typedef struct nb_replan_args
   uint8_t* line_ok;           /* optional [B][8][LS]: 0 not attempted, 1 solved, 2 unsolved */
 } nb_replan_args;
 
+/* Measurement hook: lines the pruning kept per (agent, interval) in the last nb_replan_batch, out [B][8] (host). */
+int nb_kept_lines(nb_handle* h, int32_t* out, int32_t B);
+
 /* LS = n_hull_slots + num_agents + num_static + ent_slots: agents | bases | static | non-entangling */
 int nb_line_slots(const nb_handle* h, int n_hull_slots);
 

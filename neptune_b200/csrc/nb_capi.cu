@@ -596,6 +596,15 @@ extern "C" int nb_check_async_errors(nb_handle* h, void* stream)
   return NB_OK;
 }
 
+extern "C" int nb_kept_lines(nb_handle* h, int32_t* out, int32_t B)
+{
+  if (!h || !out || B < 1 || !h->ncl.p || (size_t)B * NB_NPOL * sizeof(int) > h->ncl.cap) return NB_ERR_ARG;
+  NB_CUDA(cudaSetDevice(h->device));
+  NB_CUDA(cudaDeviceSynchronize());
+  NB_CUDA(cudaMemcpy(out, h->ncl.p, (size_t)B * NB_NPOL * sizeof(int), cudaMemcpyDeviceToHost));
+  return NB_OK;
+}
+
 extern "C" int nb_line_slots(const nb_handle* h, int n_hull_slots)
 {
   return n_hull_slots + h->par.num_agents + h->par.num_static + h->par.ent_slots;

@@ -226,6 +226,22 @@ class Scene:
     samp_g: np.ndarray | None = None       # [G][N][num_pol][S+1][2]
 
 
+def slice_scene(sc: Scene, idx) -> Scene:
+    """The same world seen by a subset of its planning agents (rows idx of every per-agent array): what one rank of a
+    sharded run plans for.  The packed host hulls are dropped (the device builds hulls from the records)."""
+    idx = np.asarray(idx)
+    b = sc.batch
+    nb = dataclasses.replace(
+        b, agent_id=np.ascontiguousarray(b.agent_id[idx]), n_int=np.ascontiguousarray(b.n_int[idx]),
+        coeff_init=np.ascontiguousarray(b.coeff_init[idx]), hull_ptr=np.zeros(len(idx) * b.n_hull_slots * NPOL + 1, np.int64),
+        hull_xy=np.zeros((0, 2)), nih0=np.ascontiguousarray(b.nih0[idx]), esv_cnt=np.ascontiguousarray(b.esv_cnt[idx]),
+        esv_alpha=np.ascontiguousarray(b.esv_alpha[idx]), esv_active=np.ascontiguousarray(b.esv_active[idx]))
+    per_agent = ("t_start", "samp", "known", "prev_pos", "prev_pos_agent", "state_A", "es0_cnt", "es0_alpha", "es0_beta", "es0_bend",
+                 "es0_active", "esA_cnt", "esA_alpha", "esA_beta", "esA_bend", "esA_active")
+    kw = {k: (None if getattr(sc, k) is None else np.ascontiguousarray(np.asarray(getattr(sc, k))[idx])) for k in per_agent}
+    return dataclasses.replace(sc, batch=nb, group=None, hull_g_xy=None, hull_g_cnt=None, samp_g=None, **kw)
+
+
 def _static_obstacles(par: Params, rng, pb):
     M = par.num_of_static_obst
     if M == 0:

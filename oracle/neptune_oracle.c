@@ -2350,7 +2350,8 @@ int orc_cycle_batch(const orc_params* par, int B, const int* agent_id, const int
                     const int* es_cnt, const int* es_alpha, const double* es_beta, const int* es_bend,
                     const int* es_active, const double* prev_pos, const double* prev_pos_agent, const double* cur,
                     double delta, int do_entangle, double* coeff_out, double* obj, int* status, int* iters,
-                    int* entangled, int* collide, int nthreads)
+                    int* entangled, int* collide, int nthreads, const unsigned char* late, const double* late_recs,
+                    const int* bp_cnt_late, const double* bp_xy_late)
 {
   const int N = par->num_agents, M = par->num_static, NA = N + M, cap = par->ent_cap, S = par->samples, P = par->num_pol;
   int rc_all = 0;
@@ -2430,12 +2431,17 @@ int orc_cycle_batch(const orc_params* par, int B, const int* agent_id, const int
     out.coeff_out = coeff_out + (size_t)b * 96, out.obj = obj + b, out.status = status + b, out.iters = iters + 2 * b;
     out.lines = 0, out.line_ok = 0;
     if (!rc) rc = orc_replan(par, &in, &out);
-    /* safetyCheckAfterReplan: every known trajectory treated as late (worst case) */
-    int col = 0;
-    for (int j = 0; j < N && !col; j++)
-      if (kn[j])
+    /* safetyCheckAfterReplan (neptune.cpp:719-752) against the trajectories that arrived during the optimisation
+     * (late == NULL: every known one, with the record it was planned against) */
+    const unsigned char* lt = late ? late + (size_t)b * N : kn;
+    const double* lrecs = late_recs ? late_recs : recs;
+    int col = 0, any_late = 0;
+    for (int j = 0; j < N; j++)
+      if (lt[j] && j != agent_id[b] - 1)
       {
-        const double* rec = recs + (size_t)j * ORC_REC;
+        any_late = 1;
+        if (col) continue;
+        const double* rec = lrecs + (size_t)j * ORC_REC;
         const double* cxj = rec + 1 + (ORC_REC_TP + 1);
         if (orc_pwp_collides(out.coeff_out, n_int[b], t_start[b], par->T_span, rec + 1, (int)rec[0] + 1, cxj,
                              cxj + ORC_REC_TP * 4, d3))
@@ -2443,18 +2449,54 @@ int orc_cycle_batch(const orc_params* par, int B, const int* agent_id, const int
       }
     collide[b] = col;
     entangled[b] = 0;
-    if (do_entangle && !rc)
-    {
-      double cxy[2 * 32];
-      for (int i = 0; i < n_int[b]; i++)
-        for (int r = 0; r < 4; r++)
+    if (do_entangle && !rc && any_late)
+    { /* :735-752: samples of the late agents re-drawn over the optimised trajectory's span, their bend points from the
+         late message, PredictAlphasBetas afresh from entangle_state_, then entangleCheckGivenPwp */
+      unsigned char* kn2 = (unsigned char*)malloc((size_t)N);
+      int* bc2 = (int*)malloc(sizeof(int) * (size_t)N);
+      double* bx2 = (double*)malloc(sizeof(double) * (size_t)N * par->bp_max * 2);
+      memcpy(bc2, bp_cnt, sizeof(int) * (size_t)N);
+      memcpy(bx2, bp_xy, sizeof(double) * (size_t)N * par->bp_max * 2);
+      for (int j = 0; j < N; j++)
+      {
+        kn2[j] = kn[j];
+        if (!lt[j] || j == agent_id[b] - 1) continue;
+        kn2[j] = 1;
+        const double* rec = lrecs + (size_t)j * ORC_REC;
+        const double* cxj = rec + 1 + (ORC_REC_TP + 1);
+        orc_sample_interval_points(rec + 1, (int)rec[0] + 1, cxj, cxj + ORC_REC_TP * 4, t_start[b],
+                                   t_start[b] + par->T_span * n_int[b], P, S, samp + (size_t)j * P * (S + 1) * 2, 0);
+        samp0[2 * j] = samp[(size_t)j * P * (S + 1) * 2];
+        samp0[2 * j + 1] = samp[(size_t)j * P * (S + 1) * 2 + 1];
+        if (bp_cnt_late)
         {
-          cxy[4 * i + r] = out.coeff_out[4 * i + r];
-          cxy[4 * n_int[b] + 4 * i + r] = out.coeff_out[32 + 4 * i + r];
+          bc2[j] = bp_cnt_late[j];
+          memcpy(bx2 + (size_t)j * par->bp_max * 2, bp_xy_late + (size_t)j * par->bp_max * 2, sizeof(double) * par->bp_max * 2);
         }
-      int e = orc_entangle_check_pwp(&es, &cx, n_int[b], cxy, samp, kn, P, S, par->T_span);
+      }
+      es.n_alpha = es_cnt[2 * b];
+      es.n_bend = es_cnt[2 * b + 1];
+      memcpy(es.alpha, es_alpha + (size_t)b * cap * 2, sizeof(int) * 2 * cap);
+      memcpy(es.beta, es_beta + (size_t)b * cap, sizeof(double) * cap);
+      memcpy(es.bend, es_bend + (size_t)b * cap, sizeof(int) * cap);
+      memcpy(es.active, es_active + (size_t)b * NA, sizeof(int) * NA);
+      orc_ectx cx2 = cx;
+      cx2.bp_cnt = bc2, cx2.bp_xy = bx2;
+      int e = orc_predict(&es, &cx2, prev_pos + (size_t)b * (N + 1) * 2, prev_pos_agent + (size_t)b * N * 2, cur + 2 * b, samp0, kn2);
+      if (!e)
+      {
+        double cxy[2 * 32];
+        for (int i = 0; i < n_int[b]; i++)
+          for (int r = 0; r < 4; r++)
+          {
+            cxy[4 * i + r] = out.coeff_out[4 * i + r];
+            cxy[4 * n_int[b] + 4 * i + r] = out.coeff_out[32 + 4 * i + r];
+          }
+        e = orc_entangle_check_pwp(&es, &cx2, n_int[b], cxy, samp, kn2, P, S, par->T_span);
+      }
       entangled[b] = e > 0;
       if (e < 0) rc = e;
+      free(kn2), free(bc2), free(bx2);
     }
     free(hptr), free(hxy), free(nih0), free(samp), free(samp0), free(es.alpha), free(es.beta), free(es.bend), free(es.active);
     if (rc)

@@ -225,7 +225,8 @@ int orc_cycle_batch(const orc_params* par, int B, const int* agent_id, const int
                     const int* es_cnt, const int* es_alpha, const double* es_beta, const int* es_bend,
                     const int* es_active, const double* prev_pos, const double* prev_pos_agent, const double* cur,
                     double delta, int do_entangle, double* coeff_out, double* obj, int* status, int* iters,
-                    int* entangled, int* collide, int nthreads);
+                    int* entangled, int* collide, int nthreads, const unsigned char* late, const double* late_recs,
+                    const int* bp_cnt_late, const double* bp_xy_late);
 
 /* ---- front end: KinodynamicSearch (kinodynamic_search.cpp), neptune_search.c ---- */
 #define ORC_SEARCH_HSTRIDE 24 /* vertices reserved per hull in the fixed-stride hull arrays */

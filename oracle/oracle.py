@@ -18,11 +18,31 @@ _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 _lib = None
 
 
+def _cpu_tag() -> str:
+    """Identifies the instruction set of this host: the library is built -march=native (the CPU arm is
+    compiled for the machine it is timed on), so a copy built on another CPU model must be rebuilt, not loaded."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            txt = f.read()
+        model = next((ln.split(":", 1)[1].strip() for ln in txt.splitlines() if ln.startswith("model name")), "?")
+        flags = next((ln.split(":", 1)[1] for ln in txt.splitlines() if ln.startswith("flags")), "")
+        return model + " | " + " ".join(sorted(x for x in flags.split() if x.startswith(("avx", "fma", "bmi", "sse4"))))
+    except OSError:
+        return "unknown"
+
+
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("neptune_oracle.c", "neptune_search.c", "neptune_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("neptune_oracle.c", "neptune_search.c", "neptune_oracle.h", "Makefile")]
+    tag_path = os.path.join(_HERE, "_build", "built_on.txt")
+    tag = _cpu_tag()
     stale = (not os.path.exists(_LIB_PATH)) or any(os.path.getmtime(f) > os.path.getmtime(_LIB_PATH) for f in srcs)
-    if force or stale:
+    other_host = (not os.path.exists(tag_path)) or open(tag_path).read() != tag
+    if force or stale or other_host:
+        if os.path.exists(_LIB_PATH):
+            os.remove(_LIB_PATH)
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+        with open(tag_path, "w") as f:
+            f.write(tag)
     return _LIB_PATH
 
 
@@ -312,8 +332,10 @@ def export_qp(batch, a: int, fallback: bool, lines, line_ok):
                 has_qc=bool(has_qc.value), n=n)
 
 
-def cycle_batch(scene, recs, nthreads: int = 1, do_entangle: bool = True, t_now=None):
-    """orc_cycle_batch over a neptune_b200.scenes.Scene: the whole per-agent cycle on the CPU."""
+def cycle_batch(scene, recs, nthreads: int = 1, do_entangle: bool = True, t_now=None, late=None, late_recs=None,
+                bp_cnt_late=None, bp_xy_late=None):
+    """orc_cycle_batch over a neptune_b200.scenes.Scene: the whole per-agent cycle on the CPU.  late [B][N] / late_recs /
+    bp_*_late: what arrives during the optimisation (default: every known trajectory, unchanged)."""
     b, par = scene.batch, scene.par
     op = make_params(par)
     B = b.B
@@ -336,7 +358,10 @@ def cycle_batch(scene, recs, nthreads: int = 1, do_entangle: bool = True, t_now=
              "prev_pos", "prev_pos_agent", "cur")
     rc = f(C.byref(op), C.c_int(B), *[_p(arrs[k]) for k in order], C.c_double(2 * par.drone_radius),
            C.c_int(int(do_entangle)), _p(out["coeff_out"]), _p(out["obj"]), _p(out["status"]), _p(out["iters"]),
-           _p(out["entangled"]), _p(out["collide"]), C.c_int(nthreads))
+           _p(out["entangled"]), _p(out["collide"]), C.c_int(nthreads),
+           None if late is None else _p(_c(late, np.uint8)), None if late_recs is None else _p(_c(late_recs, np.float64)),
+           None if bp_cnt_late is None else _p(_c(bp_cnt_late, np.int32)),
+           None if bp_xy_late is None else _p(_c(bp_xy_late, np.float64)))
     if rc == 0 and t_now is not None:
         out["new_recs"], out["new_pieces"] = np.zeros((B, 256)), np.zeros(B, np.int32)
         g = lib().orc_commit_compose_batch

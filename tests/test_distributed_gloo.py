@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from neptune_b200 import capi, config
-from neptune_b200.cycle import REC, gather_records, shard_agents
+from neptune_b200.cycle import REC, gather_records, ring_phases, shard_agents
 from neptune_b200.scenes import make_scene
 
 
@@ -20,6 +20,15 @@ def test_shard_agents_is_a_partition():
             parts = [shard_agents(n, w, r) for r in range(w)]
             assert np.array_equal(np.concatenate(parts), np.arange(n))
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_ring_phases_rotate_consistently():
+    """The three-slot record ring of the device-resident cycle (csrc/nb_cycle.cu): what cycle k commits (new) is what
+    cycle k + 1 post-checks against (late) and cycle k + 2 plans against (known); the three slots are always distinct."""
+    for k in range(12):
+        new, late, known = ring_phases(k)
+        assert sorted((new, late, known)) == [0, 1, 2]
+        assert ring_phases(k + 1)[1] == new and ring_phases(k + 2)[2] == new
 
 
 def _free_port():
