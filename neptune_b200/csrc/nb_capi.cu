@@ -283,11 +283,13 @@ __global__ void k_traj(int B, const int* n_int, const double* coeff, double T, d
   n_states[b] = cnt;
 }
 
-__global__ void __launch_bounds__(32) k_entangle(NbEntArgs a)
+// one warp per agent; in worlds with hundreds of tethers (N + M >= 256) four warps, the lanes over the tethers
+template <int NT>
+__global__ void __launch_bounds__(NT) k_entangle(NbEntArgs a)
 {
   extern __shared__ int smem_i[];
-  Group<32> g(threadIdx.x);
-  nb_entangle_task<32>(g, blockIdx.x, a, smem_i, smem_i + 4 * a.tcap);
+  Group<NT> g(threadIdx.x);
+  nb_entangle_task<NT>(g, blockIdx.x, a, smem_i, smem_i + 4 * a.tcap);
 }
 
 // ---- K1 / K5 kernels
@@ -363,8 +365,28 @@ __global__ void k_hull_index(int B, int N, const int* agent_id, const int* group
   hull_cnt[k] = (j == agent_id[b] - 1 || !known[bj]) ? 0 : hull_cnt_g[src];
 }
 
+// axis-aligned bounding box of every hull: (xmin, ymin, xmax, ymax); empty hulls get an empty box
+__global__ void k_hull_aabb(size_t n, const double* hull_xy, const int* hull_cnt, double* aabb)
+{
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int c = hull_cnt[k];
+  const double* v = hull_xy + k * NB_HMAX * 2;
+  double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+  for (int q = 0; q < c; q++)
+  {
+    x0 = fmin(x0, v[2 * q]), x1 = fmax(x1, v[2 * q]);
+    y0 = fmin(y0, v[2 * q + 1]), y1 = fmax(y1, v[2 * q + 1]);
+  }
+  aabb[4 * k] = x0, aabb[4 * k + 1] = y0, aabb[4 * k + 2] = x1, aabb[4 * k + 3] = y1;
+}
+
+// aabb (nullable): boxes of the hulls.  Two convex sets whose boxes are disjoint are disjoint, which is what gjk::collision
+// answers for them (gjk.cpp:76-148 finds a separating direction in its first iterations): those pairs -- almost all of
+// them in a large world -- skip the GJK and the 384-byte hull read.
 __global__ void k_postcheck_hulls(NbConsts cs, int B, const int* n_int, const double* coeff, const int* group,
-                                  const double* hull_xy_g, const int* hull_cnt_g, const uint8_t* late, int* collide)
+                                  const double* hull_xy_g, const int* hull_cnt_g, const uint8_t* late, int* collide,
+                                  const double* aabb)
 {
   const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j, i)
   if (k >= (size_t)B * cs.N * NB_NPOL) return;
@@ -386,6 +408,13 @@ __global__ void k_postcheck_hulls(NbConsts cs, int B, const int* n_int, const do
       y = NB_ADD(y, NB_MUL(cf[32 + 4 * i + r], cs.Ainv[r * 4 + q]));
     }
     A[2 * q] = x, A[2 * q + 1] = y;
+  }
+  if (aabb)
+  {
+    const double* bx = aabb + 4 * src;
+    const double ax0 = fmin(fmin(A[0], A[2]), fmin(A[4], A[6])), ax1 = fmax(fmax(A[0], A[2]), fmax(A[4], A[6]));
+    const double ay0 = fmin(fmin(A[1], A[3]), fmin(A[5], A[7])), ay1 = fmax(fmax(A[1], A[3]), fmax(A[5], A[7]));
+    if (ax1 < bx[0] || bx[2] < ax0 || ay1 < bx[1] || bx[3] < ay0) return;
   }
   if (nb_gjk_collision(hull_xy_g + src * NB_HMAX * 2, hn, A, 4)) atomicOr(collide + b, 1);
 }
@@ -986,7 +1015,10 @@ int ent_common(nb_handle* h, NbEntArgs* a, int mode, int B, int space, const int
 int ent_launch(nb_handle* h, const NbEntArgs& a, int B, cudaStream_t st)
 {
   const size_t sm = (size_t)(4 * a.tcap + 4) * sizeof(int);
-  k_entangle<<<B, 32, sm, st>>>(a);
+  if (a.N + a.M >= 256 && a.mode != 3)
+    k_entangle<128><<<B, 128, sm, st>>>(a);
+  else
+    k_entangle<32><<<B, 32, sm, st>>>(a);
   h->launches += 1;
   NB_CUDA(cudaGetLastError());
   return NB_OK;
@@ -1312,7 +1344,28 @@ extern "C" int nb_postcheck_hulls_batch(nb_handle* h, int32_t B, int32_t space, 
   const size_t n = (size_t)B * h->par.num_agents * NB_NPOL;
   NB_CUDA(cudaMemsetAsync(collide, 0, (size_t)B * sizeof(int), st));
   k_postcheck_hulls<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(h->cs, B, n_int, coeff, group, hull_xy_g, hull_cnt_g, late,
-                                                               collide);
+                                                               collide, nullptr);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+
+// internal (nb_cycle.cu): the same with bounding boxes of the late hulls, built once per cycle by nb_internal_hull_aabb
+int nb_internal_hull_aabb(nb_handle* h, size_t n_hulls, const double* hull_xy, const int* hull_cnt, double* aabb, cudaStream_t st)
+{
+  k_hull_aabb<<<(unsigned)((n_hulls + 127) / 128), 128, 0, st>>>(n_hulls, hull_xy, hull_cnt, aabb);
+  h->launches += 1;
+  NB_CUDA(cudaGetLastError());
+  return NB_OK;
+}
+int nb_internal_postcheck_hulls(nb_handle* h, int B, const int32_t* n_int, const double* coeff, const int32_t* group,
+                                const double* hull_xy_g, const int32_t* hull_cnt_g, const double* aabb, const uint8_t* late,
+                                int32_t* collide, cudaStream_t st)
+{
+  const size_t n = (size_t)B * h->par.num_agents * NB_NPOL;
+  NB_CUDA(cudaMemsetAsync(collide, 0, (size_t)B * sizeof(int), st));
+  k_postcheck_hulls<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(h->cs, B, n_int, coeff, group, hull_xy_g, hull_cnt_g, late,
+                                                               collide, aabb);
   h->launches += 1;
   NB_CUDA(cudaGetLastError());
   return NB_OK;

@@ -54,11 +54,12 @@ __global__ void __launch_bounds__(64) k_publish(int B, int N, const int* agent_i
 {
   __shared__ double now[NB_REC];
   __shared__ double rec[NB_REC];
+  __shared__ double pst[NB_REC];
   const int b = blockIdx.x;
   const int agent = agent_id[b];
   hd.seq = (double)*cycle_no;
   nb_commit_one(b, n_int, coeff, t_start, T, rec, now, t_now, prev, agent_id, nullptr, status, entangled, collide, fe_solved,
-                n_pieces, hd, err);
+                n_pieces, hd, err, pst);
   __syncthreads();
   const size_t slot = ((size_t)phase * N + (agent - 1)) * NB_REC;
   for (int r = 0; r < peers.world; r++)
@@ -167,7 +168,7 @@ struct nb_cycle
   size_t es_bytes = 0, es_off[5] = { 0, 0, 0, 0, 0 };
   int32_t *bp_cnt = nullptr, *bp_cnt_l = nullptr;
   double *bp_xy = nullptr, *bp_xy_l = nullptr, *latest_pos = nullptr;
-  double *hull_xy = nullptr, *hull_xy_l = nullptr, *nih0 = nullptr, *nih0_l = nullptr, *samp = nullptr;
+  double *hull_xy = nullptr, *hull_xy_l = nullptr, *nih0 = nullptr, *nih0_l = nullptr, *samp = nullptr, *aabb_l = nullptr;
   int32_t *hull_cnt = nullptr, *hull_cnt_l = nullptr;
   int64_t *hull_ptr = nullptr, *hull_ptr_l = nullptr;
   // front-end outputs
@@ -175,7 +176,7 @@ struct nb_cycle
   double *fe_coeff = nullptr, *fe_ebeta = nullptr, *fe_cost = nullptr;
   // streams, events, graphs
   cudaStream_t sB = nullptr, sC = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_hulls = nullptr, ev_B = nullptr, ev_C = nullptr, ev_prof[10] = { nullptr };
+  cudaEvent_t ev_fork = nullptr, ev_hulls = nullptr, ev_B = nullptr, ev_C = nullptr, ev_qp = nullptr, ev_C2 = nullptr, ev_prof[10] = { nullptr };
   cudaGraphExec_t graph[3] = { nullptr, nullptr, nullptr };
   int graph_G = -1;
   long long launches_per_step = 0;
@@ -260,6 +261,7 @@ int step_body(nb_cycle* c, cudaStream_t st, bool prof)
   CY_RC(nb_unpack_records_batch(h, NB_DEVICE, r_late, c->bp_cnt_l, c->bp_xy_l, nullptr, sC));
   CY_RC(nb_hulls_batch(h, G, NB_DEVICE, t_group, r_late, c->d_ones, c->d.delta, c->hull_xy_l, c->hull_cnt_l, c->hull_ptr_l, c->nih0_l,
                        nullptr, nullptr, sC));
+  CY_RC(nb_internal_hull_aabb(h, (size_t)G * N * NB_NPOL, c->hull_xy_l, c->hull_cnt_l, c->aabb_l, sC));
   if (!prof) CY_CUDA(cudaEventRecord(c->ev_C, sC));
   mark();
   // (main) the trajectories the agents plan against: trajCB bookkeeping, hulls and samples (neptune.cpp:1433-1434)
@@ -320,18 +322,22 @@ int step_body(nb_cycle* c, cudaStream_t st, bool prof)
   CY_RC(nb_replan_batch(h, &a, st));
   mark();
   // safetyCheckAfterReplan (:719-752): GJK against the late hulls, then the gated entanglement re-check
+  // the two halves are independent: the GJK half runs on stream C beside the entanglement half on the main stream
   if (!prof)
   {
-    CY_CUDA(cudaStreamWaitEvent(st, c->ev_C, 0));
+    CY_CUDA(cudaEventRecord(c->ev_qp, st));
+    CY_CUDA(cudaStreamWaitEvent(sC, c->ev_qp, 0));
     CY_CUDA(cudaStreamWaitEvent(st, c->ev_B, 0));
   }
-  CY_RC(nb_postcheck_hulls_batch(h, B, NB_DEVICE, n_int, a.coeff_out, group, c->hull_xy_l, c->hull_cnt_l, late,
-                                 out_at<int32_t>(c, L.collide), st));
+  CY_RC(nb_internal_postcheck_hulls(h, B, n_int, a.coeff_out, group, c->hull_xy_l, c->hull_cnt_l, c->aabb_l, late,
+                                    out_at<int32_t>(c, L.collide), sC));
+  if (!prof) CY_CUDA(cudaEventRecord(c->ev_C2, sC));
   nb_ent_state es0 = es_view(c->d_in + L.es_cnt, c->es_off);
   CY_RC(nb_postcheck_entangle_batch(h, B, NB_DEVICE, agent_id, known, late, c->bp_cnt, c->bp_xy, c->bp_cnt_l, c->bp_xy_l, es0,
                                     in_at<double>(c, L.prev_pos), in_at<double>(c, L.prev_pos_agent), in_at<double>(c, L.cur), n_int,
                                     a.coeff_out, in_at<double>(c, L.t_start), c->samp, 0, group, r_late,
                                     out_at<int32_t>(c, L.entangled), st));
+  if (!prof) CY_CUDA(cudaStreamWaitEvent(st, c->ev_C2, 0));
   mark();
   // commit: compose with the previous plan, DynTraj header, records into the ring of every rank (:1685-1699, publishOwnTraj)
   NbPublishHdr hd;
@@ -455,7 +461,7 @@ extern "C" int nb_cycle_create(nb_handle* h, const nb_cycle_desc* d, nb_cycle** 
     }
     CY_CUDA(cudaStreamCreateWithFlags(&c->sB, cudaStreamNonBlocking));
     CY_CUDA(cudaStreamCreateWithFlags(&c->sC, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : { &c->ev_fork, &c->ev_hulls, &c->ev_B, &c->ev_C }) CY_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : { &c->ev_fork, &c->ev_hulls, &c->ev_B, &c->ev_C, &c->ev_qp, &c->ev_C2 }) CY_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (auto& e : c->ev_prof) CY_CUDA(cudaEventCreate(&e));
     return NB_OK;
   }();
@@ -483,7 +489,7 @@ extern "C" void nb_cycle_destroy(nb_cycle* c)
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->sB) cudaStreamDestroy(c->sB);
   if (c->sC) cudaStreamDestroy(c->sC);
-  for (cudaEvent_t e : { c->ev_fork, c->ev_hulls, c->ev_B, c->ev_C })
+  for (cudaEvent_t e : { c->ev_fork, c->ev_hulls, c->ev_B, c->ev_C, c->ev_qp, c->ev_C2 })
     if (e) cudaEventDestroy(e);
   for (auto e : c->ev_prof)
     if (e) cudaEventDestroy(e);
@@ -523,6 +529,7 @@ int ensure_groups(nb_cycle* c, int G)
   CY_RC(dalloc(c, &c->hull_ptr_l, nh));
   CY_RC(dalloc(c, &c->nih0, nh * 2));
   CY_RC(dalloc(c, &c->nih0_l, nh * 2));
+  CY_RC(dalloc(c, &c->aabb_l, nh * 4));
   CY_RC(dalloc(c, &c->samp, (size_t)G * c->N * c->P * (c->S + 1) * 2));
   CY_RC(dalloc(c, &c->d_ones, (size_t)G * c->N));
   CY_CUDA(cudaMemset(c->d_ones, 1, (size_t)G * c->N));

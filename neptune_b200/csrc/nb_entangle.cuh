@@ -419,15 +419,34 @@ template <int NL>
 NB_HD int nb_excl_scan(const Group<NL>& g, int v, int& total)
 {
 #if defined(__CUDA_ARCH__)
+  constexpr int W = NL < 32 ? NL : 32;
   int x = v;
 #pragma unroll
-  for (int o = 1; o < NL; o <<= 1)
+  for (int o = 1; o < W; o <<= 1)
   {
     const int y = __shfl_up_sync(0xffffffffu, x, o);
-    if (g.lane >= o) x += y;
+    if ((g.lane & 31) >= o) x += y;
   }
-  total = __shfl_sync(0xffffffffu, x, NL - 1);
-  return x - v;
+  if (NL <= 32)
+  {
+    total = __shfl_sync(0xffffffffu, x, W - 1);
+    return x - v;
+  }
+  // several warps (a CTA per agent in worlds with hundreds of tethers): warp totals through shared memory
+  __shared__ int wtot[NL > 32 ? NL / 32 : 1];
+  const int w = g.lane >> 5;
+  if ((g.lane & 31) == 31) wtot[w] = x;
+  __syncthreads();
+  int before = 0, all = 0;
+#pragma unroll
+  for (int q = 0; q < NL / 32; q++)
+  {
+    if (q < w) before += wtot[q];
+    all += wtot[q];
+  }
+  __syncthreads();
+  total = all;
+  return before + x - v;
 #else
   total = v;
   return 0;
@@ -513,7 +532,7 @@ NB_HD int nb_collect_track(const Group<NL>& g, const NbEntCtx& cx, const int* bp
     if (g.any(stop != 0))
     {  // the sequential loop keeps the value assigned last: the highest tether index wins
 #if defined(__CUDA_ARCH__)
-      const unsigned m = __ballot_sync(0xffffffffu, stop != 0);
+      const unsigned m = __ballot_sync(0xffffffffu, stop != 0);  // (the tracker tick always runs one warp per agent)
       if (g.lane == 31 - __clz(m)) *stop_out = stop;
 #else
       *stop_out = stop;

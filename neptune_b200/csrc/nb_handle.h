@@ -66,3 +66,7 @@ void nb_set_error(const char* text);
 int nb_internal_predict_grouped(nb_handle* h, int B, const int32_t* agent_id, const uint8_t* known, const int32_t* bp_cnt,
                                 const double* bp_xy, nb_ent_state stt, const double* prev_pos, const double* prev_pos_agent,
                                 const double* cur, const double* samp_g, const int32_t* group, cudaStream_t st);
+int nb_internal_hull_aabb(nb_handle* h, size_t n_hulls, const double* hull_xy, const int* hull_cnt, double* aabb, cudaStream_t st);
+int nb_internal_postcheck_hulls(nb_handle* h, int B, const int32_t* n_int, const double* coeff, const int32_t* group,
+                                const double* hull_xy_g, const int32_t* hull_cnt_g, const double* aabb, const uint8_t* late,
+                                int32_t* collide, cudaStream_t st);

@@ -63,7 +63,7 @@ static __device__ __forceinline__ void nb_fill_header(double* r, int agent, int 
 static __device__ __forceinline__ void nb_commit_one(int b, const int* n_int, const double* coeff, const double* t_start, double T, double* r,
                               double* now, const double* t_now, const double* prev, const int* prev_agent,
                               const uint8_t* has_prev, const int* status, const int* entangled, const int* collide,
-                              const int* fe_solved, int* n_pieces, const NbPublishHdr& hd, int* err)
+                              const int* fe_solved, int* n_pieces, const NbPublishHdr& hd, int* err, double* prev_stage = nullptr)
 {
   const int n = n_int[b];
   const bool compose = t_now != nullptr;
@@ -95,6 +95,12 @@ static __device__ __forceinline__ void nb_commit_one(int b, const int* n_int, co
     return;
   }
   const double* pv = prev + (size_t)(agent - 1) * NB_REC;
+  if (prev_stage)
+  {  // the previous record into shared memory by the whole CTA: the (sequential) composition then reads it from there
+    for (int q = threadIdx.x; q < NB_REC; q += blockDim.x) prev_stage[q] = pv[q];
+    __syncthreads();
+    pv = prev_stage;
+  }
   const bool hp = has_prev == nullptr || has_prev[b];
   const bool ok = !((status && status[b] >= 2) || (entangled && entangled[b]) || (collide && collide[b]) ||
                     (fe_solved && !fe_solved[b]));
