@@ -386,8 +386,10 @@ NB_HD void nb_qp_factor_blocks(const Group<NL>& g, NbQpShared* sh, int nxy, int 
 {
   double* K = sh->K;
   const int nv = nxy + nz, ne = sh->nelem;
+#pragma unroll 1
   for (int t = 0; t < nxy; t++)
   {
+#pragma unroll 1
     for (int e = g.lane; e < ne + nv; e += NL)
     {
       const int i = e < ne ? sh->ei[e] : e - ne, j = e < ne ? sh->ej[e] : e - ne;
@@ -412,38 +414,31 @@ NB_HD void nb_qp_factor_blocks(const Group<NL>& g, NbQpShared* sh, int nxy, int 
 }
 
 #if defined(__CUDA_ARCH__)
-// x_i of K0 x = b (lane i of warp 0), both blocks in lockstep: 2 nxy dependent shuffle + FMA steps.  Row i and column i
-// of L are fetched into registers first (static indices: the loops are fully unrolled); one copy of the code serves
-// every solve of an iteration.
+// x_i of K0 x = b (lane i of warp 0), both blocks in lockstep: 2 nxy dependent shuffle + FMA steps in two short loops
+// (they stay in the instruction cache: a CTA of four warps runs this code once per solve, and straight-line code that
+// has fallen out of the cache is fetched from L2); the entry of L a step needs is loaded while the pivot travels.
 __device__ __noinline__ double nb_warp_solve(const double* K, const double* invd, int nxy, int nz, int lane, double x)
 {
-  constexpr int W = 2 * NB_DOF_MAX;
   const bool second = lane >= nxy;
   const int base = second ? nxy : 0, nb = second ? nz : nxy, il = lane - base;
   const bool mine = il < nb;
-  double L[W], Lt[W];
-#pragma unroll
-  for (int t = 0; t < W; t++)
+  const double* row = K + lane * NB_KLD + base;   // L[i][base + t], t < il
+  const double* col = K + base * NB_KLD + lane;   // L[base + t][i], t > il (stride NB_KLD)
+#pragma unroll 2
+  for (int t = 0; t < nxy; t++)
   {
-    L[t] = (mine && t < il) ? K[lane * NB_KLD + base + t] : 0.0;
-    Lt[t] = (mine && t > il && t < nb) ? K[(base + t) * NB_KLD + lane] : 0.0;
+    const double l = (mine && t < il) ? row[t] : 0.0;
+    const double xk = __shfl_sync(0xffffffffu, x, (base + t) & 31);
+    x -= l * xk;
   }
-  const double id = mine ? invd[lane] : 0.0;
-#pragma unroll
-  for (int t = 0; t < W; t++)
-    if (t < nxy)
-    {
-      const double xk = __shfl_sync(0xffffffffu, x, (base + t) & 31);
-      x -= L[t] * xk;
-    }
-  x *= id;
-#pragma unroll
-  for (int t = W - 1; t >= 0; t--)
-    if (t < nxy)
-    {
-      const double xk = __shfl_sync(0xffffffffu, x, (base + t) & 31);
-      x -= Lt[t] * xk;
-    }
+  x *= mine ? invd[lane] : 0.0;
+#pragma unroll 2
+  for (int t = nxy - 1; t >= 0; t--)
+  {
+    const double l = (mine && t > il && t < nb) ? col[t * NB_KLD] : 0.0;
+    const double xk = __shfl_sync(0xffffffffu, x, (base + t) & 31);
+    x -= l * xk;
+  }
   return mine ? x : 0.0;
 }
 #endif
@@ -741,20 +736,14 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       g.sync();
       nb_qp_ct_all<NL>(g, tb, sh, sh->du, sh->rd, sh->gobj, 1.0, 1.0, sh->gq, has_qc ? lam_q : 0.0);
       g.sync();
-      double rdn = 0.0, gn = 0.0, fsum = 0.0;
-      for (int a = g.lane; a < nv; a += NL)
-      {
+      double rdn = 0.0, gn = 0.0, fobj = fconst;
+#pragma unroll 1
+      for (int a = 0; a < nv; a++)
+      {  // nv <= 24 values in shared memory: every lane folds them itself (no exchange, no barrier)
         rdn = fmax(rdn, fabs(sh->rd[a]));
         gn = fmax(gn, fabs(sh->gobj[a]));
-        fsum += 0.5 * (sh->g0[a] + sh->gobj[a]) * sh->w[a];
+        fobj += 0.5 * (sh->g0[a] + sh->gobj[a]) * sh->w[a];
       }
-      {  // gn enters as a "sum" of one lane's value: every lane recomputes it from shared memory below
-        double e1 = 0.0;
-        g.reduce_max_sum_sum(rdn, fsum, e1);
-        gn = 0.0;
-        for (int a = 0; a < nv; a++) gn = fmax(gn, fabs(sh->gobj[a]));
-      }
-      const double fobj = fconst + fsum;
       if (!init_pass)
       {
         if (rpn <= cs.tol * (1.0 + hn) && rdn <= cs.tol * (1.0 + gn) && mu * mq <= cs.tol * (1.0 + fabs(fobj)))
