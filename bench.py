@@ -262,11 +262,14 @@ def measure_cycle(args, par, agents, rank, world, dev, workload, steps, warmup, 
     step_ms = np.array([e0.elapsed_time(e1) for e0, e1 in ev])
     total_ms = float(step_ms.sum())
     rank_ms = [total_ms]
+    rank_mhz = [clocks_rec["sm_mhz"] if clocks_rec else None]
     if world > 1:
-        tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        allt = torch.empty(world, dtype=torch.float64, device=dev)
+        tt = torch.tensor([total_ms, float(rank_mhz[0] or 0.0)], dtype=torch.float64, device=dev)
+        allt = torch.empty(2 * world, dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(allt, tt)
-        rank_ms = [float(x) for x in allt.cpu()]
+        allt = allt.cpu().numpy().reshape(world, 2)
+        rank_ms = [float(x) for x in allt[:, 0]]
+        rank_mhz = [float(x) for x in allt[:, 1]]
         total_ms = max(rank_ms)
     n_agents_all = par.num_of_agents if workload != "grid64" else world * B
     value = n_agents_all * steps / (total_ms * 1e-3)
@@ -292,6 +295,13 @@ def measure_cycle(args, par, agents, rank, world, dev, workload, steps, warmup, 
     lib.nb_set_profiling(cyc.solver.handle, 0)
     stage = {k2: float(np.mean(v)) for k2, v in stage.items()}
     kt = np.array(kt)
+    rank_stage = None
+    if world > 1:   # the same stages on every rank: where a slow rank loses its time
+        tt = torch.tensor([stage[k2] for k2 in STAGES], dtype=torch.float64, device=dev)
+        allt = torch.empty(len(STAGES) * world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allt, tt)
+        allt = allt.cpu().numpy().reshape(world, len(STAGES))
+        rank_stage = {k2: [float(x) for x in allt[:, i]] for i, k2 in enumerate(STAGES)}
 
     # ---------------- e2e: pinned host inputs -> H2D -> all kernels -> D2H, every step
     for it in range(2):
@@ -313,7 +323,7 @@ def measure_cycle(args, par, agents, rank, world, dev, workload, steps, warmup, 
     out = dict(value=value, ms_per_step=total_ms / steps, p50=float(np.median(step_ms)), p95=float(np.percentile(step_ms, 95)),
                e2e=e2e, h2d=int(h2d), d2h=int(d2h), launches=int(launches), launches_per_cycle=int(cyc.launches_per_cycle),
                kernels_ms={"k_lines": float(kt[:, 0].mean()), "k_qp": float(kt[:, 1].mean())}, stage_ms=stage,
-               rank_ms_per_step=[x / steps for x in rank_ms], clocks=clocks_rec,
+               rank_ms_per_step=[x / steps for x in rank_ms], rank_sm_mhz=rank_mhz, rank_stage_ms=rank_stage, clocks=clocks_rec,
                status_hist={str(k2): int((status == k2).sum()) for k2 in (0, 1, 2)},
                postcheck={"entangled": int(ent.sum()), "collide": int(col.sum())},
                ipm_iters_mean=float(itn.sum(axis=1).mean()), agents=int(n_agents_all), B=int(B))
@@ -541,7 +551,8 @@ def run_ours(args):
                 "gpu_launches": m["launches"], "launches_per_cycle": m["launches_per_cycle"],
                 "kernels_ms": m["kernels_ms"], "stage_ms": m["stage_ms"],
                 "exchange": {"kind": "peer-to-peer stores from k_publish + flag wait (k_wait_peers)", "wait_ms": m["stage_ms"]["exchange_wait"],
-                             "commit_ms": m["stage_ms"]["commit"], "rank_ms_per_step": m["rank_ms_per_step"]},
+                             "commit_ms": m["stage_ms"]["commit"], "rank_ms_per_step": m["rank_ms_per_step"],
+                             "rank_sm_mhz": m["rank_sm_mhz"], "rank_stage_ms": m["rank_stage_ms"]},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": ncu_traffic(dom) if args.workload == "grid64" and world == 1 else None,
                              "peak_source": which, "algorithmic_bytes_per_launch": m["alg_bytes"],
@@ -591,6 +602,7 @@ def run_ours(args):
                                 "replans_per_s": g["value"], "ms_per_cycle": g["ms_per_step"], "p50_ms": g["p50"], "p95_ms": g["p95"],
                                 "e2e_replans_per_s": g["e2e"], "h2d_bytes_per_step": g["h2d"], "agents_per_gpu": g["B"],
                                 "kernels_ms": g["kernels_ms"], "stage_ms": g["stage_ms"], "rank_ms_per_step": g["rank_ms_per_step"],
+                                "rank_stage_ms": g["rank_stage_ms"],
                                 "status_hist": g["status_hist"], "steps": args.grid1024_steps}
     if rank == 0:
         print(json.dumps(line))

@@ -39,25 +39,27 @@ void nb_set_error(const char* text) { g_err = text; }  // internal (nb_cycle.cu)
 
 // ------------------------------------------------------------------------------------------ kernels
 
-__global__ void __launch_bounds__(128) k_lines(NbConsts cs, NbLinesIn in, int LS, double* lines, uint8_t* ok,
-                                               uint8_t* keep, int* err, double* cl, int* ncl)
+// one CTA per (agent, interval): 128 threads over the LP slots, 512 in worlds with a thousand slots per interval
+template <int NT>
+__global__ void __launch_bounds__(NT) k_lines(NbConsts cs, NbLinesIn in, int LS, double* lines, uint8_t* ok,
+                                              uint8_t* keep, int* err, double* cl, int* ncl)
 {
   extern __shared__ double smem_d[];
   NbPruneShared ps;
   ps.px = smem_d;
   ps.py = ps.px + (LS + 1);
   ps.red = (int*)(ps.py + (LS + 1));
-  ps.hull = ps.red + 128;
+  ps.hull = ps.red + 512;
   ps.misc = ps.hull + (NB_PRUNE_KMAX + 1);
-  ps.valid = (uint8_t*)(ps.misc + 8);
+  ps.valid = (uint8_t*)(ps.misc + 24);  // misc holds one entry per warp (up to 16)
   const int b = blockIdx.x / NB_NPOL, i = blockIdx.x % NB_NPOL;
-  nb_lines_task<128>(threadIdx.x, b, i, cs, in, lines + (size_t)blockIdx.x * LS * 3, ok + (size_t)blockIdx.x * LS,
+  nb_lines_task<NT>(threadIdx.x, b, i, cs, in, lines + (size_t)blockIdx.x * LS * 3, ok + (size_t)blockIdx.x * LS,
                      keep + (size_t)blockIdx.x * LS, ps, err, cl + (size_t)blockIdx.x * LS * 3, ncl + blockIdx.x);
 }
 
 static size_t lines_smem_bytes(int LS)
 {
-  return (size_t)(LS + 1) * 16 + (128 + NB_PRUNE_KMAX + 1 + 8) * sizeof(int) + (size_t)(LS + 1) + 16;
+  return (size_t)(LS + 1) * 16 + (512 + NB_PRUNE_KMAX + 1 + 8 + 16) * sizeof(int) + (size_t)(LS + 1) + 16;
 }
 
 struct NbQpArgs
@@ -283,7 +285,7 @@ __global__ void k_traj(int B, const int* n_int, const double* coeff, double T, d
   n_states[b] = cnt;
 }
 
-// one warp per agent; in worlds with hundreds of tethers (N + M >= 256) four warps, the lanes over the tethers
+// one warp per agent; in worlds with hundreds of tethers four warps (N + M >= 256) or sixteen (>= 1024), lanes over the tethers
 template <int NT>
 __global__ void __launch_bounds__(NT) k_entangle(NbEntArgs a)
 {
@@ -830,7 +832,8 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   if (!h->qp_smem_set)
   {
     NB_CUDA(cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NbQpSmem)));
-    NB_CUDA(cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NB_CUDA(cudaFuncSetAttribute(k_lines<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NB_CUDA(cudaFuncSetAttribute(k_lines<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     h->qp_smem_set = 1;
   }
   if (lsm > 200 * 1024)
@@ -838,8 +841,12 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
     g_err = "nb_replan_batch: too many line slots per interval for the pruning stage";
     return NB_ERR_CAPACITY;
   }
-  k_lines<<<B * NB_NPOL, 128, lsm, st>>>(h->cs, in, LS, (double*)h->lines.p, (uint8_t*)h->line_ok.p,
-                                         (uint8_t*)h->keep.p, (int*)h->err.p, (double*)h->cl.p, (int*)h->ncl.p);
+  if (LS >= 1024 && B * NB_NPOL <= 4 * h->num_sms)   // a grid that leaves the GPU half empty: more threads per (agent, interval)
+    k_lines<512><<<B * NB_NPOL, 512, lsm, st>>>(h->cs, in, LS, (double*)h->lines.p, (uint8_t*)h->line_ok.p,
+                                                (uint8_t*)h->keep.p, (int*)h->err.p, (double*)h->cl.p, (int*)h->ncl.p);
+  else
+    k_lines<128><<<B * NB_NPOL, 128, lsm, st>>>(h->cs, in, LS, (double*)h->lines.p, (uint8_t*)h->line_ok.p,
+                                                (uint8_t*)h->keep.p, (int*)h->err.p, (double*)h->cl.p, (int*)h->ncl.p);
   if (h->profiling) cudaEventRecord(h->ev[1], st);
   k_qp<<<B, NB_QP_THREADS, sizeof(NbQpSmem), st>>>(h->cs, h->d_tables, q);
   if (h->profiling) cudaEventRecord(h->ev[2], st);
@@ -1015,7 +1022,9 @@ int ent_common(nb_handle* h, NbEntArgs* a, int mode, int B, int space, const int
 int ent_launch(nb_handle* h, const NbEntArgs& a, int B, cudaStream_t st)
 {
   const size_t sm = (size_t)(4 * a.tcap + 4) * sizeof(int);
-  if (a.N + a.M >= 256 && a.mode != 3)
+  if (a.N + a.M >= 1024 && a.mode != 3 && B <= 2 * h->num_sms)   // few agents, many tethers: sixteen warps per agent
+    k_entangle<512><<<B, 512, sm, st>>>(a);
+  else if (a.N + a.M >= 256 && a.mode != 3)
     k_entangle<128><<<B, 128, sm, st>>>(a);
   else
     k_entangle<32><<<B, 32, sm, st>>>(a);
