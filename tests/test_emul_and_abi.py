@@ -195,3 +195,16 @@ def test_dropin_headers_compile_beside_the_reference():
     for needle in ("PolySolverGurobi::optimize", "KinodynamicSearch::run", "nb_separate_batch", "nb_replan_batch", "nb_search_batch"):
         assert needle in syms, needle
     assert "GRBModel" not in syms and "glp_" not in syms     # neither Gurobi nor GLPK is referenced any more
+
+
+def test_record_wire_format_matches_reference_messages():
+    """neptune_b200/cpp/records_b200.hpp against the reference's own mu::pwp2PwpMsg / mu::pwpMsg2Pwp (utils.cpp compiled
+    where it lies): the trajectory part of a record is the PieceWisePolTraj message field for field, the round trip is the
+    reference's, the DynTraj header survives, updateTrajObstacles replaces by id (tests/cpp/records_check.cpp)."""
+    import subprocess
+    if not os.path.isdir("/root/reference/neptune/include"):
+        pytest.skip("no /root/reference in this environment")
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "_build/records_check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = subprocess.run([os.path.join(ROOT, "tests", "cpp", "_build", "records_check")], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok 500", (out.returncode, out.stdout, out.stderr)

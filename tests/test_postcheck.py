@@ -82,3 +82,62 @@ def test_gpu_records_carry_the_dyntraj_header(oracle):
         assert np.array_equal(xy[j, :bc[j]], bx[j, :bc[j]]) and (xy[j, bc[j]:] == 0).all()
         assert np.array_equal(pos[j], [sc.committed[j][1][0][3], sc.committed[j][2][0][3]])
     s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_static_representation_per_agent(oracle):
+    """nb_set_static_rep_per_agent: every agent its own staticObsRep_ (NeptuneRos::setUpCheckingPosAndStaticObs,
+    neptune_ros.cpp:852-1019, computed by nb_static_obst_rep from the agent's base and position).  PredictAlphasBetas, the
+    chain behind entStateVec and the post-check of every agent then equal the oracle run with THAT agent's representation,
+    and differ from the shared-representation run where the representations differ."""
+    import ctypes as C
+    from neptune_b200.capi import EntArrays
+    par = config("obst8")
+    sc = make_scene(par, 3003, sync=False, ent_backend=OracleEntBackend(oracle))
+    b = sc.batch
+    N, M = par.num_of_agents, par.num_of_static_obst
+    lib = capi.lib()
+    f = lib.nb_static_obst_rep
+    f.argtypes = [C.c_int32] + [C.c_void_p] * 4 + [C.c_double] + [C.c_void_p] * 2
+    polys = sc.static_raw
+    ptr = np.concatenate([[0], np.cumsum([len(q) for q in polys])]).astype(np.int64)
+    xy = np.ascontiguousarray(np.concatenate(polys), np.float64)
+    strep_all, longest_all = np.zeros((N, M, 2, 2)), np.zeros((N, M, 2))
+    rng = np.random.default_rng(5)
+    for j in range(N):
+        base = np.ascontiguousarray(par.pb[j], np.float64)
+        for attempt in range(50):     # a position from which a representation exists (the reference exits otherwise)
+            pos = np.ascontiguousarray(base + rng.normal(size=2) * 2.0)
+            if f(M, ptr.ctypes.data, xy.ctypes.data, base.ctypes.data, pos.ctypes.data, par.a_star_fraction_voxel_size,
+                 strep_all[j].ctypes.data, longest_all[j].ctypes.data) == 0:
+                break
+        else:
+            raise AssertionError("no feasible static representation found")
+    assert np.abs(strep_all - strep_all[0]).max() > 1e-3          # the agents' representations really differ
+    s = capi.Solver(par)
+    s.set_static(b.st_ptr, b.st_xy, sc.strep)
+    s.set_static_rep_per_agent(strep_all, longest_all)
+    es = EntArrays.of(par, sc.es0_cnt, sc.es0_alpha, sc.es0_beta, sc.es0_bend, sc.es0_active)
+    cur = np.ascontiguousarray(sc.state_A[:, 0, :2])
+    samp0 = np.ascontiguousarray(sc.samp[:, :, 0, 0, :])
+    got = s.entangle_predict(b.agent_id, sc.known, b.bp_cnt, b.bp_xy, es, sc.prev_pos, sc.prev_pos_agent, cur, samp0)
+    done, roll = s.entangle_rollout(b.agent_id, sc.known, b.bp_cnt, b.bp_xy, got, b.n_int, b.coeff_init, sc.samp)
+    ob = OracleEntBackend(oracle)
+    n_diff = 0
+    for a in range(b.B):
+        me = int(b.agent_id[a]) - 1
+        sl = slice(a, a + 1)
+        want = ob.predict_batch(par, b.agent_id[sl], sc.prev_pos[sl], sc.prev_pos_agent[sl], cur[sl], samp0[sl], sc.known[sl],
+                                strep_all[me], b.bp_cnt, b.bp_xy, sc.es0_cnt[sl], sc.es0_alpha[sl], sc.es0_beta[sl], sc.es0_bend[sl],
+                                sc.es0_active[sl])
+        for x, y in zip((got.cnt[sl], got.alpha[sl], got.beta[sl], got.bend[sl], got.active[sl]), want):
+            assert np.array_equal(x, y), a
+        wr = ob.rollout_batch(par, b.agent_id[sl], b.n_int[sl], b.coeff_init[sl], sc.samp[sl], sc.known[sl], strep_all[me], b.bp_cnt,
+                              b.bp_xy, *want)
+        assert wr[0][0] == done[a]
+        for x, y in zip((roll.cnt[sl], roll.alpha[sl], roll.beta[sl], roll.bend[sl], roll.active[sl]), wr[1:]):
+            assert np.array_equal(x, y), a
+        shared = ob.rollout_batch(par, b.agent_id[sl], b.n_int[sl], b.coeff_init[sl], sc.samp[sl], sc.known[sl], sc.strep, b.bp_cnt,
+                                  b.bp_xy, *want)
+        n_diff += int(not all(np.array_equal(x, y) for x, y in zip(wr[1:], shared[1:])))
+    s.close()
