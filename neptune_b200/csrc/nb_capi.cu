@@ -1511,6 +1511,15 @@ extern "C" int nb_publish_records_batch(nb_handle* h, int32_t B, int32_t space, 
   return NB_OK;
 }
 
+// phase 0: the whole post-check; 1 / 2 (device pointers, nb_cycle.cu): the part before / after the optimised trajectory is
+// needed -- phase 1 runs beside the QP
+int nb_internal_postcheck_entangle(nb_handle* h, int phase, int32_t B, int32_t space, const int32_t* agent_id, const uint8_t* known,
+                                   const uint8_t* late, const int32_t* bp_cnt, const double* bp_xy, const int32_t* bp_cnt_late,
+                                   const double* bp_xy_late, nb_ent_state st_in, const double* prev_pos,
+                                   const double* prev_pos_agent, const double* cur, const int32_t* n_int, const double* coeff,
+                                   const double* t_start, const double* samp, int32_t samp_shared, const int32_t* samp_group,
+                                   const double* late_recs, int32_t* entangled, void* stream);
+
 extern "C" int nb_postcheck_entangle_batch(nb_handle* h, int32_t B, int32_t space, const int32_t* agent_id, const uint8_t* known,
                                            const uint8_t* late, const int32_t* bp_cnt, const double* bp_xy,
                                            const int32_t* bp_cnt_late, const double* bp_xy_late, nb_ent_state st_in,
@@ -1518,6 +1527,18 @@ extern "C" int nb_postcheck_entangle_batch(nb_handle* h, int32_t B, int32_t spac
                                            const int32_t* n_int, const double* coeff, const double* t_start, const double* samp,
                                            int32_t samp_shared, const int32_t* samp_group, const double* late_recs,
                                            int32_t* entangled, void* stream)
+{
+  return nb_internal_postcheck_entangle(h, 0, B, space, agent_id, known, late, bp_cnt, bp_xy, bp_cnt_late, bp_xy_late, st_in, prev_pos,
+                                        prev_pos_agent, cur, n_int, coeff, t_start, samp, samp_shared, samp_group, late_recs,
+                                        entangled, stream);
+}
+
+int nb_internal_postcheck_entangle(nb_handle* h, int phase, int32_t B, int32_t space, const int32_t* agent_id, const uint8_t* known,
+                                   const uint8_t* late, const int32_t* bp_cnt, const double* bp_xy, const int32_t* bp_cnt_late,
+                                   const double* bp_xy_late, nb_ent_state st_in, const double* prev_pos,
+                                   const double* prev_pos_agent, const double* cur, const int32_t* n_int, const double* coeff,
+                                   const double* t_start, const double* samp, int32_t samp_shared, const int32_t* samp_group,
+                                   const double* late_recs, int32_t* entangled, void* stream)
 {
   if (!h || B < 0) return NB_ERR_ARG;
   if (B == 0) return NB_OK;
@@ -1577,6 +1598,7 @@ extern "C" int nb_postcheck_entangle_batch(nb_handle* h, int32_t B, int32_t spac
   a.out.cnt = (int32_t*)(base + o_cnt), a.out.alpha = (int32_t*)(base + o_alpha), a.out.beta = (double*)(base + o_beta);
   a.out.bend = (int32_t*)(base + o_bend), a.out.active = (int32_t*)(base + o_act);
   a.psamp = (double*)(base + o_ps), a.pknown = (unsigned char*)(base + o_pk);
+  a.phase = phase;
   if ((rc = stage_out(h, 7, space, entangled, (size_t)B, &a.result))) return rc;
   if ((rc = ent_launch(h, a, B, st))) return rc;
   if (space == NB_HOST) NB_CUDA(cudaMemcpyAsync(entangled, a.result, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, st));

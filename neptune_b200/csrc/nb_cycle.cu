@@ -176,7 +176,7 @@ struct nb_cycle
   double *fe_coeff = nullptr, *fe_ebeta = nullptr, *fe_cost = nullptr;
   // streams, events, graphs
   cudaStream_t sB = nullptr, sC = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_hulls = nullptr, ev_B = nullptr, ev_C = nullptr, ev_qp = nullptr, ev_C2 = nullptr, ev_prof[10] = { nullptr };
+  cudaEvent_t ev_fork = nullptr, ev_hulls = nullptr, ev_B = nullptr, ev_C = nullptr, ev_qp = nullptr, ev_C2 = nullptr, ev_pre = nullptr, ev_prof[10] = { nullptr };
   cudaGraphExec_t graph[3] = { nullptr, nullptr, nullptr };
   int graph_G = -1;
   long long launches_per_step = 0;
@@ -310,6 +310,22 @@ int step_body(nb_cycle* c, cudaStream_t st, bool prof)
       CY_CUDA(cudaMemcpyAsync(c->d_out + L.fe_n_int, c->fe_n_int, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   }
   mark();
+  // (stream B) first half of the entanglement post-check (neptune.cpp:735-749): the late agents' samples over the span of
+  // the trajectory being optimised, their late bend points, PredictAlphasBetas afresh -- none of it needs the optimiser's
+  // answer, so it runs beside the lines + QP kernels
+  nb_ent_state es0 = es_view(c->d_in + L.es_cnt, c->es_off);
+  double* coeff_out = out_at<double>(c, L.coeff_out);
+  if (!prof)
+  {
+    CY_CUDA(cudaEventRecord(c->ev_pre, st));
+    CY_CUDA(cudaStreamWaitEvent(sB, c->ev_pre, 0));
+    CY_CUDA(cudaStreamWaitEvent(sB, c->ev_C, 0));   // bend points of the late messages (stream C)
+  }
+  CY_RC(nb_internal_postcheck_entangle(h, 1, B, NB_DEVICE, agent_id, known, late, c->bp_cnt, c->bp_xy, c->bp_cnt_l, c->bp_xy_l, es0,
+                                       in_at<double>(c, L.prev_pos), in_at<double>(c, L.prev_pos_agent), in_at<double>(c, L.cur),
+                                       n_int, coeff_out, in_at<double>(c, L.t_start), c->samp, 0, group, r_late,
+                                       out_at<int32_t>(c, L.entangled), sB));
+  if (!prof) CY_CUDA(cudaEventRecord(c->ev_B, sB));
   // back end: separating lines + trajectory QP (:1514-1519); shared-window mode of nb_replan_batch
   nb_replan_args a;
   memset(&a, 0, sizeof(a));
@@ -332,11 +348,10 @@ int step_body(nb_cycle* c, cudaStream_t st, bool prof)
   CY_RC(nb_internal_postcheck_hulls(h, B, n_int, a.coeff_out, group, c->hull_xy_l, c->hull_cnt_l, c->aabb_l, late,
                                     out_at<int32_t>(c, L.collide), sC));
   if (!prof) CY_CUDA(cudaEventRecord(c->ev_C2, sC));
-  nb_ent_state es0 = es_view(c->d_in + L.es_cnt, c->es_off);
-  CY_RC(nb_postcheck_entangle_batch(h, B, NB_DEVICE, agent_id, known, late, c->bp_cnt, c->bp_xy, c->bp_cnt_l, c->bp_xy_l, es0,
-                                    in_at<double>(c, L.prev_pos), in_at<double>(c, L.prev_pos_agent), in_at<double>(c, L.cur), n_int,
-                                    a.coeff_out, in_at<double>(c, L.t_start), c->samp, 0, group, r_late,
-                                    out_at<int32_t>(c, L.entangled), st));
+  CY_RC(nb_internal_postcheck_entangle(h, 2, B, NB_DEVICE, agent_id, known, late, c->bp_cnt, c->bp_xy, c->bp_cnt_l, c->bp_xy_l, es0,
+                                       in_at<double>(c, L.prev_pos), in_at<double>(c, L.prev_pos_agent), in_at<double>(c, L.cur),
+                                       n_int, a.coeff_out, in_at<double>(c, L.t_start), c->samp, 0, group, r_late,
+                                       out_at<int32_t>(c, L.entangled), st));
   if (!prof) CY_CUDA(cudaStreamWaitEvent(st, c->ev_C2, 0));
   mark();
   // commit: compose with the previous plan, DynTraj header, records into the ring of every rank (:1685-1699, publishOwnTraj)
@@ -461,7 +476,7 @@ extern "C" int nb_cycle_create(nb_handle* h, const nb_cycle_desc* d, nb_cycle** 
     }
     CY_CUDA(cudaStreamCreateWithFlags(&c->sB, cudaStreamNonBlocking));
     CY_CUDA(cudaStreamCreateWithFlags(&c->sC, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : { &c->ev_fork, &c->ev_hulls, &c->ev_B, &c->ev_C, &c->ev_qp, &c->ev_C2 }) CY_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : { &c->ev_fork, &c->ev_hulls, &c->ev_B, &c->ev_C, &c->ev_qp, &c->ev_C2, &c->ev_pre }) CY_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (auto& e : c->ev_prof) CY_CUDA(cudaEventCreate(&e));
     return NB_OK;
   }();
@@ -489,7 +504,7 @@ extern "C" void nb_cycle_destroy(nb_cycle* c)
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->sB) cudaStreamDestroy(c->sB);
   if (c->sC) cudaStreamDestroy(c->sC);
-  for (cudaEvent_t e : { c->ev_fork, c->ev_hulls, c->ev_B, c->ev_C, c->ev_qp, c->ev_C2 })
+  for (cudaEvent_t e : { c->ev_fork, c->ev_hulls, c->ev_B, c->ev_C, c->ev_qp, c->ev_C2, c->ev_pre })
     if (e) cudaEventDestroy(e);
   for (auto e : c->ev_prof)
     if (e) cudaEventDestroy(e);

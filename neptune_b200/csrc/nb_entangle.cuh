@@ -850,6 +850,8 @@ struct NbEntArgs
   const double* bp_xy_late;      // [N][bp_max][2]
   double* psamp;                 // scratch [B][N][S+1][2]: interval-0 samples per planning agent
   unsigned char* pknown;         // scratch [B][N]
+  int phase;                     // mode 4: 0 whole post-check, 1 up to PredictAlphasBetas (independent of the optimised
+                                 // trajectory: runs beside the QP), 2 entangleCheckGivenPwp on the state phase 1 left
   const double* prev_pos;        // predict
   const double* prev_pos_agent;
   const double* cur;
@@ -886,11 +888,15 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
       return;
     }
   }
+  const bool resume = a.mode == 4 && a.phase == 2;   // the work state is where phase 1 left it
   if (a.mode == 1 || a.mode == 4)
   {  // work on slot 0 of the output (mode 4: on a scratch copy, the reference's local ent_state_begin)
     const size_t o = (size_t)b * (a.mode == 1 ? 9 : 1);
     es.alpha = a.out.alpha + o * a.cap * 2, es.beta = a.out.beta + o * a.cap, es.bend = a.out.bend + o * a.cap;
     es.active = a.out.active + o * NA;
+  }
+  if ((a.mode == 1 || a.mode == 4) && !resume)
+  {
     for (int q = g.lane; q < a.cap; q += NL)
     {
       es.alpha[2 * q] = a.st.alpha[((size_t)b * a.cap + q) * 2], es.alpha[2 * q + 1] = a.st.alpha[((size_t)b * a.cap + q) * 2 + 1];
@@ -904,8 +910,8 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
     es.alpha = a.st.alpha + (size_t)b * a.cap * 2, es.beta = a.st.beta + (size_t)b * a.cap;
     es.bend = a.st.bend + (size_t)b * a.cap, es.active = a.st.active + (size_t)b * NA;
   }
-  es.n_alpha = a.st.cnt[2 * b];
-  es.n_bend = a.st.cnt[2 * b + 1];
+  es.n_alpha = resume ? a.out.cnt[2 * b] : a.st.cnt[2 * b];
+  es.n_bend = resume ? a.out.cnt[2 * b + 1] : a.st.cnt[2 * b + 1];
   g.sync();
   const size_t samp_blk = (size_t)a.N * a.num_pol * (a.S + 1) * 2;
   const double* samp = a.samp ? a.samp + (a.samp_group ? (size_t)a.samp_group[b] * samp_blk : (a.samp_shared ? 0 : (size_t)b * samp_blk))
@@ -983,44 +989,52 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
     // (SamplePointsOfIntervals, :737-738: deltaT = n T / num_pol), the planning-time samples for the others; only
     // interval 0 is ever read (PredictAlphasBetas :986, entangleCheckGivenPwp :899 / :982)
     const double t0 = a.t_start[b], t1 = NB_ADD(t0, NB_MUL((double)n, a.T));
-    for (int j = g.lane; j < a.N; j += NL)
-    {
-      const bool lt = j != cx.self && late[j];
-      pk[j] = (known[j] || lt) ? 1 : 0;
-      if (lt)
-        nb_sample_interval(a.late_recs + (size_t)j * NB_REC, t0, t1, a.num_pol, a.S, 0, ps + (size_t)j * S1 * 2);
-      else
-        for (int q = 0; q < S1 * 2; q++) ps[(size_t)j * S1 * 2 + q] = samp ? samp[(size_t)j * a.num_pol * S1 * 2 + q] : 0.0;
-    }
-    g.sync();
     cx.use_alt = late, cx.bp_cnt_alt = a.bp_cnt_late, cx.bp_xy_alt = a.bp_xy_late;
     const double* pp = a.prev_pos + (size_t)b * (a.N + 1) * 2;
     const double* cur = a.cur + 2 * b;
     int r = 0;
-    // PredictAlphasBetas on the updated samples (:747-749)
-    const int nadd = nb_collect_toadd<NL>(g, cx, pp + 2 * a.N, pp, cur, a.prev_pos_agent + (size_t)b * a.N * 2, 2, ps, S1 * 2, pk,
-                                          toadd, a.tcap);
-    if (nadd < 0)
-      bad = 1;
-    else
+    if (!resume)
     {
-      if (g.lane == 0)
+      for (int j = g.lane; j < a.N; j += NL)
       {
-        if (nb_add_alpha_beta(toadd, nadd, es, pp + 2 * a.N, cx))
-          flag[3] = 1;
+        const bool lt = j != cx.self && late[j];
+        pk[j] = (known[j] || lt) ? 1 : 0;
+        if (lt)
+          nb_sample_interval(a.late_recs + (size_t)j * NB_REC, t0, t1, a.num_pol, a.S, 0, ps + (size_t)j * S1 * 2);
         else
-        {
-          flag[3] = 0;
-          nb_update_bend_pts(es, cur, cx);
-        }
+          for (int q = 0; q < S1 * 2; q++) ps[(size_t)j * S1 * 2 + q] = samp ? samp[(size_t)j * a.num_pol * S1 * 2 + q] : 0.0;
       }
       g.sync();
-      if (flag[3])
+      // PredictAlphasBetas on the updated samples (:747-749)
+      const int nadd = nb_collect_toadd<NL>(g, cx, pp + 2 * a.N, pp, cur, a.prev_pos_agent + (size_t)b * a.N * 2, 2, ps, S1 * 2,
+                                            pk, toadd, a.tcap);
+      if (nadd < 0)
         bad = 1;
-      else if (n > 0)  // entangleCheckGivenPwp (:750), interval 0 only; the scratch samples hold one interval per agent
-        r = nb_ent_interval_pass<NL>(g, es, cx, cxy, 0, ps, pk, 1, a.S, a.T, 3 * NA, toadd, a.tcap, pairs, flag);
-      if (r < 0) bad = 1;
+      else
+      {
+        if (g.lane == 0)
+        {
+          if (nb_add_alpha_beta(toadd, nadd, es, pp + 2 * a.N, cx))
+            flag[3] = 1;
+          else
+          {
+            flag[3] = 0;
+            nb_update_bend_pts(es, cur, cx);
+          }
+        }
+        g.sync();
+        if (flag[3]) bad = 1;
+      }
+      if (a.phase == 1)
+      {  // the state PredictAlphasBetas left: phase 2 resumes from it
+        if (g.lane == 0) a.out.cnt[2 * b] = es.n_alpha, a.out.cnt[2 * b + 1] = es.n_bend;
+        if (bad && g.lane == 0) *a.err = 2;
+        return;
+      }
     }
+    if (!bad && n > 0)  // entangleCheckGivenPwp (:750), interval 0 only; the scratch samples hold one interval per agent
+      r = nb_ent_interval_pass<NL>(g, es, cx, cxy, 0, ps, pk, 1, a.S, a.T, 3 * NA, toadd, a.tcap, pairs, flag);
+    if (r < 0) bad = 1;
     if (g.lane == 0) a.result[b] = r > 0 ? 1 : 0;
   }
   else if (a.mode == 2)

@@ -70,3 +70,9 @@ int nb_internal_hull_aabb(nb_handle* h, size_t n_hulls, const double* hull_xy, c
 int nb_internal_postcheck_hulls(nb_handle* h, int B, const int32_t* n_int, const double* coeff, const int32_t* group,
                                 const double* hull_xy_g, const int32_t* hull_cnt_g, const double* aabb, const uint8_t* late,
                                 int32_t* collide, cudaStream_t st);
+int nb_internal_postcheck_entangle(nb_handle* h, int phase, int32_t B, int32_t space, const int32_t* agent_id, const uint8_t* known,
+                                   const uint8_t* late, const int32_t* bp_cnt, const double* bp_xy, const int32_t* bp_cnt_late,
+                                   const double* bp_xy_late, nb_ent_state st_in, const double* prev_pos,
+                                   const double* prev_pos_agent, const double* cur, const int32_t* n_int, const double* coeff,
+                                   const double* t_start, const double* samp, int32_t samp_shared, const int32_t* samp_group,
+                                   const double* late_recs, int32_t* entangled, void* stream);
