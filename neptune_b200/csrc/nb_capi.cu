@@ -82,12 +82,13 @@ struct NbQpArgs
 #define NB_QP_SMEM_LINES 160     // kept lines whose rows live in shared memory; more: rows in global scratch
 #define NB_QP_SMEM_ROWS (NB_ROW_LINE0 + 4 * NB_QP_SMEM_LINES)
 
-#define NB_QP_THREADS 128
+#define NB_QP_THREADS 128        // four warps per agent; NB_QP_THREADS_WIDE when the batch leaves SMs idle (B <= SM count)
+#define NB_QP_THREADS_WIDE 256
 struct NbQpSmem
 {
   NbQpTable tb;  // first: destination of the bulk copy (16-byte aligned)
   NbQpShared sh;
-  double red[8 * NB_QP_THREADS / 32];
+  double red[8 * NB_QP_THREADS_WIDE / 32];
   double rows[5 * NB_QP_SMEM_ROWS];
   double cl[3 * NB_QP_SMEM_LINES];
   double xout[96];
@@ -129,17 +130,18 @@ NB_DEV void nb_mbar_wait(unsigned long long* bar, unsigned parity)
 
 // K4: one CTA of four warps per agent.  The (n, mode) table (32 KB) is staged by one bulk copy that overlaps the
 // gathering of the agent's lines (nb_qp.cuh has the solver).
-__global__ void __launch_bounds__(NB_QP_THREADS) k_qp(NbConsts cs, const NbQpTable* tables, NbQpArgs a)
+template <int NT>
+__global__ void __launch_bounds__(NT) k_qp(NbConsts cs, const NbQpTable* tables, NbQpArgs a)
 {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   NbQpSmem* sm = reinterpret_cast<NbQpSmem*>(smem_raw);
   const int b = blockIdx.x, lane = threadIdx.x;
-  Group<NB_QP_THREADS> g(lane, sm->red);
+  Group<NT> g(lane, sm->red);
   const int n = a.n_int[b];
   const double* ci = a.coeff_init + (size_t)b * 96;
   if (n < 1 || n > NB_NPOL)
   {  // device-resident batch with a corrupt n_int: nothing is indexed with it; reported by nb_check_async_errors
-    for (int q = lane; q < 96; q += NB_QP_THREADS) a.coeff_out[(size_t)b * 96 + q] = ci[q];
+    for (int q = lane; q < 96; q += NT) a.coeff_out[(size_t)b * 96 + q] = ci[q];
     if (lane == 0)
     {
       *a.err = 5;
@@ -178,8 +180,8 @@ __global__ void __launch_bounds__(NB_QP_THREADS) k_qp(NbConsts cs, const NbQpTab
     const int l0 = i < n ? sm->lstart[i] : 0, l1 = i < n ? sm->lstart[i + 1] : 0;
     if (in_smem)
     {
-      for (int q = lane; q < 3 * (l1 - l0); q += NB_QP_THREADS) sm->cl[3 * l0 + q] = src[q];
-      for (int q = lane; q < l1 - l0; q += NB_QP_THREADS) sm->l2i[l0 + q] = (unsigned char)i;
+      for (int q = lane; q < 3 * (l1 - l0); q += NT) sm->cl[3 * l0 + q] = src[q];
+      for (int q = lane; q < l1 - l0; q += NT) sm->l2i[l0 + q] = (unsigned char)i;
       if (lane == 0) sm->clb[i] = sm->cl;
     }
     else if (lane == 0)
@@ -203,7 +205,7 @@ __global__ void __launch_bounds__(NB_QP_THREADS) k_qp(NbConsts cs, const NbQpTab
       }
     }
     nb_mbar_wait(&sm->mbar, (unsigned)mode);
-    ok = nb_qp_solve<NB_QP_THREADS>(g, cs, &sm->tb, &sm->sh, R, ci, nl, sm->xout, mode == 0 ? &it0 : &it1, &obj,
+    ok = nb_qp_solve<NT>(g, cs, &sm->tb, &sm->sh, R, ci, nl, sm->xout, mode == 0 ? &it0 : &it1, &obj,
                          a.prof ? a.prof + (size_t)b * 16 : nullptr);
     if (ok) status = mode == 0 ? NB_STATUS_OK : NB_STATUS_FALLBACK;
   }
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(NB_QP_THREADS) k_qp(NbConsts cs, const NbQpTab
   const double dx = ci[3] - pfx, dy = ci[32 + 3] - pfy;
   const bool keep_z = sqrt(dx * dx + dy * dy) < 1.0;
   double* co = a.coeff_out + (size_t)b * 96;
-  for (int q = lane; q < 96; q += NB_QP_THREADS)
+  for (int q = lane; q < 96; q += NT)
   {
     const int ax = q / 32, r = q % 32;
     double v = ci[q];
@@ -831,7 +833,8 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
   const size_t lsm = lines_smem_bytes(LS);
   if (!h->qp_smem_set)
   {
-    NB_CUDA(cudaFuncSetAttribute(k_qp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NbQpSmem)));
+    NB_CUDA(cudaFuncSetAttribute(k_qp<NB_QP_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NbQpSmem)));
+    NB_CUDA(cudaFuncSetAttribute(k_qp<NB_QP_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(NbQpSmem)));
     NB_CUDA(cudaFuncSetAttribute(k_lines<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     NB_CUDA(cudaFuncSetAttribute(k_lines<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     h->qp_smem_set = 1;
@@ -848,7 +851,10 @@ extern "C" int nb_replan_batch(nb_handle* h, const nb_replan_args* a, void* stre
     k_lines<128><<<B * NB_NPOL, 128, lsm, st>>>(h->cs, in, LS, (double*)h->lines.p, (uint8_t*)h->line_ok.p,
                                                 (uint8_t*)h->keep.p, (int*)h->err.p, (double*)h->cl.p, (int*)h->ncl.p);
   if (h->profiling) cudaEventRecord(h->ev[1], st);
-  k_qp<<<B, NB_QP_THREADS, sizeof(NbQpSmem), st>>>(h->cs, h->d_tables, q);
+  if (B <= h->num_sms && !getenv("NB_QP_NARROW"))   // the batch leaves SMs idle: eight warps per agent, one row per thread in every sweep
+    k_qp<NB_QP_THREADS_WIDE><<<B, NB_QP_THREADS_WIDE, sizeof(NbQpSmem), st>>>(h->cs, h->d_tables, q);
+  else
+    k_qp<NB_QP_THREADS><<<B, NB_QP_THREADS, sizeof(NbQpSmem), st>>>(h->cs, h->d_tables, q);
   if (h->profiling) cudaEventRecord(h->ev[2], st);
   h->launches += 2;
   NB_CUDA(cudaGetLastError());

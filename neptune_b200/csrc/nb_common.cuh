@@ -42,7 +42,7 @@ struct Group
 {
   int lane;     // thread index within the group
   double* red;  // shared scratch, >= 8 * (NL / 32) doubles when NL > 32
-  static constexpr int SUB = (NL >= 128) ? 4 : 1;  // adjacent lanes that may split one item
+  static constexpr int SUB = (NL >= 256) ? 8 : ((NL >= 128) ? 4 : 1);  // adjacent lanes that may split one item
   NB_HD Group(int l, double* r = nullptr) : lane(l), red(r) {}
 #if defined(__CUDA_ARCH__)
   NB_DEV void sync() const
@@ -149,6 +149,33 @@ struct Group
       __syncthreads();
     }
   }
+  // Split reduction of (sum, max, sum): put() folds the warp by shuffles and parks one partial per warp in half `buf` of
+  // `red`; after ANY later barrier of the caller get() folds the partials.  No barrier of its own: consecutive uses
+  // alternate the halves or are separated by a barrier of the caller.
+  NB_DEV void put(int buf, double s0, double mx, double s1) const
+  {
+    constexpr int W = NL < 32 ? NL : 32;
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1)
+    {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    if (NL > 32 && (lane & 31) == 0)
+    {
+      double* r = red + buf * 3 * (NL / 32) + 3 * (lane >> 5);
+      r[0] = s0, r[1] = mx, r[2] = s1;
+    }
+    if (NL <= 32 && lane == 0 && red) red[buf * 3] = s0, red[buf * 3 + 1] = mx, red[buf * 3 + 2] = s1;
+  }
+  NB_DEV void get(int buf, double& s0, double& mx, double& s1) const
+  {
+    const double* r = red + buf * 3 * (NL > 32 ? NL / 32 : 1);
+    s0 = r[0], mx = r[1], s1 = r[2];
+#pragma unroll
+    for (int q = 1; q < NL / 32; q++) s0 += r[3 * q], mx = fmax(mx, r[3 * q + 1]), s1 += r[3 * q + 2];
+  }
   // sum over the SUB adjacent lanes that share an item
   NB_DEV double sub_sum(double v) const
   {
@@ -166,6 +193,8 @@ struct Group
   void reduce_sum_max(double&, double&) const {}
   void reduce_max_sum_sum(double&, double&, double&) const {}
   double sub_sum(double v) const { return v; }
+  void put(int, double, double, double) const {}
+  void get(int, double&, double&, double&) const {}   // one lane: the values are the lane's own
   int any(int p) const { return p; }
 #endif
 };

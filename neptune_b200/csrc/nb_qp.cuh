@@ -254,55 +254,64 @@ NB_HD void nb_qp_pass(const Group<NL>& g, const NbQpTable* tb, NbQpShared* sh, c
       R.dla[r] = wgt;
     }
   }
-  if (MODE != NB_PASS_RESID && MODE != NB_PASS_DIR_PRED) return;
+  // this lane's share of the sweep's sums is complete: one partial per warp, folded by the caller after the next barrier
+  if (MODE == NB_PASS_RESID) g.put(0, acc.sum_sl, acc.rp_max, 0.0);
+  if (MODE == NB_PASS_DIR_PRED) g.put(1, acc.sum_cross, acc.rmax, acc.sum_dd);
+  if (MODE == NB_PASS_DIR_CORR) g.put(0, 0.0, acc.rmax, 0.0);
+  if (MODE == NB_PASS_START) return;
   g.sync();
-  // per control point (i, k): what its line rows load on the x and y features
-  for (int q = g.lane; q < 4 * n; q += NL)
+  if (MODE == NB_PASS_DIR_CORR) return;
+  // per control point (i, k): what its line rows load on the x and y features.  RESID: four lanes per control point, one
+  // per kind of sum (predictor load, 1 / s, weights, multipliers); PRED: the lanes of a control point split its lines
+  constexpr int SUB = Group<NL>::SUB;
+  if (MODE == NB_PASS_RESID)
   {
-    const int i = q >> 2, k = q & 3;
-    const int fl = i * 8 + k, fx = fl, fy = NB_NFEAT_AX + fl;
-    const double* cl = R.clb[i];
-    double sxx = 0, sxy = 0, syy = 0, lx = 0, ly = 0, dlx = 0, dly = 0, ax_ = 0, ay_ = 0;
-    for (int l = R.lstart[i]; l < R.lstart[i + 1]; l++)
+    for (int q = g.lane; q < 16 * n; q += NL)
     {
-      const double n0 = cl[3 * l], n1 = cl[3 * l + 1];
-      const int r = NB_ROW_LINE0 + 4 * l + k;
-      if (MODE == NB_PASS_RESID)
+      const int cp = q >> 2, role = q & 3, i = cp >> 2, k = cp & 3;
+      const int fl = i * 8 + k, fx = fl, fy = NB_NFEAT_AX + fl;
+      const double* cl = R.clb[i];
+      const double* src = role == 0 ? R.dsa : (role == 1 ? R.inv : (role == 2 ? R.dla : R.lam));
+      double s0 = 0, s1 = 0, s2 = 0;
+      for (int l = R.lstart[i]; l < R.lstart[i + 1]; l++)
       {
-        const double t = R.dsa[r], wgt = R.dla[r], iv = R.inv[r], lam = R.lam[r];
-        lx += t * n0;
-        ly += t * n1;
-        ax_ += iv * n0;
-        ay_ += iv * n1;
-        sxx += wgt * n0 * n0;
-        sxy += wgt * n0 * n1;
-        syy += wgt * n1 * n1;
-        dlx += lam * n0;
-        dly += lam * n1;
+        const double n0 = cl[3 * l], n1 = cl[3 * l + 1], v = src[NB_ROW_LINE0 + 4 * l + k];
+        const double a = role == 2 ? v * n0 : v;
+        s0 += a * n0;
+        s1 += a * n1;
+        s2 += v * n1 * n1;
       }
+      if (role == 0)
+        sh->La[fx] += s0, sh->La[fy] += s1;
+      else if (role == 1)
+        sh->A2[fx] += s0, sh->A2[fy] += s1;
+      else if (role == 2)
+        sh->omv[fl * 4 + 0] += s0, sh->omv[fl * 4 + 1] += s2, sh->omv[fl * 4 + 3] = s1;
       else
-      {
-        const double t = R.dsa[r] * R.dla[r] * R.inv[r];
-        lx += t * n0;
-        ly += t * n1;
-      }
+        sh->du[fx] += s0, sh->du[fy] += s1;
     }
-    if (MODE == NB_PASS_RESID)
+  }
+  else
+  {
+    const int items = 4 * n * SUB;  // <= NL for SUB > 1, so every lane reaches the shuffles below
+    for (int b0 = 0; b0 < items; b0 += NL)
     {
-      sh->La[fx] += lx;
-      sh->La[fy] += ly;
-      sh->A2[fx] += ax_;
-      sh->A2[fy] += ay_;
-      sh->omv[fl * 4 + 0] += sxx;
-      sh->omv[fl * 4 + 1] += syy;
-      sh->omv[fl * 4 + 3] = sxy;
-      sh->du[fx] += dlx;
-      sh->du[fy] += dly;
-    }
-    else
-    {
-      sh->A1[fx] += lx;
-      sh->A1[fy] += ly;
+      const int q = b0 + g.lane;
+      const bool on = q < items;
+      const int cp = on ? q / SUB : 0, sub = q % SUB, i = cp >> 2, k = cp & 3;
+      const int fl = i * 8 + k;
+      const double* cl = R.clb[i];
+      double lx = 0, ly = 0;
+      if (on)
+        for (int l = R.lstart[i] + sub; l < R.lstart[i + 1]; l += SUB)
+        {
+          const int r = NB_ROW_LINE0 + 4 * l + k;
+          const double t = R.dsa[r] * R.dla[r] * R.inv[r];
+          lx += t * cl[3 * l];
+          ly += t * cl[3 * l + 1];
+        }
+      lx = g.sub_sum(lx), ly = g.sub_sum(ly);
+      if (on && sub == 0) sh->A1[fl] += lx, sh->A1[NB_NFEAT_AX + fl] += ly;
     }
   }
   g.sync();
@@ -311,8 +320,13 @@ NB_HD void nb_qp_pass(const Group<NL>& g, const NbQpTable* tb, NbQpShared* sh, c
 // dst[a] = bsign * base[a] + sign * (C^T vecF)[a] + es * extra[a]   (a = ax*dof + c); item (a, sub-lane): the SUB
 // adjacent lanes of a variable split its features and combine by shuffle
 template <int NL>
-NB_HD void nb_qp_ct_all(const Group<NL>& g, const NbQpTable* tb, const NbQpShared* sh_t, const double* vecF, double* dst,
-                        const double* base, double bsign, double sign, const double* extra, double es)
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__   // one copy for the three calls of an iteration
+#else
+inline
+#endif
+void nb_qp_ct_all(const Group<NL>& g, const NbQpTable* tb, const NbQpShared* sh_t, const double* vecF, double* dst,
+                  const double* base, double bsign, double sign, const double* extra, double es)
 {
   constexpr int SUB = Group<NL>::SUB;
   const int n = tb->n, dof = tb->dof, nv = 3 * dof;
@@ -322,21 +336,25 @@ NB_HD void nb_qp_ct_all(const Group<NL>& g, const NbQpTable* tb, const NbQpShare
     const int q = b0 + g.lane;
     const bool on = q < items;
     const int a = on ? q / SUB : 0, sub = q % SUB;
-    const int ax = sh_t->ax_of[a], c = sh_t->c_of[a];
+    const int ax = (a >= dof ? 1 : 0) + (a >= 2 * dof ? 1 : 0), c = a - ax * dof;
+    const double tail = bsign * base[a] + (extra ? extra[a] * es : 0.0);   // loaded before the sums, not after them
     double v0 = 0.0, v1 = 0.0;
     if (on)
     {
-      const double* vf = vecF + ax * NB_NFEAT_AX;
-      int fl = sub;
-      for (; fl + SUB < 8 * n; fl += 2 * SUB)
+      const double* vf = vecF + ax * NB_NFEAT_AX + sub;
+      const double* cc = &tb->C[sub][c];
+      const int cnt = (8 * n - sub + SUB - 1) / SUB;   // features sub, sub + SUB, ...
+      int k = 0;
+#pragma unroll 2
+      for (; k + 1 < cnt; k += 2)
       {
-        v0 += tb->C[fl][c] * vf[fl];
-        v1 += tb->C[fl + SUB][c] * vf[fl + SUB];
+        v0 += cc[(size_t)k * SUB * NB_DOF_MAX] * vf[k * SUB];
+        v1 += cc[(size_t)(k + 1) * SUB * NB_DOF_MAX] * vf[(k + 1) * SUB];
       }
-      if (fl < 8 * n) v0 += tb->C[fl][c] * vf[fl];
+      if (k < cnt) v0 += cc[(size_t)k * SUB * NB_DOF_MAX] * vf[k * SUB];
     }
     const double v = g.sub_sum(v0 + v1);
-    if (on && sub == 0) dst[a] = bsign * base[a] + sign * v + (extra ? extra[a] * es : 0.0);
+    if (on && sub == 0) dst[a] = tail + sign * v;
   }
 }
 
@@ -347,20 +365,31 @@ template <int NL>
 NB_HD void nb_qp_assemble(const Group<NL>& g, const NbQpTable* tb, NbQpShared* sh, bool has_qc, double lam_q)
 {
   const int n = tb->n, dof = tb->dof, np = dof * (dof + 1) / 2;
-  for (int q = g.lane; q < 4 * np; q += NL)
+  constexpr int S2 = NL >= 128 ? 2 : 1;  // adjacent lanes that split the features of one (block, pair)
+  const int items = 4 * np * S2;
+  for (int b0 = 0; b0 < items; b0 += NL)
   {
-    const int blk = q / np, p = q - blk * np;
+    const int q = b0 + g.lane;
+    const bool on = q < items;
+    const int e = on ? q / S2 : 0, sub = q % S2;
+    const int blk = e / np, p = e - blk * np;
     const int ca = sh->pca[p], cb = sh->pcb[p];
-    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-#pragma unroll 2
-    for (int fl = 0; fl < 8 * n; fl += 4)
+    double v0 = 0.0, v1 = 0.0;
+    if (on)
     {
-      v0 += sh->omv[fl * 4 + blk] * tb->PP[fl][p];
-      v1 += sh->omv[fl * 4 + 4 + blk] * tb->PP[fl + 1][p];
-      v2 += sh->omv[fl * 4 + 8 + blk] * tb->PP[fl + 2][p];
-      v3 += sh->omv[fl * 4 + 12 + blk] * tb->PP[fl + 3][p];
+      const double* om = sh->omv + blk;
+#pragma unroll 2
+      for (int fl = 2 * sub; fl < 8 * n; fl += 2 * S2)
+      {
+        v0 += om[fl * 4] * tb->PP[fl][p];
+        v1 += om[fl * 4 + 4] * tb->PP[fl + 1][p];
+      }
     }
-    double v = (v0 + v1) + (v2 + v3);
+    double v = v0 + v1;
+#if defined(__CUDA_ARCH__)
+    if (S2 == 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+#endif
+    if (!on || sub != 0) continue;
     if (blk < 3)
     {
       v += tb->Hr[ca][cb];
@@ -386,21 +415,52 @@ NB_HD void nb_qp_factor_blocks(const Group<NL>& g, NbQpShared* sh, int nxy, int 
 {
   double* K = sh->K;
   const int nv = nxy + nz, ne = sh->nelem;
+  if (NL >= 128)
+  {  // a thread owns at most two elements (ne + nv <= 172): their addresses and last step are fixed over the columns
+    double *pe[2], *pi[2], *pj[2], *pd[2];
+    int last[2];  // the element takes the updates of steps t < last
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+    {
+      const int e = g.lane + u * NL;
+      const bool on = e < ne + nv;
+      const int i = !on ? 0 : (e < ne ? sh->ei[e] : e - ne), j = !on ? 0 : (e < ne ? sh->ej[e] : e - ne);
+      const int base = i >= nxy ? nxy : 0;
+      pe[u] = K + i * NB_KLD + j, pi[u] = K + i * NB_KLD + base, pj[u] = K + j * NB_KLD + base, pd[u] = K + base * (NB_KLD + 1);
+      last[u] = on ? j - base : 0;
+    }
 #pragma unroll 1
-  for (int t = 0; t < nxy; t++)
+    for (int t = 0; t < nxy; t++)
+    {
+#pragma unroll
+      for (int u = 0; u < 2; u++)
+        if (t < last[u])
+        {
+          double d = pd[u][t * (NB_KLD + 1)];  // K[k][k], k = base + t
+          d = d > 1e-300 ? d : 1e-300;  // rank-deficiency guard (K is positive definite by construction)
+          *pe[u] -= pi[u][t] * pj[u][t] * nb_rcp(d);
+        }
+      g.sync();
+    }
+  }
+  else
   {
 #pragma unroll 1
-    for (int e = g.lane; e < ne + nv; e += NL)
+    for (int t = 0; t < nxy; t++)
     {
-      const int i = e < ne ? sh->ei[e] : e - ne, j = e < ne ? sh->ej[e] : e - ne;
-      const bool second = i >= nxy;
-      const int k = second ? nxy + t : t;
-      if ((second && t >= nz) || j <= k) continue;
-      double d = K[k * NB_KLD + k];
-      d = d > 1e-300 ? d : 1e-300;  // rank-deficiency guard (K is positive definite by construction)
-      K[i * NB_KLD + j] -= K[i * NB_KLD + k] * K[j * NB_KLD + k] * nb_rcp(d);
+#pragma unroll 1
+      for (int e = g.lane; e < ne + nv; e += NL)
+      {
+        const int i = e < ne ? sh->ei[e] : e - ne, j = e < ne ? sh->ej[e] : e - ne;
+        const bool second = i >= nxy;
+        const int k = second ? nxy + t : t;
+        if ((second && t >= nz) || j <= k) continue;
+        double d = K[k * NB_KLD + k];
+        d = d > 1e-300 ? d : 1e-300;  // rank-deficiency guard (K is positive definite by construction)
+        K[i * NB_KLD + j] -= K[i * NB_KLD + k] * K[j * NB_KLD + k] * nb_rcp(d);
+      }
+      g.sync();
     }
-    g.sync();
   }
   for (int k = g.lane; k < nv; k += NL)
   {
@@ -424,20 +484,42 @@ __device__ __noinline__ double nb_warp_solve(const double* K, const double* invd
   const bool mine = il < nb;
   const double* row = K + lane * NB_KLD + base;   // L[i][base + t], t < il
   const double* col = K + base * NB_KLD + lane;   // L[base + t][i], t > il (stride NB_KLD)
-#pragma unroll 2
-  for (int t = 0; t < nxy; t++)
+  // blocks of four steps; the entries of L of the NEXT block are loaded while this one runs, so that the chain is
+  // shuffle + FMA only (steps past the block's size carry l = 0 and change nothing)
+  const int nblk = (nxy + 3) >> 2;
+  const int tf = mine ? il : 0, tb0 = mine ? il : 1 << 20, tb1 = mine ? nb : 0;   // forward: t < tf; backward: tb0 < t < tb1
+  double l0 = 0 < tf ? row[0] : 0.0, l1 = 1 < tf ? row[1] : 0.0, l2 = 2 < tf ? row[2] : 0.0, l3 = 3 < tf ? row[3] : 0.0;
+  const double id = mine ? invd[lane] : 0.0;
+#pragma unroll 1
+  for (int k = 0; k < nblk; k++)
   {
-    const double l = (mine && t < il) ? row[t] : 0.0;
-    const double xk = __shfl_sync(0xffffffffu, x, (base + t) & 31);
-    x -= l * xk;
+    const int t = 4 * k, u = t + 4;
+    const double m0 = u < tf ? row[u] : 0.0, m1 = u + 1 < tf ? row[u + 1] : 0.0, m2 = u + 2 < tf ? row[u + 2] : 0.0,
+                 m3 = u + 3 < tf ? row[u + 3] : 0.0;
+    x -= l0 * __shfl_sync(0xffffffffu, x, (base + t) & 31);
+    x -= l1 * __shfl_sync(0xffffffffu, x, (base + t + 1) & 31);
+    x -= l2 * __shfl_sync(0xffffffffu, x, (base + t + 2) & 31);
+    x -= l3 * __shfl_sync(0xffffffffu, x, (base + t + 3) & 31);
+    l0 = m0, l1 = m1, l2 = m2, l3 = m3;
   }
-  x *= mine ? invd[lane] : 0.0;
-#pragma unroll 2
-  for (int t = nxy - 1; t >= 0; t--)
+  x *= id;
   {
-    const double l = (mine && t > il && t < nb) ? col[t * NB_KLD] : 0.0;
-    const double xk = __shfl_sync(0xffffffffu, x, (base + t) & 31);
-    x -= l * xk;
+    const int t = 4 * (nblk - 1);
+    l0 = (t > tb0 && t < tb1) ? col[t * NB_KLD] : 0.0, l1 = (t + 1 > tb0 && t + 1 < tb1) ? col[(t + 1) * NB_KLD] : 0.0;
+    l2 = (t + 2 > tb0 && t + 2 < tb1) ? col[(t + 2) * NB_KLD] : 0.0, l3 = (t + 3 > tb0 && t + 3 < tb1) ? col[(t + 3) * NB_KLD] : 0.0;
+  }
+#pragma unroll 1
+  for (int k = nblk - 1; k >= 0; k--)
+  {
+    const int t = 4 * k, u = t - 4;
+    const double m0 = (u > tb0 && u < tb1) ? col[u * NB_KLD] : 0.0, m1 = (u + 1 > tb0 && u + 1 < tb1) ? col[(u + 1) * NB_KLD] : 0.0,
+                 m2 = (u + 2 > tb0 && u + 2 < tb1) ? col[(u + 2) * NB_KLD] : 0.0,
+                 m3 = (u + 3 > tb0 && u + 3 < tb1) ? col[(u + 3) * NB_KLD] : 0.0;
+    x -= l3 * __shfl_sync(0xffffffffu, x, (base + t + 3) & 31);
+    x -= l2 * __shfl_sync(0xffffffffu, x, (base + t + 2) & 31);
+    x -= l1 * __shfl_sync(0xffffffffu, x, (base + t + 1) & 31);
+    x -= l0 * __shfl_sync(0xffffffffu, x, (base + t) & 31);
+    l0 = m0, l1 = m1, l2 = m2, l3 = m3;
   }
   return mine ? x : 0.0;
 }
@@ -446,7 +528,8 @@ __device__ __noinline__ double nb_warp_solve(const double* K, const double* invd
 // Solve K x = b in place, K = K0 (factorised blocks) + dq g g^T by Sherman-Morrison when dq != 0 (u = K0^-1 g and
 // gu = g . u precomputed in sh->uq).  Device: x in registers, pivots broadcast by shuffle, the two blocks in lockstep.
 template <int NL>
-NB_HD void nb_qp_solve_blocks(const Group<NL>& g, NbQpShared* sh, int nxy, int nz, double* b, double dq, double gu)
+NB_HD void nb_qp_solve_blocks(const Group<NL>& g, NbQpShared* sh, int nxy, int nz, double* b, double dq, double gu,
+                               long long* cyc = nullptr)
 {
   const int nv = nxy + nz;
   g.sync();
@@ -455,13 +538,15 @@ NB_HD void nb_qp_solve_blocks(const Group<NL>& g, NbQpShared* sh, int nxy, int n
   {
     const int i = g.lane;
     const bool mine = i < nv;
+    const long long c0 = cyc ? clock64() : 0;
     double x = nb_warp_solve(sh->K, sh->invd, nxy, nz, i, mine ? b[i] : 0.0);
+    if (cyc) *cyc += clock64() - c0;   // measurement hook: the substitution chain alone
     if (dq != 0.0)
     {
       double gy = mine ? sh->gq[i] * x : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) gy += __shfl_xor_sync(0xffffffffu, gy, o);
-      if (mine) x -= sh->uq[i] * (dq * gy / (1.0 + dq * gu));
+      if (mine) x -= sh->uq[i] * (dq * gy * nb_rcp(1.0 + dq * gu));
     }
     if (mine) b[i] = x;
   }
@@ -480,7 +565,7 @@ NB_HD void nb_qp_solve_blocks(const Group<NL>& g, NbQpShared* sh, int nxy, int n
   {
     double gy = 0.0;
     for (int i = 0; i < nv; i++) gy += sh->gq[i] * b[i];
-    for (int i = 0; i < nv; i++) b[i] -= sh->uq[i] * (dq * gy / (1.0 + dq * gu));
+    for (int i = 0; i < nv; i++) b[i] -= sh->uq[i] * (dq * gy * nb_rcp(1.0 + dq * gu));
   }
 #endif
   g.sync();
@@ -515,7 +600,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
 {
   // measurement hook (nb_set_profiling): SM cycles lane 0 spends per phase, summed over the iterations
 #if defined(__CUDA_ARCH__)
-  long long pt[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }, pc = prof ? clock64() : 0;
+  long long pt[16] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 }, pc = prof ? clock64() : 0;
 #define NB_QP_TICK(k)                     \
   if (prof)                               \
   {                                       \
@@ -577,6 +662,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
   const double ddx = sh->init3[0][2] - sh->pf[0], ddy = sh->init3[1][2] - sh->pf[1], ddz = sh->init3[2][2] - sh->pf[2];
   const bool has_qc = sqrt(ddx * ddx + ddy * ddy + ddz * ddz) < 1.0;  // :697-702
   const int m = 48 * n + 4 * nlines, mq = m + (has_qc ? 1 : 0);
+  const double inv_mq = 1.0 / mq;
   double bmax = 0.0, hn = 0.0;
   for (int ax = 0; ax < 3; ax++)
     for (int c = 0; c < 3; c++) bmax = fmax(bmax, fabs(sh->init3[ax][c]));
@@ -708,23 +794,13 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
     for (it = 0; it <= cs.max_iter; it++)
     {
       const bool init_pass = (it == 0);
-      // ---- residuals and weights
-      NbPassAcc acc = { 0.0, 0.0, 0.0, 0.0, 0.0 };
-      nb_qp_pass<NL, NB_PASS_RESID>(g, tb, sh, R, nlines, 0.0, al_pending, acc);
-      al_pending = 0.0;
-      NB_QP_TICK(1);
+      // ---- residuals and weights; beside them gobj = Hr w + g0 (the sweep's last barrier publishes both)
       double cval = 0.0, rp_q = 0.0;
       if (has_qc)
       {
         NB_QC_EVAL(cval);
         rp_q = cval + s_q;
       }
-      double sum_sl = acc.sum_sl, rp_max = acc.rp_max;
-      g.reduce_sum_max(sum_sl, rp_max);
-      const double mu = (sum_sl + (has_qc ? s_q * lam_q : 0.0)) / mq;
-      double rpn = rp_max;
-      if (has_qc) rpn = fmax(rpn, fabs(rp_q));
-      // gobj = Hr w + g0 ; r_d = gobj + C^T(lambda load) + lam_q grad c
       for (int a = g.lane; a < nv; a += NL)
       {
         const int ax = sh->ax_of[a], c = sh->c_of[a];
@@ -733,17 +809,44 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
         sh->gobj[a] = go;
         sh->gq[a] = has_qc ? 2.0 * e3[ax] * tb->tq[c] : 0.0;
       }
-      g.sync();
+      NbPassAcc acc = { 0.0, 0.0, 0.0, 0.0, 0.0 };
+      nb_qp_pass<NL, NB_PASS_RESID>(g, tb, sh, R, nlines, 0.0, al_pending, acc);
+      al_pending = 0.0;
+      NB_QP_TICK(1);
+      double sum_sl = acc.sum_sl, rp_max = acc.rp_max, unused_ = 0.0;
+      g.get(0, sum_sl, rp_max, unused_);
+      const double mu = (sum_sl + (has_qc ? s_q * lam_q : 0.0)) * inv_mq;
+      double rpn = rp_max;
+      if (has_qc) rpn = fmax(rpn, fabs(rp_q));
+      // r_d = gobj + C^T(lambda load) + lam_q grad c
       nb_qp_ct_all<NL>(g, tb, sh, sh->du, sh->rd, sh->gobj, 1.0, 1.0, sh->gq, has_qc ? lam_q : 0.0);
       g.sync();
+      NB_QP_TICK(11);
       double rdn = 0.0, gn = 0.0, fobj = fconst;
-#pragma unroll 1
+#if defined(__CUDA_ARCH__)
+      {  // nv <= 24 values in shared memory: every WARP folds them itself, one value per lane (no barrier)
+        const int a = g.lane & 31;
+        const bool on = a < nv;
+        const double go = on ? sh->gobj[a] : 0.0;
+        double fo = on ? 0.5 * (sh->g0[a] + go) * sh->w[a] : 0.0;
+        rdn = on ? fabs(sh->rd[a]) : 0.0, gn = fabs(go);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+          rdn = fmax(rdn, __shfl_xor_sync(0xffffffffu, rdn, o));
+          gn = fmax(gn, __shfl_xor_sync(0xffffffffu, gn, o));
+          fo += __shfl_xor_sync(0xffffffffu, fo, o);
+        }
+        fobj += fo;
+      }
+#else
       for (int a = 0; a < nv; a++)
-      {  // nv <= 24 values in shared memory: every lane folds them itself (no exchange, no barrier)
+      {
         rdn = fmax(rdn, fabs(sh->rd[a]));
         gn = fmax(gn, fabs(sh->gobj[a]));
         fobj += 0.5 * (sh->g0[a] + sh->gobj[a]) * sh->w[a];
       }
+#endif
       if (!init_pass)
       {
         if (rpn <= cs.tol * (1.0 + hn) && rdn <= cs.tol * (1.0 + gn) && mu * mq <= cs.tol * (1.0 + fabs(fobj)))
@@ -760,7 +863,8 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       NB_QP_TICK(3);
       nb_qp_factor_blocks<NL>(g, sh, nxy, nz);
       NB_QP_TICK(4);
-      const double d_q = has_qc ? lam_q / s_q : 0.0;
+      const double is_q = has_qc ? nb_rcp(s_q) : 0.0, il_q = has_qc ? nb_rcp(lam_q) : 0.0;
+      const double d_q = lam_q * is_q;
       double gu = 0.0;
       if (has_qc)
       {  // Sherman-Morrison for the rank-one term d_q gq gq^T: u = K0^-1 gq
@@ -771,24 +875,30 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
         gu = g.sum(t);
       }
       // ---- predictor
-      const double tau_q = has_qc ? (lam_q * rp_q - s_q * lam_q) / s_q : 0.0;
+      const double tau_q = (lam_q * rp_q - s_q * lam_q) * is_q;
       nb_qp_ct_all<NL>(g, tb, sh, sh->La, sh->dw, sh->rd, -1.0, -1.0, sh->gq, -tau_q);
+      NB_QP_TICK(9);
+#if defined(__CUDA_ARCH__)
+      nb_qp_solve_blocks<NL>(g, sh, nxy, nz, sh->dw, d_q, gu, prof ? &pt[12] : nullptr);
+#else
       nb_qp_solve_blocks<NL>(g, sh, nxy, nz, sh->dw, d_q, gu);
+#endif
+      NB_QP_TICK(10);
       nb_qp_features<NL>(g, tb, sh, sh->dy, sh->dw, false);
       g.sync();
       NB_QP_TICK(5);
       acc = NbPassAcc{ 0.0, 0.0, 0.0, 0.0, 0.0 };
       nb_qp_pass<NL, NB_PASS_DIR_PRED>(g, tb, sh, R, nlines, 0.0, 0.0, acc);
       double rmax = acc.rmax, scross = acc.sum_cross, sdd = acc.sum_dd;
-      g.reduce_max_sum_sum(rmax, scross, sdd);
+      g.get(1, scross, rmax, sdd);
       NB_QP_TICK(6);
       if (has_qc)
       {
         double gd = 0.0;
         for (int a = 0; a < nv; a++) gd += sh->gq[a] * sh->dw[a];
         dsa_q = -rp_q - gd;
-        dla_q = (-s_q * lam_q - lam_q * dsa_q) / s_q;
-        rmax = fmax(rmax, fmax(-dsa_q / s_q, -dla_q / lam_q));
+        dla_q = (-s_q * lam_q - lam_q * dsa_q) * is_q;
+        rmax = fmax(rmax, fmax(-dsa_q * is_q, -dla_q * il_q));
         scross += s_q * dla_q + lam_q * dsa_q;
         sdd += dsa_q * dla_q;
       }
@@ -802,19 +912,19 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
         }
         continue;
       }
-      const double a_aff = rmax > 1.0 ? 1.0 / rmax : 1.0;
-      const double mu_aff = (mu * mq + a_aff * scross + a_aff * a_aff * sdd) / mq;
-      const double rat = mu_aff / mu;
+      const double a_aff = rmax > 1.0 ? nb_rcp(rmax) : 1.0;
+      const double mu_aff = (mu * mq + a_aff * scross + a_aff * a_aff * sdd) * inv_mq;
+      const double rat = mu_aff * nb_rcp(mu);
       double sigmu = rat * rat * rat * mu;
       // do not drive the complementarity below a tenth of what the stopping test needs: at mu ~ 1e-12 the
       // normal matrix is too ill-conditioned for the dual residual to reach its tolerance
-      sigmu = fmax(sigmu, 0.1 * cs.tol * (1.0 + fabs(fobj)) / mq);
+      sigmu = fmax(sigmu, 0.1 * cs.tol * (1.0 + fabs(fobj)) * inv_mq);
       // ---- corrector: load = predictor load - ds_aff dl_aff / s + sigma mu / s, per feature
       for (int q = g.lane; q < NB_NF3; q += NL)
         if ((q & 63) < 8 * n) sh->La[q] += sigmu * sh->A2[q] - sh->A1[q];
       g.sync();
       const double rc_q = s_q * lam_q + dsa_q * dla_q - sigmu;
-      const double tau_q2 = has_qc ? (lam_q * rp_q - rc_q) / s_q : 0.0;
+      const double tau_q2 = (lam_q * rp_q - rc_q) * is_q;
       nb_qp_ct_all<NL>(g, tb, sh, sh->La, sh->dw, sh->rd, -1.0, -1.0, sh->gq, -tau_q2);
       nb_qp_solve_blocks<NL>(g, sh, nxy, nz, sh->dw, d_q, gu);
       nb_qp_features<NL>(g, tb, sh, sh->dy, sh->dw, false);
@@ -822,7 +932,8 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       NB_QP_TICK(7);
       acc = NbPassAcc{ 0.0, 0.0, 0.0, 0.0, 0.0 };
       nb_qp_pass<NL, NB_PASS_DIR_CORR>(g, tb, sh, R, nlines, sigmu, 0.0, acc);
-      rmax = g.max(acc.rmax);
+      rmax = acc.rmax;
+      g.get(0, unused_, rmax, unused_);
       NB_QP_TICK(8);
       double ds_q = 0.0, dl_q = 0.0;
       if (has_qc)
@@ -830,11 +941,11 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
         double gd = 0.0;
         for (int a = 0; a < nv; a++) gd += sh->gq[a] * sh->dw[a];
         ds_q = -rp_q - gd;
-        dl_q = (-rc_q - lam_q * ds_q) / s_q;
-        rmax = fmax(rmax, fmax(-ds_q / s_q, -dl_q / lam_q));
+        dl_q = (-rc_q - lam_q * ds_q) * is_q;
+        rmax = fmax(rmax, fmax(-ds_q * is_q, -dl_q * il_q));
       }
-      const double eta = 1.0 - 1.0 / ((it + 3.0) * (it + 3.0));
-      double al = rmax > 0.0 ? eta / rmax : 1.0;
+      const double eta = 1.0 - nb_rcp((it + 3.0) * (it + 3.0));
+      double al = rmax > 0.0 ? eta * nb_rcp(rmax) : 1.0;
       if (al > 1.0) al = 1.0;
       al_pending = al;
       if (has_qc)
@@ -849,7 +960,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
   }
 #if defined(__CUDA_ARCH__)
   if (prof && g.lane == 0)
-    for (int k = 0; k < 10; k++) prof[k] += pt[k];
+    for (int k = 0; k < 16; k++) prof[k] += pt[k];
 #endif
 #undef NB_QP_TICK
 #undef NB_QC_EVAL

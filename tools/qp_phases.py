@@ -10,7 +10,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from neptune_b200 import capi  # noqa: E402
 
-NAMES = ["setup", "resid", "rd+test", "assemble", "factor", "pred solve", "pred sweep", "corr solve", "final sweep"]
+NAMES = ["setup", "resid", "rd fold+test", "assemble", "factor", "pred features", "pred sweep", "corr solve", "final sweep",
+         "pred ct_all", "pred solve", "rd ct_all", "(chain of pred solve)"]
 
 
 def main():
@@ -28,13 +29,14 @@ def main():
     ms = (C.c_double * 2)()
     lib.nb_kernel_times(s.handle, ms, 2)
     it = res.iters.sum(axis=1)
-    tot = out[:, :9].sum(axis=1)
+    tot = out[:, :12].sum(axis=1)
     worst = int(np.argmax(tot))
     print(f"k_lines {ms[0]:.4f} ms  k_qp {ms[1]:.4f} ms; iterations mean {it.mean():.1f} max {it.max()}; "
           f"slowest warp {worst}: n={b.n_int[worst]} iters={res.iters[worst].tolist()} cycles={tot[worst]} "
           f"({tot[worst] / 1.965e6:.3f} ms at 1965 MHz)")
     print("phase           mean cycles/agent   slowest warp   per iteration (slowest)")
     for q, nme in enumerate(NAMES):
+        q = 12 if q == 12 else q
         print(f"{nme:14s} {out[:, q].mean():14.0f} {out[worst, q]:14d} {out[worst, q] / max(1, it[worst]):14.0f}")
 
 
