@@ -297,48 +297,57 @@ __global__ void __launch_bounds__(NT) k_entangle(NbEntArgs a)
 }
 
 // ---- K1 / K5 kernels
-__global__ void k_hulls(NbConsts cs, int B, const double* t_start, const double* recs, const uint8_t* known, double delta,
-                        double* hull_xy, int* hull_cnt, int64_t* hull_ptr, double* nih0, int* idx, double* samp, int* err)
+// One CTA of eight warps per (b, j): warp i builds the hull of window i (nb_hull_of_window_warp), then the threads take one
+// sample each of Neptune::SamplePointsOfCurves for the same trajectory (the record is read once per CTA).
+__global__ void __launch_bounds__(32 * NB_NPOL) k_hulls(NbConsts cs, int B, const double* t_start, const double* recs,
+                                                        const uint8_t* known, double delta, double* hull_xy, int* hull_cnt,
+                                                        int64_t* hull_ptr, double* nih0, int* idx, double* samp, int* err)
 {
-  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // (b, j, i), then the sample sets (b, j)
-  const size_t total = (size_t)B * cs.N * NB_NPOL;
-  if (k >= total)
-  {  // Neptune::SamplePointsOfCurves: one thread per (b, j), same launch (independent work)
-    const size_t q = k - total;
-    if (!samp || q >= (size_t)B * cs.N) return;
-    const int j = (int)(q % cs.N), b = (int)(q / cs.N);
-    double* out = samp + q * cs.num_pol * (cs.S + 1) * 2;
-    if (!known[q])
-    {
-      for (int e = 0; e < cs.num_pol * (cs.S + 1) * 2; e++) out[e] = 0.0;
-      return;
-    }
-    nb_sample_points(cs, recs + (size_t)j * NB_REC, t_start[b], NB_ADD(t_start[b], NB_MUL(cs.T, (double)cs.num_pol)), out,
-                     nullptr);
-    return;
-  }
-  const int i = (int)(k % NB_NPOL), j = (int)((k / NB_NPOL) % cs.N), b = (int)(k / ((size_t)NB_NPOL * cs.N));
-  hull_ptr[k] = (int64_t)k * NB_HMAX;
+  __shared__ double scr[NB_NPOL][NB_HULL_WARP_SCRATCH];
+  __shared__ double rec_s[NB_REC_PWP];
+  const size_t bj = blockIdx.x;   // (b, j)
+  const int j = (int)(bj % cs.N), b = (int)(bj / cs.N);
+  const int i = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool kn = known[bj] != 0;
+  const double ts = t_start[b];
+  if (kn)
+    for (int q = threadIdx.x; q < NB_REC_PWP; q += blockDim.x) rec_s[q] = recs[(size_t)j * NB_REC + q];
+  __syncthreads();
+  const size_t k = bj * NB_NPOL + i;
   int cnt = 0, id2[2] = { -1, -1 };
   double n0[2];
   n0[0] = n0[1] = __longlong_as_double(0x7ff8000000000000LL);
-  if (i < cs.num_pol && known[(size_t)b * cs.N + j])
+  if (i < cs.num_pol && kn)
   {
-    const double t0 = NB_ADD(t_start[b], NB_MUL((double)i, cs.T)), t1 = NB_ADD(t_start[b], NB_MUL((double)(i + 1), cs.T));
-    cnt = nb_hull_of_window(cs, recs + (size_t)j * NB_REC, t0, t1, delta, hull_xy + k * NB_HMAX * 2, n0, id2);
+    const double t0 = NB_ADD(ts, NB_MUL((double)i, cs.T)), t1 = NB_ADD(ts, NB_MUL((double)(i + 1), cs.T));
+    cnt = nb_hull_of_window_warp(cs, rec_s, t0, t1, delta, hull_xy + k * NB_HMAX * 2, n0, id2, scr[i], lane);
     if (cnt < 0 || cnt > NB_HMAX)
     {
-      *err = 3;
+      if (lane == 0) *err = 3;
       cnt = 0;
     }
   }
-  hull_cnt[k] = cnt;
-  nih0[2 * k] = n0[0];
-  nih0[2 * k + 1] = n0[1];
-  if (idx)
+  if (lane == 0)
   {
-    idx[2 * k] = id2[0];
-    idx[2 * k + 1] = id2[1];
+    hull_ptr[k] = (int64_t)k * NB_HMAX;
+    hull_cnt[k] = cnt;
+    nih0[2 * k] = n0[0];
+    nih0[2 * k + 1] = n0[1];
+    if (idx)
+    {
+      idx[2 * k] = id2[0];
+      idx[2 * k + 1] = id2[1];
+    }
+  }
+  if (!samp) return;
+  const int S1 = cs.S + 1, ns = cs.num_pol * S1;
+  double* out = samp + bj * ns * 2;
+  for (int q = threadIdx.x; q < ns; q += blockDim.x)
+  {
+    if (!kn)
+      out[2 * q] = 0.0, out[2 * q + 1] = 0.0;
+    else
+      nb_sample_one(rec_s, ts, NB_ADD(ts, NB_MUL(cs.T, (double)cs.num_pol)), cs.num_pol, cs.S, q / S1, q % S1, out + 2 * q);
   }
 }
 
@@ -1235,9 +1244,8 @@ extern "C" int nb_hulls_batch(nb_handle* h, int32_t B, int32_t space, const doub
   if ((rc = stage_out(h, 3, space, nih0, nh * 2, &dn0))) return rc;
   if ((rc = stage_out(h, 4, space, samp, (size_t)B * N * P * (S + 1) * 2, &dsamp))) return rc;
   if ((rc = stage_out(h, 5, space, idx, nh * 2, &didx))) return rc;
-  const size_t nthreads = nh + (dsamp ? (size_t)B * N : 0);
-  k_hulls<<<(unsigned)((nthreads + 63) / 64), 64, 0, st>>>(h->cs, B, dt, dr, dk, delta, dxy, dcnt, dptr, dn0, didx, dsamp,
-                                                         (int*)h->err.p);
+  k_hulls<<<(unsigned)((size_t)B * N), 32 * NB_NPOL, 0, st>>>(h->cs, B, dt, dr, dk, delta, dxy, dcnt, dptr, dn0, didx, dsamp,
+                                                           (int*)h->err.p);
   h->launches += 1;
   NB_CUDA(cudaGetLastError());
   if (space == NB_HOST)

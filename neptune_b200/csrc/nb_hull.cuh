@@ -238,46 +238,206 @@ NB_HD int nb_hull_of_window(const NbConsts& cs, const double* rec, double t0, do
   return nb_chain_sorted(pts, np, hull, NB_HMAX);
 }
 
+#if defined(__CUDACC__)
+// ---- nb_hull_of_window by ONE WARP (k_hulls): the same points, the same sorted sequence and the same chain as the
+// scalar version above, hence the same hull bit for bit, but nothing sequential except the chain itself:
+//   * piece range by ballot over the knot vector, control points one lane each;
+//   * the 4 nc inflated corners one or two per lane, sorted by RANK: a corner's place is the number of corners that
+//     precede it lexicographically (ties by index; equal corners are dropped afterwards, so their order is immaterial);
+//   * lower and upper chain at the same time on lanes 0 and 1 (Andrew's two chains do not depend on each other; the
+//     scalar code's `t = k + 1` floor for the second loop is exactly "the upper chain starts at the last point").
+// scratch: NB_HULL_WARP_SCRATCH doubles of shared memory per warp.
+#define NB_HULL_WARP_SCRATCH (2 * 64 + 2 * 64 + 2 * 2 * 66)
+__device__ __forceinline__ int nb_hull_of_window_warp(const NbConsts& cs, const double* rec, double t0, double t1, double delta,
+                                                      double* hull /*global [NB_HMAX][2]*/, double* nih0, int* idx, double* scr,
+                                                      int lane)
+{
+  const unsigned FULL = 0xffffffffu;
+  double* pts = scr;             // [64][2] inflated corners, unsorted
+  double* srt = scr + 128;       // [64][2] sorted, then de-duplicated in place
+  double* chn = scr + 256;       // [2][66][2] lower / upper chain
+  const int np = nb_rec_np(rec), nt = np + 1;
+  const double* times = nb_rec_times(rec);
+  const double* cx = nb_rec_coeff(rec, 0);
+  const double* cy = nb_rec_coeff(rec, 1);
+  const double tl = lane < nt ? times[lane] : 0.0;
+  // lower_bound(t0): first i with !(times[i] < t0); upper_bound(t1): first i with t1 < times[i]
+  const unsigned in = nt >= 32 ? FULL : ((1u << nt) - 1u);
+  const unsigned nlt = ~__ballot_sync(FULL, lane < nt && tl < t0) & in, gt = __ballot_sync(FULL, lane < nt && t1 < tl);
+  const int lb = nlt ? __ffs(nlt) - 1 : nt, ub = gt ? __ffs(gt) - 1 : nt;
+  const int first = nb_sat(lb - 1, 0, np - 1), last = nb_sat(ub - 1, 0, np - 1);
+  idx[0] = first, idx[1] = last;
+  if (last - first + 1 > NB_HPCS) return -1;
+  const int nc = 4 * (last - first + 1);
+  // control point `lane` (piece first + lane / 4, MINVO column lane % 4): neptune.cpp:379-448, same operation order
+  double px = 0, py = 0;
+  if (lane < nc)
+  {
+    const int i = first + (lane >> 2), k = lane & 3;
+    double t;
+    if (i != last)
+      t = NB_SUB(times[i + 1], times[i]);
+    else if (t1 > times[i + 1])
+      t = NB_SUB(times[i + 1], times[i]);
+    else
+      t = NB_SUB(t1, times[i]);
+    if (t > cs.T)
+      t = cs.T;
+    else if (t < 0)
+      t = 0;
+    const double sc[4] = { NB_MUL(NB_MUL(t, t), t), NB_MUL(t, t), t, 1.0 };
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+    {
+      px = NB_ADD(px, NB_MUL(NB_MUL(cx[4 * i + r], sc[r]), cs.Ainv01[r * 4 + k]));
+      py = NB_ADD(py, NB_MUL(NB_MUL(cy[4 * i + r], sc[r]), cs.Ainv01[r * 4 + k]));
+    }
+  }
+  {  // col(0) of the un-inflated hull: the lexicographic minimum of the control points
+    double mx = lane < nc ? px : __longlong_as_double(0x7ff0000000000000LL), my = lane < nc ? py : mx;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1)
+    {
+      const double ox = __shfl_xor_sync(FULL, mx, o), oy = __shfl_xor_sync(FULL, my, o);
+      if (ox < mx || (ox == mx && oy < my)) mx = ox, my = oy;
+    }
+    nih0[0] = __shfl_sync(FULL, mx, 0), nih0[1] = __shfl_sync(FULL, my, 0);
+  }
+  // inflated corners: corner p = 4 c + g is control point c moved by the g-th of (-,-) (-,+) (+,-) (+,+)
+  const int n4 = 4 * nc;
+  double qx[2], qy[2];
+#pragma unroll
+  for (int u = 0; u < 2; u++)
+  {
+    const int p = lane + 32 * u, c = p >> 2, g = p & 3;
+    const double cxp = __shfl_sync(FULL, px, c & 31), cyp = __shfl_sync(FULL, py, c & 31);
+    qx[u] = NB_ADD(cxp, NB_MUL((g & 2) ? 1.0 : -1.0, delta));
+    qy[u] = NB_ADD(cyp, NB_MUL((g & 1) ? 1.0 : -1.0, delta));
+    if (p < n4) pts[2 * p] = qx[u], pts[2 * p + 1] = qy[u];
+  }
+  __syncwarp();
+  int rk[2] = { 0, 0 };
+#pragma unroll 4
+  for (int q = 0; q < n4; q++)
+  {
+    const double x = pts[2 * q], y = pts[2 * q + 1];
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+    {
+      const int p = lane + 32 * u;
+      const bool before = x < qx[u] || (x == qx[u] && (y < qy[u] || (y == qy[u] && q < p)));
+      rk[u] += before ? 1 : 0;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 2; u++)
+    if (lane + 32 * u < n4) srt[2 * rk[u]] = qx[u], srt[2 * rk[u] + 1] = qy[u];
+  __syncwarp();
+  // drop exact duplicates (they are adjacent)
+  int m;
+  {
+    double sx[2], sy[2];
+    bool keep[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+    {
+      const int p = lane + 32 * u;
+      sx[u] = p < n4 ? srt[2 * p] : 0.0, sy[u] = p < n4 ? srt[2 * p + 1] : 0.0;
+      keep[u] = p < n4 && (p == 0 || sx[u] != srt[2 * p - 2] || sy[u] != srt[2 * p - 1]);
+    }
+    const unsigned k0 = __ballot_sync(FULL, keep[0]), k1 = __ballot_sync(FULL, keep[1]);
+    const unsigned below = (1u << lane) - 1u;
+    const int pos0 = __popc(k0 & below), pos1 = __popc(k0) + __popc(k1 & below);
+    m = __popc(k0) + __popc(k1);
+    __syncwarp();
+    if (keep[0]) srt[2 * pos0] = sx[0], srt[2 * pos0 + 1] = sy[0];
+    if (keep[1]) srt[2 * pos1] = sx[1], srt[2 * pos1 + 1] = sy[1];
+    __syncwarp();
+  }
+  if (m <= 2)
+  {
+    if (lane < m) hull[2 * lane] = srt[2 * lane], hull[2 * lane + 1] = srt[2 * lane + 1];
+    return m;
+  }
+  int k = 0;
+  if (lane < 2)
+  {  // lane 0: lower chain over srt[0 .. m-1]; lane 1: upper chain over srt[m-1 .. 0]
+    double* h = chn + lane * 2 * 66;
+    for (int s = 0; s < m; s++)
+    {
+      const double* pt = srt + 2 * (lane ? m - 1 - s : s);
+      const double x = pt[0], y = pt[1];
+      while (k >= 2)
+      {
+        const double* o = h + 2 * (k - 2);
+        const double* a = h + 2 * (k - 1);
+        const double cr = NB_SUB(NB_MUL(NB_SUB(a[0], o[0]), NB_SUB(y, o[1])), NB_MUL(NB_SUB(a[1], o[1]), NB_SUB(x, o[0])));
+        if (!(cr <= 0)) break;
+        k--;
+      }
+      h[2 * k] = x, h[2 * k + 1] = y;
+      k++;
+    }
+  }
+  __syncwarp();
+  const int kl = __shfl_sync(FULL, k, 0), ku = __shfl_sync(FULL, k, 1);
+  const int cnt = kl + ku - 2;   // lower chain, then the upper one without its two end points
+  for (int v = lane; v < cnt && v < NB_HMAX; v += 32)
+  {
+    const double* src = v < kl ? chn + 2 * v : chn + 2 * 66 + 2 * (v - kl + 1);
+    hull[2 * v] = src[0], hull[2 * v + 1] = src[1];
+  }
+  return cnt;
+}
+#endif
+
 // One interval of Neptune::SamplePointsOfIntervals (neptune.cpp:500-566): the S+1 samples of interval i when
 // [t_start, t_end] is cut into num_pol intervals; out [S+1][2], idx [S+1] (optional)
-NB_HD void nb_sample_interval(const double* rec, double t_start, double t_end, int num_pol, int S, int i, double* out,
-                              int* idx_out = nullptr)
+// sample j of interval i; returns the piece it was taken from
+NB_HD int nb_sample_one(const double* rec, double t_start, double t_end, int num_pol, int S, int i, int j, double* out)
 {
   const int np = nb_rec_np(rec), nt = np + 1;
   const double* times = nb_rec_times(rec);
   const double* cx = nb_rec_coeff(rec, 0);
   const double* cy = nb_rec_coeff(rec, 1);
   const double deltaT = NB_SUB(t_end, t_start) / (1.0 * num_pol);
+  const double ts = NB_ADD(NB_ADD(t_start, NB_MUL(deltaT, (double)i)), NB_MUL(deltaT / S, (double)j));
+  const int low = nb_upper_bound(times, nt, ts);
+  int ii;
+  double te;
+  if (low != nt)
+  {
+    ii = nb_sat(low - 1, 0, np - 1);
+    te = NB_SUB(ts, times[ii]);
+    if (te < 0)
+      te = 0;
+    else if (te > deltaT)
+      te = deltaT;
+  }
+  else
+  {
+    const int k = low - 1;
+    te = NB_SUB(times[k], times[k - 1]);
+    ii = k - 1;
+  }
+  const double tv[4] = { NB_MUL(NB_MUL(te, te), te), NB_MUL(te, te), te, 1.0 };
+  double x = 0, y = 0;
+  for (int r = 0; r < 4; r++)
+  {
+    x = NB_ADD(x, NB_MUL(cx[4 * ii + r], tv[r]));
+    y = NB_ADD(y, NB_MUL(cy[4 * ii + r], tv[r]));
+  }
+  out[0] = x;
+  out[1] = y;
+  return ii;
+}
+
+NB_HD void nb_sample_interval(const double* rec, double t_start, double t_end, int num_pol, int S, int i, double* out,
+                              int* idx_out = nullptr)
+{
   for (int j = 0; j <= S; j++)
   {
-    const double ts = NB_ADD(NB_ADD(t_start, NB_MUL(deltaT, (double)i)), NB_MUL(deltaT / S, (double)j));
-    const int low = nb_upper_bound(times, nt, ts);
-    int ii;
-    double te;
-    if (low != nt)
-    {
-      ii = nb_sat(low - 1, 0, np - 1);
-      te = NB_SUB(ts, times[ii]);
-      if (te < 0)
-        te = 0;
-      else if (te > deltaT)
-        te = deltaT;
-    }
-    else
-    {
-      const int k = low - 1;
-      te = NB_SUB(times[k], times[k - 1]);
-      ii = k - 1;
-    }
-    const double tv[4] = { NB_MUL(NB_MUL(te, te), te), NB_MUL(te, te), te, 1.0 };
-    double x = 0, y = 0;
-    for (int r = 0; r < 4; r++)
-    {
-      x = NB_ADD(x, NB_MUL(cx[4 * ii + r], tv[r]));
-      y = NB_ADD(y, NB_MUL(cy[4 * ii + r], tv[r]));
-    }
-    out[2 * j] = x;
-    out[2 * j + 1] = y;
+    const int ii = nb_sample_one(rec, t_start, t_end, num_pol, S, i, j, out + 2 * j);
     if (idx_out) idx_out[j] = ii;
   }
 }
