@@ -464,7 +464,9 @@ typedef struct nb_cycle_desc
 {
   int32_t B;                 /* agents planned by this rank */
   const int32_t* agent_id;   /* [B] 1-based ids (ctor argument id of each agent's solver) */
-  int32_t front_end;         /* 1: KinodynamicSearch::run inside the cycle (nb_search_configure must have been called) */
+  int32_t front_end;         /* 1: KinodynamicSearch::run inside the cycle (nb_search_configure must have been called);
+                                2: Neptune::replanKinodynamic (neptune.cpp:1010-1300) -- the search, then post-check and
+                                commit of the FRONT-END path itself, no LPs / QP (status 0, coeff_out = the search's path) */
   int32_t rank, world;       /* position of this rank in the exchange (world == 1: no peers) */
   const uint8_t* planned;    /* [num_agents] 1 = some rank plans this agent (its ring slot is written by a commit every
                                 cycle); 0 = nobody does (its record is carried forward).  NULL: all planned by this rank

@@ -176,7 +176,7 @@ struct nb_cycle
   double *fe_coeff = nullptr, *fe_ebeta = nullptr, *fe_cost = nullptr;
   // streams, events, graphs
   cudaStream_t sB = nullptr, sC = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_hulls = nullptr, ev_B = nullptr, ev_C = nullptr, ev_qp = nullptr, ev_C2 = nullptr, ev_pre = nullptr, ev_prof[10] = { nullptr };
+  cudaEvent_t ev_fork = nullptr, ev_hulls = nullptr, ev_B = nullptr, ev_C = nullptr, ev_qp = nullptr, ev_C2 = nullptr, ev_pre = nullptr, ev_unpack = nullptr, ev_prof[10] = { nullptr };
   cudaGraphExec_t graph[3] = { nullptr, nullptr, nullptr };
   int graph_G = -1;
   long long launches_per_step = 0;
@@ -264,10 +264,13 @@ int step_body(nb_cycle* c, cudaStream_t st, bool prof)
   CY_RC(nb_internal_hull_aabb(h, (size_t)G * N * NB_NPOL, c->hull_xy_l, c->hull_cnt_l, c->aabb_l, sC));
   if (!prof) CY_CUDA(cudaEventRecord(c->ev_C, sC));
   mark();
-  // (main) the trajectories the agents plan against: trajCB bookkeeping, hulls and samples (neptune.cpp:1433-1434)
-  CY_RC(nb_unpack_records_batch(h, NB_DEVICE, r_known, c->bp_cnt, c->bp_xy, c->latest_pos, st));
-  k_carry<<<N, 64, 0, st>>>(N, c->d_planned, r_late, r_new);
+  // (stream B) trajCB bookkeeping of the trajectories the agents plan against (bend points, latest positions) and the
+  // records of the agents this rank does not plan for, beside the hulls; (main) hulls and samples (neptune.cpp:1433-1434)
+  if (!prof) CY_CUDA(cudaStreamWaitEvent(sB, c->ev_fork, 0));
+  CY_RC(nb_unpack_records_batch(h, NB_DEVICE, r_known, c->bp_cnt, c->bp_xy, c->latest_pos, sB));
+  k_carry<<<N, 64, 0, sB>>>(N, c->d_planned, r_late, r_new);
   h->launches += 1;
+  if (!prof) CY_CUDA(cudaEventRecord(c->ev_unpack, sB));
   CY_RC(nb_hulls_batch(h, G, NB_DEVICE, t_group, r_known, c->d_ones, c->d.delta, c->hull_xy, c->hull_cnt, c->hull_ptr, c->nih0,
                        c->samp, nullptr, st));
   mark();
@@ -276,6 +279,7 @@ int step_body(nb_cycle* c, cudaStream_t st, bool prof)
   {
     CY_CUDA(cudaEventRecord(c->ev_hulls, st));
     CY_CUDA(cudaStreamWaitEvent(sB, c->ev_hulls, 0));
+    CY_CUDA(cudaStreamWaitEvent(st, c->ev_unpack, 0));   // the back end reads the bend points
   }
   CY_CUDA(cudaMemcpyAsync(c->esA, c->d_in + L.es_cnt, c->es_bytes, cudaMemcpyDeviceToDevice, sB));
   nb_ent_state esA = es_view(c->esA, c->es_off);
@@ -335,7 +339,16 @@ int step_body(nb_cycle* c, cudaStream_t st, bool prof)
   a.esv_cnt = esv_cnt, a.esv_alpha = esv_alpha, a.esv_active = esv_active, a.bp_cnt = c->bp_cnt, a.bp_xy = c->bp_xy;
   a.coeff_out = out_at<double>(c, L.coeff_out), a.obj = out_at<double>(c, L.obj), a.status = out_at<int32_t>(c, L.status);
   a.iters = out_at<int32_t>(c, L.iters);
-  CY_RC(nb_replan_batch(h, &a, st));
+  if (c->d.front_end == 2)
+  {  // Neptune::replanKinodynamic (neptune.cpp:1010-1300): no back end -- the front-end path itself (generatePwpOut of the
+     // search, :1189) goes to safetyCheckAfterReplan (:1198) and is committed (:1244-1255); status 0 = "optimised" path
+    CY_CUDA(cudaMemcpyAsync(a.coeff_out, coeff_init, (size_t)B * 96 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    CY_CUDA(cudaMemsetAsync(a.status, 0, (size_t)B * sizeof(int32_t), st));
+    CY_CUDA(cudaMemsetAsync(a.obj, 0, (size_t)B * sizeof(double), st));
+    CY_CUDA(cudaMemsetAsync(a.iters, 0, (size_t)B * 2 * sizeof(int32_t), st));
+  }
+  else
+    CY_RC(nb_replan_batch(h, &a, st));
   mark();
   // safetyCheckAfterReplan (:719-752): GJK against the late hulls, then the gated entanglement re-check
   // the two halves are independent: the GJK half runs on stream C beside the entanglement half on the main stream
@@ -476,7 +489,7 @@ extern "C" int nb_cycle_create(nb_handle* h, const nb_cycle_desc* d, nb_cycle** 
     }
     CY_CUDA(cudaStreamCreateWithFlags(&c->sB, cudaStreamNonBlocking));
     CY_CUDA(cudaStreamCreateWithFlags(&c->sC, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : { &c->ev_fork, &c->ev_hulls, &c->ev_B, &c->ev_C, &c->ev_qp, &c->ev_C2, &c->ev_pre }) CY_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    for (cudaEvent_t* e : { &c->ev_fork, &c->ev_hulls, &c->ev_B, &c->ev_C, &c->ev_qp, &c->ev_C2, &c->ev_pre, &c->ev_unpack }) CY_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (auto& e : c->ev_prof) CY_CUDA(cudaEventCreate(&e));
     return NB_OK;
   }();
@@ -504,7 +517,7 @@ extern "C" void nb_cycle_destroy(nb_cycle* c)
   if (c->h_out) cudaFreeHost(c->h_out);
   if (c->sB) cudaStreamDestroy(c->sB);
   if (c->sC) cudaStreamDestroy(c->sC);
-  for (cudaEvent_t e : { c->ev_fork, c->ev_hulls, c->ev_B, c->ev_C, c->ev_qp, c->ev_C2, c->ev_pre })
+  for (cudaEvent_t e : { c->ev_fork, c->ev_hulls, c->ev_B, c->ev_C, c->ev_qp, c->ev_C2, c->ev_pre, c->ev_unpack })
     if (e) cudaEventDestroy(e);
   for (auto e : c->ev_prof)
     if (e) cudaEventDestroy(e);

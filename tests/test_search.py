@@ -374,6 +374,69 @@ def test_gpu_cycle_with_front_end(capi, oracle, cfg, seed, sync):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("cfg,seed,sync", [("obst8", 3003, False), ("mtlp5", 2002, True)])
+def test_gpu_cycle_kinodynamic_only(capi, oracle, cfg, seed, sync):
+    """ReplanCycle(front_end=2) = Neptune::replanKinodynamic (neptune.cpp:1010-1300): the search's own path
+    (generatePwpOut :1189) is what safetyCheckAfterReplan sees (:1198) and what is composed with the previous plan
+    and published (:1244-1255); no LP, no QP.  The search equals the front_end=1 cycle's (same kernels, tested
+    against the oracle above); here: coeff_out is the search's path bit for bit, status 0, and the committed record
+    is the oracle's composePieceWisePol of the previous record with that path."""
+    import torch
+    from neptune_b200.cycle import ReplanCycle
+    from neptune_b200.scenes import search_host_inputs
+    from neptune_b200.search import static_longest_dist
+
+    par = config(cfg)
+    par.search_max_expansions = 200
+    M = par.num_of_static_obst
+    sc = make_scene(par, seed, sync=sync, ent_backend=OracleEntBackend(oracle))
+    strep = np.asarray(sc.strep, np.float64).reshape(M, 2, 2)
+    longest = static_longest_dist(sc.static_raw, strep) if M else np.zeros((0, 2))
+    dev = torch.device("cuda", 0)
+    outs = {}
+    for mode in (1, 2):
+        cyc = ReplanCycle(par, np.arange(par.num_of_agents), dev, static=(sc.batch.st_ptr, sc.batch.st_xy, sc.strep, longest),
+                          front_end=mode)
+        fe = search_host_inputs(sc, seed + 5)
+        recs_in = cyc.records_of(sc)
+        cyc.seed_records(recs_in)
+        hin, hout = cyc.host_inputs(sc, fe), cyc.host_outputs()
+        cyc.step_from_host(hin, hout)
+        cyc.check_errors()
+        B = cyc.B
+        outs[mode] = dict(fe_coeff=cyc.fetch("fe_coeff", (B, 3, 8, 4), np.float64), fe_n_int=cyc.fetch("fe_n_int", (B,), np.int32),
+                          solved=hout["fe_solved"].copy(), status=hout["status"].copy(), coeff_out=hout["coeff_out"].copy(),
+                          entangled=hout["entangled"].copy(), collide=hout["collide"].copy(), n_pieces=hout["n_pieces"].copy(),
+                          rec=cyc.records("new").copy(), t_now=hin["t_now"].copy())
+        cyc.close()
+    full, kin = outs[1], outs[2]
+    ok = kin["solved"] > 0
+    assert ok.any()
+    assert np.array_equal(kin["solved"], full["solved"]) and np.array_equal(kin["fe_n_int"][ok], full["fe_n_int"][ok])
+    assert np.array_equal(kin["fe_coeff"][ok], full["fe_coeff"][ok])          # the same search
+    assert (kin["status"] == 0).all()
+    assert np.array_equal(kin["coeff_out"][ok], kin["fe_coeff"][ok])           # no back end: the path is the search's
+    PW = capi.NB_REC_PWP_DOUBLES
+    committed = 0
+    for bi in range(len(ok)):
+        me = int(sc.batch.agent_id[bi]) - 1
+        prev = recs_in[me]
+        if not ok[bi] or kin["entangled"][bi] or kin["collide"][bi]:
+            assert np.array_equal(kin["rec"][me], prev)                          # rejected: the previous record stays
+            continue
+        n = int(kin["fe_n_int"][bi])
+        now = np.zeros(capi.NB_REC_DOUBLES)
+        now[0] = n
+        now[1:2 + n] = sc.t_start[bi] + par.T_span * np.arange(n + 1)
+        now[18:PW].reshape(3, 16, 4)[:, :n] = kin["coeff_out"][bi, :, :n]
+        npc, want, _, _ = oracle.compose_records(kin["t_now"][bi], par.dc, prev, now)
+        assert npc == kin["n_pieces"][bi]
+        assert np.array_equal(kin["rec"][me, :PW], want[:PW])
+        committed += 1
+    assert committed > 0
+
+
+@pytest.mark.gpu
 def test_cpp_shim_kinodynamic_search(capi, oracle, tmp_path):
     """The C++ drop-in class KinodynamicSearch (neptune_b200/cpp/kinodynamic_search_b200.hpp) driven like
     neptune.cpp drives the reference's (:88-97, :1421-1453, :1509-1510): same status, pieces and entStateVec as
