@@ -237,7 +237,8 @@ def measure_cycle(args, par, agents, rank, world, dev, workload, steps, warmup, 
     for k in range(steps):
         cyc.upload(hins[k % len(hins)])       # untimed: this leg measures with inputs already in HBM
         flush_l2()
-        ev[k][0].record(st)
+        cyc.align()                           # N > 1: all ranks enter the timed cycle together (device-side barrier), so
+        ev[k][0].record(st)                   # one rank's untimed upload is not another rank's exchange wait
         cyc.step()
         ev[k][1].record(st)
     barrier()
@@ -431,7 +432,8 @@ def config_dict(par, n_gpus, workload="grid64"):
             if workload != "grid64" else AGENTS_PER_GPU, "static_obstacles": par.num_of_static_obst,
             "num_pol": par.num_pol, "T_span": par.T_span, "seed": SEED if workload == "grid64" else 5005,
             "l2": "flushed between timed iterations (256 MiB write)",
-            "parallelism": f"agents sharded over {n_gpus} rank(s); committed trajectories exchanged by peer-to-peer stores from the commit kernel (no collective call)"}
+            "parallelism": f"agents sharded over {n_gpus} rank(s); committed trajectories exchanged by peer-to-peer stores from the commit kernel (no collective call)"
+                           + ("; every timed cycle starts at a device-side rank barrier (nb_cycle_align), so the untimed input upload of one rank is not counted as another rank's exchange wait" if n_gpus > 1 else "")}
 
 
 def run_small(args):

@@ -518,6 +518,11 @@ int nb_cycle_fetch(nb_cycle* c, const char* name, void* dst, int64_t bytes, void
 /* exchange set-up for world > 1: every rank exports one IPC handle (64 bytes) of its ring; after an all-gather of the
  * handles (the caller's job: torch.distributed, MPI ...) every rank opens its peers' rings */
 int nb_cycle_ipc_handle(nb_cycle* c, void* handle64);
+/* Measurement helper (no reference counterpart): a rank barrier ON THE DEVICE, enqueued on `stream` -- every rank's stream
+ * continues only when all ranks have reached this point (flags in the same peer memory as the commit).  bench.py places
+ * one before each timed cycle so that the untimed input upload of one rank is not counted as exchange wait by another.
+ * Every rank must call it the same number of times.  No-op when world == 1. */
+int nb_cycle_align(nb_cycle* c, void* stream);
 int nb_cycle_open_peers(nb_cycle* c, const void* handles /* [world][64] */);
 
 /* Measurement hook (no reference counterpart): with nb_set_profiling on, SM cycles lane 0 of every QP warp spent per

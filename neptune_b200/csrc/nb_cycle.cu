@@ -7,6 +7,7 @@
 // NVLink and signals them -- the per-cycle all-gather fused into the kernel that produces its payload.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -135,6 +136,30 @@ __global__ void k_fe_merge(int B, int cap, int NA, const int* solved, const int*
   for (int q = threadIdx.x; q < 9 * NA; q += blockDim.x) eact[(size_t)b * 9 * NA + q] = eact_h[(size_t)b * 9 * NA + q];
 }
 
+// Rank barrier on the device (nb_cycle_align): every rank raises its flag for `epoch` on every peer, then waits until all
+// peers have raised theirs here.  Same transport as the commit (plain peer stores + system-scope fences).
+__global__ void k_align(NbPeers peers, long long epoch, int* err)
+{
+  const int r = threadIdx.x;
+  if (r < peers.world)
+  {
+    volatile long long* mine = peers.flags[r] + NB_MAX_WORLD + peers.rank;
+    *mine = epoch;
+    __threadfence_system();
+    volatile long long* f = peers.flags[peers.rank] + NB_MAX_WORLD + r;
+    const long long t0 = clock64();
+    while (*f < epoch)
+    {
+      __nanosleep(200);
+      if (clock64() - t0 > 20000000000LL)
+      {
+        *err = 7;
+        break;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ the object
 struct Field
 {
@@ -159,6 +184,8 @@ struct nb_cycle
   NbPeers peers;
   void* peer_base[NB_MAX_WORLD] = { nullptr };
   long long* d_cycle = nullptr;  // device copy of k
+  long long align_epoch = 0;
+  bool split_postcheck = true;   // first half of the entanglement post-check beside the QP (NB_CYCLE_NO_SPLIT=1: one kernel after it)
   unsigned int* d_done = nullptr;
   long long k = 0;
   // intermediates
@@ -325,10 +352,11 @@ int step_body(nb_cycle* c, cudaStream_t st, bool prof)
     CY_CUDA(cudaStreamWaitEvent(sB, c->ev_pre, 0));
     CY_CUDA(cudaStreamWaitEvent(sB, c->ev_C, 0));   // bend points of the late messages (stream C)
   }
-  CY_RC(nb_internal_postcheck_entangle(h, 1, B, NB_DEVICE, agent_id, known, late, c->bp_cnt, c->bp_xy, c->bp_cnt_l, c->bp_xy_l, es0,
-                                       in_at<double>(c, L.prev_pos), in_at<double>(c, L.prev_pos_agent), in_at<double>(c, L.cur),
-                                       n_int, coeff_out, in_at<double>(c, L.t_start), c->samp, 0, group, r_late,
-                                       out_at<int32_t>(c, L.entangled), sB));
+  if (c->split_postcheck)
+    CY_RC(nb_internal_postcheck_entangle(h, 1, B, NB_DEVICE, agent_id, known, late, c->bp_cnt, c->bp_xy, c->bp_cnt_l, c->bp_xy_l, es0,
+                                         in_at<double>(c, L.prev_pos), in_at<double>(c, L.prev_pos_agent), in_at<double>(c, L.cur),
+                                         n_int, coeff_out, in_at<double>(c, L.t_start), c->samp, 0, group, r_late,
+                                         out_at<int32_t>(c, L.entangled), sB));
   if (!prof) CY_CUDA(cudaEventRecord(c->ev_B, sB));
   // back end: separating lines + trajectory QP (:1514-1519); shared-window mode of nb_replan_batch
   nb_replan_args a;
@@ -361,7 +389,7 @@ int step_body(nb_cycle* c, cudaStream_t st, bool prof)
   CY_RC(nb_internal_postcheck_hulls(h, B, n_int, a.coeff_out, group, c->hull_xy_l, c->hull_cnt_l, c->aabb_l, late,
                                     out_at<int32_t>(c, L.collide), sC));
   if (!prof) CY_CUDA(cudaEventRecord(c->ev_C2, sC));
-  CY_RC(nb_internal_postcheck_entangle(h, 2, B, NB_DEVICE, agent_id, known, late, c->bp_cnt, c->bp_xy, c->bp_cnt_l, c->bp_xy_l, es0,
+  CY_RC(nb_internal_postcheck_entangle(h, c->split_postcheck ? 2 : 0, B, NB_DEVICE, agent_id, known, late, c->bp_cnt, c->bp_xy, c->bp_cnt_l, c->bp_xy_l, es0,
                                        in_at<double>(c, L.prev_pos), in_at<double>(c, L.prev_pos_agent), in_at<double>(c, L.cur),
                                        n_int, a.coeff_out, in_at<double>(c, L.t_start), c->samp, 0, group, r_late,
                                        out_at<int32_t>(c, L.entangled), st));
@@ -401,6 +429,9 @@ extern "C" int nb_cycle_create(nb_handle* h, const nb_cycle_desc* d, nb_cycle** 
   CY_CUDA(cudaSetDevice(h->device));
   nb_cycle* c = new nb_cycle();
   c->h = h, c->d = *d;
+  // measured on the 64-agents-per-GPU worlds (tools/cycle_rank0_of.py): beside the QP the first half saves 35-50 us per cycle
+  // with up to 256 tethers per agent, but with 512 it is heavy enough to slow k_lines / k_qp down by more than it hides
+  c->split_postcheck = getenv("NB_CYCLE_NO_SPLIT") == nullptr && h->par.num_agents + h->par.num_static < 512;
   c->agent_id.assign(d->agent_id, d->agent_id + d->B);
   c->d.agent_id = c->agent_id.data();
   const int B = d->B, N = h->par.num_agents, M = h->par.num_static, NA = N + M, cap = h->par.ent_cap, S = h->par.samples;
@@ -452,7 +483,7 @@ extern "C" int nb_cycle_create(nb_handle* h, const nb_cycle_desc* d, nb_cycle** 
     CY_RC(dalloc(c, &c->d_in, (size_t)L.in_bytes));
     CY_RC(dalloc(c, &c->d_out, (size_t)L.out_bytes));
     // ring + flags in one allocation (IPC export)
-    const size_t ring_bytes = (size_t)3 * N * NB_REC * 8, flag_bytes = (size_t)NB_MAX_WORLD * 8;
+    const size_t ring_bytes = (size_t)3 * N * NB_REC * 8, flag_bytes = (size_t)2 * NB_MAX_WORLD * 8;   // arrival flags, then the flags of nb_cycle_align
     CY_CUDA(cudaMalloc((void**)&c->ring_alloc, ring_bytes + flag_bytes));
     CY_CUDA(cudaMemset(c->ring_alloc, 0, ring_bytes + flag_bytes));
     c->ring = (double*)c->ring_alloc, c->flags = (long long*)(c->ring_alloc + ring_bytes);
@@ -739,6 +770,17 @@ extern "C" int nb_cycle_fetch(nb_cycle* c, const char* name, void* dst, int64_t 
   }
   CY_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CY_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return NB_OK;
+}
+
+extern "C" int nb_cycle_align(nb_cycle* c, void* stream)
+{
+  if (!c) return NB_ERR_ARG;
+  if (c->d.world <= 1) return NB_OK;
+  CY_CUDA(cudaSetDevice(c->h->device));
+  c->align_epoch += 1;   // every rank calls this the same number of times
+  k_align<<<1, 32, 0, (cudaStream_t)stream>>>(c->peers, c->align_epoch, (int*)c->h->err.p);
+  CY_CUDA(cudaGetLastError());
   return NB_OK;
 }
 

@@ -187,6 +187,7 @@ class ReplanCycle:
         L.nb_cycle_upload_from.argtypes = [_P, _P, C.c_int32, _P]
         L.nb_cycle_download_to.argtypes = [_P, _P, _P]
         L.nb_cycle_step.argtypes = [_P, _P]
+        L.nb_cycle_align.argtypes = [_P, _P]
         L.nb_cycle_capture.argtypes = [_P, _P]
         L.nb_cycle_step_profiled.argtypes = [_P, _P, _P]
         L.nb_cycle_launches_per_step.argtypes = [_P]
@@ -255,6 +256,10 @@ class ReplanCycle:
         capi._check(self._lib.nb_cycle_capture(self._h, self._st()), "nb_cycle_capture")
         self.captured = True
         self.launches_per_cycle = int(self._lib.nb_cycle_launches_per_step(self._h))
+
+    def align(self):
+        """Rank barrier on the device, enqueued on the cycle's stream (measurement helper, nb_cycle_align)."""
+        capi._check(self._lib.nb_cycle_align(self._h, self._st()), "nb_cycle_align")
 
     def step(self):
         """One cycle on the cycle's stream (graph replay when captured), exchange included."""
