@@ -68,10 +68,15 @@ __global__ void __launch_bounds__(64) k_publish(int B, int N, const int* agent_i
     double* dst = peers.ring[r] + slot;
     for (int q = threadIdx.x; q < NB_REC; q += blockDim.x) dst[q] = rec[q];
   }
-  __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0)
   {
+    // one fence per CTA: it is cumulative over the stores of the other threads, which the barrier has ordered before it;
+    // system scope only when there are peers to publish to
+    if (peers.world > 1)
+      __threadfence_system();
+    else
+      __threadfence();
     const unsigned int prevc = atomicAdd(done, 1u);
     if (prevc == (unsigned int)B - 1)
     {  // every record of this rank is out: tell the peers

@@ -589,6 +589,74 @@ NB_HD int nb_pwp_collides(const NbConsts& cs, const double* coeff /*[3][8][4]*/,
 // after t and before p2 begins, then p2 (Neptune::replanFull neptune.cpp:1689-1699).  p1 / p2 are local
 // copies whose first / last times are adjusted exactly as the reference adjusts its arguments (:320-336).
 // Returns the number of pieces, 0 for the reference's empty "dummy" (:342-354), -1 beyond NB_TP pieces.
+// nb_compose_records in two steps for a CTA: the (sequential, short) decision which pieces make up the result, by one
+// thread, and the copying, by all of them.  plan: kind (0 all zero, 1 copy of p2 with times[0] = tm[0], 2 composed), the
+// number of pieces, their knots tm[0 .. np] and for piece e its source (0: p1, 1: p2) and index there.  Returns what
+// nb_compose_records returns (-1: more than NB_TP pieces).
+struct NbComposePlan
+{
+  int kind, np;
+  double tm[NB_TP + 1];
+  unsigned char src[NB_TP], idx[NB_TP];
+};
+
+NB_HD int nb_compose_plan(double t, const double* p1_in, const double* p2_in, NbComposePlan* pl)
+{
+  const int n1 = (int)p1_in[0], n2 = (int)p2_in[0];
+  pl->kind = 0, pl->np = 0;
+  if (n1 < 1 || n2 < 1 || n1 > NB_TP || n2 > NB_TP) return 0;
+  double t10 = p1_in[1], t1n = p1_in[1 + n1], t20 = p2_in[1];
+  if (t > t1n && t < t20) t20 = t;
+  if (t1n < t20) t20 = t1n;
+  if (t < t10) t10 = t;
+  if (fabs(t - t20) < 1e-5)
+  {
+    pl->kind = 1, pl->np = n2, pl->tm[0] = t20;
+    return n2;
+  }
+  if (t1n < t20 || t > p2_in[1 + n2] || t < t10) return 0;
+  int np = 0;
+  pl->tm[0] = t;
+  for (int i = 1; i <= n1; i++)  // i = 0 never qualifies: t1[0] <= t
+  {
+    const double ti = p1_in[1 + i];
+    if (ti > t && ti < t20)
+    {
+      if (np >= NB_TP) return -1;
+      pl->src[np] = 0, pl->idx[np] = (unsigned char)(i - 1);
+      np++;
+      pl->tm[np] = ti;
+    }
+  }
+  for (int i = 0; i <= n2; i++)
+  {
+    const double ti = i == 0 ? t20 : p2_in[1 + i];
+    if (ti > t)
+    {
+      if (np >= NB_TP) return -1;
+      pl->src[np] = i == 0 ? 0 : 1, pl->idx[np] = (unsigned char)(i == 0 ? n1 - 1 : i - 1);
+      np++;
+      pl->tm[np] = ti;
+    }
+  }
+  pl->kind = 2, pl->np = np;
+  return np;
+}
+
+// element q of the composed record
+NB_HD double nb_compose_fill(const NbComposePlan* pl, const double* p1_in, const double* p2_in, int q)
+{
+  if (pl->kind == 0) return 0.0;
+  if (pl->kind == 1) return q == 1 ? pl->tm[0] : p2_in[q];
+  if (q >= NB_REC_PWP) return p2_in[q];  // the message header is the new publication's
+  if (q == 0) return (double)pl->np;
+  if (q <= NB_TP + 1) return q - 1 <= pl->np ? pl->tm[q - 1] : 0.0;
+  const int e = q - (NB_TP + 2), ax = e / (NB_TP * 4), rem = e - ax * NB_TP * 4, piece = rem >> 2, c = rem & 3;
+  if (piece >= pl->np) return 0.0;
+  const double* src = pl->src[piece] ? p2_in : p1_in;
+  return src[1 + (NB_TP + 1) + ax * NB_TP * 4 + 4 * pl->idx[piece] + c];
+}
+
 NB_HD int nb_compose_records(double t, const double* p1_in, const double* p2_in, double* out)
 {
   const int n1 = (int)p1_in[0], n2 = (int)p2_in[0];

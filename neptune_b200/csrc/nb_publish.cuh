@@ -113,6 +113,28 @@ static __device__ __forceinline__ void nb_commit_one(int b, const int* n_int, co
     if (hd.on && src == now && threadIdx.x == 0) nb_fill_header(r, agent, b, hd, err);
     return;
   }
+  if (prev_stage)
+  {  // CTA-wide composition: one thread decides which pieces make up the result, all of them copy
+    __shared__ NbComposePlan plan;
+    __shared__ int np_s;
+    if (threadIdx.x == 0)
+    {
+      int np = nb_compose_plan(t_now[b], pv, now, &plan);
+      if (np < 0)
+      {
+        *err = 4;
+        np = 0;
+        plan.kind = 0;
+      }
+      np_s = np;
+      if (n_pieces) n_pieces[b] = np;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < NB_REC; q += blockDim.x) r[q] = nb_compose_fill(&plan, pv, now, q);
+    __syncthreads();
+    if (hd.on && threadIdx.x == 0) nb_fill_header(r, agent, b, hd, err);
+    return;
+  }
   if (threadIdx.x == 0)
   {
     int np = nb_compose_records(t_now[b], pv, now, r);
