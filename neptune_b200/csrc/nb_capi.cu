@@ -1034,15 +1034,32 @@ int ent_common(nb_handle* h, NbEntArgs* a, int mode, int B, int space, const int
   return NB_OK;
 }
 
-int ent_launch(nb_handle* h, const NbEntArgs& a, int B, cudaStream_t st)
+int ent_launch(nb_handle* h, const NbEntArgs& a_in, int B, cudaStream_t st)
 {
-  const size_t sm = (size_t)(4 * a.tcap + 4) * sizeof(int);
-  if (a.N + a.M >= 1024 && a.mode != 3 && B <= 2 * h->num_sms)   // few agents, many tethers: sixteen warps per agent
+  NbEntArgs a = a_in;
+  size_t sm = (size_t)(4 * a.tcap + 4) * sizeof(int);
+  a.stage = 0;
+  if (a.mode == 4)
+  {  // the post-check's work state in shared memory when it fits
+    const size_t extra = nb_ent_stage_bytes(a.N + a.M, a.cap);
+    if (sm + extra <= 200 * 1024) a.stage = 1, sm += extra;
+  }
+  // few agents, many tethers: sixteen warps per agent (512 tethers: measured on rank 0's share of the 8-GPU world)
+  if (a.N + a.M >= 512 && a.mode != 3 && B <= 2 * h->num_sms)
+  {
+    if (sm > 48 * 1024) NB_CUDA(cudaFuncSetAttribute(k_entangle<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_entangle<512><<<B, 512, sm, st>>>(a);
+  }
   else if (a.N + a.M >= 256 && a.mode != 3)
+  {
+    if (sm > 48 * 1024) NB_CUDA(cudaFuncSetAttribute(k_entangle<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_entangle<128><<<B, 128, sm, st>>>(a);
+  }
   else
+  {
+    if (sm > 48 * 1024) NB_CUDA(cudaFuncSetAttribute(k_entangle<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     k_entangle<32><<<B, 32, sm, st>>>(a);
+  }
   h->launches += 1;
   NB_CUDA(cudaGetLastError());
   return NB_OK;

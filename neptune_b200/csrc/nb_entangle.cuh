@@ -822,6 +822,9 @@ NB_HD int nb_ent_interval_pass(const Group<NL>& g, NbEntState& es, const NbEntCt
 }
 
 // ---- K3 task: one agent per warp-group.  mode 0 predict, 1 rollout, 2 check-given-pwp
+// shared memory of the staged work state (nb_entangle_task, mode 4), after the crossing lists
+inline size_t nb_ent_stage_bytes(int NA, int cap) { return (size_t)cap * 20 + (size_t)NA * 4 + 16; }
+
 struct NbEntArgs
 {
   int mode, N, M, cap, bp_max, num_pol, S, tcap;
@@ -850,6 +853,7 @@ struct NbEntArgs
   const double* bp_xy_late;      // [N][bp_max][2]
   double* psamp;                 // scratch [B][N][S+1][2]: interval-0 samples per planning agent
   unsigned char* pknown;         // scratch [B][N]
+  int stage;                     // mode 4: the work state lives in shared memory (host: it fits, nb_ent_stage_bytes)
   int phase;                     // mode 4: 0 whole post-check, 1 up to PredictAlphasBetas (independent of the optimised
                                  // trajectory: runs beside the QP), 2 entangleCheckGivenPwp on the state phase 1 left
   const double* prev_pos;        // predict
@@ -895,7 +899,32 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
     es.alpha = a.out.alpha + o * a.cap * 2, es.beta = a.out.beta + o * a.cap, es.bend = a.out.bend + o * a.cap;
     es.active = a.out.active + o * NA;
   }
-  if ((a.mode == 1 || a.mode == 4) && !resume)
+  bool staged = false;
+#if defined(__CUDA_ARCH__)
+  if (a.mode == 4 && a.stage)
+  {  // The work state in SHARED memory: the list automaton (one lane) walks alpha / beta / bend / active entry by entry, a
+     // chain of dependent loads that costs ~300 cycles per step from L2 and 29 from shared memory.  Only the used
+     // entries are copied.  Layout after the crossing lists: beta [cap] f64 | alpha [cap][2] | bend [cap] | active [NA].
+    double* s_beta = reinterpret_cast<double*>(flag + 4);
+    int* s_alpha = reinterpret_cast<int*>(s_beta + a.cap);
+    int* s_bend = s_alpha + 2 * a.cap;
+    int* s_active = s_bend + a.cap;
+    const int* g_alpha = resume ? es.alpha : a.st.alpha + (size_t)b * a.cap * 2;
+    const double* g_beta = resume ? es.beta : a.st.beta + (size_t)b * a.cap;
+    const int* g_bend = resume ? es.bend : a.st.bend + (size_t)b * a.cap;
+    const int* g_active = resume ? es.active : a.st.active + (size_t)b * NA;
+    const int na = resume ? a.out.cnt[2 * b] : a.st.cnt[2 * b], nbd = resume ? a.out.cnt[2 * b + 1] : a.st.cnt[2 * b + 1];
+    for (int q = g.lane; q < na; q += NL) s_alpha[2 * q] = g_alpha[2 * q], s_alpha[2 * q + 1] = g_alpha[2 * q + 1], s_beta[q] = g_beta[q];
+    for (int q = g.lane; q < nbd; q += NL) s_bend[q] = g_bend[q];
+    for (int q = g.lane; q < NA; q += NL) s_active[q] = g_active[q];
+    es.alpha = s_alpha, es.beta = s_beta, es.bend = s_bend, es.active = s_active;
+    staged = true;
+  }
+#endif
+  if (staged)
+  {
+  }
+  else if ((a.mode == 1 || a.mode == 4) && !resume)
   {
     for (int q = g.lane; q < a.cap; q += NL)
     {
@@ -905,7 +934,7 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
     }
     for (int q = g.lane; q < NA; q += NL) es.active[q] = a.st.active[(size_t)b * NA + q];
   }
-  else
+  else if (!(a.mode == 4 && resume))
   {
     es.alpha = a.st.alpha + (size_t)b * a.cap * 2, es.beta = a.st.beta + (size_t)b * a.cap;
     es.bend = a.st.bend + (size_t)b * a.cap, es.active = a.st.active + (size_t)b * NA;
@@ -1027,6 +1056,19 @@ NB_HD void nb_entangle_task(const Group<NL>& g, int b, const NbEntArgs& a, int* 
       }
       if (a.phase == 1)
       {  // the state PredictAlphasBetas left: phase 2 resumes from it
+        if (staged)
+        {  // back to the scratch slot in global memory
+          int* o_alpha = a.out.alpha + (size_t)b * a.cap * 2;
+          double* o_beta = a.out.beta + (size_t)b * a.cap;
+          int* o_bend = a.out.bend + (size_t)b * a.cap;
+          int* o_active = a.out.active + (size_t)b * NA;
+          if (g.lane == 0) flag[1] = es.n_alpha, flag[2] = es.n_bend;   // only the automaton's lane knows the new lengths
+          g.sync();
+          const int na = flag[1], nbd = flag[2];
+          for (int q = g.lane; q < na; q += NL) o_alpha[2 * q] = es.alpha[2 * q], o_alpha[2 * q + 1] = es.alpha[2 * q + 1], o_beta[q] = es.beta[q];
+          for (int q = g.lane; q < nbd; q += NL) o_bend[q] = es.bend[q];
+          for (int q = g.lane; q < NA; q += NL) o_active[q] = es.active[q];
+        }
         if (g.lane == 0) a.out.cnt[2 * b] = es.n_alpha, a.out.cnt[2 * b + 1] = es.n_bend;
         if (bad && g.lane == 0) *a.err = 2;
         return;
