@@ -116,7 +116,6 @@ static __device__ __forceinline__ void nb_commit_one(int b, const int* n_int, co
   if (prev_stage)
   {  // CTA-wide composition: one thread decides which pieces make up the result, all of them copy
     __shared__ NbComposePlan plan;
-    __shared__ int np_s;
     if (threadIdx.x == 0)
     {
       int np = nb_compose_plan(t_now[b], pv, now, &plan);
@@ -126,7 +125,6 @@ static __device__ __forceinline__ void nb_commit_one(int b, const int* n_int, co
         np = 0;
         plan.kind = 0;
       }
-      np_s = np;
       if (n_pieces) n_pieces[b] = np;
     }
     __syncthreads();
