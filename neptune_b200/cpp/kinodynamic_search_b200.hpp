@@ -32,7 +32,7 @@ public:
     par_ = nb_params();
     par_.num_pol = num_pol, par_.deg_pol = deg_pol, par_.num_agents = (int)pb.size(), par_.num_static = 0;
     par_.samples = num_sample_per_interval, par_.use_linear_constraints = 1, par_.T_span = T_span, par_.weight = 1.0;
-    par_.ent_cap = 3 * (int)pb.size() + 16, par_.bp_max = 8, par_.ent_slots = 16, par_.ipm_max_iter = 60, par_.ipm_tol = 1e-9;
+    par_.ent_cap = 3 * (int)pb.size() + 16, par_.bp_max = 8, par_.ent_slots = 16, par_.ipm_max_iter = 30, par_.ipm_tol = 1e-9;
     sp_ = nb_search_params();
     sp_.num_samples = 5, sp_.j_max = 5.0, sp_.voxel_size = 0.2, sp_.bias = 1.0, sp_.goal_size = 0.5;
     sp_.enable_entangle_check = enable_entangle_check ? 1 : 0, sp_.use_not_reaching_soln = use_not_reaching_soln ? 1 : 0;

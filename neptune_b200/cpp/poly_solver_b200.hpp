@@ -49,7 +49,7 @@ public:
     par_.T_span = T_span, par_.weight = weight_term;
     // storage capacities follow the semantic bounds of the reference's vectors and grow on demand (optimize):
     // an alphas list holds at most 3 (N + M) entries (kinodynamic_search.cpp:938-942)
-    par_.ent_cap = 3 * (int)pb.size() + 16, par_.bp_max = 8, par_.ent_slots = 16, par_.ipm_max_iter = 60, par_.ipm_tol = 1e-9;
+    par_.ent_cap = 3 * (int)pb.size() + 16, par_.bp_max = 8, par_.ent_slots = 16, par_.ipm_max_iter = 30, par_.ipm_tol = 1e-9;
     par_.drone_radius = 0.0, par_.tether_length = 0.0;
     (void)rad_term;  // rad_term_ is stored but unused by the reference in linear mode (:701-706)
   }
@@ -68,7 +68,7 @@ public:
   {
     max_runtime_ = runtime;
     const int cap = (int)(runtime / 20e-6);
-    const int it = cap < 5 ? 5 : (cap > 60 ? 60 : cap);
+    const int it = cap < 5 ? 5 : (cap > 30 ? 30 : cap);
     if (it != par_.ipm_max_iter) par_.ipm_max_iter = it, reset();
   }
   // stored and never read by the reference's linear mode either (solver_gurobi_poly.cpp:290-305, :786-801)

@@ -50,7 +50,7 @@ class Params:
     ent_cap: int = 48                # entries an alphas list can hold (semantic bound stays 3(N+M))
     bp_max: int = 8                  # bend points per agent list, base included
     ent_slots: int = 16              # LP slots per interval reserved for non-entangling constraints
-    ipm_max_iter: int = 60
+    ipm_max_iter: int = 30        # converged solves need <= 15 iterations on every scene; an infeasible first solve that does not blow up stalls the whole batch until the cap
     ipm_tol: float = 1e-9
     pb: np.ndarray | None = None     # [N][2] base positions (par_.pb)
 
