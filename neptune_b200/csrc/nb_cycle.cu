@@ -435,10 +435,12 @@ extern "C" int nb_cycle_create(nb_handle* h, const nb_cycle_desc* d, nb_cycle** 
   nb_cycle* c = new nb_cycle();
   c->h = h, c->d = *d;
   // measured (tools/cycle_rank0_of.py, bench.py grid1024 block): beside the QP the first half saves 35-50 us per cycle while
-  // SMs are idle (64 agents against 64 ... 512: 0.544 -> 0.496 ms in the 512-agent world); with 1024 agents on one GPU
-  // (every SM busy with k_lines / k_qp) it is a wash (3.69 vs 3.75 ms), so there it stays one kernel after the QP
+  // SMs are idle (64 agents against 64 ... 512: 0.544 -> 0.496 ms in the 512-agent world); in the 1224-tether world it is a
+  // wash with 1024 agents per GPU (3.69 vs 3.75 ms) and a loss with 128 (1.56 vs 1.74 ms per cycle on eight GPUs: the first
+  // half alone is as long as the QP there), so from 1024 tethers on it stays one kernel after the QP
+  const int NA_ = h->par.num_agents + h->par.num_static;
   c->split_postcheck = getenv("NB_CYCLE_NO_SPLIT") == nullptr &&
-                       (h->par.num_agents + h->par.num_static < 512 || d->B <= h->num_sms || getenv("NB_CYCLE_FORCE_SPLIT"));
+                       ((NA_ < 1024 && (NA_ < 512 || d->B <= h->num_sms)) || getenv("NB_CYCLE_FORCE_SPLIT"));
   c->agent_id.assign(d->agent_id, d->agent_id + d->B);
   c->d.agent_id = c->agent_id.data();
   const int B = d->B, N = h->par.num_agents, M = h->par.num_static, NA = N + M, cap = h->par.ent_cap, S = h->par.samples;
