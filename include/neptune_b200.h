@@ -501,6 +501,9 @@ int nb_cycle_download(nb_cycle* c, void* stream);                     /* packed 
 /* the same with caller-owned PINNED buffers of in_bytes / out_bytes (several prepared input sets, nb_pinned_alloc) */
 int nb_cycle_upload_from(nb_cycle* c, const void* host_in, int32_t n_groups, void* stream);
 int nb_cycle_download_to(nb_cycle* c, void* host_out, void* stream);
+/* bytes the last upload moved over PCIe: in_bytes for small worlds; for large ones (packed buffer >= 4 MB) only the used
+ * prefix of every entanglement-list row travels and the active-case arrays are rebuilt on the device from the lists */
+long long nb_cycle_last_upload_bytes(const nb_cycle* c);
 void* nb_pinned_alloc(int64_t bytes);   /* page-locked host memory, zeroed; NULL on failure */
 void nb_pinned_free(void* p);
 /* runs ONE real cycle (k advances), then captures the launch sequence for the current grouping in three CUDA graphs (one

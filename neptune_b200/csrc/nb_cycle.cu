@@ -165,6 +165,25 @@ __global__ void k_align(NbPeers peers, long long epoch, int* err)
   }
 }
 
+// active_cases rebuilt from the crossing list: active[id - 1] = number of entries of the list that carry id (every change
+// of active_cases in eu::addAlphaBetaToList is paired with an append / erase of alphas, entangle_utils.cpp:1402-1534).
+// One CTA per state; states: [n_states] lists of stride cap, counts cnt[2 * state] (n_alpha first).
+__global__ void k_active_from_lists(int n_states, int cap, int NA, const int* cnt, const int* alpha, int* active)
+{
+  const int q = blockIdx.x;
+  if (q >= n_states) return;
+  int* act = active + (size_t)q * NA;
+  for (int e = threadIdx.x; e < NA; e += blockDim.x) act[e] = 0;
+  __syncthreads();
+  const int n = cnt[2 * q];
+  const int* al = alpha + (size_t)q * cap * 2;
+  for (int e = threadIdx.x; e < n && e < cap; e += blockDim.x)
+  {
+    const int id = al[2 * e];
+    if (id >= 1 && id <= NA) atomicAdd(act + id - 1, 1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ the object
 struct Field
 {
@@ -190,6 +209,7 @@ struct nb_cycle
   void* peer_base[NB_MAX_WORLD] = { nullptr };
   long long* d_cycle = nullptr;  // device copy of k
   long long align_epoch = 0;
+  long long last_upload_bytes = 0;   // what the last nb_cycle_upload* moved over PCIe
   bool split_postcheck = true;   // first half of the entanglement post-check beside the QP (NB_CYCLE_NO_SPLIT=1: one kernel after it)
   unsigned int* d_done = nullptr;
   long long k = 0;
@@ -617,13 +637,11 @@ extern "C" int nb_cycle_seed_records(nb_cycle* c, const double* known_recs, cons
   return NB_OK;
 }
 
+extern "C" int nb_cycle_upload_from(nb_cycle* c, const void* host_in, int32_t n_groups, void* stream);
 extern "C" int nb_cycle_upload(nb_cycle* c, int32_t n_groups, void* stream)
 {
   if (!c) return NB_ERR_ARG;
-  CY_CUDA(cudaSetDevice(c->h->device));
-  CY_RC(ensure_groups(c, n_groups));
-  CY_CUDA(cudaMemcpyAsync(c->d_in, c->h_in, (size_t)c->lay.in_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-  return NB_OK;
+  return nb_cycle_upload_from(c, c->h_in, n_groups, stream);
 }
 
 extern "C" int nb_cycle_download(nb_cycle* c, void* stream)
@@ -639,9 +657,55 @@ extern "C" int nb_cycle_upload_from(nb_cycle* c, const void* host_in, int32_t n_
   if (!c || !host_in) return NB_ERR_ARG;
   CY_CUDA(cudaSetDevice(c->h->device));
   CY_RC(ensure_groups(c, n_groups));
-  CY_CUDA(cudaMemcpyAsync(c->d_in, host_in, (size_t)c->lay.in_bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  cudaStream_t st = (cudaStream_t)stream;
+  const nb_cycle_layout& L = c->lay;
+  const char* hp = (const char*)host_in;
+  const int B = c->d.B, cap = c->cap, NA = c->NA;
+  if ((L.in_bytes < (4 << 20) && !getenv("NB_CYCLE_SPARSE_UPLOAD")) || getenv("NB_CYCLE_DENSE_UPLOAD"))
+  {  // small worlds: one copy of the packed buffer
+    CY_CUDA(cudaMemcpyAsync(c->d_in, host_in, (size_t)L.in_bytes, cudaMemcpyHostToDevice, st));
+    c->last_upload_bytes = L.in_bytes;
+    return NB_OK;
+  }
+  // Large worlds: the entanglement lists are allocated for 3 (N + M) entries per state and hold a few dozen, and the
+  // active-case arrays ([N + M] per state) are a function of the lists.  Only the used prefix of every list row crosses
+  // PCIe (2-D copies out of the same packed host buffer) and active_cases is rebuilt on the device; everything else goes
+  // as before.  Nothing downstream reads a list beyond its count.
+  const int32_t* esv_cnt = (const int32_t*)(hp + L.esv_cnt);
+  const int32_t* es_cnt = (const int32_t*)(hp + L.es_cnt);
+  int ma = 0, me = 0, mb = 0;
+  for (int q = 0; q < B * 9; q++) ma = esv_cnt[2 * q] > ma ? esv_cnt[2 * q] : ma;
+  for (int b = 0; b < B; b++) me = es_cnt[2 * b] > me ? es_cnt[2 * b] : me, mb = es_cnt[2 * b + 1] > mb ? es_cnt[2 * b + 1] : mb;
+  ma = ma > cap ? cap : ma, me = me > cap ? cap : me, mb = mb > cap ? cap : mb;
+  long long moved = 0;
+  auto flat = [&](int64_t from, int64_t to) -> int {
+    if (to > from) CY_CUDA(cudaMemcpyAsync(c->d_in + from, hp + from, (size_t)(to - from), cudaMemcpyHostToDevice, st));
+    moved += to - from;
+    return NB_OK;
+  };
+  auto rows = [&](int64_t off, size_t pitch, size_t width, size_t n) -> int {
+    if (width > 0 && n > 0)
+      CY_CUDA(cudaMemcpy2DAsync(c->d_in + off, pitch, hp + off, pitch, width, n, cudaMemcpyHostToDevice, st));
+    moved += (long long)(width * n);
+    return NB_OK;
+  };
+  CY_RC(flat(0, L.esv_alpha));                                              // n_int ... esv_cnt
+  CY_RC(rows(L.esv_alpha, (size_t)cap * 8, (size_t)ma * 8, (size_t)B * 9));
+  CY_RC(flat(L.es_cnt, L.es_alpha));                                        // es_cnt
+  CY_RC(rows(L.es_alpha, (size_t)cap * 8, (size_t)me * 8, (size_t)B));
+  CY_RC(rows(L.es_beta, (size_t)cap * 8, (size_t)me * 8, (size_t)B));
+  CY_RC(rows(L.es_bend, (size_t)cap * 4, (size_t)mb * 4, (size_t)B));
+  CY_RC(flat(L.prev_pos, L.in_bytes));                                      // prev_pos ... front-end inputs
+  k_active_from_lists<<<B * 9, 128, 0, st>>>(B * 9, cap, NA, (const int*)(c->d_in + L.esv_cnt), (const int*)(c->d_in + L.esv_alpha),
+                                           (int*)(c->d_in + L.esv_active));
+  k_active_from_lists<<<B, 128, 0, st>>>(B, cap, NA, (const int*)(c->d_in + L.es_cnt), (const int*)(c->d_in + L.es_alpha),
+                                       (int*)(c->d_in + L.es_active));
+  CY_CUDA(cudaGetLastError());
+  c->last_upload_bytes = moved;
   return NB_OK;
 }
+
+extern "C" long long nb_cycle_last_upload_bytes(const nb_cycle* c) { return c ? c->last_upload_bytes : 0; }
 
 extern "C" int nb_cycle_download_to(nb_cycle* c, void* host_out, void* stream)
 {
@@ -752,6 +816,8 @@ extern "C" int nb_cycle_fetch(nb_cycle* c, const char* name, void* dst, int64_t 
   if (n == "ring_new") src = ring_slot(c, ph_new(kk)), have = rec;
   else if (n == "ring_late") src = ring_slot(c, ph_late(kk)), have = rec;
   else if (n == "ring_known") src = ring_slot(c, ph_known(kk)), have = rec;
+  else if (n == "in_esv_active") src = c->d_in + c->lay.esv_active, have = (size_t)c->d.B * 9 * c->NA * 4;
+  else if (n == "in_es_active") src = c->d_in + c->lay.es_active, have = (size_t)c->d.B * c->NA * 4;
   else if (n == "esA_cnt") src = c->esA + c->es_off[0], have = (size_t)c->d.B * 8;
   else if (n == "esA_alpha") src = c->esA + c->es_off[1], have = (size_t)c->d.B * c->cap * 8;
   else if (n == "esA_beta") src = c->esA + c->es_off[2], have = (size_t)c->d.B * c->cap * 8;

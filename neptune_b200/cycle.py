@@ -188,6 +188,8 @@ class ReplanCycle:
         L.nb_cycle_download_to.argtypes = [_P, _P, _P]
         L.nb_cycle_step.argtypes = [_P, _P]
         L.nb_cycle_align.argtypes = [_P, _P]
+        L.nb_cycle_last_upload_bytes.argtypes = [_P]
+        L.nb_cycle_last_upload_bytes.restype = C.c_longlong
         L.nb_cycle_capture.argtypes = [_P, _P]
         L.nb_cycle_step_profiled.argtypes = [_P, _P, _P]
         L.nb_cycle_launches_per_step.argtypes = [_P]
@@ -243,7 +245,7 @@ class ReplanCycle:
     def upload(self, host: PinnedBuffer) -> int:
         """One H2D copy of the packed per-cycle inputs."""
         capi._check(self._lib.nb_cycle_upload_from(self._h, _P(host.ptr), int(host.G), self._st()), "nb_cycle_upload_from")
-        return self.in_bytes
+        return int(self._lib.nb_cycle_last_upload_bytes(self._h))
 
     def download(self, host_out: PinnedBuffer) -> int:
         """One D2H copy of the packed results."""

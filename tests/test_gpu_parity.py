@@ -408,3 +408,36 @@ def test_entangle_random_walks_bend_points(capi, oracle):
     mx_a, mx_b = compare_backends(par, sc, OracleEntBackend(oracle), capi.DeviceEntBackend(s), trials=20)
     assert mx_a >= 8 and mx_b >= 2
     s.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,seed", [("obst8", 3004), ("mtlp5", 2005)])
+def test_cycle_sparse_upload_equals_dense(capi, oracle, cfg, seed, monkeypatch):
+    """Large worlds upload only the used prefix of every entanglement-list row and rebuild active_cases on the device
+    (nb_cycle_upload_from).  Forced on a small world here: the rebuilt arrays equal the host's, every output of the cycle
+    equals the dense upload's, and fewer bytes cross PCIe."""
+    from neptune_b200.cycle import ReplanCycle
+    from tests.ent_backends import OracleEntBackend
+    par = config(cfg)
+    sc = make_scene(par, seed, sync=False, ent_backend=OracleEntBackend(oracle))
+    b = sc.batch
+    outs = {}
+    for mode in ("dense", "sparse"):
+        monkeypatch.delenv("NB_CYCLE_DENSE_UPLOAD", raising=False)
+        monkeypatch.delenv("NB_CYCLE_SPARSE_UPLOAD", raising=False)
+        monkeypatch.setenv("NB_CYCLE_DENSE_UPLOAD" if mode == "dense" else "NB_CYCLE_SPARSE_UPLOAD", "1")
+        cyc = ReplanCycle(par, b.agent_id - 1, "cuda:0", static=(b.st_ptr, b.st_xy, sc.strep), planned=np.ones(par.num_of_agents, np.uint8))
+        cyc.seed_records(cyc.records_of(sc, seq=0))
+        hin, hout = cyc.host_inputs(sc), cyc.host_outputs()
+        moved, _ = cyc.step_from_host(hin, hout)
+        cyc.check_errors()
+        B, NA = cyc.B, par.NA
+        outs[mode] = dict(moved=moved, esv_active=cyc.fetch("in_esv_active", (B, 9, NA), np.int32), es_active=cyc.fetch("in_es_active", (B, NA), np.int32),
+                          rec=cyc.records("new").copy(), **{k: hout[k].copy() for k in ("coeff_out", "status", "entangled", "collide", "n_pieces")})
+        cyc.close()
+    d, sp = outs["dense"], outs["sparse"]
+    assert np.array_equal(d["esv_active"], b.esv_active.reshape(d["esv_active"].shape))      # the dense upload carries the host's arrays
+    assert np.array_equal(sp["esv_active"], d["esv_active"]) and np.array_equal(sp["es_active"], d["es_active"])
+    for k in ("coeff_out", "status", "entangled", "collide", "n_pieces", "rec"):
+        assert np.array_equal(sp[k], d[k]), k
+    assert sp["moved"] < d["moved"]
