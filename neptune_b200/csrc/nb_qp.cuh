@@ -344,14 +344,23 @@ void nb_qp_ct_all(const Group<NL>& g, const NbQpTable* tb, const NbQpShared* sh_
       const double* vf = vecF + ax * NB_NFEAT_AX + sub;
       const double* cc = &tb->C[sub][c];
       const int cnt = (8 * n - sub + SUB - 1) / SUB;   // features sub, sub + SUB, ...
-      int k = 0;
-#pragma unroll 2
-      for (; k + 1 < cnt; k += 2)
+      // fully unrolled with predicates: every load is issued before the first product (a shared-memory load costs ~50
+      // cycles when it sits in the dependent chain, and a rolled loop with a run-time bound leaves it there)
+      constexpr int MAXC = NB_NFEAT_AX / SUB;
+      double cv[MAXC], fv[MAXC];
+#pragma unroll
+      for (int k = 0; k < MAXC; k++)
       {
-        v0 += cc[(size_t)k * SUB * NB_DOF_MAX] * vf[k * SUB];
-        v1 += cc[(size_t)(k + 1) * SUB * NB_DOF_MAX] * vf[(k + 1) * SUB];
+        const bool in = k < cnt;
+        cv[k] = in ? cc[(size_t)k * SUB * NB_DOF_MAX] : 0.0;
+        fv[k] = in ? vf[k * SUB] : 0.0;
       }
-      if (k < cnt) v0 += cc[(size_t)k * SUB * NB_DOF_MAX] * vf[k * SUB];
+#pragma unroll
+      for (int k = 0; k < MAXC; k += 2)
+      {
+        v0 += cv[k] * fv[k];
+        if (k + 1 < MAXC) v1 += cv[k + 1] * fv[k + 1];
+      }
     }
     const double v = g.sub_sum(v0 + v1);
     if (on && sub == 0) dst[a] = tail + sign * v;
