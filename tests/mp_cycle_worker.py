@@ -42,6 +42,7 @@ def main():
     cyc.upload(hin)
     rings, coeffs = [], []
     for k in range(cycles):
+        cyc.align()      # device-side rank barrier (a no-op on one rank): every cycle starts together, results unchanged
         if graph and k == 1:
             cyc.capture()
         else:
