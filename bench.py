@@ -229,7 +229,10 @@ def measure_cycle(args, par, agents, rank, world, dev, workload, steps, warmup, 
     # ---------------- value: inputs resident in HBM before the timed region, CUDA events on the cycle's stream
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     sampler = ClockSampler(dev.index or 0) if clocks else None
-    for it in range(3):   # the sampler comes up under the same load
+    # the sampler comes up under the same load, and the GPU settles: a lease starts idle at low clocks and the first
+    # hundred graph replays run ~20 % slower than the steady state (measured with --steps 20 / 50 / 400), so every run --
+    # whatever W -- gets at least 150 untimed cycles before the timed ones
+    for it in range(max(3, 150 - warmup)):
         cyc.upload(hins[it % len(hins)])
         flush_l2()
         cyc.step()

@@ -812,6 +812,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
     NB_QP_TICK(0);
     int it = 0;
     double al_pending = 0.0;  // step of the previous iteration, applied to (s, lam, y) by the next RESID sweep
+    double mu_div = 1e300;    // divergence threshold, set from the first real iterate
     for (it = 0; it <= cs.max_iter; it++)
     {
       const bool init_pass = (it == 0);
@@ -879,6 +880,11 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
         }
         if (it == cs.max_iter) break;
         if (!(mu == mu) || !(rpn == rpn) || !(rdn == rdn)) break;
+        // diverged: on an infeasible model the multipliers run away (mu grows by ~1e5 per iteration while the steps
+        // collapse to 1e-50) long before anything overflows to NaN; a converging solve never leaves mu twelve orders of
+        // magnitude ABOVE where it started.  Same outcome as the NaN test and the iteration cap ("no solution"), sooner.
+        if (it == 1) mu_div = 1e12 * (1.0 + mu);
+        if (mu > mu_div) break;
       }
       NB_QP_TICK(2);
       // ---- K0 = Hobj + C^T W C (+ Hessian of the quadratic row), factorised block by block
@@ -971,6 +977,16 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
       double al = rmax > 0.0 ? eta * nb_rcp(rmax) : 1.0;
       if (al > 1.0) al = 1.0;
       al_pending = al;
+#if defined(__CUDA_ARCH__)
+      if (prof && g.lane == 0 && it >= 16)
+      {  // diagnostic (profiling mode): the late iterations of a solve that is not converging -- slots 13..15 hold the
+         // smallest step, the last primal residual and the last mu as raw bits
+        double* pd = reinterpret_cast<double*>(prof + 13);
+        pd[0] = (it == 16 || al < pd[0]) ? al : pd[0];
+        pd[1] = rpn;
+        pd[2] = mu;
+      }
+#endif
       if (has_qc)
       {
         s_q += al * ds_q;
@@ -983,7 +999,7 @@ NB_HD bool nb_qp_solve(const Group<NL>& g, const NbConsts& cs, const NbQpTable* 
   }
 #if defined(__CUDA_ARCH__)
   if (prof && g.lane == 0)
-    for (int k = 0; k < 16; k++) prof[k] += pt[k];
+    for (int k = 0; k < 13; k++) prof[k] += pt[k];
 #endif
 #undef NB_QP_TICK
 #undef NB_QC_EVAL

@@ -1717,6 +1717,7 @@ static int ipm_solve(const qmodel* md, double* x, int max_iter, double tol, int*
   double* Z = (double*)malloc(sizeof(double) * nv * nv);
   double* xp = (double*)malloc(sizeof(double) * nv);
   int nz = 0, it = 0, converged = 0;
+  double mu_div = 1e300;
   if (iters_out) *iters_out = 0;
   if (eq_nullspace(md->Aeq, md->beq, me, nv, Z, xp, &nz))
   {
@@ -1874,6 +1875,10 @@ static int ipm_solve(const qmodel* md, double* x, int max_iter, double tol, int*
       }
       if (it == max_iter) break;
       if (!(mu == mu) || !(rpn == rpn) || !(rdn == rdn)) break; /* NaN */
+      /* diverged (infeasible model: the multipliers run away long before anything overflows): same outcome as the NaN
+         test and the iteration cap, sooner; a converging solve never leaves mu 1e12 above where it started */
+      if (it == 1) mu_div = 1e12 * (1.0 + mu);
+      if (mu > mu_div) break;
     }
     /* K = Hr + lam_q Hess(c) + Gr^T D Gr */
     memcpy(K, Hr, sizeof(double) * nz * nz);

@@ -49,11 +49,21 @@ torch.cuda.synchronize()
 cyc.check_errors()
 ms = np.array([a.elapsed_time(b) for a, b in ev])
 print(f"world of {K} x 64 agents, rank {rank} alone: {ms.mean():.4f} ms per cycle (p50 {np.median(ms):.4f}, p95 {np.percentile(ms, 95):.4f})")
+import ctypes as C
+lib = capi.lib()
+lib.nb_set_profiling(cyc.solver.handle, 1)
+lib.nb_qp_phase_cycles.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 for q in range(len(hins)):   # per scene: stages (plain launches, one stream) and the interior-point iteration counts
     cyc.upload(hins[q])
     sm = cyc.step_profiled()
     cyc.download(hout)
     st.synchronize()
     it = hout["iters"]
+    if it[:, 0].max() >= 20:   # a first solve that ran into the cap: what its late iterations looked like
+        prof = np.zeros((cyc.B, 16), np.int64)
+        lib.nb_qp_phase_cycles(cyc.solver.handle, prof.ctypes.data_as(C.c_void_p), cyc.B)
+        w = int(np.argmax(it[:, 0]))
+        print(f"  agent {w}: iterations {it[w].tolist()}, n_int {int(hins[q]['n_int'][w])}, smallest step / last |rp| / last mu from iteration 16 on:",
+              prof[w, 13:16].view(np.float64).tolist())
     print(f"scene {q}:", {k: round(v, 4) for k, v in sm.items()}, "ipm iterations max", it.max(axis=0).tolist(), "status", np.bincount(hout["status"], minlength=3).tolist())
 cyc.close()
