@@ -20,7 +20,7 @@
 #define NB_DOF_MAX 8
 #define NB_NV_MAX 24     // 3 axes x dof_max
 #define NB_NFEAT_AX 64   // features per axis: 8 intervals x (4 pos CP + 3 vel CP + 1 acc)
-#define NB_SEP_EPS 1e-9
+#define NB_SEP_EPS 1e-6   // slack of the row check of a candidate line (rows are normalised to +-1 at the closest pair); see nb_sep.cuh
 
 // explicitly rounded FP64 operations: no FMA contraction where a sign or a comparison decides an integer result
 #if defined(__CUDA_ARCH__)

@@ -7,7 +7,12 @@
 // feasible point: the minimum-norm (maximum-margin) solution.  With pa in conv(A), pb in conv(B) the
 // closest pair and delta = |pa - pb| > 0, it is n = 2 (pa - pb) / delta^2, d = -n.(pa + pb)/2
 // (value +1 at pa, -1 at pb).  The LP is feasible iff that line separates, which is verified row by
-// row with the same 1e-9 slack the oracle uses.
+// row with the slack NB_SEP_EPS the oracle uses too.  The slack is 1e-6 of the (unit) margin, not 1e-9: for sets that
+// nearly touch (delta ~ 1e-3) along nearly parallel edges, n = 2 (pa - pb) / delta^2 is a small difference of large
+// coordinates scaled up by 1 / delta^2, and the rounding of its DIRECTION alone moves the row value of a vertex a few
+// metres along the edge by ~1e-8: with 1e-9 the solved flag of such a pair flipped with a 1e-15 perturbation of the
+// control points (the row would then be dropped, where GLPK -- feasibility tolerance 1e-7 -- reports the LP feasible),
+// and the oracle's enumeration fell back to a candidate of smaller margin.  Intersecting sets fail the check by O(1).
 #pragma once
 #include "nb_common.cuh"
 

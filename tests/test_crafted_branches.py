@@ -142,3 +142,53 @@ def test_both_solves_infeasible_is_status_2(oracle, kind):
             mdl = oracle.export_qp(b, a, fb, ref.lines[a], ref.line_ok[a])
             st, _, _ = qp_highs(mdl["P"], mdl["q"], mdl["Aeq"], mdl["beq"], mdl["G"], mdl["h"])
             assert st == "Infeasible", (a, fb, st)
+
+
+# ---------------------------------------------------------------------------------------------- crowded, inconsistent worlds
+def _crowded_worlds(oracle, n_scenes=6):
+    """Paths and entanglement states of one 64-agent grid world against the hulls of ANOTHER one (same bases, other
+    goals): what a closed loop drifts into when the committed trajectories move on and the front-end paths do not.  Hulls
+    nearly touch control polygons along parallel edges, first solves are infeasible in ways that are not structural
+    (they run and diverge), and crowded intervals carry dozens of redundant lines."""
+    import dataclasses
+
+    import bench
+    from tests.ent_backends import OracleEntBackend
+    par = bench.world_params(1)
+    agents = bench.rank_agents(par, 1, 0, "grid64")
+    _, scenes = bench.make_world(1, 0, n_scenes, OracleEntBackend(oracle), "grid64", agents=agents)
+    for a in range(n_scenes):
+        for b in range(n_scenes):
+            if a != b:
+                A, B = scenes[a].batch, scenes[b].batch
+                yield (a, b), dataclasses.replace(A, hull_ptr=B.hull_ptr, hull_xy=B.hull_xy, nih0=B.nih0)
+
+
+def test_crowded_worlds_emulation_equals_oracle(oracle):
+    """30 mixed worlds x 64 agents: solved flags of all ~500 LPs per agent identical, status path identical, coefficients
+    within tolerance -- including the first solves that RUN and fail (divergence test) and the feasible ones on which the
+    oracle's unpruned full-space model needs up to 128 iterations against 12-18 for the product's pruned one.  One of the
+    latter is also checked against HiGHS: the model is feasible and the optimum is the product's."""
+    from tests.emul import emul
+    from tests.highs_util import qp_highs
+    n_hard = n_slow = 0
+    checked_highs = False
+    for (a, b), mix in _crowded_worlds(oracle):
+        ref = ReplanResult.empty(mix)
+        assert oracle.replan_batch(mix, ref, 8) == 0
+        got = emul.replan(mix, with_lines=True)
+        assert np.array_equal(got.line_ok, ref.line_ok), (a, b)
+        assert np.array_equal(got.status, ref.status), (a, b, np.flatnonzero(got.status != ref.status))
+        assert np.abs(got.coeff_out - ref.coeff_out).max() <= 1e-6 * max(1.0, np.abs(ref.coeff_out).max()), (a, b)
+        n_hard += int(((ref.status >= 1) & (ref.iters[:, 0] > 0)).sum())
+        slow = np.flatnonzero((ref.status == 0) & (ref.iters[:, 0] > 30))
+        n_slow += len(slow)
+        if len(slow) and not checked_highs:
+            w = int(slow[0])
+            m = oracle.export_qp(mix, w, False, ref.lines[w], ref.line_ok[w])
+            st, _, f = qp_highs(m["P"], m["q"], m["Aeq"], m["beq"], m["G"], m["h"])
+            assert st == "Optimal"
+            assert abs(f + m["c0"] - got.obj[w]) <= 1e-6 * max(1.0, abs(got.obj[w]))
+            assert got.iters[w, 0] <= 30
+            checked_highs = True
+    assert n_hard >= 3 and n_slow >= 1 and checked_highs
