@@ -17,6 +17,15 @@ struct DevBuf
     cap = 0;
     size_t want = bytes + bytes / 4 + 256;
     if (cudaMalloc(&p, want) != cudaSuccess) return -1;
+    // Library-owned scratch and staging buffers start zeroed: a host-space call copies whole output arrays back, and the
+    // parts a kernel has no reason to write (list tails beyond their counts, slots of agents without a result) must not
+    // carry whatever an earlier allocation of the process left in that memory.
+    if (cudaMemset(p, 0, want) != cudaSuccess)
+    {
+      cudaFree(p);
+      p = nullptr;
+      return -1;
+    }
     cap = want;
     return 0;
   }
